@@ -1,0 +1,97 @@
+"""Parity of the tcgen05 GEMM (through the C ABI) against fp32 torch.matmul on the same bf16-rounded operands."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, a_mn, b_mn):
+    A = a.float().transpose(-1, -2) if a_mn else a.float()
+    B = b.float() if b_mn else b.float().transpose(-1, -2)
+    return A @ B
+
+
+def _rand(shape, dev, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(shape, generator=g).to(dev).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 256), (394, 768, 768), (1000, 2304, 768),
+                                   (197, 3072, 768), (640, 30522 // 8 * 8, 128), (8, 16, 24), (300, 520, 200)])
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256])
+def test_gemm_plain(cuda_dev, a_mn, b_mn, M, N, K, bn):
+    from vilmedic_b200 import ops
+    if bn != 0 and (M, N, K) not in [(256, 256, 256), (394, 768, 768), (300, 520, 200)]:
+        pytest.skip("forced tile sizes only on a subset")
+    a = _rand((K, M) if a_mn else (M, K), cuda_dev, 1)
+    b = _rand((K, N) if b_mn else (N, K), cuda_dev, 2)
+    ref = _ref(a, b, a_mn, b_mn)
+    out = ops.gemm(a, b, a_mn_major=a_mn, b_mn_major=b_mn, out_dtype=torch.float32, force_bn=bn)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-3 * scale + 1e-3, "max err %g (scale %g)" % (err, scale)
+    out16 = ops.gemm(a, b, a_mn_major=a_mn, b_mn_major=b_mn, force_bn=bn)
+    torch.cuda.synchronize()
+    assert (out16.float() - ref).abs().max().item() <= 1e-2 * scale + 1e-2
+
+
+def test_gemm_epilogue(cuda_dev):
+    from vilmedic_b200 import ops
+    M, N, K = 394, 3072, 768
+    a = _rand((M, K), cuda_dev, 3)
+    w = _rand((N, K), cuda_dev, 4) * 0.05
+    bias = torch.randn(N, device=cuda_dev)
+    res = _rand((M, N), cuda_dev, 5)
+    pre_ref = a.float() @ w.float().t() + bias
+    # bias + GELU with stashed pre-activation
+    pre = torch.empty(M, N, device=cuda_dev, dtype=torch.bfloat16)
+    h = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, aux_out=pre)
+    torch.cuda.synchronize()
+    assert (pre.float() - pre_ref).abs().max().item() < 3e-2
+    assert (h.float() - torch.nn.functional.gelu(pre_ref)).abs().max().item() < 3e-2
+    # bias + residual, bf16 and fp32 outputs
+    y = ops.gemm(a, w, bias=bias, residual=res)
+    assert (y.float() - (pre_ref + res.float())).abs().max().item() < 5e-2
+    y32 = ops.gemm(a, w, bias=bias, residual=res.float(), out_dtype=torch.float32)
+    assert (y32 - (pre_ref + res.float())).abs().max().item() < 2e-3
+    # accumulate
+    acc = torch.ones(M, N, device=cuda_dev)
+    ops.gemm(a, w, out=acc, accumulate=True, alpha=0.5)
+    assert (acc - (1 + 0.5 * (pre_ref - bias))).abs().max().item() < 2e-3
+    # GELU' epilogue (backward of the FFN activation)
+    g = _rand((M, K), cuda_dev, 6)
+    dpre = ops.gemm(g, w, act=ops.ACT_GELU_GRAD, aux_in=pre, out_dtype=torch.float32)
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).backward(g.float() @ w.float().t())
+    assert (dpre - x.grad).abs().max().item() < 2e-2
+    torch.cuda.synchronize()
+
+
+def test_gemm_batched(cuda_dev):
+    from vilmedic_b200 import ops
+    Bt, M, N, K = 5, 197, 768, 768
+    a = _rand((Bt, M, K), cuda_dev, 7)
+    w = _rand((1, N, K), cuda_dev, 8).expand(Bt, N, K)
+    # shared weight through a zero batch stride is expressed by passing stride 0
+    w0 = w[0].contiguous()
+    outs = torch.empty(Bt, M, N, device=cuda_dev, dtype=torch.float32)
+    wb = w0.unsqueeze(0).expand(Bt, N, K)
+    ops.gemm(a, wb, out=outs)
+    torch.cuda.synchronize()
+    ref = a.float() @ w0.float().t()
+    assert (outs - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+    # true batched (attention-like): per-batch B, MN-major B
+    k = _rand((Bt, 200, 64), cuda_dev, 9)
+    q = _rand((Bt, 128, 64), cuda_dev, 10)
+    s = ops.gemm(q, k, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    ref = q.float() @ k.float().transpose(1, 2)
+    assert (s - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+    v = _rand((Bt, 200, 64), cuda_dev, 11)
+    p = _rand((Bt, 128, 200), cuda_dev, 12)
+    o = ops.gemm(p, v, b_mn_major=True, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    ref = p.float() @ v.float()
+    assert (o - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3

@@ -1,0 +1,539 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (fp32 accumulators
+// in TMEM, double buffered) -> tcgen05.ld epilogue with fused bias / GELU / GELU' / residual / accumulate.
+//
+//   C[M,N] = epilogue(alpha * sum_k A'[m,k] * B'[n,k])
+//
+// A' is given either K-major  (memory A[M][lda],  k contiguous)  or MN-major (memory A[K][lda], m contiguous);
+// B' likewise: K-major = memory B[N][ldb] (the nn.Linear weight layout), MN-major = memory B[K][ldb].
+// That covers all three products of a Linear layer without any transposed copies:
+//   forward  Y  = X W^T          A=X  K-major,  B=W  K-major
+//   dgrad    dX = dY W           A=dY K-major,  B=W  MN-major   (k' = out features)
+//   wgrad    dW = dY^T X         A=dY MN-major, B=X  MN-major   (k' = tokens)
+// Replaces the cuBLAS calls behind nn.Linear in HF ViT / BertGeneration (transformers modeling_vit.py:228-230,
+// 265-268, 296-312; modeling_bert_generation.py:52-56, 89-153, 265-293) used by
+// vilmedic/blocks/vision/visual_encoder.py:56-58 and vilmedic/blocks/huggingface/decoder/decoder_model.py:23-26.
+//
+// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM allocator + MMA issuer, warps2..5 = epilogue.
+#include "common.cuh"
+#include "vlm_b200.h"
+#include <cuda.h>
+
+namespace vlm {
+
+static constexpr int GEMM_BM = 128;
+static constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle row
+static constexpr int GEMM_THREADS = 192;
+
+struct GemmEpilogue {
+  void* c;
+  long long ldc;
+  int c_fp32;
+  const float* bias;          // [N] or null
+  const void* residual;       // same dtype as c, ld = ldr
+  long long ldr;
+  int act;                    // 0 none, 1 GELU (optionally stash pre-activation), 2 multiply by GELU'(aux_in)
+  const bf16* aux_in;         // [M, ld_aux]
+  bf16* aux_out;              // [M, ld_aux]
+  long long ld_aux;
+  float alpha;
+  int accumulate;             // c += result
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int col0, int M, int N,
+                                               const GemmEpilogue& e) {
+  if (row >= M || col0 >= N) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
+
+  const bool full = (col0 + 32 <= N);
+  if (full) {
+    if (e.bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);
+        v[4 * j + 0] += b.x;
+        v[4 * j + 1] += b.y;
+        v[4 * j + 2] += b.z;
+        v[4 * j + 3] += b.w;
+      }
+    }
+    if (e.act == 1) {
+      if (e.aux_out) {
+        uint4* dst = reinterpret_cast<uint4*>(e.aux_out + (long long)row * e.ld_aux + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+          u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+          u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+          u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+          dst[j] = u;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    } else if (e.act == 2) {
+      const uint4* src = reinterpret_cast<const uint4*>(e.aux_in + (long long)row * e.ld_aux + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = __ldg(src + j);
+        const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
+        v[8 * j + 0] *= gelu_erf_grad(p0.x);
+        v[8 * j + 1] *= gelu_erf_grad(p0.y);
+        v[8 * j + 2] *= gelu_erf_grad(p1.x);
+        v[8 * j + 3] *= gelu_erf_grad(p1.y);
+        v[8 * j + 4] *= gelu_erf_grad(p2.x);
+        v[8 * j + 5] *= gelu_erf_grad(p2.y);
+        v[8 * j + 6] *= gelu_erf_grad(p3.x);
+        v[8 * j + 7] *= gelu_erf_grad(p3.y);
+      }
+    }
+    if (e.c_fp32) {
+      float* crow = reinterpret_cast<float*>(e.c) + (long long)row * e.ldc + col0;
+      if (e.residual) {
+        const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.residual) +
+                                                           (long long)row * e.ldr + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 r = __ldg(r4 + j);
+          v[4 * j + 0] += r.x;
+          v[4 * j + 1] += r.y;
+          v[4 * j + 2] += r.z;
+          v[4 * j + 3] += r.w;
+        }
+      }
+      float4* c4 = reinterpret_cast<float4*>(crow);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (e.accumulate) {
+          const float4 old = c4[j];
+          o.x += old.x;
+          o.y += old.y;
+          o.z += old.z;
+          o.w += old.w;
+        }
+        c4[j] = o;
+      }
+    } else {
+      bf16* crow = reinterpret_cast<bf16*>(e.c) + (long long)row * e.ldc + col0;
+      if (e.residual) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.residual) +
+                                                         (long long)row * e.ldr + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 u = __ldg(r4 + j);
+          const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z),
+                       p3 = unpack_bf16x2(u.w);
+          v[8 * j + 0] += p0.x;
+          v[8 * j + 1] += p0.y;
+          v[8 * j + 2] += p1.x;
+          v[8 * j + 3] += p1.y;
+          v[8 * j + 4] += p2.x;
+          v[8 * j + 5] += p2.y;
+          v[8 * j + 6] += p3.x;
+          v[8 * j + 7] += p3.y;
+        }
+      }
+      uint4* c4 = reinterpret_cast<uint4*>(crow);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (e.accumulate) {
+          const uint4 u = c4[j];
+          const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z),
+                       p3 = unpack_bf16x2(u.w);
+          v[8 * j + 0] += p0.x;
+          v[8 * j + 1] += p0.y;
+          v[8 * j + 2] += p1.x;
+          v[8 * j + 3] += p1.y;
+          v[8 * j + 4] += p2.x;
+          v[8 * j + 5] += p2.y;
+          v[8 * j + 6] += p3.x;
+          v[8 * j + 7] += p3.y;
+        }
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        c4[j] = u;
+      }
+    }
+  } else {
+    // ragged last column tile: scalar, fully predicated
+#pragma unroll 1
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      if (col >= N) break;
+      float x = v[j];
+      if (e.bias) x += e.bias[col];
+      if (e.act == 1) {
+        if (e.aux_out) e.aux_out[(long long)row * e.ld_aux + col] = __float2bfloat16(x);
+        x = gelu_erf(x);
+      } else if (e.act == 2) {
+        x *= gelu_erf_grad(__bfloat162float(e.aux_in[(long long)row * e.ld_aux + col]));
+      }
+      if (e.c_fp32) {
+        float* c = reinterpret_cast<float*>(e.c) + (long long)row * e.ldc + col;
+        if (e.residual) x += reinterpret_cast<const float*>(e.residual)[(long long)row * e.ldr + col];
+        if (e.accumulate) x += *c;
+        *c = x;
+      } else {
+        bf16* c = reinterpret_cast<bf16*>(e.c) + (long long)row * e.ldc + col;
+        if (e.residual) x += __bfloat162float(reinterpret_cast<const bf16*>(e.residual)[(long long)row * e.ldr + col]);
+        if (e.accumulate) x += __bfloat162float(*c);
+        *c = __float2bfloat16(x);
+      }
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         int M, int N, int K, int batch, int a_bmul, int b_bmul, long long c_batch_stride,
+                         long long aux_batch_stride, long long res_batch_stride, GemmEpilogue epi) {
+  using S = GemmSmem<BN>;
+  constexpr int STAGES = S::STAGES;
+  constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;  // two accumulator buffers of BN fp32 columns
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const int tiles_per_batch = m_tiles * n_tiles;
+  const int total_tiles = tiles_per_batch * batch;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  } else if (warp_idx == 1) {
+    tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_batch;
+        const int t = tile - b * tiles_per_batch;
+        const int m0 = (t / n_tiles) * GEMM_BM;
+        const int n0 = (t % n_tiles) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          const int k0 = kb * GEMM_BK;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < GEMM_BM / 64; ++j)
+              tma_load_3d(&tmap_a, &full_bar[stage], sa + j * (GEMM_BK * 128), m0 + j * 64, k0, b * a_bmul);
+          } else {
+            tma_load_3d(&tmap_a, &full_bar[stage], sa, k0, m0, b * a_bmul);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_3d(&tmap_b, &full_bar[stage], sb + j * (GEMM_BK * 128), n0 + j * 64, k0, b * b_bmul);
+          } else {
+            tma_load_3d(&tmap_b, &full_bar[stage], sb, k0, n0, b * b_bmul);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
+      // K-major: 8-row groups are 1024 B apart; advancing 16 k = +32 B inside the swizzled row.
+      // MN-major: 64-wide MN blocks are BK*128 B apart (LBO), 8-k groups 1024 B apart (SBO); 16 k = +2048 B.
+      constexpr uint32_t A_LBO = A_MN ? GEMM_BK * 128 : 0, B_LBO = B_MN ? GEMM_BK * 128 : 0;
+      constexpr uint32_t A_KSTEP = A_MN ? 2048 : 32, B_KSTEP = B_MN ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * A_KSTEP, A_LBO, 1024);
+            const uint64_t db = make_smem_desc(sb + k * B_KSTEP, B_LBO, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quad = warp_idx & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_batch;
+      const int t = tile - b * tiles_per_batch;
+      const int m0 = (t / n_tiles) * GEMM_BM;
+      const int n0 = (t % n_tiles) * BN;
+      GemmEpilogue e = epi;
+      if (b > 0) {
+        const size_t esz = e.c_fp32 ? 4 : 2;
+        e.c = reinterpret_cast<uint8_t*>(e.c) + (size_t)b * c_batch_stride * esz;
+        if (e.residual) e.residual = reinterpret_cast<const uint8_t*>(e.residual) + (size_t)b * res_batch_stride * esz;
+        if (e.aux_in) e.aux_in += (size_t)b * aux_batch_stride;
+        if (e.aux_out) e.aux_out += (size_t)b * aux_batch_stride;
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        epilogue_chunk(r, row, n0 + c * 32, M, N, e);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (err != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+      set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(err));
+      return nullptr;
+    }
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 3-D bf16 tensor map: dims {inner, rows, batch}; box {64, box_rows, 1}; 128B swizzle; OOB -> zero.
+int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch,
+                   uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -1;
+  cuuint64_t dims[3] = {inner, rows, batch};
+  cuuint64_t strides[2] = {row_stride_elems * 2, (batch > 1 ? batch_stride_elems : row_stride_elems * rows) * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu rows=%llu batch=%llu ld=%llu bstride=%llu box=%u",
+              (int)r, ptr, (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)batch,
+              (unsigned long long)row_stride_elems, (unsigned long long)batch_stride_elems, box_rows);
+    return -1;
+  }
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int batch, int a_bmul,
+                       int b_bmul, long long c_bs, long long aux_bs, long long res_bs, const GemmEpilogue& epi, int max_ctas,
+                       cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (err != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm smem=%d): %s", S::TOTAL, cudaGetErrorString(err));
+      return -1;
+    }
+    attr_set = true;
+  }
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN - 1) / BN;
+  const long long tiles = (long long)m_tiles * n_tiles * batch;
+  int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, M, N, K, batch, a_bmul, b_bmul, c_bs, aux_bs, res_bs, epi);
+  return check_launch("gemm_bf16_tcgen05");
+}
+
+static int pick_bn(int M, int N, int batch, int force_bn) {
+  if (force_bn == 64 || force_bn == 128 || force_bn == 192 || force_bn == 256) return force_bn;
+  const int sms = num_sms();
+  const long long m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  int best = 128;
+  double best_cost = 1e30;
+  const int cands[4] = {256, 192, 128, 64};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (bn > 64 && N <= bn / 2) continue;  // mostly padding
+    const long long tiles = m_tiles * ((N + bn - 1) / bn) * batch;
+    const long long waves = (tiles + sms - 1) / sms;
+    // per-tile cost ~ BN (MMA time) + a fixed part (epilogue drain / pipeline fill)
+    const double cost = (double)waves * (bn + 24.0);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+}  // namespace vlm
+
+using namespace vlm;
+
+extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, long long ldb,
+                             int b_mn_major, void* c, long long ldc, int c_is_fp32, int M, int N, int K,
+                             const float* bias, const void* residual, long long ldr, int act, const void* aux_in,
+                             void* aux_out, long long ld_aux, float alpha, int accumulate, int batch,
+                             long long a_batch_stride, long long b_batch_stride, long long c_batch_stride,
+                             long long aux_batch_stride, long long res_batch_stride, int force_bn, int max_ctas,
+                             void* stream) {
+  VLM_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "vlm_gemm_bf16: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
+  VLM_REQUIRE(a && b && c, "vlm_gemm_bf16: null operand");
+  VLM_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "vlm_gemm_bf16: lda/ldb must be multiples of 8 elements (TMA 16B stride)");
+  VLM_REQUIRE(((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)c % 16 == 0),
+              "vlm_gemm_bf16: operands must be 16B aligned");
+  VLM_REQUIRE(ldc % (c_is_fp32 ? 4 : 8) == 0, "vlm_gemm_bf16: ldc must keep rows 16B aligned");
+  VLM_REQUIRE(act >= 0 && act <= 2, "vlm_gemm_bf16: act must be 0|1|2");
+  VLM_REQUIRE(act != 2 || aux_in, "vlm_gemm_bf16: act=2 needs aux_in");
+  VLM_REQUIRE(!residual || ldr % (c_is_fp32 ? 4 : 8) == 0, "vlm_gemm_bf16: ldr alignment");
+  VLM_REQUIRE(!(aux_in || aux_out) || ld_aux % 8 == 0, "vlm_gemm_bf16: ld_aux alignment");
+  VLM_REQUIRE(!bias || ((uintptr_t)bias % 16 == 0), "vlm_gemm_bf16: bias must be 16B aligned");
+  VLM_REQUIRE(batch == 1 || (a_batch_stride % 8 == 0 && b_batch_stride % 8 == 0), "vlm_gemm_bf16: batch strides % 8");
+
+  const int bn = pick_bn(M, N, batch, force_bn);
+  CUtensorMap ta, tb;
+  // a zero batch stride broadcasts that operand: encode a single-batch map and pin the batch coordinate to 0
+  const int a_bmul = (batch > 1 && a_batch_stride != 0) ? 1 : 0, b_bmul = (batch > 1 && b_batch_stride != 0) ? 1 : 0;
+  const int a_nb = a_bmul ? batch : 1, b_nb = b_bmul ? batch : 1;
+  // A: K-major -> tensor {K, M}, box {64, 128}; MN-major -> tensor {M, K}, box {64, 64}
+  if (a_mn_major) {
+    if (make_tmap_bf16(&ta, a, (uint64_t)M, (uint64_t)K, a_nb, lda, a_batch_stride, GEMM_BK)) return -1;
+  } else {
+    if (make_tmap_bf16(&ta, a, (uint64_t)K, (uint64_t)M, a_nb, lda, a_batch_stride, GEMM_BM)) return -1;
+  }
+  if (b_mn_major) {
+    if (make_tmap_bf16(&tb, b, (uint64_t)N, (uint64_t)K, b_nb, ldb, b_batch_stride, GEMM_BK)) return -1;
+  } else {
+    if (make_tmap_bf16(&tb, b, (uint64_t)K, (uint64_t)N, b_nb, ldb, b_batch_stride, bn)) return -1;
+  }
+  GemmEpilogue e;
+  e.c = c;
+  e.ldc = ldc;
+  e.c_fp32 = c_is_fp32;
+  e.bias = bias;
+  e.residual = residual;
+  e.ldr = ldr;
+  e.act = act;
+  e.aux_in = reinterpret_cast<const bf16*>(aux_in);
+  e.aux_out = reinterpret_cast<bf16*>(aux_out);
+  e.ld_aux = ld_aux;
+  e.alpha = alpha;
+  e.accumulate = accumulate;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+
+#define VLM_GEMM_DISPATCH(BN_)                                                                                      \
+  if (a_mn_major) {                                                                                                 \
+    if (b_mn_major)                                                                                                 \
+      return launch_gemm<BN_, true, true>(ta, tb, M, N, K, batch, a_bmul, b_bmul, c_batch_stride, aux_batch_stride,                 \
+                                          res_batch_stride, e, max_ctas, s);                                        \
+    return launch_gemm<BN_, true, false>(ta, tb, M, N, K, batch, a_bmul, b_bmul, c_batch_stride, aux_batch_stride, res_batch_stride, \
+                                         e, max_ctas, s);                                                           \
+  } else {                                                                                                          \
+    if (b_mn_major)                                                                                                 \
+      return launch_gemm<BN_, false, true>(ta, tb, M, N, K, batch, a_bmul, b_bmul, c_batch_stride, aux_batch_stride,                \
+                                           res_batch_stride, e, max_ctas, s);                                       \
+    return launch_gemm<BN_, false, false>(ta, tb, M, N, K, batch, a_bmul, b_bmul, c_batch_stride, aux_batch_stride,                 \
+                                          res_batch_stride, e, max_ctas, s);                                        \
+  }
+  switch (bn) {
+    case 64: VLM_GEMM_DISPATCH(64)
+    case 128: VLM_GEMM_DISPATCH(128)
+    case 192: VLM_GEMM_DISPATCH(192)
+    default: VLM_GEMM_DISPATCH(256)
+  }
+#undef VLM_GEMM_DISPATCH
+}
