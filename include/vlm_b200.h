@@ -46,6 +46,84 @@ int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, l
                   long long c_batch_stride, long long aux_batch_stride, long long res_batch_stride, int force_bn,
                   int max_ctas, void* stream);
 
+/* ---- LayerNorm -------------------------------------------------------------------------------------------------- */
+/* y = LN(x) * gamma + beta, biased variance, one warp per row; x bf16 or fp32, y bf16; mean/rstd (fp32 [M]) optional.
+ * Replaces nn.LayerNorm in HF:vit/modeling_vit.py:333,340,455 and HF:bert_generation/modeling_bert_generation.py:52-56,
+ * 288-292,410-429.  D % 8 == 0, D <= 2048. */
+int vlm_layernorm_fwd(const void* x, int x_is_fp32, const float* gamma, const float* beta, void* y, float* mean,
+                      float* rstd, int M, int D, float eps, void* stream);
+/* dx = LN'(dy) (+ dres), dtype of x; dgamma/dbeta (fp32 [D]) are ACCUMULATED with atomics (caller zeroes). */
+int vlm_layernorm_bwd(const void* dy, const void* x, int x_is_fp32, const float* mean, const float* rstd,
+                      const float* gamma, const void* dres, void* dx, float* dgamma, float* dbeta, int M, int D,
+                      void* stream);
+
+/* ---- attention -------------------------------------------------------------------------------------------------- */
+/* O = softmax(scale * Q K^T + mask) V per (batch, head); bf16 in/out, fp32 softmax.  q/k/v/o are addressed as
+ * base + b*bs + row*rs + h*DH (elements), so packed QKV projections are consumed in place.  kmask: uint8 [B,Sk],
+ * 1 = attend (key padding / encoder_attention_mask), may be null.  causal!=0 adds the j<=i mask.  lse: fp32 [B,H,Tq]
+ * (natural log), needed by the backward.  p_drop: dropout on the probabilities (Philox seed/offset).
+ * Replaces ALL_ATTENTION_FUNCTIONS['sdpa'|'eager'] behind HF:vit/modeling_vit.py:232-247 and
+ * HF:bert_generation/modeling_bert_generation.py:114-153 (self, create_causal_mask :568-574), :181-232 (cross,
+ * create_bidirectional_mask :582-588).  DH in {48, 64, 96}. */
+int vlm_attention_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                      const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse,
+                      const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH, int causal, float scale, float p_drop,
+                      unsigned long long seed, unsigned long long offset, void* stream);
+/* Gradients dq/dk/dv (bf16, same addressing scheme with their own strides); delta: fp32 [B,H,Tq] scratch. */
+int vlm_attention_bwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                      const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                      const void* d_o, long long do_bs, long long do_rs, const float* lse, float* delta, void* dq,
+                      long long dq_bs, long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv,
+                      long long dv_bs, long long dv_rs, const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH,
+                      int causal, float scale, float p_drop, unsigned long long seed, unsigned long long offset,
+                      void* stream);
+
+/* ---- softmax cross-entropy (LM head loss, label-smoothing CE) ---------------------------------------------------- */
+/* One pass per row: loss_rows[r] (0 for ignored rows), lse_rows[r] (optional), and dlogits = (softmax - target) *
+ * grad_scale (optional, same dtype as logits, may alias logits; columns [V, ldd) are zeroed).
+ * shift_T > 0: ids is input_ids [R = B*T]; the label of row (b,t) is ids[b,t+1], the last position of each sequence
+ * is ignored — HF:loss/loss_utils.py:45-66 reached via vilmedic/blocks/huggingface/decoder/decoder_model.py:46
+ * (labels=input_ids, pads are NOT masked).  shift_T == 0: ids are labels [R], negative = ignore.
+ * smoothing: vilmedic/blocks/losses/mvqa/LabelSmoothingCrossEntropyLoss.py:38-48. */
+int vlm_softmax_ce(const void* logits, int logits_fp32, long long ld, const long long* ids, int shift_T, int R, int V,
+                   float smoothing, float grad_scale, void* dlogits, long long ldd, float* loss_rows, float* lse_rows,
+                   void* stream);
+
+/* ---- helpers around the core ------------------------------------------------------------------------------------ */
+int vlm_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+/* images fp32 [B,C,H,W] -> bf16 [B, 1+(H/P)(W/P), C*P*P], row 0 of every image = 0 (CLS slot); column order = Conv2d
+ * weight flatten (HF:vit/modeling_vit.py:151,166). */
+int vlm_patchify(const float* images, void* patches, int B, int C, int H, int W, int P, void* stream);
+/* x[b,0,:] = cls + pos[0]  (HF:vit/modeling_vit.py:117-124). */
+int vlm_vit_cls_pos(void* x, int x_is_fp32, const float* cls, const float* pos, int B, int S, int D, void* stream);
+/* dpos[s] += sum_b dx[b,s]; dcls += sum_b dx[b,0]; dbias += sum_{b,s>=1} dx[b,s]  (any of the three may be null). */
+int vlm_vit_embed_bwd(const void* dx, int dx_is_fp32, float* dpos, float* dcls, float* dbias, int B, int S, int D,
+                      void* stream);
+/* out[n] += sum_m x[m,n]  (bias gradients; caller zeroes). */
+int vlm_colsum_bf16(const void* x, long long ld, float* out, int M, int N, void* stream);
+/* mask[r] = (sum_d |f[r,d]| != 0)  — vilmedic/blocks/vision/visual_encoder.py:138. */
+int vlm_features_mask(const void* feats, uint8_t* mask, int R, int D, void* stream);
+/* z[r] = word[ids[r]] + pos[pos_offset + r % T]  (HF:bert_generation/modeling_bert_generation.py:410-429, pre-LN). */
+int vlm_embed_fwd(const long long* ids, const float* word, const float* pos, void* z, int R, int T, int D, int V,
+                  int pos_offset, void* stream);
+/* scatter-add of dz into dword / dpos (fp32, atomics; either may be null). */
+int vlm_embed_bwd(const long long* ids, const void* dz, float* dword, float* dpos, int R, int T, int D, int V,
+                  int pos_offset, void* stream);
+/* y = x * keep / (1-p), keep ~ Philox(seed, offset, element); same call on grads is the backward.  n % 8 == 0. */
+int vlm_dropout_bf16(const void* x, void* y, long long n, float p, unsigned long long seed, unsigned long long offset,
+                     void* stream);
+/* out[0] = scale * sum(x[0..n))  (deterministic single-block reduction; mean of per-row losses). */
+int vlm_sum_scale_f32(const float* x, int n, float scale, float* out, void* stream);
+
+/* ---- optimizer (vilmedic/executors/trainor.py:119-124) ------------------------------------------ */
+/* out[0] += sum(g^2)  (caller zeroes). */
+int vlm_sumsq_f32(const float* g, long long n, float* out, void* stream);
+/* AdamW over flat fp32 buffers (torch.optim.AdamW semantics), writes the bf16 mirror of p, optional global-norm clip
+ * (gnorm_sq_ptr + max_norm), grad pre-scale (1/world, 1/grad_accu, 1/loss_scale) and fused zero_grad. */
+int vlm_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int* step_ptr, int increment_step, const float* lr_scale_ptr,
+                   float grad_scale, const float* gnorm_sq_ptr, float max_norm, int zero_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,8 +12,15 @@ def _ref(a, b, a_mn, b_mn):
 
 
 def _rand(shape, dev, seed):
+    """bf16 randn whose row pitch is padded to a multiple of 8 elements (TMA needs 16-byte row strides)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
-    return torch.randn(shape, generator=g).to(dev).to(torch.bfloat16)
+    t = torch.randn(shape, generator=g).to(dev).to(torch.bfloat16)
+    pad = (-shape[-1]) % 8
+    if pad:
+        buf = torch.zeros(shape[:-1] + (shape[-1] + pad,), device=dev, dtype=torch.bfloat16)
+        buf[..., :shape[-1]] = t
+        t = buf[..., :shape[-1]]
+    return t
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])

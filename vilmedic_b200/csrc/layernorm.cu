@@ -1,0 +1,243 @@
+// LayerNorm forward / backward, one warp per row, 128-bit vector access, row cached in registers (exact two-pass
+// statistics).  HBM-bound: algorithmic bytes = read x + write y (fwd), read x,dy + write dx (bwd).
+// Replaces nn.LayerNorm in HF ViT (modeling_vit.py:333,340,455 layernorm_before/after/final) and BertGeneration
+// (modeling_bert_generation.py:52-56 SelfOutput.LayerNorm, 288-292 Output.LayerNorm, 410-429 embeddings.LayerNorm),
+// reached from vilmedic/blocks/vision/visual_encoder.py:180-186 and vilmedic/blocks/huggingface/decoder/decoder_model.py:42-47.
+#include "common.cuh"
+#include "vlm_b200.h"
+
+namespace vlm {
+
+template <typename T>
+struct Vec8;
+template <>
+struct Vec8<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float* v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float* v) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <>
+struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+
+// NV = number of 8-element vectors per lane (D <= NV*256)
+template <typename TIn, int NV>
+__global__ void __launch_bounds__(128) layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, bf16* __restrict__ y,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int M, int D, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= M) return;
+  const int nvec = D >> 3;
+  const TIn* xr = x + (size_t)row * D;
+  float v[NV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+      Vec8<TIn>::load(xr + vi * 8, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  bf16* yr = y + (size_t)row * D;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+      float g[8], b[8], o[8];
+      Vec8<float>::load(gamma + vi * 8, g);
+      Vec8<float>::load(beta + vi * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+      Vec8<bf16>::store(yr + vi * 8, o);
+    }
+  }
+}
+
+// Backward.  Persistent over rows so that the per-column dgamma/dbeta partials live in registers; one atomicAdd per
+// column per CTA at the end.  dx (+= dres) has the dtype of x.
+template <typename TIn, int NV>
+__global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restrict__ dy, const TIn* __restrict__ x,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const float* __restrict__ gamma, const TIn* __restrict__ dres,
+                                                            TIn* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int M, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = D >> 3;
+  float dg[NV][8], db[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
+
+  for (int row = blockIdx.x * 4 + warp; row < M; row += gridDim.x * 4) {
+    const TIn* xr = x + (size_t)row * D;
+    const bf16* dyr = dy + (size_t)row * D;
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NV][8], g[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        float xv[8], dv[8], gm[8];
+        Vec8<TIn>::load(xr + vi * 8, xv);
+        Vec8<bf16>::load(dyr + vi * 8, dv);
+        Vec8<float>::load(gamma + vi * 8, gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xv[j] - mu) * rs;
+          g[i][j] = dv[j] * gm[j];
+          s1 += g[i][j];
+          s2 += g[i][j] * xh[i][j];
+          dg[i][j] += dv[j] * xh[i][j];
+          db[i][j] += dv[j];
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) / (float)D, c2 = warp_sum(s2) / (float)D;
+    TIn* dxr = dx + (size_t)row * D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - c1 - xh[i][j] * c2);
+        if (dres) {
+          float r[8];
+          Vec8<TIn>::load(dres + (size_t)row * D + vi * 8, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
+        Vec8<TIn>::store(dxr + vi * 8, o);
+      }
+    }
+  }
+
+  // cross-warp reduction of the column partials, then one atomic per column per CTA
+  __shared__ float red[4][256];
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? dg[i][j] : db[i][j];
+      __syncthreads();
+      // 256 columns of this vector slot: thread t sums columns t and t+128
+      for (int c = threadIdx.x; c < 256; c += 128) {
+        const int vi = (c >> 3) + 32 * i;  // vector index within the row
+        if (vi < nvec) {
+          const float tot = red[0][c] + red[1][c] + red[2][c] + red[3][c];
+          float* dst = (pass == 0 ? dgamma : dbeta);
+          if (dst) atomicAdd(dst + vi * 8 + (c & 7), tot);
+        }
+      }
+    }
+  }
+}
+
+template <typename TIn>
+static int ln_fwd_dispatch(const TIn* x, const float* gamma, const float* beta, bf16* y, float* mean, float* rstd, int M,
+                           int D, float eps, cudaStream_t s) {
+  const int nv = (D / 8 + 31) / 32;
+  const int grid = (M + 3) / 4;
+#define LN_FWD(NV_) layernorm_fwd_kernel<TIn, NV_><<<grid, 128, 0, s>>>(x, gamma, beta, y, mean, rstd, M, D, eps)
+  switch (nv) {
+    case 1: LN_FWD(1); break;
+    case 2: LN_FWD(2); break;
+    case 3: LN_FWD(3); break;
+    case 4: LN_FWD(4); break;
+    case 5: case 6: LN_FWD(6); break;
+    case 7: case 8: LN_FWD(8); break;
+    default: set_error("layernorm: D=%d unsupported (max 2048)", D); return -1;
+  }
+#undef LN_FWD
+  return check_launch("layernorm_fwd");
+}
+
+template <typename TIn>
+static int ln_bwd_dispatch(const bf16* dy, const TIn* x, const float* mean, const float* rstd, const float* gamma,
+                           const TIn* dres, TIn* dx, float* dgamma, float* dbeta, int M, int D, cudaStream_t s) {
+  const int nv = (D / 8 + 31) / 32;
+  int grid = num_sms() * 4;
+  if (grid > (M + 3) / 4) grid = (M + 3) / 4;
+#define LN_BWD(NV_) layernorm_bwd_kernel<TIn, NV_><<<grid, 128, 0, s>>>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, M, D)
+  switch (nv) {
+    case 1: LN_BWD(1); break;
+    case 2: LN_BWD(2); break;
+    case 3: LN_BWD(3); break;
+    case 4: LN_BWD(4); break;
+    case 5: case 6: LN_BWD(6); break;
+    case 7: case 8: LN_BWD(8); break;
+    default: set_error("layernorm: D=%d unsupported (max 2048)", D); return -1;
+  }
+#undef LN_BWD
+  return check_launch("layernorm_bwd");
+}
+
+}  // namespace vlm
+
+using namespace vlm;
+
+extern "C" int vlm_layernorm_fwd(const void* x, int x_is_fp32, const float* gamma, const float* beta, void* y,
+                                 float* mean, float* rstd, int M, int D, float eps, void* stream) {
+  VLM_REQUIRE(M > 0 && D > 0 && D % 8 == 0, "vlm_layernorm_fwd: need D %% 8 == 0 (M=%d D=%d)", M, D);
+  VLM_REQUIRE(x && gamma && beta && y, "vlm_layernorm_fwd: null pointer");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (x_is_fp32)
+    return ln_fwd_dispatch<float>(reinterpret_cast<const float*>(x), gamma, beta, reinterpret_cast<bf16*>(y), mean, rstd,
+                                  M, D, eps, s);
+  return ln_fwd_dispatch<bf16>(reinterpret_cast<const bf16*>(x), gamma, beta, reinterpret_cast<bf16*>(y), mean, rstd, M, D,
+                               eps, s);
+}
+
+extern "C" int vlm_layernorm_bwd(const void* dy, const void* x, int x_is_fp32, const float* mean, const float* rstd,
+                                 const float* gamma, const void* dres, void* dx, float* dgamma, float* dbeta, int M,
+                                 int D, void* stream) {
+  VLM_REQUIRE(M > 0 && D > 0 && D % 8 == 0, "vlm_layernorm_bwd: need D %% 8 == 0 (M=%d D=%d)", M, D);
+  VLM_REQUIRE(dy && x && mean && rstd && gamma && dx, "vlm_layernorm_bwd: null pointer");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (x_is_fp32)
+    return ln_bwd_dispatch<float>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const float*>(x), mean, rstd, gamma,
+                                  reinterpret_cast<const float*>(dres), reinterpret_cast<float*>(dx), dgamma, dbeta, M, D, s);
+  return ln_bwd_dispatch<bf16>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), mean, rstd, gamma,
+                               reinterpret_cast<const bf16*>(dres), reinterpret_cast<bf16*>(dx), dgamma, dbeta, M, D, s);
+}

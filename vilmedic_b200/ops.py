@@ -80,3 +80,179 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, out=None, out_dtype=torch.
         c_int(force_bn), c_int(max_ctas), stream_ptr())
     check(rc, "vlm_gemm_bf16")
     return out
+
+
+def _L():
+    return _lib.lib()
+
+
+def layernorm_fwd(x, gamma, beta, eps, save_stats=True):
+    """x [M,D] bf16|fp32 -> (y bf16, mean, rstd)."""
+    _req(x.is_cuda and x.dim() == 2 and x.is_contiguous(), "layernorm input must be contiguous [M,D]")
+    M, D = x.shape
+    y = torch.empty((M, D), device=x.device, dtype=torch.bfloat16)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32) if save_stats else None
+    check(_L().vlm_layernorm_fwd(ptr(x), c_int(int(x.dtype == torch.float32)), ptr(gamma), ptr(beta), ptr(y), ptr(mean),
+                                 ptr(rstd), c_int(M), c_int(D), c_float(eps), stream_ptr()), "vlm_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None):
+    """Returns dx (dtype of x); ACCUMULATES into dgamma / dbeta (fp32 [D])."""
+    M, D = x.shape
+    _req(dy.is_contiguous() and dy.dtype == torch.bfloat16 and x.is_contiguous(), "layernorm_bwd: bad inputs")
+    dx = torch.empty_like(x)
+    if dres is not None:
+        _req(dres.dtype == x.dtype and dres.is_contiguous(), "dres dtype must match x")
+    check(_L().vlm_layernorm_bwd(ptr(dy), ptr(x), c_int(int(x.dtype == torch.float32)), ptr(mean), ptr(rstd), ptr(gamma),
+                                 ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta), c_int(M), c_int(D), stream_ptr()),
+          "vlm_layernorm_bwd")
+    return dx
+
+
+def _bh_strides(t, H, DH):
+    """t is a [B, T, >=H*DH] view (last dim contiguous) -> (batch stride, row stride)."""
+    _req(t.dim() == 3 and t.stride(2) == 1 and t.dtype == torch.bfloat16, "attention operand must be [B,T,H*DH] bf16 view")
+    return t.stride(0), t.stride(1)
+
+
+def attention_fwd(q, k, v, H, DH, *, kmask=None, causal=False, scale=None, p_drop=0.0, seed=0, offset=0):
+    """q [B,Tq,H*DH], k/v [B,Sk,H*DH] (possibly strided views of packed projections) -> (o [B,Tq,H*DH], lse [B,H,Tq])."""
+    B, Tq = q.shape[0], q.shape[1]
+    Sk = k.shape[1]
+    scale = (1.0 / DH ** 0.5) if scale is None else scale
+    o = torch.empty((B, Tq, H * DH), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
+    qs, ks, vs = _bh_strides(q, H, DH), _bh_strides(k, H, DH), _bh_strides(v, H, DH)
+    if kmask is not None:
+        _req(kmask.dtype == torch.uint8 and kmask.is_contiguous() and tuple(kmask.shape) == (B, Sk), "kmask must be uint8 [B,Sk]")
+    check(_L().vlm_attention_fwd(ptr(q), c_ll(qs[0]), c_ll(qs[1]), ptr(k), c_ll(ks[0]), c_ll(ks[1]), ptr(v), c_ll(vs[0]),
+                                 c_ll(vs[1]), ptr(o), c_ll(o.stride(0)), c_ll(o.stride(1)), ptr(lse), ptr(kmask),
+                                 c_int(B), c_int(H), c_int(Tq), c_int(Sk), c_int(DH), c_int(int(causal)), c_float(scale),
+                                 c_float(p_drop), c_u64(seed), c_u64(offset), stream_ptr()), "vlm_attention_fwd")
+    return o, lse
+
+
+def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, H, DH, *, kmask=None, causal=False, scale=None, p_drop=0.0, seed=0,
+                  offset=0):
+    """Writes dq/dk/dv (pre-allocated bf16 views with the q/k/v addressing scheme)."""
+    B, Tq = q.shape[0], q.shape[1]
+    Sk = k.shape[1]
+    scale = (1.0 / DH ** 0.5) if scale is None else scale
+    delta = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
+    s = [_bh_strides(t, H, DH) for t in (q, k, v, o, do, dq, dk, dv)]
+    check(_L().vlm_attention_bwd(ptr(q), c_ll(s[0][0]), c_ll(s[0][1]), ptr(k), c_ll(s[1][0]), c_ll(s[1][1]), ptr(v),
+                                 c_ll(s[2][0]), c_ll(s[2][1]), ptr(o), c_ll(s[3][0]), c_ll(s[3][1]), ptr(do),
+                                 c_ll(s[4][0]), c_ll(s[4][1]), ptr(lse), ptr(delta), ptr(dq), c_ll(s[5][0]),
+                                 c_ll(s[5][1]), ptr(dk), c_ll(s[6][0]), c_ll(s[6][1]), ptr(dv), c_ll(s[7][0]),
+                                 c_ll(s[7][1]), ptr(kmask), c_int(B), c_int(H), c_int(Tq), c_int(Sk), c_int(DH),
+                                 c_int(int(causal)), c_float(scale), c_float(p_drop), c_u64(seed), c_u64(offset),
+                                 stream_ptr()), "vlm_attention_bwd")
+
+
+def softmax_ce(logits, ids, V, *, shift_T=0, smoothing=0.0, grad_scale=1.0, dlogits=None, want_lse=False):
+    """logits [R, ld>=V] (bf16|fp32).  Returns (loss_rows fp32 [R], lse_rows|None).  dlogits may alias logits."""
+    _req(logits.dim() == 2 and logits.stride(1) == 1, "logits must be [R, ld]")
+    R = logits.shape[0]
+    loss_rows = torch.empty(R, device=logits.device, dtype=torch.float32)
+    lse_rows = torch.empty(R, device=logits.device, dtype=torch.float32) if want_lse else None
+    _req(ids.dtype == torch.int64 and ids.is_contiguous() and ids.numel() == R, "ids must be int64 [R]")
+    if dlogits is not None:
+        _req(dlogits.dtype == logits.dtype and dlogits.stride(1) == 1, "dlogits dtype must match logits")
+    check(_L().vlm_softmax_ce(ptr(logits), c_int(int(logits.dtype == torch.float32)), c_ll(logits.stride(0)), ptr(ids),
+                              c_int(shift_T), c_int(R), c_int(V), c_float(smoothing), c_float(grad_scale), ptr(dlogits),
+                              c_ll(dlogits.stride(0) if dlogits is not None else 0), ptr(loss_rows), ptr(lse_rows),
+                              stream_ptr()), "vlm_softmax_ce")
+    return loss_rows, lse_rows
+
+
+def cast_bf16(src, dst=None):
+    _req(src.is_cuda and src.dtype == torch.float32 and src.is_contiguous(), "cast_bf16: need contiguous fp32")
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    check(_L().vlm_cast_f32_to_bf16(ptr(src), ptr(dst), c_ll(src.numel()), stream_ptr()), "vlm_cast_f32_to_bf16")
+    return dst
+
+
+def patchify(images, P):
+    _req(images.is_cuda and images.dtype == torch.float32 and images.is_contiguous() and images.dim() == 4, "patchify: fp32 NCHW")
+    B, C, Hh, W = images.shape
+    S = 1 + (Hh // P) * (W // P)
+    out = torch.empty((B, S, C * P * P), device=images.device, dtype=torch.bfloat16)
+    check(_L().vlm_patchify(ptr(images), ptr(out), c_int(B), c_int(C), c_int(Hh), c_int(W), c_int(P), stream_ptr()), "vlm_patchify")
+    return out
+
+
+def vit_cls_pos(x, cls, pos):
+    B, S, D = x.shape
+    check(_L().vlm_vit_cls_pos(ptr(x), c_int(int(x.dtype == torch.float32)), ptr(cls), ptr(pos), c_int(B), c_int(S), c_int(D),
+                               stream_ptr()), "vlm_vit_cls_pos")
+
+
+def vit_embed_bwd(dx, dpos, dcls, dbias):
+    B, S, D = dx.shape
+    _req(dx.is_contiguous(), "vit_embed_bwd: dx must be contiguous")
+    check(_L().vlm_vit_embed_bwd(ptr(dx), c_int(int(dx.dtype == torch.float32)), ptr(dpos), ptr(dcls), ptr(dbias), c_int(B),
+                                 c_int(S), c_int(D), stream_ptr()), "vlm_vit_embed_bwd")
+
+
+def colsum(x, out):
+    """out[n] += sum_m x[m,n] (x bf16 [M,N] view with contiguous last dim)."""
+    _req(x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16, "colsum: bf16 [M,N]")
+    check(_L().vlm_colsum_bf16(ptr(x), c_ll(x.stride(0)), ptr(out), c_int(x.shape[0]), c_int(x.shape[1]), stream_ptr()),
+          "vlm_colsum_bf16")
+
+
+def features_mask(feats):
+    """feats bf16 [B,S,D] contiguous -> uint8 [B,S]."""
+    _req(feats.is_contiguous() and feats.dtype == torch.bfloat16, "features_mask: contiguous bf16")
+    B, S, D = feats.shape
+    mask = torch.empty((B, S), device=feats.device, dtype=torch.uint8)
+    check(_L().vlm_features_mask(ptr(feats), ptr(mask), c_int(B * S), c_int(D), stream_ptr()), "vlm_features_mask")
+    return mask
+
+
+def embed_fwd(ids, word, pos, T, pos_offset=0):
+    _req(ids.dtype == torch.int64 and ids.is_contiguous(), "ids must be contiguous int64")
+    R = ids.numel()
+    V, D = word.shape
+    z = torch.empty((R, D), device=word.device, dtype=torch.bfloat16)
+    check(_L().vlm_embed_fwd(ptr(ids), ptr(word), ptr(pos), ptr(z), c_int(R), c_int(T), c_int(D), c_int(V), c_int(pos_offset),
+                             stream_ptr()), "vlm_embed_fwd")
+    return z
+
+
+def embed_bwd(ids, dz, dword, dpos, T, V, pos_offset=0):
+    R, D = dz.shape
+    _req(dz.is_contiguous() and dz.dtype == torch.bfloat16, "embed_bwd: dz contiguous bf16")
+    check(_L().vlm_embed_bwd(ptr(ids), ptr(dz), ptr(dword), ptr(dpos), c_int(R), c_int(T), c_int(D), c_int(V),
+                             c_int(pos_offset), stream_ptr()), "vlm_embed_bwd")
+
+
+def dropout(x, p, seed, offset, out=None):
+    _req(x.is_contiguous() and x.dtype == torch.bfloat16 and x.numel() % 8 == 0, "dropout: contiguous bf16, numel % 8 == 0")
+    if out is None:
+        out = torch.empty_like(x)
+    check(_L().vlm_dropout_bf16(ptr(x), ptr(out), c_ll(x.numel()), c_float(p), c_u64(seed), c_u64(offset), stream_ptr()),
+          "vlm_dropout_bf16")
+    return out
+
+
+def sum_scale(x, scale):
+    out = torch.empty((), device=x.device, dtype=torch.float32)
+    check(_L().vlm_sum_scale_f32(ptr(x), c_int(x.numel()), c_float(scale), ptr(out), stream_ptr()), "vlm_sum_scale_f32")
+    return out
+
+
+def sumsq(g, out):
+    check(_L().vlm_sumsq_f32(ptr(g), c_ll(g.numel()), ptr(out), stream_ptr()), "vlm_sumsq_f32")
+
+
+def adamw_step(p, g, m, v, p_bf16, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, step_t=None,
+               increment_step=True, lr_scale_t=None, grad_scale=1.0, gnorm_sq_t=None, max_norm=0.0, zero_grad=True):
+    n = p.numel()
+    check(_L().vlm_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), c_ll(n), c_float(lr), c_float(betas[0]),
+                              c_float(betas[1]), c_float(eps), c_float(weight_decay), ptr(step_t), c_int(int(increment_step)),
+                              ptr(lr_scale_t), c_float(grad_scale), ptr(gnorm_sq_t), c_float(max_norm),
+                              c_int(int(zero_grad)), stream_ptr()), "vlm_adamw_step")
