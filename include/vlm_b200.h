@@ -32,7 +32,8 @@ int vlm_device_check(void);
 /* C[M,N] = epi(alpha * A'[M,K] * B'[N,K]^T), bf16 operands, fp32 accumulate in TMEM.
  *   a_mn_major=0: A' stored [M][lda] (k contiguous); 1: stored [K][lda] (m contiguous).  Same for b / N.
  *   epi: (+bias[N] fp32) -> act (0 none | 1 GELU-erf, pre-activation stashed to aux_out if non-null |
- *        2 multiply by GELU'(aux_in)) -> (+residual, dtype of C) -> (accumulate into C) -> store bf16 or fp32.
+ *        2 multiply by GELU'(aux_in)) -> dropout(p_drop; Philox(seed, offset, (row*N+col)/4), same stream as
+ *        vlm_dropout_bf16 on the flat [M,N] tensor) -> (+residual, dtype of C) -> (accumulate into C) -> store.
  *   batch>1: strided-batched; operands advance by *_batch_stride ELEMENTS per batch (bias is shared).
  *   force_bn: 0 = heuristic, else N-tile in {64,128,192,256}.  max_ctas: 0 = one per SM.
  * Replaces nn.Linear / torch.mm behind: HF:vit/modeling_vit.py:228-230,265-268,296-312 (ViT Q/K/V, out, FFN),
@@ -43,8 +44,8 @@ int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, l
                   long long ldc, int c_is_fp32, int M, int N, int K, const float* bias, const void* residual,
                   long long ldr, int act, const void* aux_in, void* aux_out, long long ld_aux, float alpha,
                   int accumulate, int batch, long long a_batch_stride, long long b_batch_stride,
-                  long long c_batch_stride, long long aux_batch_stride, long long res_batch_stride, int force_bn,
-                  int max_ctas, void* stream);
+                  long long c_batch_stride, long long aux_batch_stride, long long res_batch_stride, float p_drop,
+                  unsigned long long seed, unsigned long long offset, int force_bn, int max_ctas, void* stream);
 
 /* ---- LayerNorm -------------------------------------------------------------------------------------------------- */
 /* y = LN(x) * gamma + beta, biased variance, one warp per row; x bf16 or fp32, y bf16; mean/rstd (fp32 [M]) optional.

@@ -37,6 +37,9 @@ struct GemmEpilogue {
   long long ld_aux;
   float alpha;
   int accumulate;             // c += result
+  float p_drop;               // dropout on the activation (after bias/act, before the residual add)
+  unsigned long long seed, offset;
+  int drop_ld;                // logical row width used for the dropout element index (row * drop_ld + col)
 };
 
 template <int BN>
@@ -98,6 +101,20 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int
         v[8 * j + 5] *= gelu_erf_grad(p2.y);
         v[8 * j + 6] *= gelu_erf_grad(p3.x);
         v[8 * j + 7] *= gelu_erf_grad(p3.y);
+      }
+    }
+    if (e.p_drop > 0.f) {
+      const Philox rng(e.seed);
+      const uint32_t thr = (uint32_t)(e.p_drop * 4294967296.0f);
+      const float inv_keep = 1.f / (1.f - e.p_drop);
+      const unsigned long long base = ((unsigned long long)row * (unsigned long long)e.drop_ld + (unsigned long long)col0) >> 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 r = rng(base + j, e.offset);
+        v[4 * j + 0] = r.x >= thr ? v[4 * j + 0] * inv_keep : 0.f;
+        v[4 * j + 1] = r.y >= thr ? v[4 * j + 1] * inv_keep : 0.f;
+        v[4 * j + 2] = r.z >= thr ? v[4 * j + 2] * inv_keep : 0.f;
+        v[4 * j + 3] = r.w >= thr ? v[4 * j + 3] * inv_keep : 0.f;
       }
     }
     if (e.c_fp32) {
@@ -184,6 +201,13 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int
         x = gelu_erf(x);
       } else if (e.act == 2) {
         x *= gelu_erf_grad(__bfloat162float(e.aux_in[(long long)row * e.ld_aux + col]));
+      }
+      if (e.p_drop > 0.f) {
+        const Philox rng(e.seed);
+        const unsigned long long el = (unsigned long long)row * (unsigned long long)e.drop_ld + (unsigned long long)col;
+        const uint4 r = rng(el >> 2, e.offset);
+        const uint32_t w = (el & 3) == 0 ? r.x : ((el & 3) == 1 ? r.y : ((el & 3) == 2 ? r.z : r.w));
+        x = w >= (uint32_t)(e.p_drop * 4294967296.0f) ? x / (1.f - e.p_drop) : 0.f;
       }
       if (e.c_fp32) {
         float* c = reinterpret_cast<float*>(e.c) + (long long)row * e.ldc + col;
@@ -469,7 +493,8 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
                              const float* bias, const void* residual, long long ldr, int act, const void* aux_in,
                              void* aux_out, long long ld_aux, float alpha, int accumulate, int batch,
                              long long a_batch_stride, long long b_batch_stride, long long c_batch_stride,
-                             long long aux_batch_stride, long long res_batch_stride, int force_bn, int max_ctas,
+                             long long aux_batch_stride, long long res_batch_stride, float p_drop,
+                             unsigned long long seed, unsigned long long offset, int force_bn, int max_ctas,
                              void* stream) {
   VLM_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "vlm_gemm_bf16: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
   VLM_REQUIRE(a && b && c, "vlm_gemm_bf16: null operand");
@@ -478,6 +503,8 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
               "vlm_gemm_bf16: operands must be 16B aligned");
   VLM_REQUIRE(ldc % (c_is_fp32 ? 4 : 8) == 0, "vlm_gemm_bf16: ldc must keep rows 16B aligned");
   VLM_REQUIRE(act >= 0 && act <= 2, "vlm_gemm_bf16: act must be 0|1|2");
+  VLM_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || (N % 4 == 0 && batch == 1)),
+              "vlm_gemm_bf16: dropout needs 0<=p<1, N %% 4 == 0, batch == 1");
   VLM_REQUIRE(act != 2 || aux_in, "vlm_gemm_bf16: act=2 needs aux_in");
   VLM_REQUIRE(!residual || ldr % (c_is_fp32 ? 4 : 8) == 0, "vlm_gemm_bf16: ldr alignment");
   VLM_REQUIRE(!(aux_in || aux_out) || ld_aux % 8 == 0, "vlm_gemm_bf16: ld_aux alignment");
@@ -513,6 +540,10 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
   e.ld_aux = ld_aux;
   e.alpha = alpha;
   e.accumulate = accumulate;
+  e.p_drop = p_drop;
+  e.seed = seed;
+  e.offset = offset;
+  e.drop_ld = N;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
 
 #define VLM_GEMM_DISPATCH(BN_)                                                                                      \

@@ -23,7 +23,8 @@ def _is_bf16_cuda(t):
 
 
 def gemm(a, b, *, a_mn_major=False, b_mn_major=False, out=None, out_dtype=torch.bfloat16, bias=None, residual=None,
-         act=ACT_NONE, aux_in=None, aux_out=None, alpha=1.0, accumulate=False, force_bn=0, max_ctas=0):
+         act=ACT_NONE, aux_in=None, aux_out=None, alpha=1.0, accumulate=False, p_drop=0.0, seed=0, offset=0,
+         force_bn=0, max_ctas=0):
     """C[M,N] = epi(alpha * A' B'^T).
 
     a: [M,K] (K-major) or [K,M] (a_mn_major);  b: [N,K] (K-major, nn.Linear weight layout) or [K,N] (b_mn_major).
@@ -77,7 +78,7 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, out=None, out_dtype=torch.
         c_float(alpha), c_int(int(accumulate)), c_int(batch),
         c_ll(a.stride(0) if batched else 0), c_ll(b.stride(0) if batched else 0),
         c_ll(out.stride(0) if batched else 0), c_ll(aux_bs), c_ll(res_bs),
-        c_int(force_bn), c_int(max_ctas), stream_ptr())
+        c_float(p_drop), c_u64(seed), c_u64(offset), c_int(force_bn), c_int(max_ctas), stream_ptr())
     check(rc, "vlm_gemm_bf16")
     return out
 
