@@ -34,6 +34,7 @@ int vlm_device_check(void);
  *   epi: (+bias[N] fp32) -> act (0 none | 1 GELU-erf, pre-activation stashed to aux_out if non-null |
  *        2 multiply by GELU'(aux_in)) -> dropout(p_drop; Philox(seed, offset, (row*N+col)/4), same stream as
  *        vlm_dropout_bf16 on the flat [M,N] tensor) -> (+residual, dtype of C) -> (accumulate into C) -> store.
+ *   alpha_ptr: optional device scalar multiplied into alpha (e.g. the upstream loss gradient, no host sync).
  *   batch>1: strided-batched; operands advance by *_batch_stride ELEMENTS per batch (bias is shared).
  *   force_bn: 0 = heuristic, else N-tile in {64,128,192,256}.  max_ctas: 0 = one per SM.
  * Replaces nn.Linear / torch.mm behind: HF:vit/modeling_vit.py:228-230,265-268,296-312 (ViT Q/K/V, out, FFN),
@@ -43,7 +44,7 @@ int vlm_device_check(void);
 int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, long long ldb, int b_mn_major, void* c,
                   long long ldc, int c_is_fp32, int M, int N, int K, const float* bias, const void* residual,
                   long long ldr, int act, const void* aux_in, void* aux_out, long long ld_aux, float alpha,
-                  int accumulate, int batch, long long a_batch_stride, long long b_batch_stride,
+                  const float* alpha_ptr, int accumulate, int batch, long long a_batch_stride, long long b_batch_stride,
                   long long c_batch_stride, long long aux_batch_stride, long long res_batch_stride, float p_drop,
                   unsigned long long seed, unsigned long long offset, int force_bn, int max_ctas, void* stream);
 
@@ -100,8 +101,8 @@ int vlm_vit_cls_pos(void* x, int x_is_fp32, const float* cls, const float* pos, 
 /* dpos[s] += sum_b dx[b,s]; dcls += sum_b dx[b,0]; dbias += sum_{b,s>=1} dx[b,s]  (any of the three may be null). */
 int vlm_vit_embed_bwd(const void* dx, int dx_is_fp32, float* dpos, float* dcls, float* dbias, int B, int S, int D,
                       void* stream);
-/* out[n] += sum_m x[m,n]  (bias gradients; caller zeroes). */
-int vlm_colsum_bf16(const void* x, long long ld, float* out, int M, int N, void* stream);
+/* out[n] += (scale_ptr ? *scale_ptr : 1) * sum_m x[m,n]  (bias gradients; caller zeroes). */
+int vlm_colsum_bf16(const void* x, long long ld, float* out, int M, int N, const float* scale_ptr, void* stream);
 /* mask[r] = (sum_d |f[r,d]| != 0)  — vilmedic/blocks/vision/visual_encoder.py:138. */
 int vlm_features_mask(const void* feats, uint8_t* mask, int R, int D, void* stream);
 /* z[r] = word[ids[r]] + pos[pos_offset + r % T]  (HF:bert_generation/modeling_bert_generation.py:410-429, pre-LN). */
@@ -113,6 +114,12 @@ int vlm_embed_bwd(const long long* ids, const void* dz, float* dword, float* dpo
 /* y = x * keep / (1-p), keep ~ Philox(seed, offset, element); same call on grads is the backward.  n % 8 == 0. */
 int vlm_dropout_bf16(const void* x, void* y, long long n, float p, unsigned long long seed, unsigned long long offset,
                      void* stream);
+/* y[r,:] = mask[r / rows_per_mask] ? x[r,:] : 0 — multi-image masking, vilmedic/blocks/vision/visual_encoder.py:170-171. */
+int vlm_mask_rows_bf16(const void* x, void* y, const uint8_t* mask, int R, int D, int rows_per_mask, void* stream);
+/* fp32 activations: kind 0 = tanh (BertPooler, vilmedic/blocks/huggingface/encoder/encoder_model.py:58-60), 1 = ReLU
+ * (ConVIRT projection heads, vilmedic/models/selfsup/conVIRT.py:58-67).  The backward takes the forward output y. */
+int vlm_act_fwd_f32(const float* x, float* y, long long n, int kind, void* stream);
+int vlm_act_bwd_f32(const float* dy, const float* y, float* dx, long long n, int kind, void* stream);
 /* out[0] = scale * sum(x[0..n))  (deterministic single-block reduction; mean of per-row losses). */
 int vlm_sum_scale_f32(const float* x, int n, float scale, float* out, void* stream);
 

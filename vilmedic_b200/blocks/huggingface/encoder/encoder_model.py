@@ -1,0 +1,41 @@
+"""B200-native EncoderModel — mirror of vilmedic/blocks/huggingface/encoder/encoder_model.py:10-66: a bidirectional
+BERT-shaped text tower (BertGenerationEncoder when `encoder.proto` is None) with an optional BertPooler
+(tanh(W h[:,0] + b), :28-29,58-60).  `proto` set needs the HF hub -> NotImplementedError."""
+import torch
+import torch.nn as nn
+
+from ....arena import get_arena
+from ....cfgutil import cfg_get, to_attrdict
+from ....nn import BertTower, LinearFn, TanhFn, _lin, _root_of, bert_config
+
+
+class EncoderModel(nn.Module):
+    def __init__(self, encoder, **kwargs):
+        super().__init__()
+        encoder = to_attrdict(encoder)
+        if cfg_get(encoder, "proto") is not None:
+            raise NotImplementedError("EncoderModel(proto=%r): pretrained HF checkpoints need hub access" % encoder["proto"])
+        d = dict(encoder)
+        d.pop("proto", None)
+        add_pool = bool(d.pop("add_pooling_layer", False))
+        d["is_decoder"] = False
+        d["add_cross_attention"] = False
+        self.encoder = BertTower(bert_config(**d), with_lm_head=False)
+        self.config = self.encoder.config
+        self.pooler = None
+        if add_pool:
+            self.pooler = nn.Module()
+            self.pooler.dense = nn.Linear(self.config.hidden_size, self.config.hidden_size)
+
+    def forward(self, input_ids, attention_mask=None, **kwargs):
+        input_ids = input_ids.cuda(non_blocking=True)
+        attention_mask = attention_mask.cuda(non_blocking=True) if attention_mask is not None else None
+        x, B, T = self.encoder.hidden_states(input_ids, attention_mask)
+        D = x.shape[-1]
+        out = {"last_hidden_state": x.view(B, T, D), "pooler_output": None}
+        if self.pooler is not None:
+            arena = get_arena(_root_of(self))
+            first = x.view(B, T, D)[:, 0].contiguous()
+            h = LinearFn.apply(first, self.pooler.dense.weight, _lin(arena, self.pooler.dense), torch.float32)
+            out["pooler_output"] = TanhFn.apply(h)
+        return out

@@ -36,6 +36,7 @@ struct GemmEpilogue {
   bf16* aux_out;              // [M, ld_aux]
   long long ld_aux;
   float alpha;
+  const float* alpha_ptr;     // optional device scalar multiplied into alpha (upstream loss gradient)
   int accumulate;             // c += result
   float p_drop;               // dropout on the activation (after bias/act, before the residual add)
   unsigned long long seed, offset;
@@ -56,8 +57,9 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int
                                                const GemmEpilogue& e) {
   if (row >= M || col0 >= N) return;
   float v[32];
+  const float alpha = e.alpha_ptr ? e.alpha * __ldg(e.alpha_ptr) : e.alpha;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * alpha;
 
   const bool full = (col0 + 32 <= N);
   if (full) {
@@ -491,7 +493,8 @@ using namespace vlm;
 extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, long long ldb,
                              int b_mn_major, void* c, long long ldc, int c_is_fp32, int M, int N, int K,
                              const float* bias, const void* residual, long long ldr, int act, const void* aux_in,
-                             void* aux_out, long long ld_aux, float alpha, int accumulate, int batch,
+                             void* aux_out, long long ld_aux, float alpha, const float* alpha_ptr, int accumulate,
+                             int batch,
                              long long a_batch_stride, long long b_batch_stride, long long c_batch_stride,
                              long long aux_batch_stride, long long res_batch_stride, float p_drop,
                              unsigned long long seed, unsigned long long offset, int force_bn, int max_ctas,
@@ -539,6 +542,7 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
   e.aux_out = reinterpret_cast<bf16*>(aux_out);
   e.ld_aux = ld_aux;
   e.alpha = alpha;
+  e.alpha_ptr = alpha_ptr;
   e.accumulate = accumulate;
   e.p_drop = p_drop;
   e.seed = seed;

@@ -80,7 +80,8 @@ __global__ void vit_embed_bwd_kernel(const T* __restrict__ dx, float* __restrict
 
 // ---------------------------------------------------------------- column sums (bias gradients)
 // out[n] (+)= sum_m x[m,n]; block (32,8): each thread owns 2 adjacent columns, 8 row-lanes, grid.y row chunks.
-__global__ void colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, int M, int N, int rows_per_block) {
+__global__ void colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, int M, int N, int rows_per_block,
+                              const float* __restrict__ scale_ptr) {
   __shared__ float red[8][64];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int col = blockIdx.x * 64 + tx * 2;
@@ -100,8 +101,9 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, long long ld, float* _
   if (ty == 0) {
 #pragma unroll
     for (int k = 1; k < 8; ++k) { a0 += red[k][tx * 2]; a1 += red[k][tx * 2 + 1]; }
-    if (col < N) atomicAdd(out + col, a0);
-    if (col + 1 < N) atomicAdd(out + col + 1, a1);
+    const float sc = scale_ptr ? __ldg(scale_ptr) : 1.f;
+    if (col < N) atomicAdd(out + col, a0 * sc);
+    if (col + 1 < N) atomicAdd(out + col + 1, a1 * sc);
   }
 }
 
@@ -185,6 +187,28 @@ __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
   }
 }
 
+// ---------------------------------------------------------------- zero the rows of masked-out images
+// y[r,:] = mask[r / rows_per_mask] ? x[r,:] : 0      (vilmedic/blocks/vision/visual_encoder.py:170-171)
+__global__ void mask_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const uint8_t* __restrict__ mask, long long n8,
+                                 int vec_per_row, int rows_per_mask) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const uint4 u = reinterpret_cast<const uint4*>(x)[i];
+    reinterpret_cast<uint4*>(y)[i] = mask[r / rows_per_mask] ? u : make_uint4(0, 0, 0, 0);
+  }
+}
+
+// ---------------------------------------------------------------- small fp32 activations (BertPooler tanh, ConVIRT projection ReLU)
+// kind 0 = tanh, 1 = relu.  Backward takes the forward OUTPUT y.
+__global__ void act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int kind) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = kind == 0 ? tanhf(x[i]) : fmaxf(x[i], 0.f);
+}
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, long long n, int kind) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = kind == 0 ? dy[i] * (1.f - y[i] * y[i]) : (y[i] > 0.f ? dy[i] : 0.f);
+}
+
 // ---------------------------------------------------------------- deterministic sum of a small fp32 vector
 __global__ void sum_scale_kernel(const float* __restrict__ x, int n, float scale, float* __restrict__ out) {
   __shared__ float red[32];
@@ -245,14 +269,14 @@ extern "C" int vlm_vit_embed_bwd(const void* dx, int dx_is_fp32, float* dpos, fl
   return check_launch("vit_embed_bwd");
 }
 
-extern "C" int vlm_colsum_bf16(const void* x, long long ld, float* out, int M, int N, void* stream) {
-  VLM_REQUIRE(x && out && M > 0 && N > 0 && ld % 2 == 0 && N % 2 == 0, "vlm_colsum_bf16: bad args (M=%d N=%d)", M, N);
+extern "C" int vlm_colsum_bf16(const void* x, long long ld, float* out, int M, int N, const float* scale_ptr, void* stream) {
+  VLM_REQUIRE(x && out && M > 0 && N > 0 && ld % 2 == 0 && ld >= N + (N & 1), "vlm_colsum_bf16: bad args (M=%d N=%d ld=%lld)", M, N, ld);
   const int col_blocks = (N + 63) / 64;
   int row_blocks = (num_sms() * 4 + col_blocks - 1) / col_blocks;
   if (row_blocks > (M + 63) / 64) row_blocks = (M + 63) / 64;
   if (row_blocks < 1) row_blocks = 1;
   const int rows_per_block = (M + row_blocks - 1) / row_blocks;
-  colsum_kernel<<<dim3(col_blocks, row_blocks), dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, M, N, rows_per_block);
+  colsum_kernel<<<dim3(col_blocks, row_blocks), dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, M, N, rows_per_block, scale_ptr);
   return check_launch("colsum");
 }
 
@@ -282,6 +306,25 @@ extern "C" int vlm_dropout_bf16(const void* x, void* y, long long n, float p, un
   if (n == 0) return 0;
   dropout_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n / 8, p, 1.f / (1.f - p), seed, offset);
   return check_launch("dropout");
+}
+
+extern "C" int vlm_mask_rows_bf16(const void* x, void* y, const uint8_t* mask, int R, int D, int rows_per_mask, void* stream) {
+  VLM_REQUIRE(x && y && mask && R > 0 && D % 8 == 0 && rows_per_mask > 0, "vlm_mask_rows_bf16: bad args");
+  const long long n8 = (long long)R * (D / 8);
+  mask_rows_kernel<<<grid_for(n8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, mask, n8, D / 8, rows_per_mask);
+  return check_launch("mask_rows");
+}
+
+extern "C" int vlm_act_fwd_f32(const float* x, float* y, long long n, int kind, void* stream) {
+  VLM_REQUIRE(x && y && n > 0 && (kind == 0 || kind == 1), "vlm_act_fwd_f32: bad args");
+  act_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, kind);
+  return check_launch("act_fwd");
+}
+
+extern "C" int vlm_act_bwd_f32(const float* dy, const float* y, float* dx, long long n, int kind, void* stream) {
+  VLM_REQUIRE(dy && y && dx && n > 0 && (kind == 0 || kind == 1), "vlm_act_bwd_f32: bad args");
+  act_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n, kind);
+  return check_launch("act_bwd");
 }
 
 extern "C" int vlm_sum_scale_f32(const float* x, int n, float scale, float* out, void* stream) {

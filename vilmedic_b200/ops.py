@@ -23,7 +23,7 @@ def _is_bf16_cuda(t):
 
 
 def gemm(a, b, *, a_mn_major=False, b_mn_major=False, out=None, out_dtype=torch.bfloat16, bias=None, residual=None,
-         act=ACT_NONE, aux_in=None, aux_out=None, alpha=1.0, accumulate=False, p_drop=0.0, seed=0, offset=0,
+         act=ACT_NONE, aux_in=None, aux_out=None, alpha=1.0, alpha_t=None, accumulate=False, p_drop=0.0, seed=0, offset=0,
          force_bn=0, max_ctas=0):
     """C[M,N] = epi(alpha * A' B'^T).
 
@@ -75,7 +75,7 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, out=None, out_dtype=torch.
         ptr(out), c_ll(out.stride(-2)), c_int(int(c_fp32)),
         c_int(M), c_int(N), c_int(K),
         ptr(bias), ptr(residual), c_ll(ldr), c_int(act), ptr(aux_in), ptr(aux_out), c_ll(ld_aux),
-        c_float(alpha), c_int(int(accumulate)), c_int(batch),
+        c_float(alpha), ptr(alpha_t), c_int(int(accumulate)), c_int(batch),
         c_ll(a.stride(0) if batched else 0), c_ll(b.stride(0) if batched else 0),
         c_ll(out.stride(0) if batched else 0), c_ll(aux_bs), c_ll(res_bs),
         c_float(p_drop), c_u64(seed), c_u64(offset), c_int(force_bn), c_int(max_ctas), stream_ptr())
@@ -198,11 +198,11 @@ def vit_embed_bwd(dx, dpos, dcls, dbias):
                                  c_int(S), c_int(D), stream_ptr()), "vlm_vit_embed_bwd")
 
 
-def colsum(x, out):
-    """out[n] += sum_m x[m,n] (x bf16 [M,N] view with contiguous last dim)."""
+def colsum(x, out, scale_t=None):
+    """out[n] += scale * sum_m x[m,n] (x bf16 [M,N] view with contiguous last dim)."""
     _req(x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16, "colsum: bf16 [M,N]")
-    check(_L().vlm_colsum_bf16(ptr(x), c_ll(x.stride(0)), ptr(out), c_int(x.shape[0]), c_int(x.shape[1]), stream_ptr()),
-          "vlm_colsum_bf16")
+    check(_L().vlm_colsum_bf16(ptr(x), c_ll(x.stride(0)), ptr(out), c_int(x.shape[0]), c_int(x.shape[1]), ptr(scale_t),
+                               stream_ptr()), "vlm_colsum_bf16")
 
 
 def features_mask(feats):
@@ -238,6 +238,27 @@ def dropout(x, p, seed, offset, out=None):
     check(_L().vlm_dropout_bf16(ptr(x), ptr(out), c_ll(x.numel()), c_float(p), c_u64(seed), c_u64(offset), stream_ptr()),
           "vlm_dropout_bf16")
     return out
+
+
+def mask_rows(x, mask, rows_per_mask):
+    _req(x.dim() == 2 and x.is_contiguous() and x.dtype == torch.bfloat16, "mask_rows: contiguous bf16 [R,D]")
+    y = torch.empty_like(x)
+    check(_L().vlm_mask_rows_bf16(ptr(x), ptr(y), ptr(mask), c_int(x.shape[0]), c_int(x.shape[1]), c_int(rows_per_mask),
+                                  stream_ptr()), "vlm_mask_rows_bf16")
+    return y
+
+
+def act_fwd(x, kind):
+    _req(x.is_cuda and x.dtype == torch.float32 and x.is_contiguous(), "act_fwd: contiguous fp32")
+    y = torch.empty_like(x)
+    check(_L().vlm_act_fwd_f32(ptr(x), ptr(y), c_ll(x.numel()), c_int(kind), stream_ptr()), "vlm_act_fwd_f32")
+    return y
+
+
+def act_bwd(dy, y, kind):
+    dx = torch.empty_like(y)
+    check(_L().vlm_act_bwd_f32(ptr(dy), ptr(y), ptr(dx), c_ll(y.numel()), c_int(kind), stream_ptr()), "vlm_act_bwd_f32")
+    return dx
 
 
 def sum_scale(x, scale):
