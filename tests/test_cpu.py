@@ -1,0 +1,245 @@
+"""CPU-side checks (run with -m "not gpu"): C-ABI exports, oracle pinned to the golden vectors generated from the
+reference's own files, host logic (config handling, HF-compatible state_dict, parameter arena, gradient sync)."""
+import copy
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_header_symbol():
+    from vilmedic_b200 import _lib
+    names = _lib.header_symbols()
+    assert len(names) >= 20 and "vlm_gemm_bf16" in names and "vlm_attention_bwd" in names
+    lib = _lib.lib()
+    for n in names:
+        assert getattr(lib, n) is not None
+    assert lib.vlm_abi_version() == 1
+    assert isinstance(lib.vlm_last_error(), bytes)
+
+
+def test_no_cpu_fallback_without_library(monkeypatch):
+    from vilmedic_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libvlmb200.so")
+    with pytest.raises(_lib.VlmError):
+        _lib.lib()
+
+
+def test_product_never_imports_oracle():
+    import re
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "vilmedic_b200")):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+# ------------------------------------------------------------------------------------------------ oracle vs golden
+def _loss_inputs(n, d, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n, d, generator=g), torch.randn(n, d, generator=g)
+
+
+def test_oracle_losses_match_reference_goldens():
+    from oracle import losses as L
+    sys.path.insert(0, GOLD)
+    from make_golden import gloria_inputs
+    gold = torch.load(os.path.join(GOLD, "losses.pt"))
+    seen = set()
+    for c in gold["cases"]:
+        seen.add(c["kind"])
+        if c["kind"] == "convirt":
+            l, v = _loss_inputs(c["n"], c["d"], c["seed"])
+            l.requires_grad_(True); v.requires_grad_(True)
+            loss, ll, lv = L.convirt_loss(l, v, c["tau"], c["lambda_"])
+            gl, gv = torch.autograd.grad(loss, (l, v))
+            assert torch.allclose(loss, c["loss"], rtol=1e-6, atol=1e-6)
+            assert torch.allclose(ll, c["loss_l"], rtol=1e-5, atol=1e-5) and torch.allclose(lv, c["loss_v"], rtol=1e-5, atol=1e-5)
+            assert torch.allclose(gl[:2, :8], c["grad_l_probe"], rtol=1e-4, atol=1e-7)
+            assert torch.allclose(gv.norm(), c["grad_v_norm"], rtol=1e-4)
+        elif c["kind"] == "infonce":
+            l, v = _loss_inputs(c["n"], c["d"], c["seed"])
+            l = (l * c["scale"]).requires_grad_(True); v = (v * c["scale"]).requires_grad_(True)
+            loss, lt, li = L.infonce_loss(l, v, 0.1)
+            gl, gv = torch.autograd.grad(loss, (l, v))
+            assert torch.allclose(loss, c["loss"], rtol=1e-6, atol=1e-6)
+            assert torch.allclose(lt, c["loss_t"], rtol=1e-5, atol=1e-5) and torch.allclose(li, c["loss_i"], rtol=1e-5, atol=1e-5)
+            assert torch.allclose(gl[:2, :8], c["grad_l_probe"], rtol=1e-4, atol=1e-7)
+        elif c["kind"] == "gloria":
+            img, words, sents = gloria_inputs(c["b"], c["d"], c["hw"], c["lw"], c["seed"])
+            g = torch.Generator().manual_seed(c["seed"] + 100)
+            gi, gt = torch.randn(c["b"], c["d"], generator=g), torch.randn(c["b"], c["d"], generator=g)
+            l0, l1, att = L.gloria_local_loss(img, words, L.gloria_cap_lens(sents))
+            g0, g1 = L.gloria_global_loss(gi, gt)
+            assert torch.allclose(l0, c["local0"], rtol=1e-5) and torch.allclose(l1, c["local1"], rtol=1e-5)
+            assert torch.allclose(g0, c["global0"], rtol=1e-5) and torch.allclose(g1, c["global1"], rtol=1e-5)
+            assert torch.allclose(l0 + l1 + g0 + g1, c["loss"], rtol=1e-5)
+            assert torch.allclose(att[0][0, :2], c["attn0_probe"], rtol=1e-4, atol=1e-6)
+        elif c["kind"] == "lsce":
+            g = torch.Generator().manual_seed(c["seed"])
+            x = (torch.randn(c["n"], c["c"], generator=g) * 2).requires_grad_(True)
+            t = torch.randint(0, c["c"], (c["n"],), generator=g)
+            loss = L.label_smoothing_ce(x, t, c["smoothing"])
+            (gx,) = torch.autograd.grad(loss, (x,))
+            assert torch.allclose(loss, c["loss"], rtol=1e-6)
+            assert torch.allclose(gx[:2, :8], c["grad_probe"], rtol=1e-4, atol=1e-7)
+    assert seen == {"convirt", "infonce", "gloria", "lsce"}
+
+
+@pytest.mark.parametrize("name", ["small", "vitb_dec12"])
+def test_oracle_towers_match_frozen_hf_outputs(name):
+    """The HF composition under the installed transformers still produces the frozen vectors (guards HF drift)."""
+    from oracle.rrg import OracleRRG
+    from vilmedic_b200 import synth
+    gold = torch.load(os.path.join(GOLD, "towers.pt"))
+    c = [x for x in gold["cases"] if x["name"] == name][0]
+    torch.manual_seed(0)
+    dec = synth.bert_base_decoder(vocab=c["vocab"], layers=c["dec_layers"], dropout=0.0)
+    cnn = dict(backbone="vit", permute="no_permute", **dict(synth.vit_b16(), num_hidden_layers=c["vit_layers"]))
+    m = OracleRRG(dec, cnn).eval()
+    batch = synth.rrg_batch(c["B"], c["T"], c["vocab"])
+    feats, _ = m.enc.encode(batch["images"])
+    o = m(batch["input_ids"], batch["attention_mask"], batch["images"])
+    assert torch.allclose(o["loss"], c["loss"], rtol=1e-5)
+    assert torch.allclose(feats[:, :3, :8], c["feats_probe"], rtol=1e-3, atol=1e-4)
+    assert torch.allclose(o["logits"][:, :3, :8], c["logits_probe"], rtol=1e-3, atol=1e-4)
+    if name == "small":
+        o["loss"].backward()
+        gn = {n: p.grad.norm().item() for n, p in m.named_parameters()}
+        for k, v in c["grad_norms"].items():
+            assert abs(gn[k] - v) <= 1e-3 * max(abs(v), 1e-6) + 1e-7, (k, gn[k], v)
+
+
+# ------------------------------------------------------------------------------------------------ host logic
+def _small_cfgs():
+    from vilmedic_b200 import synth
+    dec = synth.bert_base_decoder(vocab=300, layers=2, dropout=0.0)
+    cnn = dict(proto="VisualEncoder", backbone="vit", permute="no_permute",
+               **dict(synth.vit_b16(), num_hidden_layers=2, hidden_size=128, num_attention_heads=2, intermediate_size=256))
+    return dec, cnn
+
+
+def test_state_dict_is_hf_compatible():
+    from oracle.rrg import OracleRRG
+    from vilmedic_b200.models import RRG
+    dec, cnn = _small_cfgs()
+    ref = OracleRRG(copy.deepcopy(dec), copy.deepcopy(cnn))
+    mine = RRG(copy.deepcopy(dec), copy.deepcopy(cnn))
+    a, b = ref.state_dict(), mine.state_dict()
+    assert set(a) == set(b)
+    for k in a:
+        assert tuple(a[k].shape) == tuple(b[k].shape), k
+    mine.load_state_dict(a, strict=True)
+    # tied LM head as in BertGenerationDecoder
+    d = mine.dec.decoder
+    assert d.lm_head.decoder.weight is d.bert.embeddings.word_embeddings.weight
+    assert d.lm_head.decoder.bias is d.lm_head.bias
+
+
+def test_arena_views_groups_and_spans():
+    from vilmedic_b200.arena import get_arena
+    from vilmedic_b200.models import RRG
+    dec, cnn = _small_cfgs()
+    m = RRG(dec, cnn)
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    a = get_arena(m)
+    assert a.valid() and get_arena(m) is a
+    for n, p in m.named_parameters():
+        assert torch.equal(p.detach(), before[n])
+        assert p.data_ptr() == a.flat.data_ptr() + 4 * a.offsets[id(p)]
+        assert a.offsets[id(p)] * 4 % 16 == 0
+        assert p.grad is not None and p.grad.data_ptr() == a.flat_grad.data_ptr() + 4 * a.offsets[id(p)]
+    s = m.dec.decoder.bert.encoder.layer[1].attention.self
+    fused = a.fp32(s.query.weight, s.key.weight, s.value.weight, shape=(3 * 768, 768))
+    assert torch.equal(fused[768:1536], s.key.weight.detach())
+    c = m.dec.decoder.bert.encoder.layer[0].crossattention.self
+    assert a.fp32(c.key.bias, c.value.bias, shape=(1536,)).shape == (1536,)
+    lo_d, hi_d = a.child_spans["dec"]
+    lo_e, hi_e = a.child_spans["enc"]
+    assert lo_d == 0 and hi_d == lo_e and hi_e == a.numel
+    for p in m.dec.parameters():
+        assert lo_d <= a.offsets[id(p)] < hi_d
+    for p in m.enc.parameters():
+        assert lo_e <= a.offsets[id(p)] < hi_e
+    # dropping grads (optimizer.zero_grad(set_to_none=True)) and rebinding
+    for p in m.parameters():
+        p.grad = None
+    assert a.bind_grads()
+    assert all(p.grad is not None for p in m.parameters())
+    # load_state_dict writes through the views
+    sd = {k: torch.randn_like(v) for k, v in m.state_dict().items()}
+    sd["dec.decoder.lm_head.decoder.weight"] = sd["dec.decoder.bert.embeddings.word_embeddings.weight"]
+    sd["dec.decoder.lm_head.decoder.bias"] = sd["dec.decoder.lm_head.bias"]
+    m.load_state_dict(sd)
+    assert a.valid()
+    assert torch.equal(a.fp32(s.query.weight), sd["dec.decoder.bert.encoder.layer.1.attention.self.query.weight"])
+
+
+def test_config_errors_and_defaults():
+    from vilmedic_b200.blocks.huggingface.decoder.decoder_model import DecoderModel
+    from vilmedic_b200.blocks.vision import VisualEncoder
+    from vilmedic_b200.cfgutil import AttrDict, to_attrdict
+    from vilmedic_b200.nn import bert_config
+    c = bert_config()
+    assert (c.hidden_size, c.num_hidden_layers, c.num_attention_heads, c.intermediate_size, c.vocab_size) == (1024, 24, 16, 4096, 50358)
+    with pytest.raises(NotImplementedError):
+        bert_config(hidden_size=768, num_attention_heads=8, hidden_act="relu")
+    with pytest.raises(NotImplementedError):
+        bert_config(hidden_size=320, num_attention_heads=8)      # head dim 40 has no kernel
+    with pytest.raises(NotImplementedError):
+        DecoderModel(AttrDict(proto="bert-base-uncased"))
+    with pytest.raises(NotImplementedError):
+        VisualEncoder(backbone="deit", permute="no_permute")
+    with pytest.raises(AssertionError):
+        VisualEncoder(backbone="vit", permute="bogus", num_hidden_layers=1)
+    d = to_attrdict({"a": {"b": 1}, "proto": None})
+    assert d.a.b == 1 and d.pop("proto") is None and "proto" not in d
+
+
+# ------------------------------------------------------------------------------------------------ N>1 path (gloo, 2 ranks)
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vilmedic_b200.arena import get_arena
+    from vilmedic_b200.ddp import GradSync
+    from vilmedic_b200.models import RRG
+    torch.manual_seed(0)
+    dec, cnn = _small_cfgs()
+    m = RRG(dec, cnn)
+    a = get_arena(m)
+    a.flat_grad.copy_(torch.arange(a.numel, dtype=torch.float32) * 1e-3 * (rank + 1))
+    sync = GradSync(a)
+    sync.launch_span("dec")           # as the hook at the encoder boundary would
+    scale = sync.finish()             # encoder span + tail, wait for all
+    want = torch.arange(a.numel, dtype=torch.float32) * 1e-3 * sum(r + 1 for r in range(world))
+    ok = torch.allclose(a.flat_grad, want) and abs(scale - 1.0 / world) < 1e-12
+    # p.grad views see the reduced values
+    p = m.enc.model.layernorm.weight
+    ok = ok and torch.allclose(p.grad, want[a.offsets[id(p)]:a.offsets[id(p)] + p.numel()])
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_grad_sync_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

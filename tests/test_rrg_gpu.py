@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _build(vit_layers, dec_layers, vocab, dropout=0.0):
-    from oracle import synth
+    from vilmedic_b200 import synth
     from oracle.rrg import OracleRRG
     from vilmedic_b200.models import RRG
     torch.manual_seed(0)
@@ -36,7 +36,7 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("vit_layers,dec_layers,vocab,B,T", [(2, 2, 1000, 2, 16), (12, 12, 30522, 2, 32)])
 def test_rrg_forward_backward_parity(cuda_dev, vit_layers, dec_layers, vocab, B, T):
-    from oracle import synth
+    from vilmedic_b200 import synth
     ref, mine = _build(vit_layers, dec_layers, vocab)
     batch = synth.rrg_batch(B, T, vocab)
     # ---- oracle (CPU fp32)
@@ -70,16 +70,18 @@ def test_rrg_forward_backward_parity(cuda_dev, vit_layers, dec_layers, vocab, B,
         g_ref = ref_grads[n]
         r = _rel(p.grad.cpu(), g_ref)
         r_ac = _rel(ac_grads[n], g_ref)
-        if r > worst[0]:
+        if r > worst[0] and g_ref.norm().item() > 1e-4:
             worst = (r, n)
-        assert r <= 8e-2 or r <= 3 * r_ac + 1e-2, "grad %s: rel err %.4f (torch bf16 autocast: %.4f)" % (n, r, r_ac)
+        # absolute floor: some gradients are exactly zero in exact arithmetic (key biases: softmax is shift invariant)
+        small = (p.grad.cpu().float() - g_ref).norm().item() <= 1e-5 * g_ref.numel() ** 0.5
+        assert small or r <= 8e-2 or r <= 3 * r_ac + 1e-2, "grad %s: rel err %.4f (torch bf16 autocast: %.4f)" % (n, r, r_ac)
     print("loss err %.2e (autocast %.2e); logits err %.2e (autocast %.2e); worst grad rel err %.3f at %s" % (
         e_loss, e_loss_ac, e_lg, e_lg_ac, worst[0], worst[1]))
 
 
 def test_rrg_eval_and_padding_semantics(cuda_dev):
     """eval mode returns logits; pad tokens count as targets and the last position is ignored (decoder_model.py:46)."""
-    from oracle import synth
+    from vilmedic_b200 import synth
     ref, mine = _build(1, 2, 500)
     batch = synth.rrg_batch(3, 12, 500, seed=7)
     out_ref = ref(batch["input_ids"], batch["attention_mask"], batch["images"])
@@ -97,7 +99,7 @@ def test_rrg_eval_and_padding_semantics(cuda_dev):
 
 def test_rrg_training_steps_track_oracle(cuda_dev):
     """5 AdamW steps: loss trajectory of the B200 path (fused optimizer on the flat arena) follows the fp32 oracle."""
-    from oracle import synth
+    from vilmedic_b200 import synth
     from vilmedic_b200.optim import FusedAdamW
     ref, mine = _build(2, 2, 1000)
     ref.train()

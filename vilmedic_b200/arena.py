@@ -18,25 +18,36 @@ _ALIGN = 32  # fp32 elements = 128 bytes
 class ParamArena:
     def __init__(self, root: nn.Module):
         self.root = root
-        params = []
-        seen = set()
-        groups = []
-        for m in root.modules():
-            fn = getattr(m, "_fused_param_groups", None)
-            if fn is not None:
-                for g in fn():
-                    groups.append(list(g))
-        grouped = set()
+        # allocation order: one contiguous span per top-level child (decoder / encoder / heads), inside it the fused
+        # groups first, then the remaining parameters -> the gradient all-reduce can be issued span by span while the
+        # backward of the next span is still running.
         order = []
-        for g in groups:
-            if any(id(p) in grouped for p in g):
-                continue
-            for p in g:
-                grouped.add(id(p))
-            order.append(g)
-        for p in root.parameters():
-            if id(p) not in grouped and id(p) not in seen:
-                seen.add(id(p))
+        placed = set()
+        self.child_spans = {}
+        children = list(root.named_children()) or [("", root)]
+        blocks = [(name, child) for name, child in children]
+        direct = [p for p in root.parameters(recurse=False)]
+        for name, child in blocks:
+            start = len(order)
+            for m in child.modules():
+                fn = getattr(m, "_fused_param_groups", None)
+                if fn is None:
+                    continue
+                for g in fn():
+                    g = list(g)
+                    if any(id(p) in placed for p in g):
+                        continue
+                    for p in g:
+                        placed.add(id(p))
+                    order.append(g)
+            for p in child.parameters():
+                if id(p) not in placed:
+                    placed.add(id(p))
+                    order.append([p])
+            self.child_spans[name] = (start, len(order))
+        for p in direct:
+            if id(p) not in placed:
+                placed.add(id(p))
                 order.append([p])
         dev = next(root.parameters()).device
         self.device = dev
@@ -49,6 +60,14 @@ class ParamArena:
                 offsets[id(p)] = total
                 total += p.numel()
         total = (total + _ALIGN - 1) // _ALIGN * _ALIGN
+        # element spans [lo, hi) of each top-level child in the flat buffers
+        spans = {}
+        for name, (g0, g1) in self.child_spans.items():
+            if g1 > g0:
+                lo = offsets[id(order[g0][0])]
+                hi = offsets[id(order[g1][0])] if g1 < len(order) else total
+                spans[name] = (lo, hi)
+        self.child_spans = spans
         self.numel = total
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)

@@ -12,6 +12,19 @@ from ._lib import c_float, c_int, c_ll, c_u64, c_void_p, check, ptr, stream_ptr
 
 ACT_NONE, ACT_GELU, ACT_GELU_GRAD = 0, 1, 2
 
+# Number of OUR kernels launched through this module (bench.py reports it as `gpu_launches`).
+LAUNCHES = [0]
+_KERNELS_PER_CALL = {"vlm_attention_bwd": 2, "vlm_adamw_step": 2}
+# Optional per-call CUDA-event timing of the GEMM launches (bench.py roofline pass): list of (M, N, K, batch, start, end)
+GEMM_TIMING = None
+
+_orig_check = check
+
+
+def check(rc, what):  # noqa: F811
+    _orig_check(rc, what)
+    LAUNCHES[0] += _KERNELS_PER_CALL.get(what, 1)
+
 
 def _req(cond, msg):
     if not cond:
@@ -69,6 +82,10 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, out=None, out_dtype=torch.
             ld_aux = t.stride(-2)
             if batched:
                 aux_bs = t.stride(0)
+    if GEMM_TIMING is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = _lib.lib().vlm_gemm_bf16(
         ptr(a), c_ll(a.stride(-2)), c_int(int(a_mn_major)),
         ptr(b), c_ll(b.stride(-2)), c_int(int(b_mn_major)),
@@ -80,6 +97,9 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, out=None, out_dtype=torch.
         c_ll(out.stride(0) if batched else 0), c_ll(aux_bs), c_ll(res_bs),
         c_float(p_drop), c_u64(seed), c_u64(offset), c_int(force_bn), c_int(max_ctas), stream_ptr())
     check(rc, "vlm_gemm_bf16")
+    if GEMM_TIMING is not None:
+        ev1.record()
+        GEMM_TIMING.append((M, N, K, batch, ev0, ev1))
     return out
 
 

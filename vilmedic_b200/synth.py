@@ -1,4 +1,4 @@
-"""Seeded synthetic inputs of the reference's batch shape.  TEST INFRASTRUCTURE / bench inputs."""
+"""Seeded synthetic inputs of the reference batch shape and the BASELINE model shapes; used by bench.py and the tests."""
 import torch
 
 BOS, PAD, EOS = 0, 1, 2   # vilmedic/datasets/base/utils.py:24-25 order [CLS],[PAD],[SEP],[UNK],[MASK]; config/RRG/baseline-mimic.yml:15-16,28
