@@ -123,6 +123,22 @@ int vlm_act_bwd_f32(const float* dy, const float* y, float* dx, long long n, int
 /* out[0] = scale * sum(x[0..n))  (deterministic single-block reduction; mean of per-row losses). */
 int vlm_sum_scale_f32(const float* x, int n, float scale, float* out, void* stream);
 
+/* ---- contrastive losses (ConVIRT / InfoNCE / GLoRIA-global) ------------------------------------------------------ */
+/* x fp32 [N,D] (optionally L2-normalised per row, clamp eps — ConVIRTLoss.py:25-31) split into bf16 hi/lo and packed for the
+ * 3-term tensor-core product: xa [N,3D] = [hi|hi|lo], xb [N,3D] = [hi|lo|hi], xh [N,D] = hi; any output may be null. */
+int vlm_rownorm_split(const float* x, void* xa, void* xb, void* xh, float* inv_norm, int N, int D, int normalize, float eps,
+                      void* stream);
+/* backward of the normalisation: dx = inv_norm * (dxh - xhat (xhat . dxh)). */
+int vlm_rownorm_bwd(const float* x, const float* inv_norm, const float* dxh, float* dx, int N, int D, int normalize,
+                    void* stream);
+/* S fp32 [N,N]: lse_row[i] = LSE_j(scale*S_ij), lse_col[i] = LSE_j(scale*S_ji), loss_row/col = lse - scale*S_ii.
+ * ConVIRTLoss.py:13-21 (scale 1/tau), InfoNCELoss.py:15-16 (scale 1), GLoRIALoss.py:72-75 (scale temp3). */
+int vlm_sym_lse(const float* S, int N, long long ld, float scale, float* lse_row, float* lse_col, float* loss_row,
+                float* loss_col, void* stream);
+/* dS (bf16 [N,ldd]) = g * scale * (w_row (softmax_row - I) + w_col (softmax_col - I)); g_ptr = upstream scalar or null. */
+int vlm_sym_lse_bwd(const float* S, int N, long long ld, float scale, const float* lse_row, const float* lse_col, float w_row,
+                    float w_col, const float* g_ptr, void* dS, long long ldd, void* stream);
+
 /* ---- optimizer (vilmedic/executors/trainor.py:119-124) ------------------------------------------ */
 /* out[0] += sum(g^2)  (caller zeroes). */
 int vlm_sumsq_f32(const float* g, long long n, float* out, void* stream);

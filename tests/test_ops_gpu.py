@@ -267,3 +267,81 @@ def test_adamw(cuda_dev):
     assert step.item() == 5
     assert (p - ref_p.detach()).abs().max().item() < 1e-5
     assert torch.equal(pb, p.to(torch.bfloat16))
+
+
+def test_gemm_from_fresh_thread(cuda_dev):
+    """The tensor-map encode is a driver call: it must work from a host thread that never touched CUDA (autograd workers)."""
+    import threading
+    from vilmedic_b200 import ops
+    a, b = _bf((128, 64), cuda_dev, 1), _bf((128, 64), cuda_dev, 2)
+    res = {}
+
+    def work():
+        try:
+            with torch.cuda.device(cuda_dev):
+                res["out"] = ops.gemm(a, b, out_dtype=torch.float32)
+        except Exception as e:  # pragma: no cover
+            res["err"] = e
+
+    t = threading.Thread(target=work)
+    t.start()
+    t.join()
+    assert "err" not in res, res.get("err")
+    torch.cuda.synchronize()
+    assert (res["out"] - a.float() @ b.float().t()).abs().max().item() < 1e-2
+
+
+def test_contrastive_losses(cuda_dev):
+    """ConVIRT / InfoNCE / GLoRIA-global through the kernels vs the oracle restatements (pinned to the reference's files)."""
+    from oracle import losses as L
+    from vilmedic_b200.blocks.losses import ConVIRTLoss, GLoRIAGlobalLoss, InfoNCELoss
+    for n, d in [(4, 32), (64, 768), (512, 768)]:
+        g = torch.Generator().manual_seed(n)
+        l = torch.randn(n, d, generator=g)
+        v = torch.randn(n, d, generator=g)
+        # ConVIRT
+        lr, vr = l.clone().requires_grad_(True), v.clone().requires_grad_(True)
+        ref, ref_l, ref_v = L.convirt_loss(lr, vr, 0.1, 0.75)
+        ref.backward()
+        lc, vc = l.cuda().requires_grad_(True), v.cuda().requires_grad_(True)
+        loss, ll, lv = ConVIRTLoss(tau=0.1, lambda_=0.75)(lc, vc)
+        loss.backward()
+        torch.cuda.synchronize()
+        assert abs(loss.item() - ref.item()) <= 2e-4 * abs(ref.item()) + 1e-5, (n, loss.item(), ref.item())
+        assert (ll.cpu() - ref_l).abs().max().item() <= 2e-3 and (lv.cpu() - ref_v).abs().max().item() <= 2e-3
+        for got, want in ((lc.grad, lr.grad), (vc.grad, vr.grad)):
+            assert ((got.cpu() - want).norm() / want.norm()).item() < 2e-2
+        # InfoNCE (raw dot products; tau unused as in the reference)
+        ls, vs = l * 0.05, v * 0.05
+        lr, vr = ls.clone().requires_grad_(True), vs.clone().requires_grad_(True)
+        ref, ref_t, ref_i = L.infonce_loss(lr, vr)
+        ref.backward()
+        lc, vc = ls.cuda().requires_grad_(True), vs.cuda().requires_grad_(True)
+        loss, lt, li = InfoNCELoss(tau=0.1)(lc, vc)
+        loss.backward()
+        torch.cuda.synchronize()
+        assert abs(loss.item() - ref.item()) <= 2e-4 * abs(ref.item()) + 1e-5
+        assert (lt.cpu() - ref_t).abs().max().item() <= 2e-3 and (li.cpu() - ref_i).abs().max().item() <= 2e-3
+        for got, want in ((lc.grad, lr.grad), (vc.grad, vr.grad)):
+            assert ((got.cpu() - want).norm() / want.norm()).item() < 2e-2
+        # GLoRIA global
+        r0, r1 = L.gloria_global_loss(l, v, temp3=10.0)
+        g0, g1 = GLoRIAGlobalLoss(temp3=10.0)(l.cuda(), v.cuda())
+        assert abs(g0.item() - r0.item()) <= 2e-4 * abs(r0.item()) + 1e-5 and abs(g1.item() - r1.item()) <= 2e-4 * abs(r1.item()) + 1e-5
+
+
+def test_label_smoothing_module(cuda_dev):
+    from oracle import losses as L
+    from vilmedic_b200.blocks.losses import LabelSmoothingCrossEntropy
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(256, 330, generator=g) * 2
+    t = torch.randint(0, 330, (256,), generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref = L.label_smoothing_ce(xr, t, 0.1)
+    ref.backward()
+    xc = x.cuda().requires_grad_(True)
+    loss = LabelSmoothingCrossEntropy(smoothing=0.1)(xc, t)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item()) + 1e-6
+    assert (xc.grad.cpu() - xr.grad).abs().max().item() < 1e-6

@@ -514,6 +514,18 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
   VLM_REQUIRE(!bias || ((uintptr_t)bias % 16 == 0), "vlm_gemm_bf16: bias must be 16B aligned");
   VLM_REQUIRE(batch == 1 || (a_batch_stride % 8 == 0 && b_batch_stride % 8 == 0), "vlm_gemm_bf16: batch strides % 8");
 
+  // cuTensorMapEncodeTiled is a driver call: make sure this host thread (e.g. an autograd worker) has the primary
+  // context bound before the first one, otherwise it fails with CUDA_ERROR_INVALID_CONTEXT.
+  {
+    static thread_local int bound_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (bound_dev != dev) {
+      cudaSetDevice(dev);
+      cudaFree(0);
+      bound_dev = dev;
+    }
+  }
   const int bn = pick_bn(M, N, batch, force_bn);
   CUtensorMap ta, tb;
   // a zero batch stride broadcasts that operand: encode a single-batch map and pin the batch coordinate to 0

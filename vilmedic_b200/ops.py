@@ -298,3 +298,40 @@ def adamw_step(p, g, m, v, p_bf16, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_d
                               c_float(betas[1]), c_float(eps), c_float(weight_decay), ptr(step_t), c_int(int(increment_step)),
                               ptr(lr_scale_t), c_float(grad_scale), ptr(gnorm_sq_t), c_float(max_norm),
                               c_int(int(zero_grad)), stream_ptr()), "vlm_adamw_step")
+
+
+def rownorm_split(x, normalize, eps=1e-8, want_a=True, want_b=True, want_h=True):
+    _req(x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2, "rownorm_split: contiguous fp32 [N,D]")
+    N, D = x.shape
+    mk = lambda w: torch.empty((N, w), device=x.device, dtype=torch.bfloat16)
+    xa = mk(3 * D) if want_a else None
+    xb = mk(3 * D) if want_b else None
+    xh = mk(D) if want_h else None
+    inv = torch.empty(N, device=x.device, dtype=torch.float32)
+    check(_L().vlm_rownorm_split(ptr(x), ptr(xa), ptr(xb), ptr(xh), ptr(inv), c_int(N), c_int(D), c_int(int(normalize)),
+                                 c_float(eps), stream_ptr()), "vlm_rownorm_split")
+    return xa, xb, xh, inv
+
+
+def rownorm_bwd(x, inv, dxh, normalize):
+    dx = torch.empty_like(x)
+    check(_L().vlm_rownorm_bwd(ptr(x), ptr(inv), ptr(dxh), ptr(dx), c_int(x.shape[0]), c_int(x.shape[1]), c_int(int(normalize)),
+                               stream_ptr()), "vlm_rownorm_bwd")
+    return dx
+
+
+def sym_lse(S, scale):
+    N = S.shape[0]
+    outs = [torch.empty(N, device=S.device, dtype=torch.float32) for _ in range(4)]
+    check(_L().vlm_sym_lse(ptr(S), c_int(N), c_ll(S.stride(0)), c_float(scale), ptr(outs[0]), ptr(outs[1]), ptr(outs[2]),
+                           ptr(outs[3]), stream_ptr()), "vlm_sym_lse")
+    return outs  # lse_row, lse_col, loss_row, loss_col
+
+
+def sym_lse_bwd(S, scale, lse_row, lse_col, w_row, w_col, g_t):
+    N = S.shape[0]
+    ldd = (N + 7) // 8 * 8
+    dS = torch.empty((N, ldd), device=S.device, dtype=torch.bfloat16)
+    check(_L().vlm_sym_lse_bwd(ptr(S), c_int(N), c_ll(S.stride(0)), c_float(scale), ptr(lse_row), ptr(lse_col), c_float(w_row),
+                               c_float(w_col), ptr(g_t), ptr(dS), c_ll(ldd), stream_ptr()), "vlm_sym_lse_bwd")
+    return dS[:, :N]
