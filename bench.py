@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -194,6 +195,15 @@ def run_ours(args):
             return loss.item()
         return loss
 
+    graphed = None
+
+    def run_step(batch, read_loss):
+        if graphed is None:
+            return train_step(batch, read_loss)
+        # resident leg: static inputs already hold the batch; e2e leg: pinned host tensors are copied in (H2D) every step
+        loss = graphed(None if batch is devb else batch)
+        return loss.item() if read_loss else loss
+
     def timed(batch_fn, steps, read_loss):
         if world > 1:
             dist.barrier()
@@ -202,7 +212,7 @@ def run_ours(args):
         e0.record()
         last = None
         for _ in range(steps):
-            last = train_step(batch_fn(), read_loss)
+            last = run_step(batch_fn(), read_loss)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -214,19 +224,35 @@ def run_ours(args):
         return ms, last
 
     def host_batch():
+        if graphed is not None:
+            return host                    # GraphedTrainStep copies pinned host tensors into its static inputs
         return {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
 
     # warm-up (also builds the arena / first-use attribute setup)
     for _ in range(max(args.warmup, 3)):
+        l0 = ops.LAUNCHES[0]
         train_step(devb, False)
+        launches = ops.LAUNCHES[0] - l0      # kernels of ours per step (the graph replays exactly these)
     torch.cuda.synchronize()
+    graph_note = "eager launches"
+    if not args.no_graph:
+        try:
+            from vilmedic_b200.graph import GraphedTrainStep
+            graphed = GraphedTrainStep(model, opt, devb, warmup=1,
+                                       step_fn=lambda b: (ops.rng_advance(ops.RNG_COUNTER[0], 4096), train_step(b, False))[1])
+            graph_note = "whole step replayed as one CUDA graph"
+            for _ in range(2):
+                graphed(devb)
+            torch.cuda.synchronize()
+        except Exception as e:  # pragma: no cover - reported, never silent
+            graphed = None
+            graph_note = "eager launches (graph capture failed: %s)" % (str(e).splitlines()[0][:160],)
+            torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = ops.LAUNCHES[0]
     ms, last = timed(lambda: devb, args.steps, False)
-    launches = (ops.LAUNCHES[0] - l0) // max(args.steps, 1)
     ms_e2e, last_loss = timed(host_batch, args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -235,7 +261,7 @@ def run_ours(args):
 
     roof = None
     if rank == 0 and not args.no_roofline:
-        roof = gemm_roofline(train_step, devb, ops)
+        roof = gemm_roofline(train_step, devb, ops)   # eager, instrumented pass
     if world > 1:
         dist.barrier()
 
@@ -256,6 +282,7 @@ def run_ours(args):
                                    "V=%d, B=%d/GPU, 224x224 images, T=%d, decoder dropout %.2f (BASELINE configs[1])" % (VOCAB, B, T, args.dropout),
                        "global_batch": world * B, "seq_len": T, "parallelism": "dp%d" % world,
                        "l2": "per-step working set (activations ~4 GB + 1.3 GB weights/grads) >> 126 MB L2; no explicit flush",
+                       "launch": graph_note,
                        "loss_last": float(last_loss) if last_loss is not None else None},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
@@ -280,6 +307,11 @@ def peaks():
 
 def gemm_roofline(train_step, batch, ops):
     """One instrumented training step: CUDA events around every tcgen05 GEMM launch (on the launching stream)."""
+    # Eager launches are host-bound (~1.1 k ctypes launches per step), so an empty stream would make the events time the
+    # host, not the kernels: park the GPU behind a spin kernel first, then every launch of the step is queued back to back
+    # and the event pairs bracket pure device execution.
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(0.25 * 1.9e9))
     ops.GEMM_TIMING = []
     train_step(batch, False)
     torch.cuda.synchronize()

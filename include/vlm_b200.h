@@ -46,7 +46,8 @@ int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, l
                   long long ldr, int act, const void* aux_in, void* aux_out, long long ld_aux, float alpha,
                   const float* alpha_ptr, int accumulate, int batch, long long a_batch_stride, long long b_batch_stride,
                   long long c_batch_stride, long long aux_batch_stride, long long res_batch_stride, float p_drop,
-                  unsigned long long seed, unsigned long long offset, int force_bn, int max_ctas, void* stream);
+                  unsigned long long seed, unsigned long long offset, const unsigned long long* rng_offset_ptr, int force_bn,
+                  int max_ctas, void* stream);
 
 /* ---- LayerNorm -------------------------------------------------------------------------------------------------- */
 /* y = LN(x) * gamma + beta, biased variance, one warp per row; x bf16 or fp32, y bf16; mean/rstd (fp32 [M]) optional.
@@ -70,7 +71,8 @@ int vlm_layernorm_bwd(const void* dy, const void* x, int x_is_fp32, const float*
 int vlm_attention_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                       const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse,
                       const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH, int causal, float scale, float p_drop,
-                      unsigned long long seed, unsigned long long offset, void* stream);
+                      unsigned long long seed, unsigned long long offset, const unsigned long long* rng_offset_ptr,
+                      void* stream);
 /* Gradients dq/dk/dv (bf16, same addressing scheme with their own strides); delta: fp32 [B,H,Tq] scratch. */
 int vlm_attention_bwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                       const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
@@ -78,7 +80,7 @@ int vlm_attention_bwd(const void* q, long long q_bs, long long q_rs, const void*
                       long long dq_bs, long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv,
                       long long dv_bs, long long dv_rs, const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH,
                       int causal, float scale, float p_drop, unsigned long long seed, unsigned long long offset,
-                      void* stream);
+                      const unsigned long long* rng_offset_ptr, void* stream);
 
 /* ---- softmax cross-entropy (LM head loss, label-smoothing CE) ---------------------------------------------------- */
 /* One pass per row: loss_rows[r] (0 for ignored rows), lse_rows[r] (optional), and dlogits = (softmax - target) *
@@ -113,7 +115,10 @@ int vlm_embed_bwd(const long long* ids, const void* dz, float* dword, float* dpo
                   int pos_offset, void* stream);
 /* y = x * keep / (1-p), keep ~ Philox(seed, offset, element); same call on grads is the backward.  n % 8 == 0. */
 int vlm_dropout_bf16(const void* x, void* y, long long n, float p, unsigned long long seed, unsigned long long offset,
-                     void* stream);
+                     const unsigned long long* rng_offset_ptr, void* stream);
+/* *counter += delta on the device.  Every dropout-capable entry point takes `rng_offset_ptr`: a device uint64 added to
+ * `offset`, so a CUDA-graph replay of a training step draws fresh masks (advance the counter once per step). */
+int vlm_rng_advance(unsigned long long* counter, unsigned long long delta, void* stream);
 /* y[r,:] = mask[r / rows_per_mask] ? x[r,:] : 0 — multi-image masking, vilmedic/blocks/vision/visual_encoder.py:170-171. */
 int vlm_mask_rows_bf16(const void* x, void* y, const uint8_t* mask, int R, int D, int rows_per_mask, void* stream);
 /* fp32 activations: kind 0 = tanh (BertPooler, vilmedic/blocks/huggingface/encoder/encoder_model.py:58-60), 1 = ReLU

@@ -20,7 +20,7 @@ class EncoderModel(nn.Module):
         add_pool = bool(d.pop("add_pooling_layer", False))
         d["is_decoder"] = False
         d["add_cross_attention"] = False
-        self.encoder = BertTower(bert_config(**d), with_lm_head=False)
+        self.encoder = BertTower(bert_config(**d), with_lm_head=False, flat=True)
         self.config = self.encoder.config
         self.pooler = None
         if add_pool:

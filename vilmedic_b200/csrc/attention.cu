@@ -26,6 +26,7 @@ struct AttnParams {
   float scale;
   float p_drop;
   unsigned long long seed, offset;
+  const unsigned long long* offset_ptr;  // optional device-side addend to `offset`
   // backward only
   const bf16* d_o; long long do_bs, do_rs;
   bf16* dq; bf16* dk; bf16* dv;
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnParams p) {
   const float sl2 = p.scale * 1.4426950408889634f;
   const int qrow[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
   const Philox rng(p.seed);
+  const unsigned long long off_eff = p.offset + ((p.p_drop > 0.f && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
   const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
 
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnParams p) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           const int kcol = k0 + nt * 8 + 2 * t;
-          const uint4 rnd = drop_rand4(rng, p.offset, bh, qrow[r], kcol >> 2, p.Tq, (p.Sk + 3) >> 2);
+          const uint4 rnd = drop_rand4(rng, off_eff, bh, qrow[r], kcol >> 2, p.Tq, (p.Sk + 3) >> 2);
           const uint32_t r0 = (kcol & 2) ? rnd.z : rnd.x, r1 = (kcol & 2) ? rnd.w : rnd.y;
           pe[2 * r] = r0 >= thr ? pe[2 * r] * inv_keep : 0.f;
           pe[2 * r + 1] = r1 >= thr ? pe[2 * r + 1] * inv_keep : 0.f;
@@ -289,6 +291,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnParams p) {
   for (int i = 0; i < NT; ++i) dq_acc[i][0] = dq_acc[i][1] = dq_acc[i][2] = dq_acc[i][3] = 0.f;
   const float sl2 = p.scale * 1.4426950408889634f;
   const Philox rng(p.seed);
+  const unsigned long long off_eff = p.offset + ((p.p_drop > 0.f && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
   const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
 
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnParams p) {
         float dpe = dp[nt][e];
         if (p.p_drop > 0.f) {
           const int kcol = k0 + nt * 8 + 2 * t;
-          const uint4 rnd = drop_rand4(rng, p.offset, bh, qrow[r], kcol >> 2, p.Tq, (p.Sk + 3) >> 2);
+          const uint4 rnd = drop_rand4(rng, off_eff, bh, qrow[r], kcol >> 2, p.Tq, (p.Sk + 3) >> 2);
           const uint32_t rv = (e & 1) ? ((kcol & 2) ? rnd.w : rnd.y) : ((kcol & 2) ? rnd.z : rnd.x);
           dpe = rv >= thr ? dpe * inv_keep : 0.f;
         }
@@ -414,6 +417,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
   }
   const float sl2 = p.scale * 1.4426950408889634f;
   const Philox rng(p.seed);
+  const unsigned long long off_eff = p.offset + ((p.p_drop > 0.f && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
   const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
 
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
         float dpe = dpt[nt][e];
         float pdrop = pv;
         if (p.p_drop > 0.f) {
-          const uint4 rnd = drop_rand4(rng, p.offset, bh, qq, krow[r] >> 2, p.Tq, (p.Sk + 3) >> 2);
+          const uint4 rnd = drop_rand4(rng, off_eff, bh, qq, krow[r] >> 2, p.Tq, (p.Sk + 3) >> 2);
           const int w = krow[r] & 3;
           const uint32_t rv = w == 0 ? rnd.x : (w == 1 ? rnd.y : (w == 2 ? rnd.z : rnd.w));
           const bool keep = rv >= thr;
@@ -524,7 +528,8 @@ using namespace vlm;
 extern "C" int vlm_attention_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                                  const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
                                  float* lse, const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH, int causal,
-                                 float scale, float p_drop, unsigned long long seed, unsigned long long offset, void* stream) {
+                                 float scale, float p_drop, unsigned long long seed, unsigned long long offset,
+                                 const unsigned long long* rng_offset_ptr, void* stream) {
   if (check_attn_common("vlm_attention_fwd", B, H, Tq, Sk, DH)) return -1;
   VLM_REQUIRE(q && k && v && o, "vlm_attention_fwd: null pointer");
   VLM_REQUIRE(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && o_rs % 2 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0,
@@ -532,7 +537,7 @@ extern "C" int vlm_attention_fwd(const void* q, long long q_bs, long long q_rs, 
   AttnParams p = {};
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.o = (bf16*)o; p.lse = lse; p.kmask = kmask;
   p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs; p.o_rs = o_rs;
-  p.B = B; p.H = H; p.Tq = Tq; p.Sk = Sk; p.causal = causal; p.scale = scale; p.p_drop = p_drop; p.seed = seed; p.offset = offset;
+  p.B = B; p.H = H; p.Tq = Tq; p.Sk = Sk; p.causal = causal; p.scale = scale; p.p_drop = p_drop; p.seed = seed; p.offset = offset; p.offset_ptr = rng_offset_ptr;
   dim3 grid((Tq + 63) / 64, B * H);
   cudaStream_t s = (cudaStream_t)stream;
   if (DH == 48) attn_fwd_kernel<48><<<grid, 128, 0, s>>>(p);
@@ -547,7 +552,7 @@ extern "C" int vlm_attention_bwd(const void* q, long long q_bs, long long q_rs, 
                                  void* dq, long long dq_bs, long long dq_rs, void* dk, long long dk_bs, long long dk_rs,
                                  void* dv, long long dv_bs, long long dv_rs, const uint8_t* kmask, int B, int H, int Tq,
                                  int Sk, int DH, int causal, float scale, float p_drop, unsigned long long seed,
-                                 unsigned long long offset, void* stream) {
+                                 unsigned long long offset, const unsigned long long* rng_offset_ptr, void* stream) {
   if (check_attn_common("vlm_attention_bwd", B, H, Tq, Sk, DH)) return -1;
   VLM_REQUIRE(q && k && v && o && d_o && lse && delta && dq && dk && dv, "vlm_attention_bwd: null pointer");
   VLM_REQUIRE(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && do_rs % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 &&
@@ -557,7 +562,7 @@ extern "C" int vlm_attention_bwd(const void* q, long long q_bs, long long q_rs, 
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.o = (bf16*)const_cast<void*>(o);
   p.lse = const_cast<float*>(lse); p.kmask = kmask;
   p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs; p.o_rs = o_rs;
-  p.B = B; p.H = H; p.Tq = Tq; p.Sk = Sk; p.causal = causal; p.scale = scale; p.p_drop = p_drop; p.seed = seed; p.offset = offset;
+  p.B = B; p.H = H; p.Tq = Tq; p.Sk = Sk; p.causal = causal; p.scale = scale; p.p_drop = p_drop; p.seed = seed; p.offset = offset; p.offset_ptr = rng_offset_ptr;
   p.d_o = (const bf16*)d_o; p.do_bs = do_bs; p.do_rs = do_rs;
   p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv;
   p.dq_bs = dq_bs; p.dq_rs = dq_rs; p.dk_bs = dk_bs; p.dk_rs = dk_rs; p.dv_bs = dv_bs; p.dv_rs = dv_rs;

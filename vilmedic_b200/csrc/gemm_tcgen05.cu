@@ -40,6 +40,7 @@ struct GemmEpilogue {
   int accumulate;             // c += result
   float p_drop;               // dropout on the activation (after bias/act, before the residual add)
   unsigned long long seed, offset;
+  const unsigned long long* offset_ptr;  // optional device-side addend to `offset` (CUDA-graph replayable RNG stream)
   int drop_ld;                // logical row width used for the dropout element index (row * drop_ld + col)
 };
 
@@ -362,6 +363,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int m0 = (t / n_tiles) * GEMM_BM;
       const int n0 = (t % n_tiles) * BN;
       GemmEpilogue e = epi;
+      if (e.p_drop > 0.f && e.offset_ptr) e.offset += __ldg(e.offset_ptr);
       if (b > 0) {
         const size_t esz = e.c_fp32 ? 4 : 2;
         e.c = reinterpret_cast<uint8_t*>(e.c) + (size_t)b * c_batch_stride * esz;
@@ -497,8 +499,8 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
                              int batch,
                              long long a_batch_stride, long long b_batch_stride, long long c_batch_stride,
                              long long aux_batch_stride, long long res_batch_stride, float p_drop,
-                             unsigned long long seed, unsigned long long offset, int force_bn, int max_ctas,
-                             void* stream) {
+                             unsigned long long seed, unsigned long long offset,
+                             const unsigned long long* rng_offset_ptr, int force_bn, int max_ctas, void* stream) {
   VLM_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "vlm_gemm_bf16: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
   VLM_REQUIRE(a && b && c, "vlm_gemm_bf16: null operand");
   VLM_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "vlm_gemm_bf16: lda/ldb must be multiples of 8 elements (TMA 16B stride)");
@@ -559,6 +561,7 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
   e.p_drop = p_drop;
   e.seed = seed;
   e.offset = offset;
+  e.offset_ptr = rng_offset_ptr;
   e.drop_ld = N;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
 

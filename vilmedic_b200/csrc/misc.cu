@@ -170,8 +170,9 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ ids, const bf16* 
 // ---------------------------------------------------------------- dropout (Philox4x32-10, 8 elements / thread)
 // y = x * keep / (1-p); the same (seed, offset) regenerates the mask for the backward pass.
 __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n8, float p, float scale,
-                               unsigned long long seed, unsigned long long offset) {
+                               unsigned long long seed, unsigned long long offset, const unsigned long long* offset_ptr) {
   const Philox rng(seed);
+  if (offset_ptr) offset += __ldg(offset_ptr);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const uint4 u = reinterpret_cast<const uint4*>(x)[i];
     const uint4 r0 = rng(2 * i, offset), r1 = rng(2 * i + 1, offset);
@@ -301,10 +302,10 @@ extern "C" int vlm_embed_bwd(const long long* ids, const void* dz, float* dword,
 }
 
 extern "C" int vlm_dropout_bf16(const void* x, void* y, long long n, float p, unsigned long long seed,
-                                unsigned long long offset, void* stream) {
+                                unsigned long long offset, const unsigned long long* rng_offset_ptr, void* stream) {
   VLM_REQUIRE(x && y && n >= 0 && n % 8 == 0 && p >= 0.f && p < 1.f, "vlm_dropout_bf16: need n%%8==0 and 0<=p<1");
   if (n == 0) return 0;
-  dropout_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n / 8, p, 1.f / (1.f - p), seed, offset);
+  dropout_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n / 8, p, 1.f / (1.f - p), seed, offset, rng_offset_ptr);
   return check_launch("dropout");
 }
 
@@ -325,6 +326,14 @@ extern "C" int vlm_act_bwd_f32(const float* dy, const float* y, float* dx, long 
   VLM_REQUIRE(dy && y && dx && n > 0 && (kind == 0 || kind == 1), "vlm_act_bwd_f32: bad args");
   act_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n, kind);
   return check_launch("act_bwd");
+}
+
+__global__ void u64_add_kernel(unsigned long long* p, unsigned long long v) { *p += v; }
+
+extern "C" int vlm_rng_advance(unsigned long long* counter, unsigned long long delta, void* stream) {
+  VLM_REQUIRE(counter, "vlm_rng_advance: null counter");
+  u64_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta);
+  return check_launch("rng_advance");
 }
 
 extern "C" int vlm_sum_scale_f32(const float* x, int n, float scale, float* out, void* stream) {

@@ -1,0 +1,51 @@
+"""CUDA-graph capture of the whole training step (forward + hand-written backward + gradient exchange + fused AdamW).
+
+The step issues ~1.1 k kernel launches through ctypes; replaying them as one graph removes the host from the loop
+(SURVEY.md §7 "Host overhead", guide rule 9).  Everything in the step is capture-safe by construction: no host sync,
+all scalars that change per step (AdamW step count, dropout stream position) live in device memory — the dropout
+kernels add the device counter `ops.RNG_COUNTER` to their baked (seed, offset), and the graph advances it first.
+"""
+import torch
+
+from . import ops
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, example_batch, grad_sync=None, warmup=3, step_fn=None):
+        self.model = model
+        self.opt = optimizer
+        self.sync = grad_sync
+        dev = next(model.parameters()).device
+        self.static = {k: (v.to(dev).clone() if isinstance(v, torch.Tensor) else v) for k, v in example_batch.items()}
+        self.counter = torch.zeros(1, device=dev, dtype=torch.int64)
+        ops.RNG_COUNTER[0] = self.counter
+        self._step_fn = step_fn or self._default_step
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step_fn(self.static)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step_fn(self.static)
+        torch.cuda.synchronize()
+
+    def _default_step(self, batch):
+        ops.rng_advance(self.counter, 4096)
+        out = self.model(**batch)
+        loss = out["loss"]
+        loss.backward()
+        scale = self.sync.finish() if self.sync is not None else 1.0
+        self.opt.step(grad_scale=scale)
+        return loss
+
+    def __call__(self, batch=None):
+        """Copy `batch` (host or device tensors) into the static inputs, replay, return the (device) loss tensor."""
+        if batch is not None:
+            for k, v in batch.items():
+                if isinstance(v, torch.Tensor):
+                    self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -597,55 +597,125 @@ class LMHeadCEFn(torch.autograd.Function):
         return dh, None, None, None, None, None, None, None, None
 
 
+def make_bert_layer(cfg):
+    """One HF BertLayer-shaped parameter holder (attention.self.{query,key,value}, attention.output.{dense,LayerNorm},
+    [crossattention.…], intermediate.dense, output.{dense,LayerNorm})."""
+    D = cfg.hidden_size
+    De = cfg.encoder_hidden_size or D
+    l = _Holder()
+    l.cfg = cfg
+    groups = []
+
+    def attn_block(in_kv):
+        a = _Holder()
+        a.self = _Holder()
+        a.self.query = nn.Linear(D, D)
+        a.self.key = nn.Linear(in_kv, D)
+        a.self.value = nn.Linear(in_kv, D)
+        a.output = _Holder()
+        a.output.dense = nn.Linear(D, D)
+        a.output.LayerNorm = nn.LayerNorm(D, eps=cfg.layer_norm_eps)
+        return a
+
+    l.attention = attn_block(D)
+    s = l.attention.self
+    groups += [[s.query.weight, s.key.weight, s.value.weight], [s.query.bias, s.key.bias, s.value.bias]]
+    if cfg.add_cross_attention:
+        if not cfg.is_decoder:
+            raise ValueError("add_cross_attention requires is_decoder=True")
+        l.crossattention = attn_block(De)
+        cs = l.crossattention.self
+        groups += [[cs.key.weight, cs.value.weight], [cs.key.bias, cs.value.bias]]
+    l.intermediate = _Holder()
+    l.intermediate.dense = nn.Linear(D, cfg.intermediate_size)
+    l.output = _Holder()
+    l.output.dense = nn.Linear(cfg.intermediate_size, D)
+    l.output.LayerNorm = nn.LayerNorm(D, eps=cfg.layer_norm_eps)
+    l._fused_param_groups = (lambda g=groups: g)
+    return l
+
+
+def _init_bert_weights(module, std):
+    for m in module.modules():
+        if isinstance(m, nn.Linear):
+            m.weight.data.normal_(0.0, std)
+            if m.bias is not None:
+                m.bias.data.zero_()
+        elif isinstance(m, nn.Embedding):
+            m.weight.data.normal_(0.0, std)
+            if m.padding_idx is not None:
+                m.weight.data[m.padding_idx].zero_()
+        elif isinstance(m, nn.LayerNorm):
+            m.weight.data.fill_(1.0)
+            m.bias.data.zero_()
+
+
+def run_bert_layers(layers, x, B, T, arena, anchor, cfg, kmask=None, enc=None, enc_mask=None, training=False):
+    grad = torch.is_grad_enabled()
+    for layer in layers:
+        x = BertLayerFn.apply(x, enc, anchor, layer, arena, B, T, kmask, enc_mask, bool(cfg.is_decoder), training and grad, grad)
+    return x
+
+
+class BertEncoderB200(nn.Module):
+    """transformers.models.bert.modeling_bert.BertEncoder-shaped stack (state_dict keys `layer.N.…`): hidden states in,
+    hidden states out — the `transformer` of vilmedic/models/mvqa/MVQA.py:28-30,43."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = self.config = cfg
+        self.layer = nn.ModuleList([make_bert_layer(cfg) for _ in range(cfg.num_hidden_layers)])
+        _init_bert_weights(self, cfg.initializer_range)
+
+    def forward(self, hidden_states, attention_mask=None, **kwargs):
+        """hidden_states bf16 [B,T,D] -> bf16 [B,T,D]"""
+        arena = get_arena(_root_of(self))
+        _prepare(arena, self)
+        B, T, D = hidden_states.shape
+        kmask = None
+        if attention_mask is not None:
+            kmask = (attention_mask.to(arena.device) != 0).to(torch.uint8).contiguous()
+        x = hidden_states.reshape(B * T, D).contiguous()
+        anchor = self.layer[0].output.LayerNorm.weight
+        x = run_bert_layers(self.layer, x, B, T, arena, anchor, self.cfg, kmask=kmask, training=self.training)
+        return x.view(B, T, D)
+
+
+def native_linear(linear, x2d, module, out_dtype=torch.bfloat16):
+    """y = x W^T + b through the tcgen05 GEMM for a plain nn.Linear parameter holder living in `module`'s arena."""
+    arena = get_arena(_root_of(module))
+    _prepare(arena, module)
+    return LinearFn.apply(_to_bf16(x2d).contiguous(), linear.weight, _lin(arena, linear), out_dtype)
+
+
+def native_layernorm(ln, x2d, module):
+    arena = get_arena(_root_of(module))
+    _prepare(arena, module)
+    return LayerNormFn.apply(x2d.contiguous(), ln.weight, _ln(arena, ln), ln.eps)
+
+
 class BertTower(nn.Module):
     """Post-LN transformer stack with HF BertGenerationEncoder/Decoder parameter names under `.bert` + `.lm_head`
     (decoder) — state_dict keys identical to BertGenerationDecoder (vilmedic decoder_model.py:23-26) — or bare
     encoder (`with_lm_head=False`)."""
 
-    def __init__(self, cfg, with_lm_head):
+    def __init__(self, cfg, with_lm_head, flat=False):
+        """flat=True: parameters live at `embeddings.…` / `encoder.layer.…` (BertGenerationEncoder layout, the text tower of
+        vilmedic/blocks/huggingface/encoder/encoder_model.py:24-26); otherwise under `bert.…` (BertGenerationDecoder)."""
         super().__init__()
         self.cfg = self.config = cfg
         D = cfg.hidden_size
-        self.bert = _Holder()
-        emb = self.bert.embeddings = _Holder()
+        if flat:
+            core = self
+        else:
+            core = self.bert = _Holder()
+        object.__setattr__(self, "_core", core)
+        emb = core.embeddings = _Holder()
         emb.word_embeddings = nn.Embedding(cfg.vocab_size, D, padding_idx=cfg.pad_token_id)
         emb.position_embeddings = nn.Embedding(cfg.max_position_embeddings, D)
         emb.LayerNorm = nn.LayerNorm(D, eps=cfg.layer_norm_eps)
-        self.bert.encoder = _Holder()
-        self.bert.encoder.layer = nn.ModuleList()
-        De = cfg.encoder_hidden_size or D
-        for _ in range(cfg.num_hidden_layers):
-            l = _Holder()
-            l.cfg = cfg
-            groups = []
-
-            def attn_block(in_kv):
-                a = _Holder()
-                a.self = _Holder()
-                a.self.query = nn.Linear(D, D)
-                a.self.key = nn.Linear(in_kv, D)
-                a.self.value = nn.Linear(in_kv, D)
-                a.output = _Holder()
-                a.output.dense = nn.Linear(D, D)
-                a.output.LayerNorm = nn.LayerNorm(D, eps=cfg.layer_norm_eps)
-                return a
-
-            l.attention = attn_block(D)
-            s = l.attention.self
-            groups += [[s.query.weight, s.key.weight, s.value.weight], [s.query.bias, s.key.bias, s.value.bias]]
-            if cfg.add_cross_attention:
-                if not cfg.is_decoder:
-                    raise ValueError("add_cross_attention requires is_decoder=True")
-                l.crossattention = attn_block(De)
-                cs = l.crossattention.self
-                groups += [[cs.key.weight, cs.value.weight], [cs.key.bias, cs.value.bias]]
-            l.intermediate = _Holder()
-            l.intermediate.dense = nn.Linear(D, cfg.intermediate_size)
-            l.output = _Holder()
-            l.output.dense = nn.Linear(cfg.intermediate_size, D)
-            l.output.LayerNorm = nn.LayerNorm(D, eps=cfg.layer_norm_eps)
-            l._fused_param_groups = (lambda g=groups: g)
-            self.bert.encoder.layer.append(l)
+        core.encoder = _Holder()
+        core.encoder.layer = nn.ModuleList([make_bert_layer(cfg) for _ in range(cfg.num_hidden_layers)])
         self.lm_head = None
         if with_lm_head:
             head = self.lm_head = _Holder()
@@ -657,19 +727,7 @@ class BertTower(nn.Module):
         self.reset_parameters()
 
     def reset_parameters(self):
-        std = self.cfg.initializer_range
-        for m in self.modules():
-            if isinstance(m, nn.Linear):
-                m.weight.data.normal_(0.0, std)
-                if m.bias is not None:
-                    m.bias.data.zero_()
-            elif isinstance(m, nn.Embedding):
-                m.weight.data.normal_(0.0, std)
-                if m.padding_idx is not None:
-                    m.weight.data[m.padding_idx].zero_()
-            elif isinstance(m, nn.LayerNorm):
-                m.weight.data.fill_(1.0)
-                m.bias.data.zero_()
+        _init_bert_weights(self, self.cfg.initializer_range)
 
     # ---- hidden states --------------------------------------------------------------------------------------------
     def hidden_states(self, input_ids, attention_mask=None, encoder_hidden_states=None, encoder_attention_mask=None,
@@ -680,18 +738,18 @@ class BertTower(nn.Module):
         grad = torch.is_grad_enabled()
         training = self.training
         _prepare(arena, self)
-        anchor = self.bert.embeddings.LayerNorm.weight
+        anchor = self._core.embeddings.LayerNorm.weight
         dev = arena.device
         if inputs_embeds is not None:
             B, T = inputs_embeds.shape[0], inputs_embeds.shape[1]
             x = LayerNormFn.apply(inputs_embeds.reshape(B * T, -1).contiguous(), anchor,
-                                  _ln(arena, self.bert.embeddings.LayerNorm), cfg.layer_norm_eps)
+                                  _ln(arena, self._core.embeddings.LayerNorm), cfg.layer_norm_eps)
         else:
             ids = input_ids.to(dev).long().contiguous()
             B, T = ids.shape
             if T > cfg.max_position_embeddings:
                 raise IndexError("sequence length %d exceeds max_position_embeddings %d" % (T, cfg.max_position_embeddings))
-            x = BertEmbedFn.apply(ids.view(-1), anchor, self.bert.embeddings, arena, T, 0, cfg.layer_norm_eps)
+            x = BertEmbedFn.apply(ids.view(-1), anchor, self._core.embeddings, arena, T, 0, cfg.layer_norm_eps)
         x = dropout(x, cfg.hidden_dropout_prob, training and grad)
         kmask = None
         if attention_mask is not None:
@@ -706,15 +764,15 @@ class BertTower(nn.Module):
             enc = e.reshape(e.shape[0] * e.shape[1], e.shape[2]).contiguous()
             if encoder_attention_mask is not None:
                 enc_mask = (encoder_attention_mask.to(dev) != 0).to(torch.uint8).contiguous()
-        for layer in self.bert.encoder.layer:
-            x = BertLayerFn.apply(x, enc, anchor, layer, arena, B, T, kmask, enc_mask, bool(cfg.is_decoder), training and grad, grad)
+        x = run_bert_layers(self._core.encoder.layer, x, B, T, arena, anchor, cfg, kmask=kmask, enc=enc, enc_mask=enc_mask,
+                            training=training)
         return x, B, T
 
     def lm_loss(self, x, input_ids, B, T, keep_logits):
         arena = get_arena(_root_of(self))
         ids = input_ids.to(arena.device).long().contiguous().view(-1)
         grad = torch.is_grad_enabled()
-        return LMHeadCEFn.apply(x, self.bert.embeddings.LayerNorm.weight, ids, self.lm_head, arena, B, T, keep_logits, grad)
+        return LMHeadCEFn.apply(x, self._core.embeddings.LayerNorm.weight, ids, self.lm_head, arena, B, T, keep_logits, grad)
 
     def lm_logits(self, x):
         """bf16 [M,D] -> fp32 [M,V] logits (inference)."""

@@ -17,6 +17,8 @@ LAUNCHES = [0]
 _KERNELS_PER_CALL = {"vlm_attention_bwd": 2, "vlm_adamw_step": 2}
 # Optional per-call CUDA-event timing of the GEMM launches (bench.py roofline pass): list of (M, N, K, batch, start, end)
 GEMM_TIMING = None
+# Optional device uint64 added to every dropout offset (see vlm_rng_advance): set by GraphedTrainStep.
+RNG_COUNTER = [None]
 
 _orig_check = check
 
@@ -95,7 +97,7 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, out=None, out_dtype=torch.
         c_float(alpha), ptr(alpha_t), c_int(int(accumulate)), c_int(batch),
         c_ll(a.stride(0) if batched else 0), c_ll(b.stride(0) if batched else 0),
         c_ll(out.stride(0) if batched else 0), c_ll(aux_bs), c_ll(res_bs),
-        c_float(p_drop), c_u64(seed), c_u64(offset), c_int(force_bn), c_int(max_ctas), stream_ptr())
+        c_float(p_drop), c_u64(seed), c_u64(offset), ptr(RNG_COUNTER[0]), c_int(force_bn), c_int(max_ctas), stream_ptr())
     check(rc, "vlm_gemm_bf16")
     if GEMM_TIMING is not None:
         ev1.record()
@@ -151,7 +153,7 @@ def attention_fwd(q, k, v, H, DH, *, kmask=None, causal=False, scale=None, p_dro
     check(_L().vlm_attention_fwd(ptr(q), c_ll(qs[0]), c_ll(qs[1]), ptr(k), c_ll(ks[0]), c_ll(ks[1]), ptr(v), c_ll(vs[0]),
                                  c_ll(vs[1]), ptr(o), c_ll(o.stride(0)), c_ll(o.stride(1)), ptr(lse), ptr(kmask),
                                  c_int(B), c_int(H), c_int(Tq), c_int(Sk), c_int(DH), c_int(int(causal)), c_float(scale),
-                                 c_float(p_drop), c_u64(seed), c_u64(offset), stream_ptr()), "vlm_attention_fwd")
+                                 c_float(p_drop), c_u64(seed), c_u64(offset), ptr(RNG_COUNTER[0]), stream_ptr()), "vlm_attention_fwd")
     return o, lse
 
 
@@ -169,7 +171,7 @@ def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, H, DH, *, kmask=None, causal=
                                  c_ll(s[5][1]), ptr(dk), c_ll(s[6][0]), c_ll(s[6][1]), ptr(dv), c_ll(s[7][0]),
                                  c_ll(s[7][1]), ptr(kmask), c_int(B), c_int(H), c_int(Tq), c_int(Sk), c_int(DH),
                                  c_int(int(causal)), c_float(scale), c_float(p_drop), c_u64(seed), c_u64(offset),
-                                 stream_ptr()), "vlm_attention_bwd")
+                                 ptr(RNG_COUNTER[0]), stream_ptr()), "vlm_attention_bwd")
 
 
 def softmax_ce(logits, ids, V, *, shift_T=0, smoothing=0.0, grad_scale=1.0, dlogits=None, want_lse=False):
@@ -255,8 +257,8 @@ def dropout(x, p, seed, offset, out=None):
     _req(x.is_contiguous() and x.dtype == torch.bfloat16 and x.numel() % 8 == 0, "dropout: contiguous bf16, numel % 8 == 0")
     if out is None:
         out = torch.empty_like(x)
-    check(_L().vlm_dropout_bf16(ptr(x), ptr(out), c_ll(x.numel()), c_float(p), c_u64(seed), c_u64(offset), stream_ptr()),
-          "vlm_dropout_bf16")
+    check(_L().vlm_dropout_bf16(ptr(x), ptr(out), c_ll(x.numel()), c_float(p), c_u64(seed), c_u64(offset), ptr(RNG_COUNTER[0]),
+                                stream_ptr()), "vlm_dropout_bf16")
     return out
 
 
@@ -335,3 +337,7 @@ def sym_lse_bwd(S, scale, lse_row, lse_col, w_row, w_col, g_t):
     check(_L().vlm_sym_lse_bwd(ptr(S), c_int(N), c_ll(S.stride(0)), c_float(scale), ptr(lse_row), ptr(lse_col), c_float(w_row),
                                c_float(w_col), ptr(g_t), ptr(dS), c_ll(ldd), stream_ptr()), "vlm_sym_lse_bwd")
     return dS[:, :N]
+
+
+def rng_advance(counter, delta):
+    check(_L().vlm_rng_advance(ptr(counter), c_u64(delta), stream_ptr()), "vlm_rng_advance")
