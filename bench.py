@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="resident-input leg only (for profiler runs)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -253,7 +254,11 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ms, last = timed(lambda: devb, args.steps, False)
-    ms_e2e, last_loss = timed(host_batch, args.steps, True)
+    if args.quick:
+        ms_e2e, last_loss = ms, None
+        args.no_roofline = args.no_cpu_baseline = True
+    else:
+        ms_e2e, last_loss = timed(host_batch, args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
 
     value = world * B * args.steps / (ms / 1e3)

@@ -102,3 +102,66 @@ def test_gemm_batched(cuda_dev):
     torch.cuda.synchronize()
     ref = p.float() @ v.float()
     assert (o - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 768, 768), (1000, 2304, 768), (12608, 768, 768), (640, 30522, 128),
+                                   (300, 520, 200)])
+@pytest.mark.parametrize("bn", [1128, 1256])
+def test_gemm_2cta(cuda_dev, a_mn, b_mn, M, N, K, bn):
+    """cta_group::2 kernel (CTA pair per 256 x BN tile), forced through force_bn = 1000 + BN."""
+    from vilmedic_b200 import ops
+    if (M, N, K) == (12608, 768, 768) and (a_mn or b_mn):
+        pytest.skip("big shape only in the forward layout")
+    a = _rand((K, M) if a_mn else (M, K), cuda_dev, 1)
+    b = _rand((K, N) if b_mn else (N, K), cuda_dev, 2)
+    ref = _ref(a, b, a_mn, b_mn)
+    out = ops.gemm(a, b, a_mn_major=a_mn, b_mn_major=b_mn, out_dtype=torch.float32, force_bn=bn)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-3 * scale + 1e-3, "max err %g (scale %g)" % (err, scale)
+
+
+def test_gemm_2cta_epilogue_and_repeat(cuda_dev):
+    from vilmedic_b200 import ops
+    M, N, K = 1576, 3072, 768
+    a = _rand((M, K), cuda_dev, 3)
+    w = _rand((N, K), cuda_dev, 4) * 0.05
+    bias = torch.randn(N, device=cuda_dev)
+    pre_ref = a.float() @ w.float().t() + bias
+    pre = torch.empty(M, N, device=cuda_dev, dtype=torch.bfloat16)
+    for _ in range(3):   # back-to-back launches exercise TMEM alloc/dealloc + barrier re-init across kernels
+        h = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, aux_out=pre, force_bn=1256)
+    torch.cuda.synchronize()
+    assert (pre.float() - pre_ref).abs().max().item() < 3e-2
+    assert (h.float() - torch.nn.functional.gelu(pre_ref)).abs().max().item() < 3e-2
+    acc = torch.ones(N, K, device=cuda_dev)
+    g = _rand((M, N), cuda_dev, 5)
+    ops.gemm(g, a, a_mn_major=True, b_mn_major=True, out=acc, accumulate=True, force_bn=1128)   # wgrad layout
+    torch.cuda.synchronize()
+    ref = 1 + g.float().t() @ a.float()
+    assert (acc - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+
+
+def test_gemm_split_k_wgrad(cuda_dev):
+    """Weight-gradient shape (few output tiles, K = tokens): the split-K path accumulates with atomics into fp32 C."""
+    from vilmedic_b200 import ops
+    for (M, N, K) in [(768, 768, 8192), (2304, 768, 12608), (768, 3072, 8192), (330, 768, 1024)]:
+        dy = _rand((K, M), cuda_dev, 1)        # [tokens, out]  -> A' MN-major
+        x = _rand((K, N), cuda_dev, 2)         # [tokens, in]   -> B' MN-major
+        acc = torch.full((M, N), 0.5, device=cuda_dev)
+        ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out=acc, accumulate=True)
+        torch.cuda.synchronize()
+        ref = 0.5 + dy.float().t() @ x.float()
+        assert (acc - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-2, (M, N, K)
+
+
+def test_gemm_unaligned_n_output(cuda_dev):
+    from vilmedic_b200 import ops
+    a, w = _rand((37, 768), cuda_dev, 1), _rand((330, 768), cuda_dev, 2)
+    bias = torch.randn(332, device=cuda_dev)
+    out = ops.gemm(a, w, bias=bias, out_dtype=torch.float32)
+    assert out.shape == (37, 330)
+    ref = a.float() @ w.float().t() + bias[:330]
+    assert (out - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3

@@ -1,0 +1,217 @@
+// Fused GEMM epilogue shared by the 1-CTA and 2-CTA tcgen05 GEMM kernels: one thread owns one accumulator row and
+// processes it in chunks of 32 fp32 columns read from TMEM.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace vlm {
+
+struct GemmEpilogue {
+  void* c;
+  long long ldc;
+  int c_fp32;
+  const float* bias;          // [N] or null
+  const void* residual;       // same dtype as c, ld = ldr
+  long long ldr;
+  int act;                    // 0 none, 1 GELU (optionally stash pre-activation), 2 multiply by GELU'(aux_in)
+  const bf16* aux_in;         // [M, ld_aux]
+  bf16* aux_out;              // [M, ld_aux]
+  long long ld_aux;
+  float alpha;
+  const float* alpha_ptr;     // optional device scalar multiplied into alpha (upstream loss gradient)
+  int accumulate;             // c += result
+  int atomic;                 // split-K: fp32 C is updated with atomic adds (implies accumulate)
+  float p_drop;               // dropout on the activation (after bias/act, before the residual add)
+  unsigned long long seed, offset;
+  const unsigned long long* offset_ptr;  // optional device-side addend to `offset` (CUDA-graph replayable RNG stream)
+  int drop_ld;                // logical row width used for the dropout element index (row * drop_ld + col)
+};
+
+__device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int col0, int M, int N,
+                                               const GemmEpilogue& e) {
+  if (row >= M || col0 >= N) return;
+  float v[32];
+  const float alpha = e.alpha_ptr ? e.alpha * __ldg(e.alpha_ptr) : e.alpha;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * alpha;
+
+  const bool full = (col0 + 32 <= N);
+  if (full) {
+    if (e.bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);
+        v[4 * j + 0] += b.x;
+        v[4 * j + 1] += b.y;
+        v[4 * j + 2] += b.z;
+        v[4 * j + 3] += b.w;
+      }
+    }
+    if (e.act == 1) {
+      if (e.aux_out) {
+        uint4* dst = reinterpret_cast<uint4*>(e.aux_out + (long long)row * e.ld_aux + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+          u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+          u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+          u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+          dst[j] = u;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    } else if (e.act == 2) {
+      const uint4* src = reinterpret_cast<const uint4*>(e.aux_in + (long long)row * e.ld_aux + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = __ldg(src + j);
+        const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
+        v[8 * j + 0] *= gelu_erf_grad(p0.x);
+        v[8 * j + 1] *= gelu_erf_grad(p0.y);
+        v[8 * j + 2] *= gelu_erf_grad(p1.x);
+        v[8 * j + 3] *= gelu_erf_grad(p1.y);
+        v[8 * j + 4] *= gelu_erf_grad(p2.x);
+        v[8 * j + 5] *= gelu_erf_grad(p2.y);
+        v[8 * j + 6] *= gelu_erf_grad(p3.x);
+        v[8 * j + 7] *= gelu_erf_grad(p3.y);
+      }
+    }
+    if (e.p_drop > 0.f) {
+      const Philox rng(e.seed);
+      const uint32_t thr = (uint32_t)(e.p_drop * 4294967296.0f);
+      const float inv_keep = 1.f / (1.f - e.p_drop);
+      const unsigned long long base = ((unsigned long long)row * (unsigned long long)e.drop_ld + (unsigned long long)col0) >> 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 r = rng(base + j, e.offset);
+        v[4 * j + 0] = r.x >= thr ? v[4 * j + 0] * inv_keep : 0.f;
+        v[4 * j + 1] = r.y >= thr ? v[4 * j + 1] * inv_keep : 0.f;
+        v[4 * j + 2] = r.z >= thr ? v[4 * j + 2] * inv_keep : 0.f;
+        v[4 * j + 3] = r.w >= thr ? v[4 * j + 3] * inv_keep : 0.f;
+      }
+    }
+    if (e.c_fp32) {
+      float* crow = reinterpret_cast<float*>(e.c) + (long long)row * e.ldc + col0;
+      if (e.residual) {
+        const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.residual) +
+                                                           (long long)row * e.ldr + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 r = __ldg(r4 + j);
+          v[4 * j + 0] += r.x;
+          v[4 * j + 1] += r.y;
+          v[4 * j + 2] += r.z;
+          v[4 * j + 3] += r.w;
+        }
+      }
+      float4* c4 = reinterpret_cast<float4*>(crow);
+      if (e.atomic) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(c4 + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        return;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (e.accumulate) {
+          const float4 old = c4[j];
+          o.x += old.x;
+          o.y += old.y;
+          o.z += old.z;
+          o.w += old.w;
+        }
+        c4[j] = o;
+      }
+    } else {
+      bf16* crow = reinterpret_cast<bf16*>(e.c) + (long long)row * e.ldc + col0;
+      if (e.residual) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.residual) +
+                                                         (long long)row * e.ldr + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 u = __ldg(r4 + j);
+          const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z),
+                       p3 = unpack_bf16x2(u.w);
+          v[8 * j + 0] += p0.x;
+          v[8 * j + 1] += p0.y;
+          v[8 * j + 2] += p1.x;
+          v[8 * j + 3] += p1.y;
+          v[8 * j + 4] += p2.x;
+          v[8 * j + 5] += p2.y;
+          v[8 * j + 6] += p3.x;
+          v[8 * j + 7] += p3.y;
+        }
+      }
+      uint4* c4 = reinterpret_cast<uint4*>(crow);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (e.accumulate) {
+          const uint4 u = c4[j];
+          const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z),
+                       p3 = unpack_bf16x2(u.w);
+          v[8 * j + 0] += p0.x;
+          v[8 * j + 1] += p0.y;
+          v[8 * j + 2] += p1.x;
+          v[8 * j + 3] += p1.y;
+          v[8 * j + 4] += p2.x;
+          v[8 * j + 5] += p2.y;
+          v[8 * j + 6] += p3.x;
+          v[8 * j + 7] += p3.y;
+        }
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        c4[j] = u;
+      }
+    }
+  } else {
+    // ragged last column tile: scalar, fully predicated (unrolled so that v[] stays in registers)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      if (col >= N) continue;
+      float x = v[j];
+      if (e.bias) x += e.bias[col];
+      if (e.act == 1) {
+        if (e.aux_out) e.aux_out[(long long)row * e.ld_aux + col] = __float2bfloat16(x);
+        x = gelu_erf(x);
+      } else if (e.act == 2) {
+        x *= gelu_erf_grad(__bfloat162float(e.aux_in[(long long)row * e.ld_aux + col]));
+      }
+      if (e.p_drop > 0.f) {
+        const Philox rng(e.seed);
+        const unsigned long long el = (unsigned long long)row * (unsigned long long)e.drop_ld + (unsigned long long)col;
+        const uint4 r = rng(el >> 2, e.offset);
+        const uint32_t w = (el & 3) == 0 ? r.x : ((el & 3) == 1 ? r.y : ((el & 3) == 2 ? r.z : r.w));
+        x = w >= (uint32_t)(e.p_drop * 4294967296.0f) ? x / (1.f - e.p_drop) : 0.f;
+      }
+      if (e.c_fp32) {
+        float* c = reinterpret_cast<float*>(e.c) + (long long)row * e.ldc + col;
+        if (e.residual) x += reinterpret_cast<const float*>(e.residual)[(long long)row * e.ldr + col];
+        if (e.atomic) {
+          atomicAdd(c, x);
+          continue;
+        }
+        if (e.accumulate) x += *c;
+        *c = x;
+      } else {
+        bf16* c = reinterpret_cast<bf16*>(e.c) + (long long)row * e.ldc + col;
+        if (e.residual) x += __bfloat162float(reinterpret_cast<const bf16*>(e.residual)[(long long)row * e.ldr + col]);
+        if (e.accumulate) x += __bfloat162float(*c);
+        *c = __float2bfloat16(x);
+      }
+    }
+  }
+}
+
+
+// host-side pieces shared by the GEMM translation units
+int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch,
+                   uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows);
+
+}  // namespace vlm

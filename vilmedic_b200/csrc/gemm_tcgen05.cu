@@ -13,36 +13,20 @@
 // 265-268, 296-312; modeling_bert_generation.py:52-56, 89-153, 265-293) used by
 // vilmedic/blocks/vision/visual_encoder.py:56-58 and vilmedic/blocks/huggingface/decoder/decoder_model.py:23-26.
 //
-// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM allocator + MMA issuer, warps2..5 = epilogue.
-#include "common.cuh"
-#include "vlm_b200.h"
+// Warp roles (320 threads): warp0 = TMA producer, warp1 = TMEM allocator + MMA issuer, warps2..9 = epilogue
+// (warp w drains TMEM lane quadrant w%4, column half (w-2)/4).
 #include <cuda.h>
+#include <cstdlib>
+#include "common.cuh"
+#include "gemm_epilogue.cuh"
+#include "vlm_b200.h"
 
 namespace vlm {
 
 static constexpr int GEMM_BM = 128;
 static constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle row
-static constexpr int GEMM_THREADS = 192;
-
-struct GemmEpilogue {
-  void* c;
-  long long ldc;
-  int c_fp32;
-  const float* bias;          // [N] or null
-  const void* residual;       // same dtype as c, ld = ldr
-  long long ldr;
-  int act;                    // 0 none, 1 GELU (optionally stash pre-activation), 2 multiply by GELU'(aux_in)
-  const bf16* aux_in;         // [M, ld_aux]
-  bf16* aux_out;              // [M, ld_aux]
-  long long ld_aux;
-  float alpha;
-  const float* alpha_ptr;     // optional device scalar multiplied into alpha (upstream loss gradient)
-  int accumulate;             // c += result
-  float p_drop;               // dropout on the activation (after bias/act, before the residual add)
-  unsigned long long seed, offset;
-  const unsigned long long* offset_ptr;  // optional device-side addend to `offset` (CUDA-graph replayable RNG stream)
-  int drop_ld;                // logical row width used for the dropout element index (row * drop_ld + col)
-};
+static constexpr int GEMM_EPI_WARPS = 8;            // two warps per TMEM lane quadrant, each owns half of the columns
+static constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 template <int BN>
 struct GemmSmem {
@@ -54,184 +38,12 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
 };
 
-__device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int col0, int M, int N,
-                                               const GemmEpilogue& e) {
-  if (row >= M || col0 >= N) return;
-  float v[32];
-  const float alpha = e.alpha_ptr ? e.alpha * __ldg(e.alpha_ptr) : e.alpha;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * alpha;
-
-  const bool full = (col0 + 32 <= N);
-  if (full) {
-    if (e.bias) {
-      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg(b4 + j);
-        v[4 * j + 0] += b.x;
-        v[4 * j + 1] += b.y;
-        v[4 * j + 2] += b.z;
-        v[4 * j + 3] += b.w;
-      }
-    }
-    if (e.act == 1) {
-      if (e.aux_out) {
-        uint4* dst = reinterpret_cast<uint4*>(e.aux_out + (long long)row * e.ld_aux + col0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u;
-          u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-          u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-          u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-          u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-          dst[j] = u;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-    } else if (e.act == 2) {
-      const uint4* src = reinterpret_cast<const uint4*>(e.aux_in + (long long)row * e.ld_aux + col0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 u = __ldg(src + j);
-        const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
-        v[8 * j + 0] *= gelu_erf_grad(p0.x);
-        v[8 * j + 1] *= gelu_erf_grad(p0.y);
-        v[8 * j + 2] *= gelu_erf_grad(p1.x);
-        v[8 * j + 3] *= gelu_erf_grad(p1.y);
-        v[8 * j + 4] *= gelu_erf_grad(p2.x);
-        v[8 * j + 5] *= gelu_erf_grad(p2.y);
-        v[8 * j + 6] *= gelu_erf_grad(p3.x);
-        v[8 * j + 7] *= gelu_erf_grad(p3.y);
-      }
-    }
-    if (e.p_drop > 0.f) {
-      const Philox rng(e.seed);
-      const uint32_t thr = (uint32_t)(e.p_drop * 4294967296.0f);
-      const float inv_keep = 1.f / (1.f - e.p_drop);
-      const unsigned long long base = ((unsigned long long)row * (unsigned long long)e.drop_ld + (unsigned long long)col0) >> 2;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint4 r = rng(base + j, e.offset);
-        v[4 * j + 0] = r.x >= thr ? v[4 * j + 0] * inv_keep : 0.f;
-        v[4 * j + 1] = r.y >= thr ? v[4 * j + 1] * inv_keep : 0.f;
-        v[4 * j + 2] = r.z >= thr ? v[4 * j + 2] * inv_keep : 0.f;
-        v[4 * j + 3] = r.w >= thr ? v[4 * j + 3] * inv_keep : 0.f;
-      }
-    }
-    if (e.c_fp32) {
-      float* crow = reinterpret_cast<float*>(e.c) + (long long)row * e.ldc + col0;
-      if (e.residual) {
-        const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.residual) +
-                                                           (long long)row * e.ldr + col0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 r = __ldg(r4 + j);
-          v[4 * j + 0] += r.x;
-          v[4 * j + 1] += r.y;
-          v[4 * j + 2] += r.z;
-          v[4 * j + 3] += r.w;
-        }
-      }
-      float4* c4 = reinterpret_cast<float4*>(crow);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        if (e.accumulate) {
-          const float4 old = c4[j];
-          o.x += old.x;
-          o.y += old.y;
-          o.z += old.z;
-          o.w += old.w;
-        }
-        c4[j] = o;
-      }
-    } else {
-      bf16* crow = reinterpret_cast<bf16*>(e.c) + (long long)row * e.ldc + col0;
-      if (e.residual) {
-        const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.residual) +
-                                                         (long long)row * e.ldr + col0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 u = __ldg(r4 + j);
-          const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z),
-                       p3 = unpack_bf16x2(u.w);
-          v[8 * j + 0] += p0.x;
-          v[8 * j + 1] += p0.y;
-          v[8 * j + 2] += p1.x;
-          v[8 * j + 3] += p1.y;
-          v[8 * j + 4] += p2.x;
-          v[8 * j + 5] += p2.y;
-          v[8 * j + 6] += p3.x;
-          v[8 * j + 7] += p3.y;
-        }
-      }
-      uint4* c4 = reinterpret_cast<uint4*>(crow);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (e.accumulate) {
-          const uint4 u = c4[j];
-          const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z),
-                       p3 = unpack_bf16x2(u.w);
-          v[8 * j + 0] += p0.x;
-          v[8 * j + 1] += p0.y;
-          v[8 * j + 2] += p1.x;
-          v[8 * j + 3] += p1.y;
-          v[8 * j + 4] += p2.x;
-          v[8 * j + 5] += p2.y;
-          v[8 * j + 6] += p3.x;
-          v[8 * j + 7] += p3.y;
-        }
-        uint4 u;
-        u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-        u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-        u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-        u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-        c4[j] = u;
-      }
-    }
-  } else {
-    // ragged last column tile: scalar, fully predicated
-#pragma unroll 1
-    for (int j = 0; j < 32; ++j) {
-      const int col = col0 + j;
-      if (col >= N) break;
-      float x = v[j];
-      if (e.bias) x += e.bias[col];
-      if (e.act == 1) {
-        if (e.aux_out) e.aux_out[(long long)row * e.ld_aux + col] = __float2bfloat16(x);
-        x = gelu_erf(x);
-      } else if (e.act == 2) {
-        x *= gelu_erf_grad(__bfloat162float(e.aux_in[(long long)row * e.ld_aux + col]));
-      }
-      if (e.p_drop > 0.f) {
-        const Philox rng(e.seed);
-        const unsigned long long el = (unsigned long long)row * (unsigned long long)e.drop_ld + (unsigned long long)col;
-        const uint4 r = rng(el >> 2, e.offset);
-        const uint32_t w = (el & 3) == 0 ? r.x : ((el & 3) == 1 ? r.y : ((el & 3) == 2 ? r.z : r.w));
-        x = w >= (uint32_t)(e.p_drop * 4294967296.0f) ? x / (1.f - e.p_drop) : 0.f;
-      }
-      if (e.c_fp32) {
-        float* c = reinterpret_cast<float*>(e.c) + (long long)row * e.ldc + col;
-        if (e.residual) x += reinterpret_cast<const float*>(e.residual)[(long long)row * e.ldr + col];
-        if (e.accumulate) x += *c;
-        *c = x;
-      } else {
-        bf16* c = reinterpret_cast<bf16*>(e.c) + (long long)row * e.ldc + col;
-        if (e.residual) x += __bfloat162float(reinterpret_cast<const bf16*>(e.residual)[(long long)row * e.ldr + col]);
-        if (e.accumulate) x += __bfloat162float(*c);
-        *c = __float2bfloat16(x);
-      }
-    }
-  }
-}
-
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         int M, int N, int K, int batch, int a_bmul, int b_bmul, long long c_batch_stride,
-                         long long aux_batch_stride, long long res_batch_stride, GemmEpilogue epi) {
+                         int M, int N, int K, int batch, int a_bmul, int b_bmul, int split_k,
+                         long long c_batch_stride, long long aux_batch_stride, long long res_batch_stride,
+                         GemmEpilogue epi) {
   using S = GemmSmem<BN>;
   constexpr int STAGES = S::STAGES;
   constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;  // two accumulator buffers of BN fp32 columns
@@ -252,6 +64,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
   const int tiles_per_batch = m_tiles * n_tiles;
   const int total_tiles = tiles_per_batch * batch;
+  // split-K: work item = (tile, split); split s covers k-blocks [s*kb_per, min(k_blocks, (s+1)*kb_per))
+  const int kb_per = (k_blocks + split_k - 1) / split_k;
+  const int total_work = total_tiles * split_k;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -264,7 +79,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[i], GEMM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   } else if (warp_idx == 1) {
@@ -280,12 +95,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int tile = work % total_tiles, split = work / total_tiles;
+        const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+        if (kb0 >= kb1) continue;
         const int b = tile / tiles_per_batch;
         const int t = tile - b * tiles_per_batch;
         const int m0 = (t / n_tiles) * GEMM_BM;
         const int n0 = (t % n_tiles) * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
@@ -324,11 +142,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int split = work / total_tiles;
+        const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+        if (kb0 >= kb1) continue;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
@@ -337,7 +158,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t da = make_smem_desc(sa + k * A_KSTEP, A_LBO, 1024);
             const uint64_t db = make_smem_desc(sb + k * B_KSTEP, B_LBO, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
           if (++stage == STAGES) {
@@ -353,16 +174,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int quad = warp_idx & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue warps (2..9) =====================
+    const int quad = warp_idx & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp_idx - 2) >> 2;          // which half of the tile's columns this warp drains
+    constexpr int CHUNKS = BN / 32;                // BN in {64,128,192,256} -> 2,4,6,8 chunks
+    const int c_begin = half * (CHUNKS / 2), c_end = (half + 1) * (CHUNKS / 2);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      const int tile = work % total_tiles, split = work / total_tiles;
+      const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+      if (kb0 >= kb1) continue;
       const int b = tile / tiles_per_batch;
       const int t = tile - b * tiles_per_batch;
       const int m0 = (t / n_tiles) * GEMM_BM;
       const int n0 = (t % n_tiles) * BN;
       GemmEpilogue e = epi;
+      if (split > 0) {  // bias / residual are added once, by the first K split
+        e.bias = nullptr;
+        e.residual = nullptr;
+      }
       if (e.p_drop > 0.f && e.offset_ptr) e.offset += __ldg(e.offset_ptr);
       if (b > 0) {
         const size_t esz = e.c_fp32 ? 4 : 2;
@@ -376,7 +207,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
@@ -445,7 +276,7 @@ int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t ro
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int batch, int a_bmul,
-                       int b_bmul, long long c_bs, long long aux_bs, long long res_bs, const GemmEpilogue& epi, int max_ctas,
+                       int b_bmul, int split_k, long long c_bs, long long aux_bs, long long res_bs, const GemmEpilogue& epi, int max_ctas,
                        cudaStream_t stream) {
   using S = GemmSmem<BN>;
   auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN>;
@@ -459,10 +290,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
     attr_set = true;
   }
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN - 1) / BN;
-  const long long tiles = (long long)m_tiles * n_tiles * batch;
+  const long long tiles = (long long)m_tiles * n_tiles * batch * split_k;
   int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, M, N, K, batch, a_bmul, b_bmul, c_bs, aux_bs, res_bs, epi);
+  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_bs, aux_bs, res_bs, epi);
   return check_launch("gemm_bf16_tcgen05");
 }
 
@@ -482,6 +313,42 @@ static int pick_bn(int M, int N, int batch, int force_bn) {
     const double cost = (double)waves * (bn + 24.0);
     if (cost < best_cost) {
       best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+int gemm2_dispatch(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, int M, int N, int K,
+                   int bn, const GemmEpilogue& e, cudaStream_t s);
+
+// 0 = 1-CTA kernel, else the N tile (128 | 256) of the 2-CTA kernel.  force_bn >= 1000 forces 2-CTA with bn = force_bn-1000.
+static int pick_2cta(int M, int N, int K, int batch, int force_bn, int bn1) {
+  if (batch != 1) return 0;
+  if (force_bn >= 1000) return force_bn - 1000;
+  if (force_bn != 0) return 0;
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* env = getenv("VLM_GEMM_2CTA");
+    enabled = (env && env[0] == '1') ? 1 : 0;   // opt-in until the pair kernel has soaked
+  }
+  if (!enabled || M < 512 || N < 128) return 0;
+  const int sms = num_sms();
+  const long long m1 = (M + GEMM_BM - 1) / GEMM_BM, m2 = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const long long t1 = m1 * ((N + bn1 - 1) / bn1);
+  const double cost1 = (double)((t1 + sms - 1) / sms) * (bn1 + 24.0);
+  int best = 0;
+  double best_cost = cost1;
+  const int cands[2] = {256, 128};
+  for (int i = 0; i < 2; ++i) {
+    const int bn = cands[i];
+    if (N <= bn / 2) continue;
+    const long long t2 = m2 * ((N + bn - 1) / bn);
+    const long long pairs = sms / 2;
+    // a pair finishes a 256 x bn tile in the time a single CTA needs for 128 x bn, with 1.5x less L2->smem traffic
+    const double cost2 = (double)((t2 + pairs - 1) / pairs) * (bn + 24.0) * 0.85;
+    if (cost2 < best_cost) {
+      best_cost = cost2;
       best = bn;
     }
   }
@@ -528,7 +395,9 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
       bound_dev = dev;
     }
   }
-  const int bn = pick_bn(M, N, batch, force_bn);
+  const int bn = pick_bn(M, N, batch, force_bn >= 1000 ? 0 : force_bn);
+  const int bn2 = pick_2cta(M, N, K, batch, force_bn, bn);
+  VLM_REQUIRE(bn2 == 0 || bn2 == 128 || bn2 == 256, "vlm_gemm_bf16: 2-CTA N tile must be 128 or 256");
   CUtensorMap ta, tb;
   // a zero batch stride broadcasts that operand: encode a single-batch map and pin the batch coordinate to 0
   const int a_bmul = (batch > 1 && a_batch_stride != 0) ? 1 : 0, b_bmul = (batch > 1 && b_batch_stride != 0) ? 1 : 0;
@@ -564,19 +433,35 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
   e.offset_ptr = rng_offset_ptr;
   e.drop_ld = N;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // split-K for under-filled grids (weight gradients: few output tiles, K = number of tokens): fp32 C, accumulate
+  // semantics, atomics in the epilogue.
+  int split_k = 1;
+  e.atomic = 0;
+  if (bn2 == 0 && c_is_fp32 && accumulate && act == 0 && p_drop == 0.f && !residual) {
+    const long long tiles = (long long)((M + GEMM_BM - 1) / GEMM_BM) * ((N + bn - 1) / bn) * batch;
+    const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+    const int sms = num_sms();
+    if (tiles * 2 <= sms && k_blocks >= 16) {
+      split_k = (int)((sms + tiles - 1) / tiles);
+      if (split_k > k_blocks / 8) split_k = k_blocks / 8;
+      if (split_k < 1) split_k = 1;
+    }
+    e.atomic = split_k > 1;
+  }
+  if (bn2 != 0) return gemm2_dispatch(a, lda, a_mn_major, b, ldb, b_mn_major, M, N, K, bn2, e, s);
 
 #define VLM_GEMM_DISPATCH(BN_)                                                                                      \
   if (a_mn_major) {                                                                                                 \
     if (b_mn_major)                                                                                                 \
-      return launch_gemm<BN_, true, true>(ta, tb, M, N, K, batch, a_bmul, b_bmul, c_batch_stride, aux_batch_stride,                 \
+      return launch_gemm<BN_, true, true>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                 \
                                           res_batch_stride, e, max_ctas, s);                                        \
-    return launch_gemm<BN_, true, false>(ta, tb, M, N, K, batch, a_bmul, b_bmul, c_batch_stride, aux_batch_stride, res_batch_stride, \
+    return launch_gemm<BN_, true, false>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride, res_batch_stride, \
                                          e, max_ctas, s);                                                           \
   } else {                                                                                                          \
     if (b_mn_major)                                                                                                 \
-      return launch_gemm<BN_, false, true>(ta, tb, M, N, K, batch, a_bmul, b_bmul, c_batch_stride, aux_batch_stride,                \
+      return launch_gemm<BN_, false, true>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                \
                                            res_batch_stride, e, max_ctas, s);                                       \
-    return launch_gemm<BN_, false, false>(ta, tb, M, N, K, batch, a_bmul, b_bmul, c_batch_stride, aux_batch_stride,                 \
+    return launch_gemm<BN_, false, false>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                 \
                                           res_batch_stride, e, max_ctas, s);                                        \
   }
   switch (bn) {

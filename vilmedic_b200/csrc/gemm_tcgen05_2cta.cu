@@ -1,0 +1,297 @@
+// 2-CTA (cta_group::2) variant of the bf16 GEMM: a CTA pair on one TPC computes a 256 x BN tile with ONE
+// tcgen05.mma.cta_group::2 instruction stream issued by the leader CTA.  Each CTA stages its own 128 A rows and HALF of
+// the B tile, so the L2->smem traffic per FLOP drops 1.5x versus the 1-CTA kernel (which is L2-bandwidth bound at
+// ~87 FLOP/B) and the smem ring gets 6 stages of 32 KB.  Same operand conventions / epilogue as gemm_tcgen05.cu.
+//
+// Protocol (per pair; CTA rank r in {0 = leader, 1}):
+//   full[s]   lives in the leader: 1 arrival (leader producer, expect_tx = bytes of BOTH CTAs); both producers' TMA
+//             (cp.async.bulk.tensor ... .cta_group::2) complete_tx on the leader's barrier (peer bit cleared).
+//   empty[s]  one per CTA: the leader's tcgen05.commit.cta_group::2 multicasts the arrival to both.
+//   tmem_full[a]  one per CTA (multicast commit);  tmem_empty[a] in the leader: 2 x EPI_WARPS arrivals (remote arrive
+//             from the peer's epilogue warps).
+#include <cuda.h>
+#include "common.cuh"
+#include "gemm_epilogue.cuh"
+#include "vlm_b200.h"
+
+namespace vlm {
+
+static constexpr int G2_BM = 128;   // rows per CTA (pair: 256)
+static constexpr int G2_BK = 64;
+static constexpr int G2_EPI_WARPS = 8;
+static constexpr int G2_THREADS = 64 + 32 * G2_EPI_WARPS;
+static constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
+
+template <int BN>
+struct G2Smem {
+  static constexpr int A_BYTES = G2_BM * G2_BK * 2;            // 16 KB
+  static constexpr int B_BYTES = (BN / 2) * G2_BK * 2;         // this CTA's half of B
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"((uint32_t)NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"((uint32_t)NCOLS) : "memory");
+}
+// TMA load whose completion bytes are signalled on the LEADER CTA's mbarrier.
+__device__ __forceinline__ void tma_load_3d_2cta(const void* desc, uint64_t* bar_local_addr, void* smem_dst, int c0, int c1, int c2) {
+  const uint32_t bar = smem_u32(bar_local_addr) & PEER_BIT_MASK;
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit -> arrive on the barrier at the same smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  const uint16_t mask = 0x3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+// arrive on the leader CTA's copy of a barrier (works from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar_local_addr) {
+  const uint32_t bar = smem_u32(bar_local_addr) & PEER_BIT_MASK;
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
+                          int K, GemmEpilogue epi) {
+  using S = G2Smem<BN>;
+  constexpr int STAGES = S::STAGES;
+  constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  const int m_tiles = (M + 2 * G2_BM - 1) / (2 * G2_BM);
+  const int n_tiles = (N + BN - 1) / BN;
+  const int k_blocks = (K + G2_BK - 1) / G2_BK;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 2 * G2_EPI_WARPS);
+    }
+    fence_barrier_init();
+  } else if (warp_idx == 1) {
+    tmem_alloc_2cta<TMEM_COLS>(tmem_ptr_smem);
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barrier inits + TMEM allocation visible pair-wide before any remote arrive / multicast
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        const int m0 = (tile / n_tiles) * (2 * G2_BM) + (int)rank * G2_BM;
+        const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+          const int k0 = kb * G2_BK;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < G2_BM / 64; ++j)
+              tma_load_3d_2cta(&tmap_a, &full_bar[stage], sa + j * (G2_BK * 128), m0 + j * 64, k0, 0);
+          } else {
+            tma_load_3d_2cta(&tmap_a, &full_bar[stage], sa, k0, m0, 0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j)
+              tma_load_3d_2cta(&tmap_b, &full_bar[stage], sb + j * (G2_BK * 128), n0 + j * 64, k0, 0);
+          } else {
+            tma_load_3d_2cta(&tmap_b, &full_bar[stage], sb, k0, n0, 0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * G2_BM, BN, A_MN, B_MN);
+      constexpr uint32_t A_LBO = A_MN ? G2_BK * 128 : 16, B_LBO = B_MN ? G2_BK * 128 : 16;
+      constexpr uint32_t A_KSTEP = A_MN ? 2048 : 32, B_KSTEP = B_MN ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < G2_BK / 16; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * A_KSTEP, A_LBO, 1024);
+            const uint64_t db = make_smem_desc(sb + k * B_KSTEP, B_LBO, 1024);
+            umma_bf16_2cta(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2cta(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_2cta(&tmem_full_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..9), both CTAs: own 128 rows =====================
+    const int quad = warp_idx & 3;
+    const int half = (warp_idx - 2) >> 2;
+    constexpr int CHUNKS = BN / 32;
+    const int c_begin = half * (CHUNKS / 2), c_end = (half + 1) * (CHUNKS / 2);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+      const int m0 = (tile / n_tiles) * (2 * G2_BM) + (int)rank * G2_BM;
+      const int n0 = (tile % n_tiles) * BN;
+      GemmEpilogue e = epi;
+      if (e.p_drop > 0.f && e.offset_ptr) e.offset += __ldg(e.offset_ptr);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        epilogue_chunk(r, row, n0 + c * 32, M, N, e);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // nobody exits (or frees TMEM) while the peer may still multicast / read
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpilogue& epi,
+                        cudaStream_t stream) {
+  using S = G2Smem<BN>;
+  auto kern = gemm2_bf16_tcgen05_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (err != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm2 smem=%d): %s", S::TOTAL, cudaGetErrorString(err));
+      return -1;
+    }
+    attr_set = true;
+  }
+  const int m_tiles = (M + 2 * G2_BM - 1) / (2 * G2_BM), n_tiles = (N + BN - 1) / BN;
+  const long long tiles = (long long)m_tiles * n_tiles;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = (int)(tiles < max_pairs ? tiles : max_pairs);
+  kern<<<2 * pairs, G2_THREADS, S::TOTAL, stream>>>(ta, tb, M, N, K, epi);
+  return check_launch("gemm2_bf16_tcgen05");
+}
+
+// Entry used by vlm_gemm_bf16 for large non-batched problems.  bn in {128, 256}.
+int gemm2_dispatch(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, int M, int N, int K,
+                   int bn, const GemmEpilogue& e, cudaStream_t s) {
+  CUtensorMap ta, tb;
+  if (a_mn) {
+    if (make_tmap_bf16(&ta, a, (uint64_t)M, (uint64_t)K, 1, lda, 0, G2_BK)) return -1;
+  } else {
+    if (make_tmap_bf16(&ta, a, (uint64_t)K, (uint64_t)M, 1, lda, 0, G2_BM)) return -1;
+  }
+  if (b_mn) {
+    if (make_tmap_bf16(&tb, b, (uint64_t)N, (uint64_t)K, 1, ldb, 0, G2_BK)) return -1;
+  } else {
+    if (make_tmap_bf16(&tb, b, (uint64_t)K, (uint64_t)N, 1, ldb, 0, bn / 2)) return -1;
+  }
+#define G2_DISPATCH(BN_)                                                                 \
+  if (a_mn) {                                                                            \
+    if (b_mn) return launch_gemm2<BN_, true, true>(ta, tb, M, N, K, e, s);               \
+    return launch_gemm2<BN_, true, false>(ta, tb, M, N, K, e, s);                        \
+  } else {                                                                               \
+    if (b_mn) return launch_gemm2<BN_, false, true>(ta, tb, M, N, K, e, s);              \
+    return launch_gemm2<BN_, false, false>(ta, tb, M, N, K, e, s);                       \
+  }
+  if (bn == 128) { G2_DISPATCH(128) }
+  G2_DISPATCH(256)
+#undef G2_DISPATCH
+}
+
+}  // namespace vlm

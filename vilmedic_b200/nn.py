@@ -78,12 +78,23 @@ class LinearFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        dy = dy.contiguous()
-        if dy.dtype != torch.bfloat16:
-            dy = ops.cast_bf16(dy.float().contiguous())
+        dy = _bf16_rows(dy)
         _wgrad(dy, ctx.x, ctx.P)
         dx = _dgrad(dy, ctx.P)
         return dx, None, None, None
+
+
+def _bf16_rows(t):
+    """2-D bf16 tensor whose row pitch is a multiple of 8 elements (TMA needs 16-byte strides); zero padded."""
+    N = t.shape[-1]
+    if t.dtype == torch.bfloat16 and t.stride(-1) == 1 and t.stride(-2) % 8 == 0:
+        return t
+    if N % 8 == 0:
+        t = t.contiguous()
+        return t if t.dtype == torch.bfloat16 else ops.cast_bf16(t.float().contiguous())
+    buf = torch.zeros((t.shape[0], (N + 7) // 8 * 8), device=t.device, dtype=torch.bfloat16)
+    buf[:, :N] = t
+    return buf[:, :N]
 
 
 class LayerNormFn(torch.autograd.Function):

@@ -62,8 +62,12 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, out=None, out_dtype=torch.
     if batched:
         _req(b.shape[0] == batch, "batch mismatch")
     if out is None:
-        shape = (batch, M, N) if batched else (M, N)
+        al = 4 if out_dtype == torch.float32 else 8          # rows must stay 16-byte aligned
+        Np = (N + al - 1) // al * al
+        shape = (batch, M, Np) if batched else (M, Np)
         out = torch.empty(shape, device=a.device, dtype=out_dtype)
+        if Np != N:
+            out = out[..., :N]
     _req(out.is_cuda and out.dtype in (torch.bfloat16, torch.float32) and out.stride(-1) == 1, "bad gemm out")
     _req(tuple(out.shape[-2:]) == (M, N), "gemm out shape %s != (%d,%d)" % (tuple(out.shape), M, N))
     c_fp32 = out.dtype == torch.float32
