@@ -110,9 +110,10 @@ int vlm_features_mask(const void* feats, uint8_t* mask, int R, int D, void* stre
 /* z[r] = word[ids[r]] + pos[pos_offset + r % T]  (HF:bert_generation/modeling_bert_generation.py:410-429, pre-LN). */
 int vlm_embed_fwd(const long long* ids, const float* word, const float* pos, void* z, int R, int T, int D, int V,
                   int pos_offset, void* stream);
-/* scatter-add of dz into dword / dpos (fp32, atomics; either may be null). */
+/* scatter-add of dz into dword / dpos (fp32, atomics; either may be null); rows with id == padding_idx (< 0: none) get no
+ * gradient, as nn.Embedding(padding_idx=pad_token_id) in HF:bert_generation/modeling_bert_generation.py:400. */
 int vlm_embed_bwd(const long long* ids, const void* dz, float* dword, float* dpos, int R, int T, int D, int V,
-                  int pos_offset, void* stream);
+                  int pos_offset, int padding_idx, void* stream);
 /* y = x * keep / (1-p), keep ~ Philox(seed, offset, element); same call on grads is the backward.  n % 8 == 0. */
 int vlm_dropout_bf16(const void* x, void* y, long long n, float p, unsigned long long seed, unsigned long long offset,
                      const unsigned long long* rng_offset_ptr, void* stream);

@@ -134,8 +134,9 @@ def test_gemm_2cta_epilogue_and_repeat(cuda_dev):
     for _ in range(3):   # back-to-back launches exercise TMEM alloc/dealloc + barrier re-init across kernels
         h = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, aux_out=pre, force_bn=1256)
     torch.cuda.synchronize()
-    assert (pre.float() - pre_ref).abs().max().item() < 3e-2
-    assert (h.float() - torch.nn.functional.gelu(pre_ref)).abs().max().item() < 3e-2
+    assert ((pre.float() - pre_ref).abs() - 2 ** -8 * pre_ref.abs()).max().item() < 2e-3
+    gref = torch.nn.functional.gelu(pre_ref)
+    assert ((h.float() - gref).abs() - 2 ** -8 * gref.abs()).max().item() < 2e-3
     acc = torch.ones(N, K, device=cuda_dev)
     g = _rand((M, N), cuda_dev, 5)
     ops.gemm(g, a, a_mn_major=True, b_mn_major=True, out=acc, accumulate=True, force_bn=1128)   # wgrad layout

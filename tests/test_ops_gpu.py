@@ -219,6 +219,11 @@ def test_embed_colsum_mask_dropout_cast(cuda_dev):
     ops.embed_bwd(ids.view(-1), dz, dword, dpos, T, V)
     rw = torch.zeros_like(word).index_add_(0, ids.view(-1), dz.float())
     assert (dword - rw).abs().max().item() < 1e-3
+    pad = int(ids[0, 0])
+    dword2 = torch.zeros_like(word)
+    ops.embed_bwd(ids.view(-1), dz, dword2, None, T, V, padding_idx=pad)
+    rw[pad] = 0
+    assert (dword2 - rw).abs().max().item() < 1e-3 and dword2[pad].abs().sum().item() == 0
     assert (dpos[:T] - dz.float().view(B, T, D).sum(0)).abs().max().item() < 1e-3
     # colsum
     x = _bf((1001, 770), cuda_dev, 2)

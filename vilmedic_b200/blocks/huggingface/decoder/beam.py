@@ -6,9 +6,10 @@ Follows the loop the reference intends for bin/ensemble.py — vilmedic/blocks/h
   rank num_beams are skipped, finished hypotheses scored sum_logprobs / len**length_penalty), reorder by beam index.
 With one model and num_beams=1 this is greedy argmax decoding.
 
-Round-1 status: the model math runs on the sm_100a kernels (full-prefix recompute, no KV cache yet); the per-step
-selection (log_softmax / top-k / bookkeeping over [B*k, V] fp32 logits) is still torch glue — the fused
-log-softmax+top-2k step kernel and the cached single-token decoder step are the next items for this file.
+Round-1 status: the model math runs on the sm_100a kernels through the KV-cached single-token step
+(generation.DecodeState / decode_step; `use_cache=False` falls back to full-prefix recompute as a cross-check); the
+per-step selection (log_softmax / top-k / hypothesis bookkeeping over [B*k, V] fp32 logits) is still torch glue — the
+fused log-softmax+top-2k kernel is the next item for this file.
 """
 import torch
 
@@ -41,7 +42,7 @@ class _Hyps:
 
 @torch.no_grad()
 def beam_search(models, encs, masks, input_ids, max_length, num_beams, bos_token_id, eos_token_id, pad_token_id,
-                length_penalty=1.0):
+                length_penalty=1.0, use_cache=True):
     dev = input_ids.device
     B = input_ids.shape[0]
     k = num_beams
@@ -54,11 +55,23 @@ def beam_search(models, encs, masks, input_ids, max_length, num_beams, bos_token
     hyps = [_Hyps(k, length_penalty) for _ in range(B)]
     done = [False] * B
     cur_len = ids.shape[1]
+    states = None
+    if use_cache:
+        from .generation import DecodeState
+        states = [DecodeState(m, B * k, max_length, e, mk) for m, e, mk in zip(models, encs_k, masks_k)]
+        for t in range(cur_len - 1):                 # prime the caches with the prompt (normally just BOS: nothing to do)
+            for m, st in zip(models, states):
+                m.decode_step(st, ids[:, t])
     while cur_len < max_length:
         logits = None
-        for m, e, mk in zip(models, encs_k, masks_k):
-            l = m.next_token_logits(ids, e, mk)
-            logits = l if logits is None else logits + l
+        if states is not None:
+            for m, st in zip(models, states):
+                l = m.decode_step(st, ids[:, -1])
+                logits = l if logits is None else logits + l
+        else:
+            for m, e, mk in zip(models, encs_k, masks_k):
+                l = m.next_token_logits(ids, e, mk)
+                logits = l if logits is None else logits + l
         V = logits.shape[-1]
         scores = torch.log_softmax(logits.float(), dim=-1) + beam_scores[:, None]
         if k == 1:
@@ -102,6 +115,9 @@ def beam_search(models, encs, masks, input_ids, max_length, num_beams, bos_token
         beam_scores = new_scores.view(-1).to(dev)
         idx = new_idx.view(-1).to(dev)
         ids = torch.cat([ids[idx], new_tok.view(-1, 1).to(dev)], dim=1)
+        if states is not None:
+            for st in states:
+                st.reorder(idx)
         cur_len += 1
         if all(done):
             break

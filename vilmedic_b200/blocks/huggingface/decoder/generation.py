@@ -1,13 +1,100 @@
-"""Greedy / beam-search decoding for the B200 decoder tower — placeholder until the KV-cache step
-kernels land; `generate` re-runs the full prefix each step (correct, O(T^2)), selection logic follows HF
-GenerationMixin._beam_search / the reference's ensemble loop (vilmedic/blocks/huggingface/decoder/beam_search.py:222-342)."""
+"""Incremental decoding for the B200 decoder tower: a KV-cached single-token step built from
+the same kernels as training — per layer: q / kv projections (the kv GEMM writes straight into the cache slot of the
+current position), fused attention over the cached keys (T_q = 1), cross-attention over K/V projected ONCE per
+sequence, FFN; then the tied LM head on the last hidden state.  Mirrors HF's cached `generate` loop used by
+vilmedic/blocks/huggingface/decoder/evaluation.py:73-78.  HBM-bound by design: every step streams the decoder
+weights (275 MB bf16 at BERT-base) plus the KV cache.
+"""
 import torch
+
+from .... import ops
+from ....arena import get_arena
+from ....nn import _ln, _lin, _prepare, _root_of
+
+
+class DecodeState:
+    """Per-model decoding state for `rows` = batch * beams sequences."""
+
+    def __init__(self, tower, rows, max_len, enc, enc_mask):
+        cfg = tower.cfg
+        self.tower = tower
+        self.rows, self.max_len, self.t = rows, max_len, 0
+        D = cfg.hidden_size
+        dev = enc.device if enc is not None else next(tower.parameters()).device
+        self.arena = get_arena(_root_of(tower))
+        _prepare(self.arena, tower)
+        self.self_kv = [torch.empty((rows, max_len, 2 * D), device=dev, dtype=torch.bfloat16) for _ in tower._core.encoder.layer]
+        self.cross_kv = []
+        self.enc_mask = None
+        if enc is not None:
+            e = enc if enc.dtype == torch.bfloat16 else ops.cast_bf16(enc.float().contiguous())
+            Se = e.shape[1]
+            e2 = e.reshape(rows * Se, e.shape[2]).contiguous()
+            for layer in tower._core.encoder.layer:
+                ca = layer.crossattention.self
+                Pkv = _lin(self.arena, ca.key, ca.value)
+                self.cross_kv.append(ops.gemm(e2, Pkv.w, bias=Pkv.b).view(rows, Se, 2 * D))
+            if enc_mask is not None:
+                self.enc_mask = (enc_mask != 0).to(torch.uint8).contiguous()
+
+    def reorder(self, idx):
+        """Beam bookkeeping: row r continues hypothesis idx[r] (cache reorder of beam_search.py:317-319).  Cross K/V are
+        identical for all beams of a batch element, so only the self-attention cache moves."""
+        for i, kv in enumerate(self.self_kv):
+            self.self_kv[i] = kv.index_select(0, idx)
 
 
 class GenerationMixinB200:
     @torch.no_grad()
+    def decode_step(self, state, tokens):
+        """tokens int64 [rows] at position state.t -> fp32 next-token logits [rows, V]; advances the state."""
+        cfg = self.cfg
+        arena = state.arena
+        D, H = cfg.hidden_size, cfg.num_attention_heads
+        DH = D // H
+        eps = cfg.layer_norm_eps
+        R, t = state.rows, state.t
+        if t >= state.max_len:
+            raise IndexError("decode_step beyond max_len")
+        core = self._core
+        emb = core.embeddings
+        z = ops.embed_fwd(tokens.contiguous(), arena.fp32(emb.word_embeddings.weight), arena.fp32(emb.position_embeddings.weight), 1, t)
+        lnp = _ln(arena, emb.LayerNorm)
+        x, _, _ = ops.layernorm_fwd(z, lnp[0], lnp[1], eps, save_stats=False)
+        for li, layer in enumerate(core.encoder.layer):
+            sa = layer.attention
+            Pq = _lin(arena, sa.self.query)
+            Pkv = _lin(arena, sa.self.key, sa.self.value)
+            Po = _lin(arena, sa.output.dense)
+            ln1 = _ln(arena, sa.output.LayerNorm)
+            q = ops.gemm(x, Pq.w, bias=Pq.b)
+            kv = state.self_kv[li]
+            ops.gemm(x, Pkv.w, bias=Pkv.b, out=kv[:, t, :])
+            ctx, _ = ops.attention_fwd(q.view(R, 1, D), kv[:, :t + 1, :D], kv[:, :t + 1, D:], H, DH)
+            z1 = ops.gemm(ctx.view(R, D), Po.w, bias=Po.b, residual=x)
+            x1, _, _ = ops.layernorm_fwd(z1, ln1[0], ln1[1], eps, save_stats=False)
+            if state.cross_kv:
+                ca = layer.crossattention
+                Pqc, Poc = _lin(arena, ca.self.query), _lin(arena, ca.output.dense)
+                ln2 = _ln(arena, ca.output.LayerNorm)
+                ckv = state.cross_kv[li]
+                qc = ops.gemm(x1, Pqc.w, bias=Pqc.b)
+                ctx2, _ = ops.attention_fwd(qc.view(R, 1, D), ckv[:, :, :D], ckv[:, :, D:], H, DH, kmask=state.enc_mask)
+                z2 = ops.gemm(ctx2.view(R, D), Poc.w, bias=Poc.b, residual=x1)
+                x2, _, _ = ops.layernorm_fwd(z2, ln2[0], ln2[1], eps, save_stats=False)
+            else:
+                x2 = x1
+            P1, P2 = _lin(arena, layer.intermediate.dense), _lin(arena, layer.output.dense)
+            ln3 = _ln(arena, layer.output.LayerNorm)
+            h = ops.gemm(x2, P1.w, bias=P1.b, act=ops.ACT_GELU)
+            z3 = ops.gemm(h, P2.w, bias=P2.b, residual=x2)
+            x, _, _ = ops.layernorm_fwd(z3, ln3[0], ln3[1], eps, save_stats=False)
+        state.t += 1
+        return self.lm_logits(x)
+
+    @torch.no_grad()
     def next_token_logits(self, input_ids, encoder_hidden_states=None, encoder_attention_mask=None):
-        """fp32 logits [B, V] of the last position."""
+        """fp32 logits [B, V] of the last position by full-prefix recompute (no cache; used by tests as a cross-check)."""
         x, B, T = self.hidden_states(input_ids, None, encoder_hidden_states, encoder_attention_mask)
         last = x.view(B, T, -1)[:, -1].contiguous()
         return self.lm_logits(last)
@@ -15,7 +102,7 @@ class GenerationMixinB200:
     @torch.no_grad()
     def generate(self, input_ids=None, encoder_hidden_states=None, encoder_attention_mask=None, max_length=None,
                  num_beams=1, bos_token_id=None, eos_token_id=None, pad_token_id=None, length_penalty=1.0,
-                 ensemble=None, **kwargs):
+                 ensemble=None, use_cache=True, **kwargs):
         from .beam import beam_search
         models = [self] if ensemble is None else list(ensemble)
         enc = encoder_hidden_states if isinstance(encoder_hidden_states, (list, tuple)) else [encoder_hidden_states] * len(models)
@@ -25,4 +112,4 @@ class GenerationMixinB200:
                            bos_token_id=cfg.bos_token_id if bos_token_id is None else bos_token_id,
                            eos_token_id=cfg.eos_token_id if eos_token_id is None else eos_token_id,
                            pad_token_id=cfg.pad_token_id if pad_token_id is None else pad_token_id,
-                           length_penalty=length_penalty)
+                           length_penalty=length_penalty, use_cache=use_cache)

@@ -53,6 +53,9 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pr
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // A [ROWS x DH] bf16 tile in shared memory; row pitch DH+8 elements (16 B pad -> conflict-free ldmatrix).
 template <int ROWS, int DH>
@@ -83,10 +86,12 @@ template <int DH>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnParams p) {
   constexpr int KS = DH / 16;   // k-steps over the head dim
   constexpr int NT = DH / 8;    // n-tiles of the output
+  constexpr int NBUF = (DH <= 64) ? 2 : 1;   // K/V blocks are double-buffered (cp.async prefetch) when they fit 48 KB
   __shared__ __align__(16) Tile<64, DH> sQ;
-  __shared__ __align__(16) Tile<64, DH> sK;
-  __shared__ __align__(16) Tile<64, DH> sV;
-  __shared__ uint8_t sMask[64];
+  __shared__ __align__(16) Tile<64, DH> sKb[NBUF];
+  __shared__ __align__(16) Tile<64, DH> sVb[NBUF];
+  __shared__ uint8_t sMaskb[NBUF][64];
+  __shared__ int sFull[NBUF][2];
 
   const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
   const int q0 = blockIdx.x * 64;
@@ -117,16 +122,36 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnParams p) {
 
   int k_end = p.Sk;
   if (p.causal) k_end = min(p.Sk, q0 + 64);
-  for (int k0 = 0; k0 < k_end; k0 += 64) {
-    __syncthreads();  // previous iteration's readers done
-    sK.load_async(kb, p.k_rs, k0, p.Sk);
-    sV.load_async(vb, p.v_rs, k0, p.Sk);
+  const int nblk = (k_end + 63) / 64;
+  auto issue = [&](int blk, int buf) {
+    const int kk0 = blk * 64;
+    sKb[buf].load_async(kb, p.k_rs, kk0, p.Sk);
+    sVb[buf].load_async(vb, p.v_rs, kk0, p.Sk);
     if (threadIdx.x < 64) {
-      const int kk = k0 + threadIdx.x;
-      sMask[threadIdx.x] = (kk < p.Sk) && (!p.kmask || p.kmask[(long long)b * p.Sk + kk]);
+      const int kk = kk0 + threadIdx.x;
+      const bool ok = (kk < p.Sk) && (!p.kmask || p.kmask[(long long)b * p.Sk + kk]);
+      sMaskb[buf][threadIdx.x] = ok;
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) sFull[buf][warp] = (bal == 0xffffffffu);
     }
-    cp_async_wait_all();
+    cp_async_commit();
+  };
+  if (NBUF == 2 && nblk > 0) issue(0, 0);
+  for (int it = 0; it < nblk; ++it) {
+    const int k0 = it * 64;
+    const int cur = (NBUF == 2) ? (it & 1) : 0;
+    if (NBUF == 2) {
+      if (it + 1 < nblk) { issue(it + 1, cur ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    } else {
+      issue(it, 0);
+      cp_async_wait<0>();
+    }
     __syncthreads();
+    Tile<64, DH>& sK = sKb[cur];
+    Tile<64, DH>& sV = sVb[cur];
+    const uint8_t* sMask = sMaskb[cur];
+    // whole block attendable (no padding, not on / above the causal diagonal) -> predicate-free fast path
+    const bool nomask = sFull[cur][0] && sFull[cur][1] && (!p.causal || (k0 + 63 <= q0));
 
     float s[8][4];
 #pragma unroll
@@ -144,16 +169,27 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnParams p) {
     }
     // mask + running max
     float m_new[2] = {m_run[0], m_run[1]};
+    if (nomask) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int kc = nt * 8 + 2 * t + (e & 1);
-        const int r = e >> 1;
-        bool ok = sMask[kc];
-        if (p.causal) ok = ok && (k0 + kc <= qrow[r]);
-        s[nt][e] = ok ? s[nt][e] * sl2 : -INFINITY;
-        m_new[r] = fmaxf(m_new[r], s[nt][e]);
+        for (int e = 0; e < 4; ++e) {
+          s[nt][e] *= sl2;
+          m_new[e >> 1] = fmaxf(m_new[e >> 1], s[nt][e]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int kc = nt * 8 + 2 * t + (e & 1);
+          const int r = e >> 1;
+          bool ok = sMask[kc];
+          if (p.causal) ok = ok && (k0 + kc <= qrow[r]);
+          s[nt][e] = ok ? s[nt][e] * sl2 : -INFINITY;
+          m_new[r] = fmaxf(m_new[r], s[nt][e]);
+        }
       }
     }
 #pragma unroll
@@ -211,6 +247,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnParams p) {
         mma_bf16_16816(o_acc[2 * np + 1], pf[j], vf + 2);
       }
     }
+    __syncthreads();  // everyone is done with buffer `cur` before the next prefetch overwrites it
   }
   // finalize: l over the 4 lanes of a row quad
 #pragma unroll
@@ -241,10 +278,12 @@ template <int DH>
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnParams p) {
   constexpr int KS = DH / 16;
   constexpr int NT = DH / 8;
+  constexpr int NBUF = (DH <= 64) ? 2 : 1;
   __shared__ __align__(16) Tile<64, DH> sDO;  // holds Q first (fragments go to registers), then dO
-  __shared__ __align__(16) Tile<64, DH> sK;
-  __shared__ __align__(16) Tile<64, DH> sV;
-  __shared__ uint8_t sMask[64];
+  __shared__ __align__(16) Tile<64, DH> sKb[NBUF];
+  __shared__ __align__(16) Tile<64, DH> sVb[NBUF];
+  __shared__ uint8_t sMaskb[NBUF][64];
+  __shared__ int sFull[NBUF][2];
 
   const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
   const int q0 = blockIdx.x * 64;
@@ -297,16 +336,36 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnParams p) {
 
   int k_end = p.Sk;
   if (p.causal) k_end = min(p.Sk, q0 + 64);
-  for (int k0 = 0; k0 < k_end; k0 += 64) {
-    __syncthreads();
-    sK.load_async(kb, p.k_rs, k0, p.Sk);
-    sV.load_async(vb, p.v_rs, k0, p.Sk);
+  const int nblk = (k_end + 63) / 64;
+  auto issue = [&](int blk, int buf) {
+    const int kk0 = blk * 64;
+    sKb[buf].load_async(kb, p.k_rs, kk0, p.Sk);
+    sVb[buf].load_async(vb, p.v_rs, kk0, p.Sk);
     if (threadIdx.x < 64) {
-      const int kk = k0 + threadIdx.x;
-      sMask[threadIdx.x] = (kk < p.Sk) && (!p.kmask || p.kmask[(long long)b * p.Sk + kk]);
+      const int kk = kk0 + threadIdx.x;
+      const bool ok = (kk < p.Sk) && (!p.kmask || p.kmask[(long long)b * p.Sk + kk]);
+      sMaskb[buf][threadIdx.x] = ok;
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) sFull[buf][warp] = (bal == 0xffffffffu);
     }
-    cp_async_wait_all();
+    cp_async_commit();
+  };
+  __syncthreads();  // the delta pass above read sDO; K/V buffers are free
+  if (NBUF == 2 && nblk > 0) issue(0, 0);
+  for (int it = 0; it < nblk; ++it) {
+    const int k0 = it * 64;
+    const int cur = (NBUF == 2) ? (it & 1) : 0;
+    if (NBUF == 2) {
+      if (it + 1 < nblk) { issue(it + 1, cur ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    } else {
+      issue(it, 0);
+      cp_async_wait<0>();
+    }
     __syncthreads();
+    Tile<64, DH>& sK = sKb[cur];
+    Tile<64, DH>& sV = sVb[cur];
+    const uint8_t* sMask = sMaskb[cur];
+    const bool nomask = sFull[cur][0] && sFull[cur][1] && (!p.causal || (k0 + 63 <= q0)) && (q0 + 64 <= p.Tq);
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -334,8 +393,11 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnParams p) {
       for (int e = 0; e < 4; ++e) {
         const int kc = nt * 8 + 2 * t + (e & 1);
         const int r = e >> 1;
-        bool ok = sMask[kc] && (qrow[r] < p.Tq);
-        if (p.causal) ok = ok && (k0 + kc <= qrow[r]);
+        bool ok = true;
+        if (!nomask) {
+          ok = sMask[kc] && (qrow[r] < p.Tq);
+          if (p.causal) ok = ok && (k0 + kc <= qrow[r]);
+        }
         const float pe = ok ? exp2f(s[nt][e] * sl2 - lse[r]) : 0.f;
         float dpe = dp[nt][e];
         if (p.p_drop > 0.f) {
@@ -360,6 +422,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnParams p) {
         mma_bf16_16816(dq_acc[2 * np + 1], dsf[j], kf + 2);
       }
     }
+    __syncthreads();
   }
   bf16* dqb = p.dq + (long long)b * p.dq_bs + h * DH;
 #pragma unroll
@@ -380,9 +443,10 @@ template <int DH>
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
   constexpr int KS = DH / 16;
   constexpr int NT = DH / 8;
-  __shared__ __align__(16) Tile<64, DH> sQ;   // holds K first (fragments go to registers), then Q blocks
-  __shared__ __align__(16) Tile<64, DH> sDO;  // holds V first, then dO blocks
-  __shared__ float sLse[64], sDelta[64];
+  constexpr int NBUF = (DH <= 64) ? 2 : 1;
+  __shared__ __align__(16) Tile<64, DH> sQb[NBUF];   // buffer 0 holds K first (fragments go to registers), then Q blocks
+  __shared__ __align__(16) Tile<64, DH> sDOb[NBUF];  // buffer 0 holds V first, then dO blocks
+  __shared__ float sLseb[NBUF][64], sDeltab[NBUF][64];
 
   const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
   const int k0 = blockIdx.x * 64;
@@ -393,16 +457,17 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
   const bf16* vb = p.v + (long long)b * p.v_bs + h * DH;
   const bf16* dob = p.d_o + (long long)b * p.do_bs + h * DH;
 
-  sQ.load_async(kb, p.k_rs, k0, p.Sk);
-  sDO.load_async(vb, p.v_rs, k0, p.Sk);
+  sQb[0].load_async(kb, p.k_rs, k0, p.Sk);
+  sDOb[0].load_async(vb, p.v_rs, k0, p.Sk);
   cp_async_wait_all();
   __syncthreads();
   uint32_t kf[KS][4], vf[KS][4];
 #pragma unroll
   for (int kk = 0; kk < KS; ++kk) {
-    ldsm_x4(kf[kk], sQ.at(warp * 16 + (lane & 15), kk * 16 + (lane >> 4) * 8));
-    ldsm_x4(vf[kk], sDO.at(warp * 16 + (lane & 15), kk * 16 + (lane >> 4) * 8));
+    ldsm_x4(kf[kk], sQb[0].at(warp * 16 + (lane & 15), kk * 16 + (lane >> 4) * 8));
+    ldsm_x4(vf[kk], sDOb[0].at(warp * 16 + (lane & 15), kk * 16 + (lane >> 4) * 8));
   }
+  __syncthreads();  // K/V fragments are in registers: buffer 0 may be refilled with Q / dO blocks
   const int krow[2] = {k0 + warp * 16 + g, k0 + warp * 16 + g + 8};
   bool kok[2];
 #pragma unroll
@@ -423,17 +488,36 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
 
   int q_begin = 0;
   if (p.causal) q_begin = (k0 / 64) * 64;  // queries before this key block never attend to it
-  for (int q0 = q_begin; q0 < p.Tq; q0 += 64) {
-    __syncthreads();
-    sQ.load_async(qb, p.q_rs, q0, p.Tq);
-    sDO.load_async(dob, p.do_rs, q0, p.Tq);
+  const int nblk = (p.Tq - q_begin + 63) / 64;
+  auto issue = [&](int blk, int buf) {
+    const int qq0 = q_begin + blk * 64;
+    sQb[buf].load_async(qb, p.q_rs, qq0, p.Tq);
+    sDOb[buf].load_async(dob, p.do_rs, qq0, p.Tq);
     if (threadIdx.x < 64) {
-      const int qq = q0 + threadIdx.x;
-      sLse[threadIdx.x] = qq < p.Tq ? p.lse[(long long)bh * p.Tq + qq] * 1.4426950408889634f : INFINITY;
-      sDelta[threadIdx.x] = qq < p.Tq ? p.delta[(long long)bh * p.Tq + qq] : 0.f;
+      const int qq = qq0 + threadIdx.x;
+      sLseb[buf][threadIdx.x] = qq < p.Tq ? p.lse[(long long)bh * p.Tq + qq] * 1.4426950408889634f : INFINITY;
+      sDeltab[buf][threadIdx.x] = qq < p.Tq ? p.delta[(long long)bh * p.Tq + qq] : 0.f;
     }
-    cp_async_wait_all();
+    cp_async_commit();
+  };
+  const bool keys_ok = __all_sync(0xffffffffu, kok[0] && kok[1]);
+  if (NBUF == 2 && nblk > 0) issue(0, 0);
+  for (int it = 0; it < nblk; ++it) {
+    const int q0 = q_begin + it * 64;
+    const int cur = (NBUF == 2) ? (it & 1) : 0;
+    if (NBUF == 2) {
+      if (it + 1 < nblk) { issue(it + 1, cur ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    } else {
+      issue(it, 0);
+      cp_async_wait<0>();
+    }
     __syncthreads();
+    Tile<64, DH>& sQ = sQb[cur];
+    Tile<64, DH>& sDO = sDOb[cur];
+    const float* sLse = sLseb[cur];
+    const float* sDelta = sDeltab[cur];
+    // rows beyond Tq carry lse = +inf (probability 0), so only key validity and the causal diagonal need predicates
+    const bool nomask = keys_ok && (!p.causal || (q0 >= k0 + 63));
     // S^T[key, query] and dP^T[key, query]
     float st[8][4], dpt[8][4];
 #pragma unroll
@@ -463,8 +547,11 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
         const int qc = nt * 8 + 2 * t + (e & 1);  // query column within the block
         const int r = e >> 1;                     // key row
         const int qq = q0 + qc;
-        bool ok = kok[r] && (qq < p.Tq);
-        if (p.causal) ok = ok && (krow[r] <= qq);
+        bool ok = true;
+        if (!nomask) {
+          ok = kok[r] && (qq < p.Tq);
+          if (p.causal) ok = ok && (krow[r] <= qq);
+        }
         float pv = ok ? exp2f(st[nt][e] * sl2 - sLse[qc]) : 0.f;
         float dpe = dpt[nt][e];
         float pdrop = pv;
@@ -498,6 +585,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
         mma_bf16_16816(dk_acc[2 * np + 1], dstf[j], bq + 2);
       }
     }
+    __syncthreads();
   }
   bf16* dkb = p.dk + (long long)b * p.dk_bs + h * DH;
   bf16* dvb = p.dv + (long long)b * p.dv_bs + h * DH;

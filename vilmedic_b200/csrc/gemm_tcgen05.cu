@@ -395,7 +395,15 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
       bound_dev = dev;
     }
   }
-  const int bn = pick_bn(M, N, batch, force_bn >= 1000 ? 0 : force_bn);
+  // split-K candidates (weight gradients: fp32 C accumulated in place, K = number of tokens) prefer wide N tiles and
+  // fill the machine along K instead of shrinking the tile.
+  const bool splitk_ok = c_is_fp32 && accumulate && act == 0 && p_drop == 0.f && !residual && batch == 1 && K >= 1024;
+  int bn = pick_bn(M, N, batch, force_bn >= 1000 ? 0 : force_bn);
+  if (splitk_ok && force_bn == 0) {
+    const int wide = N >= 192 ? 256 : (N >= 96 ? 128 : 64);
+    const long long tiles_wide = (long long)((M + GEMM_BM - 1) / GEMM_BM) * ((N + wide - 1) / wide);
+    if (tiles_wide < num_sms()) bn = wide;
+  }
   const int bn2 = pick_2cta(M, N, K, batch, force_bn, bn);
   VLM_REQUIRE(bn2 == 0 || bn2 == 128 || bn2 == 256, "vlm_gemm_bf16: 2-CTA N tile must be 128 or 256");
   CUtensorMap ta, tb;
@@ -437,13 +445,13 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
   // semantics, atomics in the epilogue.
   int split_k = 1;
   e.atomic = 0;
-  if (bn2 == 0 && c_is_fp32 && accumulate && act == 0 && p_drop == 0.f && !residual) {
-    const long long tiles = (long long)((M + GEMM_BM - 1) / GEMM_BM) * ((N + bn - 1) / bn) * batch;
+  if (bn2 == 0 && splitk_ok) {
+    const long long tiles = (long long)((M + GEMM_BM - 1) / GEMM_BM) * ((N + bn - 1) / bn);
     const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
     const int sms = num_sms();
-    if (tiles * 2 <= sms && k_blocks >= 16) {
-      split_k = (int)((sms + tiles - 1) / tiles);
-      if (split_k > k_blocks / 8) split_k = k_blocks / 8;
+    if (tiles * 2 <= sms) {
+      split_k = (int)(sms / tiles);
+      if (split_k > k_blocks / 4) split_k = k_blocks / 4;
       if (split_k < 1) split_k = 1;
     }
     e.atomic = split_k > 1;

@@ -147,7 +147,7 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float*
 
 // dword[ids[r],:] += dz[r,:] ; dpos[pos_offset + r % T,:] += dz[r,:]
 __global__ void embed_bwd_kernel(const long long* __restrict__ ids, const bf16* __restrict__ dz, float* __restrict__ dword,
-                                 float* __restrict__ dpos, int R, int T, int D, int V, int pos_offset) {
+                                 float* __restrict__ dpos, int R, int T, int D, int V, int pos_offset, int padding_idx) {
   const int nvec = D / 2;
   const long long total = (long long)R * nvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -156,7 +156,7 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ ids, const bf16* 
     long long id = ids[r];
     if (id < 0 || id >= V) id = 0;
     const float2 g = unpack_bf16x2(reinterpret_cast<const uint32_t*>(dz)[i]);
-    if (dword) {
+    if (dword && id != padding_idx) {  // nn.Embedding(padding_idx=...) never accumulates into the padding row
       atomicAdd(dword + (size_t)id * D + v * 2, g.x);
       atomicAdd(dword + (size_t)id * D + v * 2 + 1, g.y);
     }
@@ -295,9 +295,9 @@ extern "C" int vlm_embed_fwd(const long long* ids, const float* word, const floa
 }
 
 extern "C" int vlm_embed_bwd(const long long* ids, const void* dz, float* dword, float* dpos, int R, int T, int D, int V,
-                             int pos_offset, void* stream) {
+                             int pos_offset, int padding_idx, void* stream) {
   VLM_REQUIRE(ids && dz && R > 0 && T > 0 && D % 2 == 0 && V > 0, "vlm_embed_bwd: bad args");
-  embed_bwd_kernel<<<grid_for((long long)R * D / 2, 256), 256, 0, (cudaStream_t)stream>>>(ids, (const bf16*)dz, dword, dpos, R, T, D, V, pos_offset);
+  embed_bwd_kernel<<<grid_for((long long)R * D / 2, 256), 256, 0, (cudaStream_t)stream>>>(ids, (const bf16*)dz, dword, dpos, R, T, D, V, pos_offset, padding_idx);
   return check_launch("embed_bwd");
 }
 

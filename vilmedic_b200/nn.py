@@ -440,8 +440,9 @@ class BertEmbedFn(torch.autograd.Function):
         ids, z, mean, rstd, lnp, emb, arena, T, pos_offset = ctx.saved
         dz = ops.layernorm_bwd(dy.contiguous(), z, mean, rstd, lnp[0], lnp[2], lnp[3])
         V = emb.word_embeddings.weight.shape[0]
+        pad = emb.word_embeddings.padding_idx
         ops.embed_bwd(ids, dz, arena.grad(emb.word_embeddings.weight), arena.grad(emb.position_embeddings.weight), T, V,
-                      pos_offset)
+                      pos_offset, -1 if pad is None else int(pad))
         return None, None, None, None, None, None, None
 
 

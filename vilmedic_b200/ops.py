@@ -250,11 +250,11 @@ def embed_fwd(ids, word, pos, T, pos_offset=0):
     return z
 
 
-def embed_bwd(ids, dz, dword, dpos, T, V, pos_offset=0):
+def embed_bwd(ids, dz, dword, dpos, T, V, pos_offset=0, padding_idx=-1):
     R, D = dz.shape
     _req(dz.is_contiguous() and dz.dtype == torch.bfloat16, "embed_bwd: dz contiguous bf16")
     check(_L().vlm_embed_bwd(ptr(ids), ptr(dz), ptr(dword), ptr(dpos), c_int(R), c_int(T), c_int(D), c_int(V),
-                             c_int(pos_offset), stream_ptr()), "vlm_embed_bwd")
+                             c_int(pos_offset), c_int(padding_idx), stream_ptr()), "vlm_embed_bwd")
 
 
 def dropout(x, p, seed, offset, out=None):
