@@ -55,10 +55,14 @@ int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, l
  * 288-292,410-429.  D % 8 == 0, D <= 2048. */
 int vlm_layernorm_fwd(const void* x, int x_is_fp32, const float* gamma, const float* beta, void* y, float* mean,
                       float* rstd, int M, int D, float eps, void* stream);
-/* dx = LN'(dy) (+ dres), dtype of x; dgamma/dbeta (fp32 [D]) are ACCUMULATED with atomics (caller zeroes). */
+/* dx = LN'(dy) (+ dres), dtype of x; dgamma/dbeta (fp32 [D]) are ACCUMULATED with atomics (caller zeroes).
+ * Fused extras (all optional): dx_drop = dropout(dx) with the same Philox stream as the forward GEMM epilogue that
+ * produced the LN input (p_drop, seed, offset, rng_offset_ptr); colsum[D] += column sums of dx_drop (or dx) — the
+ * bias gradient of the Linear whose output fed this LayerNorm. */
 int vlm_layernorm_bwd(const void* dy, const void* x, int x_is_fp32, const float* mean, const float* rstd,
                       const float* gamma, const void* dres, void* dx, float* dgamma, float* dbeta, int M, int D,
-                      void* stream);
+                      void* dx_drop, float p_drop, unsigned long long seed, unsigned long long offset,
+                      const unsigned long long* rng_offset_ptr, float* colsum, void* stream);
 
 /* ---- attention -------------------------------------------------------------------------------------------------- */
 /* O = softmax(scale * Q K^T + mask) V per (batch, head); bf16 in/out, fp32 softmax.  q/k/v/o are addressed as

@@ -44,8 +44,10 @@ class _Hyps:
 
 
 @torch.no_grad()
-def ensemble_beam_search(decoders, encs, masks, num_beams, max_length, bos, eos, pad, length_penalty=1.0):
-    """Sum-of-logits ensemble beam search (beam_search.py:243-320); greedy when num_beams == 1."""
+def ensemble_beam_search(decoders, encs, masks, num_beams, max_length, bos, eos, pad, length_penalty=1.0, gaps=None):
+    """Sum-of-logits ensemble beam search (beam_search.py:243-320); greedy when num_beams == 1.
+    gaps: optional list that receives, per step, the smallest score gap between adjacent candidates among the top
+    2k+1 (k>1) or top-2 (greedy) — how close the fp32 search came to a tie (tests use it to qualify bit-exactness)."""
     B, k = encs[0].shape[0], num_beams
     ids = torch.full((B * k, 1), bos, dtype=torch.long)
     encs = [e.repeat_interleave(k, 0) for e in encs]
@@ -60,6 +62,20 @@ def ensemble_beam_search(decoders, encs, masks, num_beams, max_length, bos, eos,
         logits = sum(next_logits(d, ids, e, m) for d, e, m in zip(decoders, encs, masks))        # :254
         lp = torch.log_softmax(logits, -1) + scores[:, None]                                     # :260-265
         V = lp.shape[-1]
+        if gaps is not None:
+            # distance to a different search decision: greedy = top-1 vs top-2; beam = the k-th kept non-EOS
+            # candidate vs the first one left out (a bf16 implementation may legitimately flip closer calls)
+            for b in range(B):
+                if done[b]:
+                    continue
+                if k == 1:
+                    top = torch.topk(lp[b], 2).values
+                    gaps.append(float(top[0] - top[1]))
+                else:
+                    ts_, ti_ = torch.topk(lp.view(B, k * V)[b], min(2 * k + 2, k * V))
+                    keep = [float(v) for v, i in zip(ts_, ti_) if int(i) % V != eos and float(v) > -1e8]
+                    if len(keep) > k:
+                        gaps.append(keep[k - 1] - keep[k])
         if k == 1:
             s, t = lp.max(-1)
             t = torch.where(torch.tensor(done), torch.full_like(t, pad), t)

@@ -243,3 +243,46 @@ def test_grad_sync_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+# ------------------------------------------------------------------------------------------------ beam-search logic
+class _OracleAsModel:
+    """Adapter: lets the product's beam_search drive ORACLE logits, so the selection logic is compared on identical numbers."""
+
+    def __init__(self, decoder):
+        self.d = decoder
+
+    def next_token_logits(self, ids, enc, mask):
+        from oracle.decode import next_logits
+        return next_logits(self.d, ids, enc, mask)
+
+
+@pytest.mark.parametrize("k,n_models", [(1, 1), (3, 1), (4, 2)])
+def test_beam_search_logic_matches_oracle_and_hf(k, n_models):
+    from oracle import decode
+    from oracle.rrg import OracleRRG
+    from vilmedic_b200 import synth
+    from vilmedic_b200.blocks.huggingface.decoder.beam import beam_search
+    refs = []
+    for s in range(n_models):
+        torch.manual_seed(s)
+        dec = synth.bert_base_decoder(vocab=120, layers=1, dropout=0.0)
+        cnn = dict(backbone="vit", permute="no_permute", **dict(synth.vit_b16(), num_hidden_layers=1, hidden_size=128,
+                                                                  num_attention_heads=2, intermediate_size=256))
+        dec["hidden_size"], dec["num_attention_heads"], dec["intermediate_size"] = 128, 2, 256
+        m = OracleRRG(dec, cnn).eval()
+        with torch.no_grad():
+            m.dec.decoder.bert.embeddings.word_embeddings.weight.mul_(40.0)
+            m.dec.decoder.bert.embeddings.word_embeddings.weight[2].mul_(2.0)   # make EOS competitive: exercises finished hyps
+        refs.append(m)
+    batch = synth.rrg_batch(3, 8, 120, seed=4)
+    encs, masks = zip(*[m.enc.encode(batch["images"]) for m in refs])
+    want = decode.ensemble_beam_search([m.dec.decoder for m in refs], list(encs), list(masks), k, 10, 0, 2, 1)
+    got = beam_search([_OracleAsModel(m.dec.decoder) for m in refs], list(encs), list(masks),
+                      input_ids=torch.zeros((3, 1), dtype=torch.long), max_length=10, num_beams=k, bos_token_id=0,
+                      eos_token_id=2, pad_token_id=1, use_cache=False)
+    assert got.shape == want.shape and torch.equal(got, want)
+    if n_models == 1:
+        hf = decode.hf_generate(refs[0].dec.decoder, encs[0], masks[0], k, 10, 0, 2, 1)
+        L = min(hf.shape[1], want.shape[1])
+        assert torch.equal(want[:, :L], hf[:, :L])

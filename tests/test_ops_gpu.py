@@ -350,3 +350,27 @@ def test_label_smoothing_module(cuda_dev):
     torch.cuda.synchronize()
     assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item()) + 1e-6
     assert (xc.grad.cpu() - xr.grad).abs().max().item() < 1e-6
+
+
+def test_layernorm_bwd_fused_dropout_and_colsum(cuda_dev):
+    """LN backward with the dropout mask of the forward GEMM epilogue and the bias-gradient column sums fused in."""
+    from vilmedic_b200 import ops
+    M, D = 300, 768
+    x, dy = _bf((M, D), cuda_dev, 1, 2.0), _bf((M, D), cuda_dev, 2)
+    gamma, beta = torch.rand(D, device=cuda_dev) + 0.5, torch.zeros(D, device=cuda_dev)
+    _, mean, rstd = ops.layernorm_fwd(x, gamma, beta, 1e-12)
+    dg, db, cs = (torch.zeros(D, device=cuda_dev) for _ in range(3))
+    dx, dxd = ops.layernorm_bwd(dy, x, mean, rstd, gamma, dg, db, drop=(0.1, 11, 5), colsum=cs)
+    dg2, db2 = torch.zeros(D, device=cuda_dev), torch.zeros(D, device=cuda_dev)
+    dx_plain = ops.layernorm_bwd(dy, x, mean, rstd, gamma, dg2, db2)
+    torch.cuda.synchronize()
+    assert torch.equal(dx, dx_plain)
+    ref_drop = ops.dropout(dx_plain, 0.1, 11, 5)            # same Philox stream as the GEMM epilogue / dropout kernel
+    keep = ref_drop != 0
+    assert torch.equal(dxd != 0, keep)
+    assert (dxd.float() - ref_drop.float()).abs().max().item() <= 2 ** -7 * ref_drop.float().abs().max().item()
+    assert (cs - dxd.float().sum(0)).abs().max().item() < 5e-2
+    # and the forward epilogue uses the same mask
+    a, w = _bf((M, 64), cuda_dev, 3), _bf((D, 64), cuda_dev, 4)
+    y = ops.gemm(a, w, p_drop=0.1, seed=11, offset=5)
+    assert torch.equal(y != 0, keep | (y != 0)) and ((y == 0) & keep).float().mean().item() < 1e-3

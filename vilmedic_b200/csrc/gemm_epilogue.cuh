@@ -32,8 +32,13 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int
   if (row >= M || col0 >= N) return;
   float v[32];
   const float alpha = e.alpha_ptr ? e.alpha * __ldg(e.alpha_ptr) : e.alpha;
+  if (alpha != 1.0f) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * alpha;
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * alpha;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  }
 
   const bool full = (col0 + 32 <= N);
   if (full) {

@@ -97,14 +97,21 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const TIn* __restrict__ dres,
                                                             TIn* __restrict__ dx, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, int M, int D) {
+                                                            float* __restrict__ dbeta, int M, int D, TIn* __restrict__ dx_drop,
+                                                            float p_drop, unsigned long long seed, unsigned long long offset,
+                                                            const unsigned long long* __restrict__ offset_ptr,
+                                                            float* __restrict__ colsum) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D >> 3;
-  float dg[NV][8], db[NV][8];
+  float dg[NV][8], db[NV][8], cs[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = cs[i][j] = 0.f;
+  const Philox rng(seed);
+  if (dx_drop && offset_ptr) offset += __ldg(offset_ptr);
+  const uint32_t thr = (uint32_t)(p_drop * 4294967296.0f);
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
 
   for (int row = blockIdx.x * 4 + warp; row < M; row += gridDim.x * 4) {
     const TIn* xr = x + (size_t)row * D;
@@ -147,26 +154,41 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
           for (int j = 0; j < 8; ++j) o[j] += r[j];
         }
         Vec8<TIn>::store(dxr + vi * 8, o);
+        if (dx_drop) {
+          // same Philox stream as the GEMM epilogue / vlm_dropout_bf16 on the flat [M, D] tensor
+          const unsigned long long base = ((unsigned long long)row * (unsigned long long)D + (unsigned long long)vi * 8ull) >> 2;
+          const uint4 r0 = rng(base, offset), r1 = rng(base + 1, offset);
+          o[0] = r0.x >= thr ? o[0] * inv_keep : 0.f; o[1] = r0.y >= thr ? o[1] * inv_keep : 0.f;
+          o[2] = r0.z >= thr ? o[2] * inv_keep : 0.f; o[3] = r0.w >= thr ? o[3] * inv_keep : 0.f;
+          o[4] = r1.x >= thr ? o[4] * inv_keep : 0.f; o[5] = r1.y >= thr ? o[5] * inv_keep : 0.f;
+          o[6] = r1.z >= thr ? o[6] * inv_keep : 0.f; o[7] = r1.w >= thr ? o[7] * inv_keep : 0.f;
+          Vec8<TIn>::store(dx_drop + (size_t)row * D + vi * 8, o);
+        }
+        if (colsum) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cs[i][j] += o[j];
+        }
       }
     }
   }
 
   // cross-warp reduction of the column partials, then one atomic per column per CTA
   __shared__ float red[4][256];
-#pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
+  const int npass = colsum ? 3 : 2;
+#pragma unroll 1
+  for (int pass = 0; pass < npass; ++pass) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? dg[i][j] : db[i][j];
+      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? dg[i][j] : (pass == 1 ? db[i][j] : cs[i][j]);
       __syncthreads();
       // 256 columns of this vector slot: thread t sums columns t and t+128
       for (int c = threadIdx.x; c < 256; c += 128) {
         const int vi = (c >> 3) + 32 * i;  // vector index within the row
         if (vi < nvec) {
           const float tot = red[0][c] + red[1][c] + red[2][c] + red[3][c];
-          float* dst = (pass == 0 ? dgamma : dbeta);
+          float* dst = (pass == 0 ? dgamma : (pass == 1 ? dbeta : colsum));
           if (dst) atomicAdd(dst + vi * 8 + (c & 7), tot);
         }
       }
@@ -195,11 +217,13 @@ static int ln_fwd_dispatch(const TIn* x, const float* gamma, const float* beta, 
 
 template <typename TIn>
 static int ln_bwd_dispatch(const bf16* dy, const TIn* x, const float* mean, const float* rstd, const float* gamma,
-                           const TIn* dres, TIn* dx, float* dgamma, float* dbeta, int M, int D, cudaStream_t s) {
+                           const TIn* dres, TIn* dx, float* dgamma, float* dbeta, int M, int D, TIn* dx_drop, float p_drop,
+                           unsigned long long seed, unsigned long long offset, const unsigned long long* offset_ptr,
+                           float* colsum, cudaStream_t s) {
   const int nv = (D / 8 + 31) / 32;
   int grid = num_sms() * 4;
   if (grid > (M + 3) / 4) grid = (M + 3) / 4;
-#define LN_BWD(NV_) layernorm_bwd_kernel<TIn, NV_><<<grid, 128, 0, s>>>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, M, D)
+#define LN_BWD(NV_) layernorm_bwd_kernel<TIn, NV_><<<grid, 128, 0, s>>>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, M, D, dx_drop, p_drop, seed, offset, offset_ptr, colsum)
   switch (nv) {
     case 1: LN_BWD(1); break;
     case 2: LN_BWD(2); break;
@@ -231,13 +255,17 @@ extern "C" int vlm_layernorm_fwd(const void* x, int x_is_fp32, const float* gamm
 
 extern "C" int vlm_layernorm_bwd(const void* dy, const void* x, int x_is_fp32, const float* mean, const float* rstd,
                                  const float* gamma, const void* dres, void* dx, float* dgamma, float* dbeta, int M,
-                                 int D, void* stream) {
+                                 int D, void* dx_drop, float p_drop, unsigned long long seed, unsigned long long offset,
+                                 const unsigned long long* rng_offset_ptr, float* colsum, void* stream) {
   VLM_REQUIRE(M > 0 && D > 0 && D % 8 == 0, "vlm_layernorm_bwd: need D %% 8 == 0 (M=%d D=%d)", M, D);
   VLM_REQUIRE(dy && x && mean && rstd && gamma && dx, "vlm_layernorm_bwd: null pointer");
+  VLM_REQUIRE(!dx_drop || (p_drop > 0.f && p_drop < 1.f && D % 4 == 0), "vlm_layernorm_bwd: dx_drop needs 0 < p_drop < 1");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (x_is_fp32)
     return ln_bwd_dispatch<float>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const float*>(x), mean, rstd, gamma,
-                                  reinterpret_cast<const float*>(dres), reinterpret_cast<float*>(dx), dgamma, dbeta, M, D, s);
+                                  reinterpret_cast<const float*>(dres), reinterpret_cast<float*>(dx), dgamma, dbeta, M, D,
+                                  reinterpret_cast<float*>(dx_drop), p_drop, seed, offset, rng_offset_ptr, colsum, s);
   return ln_bwd_dispatch<bf16>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), mean, rstd, gamma,
-                               reinterpret_cast<const bf16*>(dres), reinterpret_cast<bf16*>(dx), dgamma, dbeta, M, D, s);
+                               reinterpret_cast<const bf16*>(dres), reinterpret_cast<bf16*>(dx), dgamma, dbeta, M, D,
+                               reinterpret_cast<bf16*>(dx_drop), p_drop, seed, offset, rng_offset_ptr, colsum, s);
 }

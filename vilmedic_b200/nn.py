@@ -53,10 +53,10 @@ def _ln(arena, ln):
     return (arena.fp32(ln.weight), arena.fp32(ln.bias), arena.grad(ln.weight), arena.grad(ln.bias))
 
 
-def _wgrad(dy, x, P, scale_t=None):
-    """P.gw += dy^T x ; P.gb += colsum(dy).  dy [M,N], x [M,K] bf16."""
+def _wgrad(dy, x, P, scale_t=None, bias=True):
+    """P.gw += dy^T x ; P.gb += colsum(dy) (skipped when the producer of dy already accumulated it).  dy [M,N], x [M,K]."""
     ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out=P.gw, accumulate=True, alpha_t=scale_t)
-    if P.gb is not None:
+    if bias and P.gb is not None:
         ops.colsum(dy, P.gb, scale_t)
 
 
@@ -98,18 +98,21 @@ def _bf16_rows(t):
 
 
 class LayerNormFn(torch.autograd.Function):
+    """colsum: optional fp32 [D] gradient buffer of the bias of the Linear that produced x (its bias gradient is the
+    column sum of dx, accumulated inside the LN backward kernel)."""
+
     @staticmethod
-    def forward(ctx, x, anchor, lnp, eps):
+    def forward(ctx, x, anchor, lnp, eps, colsum=None):
         g, b, gg, gb = lnp
         y, mean, rstd = ops.layernorm_fwd(x, g, b, eps)
-        ctx.saved = (x, mean, rstd, lnp)
+        ctx.saved = (x, mean, rstd, lnp, colsum)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, mean, rstd, (g, b, gg, gb) = ctx.saved
-        dx = ops.layernorm_bwd(dy.contiguous(), x, mean, rstd, g, gg, gb)
-        return dx, None, None, None
+        x, mean, rstd, (g, b, gg, gb), colsum = ctx.saved
+        dx = ops.layernorm_bwd(dy.contiguous(), x, mean, rstd, g, gg, gb, colsum=colsum)
+        return dx, None, None, None, None
 
 
 class DropoutFn(torch.autograd.Function):
@@ -197,7 +200,9 @@ class ViTLayerFn(torch.autograd.Function):
     """One pre-LN ViT block (HF modeling_vit.py:315-346) on a [B*S, D] bf16 residual stream."""
 
     @staticmethod
-    def forward(ctx, x, anchor, layer, arena, B, S, save):
+    def forward(ctx, x, anchor, layer, arena, B, S, save, prev_gb=None, own_b2_fused=False):
+        """prev_gb: gradient buffer of the bias of the Linear that produced x (previous layer's FFN-down): this layer's
+        backward accumulates colsum(dx) into it.  own_b2_fused: the consumer of x2's gradient does the same for P2.gb."""
         cfg = layer.cfg
         D, H = cfg.hidden_size, cfg.num_attention_heads
         DH = D // H
@@ -219,20 +224,22 @@ class ViTLayerFn(torch.autograd.Function):
         x2 = ops.gemm(hmid, P2.w, bias=P2.b, residual=x1)
         if save:
             ctx.saved = (x, h1, mean1, rstd1, qkv, ctxv, lse, x1, h2, mean2, rstd2, pre, hmid, Pqkv, Po, P1, P2, ln1, ln2, B, S, H, DH)
+            ctx.fuse = (prev_gb, own_b2_fused)
         return x2
 
     @staticmethod
     def backward(ctx, dx2):
         (x, h1, mean1, rstd1, qkv, ctxv, lse, x1, h2, mean2, rstd2, pre, hmid, Pqkv, Po, P1, P2, ln1, ln2, B, S, H, DH) = ctx.saved
         D = H * DH
+        prev_gb, own_b2_fused = ctx.fuse
         dx2 = dx2.contiguous()
-        _wgrad(dx2, hmid, P2)
+        _wgrad(dx2, hmid, P2, bias=not own_b2_fused)
         dpre = _dgrad(dx2, P2, act=ops.ACT_GELU_GRAD, aux_in=pre)
         _wgrad(dpre, h2, P1)
         dh2 = _dgrad(dpre, P1)
-        dx1 = ops.layernorm_bwd(dh2, x1, mean2, rstd2, ln2[0], ln2[2], ln2[3], dres=dx2)
+        dx1 = ops.layernorm_bwd(dh2, x1, mean2, rstd2, ln2[0], ln2[2], ln2[3], dres=dx2, colsum=Po.gb)
         ctx2d = ctxv.view(B * S, D)
-        _wgrad(dx1, ctx2d, Po)
+        _wgrad(dx1, ctx2d, Po, bias=False)
         dctx = _dgrad(dx1, Po).view(B, S, D)
         dqkv = torch.empty_like(qkv)
         q3, d3 = qkv.view(B, S, 3 * D), dqkv.view(B, S, 3 * D)
@@ -240,8 +247,8 @@ class ViTLayerFn(torch.autograd.Function):
                           d3[:, :, :D], d3[:, :, D:2 * D], d3[:, :, 2 * D:], H, DH)
         _wgrad(dqkv, h1, Pqkv)
         dh1 = _dgrad(dqkv, Pqkv)
-        dx = ops.layernorm_bwd(dh1, x, mean1, rstd1, ln1[0], ln1[2], ln1[3], dres=dx1)
-        return dx, None, None, None, None, None, None
+        dx = ops.layernorm_bwd(dh1, x, mean1, rstd1, ln1[0], ln1[2], ln1[3], dres=dx1, colsum=prev_gb)
+        return dx, None, None, None, None, None, None, None, None
 
 
 class _Cfg:
@@ -349,9 +356,11 @@ class ViTTower(nn.Module):
         B = images.shape[0]
         x = ViTEmbedFn.apply(images, anchor, self, arena)
         S = x.shape[0] // B
+        prev_gb = None                       # layer 0's input comes from the patch embedding (its bias grad: vit_embed_bwd)
         for layer in self.encoder.layer:
-            x = ViTLayerFn.apply(x, anchor, layer, arena, B, S, grad)
-        x = LayerNormFn.apply(x, anchor, _ln(arena, self.layernorm), cfg.layer_norm_eps)
+            x = ViTLayerFn.apply(x, anchor, layer, arena, B, S, grad, prev_gb, True)
+            prev_gb = arena.grad(layer.output.dense.bias)
+        x = LayerNormFn.apply(x, anchor, _ln(arena, self.layernorm), cfg.layer_norm_eps, prev_gb)
         return x.view(B, S, cfg.hidden_size)
 
 
@@ -524,9 +533,17 @@ class BertLayerFn(torch.autograd.Function):
             return ops.dropout(g, p_h, s, o)
 
         ln1, ln3 = c["ln1"], c["ln3"]
-        dz3 = ops.layernorm_bwd(dx3.contiguous(), c["z3"], c["m3"], c["r3"], ln3[0], ln3[2], ln3[3])
-        dz3d = drop(dz3, "h3")
-        _wgrad(dz3d, c["hmid"], c["P2"])
+
+        def ln_bwd(dy, z, m, r, ln, name, P):
+            """LN backward with the hidden-dropout mask and the bias gradient of `P` fused in; returns (dz, dropped dz)."""
+            if p_h > 0:
+                s_, o_ = rng[name]
+                return ops.layernorm_bwd(dy, z, m, r, ln[0], ln[2], ln[3], drop=(p_h, s_, o_), colsum=P.gb)
+            dz = ops.layernorm_bwd(dy, z, m, r, ln[0], ln[2], ln[3], colsum=P.gb)
+            return dz, dz
+
+        dz3, dz3d = ln_bwd(dx3.contiguous(), c["z3"], c["m3"], c["r3"], ln3, "h3", c["P2"])
+        _wgrad(dz3d, c["hmid"], c["P2"], bias=False)
         dpre = _dgrad(dz3d, c["P2"], act=ops.ACT_GELU_GRAD, aux_in=c["pre"])
         _wgrad(dpre, c["x2"], c["P1"])
         dx2 = _dgrad(dpre, c["P1"], residual=dz3)
@@ -534,9 +551,8 @@ class BertLayerFn(torch.autograd.Function):
         if c["cross"]:
             ln2 = c["ln2"]
             Se = c["Se"]
-            dz2 = ops.layernorm_bwd(dx2, c["z2"], c["m2"], c["r2"], ln2[0], ln2[2], ln2[3])
-            dz2d = drop(dz2, "h2")
-            _wgrad(dz2d, c["ctx2"].view(B * T, D), c["Poc"])
+            dz2, dz2d = ln_bwd(dx2, c["z2"], c["m2"], c["r2"], ln2, "h2", c["Poc"])
+            _wgrad(dz2d, c["ctx2"].view(B * T, D), c["Poc"], bias=False)
             dctx2 = _dgrad(dz2d, c["Poc"]).view(B, T, D)
             dqc = torch.empty_like(c["qc"])
             dkvc = torch.empty_like(c["kvc"])
@@ -551,9 +567,8 @@ class BertLayerFn(torch.autograd.Function):
             denc = _dgrad(dkvc, c["Pkv"])
         else:
             dx1 = dx2
-        dz1 = ops.layernorm_bwd(dx1, c["z1"], c["m1"], c["r1"], ln1[0], ln1[2], ln1[3])
-        dz1d = drop(dz1, "h1")
-        _wgrad(dz1d, c["ctx1"].view(B * T, D), c["Po"])
+        dz1, dz1d = ln_bwd(dx1, c["z1"], c["m1"], c["r1"], ln1, "h1", c["Po"])
+        _wgrad(dz1d, c["ctx1"].view(B * T, D), c["Po"], bias=False)
         dctx1 = _dgrad(dz1d, c["Po"]).view(B, T, D)
         dqkv = torch.empty_like(c["qkv"])
         q3, d3 = c["qkv"].view(B, T, 3 * D), dqkv.view(B, T, 3 * D)

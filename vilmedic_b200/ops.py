@@ -125,16 +125,22 @@ def layernorm_fwd(x, gamma, beta, eps, save_stats=True):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None):
-    """Returns dx (dtype of x); ACCUMULATES into dgamma / dbeta (fp32 [D])."""
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None, drop=None, colsum=None):
+    """Returns dx (dtype of x) — or (dx, dropout(dx)) when drop=(p, seed, offset); ACCUMULATES into dgamma / dbeta and,
+    if given, the column sums of the (dropped) dx into `colsum` (fp32 [D])."""
     M, D = x.shape
     _req(dy.is_contiguous() and dy.dtype == torch.bfloat16 and x.is_contiguous(), "layernorm_bwd: bad inputs")
     dx = torch.empty_like(x)
     if dres is not None:
         _req(dres.dtype == x.dtype and dres.is_contiguous(), "dres dtype must match x")
+    dxd = torch.empty_like(x) if drop is not None else None
+    p, seed, off = drop if drop is not None else (0.0, 0, 0)
     check(_L().vlm_layernorm_bwd(ptr(dy), ptr(x), c_int(int(x.dtype == torch.float32)), ptr(mean), ptr(rstd), ptr(gamma),
-                                 ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta), c_int(M), c_int(D), stream_ptr()),
+                                 ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta), c_int(M), c_int(D), ptr(dxd), c_float(p),
+                                 c_u64(seed), c_u64(off), ptr(RNG_COUNTER[0]), ptr(colsum), stream_ptr()),
           "vlm_layernorm_bwd")
+    if drop is not None:
+        return dx, dxd
     return dx
 
 
