@@ -374,3 +374,64 @@ def test_layernorm_bwd_fused_dropout_and_colsum(cuda_dev):
     a, w = _bf((M, 64), cuda_dev, 3), _bf((D, 64), cuda_dev, 4)
     y = ops.gemm(a, w, p_drop=0.1, seed=11, offset=5)
     assert torch.equal(y != 0, keep | (y != 0)) and ((y == 0) & keep).float().mean().item() < 1e-3
+
+
+@pytest.mark.parametrize("B,H,Tq,Sk,causal,masked", [
+    (2, 12, 197, 197, False, False),   # ViT self-attention (Nq = 224, two key tiles)
+    (3, 12, 128, 128, True, True),     # decoder causal self-attention with key padding
+    (2, 12, 128, 197, False, True),    # cross-attention
+    (2, 4, 128, 394, False, True),     # cross-attention over two images (four key tiles)
+    (1, 2, 5, 3, False, False),        # tiny / ragged
+    (5, 3, 256, 130, False, False),    # max query length
+])
+def test_attention_bwd_tcgen05(cuda_dev, B, H, Tq, Sk, causal, masked):
+    """tcgen05 backward (TMEM accumulators, transposed formulation) against autograd of the fp32 reference."""
+    from vilmedic_b200 import ops
+    DH = 64
+    D = H * DH
+    if Tq == Sk:
+        qkv = _bf((B, Tq, 3 * D), cuda_dev, 3)
+        q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+    else:
+        q = _bf((B, Tq, D), cuda_dev, 3)
+        kv = _bf((B, Sk, 2 * D), cuda_dev, 4)
+        k, v = kv[:, :, :D], kv[:, :, D:]
+    kmask = None
+    if masked:
+        lens = torch.randint(max(1, Sk // 2), Sk + 1, (B,))
+        kmask = (torch.arange(Sk)[None, :] < lens[:, None]).to(torch.uint8).to(cuda_dev).contiguous()
+    o, lse = ops.attention_fwd(q, k, v, H, DH, kmask=kmask, causal=causal)
+    qr, kr, vr = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
+    ref = _attn_ref(qr, kr, vr, H, DH, kmask, causal)
+    do = _bf((B, Tq, D), cuda_dev, 5)
+    ref.backward(do.float())
+    if Tq == Sk:
+        dqkv = torch.zeros(B, Tq, 3 * D, device=cuda_dev, dtype=torch.bfloat16)
+        dq, dk, dv = dqkv[:, :, :D], dqkv[:, :, D:2 * D], dqkv[:, :, 2 * D:]
+    else:
+        dq = torch.zeros(B, Tq, D, device=cuda_dev, dtype=torch.bfloat16)
+        dkv = torch.zeros(B, Sk, 2 * D, device=cuda_dev, dtype=torch.bfloat16)
+        dk, dv = dkv[:, :, :D], dkv[:, :, D:]
+    ops.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, H, DH, kmask=kmask, causal=causal, force_tc=True)
+    torch.cuda.synchronize()
+    for name, got, want in (("dq", dq, qr.grad), ("dk", dk, kr.grad), ("dv", dv, vr.grad)):
+        err = (got.float() - want).abs().max().item()
+        assert err < 3e-2 * max(1.0, want.abs().max().item()), "%s err %g" % (name, err)
+
+
+def test_attention_bwd_tcgen05_dropout_matches_mma_path(cuda_dev):
+    """With p > 0 both backward implementations regenerate the same Philox mask as the forward."""
+    from vilmedic_b200 import ops
+    B, H, T, DH = 2, 4, 128, 64
+    D = H * DH
+    q, k, v = _bf((B, T, D), cuda_dev, 1), _bf((B, T, D), cuda_dev, 2), _bf((B, T, D), cuda_dev, 3)
+    o, lse = ops.attention_fwd(q, k, v, H, DH, causal=True, p_drop=0.1, seed=7, offset=3)
+    do = _bf((B, T, D), cuda_dev, 9)
+    outs = []
+    for tc in (False, True):
+        dq, dk, dv = (torch.zeros(B, T, D, device=cuda_dev, dtype=torch.bfloat16) for _ in range(3))
+        ops.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, H, DH, causal=True, p_drop=0.1, seed=7, offset=3, force_tc=tc)
+        outs.append((dq.float(), dk.float(), dv.float()))
+    torch.cuda.synchronize()
+    for a, b in zip(*outs):
+        assert (a - b).abs().max().item() < 4e-2 * max(1.0, a.abs().max().item())

@@ -10,6 +10,7 @@
 // Round-1 implementation note: the inner products use the register-level mma.sync m16n8k16 bf16 path (HMMA).  The
 // tiles here are 64x64x{48,64,96} per warp-group with Sk <= a few hundred, i.e. latency- not throughput-bound; the
 // tcgen05 rewrite (S/P in TMEM) is the next step for this file.  GEMM-shaped projections around it are tcgen05.
+#include <cstdlib>
 #include "common.cuh"
 #include "vlm_b200.h"
 
@@ -603,6 +604,14 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
   }
 }
 
+int attention_bwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                              const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                              const void* d_o, long long do_bs, long long do_rs, const float* lse, void* dq, long long dq_bs,
+                              long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv, long long dv_bs,
+                              long long dv_rs, const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH, int causal,
+                              float scale, float p_drop, unsigned long long seed, unsigned long long offset,
+                              const unsigned long long* rng_offset_ptr, cudaStream_t stream);
+
 static int check_attn_common(const char* who, int B, int H, int Tq, int Sk, int DH) {
   if (B <= 0 || H <= 0 || Tq <= 0 || Sk <= 0) { set_error("%s: bad shape B=%d H=%d Tq=%d Sk=%d", who, B, H, Tq, Sk); return -1; }
   if (DH != 48 && DH != 64 && DH != 96) { set_error("%s: head dim %d unsupported (48, 64, 96)", who, DH); return -1; }
@@ -643,6 +652,21 @@ extern "C" int vlm_attention_bwd(const void* q, long long q_bs, long long q_rs, 
                                  unsigned long long offset, const unsigned long long* rng_offset_ptr, void* stream) {
   if (check_attn_common("vlm_attention_bwd", B, H, Tq, Sk, DH)) return -1;
   VLM_REQUIRE(q && k && v && o && d_o && lse && delta && dq && dk && dv, "vlm_attention_bwd: null pointer");
+  {
+    // tcgen05 path (head dim 64, Tq <= 256): VLM_ATTN_TC=1 routes supported shapes to attention_tc.cu
+    static int use_tc = -1;
+    if (use_tc < 0) {
+      const char* env = getenv("VLM_ATTN_TC");
+      use_tc = (env && env[0] == '1') ? 1 : 0;
+    }
+    if (use_tc) {
+      const int r = attention_bwd_tc_dispatch(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, d_o, do_bs, do_rs, lse,
+                                              dq, dq_bs, dq_rs, dk, dk_bs, dk_rs, dv, dv_bs, dv_rs, kmask, B, H, Tq, Sk, DH,
+                                              causal, scale, p_drop, seed, offset, rng_offset_ptr, (cudaStream_t)stream);
+      if (r < 0) return r;
+      if (r == 1) return 0;
+    }
+  }
   VLM_REQUIRE(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && do_rs % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 &&
                   v_bs % 8 == 0 && do_bs % 8 == 0 && o_rs % 2 == 0 && dq_rs % 2 == 0 && dk_rs % 2 == 0 && dv_rs % 2 == 0,
               "vlm_attention_bwd: strides must keep 16B alignment");
@@ -661,4 +685,26 @@ extern "C" int vlm_attention_bwd(const void* q, long long q_bs, long long q_rs, 
   else if (DH == 64) { attn_bwd_dq_kernel<64><<<gq, 128, 0, s>>>(p); attn_bwd_dkv_kernel<64><<<gk, 128, 0, s>>>(p); }
   else { attn_bwd_dq_kernel<96><<<gq, 128, 0, s>>>(p); attn_bwd_dkv_kernel<96><<<gk, 128, 0, s>>>(p); }
   return check_launch("attention_bwd");
+}
+
+// Explicit entry to the tcgen05 backward (tests / benchmarks); fails if the shape is outside its envelope.
+extern "C" int vlm_attention_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                    const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                                    const void* d_o, long long do_bs, long long do_rs, const float* lse, void* dq,
+                                    long long dq_bs, long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv,
+                                    long long dv_bs, long long dv_rs, const uint8_t* kmask, int B, int H, int Tq, int Sk,
+                                    int DH, int causal, float scale, float p_drop, unsigned long long seed,
+                                    unsigned long long offset, const unsigned long long* rng_offset_ptr, void* stream) {
+  if (check_attn_common("vlm_attention_bwd_tc", B, H, Tq, Sk, DH)) return -1;
+  VLM_REQUIRE(q && k && v && o && d_o && lse && dq && dk && dv, "vlm_attention_bwd_tc: null pointer");
+  VLM_REQUIRE(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && do_rs % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 &&
+                  v_bs % 8 == 0 && do_bs % 8 == 0, "vlm_attention_bwd_tc: strides must keep 16B alignment");
+  const int r = attention_bwd_tc_dispatch(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, d_o, do_bs, do_rs, lse, dq,
+                                          dq_bs, dq_rs, dk, dk_bs, dk_rs, dv, dv_bs, dv_rs, kmask, B, H, Tq, Sk, DH, causal,
+                                          scale, p_drop, seed, offset, rng_offset_ptr, (cudaStream_t)stream);
+  if (r == 0) {
+    set_error("vlm_attention_bwd_tc: shape outside the tcgen05 envelope (DH=64, Tq<=256, Tq<=128 with dropout)");
+    return -1;
+  }
+  return r < 0 ? r : 0;
 }

@@ -1,0 +1,458 @@
+// tcgen05 attention BACKWARD for head dim 64 and Tq <= 256 (ViT S=197, decoder T=128, cross 128 x 197[*N]).
+//
+// One persistent CTA per SM walks over (batch, head) items; for every 128-key tile j of the item it runs the five
+// products of the attention backward on the 5th-gen tensor cores with all accumulators in TMEM, in the TRANSPOSED
+// formulation (rows = keys), so that P^T / dS^T are directly the A operands of the dV / dK products and dS (the A
+// operand of dQ) is the same shared-memory tile read through an MN-major descriptor:
+//     S^T  = K_j Q^T                 (M=128 keys, N=Nq, K=64)    TMEM cols [0, Nq)
+//     dP^T = V_j dO^T                (same shape, same columns, after P^T has been extracted)
+//     dV_j = P^T dO                  (M=128, N=64, K=Nq)         TMEM cols [256, 320)
+//     dK_j = dS^T Q                  (M=128, N=64, K=Nq)         TMEM cols [320, 384)
+//     dQ  += dS K_j                  (M=128 per q block, N=64, K=128 keys)  TMEM cols [384, 512), accumulated over j
+// Warp roles: warp0 = TMA producer (4-D tensor maps straight over the packed QKV / dO layouts), warp1 = MMA issuer,
+// warps 2..9 = 256 "softmax" threads (thread <-> key row, two warps per TMEM lane quadrant split the query columns):
+//   pass A:  P^T = exp2(S^T*scale*log2e - lse2[q]) with key-padding / causal masks (+ Philox dropout) -> bf16, written
+//            to shared memory in the canonical K-major SWIZZLE_128B layout the UMMA descriptors expect;
+//   pass B:  dS^T = P^T * (dP^T - delta[q]) * scale, in place;
+//   epilogue: dV_j, dK_j (and dQ after the last key tile) TMEM -> bf16 -> global.
+// delta = rowsum(dO * O) and lse2 are staged per item by the same threads.  Same math / same dropout stream as the
+// mma.sync kernels in attention.cu (those remain the path for other head dims, longer queries and the forward).
+#include <cuda.h>
+#include "common.cuh"
+#include "gemm_epilogue.cuh"
+#include "vlm_b200.h"
+
+namespace vlm {
+
+struct AttnTcParams {
+  const bf16* o; const bf16* d_o;
+  long long o_bs, o_rs, do_bs, do_rs;
+  bf16* dq; bf16* dk; bf16* dv;
+  long long dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
+  const float* lse;        // [B,H,Tq] natural log
+  const uint8_t* kmask;    // [B,Sk] or null
+  int B, H, Tq, Sk, Nq;    // Nq = Tq rounded up to 32
+  int causal;
+  float scale, p_drop;
+  unsigned long long seed, offset;
+  const unsigned long long* offset_ptr;
+};
+
+__device__ __forceinline__ void tma_load_4d(const void* desc, uint64_t* bar, void* smem_dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+static constexpr int ATC_THREADS = 320;          // 2 control warps + 8 compute warps
+static constexpr int ATC_S_COL = 0, ATC_DV_COL = 256, ATC_DK_COL = 320, ATC_DQ_COL = 384;
+
+template <int ATOMS, bool DROPOUT>
+struct AtcSmem {
+  static constexpr int NQ_MAX = ATOMS * 64;
+  static constexpr int Q_BYTES = NQ_MAX * 128;
+  static constexpr int KV_BYTES = 128 * 128;
+  static constexpr int PT_BYTES = ATOMS * 16384;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_DO = OFF_Q + Q_BYTES;
+  static constexpr int OFF_K = OFF_DO + Q_BYTES;           // 2 buffers
+  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;       // 2 buffers
+  static constexpr int OFF_PT = OFF_V + 2 * KV_BYTES;
+  static constexpr int OFF_P2 = OFF_PT + PT_BYTES;
+  static constexpr int OFF_LSE = OFF_P2 + (DROPOUT ? PT_BYTES : 0);
+  static constexpr int OFF_DELTA = OFF_LSE + NQ_MAX * 4;
+  static constexpr int OFF_BAR = OFF_DELTA + NQ_MAX * 4;
+  static constexpr int NUM_BARS = 13;
+  static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
+};
+
+// byte offset of element (row r, column q) inside a K-major SWIZZLE_128B tile made of 64-column atoms of 128 rows
+__device__ __forceinline__ uint32_t pt_offset16(int r, int q0) {  // q0 multiple of 8: start of a 16-byte unit
+  return (uint32_t)((q0 >> 6) * 16384 + r * 128 + ((((q0 & 63) >> 3) ^ (r & 7)) << 4));
+}
+
+template <int ATOMS, bool DROPOUT>
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, AttnTcParams p) {
+  using S = AtcSmem<ATOMS, DROPOUT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + S::OFF_Q;
+  uint8_t* sDO = smem + S::OFF_DO;
+  uint8_t* sK = smem + S::OFF_K;
+  uint8_t* sV = smem + S::OFF_V;
+  uint8_t* sPT = smem + S::OFF_PT;
+  uint8_t* sP2 = smem + S::OFF_P2;
+  float* sLse = reinterpret_cast<float*>(smem + S::OFF_LSE);
+  float* sDelta = reinterpret_cast<float*>(smem + S::OFF_DELTA);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* qdo_full = bars + 0;
+  uint64_t* qdo_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;    // [2]
+  uint64_t* kv_empty = bars + 4;   // [2]
+  uint64_t* s_full = bars + 6;
+  uint64_t* p_ready = bars + 7;
+  uint64_t* dp_full = bars + 8;
+  uint64_t* dv_done = bars + 9;
+  uint64_t* ds_ready = bars + 10;
+  uint64_t* out_full = bars + 11;
+  uint64_t* out_free = bars + 12;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + S::NUM_BARS);
+
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nitems = p.B * p.H;
+  const int ntiles = (p.Sk + 127) / 128;
+  const int Nq = p.Nq;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_do);
+    mbar_init(qdo_full, 1);
+    mbar_init(qdo_empty, 1);
+    mbar_init(&kv_full[0], 1);
+    mbar_init(&kv_full[1], 1);
+    mbar_init(&kv_empty[0], 1);
+    mbar_init(&kv_empty[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 8);
+    mbar_init(dp_full, 1);
+    mbar_init(dv_done, 1);
+    mbar_init(ds_ready, 8);
+    mbar_init(out_full, 1);
+    mbar_init(out_free, 8);
+    fence_barrier_init();
+  } else if (warp_idx == 1) {
+    tmem_alloc<512>(tmem_ptr_smem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint32_t item_cnt = 0, tile_cnt = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++item_cnt) {
+        const int b = item / p.H, h = item % p.H;
+        mbar_wait(qdo_empty, (item_cnt & 1u) ^ 1u);
+        mbar_expect_tx(qdo_full, 2u * (uint32_t)Nq * 128u);
+        tma_load_4d(&tm_q, qdo_full, sQ, 0, h, 0, b);
+        tma_load_4d(&tm_do, qdo_full, sDO, 0, h, 0, b);
+        for (int j = 0; j < ntiles; ++j, ++tile_cnt) {
+          const int buf = tile_cnt & 1u;
+          const uint32_t ph = (tile_cnt >> 1) & 1u;
+          mbar_wait(&kv_empty[buf], ph ^ 1u);
+          mbar_expect_tx(&kv_full[buf], 2u * S::KV_BYTES);
+          tma_load_4d(&tm_k, &kv_full[buf], sK + buf * S::KV_BYTES, 0, h, j * 128, b);
+          tma_load_4d(&tm_v, &kv_full[buf], sV + buf * S::KV_BYTES, 0, h, j * 128, b);
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t id_s = make_idesc_bf16(128, Nq, false, false);     // S^T, dP^T : K-major x K-major
+      const uint32_t id_dv = make_idesc_bf16(128, 64, false, true);      // dV, dK   : K-major A, MN-major B
+      const uint32_t id_dq = make_idesc_bf16(128, 64, true, true);       // dQ       : MN-major A and B
+      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aPT = smem_u32(sPT);
+      const int nq16 = Nq / 16;
+      const int q_blocks = (Nq + 127) / 128;
+      uint32_t item_cnt = 0, tile_cnt = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++item_cnt) {
+        mbar_wait(qdo_full, item_cnt & 1u);
+        tc_fence_after();
+        for (int j = 0; j < ntiles; ++j, ++tile_cnt) {
+          const int buf = tile_cnt & 1u;
+          const uint32_t kvph = (tile_cnt >> 1) & 1u, tph = tile_cnt & 1u;
+          const uint32_t aK = smem_u32(sK + buf * S::KV_BYTES), aV = smem_u32(sV + buf * S::KV_BYTES);
+          mbar_wait(&kv_full[buf], kvph);
+          tc_fence_after();
+          // (1) S^T = K_j Q^T
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + ATC_S_COL, make_smem_desc(aK + k * 32, 16, 1024), make_smem_desc(aQ + k * 32, 16, 1024), id_s, k > 0);
+          umma_commit(s_full);
+          mbar_wait(p_ready, tph);
+          tc_fence_after();
+          // (2) dP^T = V_j dO^T  (same TMEM columns; P^T has been extracted)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + ATC_S_COL, make_smem_desc(aV + k * 32, 16, 1024), make_smem_desc(aDO + k * 32, 16, 1024), id_s, k > 0);
+          umma_commit(dp_full);
+          mbar_wait(out_free, tph ^ 1u);   // dV / dK / dQ accumulators of the previous tile have been drained
+          tc_fence_after();
+          // (3) dV_j = P^T dO
+          for (int k = 0; k < nq16; ++k)
+            umma_bf16(tmem_base + ATC_DV_COL, make_smem_desc(aPT + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                      make_smem_desc(aDO + k * 2048, 16384, 1024), id_dv, k > 0);
+          umma_commit(dv_done);
+          mbar_wait(ds_ready, tph);
+          tc_fence_after();
+          // (4) dK_j = dS^T Q
+          for (int k = 0; k < nq16; ++k)
+            umma_bf16(tmem_base + ATC_DK_COL, make_smem_desc(aPT + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                      make_smem_desc(aQ + k * 2048, 16384, 1024), id_dv, k > 0);
+          // (5) dQ[mb] += dS K_j   (dS = the dS^T tile through an MN-major descriptor: 64-query blocks 16 KB apart)
+          for (int mb = 0; mb < q_blocks; ++mb)
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(tmem_base + ATC_DQ_COL + mb * 64, make_smem_desc(aPT + mb * 32768 + k * 2048, 16384, 1024),
+                        make_smem_desc(aK + k * 2048, 16384, 1024), id_dq, (j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(out_full);
+          umma_commit(&kv_empty[buf]);
+          if (j == ntiles - 1) umma_commit(qdo_empty);
+        }
+      }
+    }
+  } else {
+    // ===================================================== compute warps (256 threads)
+    const int quad = warp_idx & 3;             // TMEM lane quadrant
+    const int half = (warp_idx - 2) >> 2;      // which half of the query columns / output columns
+    const int r = quad * 32 + lane;            // key row inside the tile
+    const int ct = threadIdx.x - 64;           // 0..255
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const Philox rng(p.seed);
+    const unsigned long long off_eff = p.offset + ((DROPOUT && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
+    const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
+    const float inv_keep = DROPOUT ? 1.f / (1.f - p.p_drop) : 1.f;
+    const int Sk4 = (p.Sk + 3) >> 2;
+    const int half_cols = Nq >> 1;             // multiple of 16
+    uint32_t tile_cnt = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int b = item / p.H, h = item % p.H;
+      // ---- per-item staging: lse (log2 units, +inf beyond Tq) and delta = rowsum(dO * O)
+      named_bar_sync(1, 256);
+      if (ct < Nq) {
+        float l2 = INFINITY, dl = 0.f;
+        if (ct < p.Tq) {
+          l2 = p.lse[(long long)item * p.Tq + ct] * 1.4426950408889634f;
+          const uint4* o4 = reinterpret_cast<const uint4*>(p.o + (long long)b * p.o_bs + (long long)ct * p.o_rs + h * 64);
+          const uint4* g4 = reinterpret_cast<const uint4*>(p.d_o + (long long)b * p.do_bs + (long long)ct * p.do_rs + h * 64);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 a = __ldg(o4 + i), g = __ldg(g4 + i);
+            const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+            const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
+            dl += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
+          }
+        }
+        sLse[ct] = l2;
+        sDelta[ct] = dl;
+      }
+      named_bar_sync(1, 256);
+      for (int j = 0; j < ntiles; ++j, ++tile_cnt) {
+        const uint32_t tph = tile_cnt & 1u;
+        const int kk = j * 128 + r;
+        const bool kvalid = (kk < p.Sk) && (!p.kmask || p.kmask[(long long)b * p.Sk + kk]);
+        // ---------------- pass A: P^T
+        mbar_wait(s_full, tph);
+        tc_fence_after();
+        for (int c = 0; c < half_cols; c += 16) {
+          const int q0 = half * half_cols + c;
+          uint32_t v[16];
+          tmem_ld16(lane_taddr + ATC_S_COL + q0, v);
+          tmem_ld_wait();
+          float pv[16], pd[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int q = q0 + i;
+            const bool ok = kvalid && (!p.causal || kk <= q);
+            pv[i] = ok ? exp2f(__uint_as_float(v[i]) * sl2 - sLse[q]) : 0.f;
+            if (DROPOUT) {
+              const unsigned long long idx = ((unsigned long long)item * p.Tq + q) * (unsigned long long)Sk4 + (kk >> 2);
+              const uint4 rnd = rng(idx, off_eff);
+              const int w = kk & 3;
+              const uint32_t rv = w == 0 ? rnd.x : (w == 1 ? rnd.y : (w == 2 ? rnd.z : rnd.w));
+              pd[i] = rv >= thr ? pv[i] * inv_keep : 0.f;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            uint4 w;
+            if (DROPOUT) {
+              w.x = pack_bf16x2(pd[8 * u + 0], pd[8 * u + 1]); w.y = pack_bf16x2(pd[8 * u + 2], pd[8 * u + 3]);
+              w.z = pack_bf16x2(pd[8 * u + 4], pd[8 * u + 5]); w.w = pack_bf16x2(pd[8 * u + 6], pd[8 * u + 7]);
+              *reinterpret_cast<uint4*>(sPT + pt_offset16(r, q0 + 8 * u)) = w;
+            }
+            w.x = pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]); w.y = pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]);
+            w.z = pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]); w.w = pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]);
+            *reinterpret_cast<uint4*>((DROPOUT ? sP2 : sPT) + pt_offset16(r, q0 + 8 * u)) = w;
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+        // ---------------- pass B: dS^T (in place over P^T)
+        mbar_wait(dp_full, tph);
+        mbar_wait(dv_done, tph);
+        tc_fence_after();
+        for (int c = 0; c < half_cols; c += 16) {
+          const int q0 = half * half_cols + c;
+          uint32_t v[16];
+          tmem_ld16(lane_taddr + ATC_S_COL + q0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t off = pt_offset16(r, q0 + 8 * u);
+            const uint4 pw = *reinterpret_cast<const uint4*>((DROPOUT ? sP2 : sPT) + off);
+            uint4 kw = pw;
+            if (DROPOUT) kw = *reinterpret_cast<const uint4*>(sPT + off);   // dropped P: zero <=> dropped (or P == 0)
+            const uint32_t pw4[4] = {pw.x, pw.y, pw.z, pw.w}, kw4[4] = {kw.x, kw.y, kw.z, kw.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 pp = unpack_bf16x2(pw4[e]), kp = unpack_bf16x2(kw4[e]);
+              const int q = q0 + 8 * u + 2 * e;
+              float d0 = __uint_as_float(v[8 * u + 2 * e]), d1 = __uint_as_float(v[8 * u + 2 * e + 1]);
+              if (DROPOUT) {
+                d0 = kp.x != 0.f ? d0 * inv_keep : 0.f;
+                d1 = kp.y != 0.f ? d1 * inv_keep : 0.f;
+              }
+              ow[e] = pack_bf16x2(pp.x * (d0 - sDelta[q]) * p.scale, pp.y * (d1 - sDelta[q + 1]) * p.scale);
+            }
+            *reinterpret_cast<uint4*>(sPT + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ds_ready);
+        // ---------------- epilogue: dV_j, dK_j (+ dQ after the last key tile)
+        mbar_wait(out_full, tph);
+        tc_fence_after();
+        {
+          uint32_t acc[32];
+          tmem_ld32(lane_taddr + ATC_DV_COL + half * 32, acc);
+          tmem_ld_wait();
+          if (kk < p.Sk) {
+            uint4* dst = reinterpret_cast<uint4*>(p.dv + (long long)b * p.dv_bs + (long long)kk * p.dv_rs + h * 64 + half * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]), __uint_as_float(acc[8 * i + 1])),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3])),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7])));
+          }
+          tmem_ld32(lane_taddr + ATC_DK_COL + half * 32, acc);
+          tmem_ld_wait();
+          if (kk < p.Sk) {
+            uint4* dst = reinterpret_cast<uint4*>(p.dk + (long long)b * p.dk_bs + (long long)kk * p.dk_rs + h * 64 + half * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]), __uint_as_float(acc[8 * i + 1])),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3])),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7])));
+          }
+          if (j == ntiles - 1) {
+            const int q_blocks = (Nq + 127) / 128;
+            for (int mb = 0; mb < q_blocks; ++mb) {
+              tmem_ld32(lane_taddr + ATC_DQ_COL + mb * 64 + half * 32, acc);
+              tmem_ld_wait();
+              const int q = mb * 128 + r;
+              if (q < p.Tq) {
+                uint4* dst = reinterpret_cast<uint4*>(p.dq + (long long)b * p.dq_bs + (long long)q * p.dq_rs + h * 64 + half * 32);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]), __uint_as_float(acc[8 * i + 1])),
+                                      pack_bf16x2(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3])),
+                                      pack_bf16x2(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])),
+                                      pack_bf16x2(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7])));
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(out_free);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int ATOMS, bool DROPOUT>
+static int launch_attn_bwd_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                              const AttnTcParams& p, cudaStream_t stream) {
+  using S = AtcSmem<ATOMS, DROPOUT>;
+  auto kern = attn_bwd_tc_kernel<ATOMS, DROPOUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (err != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn_bwd_tc smem=%d): %s", S::TOTAL, cudaGetErrorString(err));
+      return -1;
+    }
+    attr_set = true;
+  }
+  const int items = p.B * p.H;
+  const int grid = items < num_sms() ? items : num_sms();
+  kern<<<grid, ATC_THREADS, S::TOTAL, stream>>>(tq, tk, tv, tdo, p);
+  return check_launch("attn_bwd_tc");
+}
+
+// returns 1 if the shape is handled by the tcgen05 kernel (and it was launched), 0 if not supported, <0 on error
+int attention_bwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                              const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                              const void* d_o, long long do_bs, long long do_rs, const float* lse, void* dq, long long dq_bs,
+                              long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv, long long dv_bs,
+                              long long dv_rs, const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH, int causal,
+                              float scale, float p_drop, unsigned long long seed, unsigned long long offset,
+                              const unsigned long long* rng_offset_ptr, cudaStream_t stream) {
+  if (DH != 64 || Tq > 256 || (p_drop > 0.f && Tq > 128)) return 0;
+  if ((o_rs % 8) || (do_rs % 8) || (dq_rs % 8) || (dk_rs % 8) || (dv_rs % 8) || (o_bs % 8) || (do_bs % 8) || (dq_bs % 8) ||
+      (dk_bs % 8) || (dv_bs % 8))
+    return 0;  // 16-byte vector access on the row pointers
+  bind_context_for_driver_calls();
+  const int Nq = (Tq + 31) / 32 * 32;
+  CUtensorMap tq, tk, tv, tdo;
+  auto mk = [&](CUtensorMap* tm, const void* ptr, long long bs, long long rs, int rows, int box_rows) {
+    const uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)rows, (uint64_t)B};
+    const uint64_t strides[3] = {64, (uint64_t)rs, (uint64_t)bs};
+    const uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
+    return make_tmap_bf16_nd(tm, ptr, 4, dims, strides, box);
+  };
+  if (mk(&tq, q, q_bs, q_rs, Tq, Nq) || mk(&tdo, d_o, do_bs, do_rs, Tq, Nq) || mk(&tk, k, k_bs, k_rs, Sk, 128) ||
+      mk(&tv, v, v_bs, v_rs, Sk, 128))
+    return -1;
+  AttnTcParams p;
+  p.o = (const bf16*)o; p.d_o = (const bf16*)d_o;
+  p.o_bs = o_bs; p.o_rs = o_rs; p.do_bs = do_bs; p.do_rs = do_rs;
+  p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv;
+  p.dq_bs = dq_bs; p.dq_rs = dq_rs; p.dk_bs = dk_bs; p.dk_rs = dk_rs; p.dv_bs = dv_bs; p.dv_rs = dv_rs;
+  p.lse = lse; p.kmask = kmask; p.B = B; p.H = H; p.Tq = Tq; p.Sk = Sk; p.Nq = Nq; p.causal = causal;
+  p.scale = scale; p.p_drop = p_drop; p.seed = seed; p.offset = offset; p.offset_ptr = rng_offset_ptr;
+  int rc;
+  if (p_drop > 0.f) rc = launch_attn_bwd_tc<2, true>(tq, tk, tv, tdo, p, stream);
+  else if (Nq <= 128) rc = launch_attn_bwd_tc<2, false>(tq, tk, tv, tdo, p, stream);
+  else rc = launch_attn_bwd_tc<4, false>(tq, tk, tv, tdo, p, stream);
+  return rc ? rc : 1;
+}
+
+}  // namespace vlm

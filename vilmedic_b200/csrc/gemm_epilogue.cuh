@@ -218,5 +218,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int
 // host-side pieces shared by the GEMM translation units
 int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch,
                    uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows);
+int make_tmap_bf16_nd(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                      const uint32_t* box);
+void bind_context_for_driver_calls();
 
 }  // namespace vlm

@@ -274,6 +274,43 @@ int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t ro
   return 0;
 }
 
+// Generic bf16 tiled tensor map (rank <= 5), 128B swizzle, zero OOB fill; strides in ELEMENTS for dims 1..rank-1.
+int make_tmap_bf16_nd(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                      const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -1;
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) st[i - 1] = strides_elems[i - 1] * 2;
+  }
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), d, st, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(rank %d) failed (%d): ptr=%p dims=%llu,%llu,%llu,%llu", rank, (int)r, ptr,
+              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0));
+    return -1;
+  }
+  return 0;
+}
+
+// make sure the calling host thread has the primary context bound (cuTensorMapEncodeTiled is a driver call)
+void bind_context_for_driver_calls() {
+  static thread_local int bound_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (bound_dev != dev) {
+    cudaSetDevice(dev);
+    cudaFree(0);
+    bound_dev = dev;
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int batch, int a_bmul,
                        int b_bmul, int split_k, long long c_bs, long long aux_bs, long long res_bs, const GemmEpilogue& epi, int max_ctas,
@@ -385,16 +422,7 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
 
   // cuTensorMapEncodeTiled is a driver call: make sure this host thread (e.g. an autograd worker) has the primary
   // context bound before the first one, otherwise it fails with CUDA_ERROR_INVALID_CONTEXT.
-  {
-    static thread_local int bound_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (bound_dev != dev) {
-      cudaSetDevice(dev);
-      cudaFree(0);
-      bound_dev = dev;
-    }
-  }
+  bind_context_for_driver_calls();
   // split-K candidates (weight gradients: fp32 C accumulated in place, K = number of tokens) prefer wide N tiles and
   // fill the machine along K instead of shrinking the tile.
   const bool splitk_ok = c_is_fp32 && accumulate && act == 0 && p_drop == 0.f && !residual && batch == 1 && K >= 1024;

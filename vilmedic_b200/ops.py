@@ -168,13 +168,23 @@ def attention_fwd(q, k, v, H, DH, *, kmask=None, causal=False, scale=None, p_dro
 
 
 def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, H, DH, *, kmask=None, causal=False, scale=None, p_drop=0.0, seed=0,
-                  offset=0):
-    """Writes dq/dk/dv (pre-allocated bf16 views with the q/k/v addressing scheme)."""
+                  offset=0, force_tc=False):
+    """Writes dq/dk/dv (pre-allocated bf16 views with the q/k/v addressing scheme).  force_tc: call the tcgen05 kernel
+    explicitly (tests); otherwise libvlmb200 picks (VLM_ATTN_TC=1 routes supported shapes to tcgen05)."""
     B, Tq = q.shape[0], q.shape[1]
     Sk = k.shape[1]
     scale = (1.0 / DH ** 0.5) if scale is None else scale
-    delta = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
     s = [_bh_strides(t, H, DH) for t in (q, k, v, o, do, dq, dk, dv)]
+    if force_tc:
+        check(_L().vlm_attention_bwd_tc(ptr(q), c_ll(s[0][0]), c_ll(s[0][1]), ptr(k), c_ll(s[1][0]), c_ll(s[1][1]), ptr(v),
+                                        c_ll(s[2][0]), c_ll(s[2][1]), ptr(o), c_ll(s[3][0]), c_ll(s[3][1]), ptr(do),
+                                        c_ll(s[4][0]), c_ll(s[4][1]), ptr(lse), ptr(dq), c_ll(s[5][0]), c_ll(s[5][1]),
+                                        ptr(dk), c_ll(s[6][0]), c_ll(s[6][1]), ptr(dv), c_ll(s[7][0]), c_ll(s[7][1]),
+                                        ptr(kmask), c_int(B), c_int(H), c_int(Tq), c_int(Sk), c_int(DH), c_int(int(causal)),
+                                        c_float(scale), c_float(p_drop), c_u64(seed), c_u64(offset), ptr(RNG_COUNTER[0]),
+                                        stream_ptr()), "vlm_attention_bwd_tc")
+        return
+    delta = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
     check(_L().vlm_attention_bwd(ptr(q), c_ll(s[0][0]), c_ll(s[0][1]), ptr(k), c_ll(s[1][0]), c_ll(s[1][1]), ptr(v),
                                  c_ll(s[2][0]), c_ll(s[2][1]), ptr(o), c_ll(s[3][0]), c_ll(s[3][1]), ptr(do),
                                  c_ll(s[4][0]), c_ll(s[4][1]), ptr(lse), ptr(delta), ptr(dq), c_ll(s[5][0]),
