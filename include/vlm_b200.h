@@ -86,6 +86,13 @@ int vlm_attention_bwd(const void* q, long long q_bs, long long q_rs, const void*
                       int causal, float scale, float p_drop, unsigned long long seed, unsigned long long offset,
                       const unsigned long long* rng_offset_ptr, void* stream);
 
+/* Same contract as vlm_attention_fwd, on the tcgen05 kernel (DH = 64, Sk <= 256: S = Q K^T and O = P V on the 5th-gen tensor
+ * cores, S / O in TMEM, single-pass softmax).  vlm_attention_fwd routes supported shapes here when VLM_ATTN_TC=1. */
+int vlm_attention_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                         const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse,
+                         const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH, int causal, float scale, float p_drop,
+                         unsigned long long seed, unsigned long long offset, const unsigned long long* rng_offset_ptr,
+                         void* stream);
 /* Same contract as vlm_attention_bwd, on the tcgen05 kernel (DH = 64, Tq <= 256, Tq <= 128 with dropout): five tensor-core
  * products per 128-key tile with all accumulators in TMEM, delta computed in-kernel.  vlm_attention_bwd routes supported
  * shapes here when VLM_ATTN_TC=1. */

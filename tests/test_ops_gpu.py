@@ -369,7 +369,7 @@ def test_layernorm_bwd_fused_dropout_and_colsum(cuda_dev):
     keep = ref_drop != 0
     assert torch.equal(dxd != 0, keep)
     assert (dxd.float() - ref_drop.float()).abs().max().item() <= 2 ** -7 * ref_drop.float().abs().max().item()
-    assert (cs - dxd.float().sum(0)).abs().max().item() < 5e-2
+    assert (cs - dxd.float().sum(0)).abs().max().item() < 2e-1   # fp32 partial sums vs a sum of 300 bf16-rounded values
     # and the forward epilogue uses the same mask
     a, w = _bf((M, 64), cuda_dev, 3), _bf((D, 64), cuda_dev, 4)
     y = ops.gemm(a, w, p_drop=0.1, seed=11, offset=5)
@@ -435,3 +435,42 @@ def test_attention_bwd_tcgen05_dropout_matches_mma_path(cuda_dev):
     torch.cuda.synchronize()
     for a, b in zip(*outs):
         assert (a - b).abs().max().item() < 4e-2 * max(1.0, a.abs().max().item())
+
+
+@pytest.mark.parametrize("B,H,Tq,Sk,causal,masked,p_drop", [
+    (2, 12, 197, 197, False, False, 0.0),   # ViT self-attention
+    (3, 12, 128, 128, True, True, 0.0),     # decoder causal self-attention with key padding
+    (2, 12, 128, 197, False, True, 0.0),    # cross-attention
+    (1, 2, 5, 3, False, False, 0.0),        # tiny / ragged
+    (2, 3, 300, 256, False, True, 0.0),     # three query tiles, max keys
+    (2, 4, 128, 128, True, False, 0.1),     # dropout: must reproduce the mma.sync kernel's mask bit for bit
+])
+def test_attention_fwd_tcgen05(cuda_dev, B, H, Tq, Sk, causal, masked, p_drop):
+    from vilmedic_b200 import ops
+    DH = 64
+    D = H * DH
+    q = _bf((B, Tq, D), cuda_dev, 3)
+    kv = _bf((B, Sk, 2 * D), cuda_dev, 4)
+    k, v = kv[:, :, :D], kv[:, :, D:]
+    kmask = None
+    if masked:
+        lens = torch.randint(max(1, Sk // 2), Sk + 1, (B,))
+        kmask = (torch.arange(Sk)[None, :] < lens[:, None]).to(torch.uint8).to(cuda_dev).contiguous()
+    o, lse = ops.attention_fwd(q, k, v, H, DH, kmask=kmask, causal=causal, p_drop=p_drop, seed=5, offset=9, force_tc=True)
+    o2, lse2 = ops.attention_fwd(q, k, v, H, DH, kmask=kmask, causal=causal, p_drop=p_drop, seed=5, offset=9)
+    torch.cuda.synchronize()
+    assert (lse - lse2).abs().max().item() < 2e-3
+    assert (o.float() - o2.float()).abs().max().item() < 2e-2
+    if p_drop == 0.0:
+        ref = _attn_ref(q.float(), k.float(), v.float(), H, DH, kmask, causal)
+        assert (o.float() - ref).abs().max().item() < 2e-2
+    # tcgen05 forward feeding the tcgen05 backward
+    do = _bf((B, Tq, D), cuda_dev, 5)
+    g1 = [torch.zeros_like(t) for t in (q, kv[:, :, :D].contiguous(), kv[:, :, D:].contiguous())]
+    g2 = [torch.zeros_like(t) for t in g1]
+    ops.attention_bwd(q, k, v, o, do, lse, g1[0], g1[1], g1[2], H, DH, kmask=kmask, causal=causal, p_drop=p_drop, seed=5, offset=9,
+                      force_tc=(Tq <= 256 and (p_drop == 0 or Tq <= 128)))
+    ops.attention_bwd(q, k, v, o2, do, lse2, g2[0], g2[1], g2[2], H, DH, kmask=kmask, causal=causal, p_drop=p_drop, seed=5, offset=9)
+    torch.cuda.synchronize()
+    for a, b in zip(g1, g2):
+        assert (a.float() - b.float()).abs().max().item() < 4e-2 * max(1.0, b.float().abs().max().item())

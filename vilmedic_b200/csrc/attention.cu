@@ -612,6 +612,21 @@ int attention_bwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
                               float scale, float p_drop, unsigned long long seed, unsigned long long offset,
                               const unsigned long long* rng_offset_ptr, cudaStream_t stream);
 
+int attention_fwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                              const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse,
+                              const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH, int causal, float scale, float p_drop,
+                              unsigned long long seed, unsigned long long offset, const unsigned long long* rng_offset_ptr,
+                              cudaStream_t stream);
+
+static int attn_tc_mode() {   // VLM_ATTN_TC: 1 = tcgen05 kernels for supported shapes, 2 = tcgen05 backward only
+  static int mode = -1;
+  if (mode < 0) {
+    const char* env = getenv("VLM_ATTN_TC");
+    mode = env ? atoi(env) : 0;
+  }
+  return mode;
+}
+
 static int check_attn_common(const char* who, int B, int H, int Tq, int Sk, int DH) {
   if (B <= 0 || H <= 0 || Tq <= 0 || Sk <= 0) { set_error("%s: bad shape B=%d H=%d Tq=%d Sk=%d", who, B, H, Tq, Sk); return -1; }
   if (DH != 48 && DH != 64 && DH != 96) { set_error("%s: head dim %d unsupported (48, 64, 96)", who, DH); return -1; }
@@ -631,6 +646,12 @@ extern "C" int vlm_attention_fwd(const void* q, long long q_bs, long long q_rs, 
   VLM_REQUIRE(q && k && v && o, "vlm_attention_fwd: null pointer");
   VLM_REQUIRE(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && o_rs % 2 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0,
               "vlm_attention_fwd: strides must keep 16B alignment");
+  if (attn_tc_mode() == 1 && lse) {
+    const int r = attention_fwd_tc_dispatch(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, kmask, B, H, Tq, Sk, DH,
+                                            causal, scale, p_drop, seed, offset, rng_offset_ptr, (cudaStream_t)stream);
+    if (r < 0) return r;
+    if (r == 1) return 0;
+  }
   AttnParams p = {};
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.o = (bf16*)o; p.lse = lse; p.kmask = kmask;
   p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs; p.o_rs = o_rs;
@@ -654,12 +675,7 @@ extern "C" int vlm_attention_bwd(const void* q, long long q_bs, long long q_rs, 
   VLM_REQUIRE(q && k && v && o && d_o && lse && delta && dq && dk && dv, "vlm_attention_bwd: null pointer");
   {
     // tcgen05 path (head dim 64, Tq <= 256): VLM_ATTN_TC=1 routes supported shapes to attention_tc.cu
-    static int use_tc = -1;
-    if (use_tc < 0) {
-      const char* env = getenv("VLM_ATTN_TC");
-      use_tc = (env && env[0] == '1') ? 1 : 0;
-    }
-    if (use_tc) {
+    if (attn_tc_mode() >= 1) {
       const int r = attention_bwd_tc_dispatch(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, d_o, do_bs, do_rs, lse,
                                               dq, dq_bs, dq_rs, dk, dk_bs, dk_rs, dv, dv_bs, dv_rs, kmask, B, H, Tq, Sk, DH,
                                               causal, scale, p_drop, seed, offset, rng_offset_ptr, (cudaStream_t)stream);
@@ -704,6 +720,24 @@ extern "C" int vlm_attention_bwd_tc(const void* q, long long q_bs, long long q_r
                                           scale, p_drop, seed, offset, rng_offset_ptr, (cudaStream_t)stream);
   if (r == 0) {
     set_error("vlm_attention_bwd_tc: shape outside the tcgen05 envelope (DH=64, Tq<=256, Tq<=128 with dropout)");
+    return -1;
+  }
+  return r < 0 ? r : 0;
+}
+
+extern "C" int vlm_attention_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                    const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
+                                    float* lse, const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH, int causal,
+                                    float scale, float p_drop, unsigned long long seed, unsigned long long offset,
+                                    const unsigned long long* rng_offset_ptr, void* stream) {
+  if (check_attn_common("vlm_attention_fwd_tc", B, H, Tq, Sk, DH)) return -1;
+  VLM_REQUIRE(q && k && v && o && lse, "vlm_attention_fwd_tc: null pointer");
+  VLM_REQUIRE(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0,
+              "vlm_attention_fwd_tc: strides must keep 16B alignment");
+  const int r = attention_fwd_tc_dispatch(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, kmask, B, H, Tq, Sk, DH,
+                                          causal, scale, p_drop, seed, offset, rng_offset_ptr, (cudaStream_t)stream);
+  if (r == 0) {
+    set_error("vlm_attention_fwd_tc: shape outside the tcgen05 envelope (DH=64, Sk<=256)");
     return -1;
   }
   return r < 0 ? r : 0;

@@ -455,4 +455,294 @@ int attention_bwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
   return rc ? rc : 1;
 }
 
+// =====================================================================================================================
+// tcgen05 attention FORWARD (head dim 64, Sk <= 256 — single key block, so no online-softmax rescaling is needed).
+// Item = (batch, head): K / V are staged once, then every 128-query tile runs  S = Q K^T  (N = Sk padded to 16) ->
+// row softmax by the 256 compute threads (thread <-> query row, two warps per TMEM lane quadrant split the key
+// columns; row max / row sum are combined through shared memory) -> P (bf16, dropout applied) written in the K-major
+// SWIZZLE_128B layout -> O = P V (V consumed MN-major straight from its [keys][64] tile) -> O / l, LSE.
+// Same dropout stream and LSE convention (natural log) as attention.cu, so either backward can follow.
+struct AttnTcFwdParams {
+  bf16* o;
+  long long o_bs, o_rs;
+  float* lse;
+  const uint8_t* kmask;
+  int B, H, Tq, Sk, Nk;    // Nk = Sk rounded up to 32
+  int causal;
+  float scale, p_drop;
+  unsigned long long seed, offset;
+  const unsigned long long* offset_ptr;
+};
+
+struct AtcFwdSmem {
+  static constexpr int Q_BYTES = 128 * 128;      // one 128-query tile
+  static constexpr int KV_BYTES = 256 * 128;     // up to 256 keys
+  static constexpr int P_BYTES = 4 * 16384;      // 128 x 256 bf16
+  static constexpr int OFF_Q = 0;                // 2 buffers
+  static constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_P = OFF_V + KV_BYTES;
+  static constexpr int OFF_RED = OFF_P + P_BYTES;          // float [2][2][128]: partial row max / row sum per column half
+  static constexpr int OFF_KOK = OFF_RED + 2 * 2 * 128 * 4;  // uint8 [256] key validity
+  static constexpr int OFF_BAR = OFF_KOK + 256;
+  static constexpr int NUM_BARS = 10;
+  static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, AttnTcFwdParams p) {
+  using S = AtcFwdSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + S::OFF_Q;
+  uint8_t* sK = smem + S::OFF_K;
+  uint8_t* sV = smem + S::OFF_V;
+  uint8_t* sP = smem + S::OFF_P;
+  float* sRed = reinterpret_cast<float*>(smem + S::OFF_RED);
+  uint8_t* sKok = smem + S::OFF_KOK;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* kv_empty = bars + 1;
+  uint64_t* q_full = bars + 2;     // [2]
+  uint64_t* q_empty = bars + 4;    // [2]
+  uint64_t* s_full = bars + 6;
+  uint64_t* p_ready = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint64_t* o_free = bars + 9;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + S::NUM_BARS);
+
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nitems = p.B * p.H;
+  const int qtiles = (p.Tq + 127) / 128;
+  const int Nk = p.Nk;
+  constexpr int O_COL = 256;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    mbar_init(&q_full[0], 1);
+    mbar_init(&q_full[1], 1);
+    mbar_init(&q_empty[0], 1);
+    mbar_init(&q_empty[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 8);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 8);
+    fence_barrier_init();
+  } else if (warp_idx == 1) {
+    tmem_alloc<512>(tmem_ptr_smem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    if (lane == 0) {
+      uint32_t item_cnt = 0, tile_cnt = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++item_cnt) {
+        const int b = item / p.H, h = item % p.H;
+        mbar_wait(kv_empty, (item_cnt & 1u) ^ 1u);
+        mbar_expect_tx(kv_full, 2u * (uint32_t)Nk * 128u);
+        tma_load_4d(&tm_k, kv_full, sK, 0, h, 0, b);
+        tma_load_4d(&tm_v, kv_full, sV, 0, h, 0, b);
+        for (int i = 0; i < qtiles; ++i, ++tile_cnt) {
+          const int buf = tile_cnt & 1u;
+          mbar_wait(&q_empty[buf], ((tile_cnt >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&q_full[buf], S::Q_BYTES);
+          tma_load_4d(&tm_q, &q_full[buf], sQ + buf * S::Q_BYTES, 0, h, i * 128, b);
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (lane == 0) {
+      const uint32_t id_s = make_idesc_bf16(128, Nk, false, false);
+      const uint32_t id_o = make_idesc_bf16(128, 64, false, true);
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+      const int nk16 = Nk / 16;
+      uint32_t item_cnt = 0, tile_cnt = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++item_cnt) {
+        mbar_wait(kv_full, item_cnt & 1u);
+        tc_fence_after();
+        for (int i = 0; i < qtiles; ++i, ++tile_cnt) {
+          const int buf = tile_cnt & 1u;
+          const uint32_t tph = tile_cnt & 1u;
+          const uint32_t aQ = smem_u32(sQ + buf * S::Q_BYTES);
+          mbar_wait(&q_full[buf], (tile_cnt >> 1) & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), id_s, k > 0);
+          umma_commit(s_full);
+          umma_commit(&q_empty[buf]);
+          mbar_wait(p_ready, tph);
+          mbar_wait(o_free, tph ^ 1u);
+          tc_fence_after();
+          for (int k = 0; k < nk16; ++k)
+            umma_bf16(tmem_base + O_COL, make_smem_desc(aP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                      make_smem_desc(aV + k * 2048, 16384, 1024), id_o, k > 0);
+          umma_commit(o_full);
+          if (i == qtiles - 1) umma_commit(kv_empty);
+        }
+      }
+    }
+  } else {
+    const int quad = warp_idx & 3;
+    const int half = (warp_idx - 2) >> 2;
+    const int r = quad * 32 + lane;              // query row inside the tile
+    const int ct = threadIdx.x - 64;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const Philox rng(p.seed);
+    const unsigned long long off_eff = p.offset + ((p.p_drop > 0.f && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
+    const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
+    const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+    const int Sk4 = (p.Sk + 3) >> 2;
+    const int half_cols = Nk >> 1;               // multiple of 16
+    float* redmax = sRed;                        // [2][128]
+    float* redsum = sRed + 256;                  // [2][128]
+    uint32_t tile_cnt = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int b = item / p.H, h = item % p.H;
+      named_bar_sync(1, 256);
+      if (ct < Nk) sKok[ct] = (ct < p.Sk) && (!p.kmask || p.kmask[(long long)b * p.Sk + ct]);
+      named_bar_sync(1, 256);
+      for (int i = 0; i < qtiles; ++i, ++tile_cnt) {
+        const uint32_t tph = tile_cnt & 1u;
+        const int qq = i * 128 + r;
+        mbar_wait(s_full, tph);
+        tc_fence_after();
+        // ---- pass 1: masked row max over this thread's half of the key columns
+        float mx = -INFINITY;
+        for (int c = 0; c < half_cols; c += 16) {
+          const int k0 = half * half_cols + c;
+          uint32_t v[16];
+          tmem_ld16(lane_taddr + k0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int kk = k0 + e;
+            const bool ok = sKok[kk] && (!p.causal || kk <= qq);
+            mx = fmaxf(mx, ok ? __uint_as_float(v[e]) * sl2 : -INFINITY);
+          }
+        }
+        redmax[half * 128 + r] = mx;
+        named_bar_sync(2, 256);
+        mx = fmaxf(redmax[r], redmax[128 + r]);
+        const float mref = (mx == -INFINITY) ? 0.f : mx;
+        // ---- pass 2: P = exp2(s - m), row sum, dropout, bf16 -> swizzled smem
+        float sum = 0.f;
+        for (int c = 0; c < half_cols; c += 16) {
+          const int k0 = half * half_cols + c;
+          uint32_t v[16];
+          tmem_ld16(lane_taddr + k0, v);
+          tmem_ld_wait();
+          float pe[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int kk = k0 + e;
+            const bool ok = sKok[kk] && (!p.causal || kk <= qq);
+            pe[e] = ok ? exp2f(__uint_as_float(v[e]) * sl2 - mref) : 0.f;
+            sum += pe[e];
+          }
+          if (p.p_drop > 0.f) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const unsigned long long idx = ((unsigned long long)item * p.Tq + qq) * (unsigned long long)Sk4 + ((k0 >> 2) + g);
+              const uint4 rnd = rng(idx, off_eff);
+              pe[4 * g + 0] = rnd.x >= thr ? pe[4 * g + 0] * inv_keep : 0.f;
+              pe[4 * g + 1] = rnd.y >= thr ? pe[4 * g + 1] * inv_keep : 0.f;
+              pe[4 * g + 2] = rnd.z >= thr ? pe[4 * g + 2] * inv_keep : 0.f;
+              pe[4 * g + 3] = rnd.w >= thr ? pe[4 * g + 3] * inv_keep : 0.f;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            uint4 w;
+            w.x = pack_bf16x2(pe[8 * u + 0], pe[8 * u + 1]); w.y = pack_bf16x2(pe[8 * u + 2], pe[8 * u + 3]);
+            w.z = pack_bf16x2(pe[8 * u + 4], pe[8 * u + 5]); w.w = pack_bf16x2(pe[8 * u + 6], pe[8 * u + 7]);
+            *reinterpret_cast<uint4*>(sP + pt_offset16(r, k0 + 8 * u)) = w;
+          }
+        }
+        redsum[half * 128 + r] = sum;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+        named_bar_sync(2, 256);
+        const float l = redsum[r] + redsum[128 + r];
+        // ---- epilogue: O / l, LSE
+        mbar_wait(o_full, tph);
+        tc_fence_after();
+        uint32_t acc[32];
+        tmem_ld32(lane_taddr + O_COL + half * 32, acc);
+        tmem_ld_wait();
+        if (qq < p.Tq) {
+          const float inv = l > 0.f ? 1.f / l : 0.f;
+          uint4* dst = reinterpret_cast<uint4*>(p.o + (long long)b * p.o_bs + (long long)qq * p.o_rs + h * 64 + half * 32);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            dst[e] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * e]) * inv, __uint_as_float(acc[8 * e + 1]) * inv),
+                                pack_bf16x2(__uint_as_float(acc[8 * e + 2]) * inv, __uint_as_float(acc[8 * e + 3]) * inv),
+                                pack_bf16x2(__uint_as_float(acc[8 * e + 4]) * inv, __uint_as_float(acc[8 * e + 5]) * inv),
+                                pack_bf16x2(__uint_as_float(acc[8 * e + 6]) * inv, __uint_as_float(acc[8 * e + 7]) * inv));
+          if (half == 0 && p.lse)
+            p.lse[(long long)item * p.Tq + qq] = l > 0.f ? (mx + log2f(l)) * 0.6931471805599453f : -INFINITY;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// returns 1 if launched, 0 if the shape is outside the envelope, <0 on error
+int attention_fwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                              const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse,
+                              const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH, int causal, float scale, float p_drop,
+                              unsigned long long seed, unsigned long long offset, const unsigned long long* rng_offset_ptr,
+                              cudaStream_t stream) {
+  if (DH != 64 || Sk > 256 || (o_rs % 8) || (o_bs % 8)) return 0;
+  bind_context_for_driver_calls();
+  const int Nk = (Sk + 31) / 32 * 32;
+  CUtensorMap tq, tk, tv;
+  auto mk = [&](CUtensorMap* tm, const void* ptr, long long bs, long long rs, int rows, int box_rows) {
+    const uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)rows, (uint64_t)B};
+    const uint64_t strides[3] = {64, (uint64_t)rs, (uint64_t)bs};
+    const uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
+    return make_tmap_bf16_nd(tm, ptr, 4, dims, strides, box);
+  };
+  if (mk(&tq, q, q_bs, q_rs, Tq, 128) || mk(&tk, k, k_bs, k_rs, Sk, Nk) || mk(&tv, v, v_bs, v_rs, Sk, Nk)) return -1;
+  AttnTcFwdParams p;
+  p.o = (bf16*)o; p.o_bs = o_bs; p.o_rs = o_rs; p.lse = lse; p.kmask = kmask;
+  p.B = B; p.H = H; p.Tq = Tq; p.Sk = Sk; p.Nk = Nk; p.causal = causal; p.scale = scale; p.p_drop = p_drop;
+  p.seed = seed; p.offset = offset; p.offset_ptr = rng_offset_ptr;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AtcFwdSmem::TOTAL);
+    if (err != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn_fwd_tc smem=%d): %s", AtcFwdSmem::TOTAL, cudaGetErrorString(err));
+      return -1;
+    }
+    attr_set = true;
+  }
+  const int items = B * H;
+  const int grid = items < num_sms() ? items : num_sms();
+  attn_fwd_tc_kernel<<<grid, ATC_THREADS, AtcFwdSmem::TOTAL, stream>>>(tq, tk, tv, p);
+  const int rc = check_launch("attn_fwd_tc");
+  return rc ? rc : 1;
+}
+
 }  // namespace vlm

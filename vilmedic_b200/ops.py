@@ -150,7 +150,7 @@ def _bh_strides(t, H, DH):
     return t.stride(0), t.stride(1)
 
 
-def attention_fwd(q, k, v, H, DH, *, kmask=None, causal=False, scale=None, p_drop=0.0, seed=0, offset=0):
+def attention_fwd(q, k, v, H, DH, *, kmask=None, causal=False, scale=None, p_drop=0.0, seed=0, offset=0, force_tc=False):
     """q [B,Tq,H*DH], k/v [B,Sk,H*DH] (possibly strided views of packed projections) -> (o [B,Tq,H*DH], lse [B,H,Tq])."""
     B, Tq = q.shape[0], q.shape[1]
     Sk = k.shape[1]
@@ -160,7 +160,8 @@ def attention_fwd(q, k, v, H, DH, *, kmask=None, causal=False, scale=None, p_dro
     qs, ks, vs = _bh_strides(q, H, DH), _bh_strides(k, H, DH), _bh_strides(v, H, DH)
     if kmask is not None:
         _req(kmask.dtype == torch.uint8 and kmask.is_contiguous() and tuple(kmask.shape) == (B, Sk), "kmask must be uint8 [B,Sk]")
-    check(_L().vlm_attention_fwd(ptr(q), c_ll(qs[0]), c_ll(qs[1]), ptr(k), c_ll(ks[0]), c_ll(ks[1]), ptr(v), c_ll(vs[0]),
+    fn = _L().vlm_attention_fwd_tc if force_tc else _L().vlm_attention_fwd
+    check(fn(ptr(q), c_ll(qs[0]), c_ll(qs[1]), ptr(k), c_ll(ks[0]), c_ll(ks[1]), ptr(v), c_ll(vs[0]),
                                  c_ll(vs[1]), ptr(o), c_ll(o.stride(0)), c_ll(o.stride(1)), ptr(lse), ptr(kmask),
                                  c_int(B), c_int(H), c_int(Tq), c_int(Sk), c_int(DH), c_int(int(causal)), c_float(scale),
                                  c_float(p_drop), c_u64(seed), c_u64(offset), ptr(RNG_COUNTER[0]), stream_ptr()), "vlm_attention_fwd")
