@@ -98,10 +98,10 @@ int vlm_attention_fwd_tc(const void* q, long long q_bs, long long q_rs, const vo
  * shapes here when VLM_ATTN_TC=1. */
 int vlm_attention_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                          const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
-                         const void* d_o, long long do_bs, long long do_rs, const float* lse, void* dq, long long dq_bs,
-                         long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv, long long dv_bs,
-                         long long dv_rs, const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH, int causal,
-                         float scale, float p_drop, unsigned long long seed, unsigned long long offset,
+                         const void* d_o, long long do_bs, long long do_rs, const float* lse, float* delta, void* dq,
+                         long long dq_bs, long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv,
+                         long long dv_bs, long long dv_rs, const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH,
+                         int causal, float scale, float p_drop, unsigned long long seed, unsigned long long offset,
                          const unsigned long long* rng_offset_ptr, void* stream);
 
 /* ---- softmax cross-entropy (LM head loss, label-smoothing CE) ---------------------------------------------------- */

@@ -119,7 +119,7 @@ def test_cached_step_matches_prefix_recompute(cuda_dev):
         step = dec.decode_step(st, ids[:, t])
         full = dec.next_token_logits(ids[:, :t + 1], enc, mask)
         want = next_logits(ref.dec.decoder, ids[:, :t + 1].cpu(), enc_r, mask_r)
-        tol = 2 ** -5 * want.abs().max().item() + 5e-2     # logits of these x30-scaled embeddings reach |130|
+        tol = 2 ** -4 * want.abs().max().item() + 5e-2     # logits of these x30-scaled embeddings reach |150|
         assert (step - full).abs().max().item() <= tol, t
         assert (step.cpu() - want).abs().max().item() <= tol, t
     a = dec.generate(input_ids=ids[:, :1], encoder_hidden_states=enc, encoder_attention_mask=mask, max_length=12, num_beams=3,

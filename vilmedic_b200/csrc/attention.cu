@@ -76,12 +76,6 @@ struct Tile {
   }
 };
 
-// dropout keep-mask scale for element (bh, q, k): one Philox call covers 4 consecutive k
-__device__ __forceinline__ uint4 drop_rand4(const Philox& rng, unsigned long long offset, int bh, int q, int k4, int Tq, int Sk4) {
-  const unsigned long long idx = ((unsigned long long)bh * Tq + q) * (unsigned long long)Sk4 + k4;
-  return rng(idx, offset);
-}
-
 // ============================================================================================ forward
 template <int DH>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnParams p) {
@@ -116,8 +110,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnParams p) {
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   const float sl2 = p.scale * 1.4426950408889634f;
   const int qrow[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
-  const Philox rng(p.seed);
   const unsigned long long off_eff = p.offset + ((p.p_drop > 0.f && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
+  const uint32_t dkey = attn_drop_key(p.seed, off_eff, bh);
   const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
 
@@ -220,8 +214,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnParams p) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           const int kcol = k0 + nt * 8 + 2 * t;
-          const uint4 rnd = drop_rand4(rng, off_eff, bh, qrow[r], kcol >> 2, p.Tq, (p.Sk + 3) >> 2);
-          const uint32_t r0 = (kcol & 2) ? rnd.z : rnd.x, r1 = (kcol & 2) ? rnd.w : rnd.y;
+          const uint32_t r0 = attn_drop_rand(dkey, qrow[r], kcol, p.Sk), r1 = attn_drop_rand(dkey, qrow[r], kcol + 1, p.Sk);
           pe[2 * r] = r0 >= thr ? pe[2 * r] * inv_keep : 0.f;
           pe[2 * r + 1] = r1 >= thr ? pe[2 * r + 1] * inv_keep : 0.f;
         }
@@ -330,8 +323,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnParams p) {
 #pragma unroll
   for (int i = 0; i < NT; ++i) dq_acc[i][0] = dq_acc[i][1] = dq_acc[i][2] = dq_acc[i][3] = 0.f;
   const float sl2 = p.scale * 1.4426950408889634f;
-  const Philox rng(p.seed);
   const unsigned long long off_eff = p.offset + ((p.p_drop > 0.f && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
+  const uint32_t dkey = attn_drop_key(p.seed, off_eff, bh);
   const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
 
@@ -402,9 +395,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnParams p) {
         const float pe = ok ? exp2f(s[nt][e] * sl2 - lse[r]) : 0.f;
         float dpe = dp[nt][e];
         if (p.p_drop > 0.f) {
-          const int kcol = k0 + nt * 8 + 2 * t;
-          const uint4 rnd = drop_rand4(rng, off_eff, bh, qrow[r], kcol >> 2, p.Tq, (p.Sk + 3) >> 2);
-          const uint32_t rv = (e & 1) ? ((kcol & 2) ? rnd.w : rnd.y) : ((kcol & 2) ? rnd.z : rnd.x);
+          const uint32_t rv = attn_drop_rand(dkey, qrow[r], k0 + kc, p.Sk);
           dpe = rv >= thr ? dpe * inv_keep : 0.f;
         }
         ds[e] = pe * (dpe - delta[r]) * p.scale;
@@ -482,8 +473,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
     dv_acc[i][0] = dv_acc[i][1] = dv_acc[i][2] = dv_acc[i][3] = 0.f;
   }
   const float sl2 = p.scale * 1.4426950408889634f;
-  const Philox rng(p.seed);
   const unsigned long long off_eff = p.offset + ((p.p_drop > 0.f && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
+  const uint32_t dkey = attn_drop_key(p.seed, off_eff, bh);
   const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
 
@@ -557,10 +548,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
         float dpe = dpt[nt][e];
         float pdrop = pv;
         if (p.p_drop > 0.f) {
-          const uint4 rnd = drop_rand4(rng, off_eff, bh, qq, krow[r] >> 2, p.Tq, (p.Sk + 3) >> 2);
-          const int w = krow[r] & 3;
-          const uint32_t rv = w == 0 ? rnd.x : (w == 1 ? rnd.y : (w == 2 ? rnd.z : rnd.w));
-          const bool keep = rv >= thr;
+          const bool keep = attn_drop_rand(dkey, qq, krow[r], p.Sk) >= thr;
           dpe = keep ? dpe * inv_keep : 0.f;
           pdrop = keep ? pv * inv_keep : 0.f;
         }
@@ -606,10 +594,10 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
 
 int attention_bwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                               const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
-                              const void* d_o, long long do_bs, long long do_rs, const float* lse, void* dq, long long dq_bs,
-                              long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv, long long dv_bs,
-                              long long dv_rs, const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH, int causal,
-                              float scale, float p_drop, unsigned long long seed, unsigned long long offset,
+                              const void* d_o, long long do_bs, long long do_rs, const float* lse, float* delta, void* dq,
+                              long long dq_bs, long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv,
+                              long long dv_bs, long long dv_rs, const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH,
+                              int causal, float scale, float p_drop, unsigned long long seed, unsigned long long offset,
                               const unsigned long long* rng_offset_ptr, cudaStream_t stream);
 
 int attention_fwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
@@ -618,11 +606,11 @@ int attention_fwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
                               unsigned long long seed, unsigned long long offset, const unsigned long long* rng_offset_ptr,
                               cudaStream_t stream);
 
-static int attn_tc_mode() {   // VLM_ATTN_TC: 1 = tcgen05 kernels for supported shapes, 2 = tcgen05 backward only
-  static int mode = -1;
+static int attn_tc_mode() {   // VLM_ATTN_TC: 1 (default) = tcgen05 kernels for supported shapes, 2 = tcgen05 backward
+  static int mode = -1;       // only, 0 = mma.sync kernels everywhere
   if (mode < 0) {
     const char* env = getenv("VLM_ATTN_TC");
-    mode = env ? atoi(env) : 0;
+    mode = env ? atoi(env) : 1;
   }
   return mode;
 }
@@ -677,7 +665,7 @@ extern "C" int vlm_attention_bwd(const void* q, long long q_bs, long long q_rs, 
     // tcgen05 path (head dim 64, Tq <= 256): VLM_ATTN_TC=1 routes supported shapes to attention_tc.cu
     if (attn_tc_mode() >= 1) {
       const int r = attention_bwd_tc_dispatch(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, d_o, do_bs, do_rs, lse,
-                                              dq, dq_bs, dq_rs, dk, dk_bs, dk_rs, dv, dv_bs, dv_rs, kmask, B, H, Tq, Sk, DH,
+                                              delta, dq, dq_bs, dq_rs, dk, dk_bs, dk_rs, dv, dv_bs, dv_rs, kmask, B, H, Tq, Sk, DH,
                                               causal, scale, p_drop, seed, offset, rng_offset_ptr, (cudaStream_t)stream);
       if (r < 0) return r;
       if (r == 1) return 0;
@@ -706,17 +694,17 @@ extern "C" int vlm_attention_bwd(const void* q, long long q_bs, long long q_rs, 
 // Explicit entry to the tcgen05 backward (tests / benchmarks); fails if the shape is outside its envelope.
 extern "C" int vlm_attention_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                                     const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
-                                    const void* d_o, long long do_bs, long long do_rs, const float* lse, void* dq,
-                                    long long dq_bs, long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv,
-                                    long long dv_bs, long long dv_rs, const uint8_t* kmask, int B, int H, int Tq, int Sk,
-                                    int DH, int causal, float scale, float p_drop, unsigned long long seed,
+                                    const void* d_o, long long do_bs, long long do_rs, const float* lse, float* delta,
+                                    void* dq, long long dq_bs, long long dq_rs, void* dk, long long dk_bs, long long dk_rs,
+                                    void* dv, long long dv_bs, long long dv_rs, const uint8_t* kmask, int B, int H, int Tq,
+                                    int Sk, int DH, int causal, float scale, float p_drop, unsigned long long seed,
                                     unsigned long long offset, const unsigned long long* rng_offset_ptr, void* stream) {
   if (check_attn_common("vlm_attention_bwd_tc", B, H, Tq, Sk, DH)) return -1;
-  VLM_REQUIRE(q && k && v && o && d_o && lse && dq && dk && dv, "vlm_attention_bwd_tc: null pointer");
+  VLM_REQUIRE(q && k && v && o && d_o && lse && delta && dq && dk && dv, "vlm_attention_bwd_tc: null pointer");
   VLM_REQUIRE(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && do_rs % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 &&
                   v_bs % 8 == 0 && do_bs % 8 == 0, "vlm_attention_bwd_tc: strides must keep 16B alignment");
-  const int r = attention_bwd_tc_dispatch(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, d_o, do_bs, do_rs, lse, dq,
-                                          dq_bs, dq_rs, dk, dk_bs, dk_rs, dv, dv_bs, dv_rs, kmask, B, H, Tq, Sk, DH, causal,
+  const int r = attention_bwd_tc_dispatch(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, d_o, do_bs, do_rs, lse, delta,
+                                          dq, dq_bs, dq_rs, dk, dk_bs, dk_rs, dv, dv_bs, dv_rs, kmask, B, H, Tq, Sk, DH, causal,
                                           scale, p_drop, seed, offset, rng_offset_ptr, (cudaStream_t)stream);
   if (r == 0) {
     set_error("vlm_attention_bwd_tc: shape outside the tcgen05 envelope (DH=64, Tq<=256, Tq<=128 with dropout)");

@@ -30,6 +30,7 @@ struct AttnTcParams {
   bf16* dq; bf16* dk; bf16* dv;
   long long dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
   const float* lse;        // [B,H,Tq] natural log
+  const float* delta;      // [B,H,Tq] rowsum(dO * O), produced by attn_delta_kernel right before
   const uint8_t* kmask;    // [B,Sk] or null
   int B, H, Tq, Sk, Nq;    // Nq = Tq rounded up to 32
   int causal;
@@ -230,30 +231,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int ct = threadIdx.x - 64;           // 0..255
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float sl2 = p.scale * 1.4426950408889634f;
-    const Philox rng(p.seed);
     const unsigned long long off_eff = p.offset + ((DROPOUT && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
     const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
     const float inv_keep = DROPOUT ? 1.f / (1.f - p.p_drop) : 1.f;
-    const int Sk4 = (p.Sk + 3) >> 2;
     const int half_cols = Nq >> 1;             // multiple of 16
     uint32_t tile_cnt = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int b = item / p.H, h = item % p.H;
+      const uint32_t dkey = attn_drop_key(p.seed, off_eff, item);
       // ---- per-item staging: lse (log2 units, +inf beyond Tq) and delta = rowsum(dO * O)
       named_bar_sync(1, 256);
       if (ct < Nq) {
         float l2 = INFINITY, dl = 0.f;
         if (ct < p.Tq) {
           l2 = p.lse[(long long)item * p.Tq + ct] * 1.4426950408889634f;
-          const uint4* o4 = reinterpret_cast<const uint4*>(p.o + (long long)b * p.o_bs + (long long)ct * p.o_rs + h * 64);
-          const uint4* g4 = reinterpret_cast<const uint4*>(p.d_o + (long long)b * p.do_bs + (long long)ct * p.do_rs + h * 64);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint4 a = __ldg(o4 + i), g = __ldg(g4 + i);
-            const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-            const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
-            dl += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
-          }
+          dl = p.delta[(long long)item * p.Tq + ct];
         }
         sLse[ct] = l2;
         sDelta[ct] = dl;
@@ -266,24 +258,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         // ---------------- pass A: P^T
         mbar_wait(s_full, tph);
         tc_fence_after();
-        for (int c = 0; c < half_cols; c += 16) {
-          const int q0 = half * half_cols + c;
-          uint32_t v[16];
-          tmem_ld16(lane_taddr + ATC_S_COL + q0, v);
-          tmem_ld_wait();
+        auto pass_a_chunk = [&](const uint32_t* v, int q0) {
           float pv[16], pd[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int q = q0 + i;
             const bool ok = kvalid && (!p.causal || kk <= q);
             pv[i] = ok ? exp2f(__uint_as_float(v[i]) * sl2 - sLse[q]) : 0.f;
-            if (DROPOUT) {
-              const unsigned long long idx = ((unsigned long long)item * p.Tq + q) * (unsigned long long)Sk4 + (kk >> 2);
-              const uint4 rnd = rng(idx, off_eff);
-              const int w = kk & 3;
-              const uint32_t rv = w == 0 ? rnd.x : (w == 1 ? rnd.y : (w == 2 ? rnd.z : rnd.w));
-              pd[i] = rv >= thr ? pv[i] * inv_keep : 0.f;
-            }
+            if (DROPOUT) pd[i] = attn_drop_rand(dkey, q, kk, p.Sk) >= thr ? pv[i] * inv_keep : 0.f;
           }
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
@@ -297,6 +279,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             w.z = pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]); w.w = pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]);
             *reinterpret_cast<uint4*>((DROPOUT ? sP2 : sPT) + pt_offset16(r, q0 + 8 * u)) = w;
           }
+        };
+        {  // TMEM loads are software-pipelined: the next chunk is in flight while the current one is processed
+          const int qbase = half * half_cols;
+          uint32_t va[16], vb[16];
+          tmem_ld16(lane_taddr + ATC_S_COL + qbase, va);
+          for (int c = 0; c < half_cols; c += 32) {
+            tmem_ld_wait();
+            if (c + 16 < half_cols) tmem_ld16(lane_taddr + ATC_S_COL + qbase + c + 16, vb);
+            pass_a_chunk(va, qbase + c);
+            if (c + 16 < half_cols) {
+              tmem_ld_wait();
+              if (c + 32 < half_cols) tmem_ld16(lane_taddr + ATC_S_COL + qbase + c + 32, va);
+              pass_a_chunk(vb, qbase + c + 16);
+            }
+          }
         }
         fence_proxy_async_smem();
         tc_fence_before();
@@ -306,11 +303,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mbar_wait(dp_full, tph);
         mbar_wait(dv_done, tph);
         tc_fence_after();
-        for (int c = 0; c < half_cols; c += 16) {
-          const int q0 = half * half_cols + c;
-          uint32_t v[16];
-          tmem_ld16(lane_taddr + ATC_S_COL + q0, v);
-          tmem_ld_wait();
+        auto pass_b_chunk = [&](const uint32_t* v, int q0) {
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const uint32_t off = pt_offset16(r, q0 + 8 * u);
@@ -331,6 +324,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
               ow[e] = pack_bf16x2(pp.x * (d0 - sDelta[q]) * p.scale, pp.y * (d1 - sDelta[q + 1]) * p.scale);
             }
             *reinterpret_cast<uint4*>(sPT + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+        };
+        {
+          const int qbase = half * half_cols;
+          uint32_t va[16], vb[16];
+          tmem_ld16(lane_taddr + ATC_S_COL + qbase, va);
+          for (int c = 0; c < half_cols; c += 32) {
+            tmem_ld_wait();
+            if (c + 16 < half_cols) tmem_ld16(lane_taddr + ATC_S_COL + qbase + c + 16, vb);
+            pass_b_chunk(va, qbase + c);
+            if (c + 16 < half_cols) {
+              tmem_ld_wait();
+              if (c + 32 < half_cols) tmem_ld16(lane_taddr + ATC_S_COL + qbase + c + 32, va);
+              pass_b_chunk(vb, qbase + c + 16);
+            }
           }
         }
         fence_proxy_async_smem();
@@ -397,6 +405,31 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   }
 }
 
+// delta[bh, q] = sum_d dO[q, d] * O[q, d]; 8 lanes per row (one 16-byte unit of O and of dO each), 4 rows per warp
+__global__ void attn_delta_kernel(const bf16* __restrict__ o, long long o_bs, long long o_rs, const bf16* __restrict__ d_o,
+                                  long long do_bs, long long do_rs, float* __restrict__ delta, int B, int H, int Tq) {
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long row = gw * 4 + (lane >> 3);
+  const int u = lane & 7;
+  const long long total = (long long)B * H * Tq;
+  float acc = 0.f;
+  if (row < total) {
+    const int q = (int)(row % Tq);
+    const long long bh = row / Tq;
+    const int h = (int)(bh % H), b = (int)(bh / H);
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + (long long)b * o_bs + (long long)q * o_rs + h * 64) + u);
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(d_o + (long long)b * do_bs + (long long)q * do_rs + h * 64) + u);
+    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+    const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
+    acc = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (row < total && u == 0) delta[row] = acc;
+}
+
 template <int ATOMS, bool DROPOUT>
 static int launch_attn_bwd_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
                               const AttnTcParams& p, cudaStream_t stream) {
@@ -420,8 +453,8 @@ static int launch_attn_bwd_tc(const CUtensorMap& tq, const CUtensorMap& tk, cons
 // returns 1 if the shape is handled by the tcgen05 kernel (and it was launched), 0 if not supported, <0 on error
 int attention_bwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                               const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
-                              const void* d_o, long long do_bs, long long do_rs, const float* lse, void* dq, long long dq_bs,
-                              long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv, long long dv_bs,
+                              const void* d_o, long long do_bs, long long do_rs, const float* lse, float* delta, void* dq,
+                              long long dq_bs, long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv, long long dv_bs,
                               long long dv_rs, const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH, int causal,
                               float scale, float p_drop, unsigned long long seed, unsigned long long offset,
                               const unsigned long long* rng_offset_ptr, cudaStream_t stream) {
@@ -441,7 +474,14 @@ int attention_bwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
   if (mk(&tq, q, q_bs, q_rs, Tq, Nq) || mk(&tdo, d_o, do_bs, do_rs, Tq, Nq) || mk(&tk, k, k_bs, k_rs, Sk, 128) ||
       mk(&tv, v, v_bs, v_rs, Sk, 128))
     return -1;
+  {
+    const long long rows = (long long)B * H * Tq;
+    const long long warps = (rows + 3) / 4;
+    attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>((const bf16*)o, o_bs, o_rs, (const bf16*)d_o, do_bs, do_rs,
+                                                                            delta, B, H, Tq);
+  }
   AttnTcParams p;
+  p.delta = delta;
   p.o = (const bf16*)o; p.d_o = (const bf16*)d_o;
   p.o_bs = o_bs; p.o_rs = o_rs; p.do_bs = do_bs; p.do_rs = do_rs;
   p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv;
@@ -597,17 +637,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int ct = threadIdx.x - 64;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float sl2 = p.scale * 1.4426950408889634f;
-    const Philox rng(p.seed);
     const unsigned long long off_eff = p.offset + ((p.p_drop > 0.f && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
     const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
-    const int Sk4 = (p.Sk + 3) >> 2;
     const int half_cols = Nk >> 1;               // multiple of 16
     float* redmax = sRed;                        // [2][128]
     float* redsum = sRed + 256;                  // [2][128]
     uint32_t tile_cnt = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int b = item / p.H, h = item % p.H;
+      const uint32_t dkey = attn_drop_key(p.seed, off_eff, item);
       named_bar_sync(1, 256);
       if (ct < Nk) sKok[ct] = (ct < p.Sk) && (!p.kmask || p.kmask[(long long)b * p.Sk + ct]);
       named_bar_sync(1, 256);
@@ -651,14 +690,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           }
           if (p.p_drop > 0.f) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const unsigned long long idx = ((unsigned long long)item * p.Tq + qq) * (unsigned long long)Sk4 + ((k0 >> 2) + g);
-              const uint4 rnd = rng(idx, off_eff);
-              pe[4 * g + 0] = rnd.x >= thr ? pe[4 * g + 0] * inv_keep : 0.f;
-              pe[4 * g + 1] = rnd.y >= thr ? pe[4 * g + 1] * inv_keep : 0.f;
-              pe[4 * g + 2] = rnd.z >= thr ? pe[4 * g + 2] * inv_keep : 0.f;
-              pe[4 * g + 3] = rnd.w >= thr ? pe[4 * g + 3] * inv_keep : 0.f;
-            }
+            for (int e = 0; e < 16; ++e) pe[e] = attn_drop_rand(dkey, qq, k0 + e, p.Sk) >= thr ? pe[e] * inv_keep : 0.f;
           }
 #pragma unroll
           for (int u = 0; u < 2; ++u) {

@@ -228,6 +228,24 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+// Attention-probability dropout uses a cheap per-element counter hash (one decision per (batch*head, query, key)): the
+// tcgen05 backward walks the score matrix transposed, so a generator that amortises over 4 consecutive keys (Philox)
+// would cost a full call per element there.  key = splitmix64(seed, offset, bh); word = lowbias32(key ^ elem * phi).
+__device__ __forceinline__ uint32_t attn_drop_key(unsigned long long seed, unsigned long long offset, int bh) {
+  unsigned long long z = seed ^ (offset * 0x9E3779B97F4A7C15ull) ^ ((unsigned long long)(bh + 1) * 0xD6E8FEB86659FD93ull);
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)z ^ (uint32_t)(z >> 32);
+}
+__device__ __forceinline__ uint32_t attn_drop_rand(uint32_t key, int q, int k, int Sk) {
+  uint32_t x = ((uint32_t)q * (uint32_t)Sk + (uint32_t)k) * 0x9E3779B1u ^ key;
+  x ^= x >> 16; x *= 0x7FEB352Du;
+  x ^= x >> 15; x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+
 // Counter-based RNG for dropout: Philox4x32-10.  (seed, offset) fixed per launch; `idx` = element group index.
 struct Philox {
   uint32_t key0, key1;

@@ -221,9 +221,17 @@ static int ln_bwd_dispatch(const bf16* dy, const TIn* x, const float* mean, cons
                            unsigned long long seed, unsigned long long offset, const unsigned long long* offset_ptr,
                            float* colsum, cudaStream_t s) {
   const int nv = (D / 8 + 31) / 32;
-  int grid = num_sms() * 4;
-  if (grid > (M + 3) / 4) grid = (M + 3) / 4;
-#define LN_BWD(NV_) layernorm_bwd_kernel<TIn, NV_><<<grid, 128, 0, s>>>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, M, D, dx_drop, p_drop, seed, offset, offset_ptr, colsum)
+  // persistent grid = exactly one resident wave (SMs x occupancy): a partial second wave would cost a full pass
+#define LN_BWD(NV_)                                                                                                     \
+  {                                                                                                                     \
+    static int occ = 0;                                                                                                 \
+    if (occ == 0) {                                                                                                     \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_bwd_kernel<TIn, NV_>, 128, 0) != cudaSuccess || occ < 1) occ = 2; \
+    }                                                                                                                   \
+    int grid = num_sms() * occ;                                                                                         \
+    if (grid > (M + 3) / 4) grid = (M + 3) / 4;                                                                         \
+    layernorm_bwd_kernel<TIn, NV_><<<grid, 128, 0, s>>>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, M, D, dx_drop, p_drop, seed, offset, offset_ptr, colsum); \
+  }
   switch (nv) {
     case 1: LN_BWD(1); break;
     case 2: LN_BWD(2); break;

@@ -14,7 +14,7 @@ ACT_NONE, ACT_GELU, ACT_GELU_GRAD = 0, 1, 2
 
 # Number of OUR kernels launched through this module (bench.py reports it as `gpu_launches`).
 LAUNCHES = [0]
-_KERNELS_PER_CALL = {"vlm_attention_bwd": 2, "vlm_adamw_step": 2}
+_KERNELS_PER_CALL = {"vlm_attention_bwd": 2, "vlm_attention_bwd_tc": 2, "vlm_adamw_step": 2}
 # Optional per-call CUDA-event timing of the GEMM launches (bench.py roofline pass): list of (M, N, K, batch, start, end)
 GEMM_TIMING = None
 # Optional device uint64 added to every dropout offset (see vlm_rng_advance): set by GraphedTrainStep.
@@ -176,16 +176,16 @@ def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, H, DH, *, kmask=None, causal=
     Sk = k.shape[1]
     scale = (1.0 / DH ** 0.5) if scale is None else scale
     s = [_bh_strides(t, H, DH) for t in (q, k, v, o, do, dq, dk, dv)]
+    delta = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
     if force_tc:
         check(_L().vlm_attention_bwd_tc(ptr(q), c_ll(s[0][0]), c_ll(s[0][1]), ptr(k), c_ll(s[1][0]), c_ll(s[1][1]), ptr(v),
                                         c_ll(s[2][0]), c_ll(s[2][1]), ptr(o), c_ll(s[3][0]), c_ll(s[3][1]), ptr(do),
-                                        c_ll(s[4][0]), c_ll(s[4][1]), ptr(lse), ptr(dq), c_ll(s[5][0]), c_ll(s[5][1]),
+                                        c_ll(s[4][0]), c_ll(s[4][1]), ptr(lse), ptr(delta), ptr(dq), c_ll(s[5][0]), c_ll(s[5][1]),
                                         ptr(dk), c_ll(s[6][0]), c_ll(s[6][1]), ptr(dv), c_ll(s[7][0]), c_ll(s[7][1]),
                                         ptr(kmask), c_int(B), c_int(H), c_int(Tq), c_int(Sk), c_int(DH), c_int(int(causal)),
                                         c_float(scale), c_float(p_drop), c_u64(seed), c_u64(offset), ptr(RNG_COUNTER[0]),
                                         stream_ptr()), "vlm_attention_bwd_tc")
         return
-    delta = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
     check(_L().vlm_attention_bwd(ptr(q), c_ll(s[0][0]), c_ll(s[0][1]), ptr(k), c_ll(s[1][0]), c_ll(s[1][1]), ptr(v),
                                  c_ll(s[2][0]), c_ll(s[2][1]), ptr(o), c_ll(s[3][0]), c_ll(s[3][1]), ptr(do),
                                  c_ll(s[4][0]), c_ll(s[4][1]), ptr(lse), ptr(delta), ptr(dq), c_ll(s[5][0]),
