@@ -167,6 +167,38 @@ int vlm_sym_lse(const float* S, int N, long long ld, float scale, float* lse_row
 int vlm_sym_lse_bwd(const float* S, int N, long long ld, float scale, const float* lse_row, const float* lse_col, float w_row,
                     float w_col, const float* g_ptr, void* dS, long long ldd, void* stream);
 
+/* ---- GLoRIA local (word x region) loss — vilmedic/blocks/losses/selfsup/GLoRIALoss.py:13-51,78-129 ---------------- */
+/* All (image i, caption j) pairs are evaluated at once instead of the reference's Python loop over captions (:86-119).
+ * Layouts: Xc bf16 [B,S,D] regions; Ww bf16 / Q fp32 [NL = B*L, D] words (row j*L+w; rows w >= cap_lens[j] zero);
+ * A/P1 fp32 [B*S, NL]; P2 fp32 + bf16 [B,S,NL]; WC fp32 [B,NL,D]; cos / wnorm fp32 [B,NL]; sims fp32 [B,B].
+ * The GEMMs between these kernels are vlm_gemm_bf16 calls (see vilmedic_b200/blocks/losses/gloria.py). */
+/* out[b][c][r] = in[b][r][c] (fp32 in; bf16 or fp32 out); rows c in [C,Cout) and c >= row_limit[b] are zero-filled.
+ * Converts the reference's [B,D,ih*iw] / [B,D,Lw] feature layouts (:19-25, :92) to K-major rows and back.  With bf16 output,
+ * out_lo (optional) receives bf16(x - hi) so that hi*hi + lo*hi + hi*lo tensor-core products carry ~16 mantissa bits. */
+int vlm_transpose_cast(const float* in, void* out, void* out_lo, int out_bf16, int batch, int R, int C, long long in_ld, long long in_bs,
+                       long long out_ld, long long out_bs, int Cout, const int* row_limit, void* stream);
+/* P1 = softmax over the words of each caption (:32-33). */
+int vlm_gloria_word_softmax(const float* A, float* P1, const int* cap_lens, int rows, int NB, int L, long long ld, void* stream);
+/* P2 = softmax over regions of temp1 * P1, per (image, caption, word) (:38-43); fp32 and bf16 hi/lo copies. */
+int vlm_gloria_region_softmax(const float* P1, float* P2, void* P2h, void* P2l, const int* cap_lens, int NI, int S, int NB, int L,
+                              float temp1, void* stream);
+/* cos[i,(j,w)] = q.wc / max(|q||wc|, eps)  (cosine_similarity, :5-10, called at :109); also the two norms. */
+int vlm_gloria_cos(const float* WC, const float* Q, const int* cap_lens, float* cosv, float* wnorm, float* qnorm, int NI, int NB,
+                   int L, int D, float eps, void* stream);
+/* sims[i,j] = temp3 * log sum_w exp(temp2 * cos[i,(j,w)])  (:112-122, agg "sum"). */
+int vlm_gloria_sims(const float* cosv, const int* cap_lens, float* sims, int NB, int L, float temp2, float temp3, void* stream);
+/* Backward through CE (both directions, means over B; g0/g1 = upstream scalars or null = 1), log-sum-exp and cosine:
+ * dWC bf16 [B,NL,D] and the direct word gradient dQ fp32 [NL,D]. */
+int vlm_gloria_cos_bwd(const float* WC, const float* Q, const int* cap_lens, const float* cosv, const float* wnorm,
+                       const float* qnorm, const float* sims, const float* lse_row, const float* lse_col, const float* g0,
+                       const float* g1, void* dWC, float* dQ, int NB, int L, int D, float temp2, float temp3, float eps,
+                       void* stream);
+/* G [B,S,ld] (= dL/dP2) <- temp1 * P2 (G - sum_s P2 G), in place (= dL/dP1). */
+int vlm_gloria_region_softmax_bwd(const float* P2, float* G, int NI, int S, long long ld, float temp1, void* stream);
+/* dA bf16 = P1 (G - sum_w P1 G) per caption segment. */
+int vlm_gloria_word_softmax_bwd(const float* P1, const float* G, void* dA, const int* cap_lens, int rows, int NB, int L,
+                                long long ld, void* stream);
+
 /* ---- optimizer (vilmedic/executors/trainor.py:119-124) ------------------------------------------ */
 /* out[0] += sum(g^2)  (caller zeroes). */
 int vlm_sumsq_f32(const float* g, long long n, float* out, void* stream);

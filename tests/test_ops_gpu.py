@@ -474,3 +474,60 @@ def test_attention_fwd_tcgen05(cuda_dev, B, H, Tq, Sk, causal, masked, p_drop):
     torch.cuda.synchronize()
     for a, b in zip(g1, g2):
         assert (a.float() - b.float()).abs().max().item() < 4e-2 * max(1.0, b.float().abs().max().item())
+
+
+def test_gloria_local_loss(cuda_dev):
+    """GLoRIA local (word x region) loss + full GLoRIALoss vs the oracle restatement (pinned to the reference's
+    GLoRIALoss.py through tests/golden/losses.pt) — losses, attention maps and input gradients, ragged caption lengths."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden import gloria_inputs
+    from oracle import losses as L
+    from vilmedic_b200.blocks.losses import GLoRIALoss, gloria_attention_fn, local_loss
+    for b, d, hw, lw, seed, scale in [(4, 32, 5, 9, 3, 1.0), (8, 768, 19, 24, 4, 1.0), (16, 768, 19, 40, 11, 0.2), (3, 64, 4, 3, 5, 0.5)]:
+        img, words, sents = gloria_inputs(b, d, hw, lw, seed)
+        if lw == 3:
+            sents = [["[SEP]"], ["a", "[SEP]"], ["a", "b", "[CLS]"]]  # cap_lens 1, 2, 3 (single-word caption included)
+        img, words = img * scale, words * scale
+        lens = L.gloria_cap_lens(sents)
+        ir, wr = img.clone().requires_grad_(True), words.clone().requires_grad_(True)
+        r0, r1, ratt = L.gloria_local_loss(ir, wr, lens)
+        (r0 + 2.0 * r1).backward()
+        ic, wc = img.cuda().requires_grad_(True), words.cuda().requires_grad_(True)
+        l0, l1, att = local_loss(ic, wc, lens)
+        (l0 + 2.0 * l1).backward()
+        torch.cuda.synchronize()
+        tol = 2e-3 * max(1.0, abs(r0.item()))
+        assert abs(l0.item() - r0.item()) <= tol and abs(l1.item() - r1.item()) <= tol, (b, d, l0.item(), r0.item(), l1.item(), r1.item())
+        assert len(att) == b
+        for got, want in zip(att, ratt):
+            assert tuple(got.shape) == tuple(want.shape)
+            assert (got.cpu() - want).abs().max().item() <= 2e-3, (b, d, (got.cpu() - want).abs().max().item())
+        for got, want, nm in ((ic.grad, ir.grad, "img"), (wc.grad, wr.grad, "words")):
+            rel = ((got.cpu() - want).norm() / want.norm().clamp_min(1e-12)).item()
+            assert rel < 3e-2, (b, d, nm, rel)
+        # words beyond cap_len get exactly zero gradient (the reference slices them away, GLoRIALoss.py:92)
+        for j, n in enumerate(lens):
+            assert wc.grad[j, :, n:].abs().max().item() == 0.0 if n < lw else True
+    # full module: same signature / return as the reference
+    b, d, hw, lw, seed = 8, 768, 19, 24, 4
+    img, words, sents = gloria_inputs(b, d, hw, lw, seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    gi, gt = torch.randn(b, d, generator=g), torch.randn(b, d, generator=g)
+    lens = L.gloria_cap_lens(sents)
+    rl0, rl1, _ = L.gloria_local_loss(img, words, lens)
+    rg0, rg1 = L.gloria_global_loss(gi, gt)
+    ref = (rl0 + rl1) * 1.0 + (rg0 + rg1) * 1.0
+    loss, attn = GLoRIALoss(temp1=4.0, temp2=5.0, temp3=10.0)(gi.cuda(), img.cuda(), words.cuda(), gt.cuda(), sents)
+    assert abs(loss.item() - ref.item()) <= 2e-3 * abs(ref.item()), (loss.item(), ref.item())
+    gold = [c for c in torch.load(os.path.join(os.path.dirname(__file__), "golden", "losses.pt"))["cases"]
+            if c["kind"] == "gloria" and c["b"] == b and c["d"] == d][0]
+    assert abs(loss.item() - gold["loss"].item()) <= 2e-3 * abs(gold["loss"].item()), (loss.item(), gold["loss"].item())
+    assert (attn[0][0, :2].cpu() - gold["attn0_probe"]).abs().max().item() <= 2e-3
+    # helper parity: gloria_attention_fn(query, context, temp1)
+    q = torch.randn(b, d, 7, generator=g) * 0.2
+    ctxt = img * 0.2
+    rw, ra = L.gloria_attention(q, ctxt, 4.0)
+    gw, ga = gloria_attention_fn(q.cuda(), ctxt.cuda(), 4.0)
+    assert (ga.cpu() - ra).abs().max().item() <= 2e-3
+    assert ((gw.cpu() - rw).norm() / rw.norm()).item() <= 1e-2

@@ -1,5 +1,5 @@
 """Micro-benchmark of the tcgen05 GEMM on the shapes of the RRG training step: every tile configuration x operand
-layout, CUDA-event timed back-to-back launches (GPU-bound).  Usage: python tools/gemm_bench.py [--json out.json]"""
+layout, CUDA-event timed back-to-back launches (GPU-bound).  Usage: python tools/gemm_bench.py [--json out.json] [--only "<substring of shape name>"] [--cfg <force_bn>] [--epi none|bias|gelu|res|gelugrad|acc]"""
 import json
 import os
 import sys
@@ -78,8 +78,15 @@ def main():
     dev = torch.device("cuda:0")
     rows = []
     print("%-22s %-18s " % ("shape", "MxNxK") + " ".join("%12s" % ("cfg%d" % c) for c in CONFIGS))
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    cfgs = [int(sys.argv[sys.argv.index("--cfg") + 1])] if "--cfg" in sys.argv else CONFIGS
+    epi_override = sys.argv[sys.argv.index("--epi") + 1] if "--epi" in sys.argv else None
     for (name, M, N, K, layout, epi) in SHAPES:
-        res = [run(name, M, N, K, layout, epi, c, dev) for c in CONFIGS]
+        if only and only not in name:
+            continue
+        if epi_override:
+            epi = epi_override
+        res = [run(name, M, N, K, layout, epi, c, dev) if c in cfgs else None for c in CONFIGS]
         rows.append({"name": name, "M": M, "N": N, "K": K, "layout": layout, "epi": epi, "results": dict(zip(map(str, CONFIGS), res))})
         cells = []
         for r in res:

@@ -3,4 +3,5 @@
 from torch.nn.modules.loss import *  # noqa: F401,F403
 
 from .contrastive import ConVIRTLoss, GLoRIAGlobalLoss, InfoNCELoss  # noqa: F401
+from .gloria import GLoRIALoss, cosine_similarity, gloria_attention_fn, global_loss, local_loss  # noqa: F401
 from .label_smoothing import LabelSmoothingCrossEntropy  # noqa: F401

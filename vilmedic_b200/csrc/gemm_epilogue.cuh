@@ -215,165 +215,6 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Coalesced epilogue.  In the accumulator layout every thread owns one ROW, so direct global accesses touch 32 different
-// 128-byte lines per warp instruction (32 LSU wavefronts each) and the LSU, not the tensor pipe, bounds K<=768 GEMMs.
-// Each epilogue warp therefore owns a 4 KB shared-memory staging tile (32 rows x 128 B, 16-byte units XOR-swizzled by
-// row & 7): rows are written/read by their owner thread, while global memory is accessed by the whole warp along rows
-// (8 rows x 64 B for bf16, 4 rows x 128 B for fp32 per instruction: 4-8x fewer wavefronts).
-__device__ __forceinline__ uint32_t stg_off(int row, int unit) { return (uint32_t)(row * 128 + ((unit ^ (row & 7)) << 4)); }
-
-template <int UNITS>  // 16-byte units per row: 4 (32 bf16) or 8 (32 fp32)
-__device__ __forceinline__ void stage_load(uint8_t* stg, const uint8_t* gtile, long long pitch_bytes, int lane, int rows_valid) {
-  constexpr int RPI = 32 / UNITS;
-#pragma unroll
-  for (int i = 0; i < 32 / RPI; ++i) {
-    const int r = i * RPI + lane / UNITS, u = lane % UNITS;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (r < rows_valid) val = *reinterpret_cast<const uint4*>(gtile + (long long)r * pitch_bytes + u * 16);
-    *reinterpret_cast<uint4*>(stg + stg_off(r, u)) = val;
-  }
-  __syncwarp();
-}
-template <int UNITS>
-__device__ __forceinline__ void stage_store(uint8_t* stg, uint8_t* gtile, long long pitch_bytes, int lane, int rows_valid) {
-  constexpr int RPI = 32 / UNITS;
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 32 / RPI; ++i) {
-    const int r = i * RPI + lane / UNITS, u = lane % UNITS;
-    if (r < rows_valid)
-      *reinterpret_cast<uint4*>(gtile + (long long)r * pitch_bytes + u * 16) = *reinterpret_cast<const uint4*>(stg + stg_off(r, u));
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ void stg_put_bf16(uint8_t* stg, int lane, const float* v) {   // own row <- 32 floats as bf16
-#pragma unroll
-  for (int u = 0; u < 4; ++u)
-    *reinterpret_cast<uint4*>(stg + stg_off(lane, u)) =
-        make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
-                   pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
-}
-__device__ __forceinline__ void stg_put_f32(uint8_t* stg, int lane, const float* v) {
-#pragma unroll
-  for (int u = 0; u < 8; ++u)
-    *reinterpret_cast<float4*>(stg + stg_off(lane, u)) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-}
-__device__ __forceinline__ void stg_get_bf16(const uint8_t* stg, int lane, float* f) {   // own row -> 32 floats
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const uint4 w = *reinterpret_cast<const uint4*>(stg + stg_off(lane, u));
-    const float2 a = unpack_bf16x2(w.x), b = unpack_bf16x2(w.y), c = unpack_bf16x2(w.z), d = unpack_bf16x2(w.w);
-    f[8 * u] = a.x; f[8 * u + 1] = a.y; f[8 * u + 2] = b.x; f[8 * u + 3] = b.y;
-    f[8 * u + 4] = c.x; f[8 * u + 5] = c.y; f[8 * u + 6] = d.x; f[8 * u + 7] = d.y;
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ void stg_get_f32(const uint8_t* stg, int lane, float* f) {
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const float4 w = *reinterpret_cast<const float4*>(stg + stg_off(lane, u));
-    f[4 * u] = w.x; f[4 * u + 1] = w.y; f[4 * u + 2] = w.z; f[4 * u + 3] = w.w;
-  }
-  __syncwarp();
-}
-
-// One 32-row x 32-column chunk of the warp's slab (rows row0 .. row0+31, thread `lane` owns row0+lane).
-__device__ __forceinline__ void epilogue_chunk_warp(const uint32_t* acc, int row0, int lane, int col0, int M, int N,
-                                                    const GemmEpilogue& e, uint8_t* stg) {
-  const int rows_valid = min(32, M - row0);
-  if (rows_valid <= 0 || col0 >= N) return;                    // warp-uniform
-  if (col0 + 32 > N || e.atomic) {                             // ragged last column tile / split-K atomics: per-thread path
-    epilogue_chunk(acc, row0 + lane, col0, M, N, e);
-    return;
-  }
-  const int row = row0 + lane;
-  float v[32];
-  const float alpha = e.alpha_ptr ? e.alpha * __ldg(e.alpha_ptr) : e.alpha;
-  if (alpha != 1.0f) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * alpha;
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-  }
-  if (e.bias) {
-    const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 b = __ldg(b4 + j);
-      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-    }
-  }
-  if (e.act == 1) {
-    if (e.aux_out) {
-      stg_put_bf16(stg, lane, v);
-      stage_store<4>(stg, reinterpret_cast<uint8_t*>(e.aux_out + (long long)row0 * e.ld_aux + col0), e.ld_aux * 2, lane, rows_valid);
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (e.act == 2) {
-    float a[32];
-    stage_load<4>(stg, reinterpret_cast<const uint8_t*>(e.aux_in + (long long)row0 * e.ld_aux + col0), e.ld_aux * 2, lane, rows_valid);
-    stg_get_bf16(stg, lane, a);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(a[j]);
-  }
-  if (e.p_drop > 0.f) {
-    const Philox rng(e.seed);
-    const uint32_t thr = (uint32_t)(e.p_drop * 4294967296.0f);
-    const float inv_keep = 1.f / (1.f - e.p_drop);
-    const unsigned long long base = ((unsigned long long)row * (unsigned long long)e.drop_ld + (unsigned long long)col0) >> 2;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint4 r = rng(base + j, e.offset);
-      v[4 * j + 0] = r.x >= thr ? v[4 * j + 0] * inv_keep : 0.f;
-      v[4 * j + 1] = r.y >= thr ? v[4 * j + 1] * inv_keep : 0.f;
-      v[4 * j + 2] = r.z >= thr ? v[4 * j + 2] * inv_keep : 0.f;
-      v[4 * j + 3] = r.w >= thr ? v[4 * j + 3] * inv_keep : 0.f;
-    }
-  }
-  if (e.c_fp32) {
-    float* ctile = reinterpret_cast<float*>(e.c) + (long long)row0 * e.ldc + col0;
-    if (e.residual) {
-      float a[32];
-      stage_load<8>(stg, reinterpret_cast<const uint8_t*>(reinterpret_cast<const float*>(e.residual) + (long long)row0 * e.ldr + col0),
-                    e.ldr * 4, lane, rows_valid);
-      stg_get_f32(stg, lane, a);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += a[j];
-    }
-    if (e.accumulate) {
-      float a[32];
-      stage_load<8>(stg, reinterpret_cast<const uint8_t*>(ctile), e.ldc * 4, lane, rows_valid);
-      stg_get_f32(stg, lane, a);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += a[j];
-    }
-    stg_put_f32(stg, lane, v);
-    stage_store<8>(stg, reinterpret_cast<uint8_t*>(ctile), e.ldc * 4, lane, rows_valid);
-  } else {
-    bf16* ctile = reinterpret_cast<bf16*>(e.c) + (long long)row0 * e.ldc + col0;
-    if (e.residual) {
-      float a[32];
-      stage_load<4>(stg, reinterpret_cast<const uint8_t*>(reinterpret_cast<const bf16*>(e.residual) + (long long)row0 * e.ldr + col0),
-                    e.ldr * 2, lane, rows_valid);
-      stg_get_bf16(stg, lane, a);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += a[j];
-    }
-    if (e.accumulate) {
-      float a[32];
-      stage_load<4>(stg, reinterpret_cast<const uint8_t*>(ctile), e.ldc * 2, lane, rows_valid);
-      stg_get_bf16(stg, lane, a);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += a[j];
-    }
-    stg_put_bf16(stg, lane, v);
-    stage_store<4>(stg, reinterpret_cast<uint8_t*>(ctile), e.ldc * 2, lane, rows_valid);
-  }
-}
-
 // host-side pieces shared by the GEMM translation units
 int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch,
                    uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows);

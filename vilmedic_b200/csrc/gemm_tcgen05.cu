@@ -30,12 +30,11 @@ static constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 template <int BN>
 struct GemmSmem {
-  static constexpr int STAGES = (BN >= 192) ? 4 : 6;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;             // epilogue staging: 4 KB per epilogue warp
-  static constexpr int BAR_OFFSET = STG_OFFSET + GEMM_EPI_WARPS * 4096;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
 };
 
@@ -205,15 +204,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int row0 = m0 + quad * 32;
-      uint8_t* stg = smem + S::STG_OFFSET + (warp_idx - 2) * 4096;
+      const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int c = c_begin; c < c_end; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
-        epilogue_chunk_warp(r, row0, lane, n0 + c * 32, M, N, e, stg);
+        epilogue_chunk(r, row, n0 + c * 32, M, N, e);
       }
       tc_fence_before();
       __syncwarp();

@@ -27,9 +27,8 @@ struct G2Smem {
   static constexpr int A_BYTES = G2_BM * G2_BK * 2;            // 16 KB
   static constexpr int B_BYTES = (BN / 2) * G2_BK * 2;         // this CTA's half of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
-  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;             // epilogue staging: 4 KB per epilogue warp
-  static constexpr int BAR_OFFSET = STG_OFFSET + G2_EPI_WARPS * 4096;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
@@ -219,15 +218,14 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       if (e.p_drop > 0.f && e.offset_ptr) e.offset += __ldg(e.offset_ptr);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int row0 = m0 + quad * 32;
-      uint8_t* stg = smem + S::STG_OFFSET + (warp_idx - 2) * 4096;
+      const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int c = c_begin; c < c_end; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
-        epilogue_chunk_warp(r, row0, lane, n0 + c * 32, M, N, e, stg);
+        epilogue_chunk(r, row, n0 + c * 32, M, N, e);
       }
       tc_fence_before();
       __syncwarp();

@@ -360,5 +360,76 @@ def sym_lse_bwd(S, scale, lse_row, lse_col, w_row, w_col, g_t):
     return dS[:, :N]
 
 
+# ---- GLoRIA local loss pieces (csrc/gloria.cu) ---------------------------------------------------------------------------
+def transpose_cast(x, out_dtype, c_out=None, row_limit=None, want_lo=False):
+    """x fp32 [B, R, C] -> [B, c_out or C, R] (bf16 or fp32); rows >= C or >= row_limit[b] are zero.
+    want_lo (bf16 only): returns (hi, lo) with x ~= hi + lo."""
+    _req(x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.stride(-1) == 1, "transpose_cast: x must be CUDA fp32 [B,R,C]")
+    B, R, C = x.shape
+    Co = C if c_out is None else c_out
+    out = torch.empty((B, Co, R), device=x.device, dtype=out_dtype)
+    lo = torch.empty_like(out) if (want_lo and out_dtype == torch.bfloat16) else None
+    check(_L().vlm_transpose_cast(ptr(x), ptr(out), ptr(lo), c_int(int(out_dtype == torch.bfloat16)), c_int(B), c_int(R), c_int(C),
+                                  c_ll(x.stride(1)), c_ll(x.stride(0)), c_ll(R), c_ll(Co * R), c_int(Co), ptr(row_limit),
+                                  stream_ptr()), "vlm_transpose_cast")
+    return (out, lo) if want_lo else out
+
+
+def gloria_word_softmax(A, cap_lens, NB, L):
+    P1 = torch.empty_like(A)
+    check(_L().vlm_gloria_word_softmax(ptr(A), ptr(P1), ptr(cap_lens), c_int(A.shape[0]), c_int(NB), c_int(L), c_ll(A.stride(0)),
+                                       stream_ptr()), "vlm_gloria_word_softmax")
+    return P1
+
+
+def gloria_region_softmax(P1, cap_lens, NI, S, NB, L, temp1):
+    P2 = torch.empty_like(P1)
+    P2h = torch.empty(P1.shape, device=P1.device, dtype=torch.bfloat16)
+    P2l = torch.empty_like(P2h)
+    check(_L().vlm_gloria_region_softmax(ptr(P1), ptr(P2), ptr(P2h), ptr(P2l), ptr(cap_lens), c_int(NI), c_int(S), c_int(NB), c_int(L),
+                                         c_float(temp1), stream_ptr()), "vlm_gloria_region_softmax")
+    return P2, P2h, P2l
+
+
+def gloria_cos(WC, Q, cap_lens, NB, L, eps=1e-8):
+    NI, NL, D = WC.shape
+    cosv = torch.empty((NI, NL), device=WC.device, dtype=torch.float32)
+    wnorm = torch.empty_like(cosv)
+    qnorm = torch.empty(NL, device=WC.device, dtype=torch.float32)
+    check(_L().vlm_gloria_cos(ptr(WC), ptr(Q), ptr(cap_lens), ptr(cosv), ptr(wnorm), ptr(qnorm), c_int(NI), c_int(NB), c_int(L),
+                              c_int(D), c_float(eps), stream_ptr()), "vlm_gloria_cos")
+    return cosv, wnorm, qnorm
+
+
+def gloria_sims(cosv, cap_lens, NB, L, temp2, temp3):
+    sims = torch.empty((NB, NB), device=cosv.device, dtype=torch.float32)
+    check(_L().vlm_gloria_sims(ptr(cosv), ptr(cap_lens), ptr(sims), c_int(NB), c_int(L), c_float(temp2), c_float(temp3),
+                               stream_ptr()), "vlm_gloria_sims")
+    return sims
+
+
+def gloria_cos_bwd(WC, Q, cap_lens, cosv, wnorm, qnorm, sims, lse_row, lse_col, g0, g1, NB, L, temp2, temp3, eps=1e-8):
+    NI, NL, D = WC.shape
+    dWC = torch.empty((NI, NL, D), device=WC.device, dtype=torch.bfloat16)
+    dQ = torch.empty((NL, D), device=WC.device, dtype=torch.float32)
+    check(_L().vlm_gloria_cos_bwd(ptr(WC), ptr(Q), ptr(cap_lens), ptr(cosv), ptr(wnorm), ptr(qnorm), ptr(sims), ptr(lse_row),
+                                  ptr(lse_col), ptr(g0), ptr(g1), ptr(dWC), ptr(dQ), c_int(NB), c_int(L), c_int(D), c_float(temp2),
+                                  c_float(temp3), c_float(eps), stream_ptr()), "vlm_gloria_cos_bwd")
+    return dWC, dQ
+
+
+def gloria_region_softmax_bwd(P2, G, NI, S, temp1):
+    check(_L().vlm_gloria_region_softmax_bwd(ptr(P2), ptr(G), c_int(NI), c_int(S), c_ll(P2.shape[-1]), c_float(temp1),
+                                             stream_ptr()), "vlm_gloria_region_softmax_bwd")
+    return G
+
+
+def gloria_word_softmax_bwd(P1, G, cap_lens, NB, L):
+    dA = torch.empty(P1.shape, device=P1.device, dtype=torch.bfloat16)
+    check(_L().vlm_gloria_word_softmax_bwd(ptr(P1), ptr(G), ptr(dA), ptr(cap_lens), c_int(P1.shape[0]), c_int(NB), c_int(L),
+                                           c_ll(P1.stride(0)), stream_ptr()), "vlm_gloria_word_softmax_bwd")
+    return dA
+
+
 def rng_advance(counter, delta):
     check(_L().vlm_rng_advance(ptr(counter), c_u64(delta), stream_ptr()), "vlm_rng_advance")
