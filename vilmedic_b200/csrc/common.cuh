@@ -156,6 +156,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- UMMA descriptors (bit layout: cute/arch/mma_sm100_desc.hpp of CUTLASS; restated, not copied) ----
@@ -186,21 +195,32 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
 // ---- misc math ----
 // erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output resolution): one MUFU.RCP + one
 // MUFU.EX2 + 7 FMA-class ops instead of the ~25-instruction branchy erff().  `e` returns exp(-x^2) for reuse.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float erf_as(float x, float& e) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));      // MUFU.RCP (2 ulp): abs error of erf stays < 3e-7
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  e = __expf(-ax * ax);
+  e = ex2_approx(ax * ax * -1.4426950408889634f);
   return copysignf(fmaf(-p, e, 1.0f), x);
 }
 // exact-erf GELU of HF (hidden_act="gelu"): 0.5 x (1 + erf(x / sqrt 2))
 __device__ __forceinline__ float gelu_erf(float x) {
   float e;
-  return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f, e));
+  const float h = 0.5f * x;
+  return fmaf(h, erf_as(x * 0.70710678118654752f, e), h);
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   float e;  // = exp(-x^2 / 2)

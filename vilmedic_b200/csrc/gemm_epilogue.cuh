@@ -1,5 +1,8 @@
 // Fused GEMM epilogue shared by the 1-CTA and 2-CTA tcgen05 GEMM kernels: one thread owns one accumulator row and
-// processes it in chunks of 32 fp32 columns read from TMEM.
+// processes it in chunks of 16 or 32 fp32 columns read from TMEM.  The epilogue is instruction-issue / latency bound, not
+// bandwidth bound (ncu, profiles/ncu_gemm_r1_epilogue.txt): 2 epilogue warps per SM sub-partition reached only 38 % issue
+// utilisation on the bias+GELU epilogue, so the 1-CTA kernel runs 16 epilogue warps (4 per sub-partition, 16-column chunks,
+// <= 112 registers) and the operand loads of a chunk are issued under its TMEM load.
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -27,25 +30,55 @@ struct GemmEpilogue {
   int drop_ld;                // logical row width used for the dropout element index (row * drop_ld + col)
 };
 
-__device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int col0, int M, int N,
-                                               const GemmEpilogue& e) {
-  if (row >= M || col0 >= N) return;
-  float v[32];
+// One chunk = W (16 or 32) consecutive fp32 accumulator columns of this thread's row, read from TMEM at `taddr`.
+// Order of operations: issue the TMEM load, issue the global loads the epilogue needs (GELU' input, residual, old C) while
+// it is in flight, wait, do the math, store.  Must be called by all 32 lanes (tcgen05.ld / wait::ld are warp-collective).
+template <int W>
+__device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0, int M, int N, const GemmEpilogue& e) {
+  static_assert(W == 16 || W == 32, "chunk width");
+  uint32_t acc[W];
+  if constexpr (W == 32) tmem_ld32(taddr, acc);
+  else tmem_ld16(taddr, acc);
+  const bool live = row < M && col0 < N;
+  const bool full = live && (col0 + W <= N);
+  // ---- prefetch (bf16 operands: W/8 x 16 B per row; fp32: W/4 x 16 B)
+  uint4 aux[W / 8], res16[W / 8];
+  float4 res32[W / 4];
+  const bool pre_aux = full && e.act == 2;
+  const bool pre_res16 = full && !e.c_fp32 && e.residual != nullptr;
+  const bool pre_res32 = full && e.c_fp32 && e.residual != nullptr;
+  if (pre_aux) {
+    const uint4* src = reinterpret_cast<const uint4*>(e.aux_in + (long long)row * e.ld_aux + col0);
+#pragma unroll
+    for (int j = 0; j < W / 8; ++j) aux[j] = __ldg(src + j);
+  }
+  if (pre_res16) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.residual) + (long long)row * e.ldr + col0);
+#pragma unroll
+    for (int j = 0; j < W / 8; ++j) res16[j] = __ldg(r4 + j);
+  }
+  if (pre_res32) {
+    const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.residual) + (long long)row * e.ldr + col0);
+#pragma unroll
+    for (int j = 0; j < W / 4; ++j) res32[j] = __ldg(r4 + j);
+  }
+  tmem_ld_wait();
+  if (!live) return;
+  float v[W];
   const float alpha = e.alpha_ptr ? e.alpha * __ldg(e.alpha_ptr) : e.alpha;
   if (alpha != 1.0f) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * alpha;
+    for (int j = 0; j < W; ++j) v[j] = __uint_as_float(acc[j]) * alpha;
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+    for (int j = 0; j < W; ++j) v[j] = __uint_as_float(acc[j]);
   }
 
-  const bool full = (col0 + 32 <= N);
   if (full) {
     if (e.bias) {
       const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < W / 4; ++j) {
         const float4 b = __ldg(b4 + j);
         v[4 * j + 0] += b.x;
         v[4 * j + 1] += b.y;
@@ -57,7 +90,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int
       if (e.aux_out) {
         uint4* dst = reinterpret_cast<uint4*>(e.aux_out + (long long)row * e.ld_aux + col0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < W / 8; ++j) {
           uint4 u;
           u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
           u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
@@ -67,12 +100,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int
         }
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      for (int j = 0; j < W; ++j) v[j] = gelu_erf(v[j]);
     } else if (e.act == 2) {
-      const uint4* src = reinterpret_cast<const uint4*>(e.aux_in + (long long)row * e.ld_aux + col0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 u = __ldg(src + j);
+      for (int j = 0; j < W / 8; ++j) {
+        const uint4 u = aux[j];
         const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
         v[8 * j + 0] *= gelu_erf_grad(p0.x);
         v[8 * j + 1] *= gelu_erf_grad(p0.y);
@@ -90,7 +122,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int
       const float inv_keep = 1.f / (1.f - e.p_drop);
       const unsigned long long base = ((unsigned long long)row * (unsigned long long)e.drop_ld + (unsigned long long)col0) >> 2;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < W / 4; ++j) {
         const uint4 r = rng(base + j, e.offset);
         v[4 * j + 0] = r.x >= thr ? v[4 * j + 0] * inv_keep : 0.f;
         v[4 * j + 1] = r.y >= thr ? v[4 * j + 1] * inv_keep : 0.f;
@@ -101,11 +133,9 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int
     if (e.c_fp32) {
       float* crow = reinterpret_cast<float*>(e.c) + (long long)row * e.ldc + col0;
       if (e.residual) {
-        const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.residual) +
-                                                           (long long)row * e.ldr + col0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 r = __ldg(r4 + j);
+        for (int j = 0; j < W / 4; ++j) {
+          const float4 r = res32[j];
           v[4 * j + 0] += r.x;
           v[4 * j + 1] += r.y;
           v[4 * j + 2] += r.z;
@@ -115,29 +145,29 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int
       float4* c4 = reinterpret_cast<float4*>(crow);
       if (e.atomic) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(c4 + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        for (int j = 0; j < W / 4; ++j) atomicAdd(c4 + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
         return;
       }
+      if (e.accumulate) {
+        float4 old[W / 4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        if (e.accumulate) {
-          const float4 old = c4[j];
-          o.x += old.x;
-          o.y += old.y;
-          o.z += old.z;
-          o.w += old.w;
+        for (int j = 0; j < W / 4; ++j) old[j] = c4[j];
+#pragma unroll
+        for (int j = 0; j < W / 4; ++j) {
+          v[4 * j + 0] += old[j].x;
+          v[4 * j + 1] += old[j].y;
+          v[4 * j + 2] += old[j].z;
+          v[4 * j + 3] += old[j].w;
         }
-        c4[j] = o;
       }
+#pragma unroll
+      for (int j = 0; j < W / 4; ++j) c4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     } else {
       bf16* crow = reinterpret_cast<bf16*>(e.c) + (long long)row * e.ldc + col0;
       if (e.residual) {
-        const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.residual) +
-                                                         (long long)row * e.ldr + col0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 u = __ldg(r4 + j);
+        for (int j = 0; j < W / 8; ++j) {
+          const uint4 u = res16[j];
           const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z),
                        p3 = unpack_bf16x2(u.w);
           v[8 * j + 0] += p0.x;
@@ -152,7 +182,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int
       }
       uint4* c4 = reinterpret_cast<uint4*>(crow);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < W / 8; ++j) {
         if (e.accumulate) {
           const uint4 u = c4[j];
           const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z),
@@ -177,7 +207,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* acc, int row, int
   } else {
     // ragged last column tile: scalar, fully predicated (unrolled so that v[] stays in registers)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < W; ++j) {
       const int col = col0 + j;
       if (col >= N) continue;
       float x = v[j];

@@ -14,7 +14,7 @@
 // vilmedic/blocks/vision/visual_encoder.py:56-58 and vilmedic/blocks/huggingface/decoder/decoder_model.py:23-26.
 //
 // Warp roles (320 threads): warp0 = TMA producer, warp1 = TMEM allocator + MMA issuer, warps2..9 = epilogue
-// (warp w drains TMEM lane quadrant w%4, column half (w-2)/4).
+// (warp w drains TMEM lane quadrant w%4, column slice (w-2)/4).
 #include <cuda.h>
 #include <cstdlib>
 #include "common.cuh"
@@ -25,7 +25,8 @@ namespace vlm {
 
 static constexpr int GEMM_BM = 128;
 static constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle row
-static constexpr int GEMM_EPI_WARPS = 8;            // two warps per TMEM lane quadrant, each owns half of the columns
+static constexpr int GEMM_EPI_WARPS = 16;           // four warps per TMEM lane quadrant, each owns a quarter of the columns
+static constexpr int GEMM_EPI_W = 16;               // accumulator columns per epilogue chunk
 static constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 template <int BN>
@@ -39,7 +40,7 @@ struct GemmSmem {
 };
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __maxnreg__(112)   // 18 warps x 32 x 112 = 64512 of the SM's 65536 registers (1 CTA / SM)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          int M, int N, int K, int batch, int a_bmul, int b_bmul, int split_k,
                          long long c_batch_stride, long long aux_batch_stride, long long res_batch_stride,
@@ -176,9 +177,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else {
     // ===================== epilogue warps (2..9) =====================
     const int quad = warp_idx & 3;                 // TMEM lane quadrant this warp may access
-    const int half = (warp_idx - 2) >> 2;          // which half of the tile's columns this warp drains
-    constexpr int CHUNKS = BN / 32;                // BN in {64,128,192,256} -> 2,4,6,8 chunks
-    const int c_begin = half * (CHUNKS / 2), c_end = (half + 1) * (CHUNKS / 2);
+    const int part = (warp_idx - 2) >> 2;          // which slice of the tile's columns this warp drains
+    constexpr int PARTS = GEMM_EPI_WARPS / 4;
+    constexpr int CHUNKS = BN / GEMM_EPI_W;        // BN in {64,128,192,256} -> 4,8,12,16 chunks of 16 columns
+    static_assert(CHUNKS % PARTS == 0, "column chunks must split evenly over the epilogue warps");
+    const int c_begin = part * (CHUNKS / PARTS), c_end = (part + 1) * (CHUNKS / PARTS);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
@@ -207,12 +210,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        epilogue_chunk(r, row, n0 + c * 32, M, N, e);
-      }
+      for (int c = c_begin; c < c_end; ++c)
+        epilogue_chunk<GEMM_EPI_W>(taddr + c * GEMM_EPI_W, row, n0 + c * GEMM_EPI_W, M, N, e);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);

@@ -221,12 +221,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        epilogue_chunk(r, row, n0 + c * 32, M, N, e);
-      }
+      for (int c = c_begin; c < c_end; ++c) epilogue_chunk<32>(taddr + c * 32, row, n0 + c * 32, M, N, e);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
