@@ -25,9 +25,11 @@ namespace vlm {
 
 static constexpr int GEMM_BM = 128;
 static constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle row
-static constexpr int GEMM_EPI_WARPS = 16;           // four warps per TMEM lane quadrant, each owns a quarter of the columns
+// Epilogue warps: PARTS per TMEM lane quadrant (warp w drains quadrant w%4, 16-column chunks c = part, part+PARTS, ...).
+// Register budget is per SM sub-partition (16384 registers, warps are dealt round-robin): 2 + 4*4 = 18 warps -> 5 on one
+// sub-partition -> <= 96 registers; 2 + 4*3 = 14 warps -> 4 per sub-partition -> <= 128 registers.
 static constexpr int GEMM_EPI_W = 16;               // accumulator columns per epilogue chunk
-static constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+__host__ __device__ constexpr int gemm_threads(int parts) { return 64 + 128 * parts; }
 
 template <int BN>
 struct GemmSmem {
@@ -39,8 +41,8 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
 };
 
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __maxnreg__(112)   // 18 warps x 32 x 112 = 64512 of the SM's 65536 registers (1 CTA / SM)
+template <int BN, bool A_MN, bool B_MN, int PARTS>
+__global__ void __launch_bounds__(gemm_threads(PARTS), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          int M, int N, int K, int batch, int a_bmul, int b_bmul, int split_k,
                          long long c_batch_stride, long long aux_batch_stride, long long res_batch_stride,
@@ -80,7 +82,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], GEMM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[i], 4 * PARTS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   } else if (warp_idx == 1) {
@@ -178,10 +180,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ===================== epilogue warps (2..9) =====================
     const int quad = warp_idx & 3;                 // TMEM lane quadrant this warp may access
     const int part = (warp_idx - 2) >> 2;          // which slice of the tile's columns this warp drains
-    constexpr int PARTS = GEMM_EPI_WARPS / 4;
     constexpr int CHUNKS = BN / GEMM_EPI_W;        // BN in {64,128,192,256} -> 4,8,12,16 chunks of 16 columns
-    static_assert(CHUNKS % PARTS == 0, "column chunks must split evenly over the epilogue warps");
-    const int c_begin = part * (CHUNKS / PARTS), c_end = (part + 1) * (CHUNKS / PARTS);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
@@ -210,7 +209,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c)
+      for (int c = part; c < CHUNKS; c += PARTS)
         epilogue_chunk<GEMM_EPI_W>(taddr + c * GEMM_EPI_W, row, n0 + c * GEMM_EPI_W, M, N, e);
       tc_fence_before();
       __syncwarp();
@@ -310,12 +309,21 @@ void bind_context_for_driver_calls() {
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int batch, int a_bmul,
+static int epi_parts() {   // debug knob: VLM_GEMM_EPI_PARTS=3|4 (epilogue warps per TMEM quadrant)
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("VLM_GEMM_EPI_PARTS");
+    v = (s && atoi(s) == 3) ? 3 : 4;
+  }
+  return v;
+}
+
+template <int BN, bool A_MN, bool B_MN, int PARTS>
+static int launch_gemm_p(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int batch, int a_bmul,
                        int b_bmul, int split_k, long long c_bs, long long aux_bs, long long res_bs, const GemmEpilogue& epi, int max_ctas,
                        cudaStream_t stream) {
   using S = GemmSmem<BN>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN, PARTS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -329,8 +337,17 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
   const long long tiles = (long long)m_tiles * n_tiles * batch * split_k;
   int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_bs, aux_bs, res_bs, epi);
+  kern<<<grid, gemm_threads(PARTS), S::TOTAL, stream>>>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_bs, aux_bs, res_bs, epi);
   return check_launch("gemm_bf16_tcgen05");
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int batch, int a_bmul,
+                       int b_bmul, int split_k, long long c_bs, long long aux_bs, long long res_bs, const GemmEpilogue& epi, int max_ctas,
+                       cudaStream_t stream) {
+  if (epi_parts() == 3)
+    return launch_gemm_p<BN, A_MN, B_MN, 3>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_bs, aux_bs, res_bs, epi, max_ctas, stream);
+  return launch_gemm_p<BN, A_MN, B_MN, 4>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_bs, aux_bs, res_bs, epi, max_ctas, stream);
 }
 
 static int pick_bn(int M, int N, int batch, int force_bn) {
