@@ -1,10 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 F='loss_type\|Swig\|swig\|Docs:\|^$'
-echo "=== gemm tests (parts=4)"; timeout 900 python -m pytest tests/test_gemm_gpu.py -m gpu -q -x 2>&1 | grep -v "$F" | grep -E "^E  |passed|failed|FAILED|Error" | cut -c1-600 | tail -10
-echo "=== gemm tests (parts=3)"; VLM_GEMM_EPI_PARTS=3 timeout 900 python -m pytest tests/test_gemm_gpu.py -m gpu -q -x 2>&1 | grep -v "$F" | grep -E "^E  |passed|failed|FAILED|Error" | cut -c1-600 | tail -10
-for P in 4 3; do
-echo "=== gemm sweep parts=$P"; VLM_GEMM_EPI_PARTS=$P timeout 300 python tools/gemm_bench.py --json gpurun_out/gemm_sweep_r1g_p$P.json 2>&1 | tail -14
-echo "=== epilogue variants on ffn-up parts=$P"; for e in none bias gelu res gelugrad; do VLM_GEMM_EPI_PARTS=$P timeout 100 python tools/gemm_bench.py --only "vit ffn-up fwd" --epi $e --cfg 0 2>&1 | tail -1; done
-echo "=== bench parts=$P"; VLM_GEMM_EPI_PARTS=$P timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | grep -v "$F" | tail -1 | tee gpurun_out/bench_r1g_p$P.json | cut -c1-200
-done
+echo "=== gemm tests"; timeout 900 python -m pytest tests/test_gemm_gpu.py -m gpu -q -x 2>&1 | grep -v "$F" | grep -E "^E  |passed|failed|FAILED|Error" | cut -c1-600 | tail -10
+echo "=== epilogue variants on ffn-up"; for e in none bias gelu res gelugrad; do timeout 100 python tools/gemm_bench.py --only "vit ffn-up fwd" --epi $e --cfg 0 2>&1 | tail -1 | cut -c1-70; done
+echo "=== gemm sweep"; timeout 300 python tools/gemm_bench.py --json gpurun_out/gemm_sweep_r1h.json 2>&1 | tail -14
+echo "=== bench"; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | grep -v "$F" | tail -1 | tee gpurun_out/bench_r1h.json | cut -c1-2400

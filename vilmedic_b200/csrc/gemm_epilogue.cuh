@@ -33,8 +33,11 @@ struct GemmEpilogue {
 // One chunk = W (16 or 32) consecutive fp32 accumulator columns of this thread's row, read from TMEM at `taddr`.
 // Order of operations: issue the TMEM load, issue the global loads the epilogue needs (GELU' input, residual, old C) while
 // it is in flight, wait, do the math, store.  Must be called by all 32 lanes (tcgen05.ld / wait::ld are warp-collective).
+// `stg` != null (bf16 C, no accumulation, full-width chunk): the result row goes to the warp's 128B-swizzled staging tile
+// (32 rows x 64 B; this chunk fills 16-byte units unit0 .. unit0 + W/8 - 1 of row `srow`) for a TMA tensor store.
 template <int W>
-__device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0, int M, int N, const GemmEpilogue& e) {
+__device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0, int M, int N, const GemmEpilogue& e,
+                                               uint8_t* stg = nullptr, int srow = 0, int unit0 = 0) {
   static_assert(W == 16 || W == 32, "chunk width");
   uint32_t acc[W];
   if constexpr (W == 32) tmem_ld32(taddr, acc);
@@ -179,6 +182,21 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0
           v[8 * j + 6] += p3.x;
           v[8 * j + 7] += p3.y;
         }
+      }
+      if (stg) {
+        // staging tile: 64-byte rows packed two per 128-byte line; 16-byte unit index XOR (line & 7) = SWIZZLE_128B
+        const int line = srow >> 1;
+#pragma unroll
+        for (int j = 0; j < W / 8; ++j) {
+          uint4 u;
+          u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+          u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+          u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+          u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+          const int unit = ((srow & 1) << 2) + unit0 + j;
+          *reinterpret_cast<uint4*>(stg + line * 128 + ((unit ^ (line & 7)) << 4)) = u;
+        }
+        return;
       }
       uint4* c4 = reinterpret_cast<uint4*>(crow);
 #pragma unroll

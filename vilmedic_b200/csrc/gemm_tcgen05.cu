@@ -28,8 +28,8 @@ static constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle row
 // Epilogue warps: PARTS per TMEM lane quadrant (warp w drains quadrant w%4, 16-column chunks c = part, part+PARTS, ...).
 // Register budget is per SM sub-partition (16384 registers, warps are dealt round-robin): 2 + 4*4 = 18 warps -> 5 on one
 // sub-partition -> <= 96 registers; 2 + 4*3 = 14 warps -> 4 per sub-partition -> <= 128 registers.
-static constexpr int GEMM_EPI_W = 16;               // accumulator columns per epilogue chunk
 __host__ __device__ constexpr int gemm_threads(int parts) { return 64 + 128 * parts; }
+static constexpr int GEMM_MAX_EPI_WARPS = 12;
 
 template <int BN>
 struct GemmSmem {
@@ -37,13 +37,16 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;            // epilogue staging: one 32x32 bf16 tile per epilogue warp
+  static constexpr int STG_BYTES = 32 * 32 * 2;
+  static constexpr int BAR_OFFSET = STG_OFFSET + GEMM_MAX_EPI_WARPS * STG_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
 };
 
-template <int BN, bool A_MN, bool B_MN, int PARTS>
+template <int BN, bool A_MN, bool B_MN, int PARTS, int GEMM_EPI_W>
 __global__ void __launch_bounds__(gemm_threads(PARTS), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_c, int tma_store,
                          int M, int N, int K, int batch, int a_bmul, int b_bmul, int split_k,
                          long long c_batch_stride, long long aux_batch_stride, long long res_batch_stride,
                          GemmEpilogue epi) {
@@ -74,6 +77,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (tma_store) tma_prefetch_desc(&tmap_c);
 #pragma unroll
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -177,10 +181,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else {
-    // ===================== epilogue warps (2..9) =====================
+    // ===================== epilogue warps (2 .. 2+4*PARTS) =====================
+    // Warp w drains TMEM lane quadrant w%4 (rows quad*32 .. +32 of the tile) and the 32-column spans s = part, part+PARTS, ...
+    // Each span is two 16-column chunks.  bf16 C without accumulation leaves through shared memory: every lane writes its
+    // row into a 128B-swizzled 32x32 staging tile and one lane issues a TMA tensor store (full-line writes, clipped at the
+    // M / N edges by the tensor map), so the epilogue warps never wait on global stores.
+    static_assert(GEMM_EPI_W == 16, "a span is two 16-column chunks");
     const int quad = warp_idx & 3;                 // TMEM lane quadrant this warp may access
-    const int part = (warp_idx - 2) >> 2;          // which slice of the tile's columns this warp drains
-    constexpr int CHUNKS = BN / GEMM_EPI_W;        // BN in {64,128,192,256} -> 4,8,12,16 chunks of 16 columns
+    const int part = (warp_idx - 2) >> 2;          // which spans of the tile's columns this warp drains
+    constexpr int SPANS = BN / 32;
+    uint8_t* stg = smem + S::STG_OFFSET + (warp_idx - 2) * S::STG_BYTES;
+    const unsigned long long rng_add = (epi.p_drop > 0.f && epi.offset_ptr) ? __ldg(epi.offset_ptr) : 0ull;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
@@ -196,7 +207,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         e.bias = nullptr;
         e.residual = nullptr;
       }
-      if (e.p_drop > 0.f && e.offset_ptr) e.offset += __ldg(e.offset_ptr);
+      e.offset += rng_add;
       if (b > 0) {
         const size_t esz = e.c_fp32 ? 4 : 2;
         e.c = reinterpret_cast<uint8_t*>(e.c) + (size_t)b * c_batch_stride * esz;
@@ -209,8 +220,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = part; c < CHUNKS; c += PARTS)
-        epilogue_chunk<GEMM_EPI_W>(taddr + c * GEMM_EPI_W, row, n0 + c * GEMM_EPI_W, M, N, e);
+      for (int sp = part; sp < SPANS; sp += PARTS) {
+        const int col_s = n0 + sp * 32;
+        if (col_s >= N) break;
+        const bool staged = tma_store != 0 && col_s + 32 <= N;       // warp-uniform
+        if (staged) {                                                // the previous store must have drained the tile
+          if (lane == 0) bulk_wait_read_all();
+          __syncwarp();
+        }
+        epilogue_chunk<16>(taddr + sp * 32, row, col_s, M, N, e, staged ? stg : nullptr, lane, 0);
+        epilogue_chunk<16>(taddr + sp * 32 + 16, row, col_s + 16, M, N, e, staged ? stg : nullptr, lane, 2);
+        if (staged) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmap_c, stg, col_s, m0 + quad * 32, b);
+            bulk_commit_group();
+          }
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -219,6 +247,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         acc_phase ^= 1u;
       }
     }
+    if (tma_store && lane == 0) bulk_wait_all();                     // global writes complete before the CTA retires
   }
 
   tc_fence_before();
@@ -309,21 +338,14 @@ void bind_context_for_driver_calls() {
   }
 }
 
-static int epi_parts() {   // debug knob: VLM_GEMM_EPI_PARTS=3|4 (epilogue warps per TMEM quadrant)
-  static int v = -1;
-  if (v < 0) {
-    const char* s = getenv("VLM_GEMM_EPI_PARTS");
-    v = (s && atoi(s) == 3) ? 3 : 4;
-  }
-  return v;
-}
+static constexpr int GEMM_PARTS = 3;   // epilogue warps per TMEM lane quadrant (14 warps per CTA, <= 128 registers each)
 
-template <int BN, bool A_MN, bool B_MN, int PARTS>
-static int launch_gemm_p(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int batch, int a_bmul,
-                       int b_bmul, int split_k, long long c_bs, long long aux_bs, long long res_bs, const GemmEpilogue& epi, int max_ctas,
-                       cudaStream_t stream) {
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int tma_store, int M, int N, int K,
+                       int batch, int a_bmul, int b_bmul, int split_k, long long c_bs, long long aux_bs, long long res_bs,
+                       const GemmEpilogue& epi, int max_ctas, cudaStream_t stream) {
   using S = GemmSmem<BN>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN, PARTS>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN, GEMM_PARTS, 16>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -337,17 +359,9 @@ static int launch_gemm_p(const CUtensorMap& ta, const CUtensorMap& tb, int M, in
   const long long tiles = (long long)m_tiles * n_tiles * batch * split_k;
   int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  kern<<<grid, gemm_threads(PARTS), S::TOTAL, stream>>>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_bs, aux_bs, res_bs, epi);
+  kern<<<grid, gemm_threads(GEMM_PARTS), S::TOTAL, stream>>>(ta, tb, tc, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k, c_bs,
+                                                             aux_bs, res_bs, epi);
   return check_launch("gemm_bf16_tcgen05");
-}
-
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int batch, int a_bmul,
-                       int b_bmul, int split_k, long long c_bs, long long aux_bs, long long res_bs, const GemmEpilogue& epi, int max_ctas,
-                       cudaStream_t stream) {
-  if (epi_parts() == 3)
-    return launch_gemm_p<BN, A_MN, B_MN, 3>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_bs, aux_bs, res_bs, epi, max_ctas, stream);
-  return launch_gemm_p<BN, A_MN, B_MN, 4>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_bs, aux_bs, res_bs, epi, max_ctas, stream);
 }
 
 static int pick_bn(int M, int N, int batch, int force_bn) {
@@ -500,20 +514,31 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
     }
     e.atomic = split_k > 1;
   }
+  // C tensor map for the TMA-store epilogue: bf16 C, plain store (no accumulate / split-K atomics), 16-byte aligned pitch.
+  CUtensorMap tc = ta;
+  int tma_store = 0;
+  if (bn2 == 0 && !c_is_fp32 && !accumulate && !e.atomic && (ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0 &&
+      (batch == 1 || (c_batch_stride % 8) == 0)) {
+    const uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)batch};
+    const uint64_t strides[2] = {(uint64_t)ldc, (uint64_t)(batch > 1 ? c_batch_stride : ldc * (long long)M)};
+    const uint32_t box[3] = {32, 32, 1};
+    if (make_tmap_bf16_nd(&tc, c, 3, dims, strides, box)) return -1;
+    tma_store = 1;
+  }
   if (bn2 != 0) return gemm2_dispatch(a, lda, a_mn_major, b, ldb, b_mn_major, M, N, K, bn2, e, s);
 
 #define VLM_GEMM_DISPATCH(BN_)                                                                                      \
   if (a_mn_major) {                                                                                                 \
     if (b_mn_major)                                                                                                 \
-      return launch_gemm<BN_, true, true>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                 \
+      return launch_gemm<BN_, true, true>(ta, tb, tc, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                 \
                                           res_batch_stride, e, max_ctas, s);                                        \
-    return launch_gemm<BN_, true, false>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride, res_batch_stride, \
+    return launch_gemm<BN_, true, false>(ta, tb, tc, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride, res_batch_stride, \
                                          e, max_ctas, s);                                                           \
   } else {                                                                                                          \
     if (b_mn_major)                                                                                                 \
-      return launch_gemm<BN_, false, true>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                \
+      return launch_gemm<BN_, false, true>(ta, tb, tc, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                \
                                            res_batch_stride, e, max_ctas, s);                                       \
-    return launch_gemm<BN_, false, false>(ta, tb, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                 \
+    return launch_gemm<BN_, false, false>(ta, tb, tc, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                 \
                                           res_batch_stride, e, max_ctas, s);                                        \
   }
   switch (bn) {
