@@ -160,7 +160,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   } else if (warp_idx == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    // whole warp runs the loop (uniform datapath for descriptors / barriers), one elected lane issues the tcgen05 ops
+    {
+      const bool leader = elect_one();
       const uint32_t id_s = make_idesc_bf16(128, Nq, false, false);     // S^T, dP^T : K-major x K-major
       const uint32_t id_dv = make_idesc_bf16(128, 64, false, true);      // dV, dK   : K-major A, MN-major B
       const uint32_t id_dq = make_idesc_bf16(128, 64, true, true);       // dQ       : MN-major A and B
@@ -178,39 +180,51 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           mbar_wait(&kv_full[buf], kvph);
           tc_fence_after();
           // (1) S^T = K_j Q^T
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + ATC_S_COL, make_smem_desc(aK + k * 32, 16, 1024), make_smem_desc(aQ + k * 32, 16, 1024), id_s, k > 0);
-          umma_commit(s_full);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + ATC_S_COL, make_smem_desc(aK + k * 32, 16, 1024), make_smem_desc(aQ + k * 32, 16, 1024), id_s, k > 0);
+            umma_commit(s_full);
+          }
+          __syncwarp();
           mbar_wait(p_ready, tph);
           tc_fence_after();
           // (2) dP^T = V_j dO^T  (same TMEM columns; P^T has been extracted)
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + ATC_S_COL, make_smem_desc(aV + k * 32, 16, 1024), make_smem_desc(aDO + k * 32, 16, 1024), id_s, k > 0);
-          umma_commit(dp_full);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + ATC_S_COL, make_smem_desc(aV + k * 32, 16, 1024), make_smem_desc(aDO + k * 32, 16, 1024), id_s, k > 0);
+            umma_commit(dp_full);
+          }
+          __syncwarp();
           mbar_wait(out_free, tph ^ 1u);   // dV / dK / dQ accumulators of the previous tile have been drained
           tc_fence_after();
           // (3) dV_j = P^T dO
-          for (int k = 0; k < nq16; ++k)
-            umma_bf16(tmem_base + ATC_DV_COL, make_smem_desc(aPT + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                      make_smem_desc(aDO + k * 2048, 16384, 1024), id_dv, k > 0);
-          umma_commit(dv_done);
+          if (leader) {
+            for (int k = 0; k < nq16; ++k)
+              umma_bf16(tmem_base + ATC_DV_COL, make_smem_desc(aPT + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                        make_smem_desc(aDO + k * 2048, 16384, 1024), id_dv, k > 0);
+            umma_commit(dv_done);
+          }
+          __syncwarp();
           mbar_wait(ds_ready, tph);
           tc_fence_after();
-          // (4) dK_j = dS^T Q
-          for (int k = 0; k < nq16; ++k)
-            umma_bf16(tmem_base + ATC_DK_COL, make_smem_desc(aPT + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                      make_smem_desc(aQ + k * 2048, 16384, 1024), id_dv, k > 0);
-          // (5) dQ[mb] += dS K_j   (dS = the dS^T tile through an MN-major descriptor: 64-query blocks 16 KB apart)
-          for (int mb = 0; mb < q_blocks; ++mb)
+          if (leader) {
+            // (4) dK_j = dS^T Q
+            for (int k = 0; k < nq16; ++k)
+              umma_bf16(tmem_base + ATC_DK_COL, make_smem_desc(aPT + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                        make_smem_desc(aQ + k * 2048, 16384, 1024), id_dv, k > 0);
+            // (5) dQ[mb] += dS K_j   (dS = the dS^T tile through an MN-major descriptor: 64-query blocks 16 KB apart)
+            for (int mb = 0; mb < q_blocks; ++mb)
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              umma_bf16(tmem_base + ATC_DQ_COL + mb * 64, make_smem_desc(aPT + mb * 32768 + k * 2048, 16384, 1024),
-                        make_smem_desc(aK + k * 2048, 16384, 1024), id_dq, (j > 0 || k > 0) ? 1u : 0u);
-          umma_commit(out_full);
-          umma_commit(&kv_empty[buf]);
-          if (j == ntiles - 1) umma_commit(qdo_empty);
+              for (int k = 0; k < 8; ++k)
+                umma_bf16(tmem_base + ATC_DQ_COL + mb * 64, make_smem_desc(aPT + mb * 32768 + k * 2048, 16384, 1024),
+                          make_smem_desc(aK + k * 2048, 16384, 1024), id_dq, (j > 0 || k > 0) ? 1u : 0u);
+            umma_commit(out_full);
+            umma_commit(&kv_empty[buf]);
+            if (j == ntiles - 1) umma_commit(qdo_empty);
+          }
+          __syncwarp();
         }
       }
     }
@@ -590,7 +604,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
     }
   } else if (warp_idx == 1) {
-    if (lane == 0) {
+    {   // whole warp runs the loop, one elected lane issues (see the backward kernel)
+      const bool leader = elect_one();
       const uint32_t id_s = make_idesc_bf16(128, Nk, false, false);
       const uint32_t id_o = make_idesc_bf16(128, 64, false, true);
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
@@ -605,19 +620,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           const uint32_t aQ = smem_u32(sQ + buf * S::Q_BYTES);
           mbar_wait(&q_full[buf], (tile_cnt >> 1) & 1u);
           tc_fence_after();
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), id_s, k > 0);
-          umma_commit(s_full);
-          umma_commit(&q_empty[buf]);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), id_s, k > 0);
+            umma_commit(s_full);
+            umma_commit(&q_empty[buf]);
+          }
+          __syncwarp();
           mbar_wait(p_ready, tph);
           mbar_wait(o_free, tph ^ 1u);
           tc_fence_after();
-          for (int k = 0; k < nk16; ++k)
-            umma_bf16(tmem_base + O_COL, make_smem_desc(aP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                      make_smem_desc(aV + k * 2048, 16384, 1024), id_o, k > 0);
-          umma_commit(o_full);
-          if (i == qtiles - 1) umma_commit(kv_empty);
+          if (leader) {
+            for (int k = 0; k < nk16; ++k)
+              umma_bf16(tmem_base + O_COL, make_smem_desc(aP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                        make_smem_desc(aV + k * 2048, 16384, 1024), id_o, k > 0);
+            umma_commit(o_full);
+            if (i == qtiles - 1) umma_commit(kv_empty);
+          }
+          __syncwarp();
         }
       }
     }

@@ -33,7 +33,7 @@ struct GemmEpilogue {
 // One chunk = W (16 or 32) consecutive fp32 accumulator columns of this thread's row, read from TMEM at `taddr`.
 // Order of operations: issue the TMEM load, issue the global loads the epilogue needs (GELU' input, residual, old C) while
 // it is in flight, wait, do the math, store.  Must be called by all 32 lanes (tcgen05.ld / wait::ld are warp-collective).
-// `stg` != null (bf16 C, no accumulation, full-width chunk): the result row goes to the warp's 128B-swizzled staging tile
+// `stg` != null (bf16 C, no accumulation, full-width chunk): the result row goes to the warp's 64B-swizzled staging tile
 // (32 rows x 64 B; this chunk fills 16-byte units unit0 .. unit0 + W/8 - 1 of row `srow`) for a TMA tensor store.
 template <int W>
 __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0, int M, int N, const GemmEpilogue& e,
@@ -184,8 +184,8 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0
         }
       }
       if (stg) {
-        // staging tile: 64-byte rows packed two per 128-byte line; 16-byte unit index XOR (line & 7) = SWIZZLE_128B
-        const int line = srow >> 1;
+        // staging tile: dense 64-byte rows, CU_TENSOR_MAP_SWIZZLE_64B: 16-byte unit index ^= address bits [7,9) = (row >> 1) & 3
+        // (8 consecutive rows land on 8 distinct 16-byte slots of a 128-byte bank line: conflict-free)
 #pragma unroll
         for (int j = 0; j < W / 8; ++j) {
           uint4 u;
@@ -193,8 +193,8 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0
           u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
           u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
           u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-          const int unit = ((srow & 1) << 2) + unit0 + j;
-          *reinterpret_cast<uint4*>(stg + line * 128 + ((unit ^ (line & 7)) << 4)) = u;
+          const int unit = (unit0 + j) ^ ((srow >> 1) & 3);
+          *reinterpret_cast<uint4*>(stg + srow * 64 + (unit << 4)) = u;
         }
         return;
       }
@@ -267,7 +267,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0
 int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch,
                    uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows);
 int make_tmap_bf16_nd(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                      const uint32_t* box);
+                      const uint32_t* box, int swizzle_bytes = 128);
 void bind_context_for_driver_calls();
 
 }  // namespace vlm

@@ -139,52 +139,62 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
-      // K-major: 8-row groups are 1024 B apart; advancing 16 k = +32 B inside the swizzled row.
-      // MN-major: 64-wide MN blocks are BK*128 B apart (LBO), 8-k groups 1024 B apart (SBO); 16 k = +2048 B.
-      constexpr uint32_t A_LBO = A_MN ? GEMM_BK * 128 : 0, B_LBO = B_MN ? GEMM_BK * 128 : 0;
-      constexpr uint32_t A_KSTEP = A_MN ? 2048 : 32, B_KSTEP = B_MN ? 2048 : 32;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-        const int split = work / total_tiles;
-        const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
-        if (kb0 >= kb1) continue;
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+    // The whole warp runs the loop (so tile / stage / descriptor arithmetic stays on the uniform datapath) and one elected
+    // lane issues.  ncu showed the single-lane version spending ~100 dependent instructions (ELECT + R2UR per operand) per
+    // k-block: 930 cycles of issue latency for 349 cycles of tensor work (profiles/ncu_gemm_r1_epilogue.txt).
+    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
+    // K-major: 8-row groups are 1024 B apart; advancing 16 k = +32 B inside the swizzled row.
+    // MN-major: 64-wide MN blocks are BK*128 B apart (LBO), 8-k groups 1024 B apart (SBO); 16 k = +2048 B.
+    constexpr uint32_t A_LBO = A_MN ? GEMM_BK * 128 : 0, B_LBO = B_MN ? GEMM_BK * 128 : 0;
+    constexpr uint32_t A_KSTEP = A_MN ? 2048 : 32, B_KSTEP = B_MN ? 2048 : 32;
+    // descriptor = hi word (SBO 1024 B, version 1, SWIZZLE_128B) : lo word (start address >> 4 | LBO >> 4 << 16)
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_lo0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | ((A_LBO >> 4) << 16);
+    const uint32_t b_lo0 = (((smem_u32(smem) + S::A_BYTES) >> 4) & 0x3FFFu) | ((B_LBO >> 4) << 16);
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      const int split = work / total_tiles;
+      const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+      if (kb0 >= kb1) continue;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint32_t sb = sa + S::A_BYTES;
+        const uint32_t a_lo = a_lo0 + (uint32_t)stage * (S::STAGE_BYTES >> 4);
+        const uint32_t b_lo = b_lo0 + (uint32_t)stage * (S::STAGE_BYTES >> 4);
+        if (leader) {
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * A_KSTEP, A_LBO, 1024);
-            const uint64_t db = make_smem_desc(sb + k * B_KSTEP, B_LBO, 1024);
+            const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(a_lo + k * (A_KSTEP >> 4));
+            const uint64_t db = ((uint64_t)DESC_HI << 32) | (uint64_t)(b_lo + k * (B_KSTEP >> 4));
             umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1u;
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
         }
+      }
+      if (leader) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
       }
     }
   } else {
     // ===================== epilogue warps (2 .. 2+4*PARTS) =====================
     // Warp w drains TMEM lane quadrant w%4 (rows quad*32 .. +32 of the tile) and the 32-column spans s = part, part+PARTS, ...
     // Each span is two 16-column chunks.  bf16 C without accumulation leaves through shared memory: every lane writes its
-    // row into a 128B-swizzled 32x32 staging tile and one lane issues a TMA tensor store (full-line writes, clipped at the
+    // row into a 64B-swizzled 32x32 staging tile and one lane issues a TMA tensor store (full-line writes, clipped at the
     // M / N edges by the tensor map), so the epilogue warps never wait on global stores.
     static_assert(GEMM_EPI_W == 16, "a span is two 16-column chunks");
     const int quad = warp_idx & 3;                 // TMEM lane quadrant this warp may access
@@ -303,7 +313,7 @@ int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t ro
 
 // Generic bf16 tiled tensor map (rank <= 5), 128B swizzle, zero OOB fill; strides in ELEMENTS for dims 1..rank-1.
 int make_tmap_bf16_nd(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                      const uint32_t* box) {
+                      const uint32_t* box, int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return -1;
   cuuint64_t d[5], st[4];
@@ -314,9 +324,10 @@ int make_tmap_bf16_nd(CUtensorMap* tm, const void* ptr, int rank, const uint64_t
     es[i] = 1;
     if (i > 0) st[i - 1] = strides_elems[i - 1] * 2;
   }
+  const CUtensorMapSwizzle sw = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                               : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B);
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), d, st, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(rank %d) failed (%d): ptr=%p dims=%llu,%llu,%llu,%llu", rank, (int)r, ptr,
               (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
@@ -517,12 +528,16 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
   // C tensor map for the TMA-store epilogue: bf16 C, plain store (no accumulate / split-K atomics), 16-byte aligned pitch.
   CUtensorMap tc = ta;
   int tma_store = 0;
-  if (bn2 == 0 && !c_is_fp32 && !accumulate && !e.atomic && (ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0 &&
+  static const bool tma_store_enabled = [] {   // debug knob: VLM_GEMM_TMA_STORE=0 keeps the direct-store epilogue
+    const char* v = getenv("VLM_GEMM_TMA_STORE");
+    return !(v && v[0] == '0');
+  }();
+  if (tma_store_enabled && bn2 == 0 && !c_is_fp32 && !accumulate && !e.atomic && (ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0 &&
       (batch == 1 || (c_batch_stride % 8) == 0)) {
     const uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)batch};
     const uint64_t strides[2] = {(uint64_t)ldc, (uint64_t)(batch > 1 ? c_batch_stride : ldc * (long long)M)};
     const uint32_t box[3] = {32, 32, 1};
-    if (make_tmap_bf16_nd(&tc, c, 3, dims, strides, box)) return -1;
+    if (make_tmap_bf16_nd(&tc, c, 3, dims, strides, box, 64)) return -1;
     tma_store = 1;
   }
   if (bn2 != 0) return gemm2_dispatch(a, lda, a_mn_major, b, ldb, b_mn_major, M, N, K, bn2, e, s);
