@@ -1,10 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 F='loss_type\|Swig\|swig\|Docs:\|^$'
-echo "=== gemm tests (TMA store off: validates the warp-uniform MMA issuer)"; VLM_GEMM_TMA_STORE=0 timeout 900 python -m pytest tests/test_gemm_gpu.py -m gpu -q -x 2>&1 | grep -v "$F" | grep -E "^E  |passed|failed|FAILED|Error" | cut -c1-300 | tail -5
-echo "=== variants, TMA store off"; for e in none gelu; do VLM_GEMM_TMA_STORE=0 timeout 100 python tools/gemm_bench.py --only "vit ffn-up fwd" --epi $e --cfg 0 2>&1 | tail -1 | cut -c1-70; done
-echo "=== gemm tests (TMA store on)"; timeout 900 python -m pytest tests/test_gemm_gpu.py -m gpu -q -x 2>&1 | grep -v "$F" | grep -E "^E  |passed|failed|FAILED|Error" | cut -c1-300 | tail -5
-echo "=== sanitizer"; timeout 300 compute-sanitizer --tool memcheck --print-limit 5 python tools/gemm_bench.py --only "dec out fwd" --cfg 0 --epi none 2>&1 | grep -v "$F" | head -40 | cut -c1-200
+echo "=== gemm + attention tests"; timeout 900 python -m pytest tests/test_gemm_gpu.py tests/test_ops_gpu.py -m gpu -q -x 2>&1 | grep -v "$F" | grep -E "^E  |passed|failed|FAILED|Error" | cut -c1-300 | tail -5
 echo "=== epilogue variants on ffn-up"; for e in none bias gelu res gelugrad; do timeout 100 python tools/gemm_bench.py --only "vit ffn-up fwd" --epi $e --cfg 0 2>&1 | tail -1 | cut -c1-70; done
-echo "=== gemm sweep"; timeout 300 python tools/gemm_bench.py --json gpurun_out/gemm_sweep_r1h.json 2>&1 | tail -14
-echo "=== bench"; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | grep -v "$F" | tail -1 | tee gpurun_out/bench_r1h.json | cut -c1-2400
+echo "=== gemm sweep"; timeout 300 python tools/gemm_bench.py --json gpurun_out/gemm_sweep_r1i.json 2>&1 | tail -14 | cut -c1-100
+echo "=== bench"; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | grep -v "$F" | tail -1 | tee gpurun_out/bench_r1i.json | cut -c1-2400

@@ -33,11 +33,8 @@ struct GemmEpilogue {
 // One chunk = W (16 or 32) consecutive fp32 accumulator columns of this thread's row, read from TMEM at `taddr`.
 // Order of operations: issue the TMEM load, issue the global loads the epilogue needs (GELU' input, residual, old C) while
 // it is in flight, wait, do the math, store.  Must be called by all 32 lanes (tcgen05.ld / wait::ld are warp-collective).
-// `stg` != null (bf16 C, no accumulation, full-width chunk): the result row goes to the warp's 64B-swizzled staging tile
-// (32 rows x 64 B; this chunk fills 16-byte units unit0 .. unit0 + W/8 - 1 of row `srow`) for a TMA tensor store.
 template <int W>
-__device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0, int M, int N, const GemmEpilogue& e,
-                                               uint8_t* stg = nullptr, int srow = 0, int unit0 = 0) {
+__device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0, int M, int N, const GemmEpilogue& e) {
   static_assert(W == 16 || W == 32, "chunk width");
   uint32_t acc[W];
   if constexpr (W == 32) tmem_ld32(taddr, acc);
@@ -183,21 +180,6 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0
           v[8 * j + 7] += p3.y;
         }
       }
-      if (stg) {
-        // staging tile: dense 64-byte rows, CU_TENSOR_MAP_SWIZZLE_64B: 16-byte unit index ^= address bits [7,9) = (row >> 1) & 3
-        // (8 consecutive rows land on 8 distinct 16-byte slots of a 128-byte bank line: conflict-free)
-#pragma unroll
-        for (int j = 0; j < W / 8; ++j) {
-          uint4 u;
-          u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-          u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-          u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-          u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-          const int unit = (unit0 + j) ^ ((srow >> 1) & 3);
-          *reinterpret_cast<uint4*>(stg + srow * 64 + (unit << 4)) = u;
-        }
-        return;
-      }
       uint4* c4 = reinterpret_cast<uint4*>(crow);
 #pragma unroll
       for (int j = 0; j < W / 8; ++j) {
@@ -262,6 +244,116 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0
   }
 }
 
+
+// ---- staged fast path -------------------------------------------------------------------------------------------------
+// One 32-column span of one accumulator row per lane, bf16 C without accumulation, interior of the N range (col0 + 32 <= N).
+// `pre` holds the row's 32 bf16 inputs of this span (GELU' argument if act == 2, else the residual) loaded at tile start,
+// i.e. under the mainloop of the tile, so no global-load latency is exposed here.  The result (and, for act == 1 with
+// aux_out, the pre-activation) leaves through the warp's 32x32 bf16 staging tile (dense 64-byte rows, SWIZZLE_64B: 16-byte
+// unit ^= (row >> 1) & 3 — conflict-free for row-per-lane 16-byte accesses) and TMA tensor stores issued by lane 0; rows
+// >= M are clipped by the tensor map.  Must be called by all 32 lanes.
+__device__ __forceinline__ void stg_write_row(uint8_t* stg, int lane, const uint32_t* packed /* 16 x bf16x2 */) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int unit = u ^ ((lane >> 1) & 3);
+    *reinterpret_cast<uint4*>(stg + lane * 64 + (unit << 4)) =
+        make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
+  }
+}
+
+__device__ __noinline__ void epilogue_span_staged(uint32_t taddr, int row, int row0, int col0, int batch_idx, int lane,
+                                                  const GemmEpilogue& e, float alpha, uint4 pre0, uint4 pre1, uint4 pre2,
+                                                  uint4 pre3, bool has_pre, uint8_t* stg, const CUtensorMap* tmap_c,
+                                                  const CUtensorMap* tmap_aux) {
+  if (lane == 0) bulk_wait_read_all();          // the previous TMA store has drained the staging tile
+  __syncwarp();
+  const bool stash = e.act == 1 && e.aux_out != nullptr;
+  uint32_t stashed[16];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {                 // two 16-column halves
+    uint32_t acc[16];
+    tmem_ld16(taddr + 16 * h, acc);
+    tmem_ld_wait();
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) * alpha;
+    if (e.bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0 + 16 * h);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 b = __ldg(b4 + j);
+        v[4 * j + 0] += b.x;
+        v[4 * j + 1] += b.y;
+        v[4 * j + 2] += b.z;
+        v[4 * j + 3] += b.w;
+      }
+    }
+    const uint4 pa = h == 0 ? pre0 : pre2, pb = h == 0 ? pre1 : pre3;
+    const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+    if (e.act == 1) {
+      if (stash) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) stashed[8 * h + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+    } else if (e.act == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 x = unpack_bf16x2(pw[j]);
+        v[2 * j] *= gelu_erf_grad(x.x);
+        v[2 * j + 1] *= gelu_erf_grad(x.y);
+      }
+    }
+    if (e.p_drop > 0.f) {
+      const Philox rng(e.seed);
+      const uint32_t thr = (uint32_t)(e.p_drop * 4294967296.0f);
+      const float inv_keep = 1.f / (1.f - e.p_drop);
+      const unsigned long long base =
+          ((unsigned long long)row * (unsigned long long)e.drop_ld + (unsigned long long)(col0 + 16 * h)) >> 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 r = rng(base + j, e.offset);
+        v[4 * j + 0] = r.x >= thr ? v[4 * j + 0] * inv_keep : 0.f;
+        v[4 * j + 1] = r.y >= thr ? v[4 * j + 1] * inv_keep : 0.f;
+        v[4 * j + 2] = r.z >= thr ? v[4 * j + 2] * inv_keep : 0.f;
+        v[4 * j + 3] = r.w >= thr ? v[4 * j + 3] * inv_keep : 0.f;
+      }
+    }
+    if (e.act != 2 && has_pre) {                // residual add (bf16)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 x = unpack_bf16x2(pw[j]);
+        v[2 * j] += x.x;
+        v[2 * j + 1] += x.y;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int unit = (2 * h + u) ^ ((lane >> 1) & 3);
+      *reinterpret_cast<uint4*>(stg + lane * 64 + (unit << 4)) =
+          make_uint4(pack_bf16x2(v[8 * u + 0], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                     pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+    }
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(tmap_c, stg, col0, row0, batch_idx);
+    bulk_commit_group();
+  }
+  if (stash) {                                  // second trip through the same tile for the GELU pre-activation
+    if (lane == 0) bulk_wait_read_all();
+    __syncwarp();
+    stg_write_row(stg, lane, stashed);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(tmap_aux, stg, col0, row0, batch_idx);
+      bulk_commit_group();
+    }
+  }
+}
 
 // host-side pieces shared by the GEMM translation units
 int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch,

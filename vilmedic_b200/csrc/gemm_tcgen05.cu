@@ -46,7 +46,7 @@ struct GemmSmem {
 template <int BN, bool A_MN, bool B_MN, int PARTS, int GEMM_EPI_W>
 __global__ void __launch_bounds__(gemm_threads(PARTS), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_c, int tma_store,
+                         const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux, int tma_store,
                          int M, int N, int K, int batch, int a_bmul, int b_bmul, int split_k,
                          long long c_batch_stride, long long aux_batch_stride, long long res_batch_stride,
                          GemmEpilogue epi) {
@@ -77,7 +77,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    if (tma_store) tma_prefetch_desc(&tmap_c);
+    if (tma_store) {
+      tma_prefetch_desc(&tmap_c);
+      tma_prefetch_desc(&tmap_aux);
+    }
 #pragma unroll
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -225,28 +228,46 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (e.aux_in) e.aux_in += (size_t)b * aux_batch_stride;
         if (e.aux_out) e.aux_out += (size_t)b * aux_batch_stride;
       }
+      const int row = m0 + quad * 32 + lane;
+      // Fast path: bf16 C by TMA store, every span of the tile inside N.  The per-row inputs of this warp's spans (GELU'
+      // argument or residual) are requested now, before waiting for the accumulator: their DRAM latency hides under the
+      // mainloop of this tile.
+      const bool fast = tma_store != 0 && n0 + BN <= N;                  // warp-uniform
+      constexpr int NSP = (SPANS + PARTS - 1) / PARTS;
+      uint4 pre[NSP][4];
+      const bf16* pre_src = e.act == 2 ? e.aux_in : reinterpret_cast<const bf16*>(e.residual);
+      const long long pre_ld = e.act == 2 ? e.ld_aux : e.ldr;
+      const bool has_pre = fast && pre_src != nullptr;
+      if (has_pre && row < M) {
+#pragma unroll
+        for (int i = 0; i < NSP; ++i) {
+          const int sp = part + i * PARTS;
+          if (sp < SPANS) {
+            const uint4* src = reinterpret_cast<const uint4*>(pre_src + (long long)row * pre_ld + n0 + sp * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pre[i][j] = __ldg(src + j);
+          }
+        }
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int sp = part; sp < SPANS; sp += PARTS) {
-        const int col_s = n0 + sp * 32;
-        if (col_s >= N) break;
-        const bool staged = tma_store != 0 && col_s + 32 <= N;       // warp-uniform
-        if (staged) {                                                // the previous store must have drained the tile
-          if (lane == 0) bulk_wait_read_all();
-          __syncwarp();
+      if (fast) {
+        const float alpha = e.alpha_ptr ? e.alpha * __ldg(e.alpha_ptr) : e.alpha;
+#pragma unroll
+        for (int i = 0; i < NSP; ++i) {
+          const int sp = part + i * PARTS;
+          if (sp < SPANS)
+            epilogue_span_staged(taddr + sp * 32, row, m0 + quad * 32, n0 + sp * 32, b, lane, e, alpha, pre[i][0], pre[i][1],
+                                 pre[i][2], pre[i][3], has_pre, stg, &tmap_c, &tmap_aux);
         }
-        epilogue_chunk<16>(taddr + sp * 32, row, col_s, M, N, e, staged ? stg : nullptr, lane, 0);
-        epilogue_chunk<16>(taddr + sp * 32 + 16, row, col_s + 16, M, N, e, staged ? stg : nullptr, lane, 2);
-        if (staged) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_3d(&tmap_c, stg, col_s, m0 + quad * 32, b);
-            bulk_commit_group();
-          }
+      } else {
+#pragma unroll 1
+        for (int sp = part; sp < SPANS; sp += PARTS) {
+          const int col_s = n0 + sp * 32;
+          if (col_s >= N) break;
+          epilogue_chunk<16>(taddr + sp * 32, row, col_s, M, N, e);
+          epilogue_chunk<16>(taddr + sp * 32 + 16, row, col_s + 16, M, N, e);
         }
       }
       tc_fence_before();
@@ -352,7 +373,8 @@ void bind_context_for_driver_calls() {
 static constexpr int GEMM_PARTS = 3;   // epilogue warps per TMEM lane quadrant (14 warps per CTA, <= 128 registers each)
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int tma_store, int M, int N, int K,
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx, int tma_store,
+                       int M, int N, int K,
                        int batch, int a_bmul, int b_bmul, int split_k, long long c_bs, long long aux_bs, long long res_bs,
                        const GemmEpilogue& epi, int max_ctas, cudaStream_t stream) {
   using S = GemmSmem<BN>;
@@ -370,8 +392,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const long long tiles = (long long)m_tiles * n_tiles * batch * split_k;
   int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  kern<<<grid, gemm_threads(GEMM_PARTS), S::TOTAL, stream>>>(ta, tb, tc, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k, c_bs,
-                                                             aux_bs, res_bs, epi);
+  kern<<<grid, gemm_threads(GEMM_PARTS), S::TOTAL, stream>>>(ta, tb, tc, tx, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k,
+                                                             c_bs, aux_bs, res_bs, epi);
   return check_launch("gemm_bf16_tcgen05");
 }
 
@@ -526,7 +548,7 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
     e.atomic = split_k > 1;
   }
   // C tensor map for the TMA-store epilogue: bf16 C, plain store (no accumulate / split-K atomics), 16-byte aligned pitch.
-  CUtensorMap tc = ta;
+  CUtensorMap tc = ta, tx = ta;
   int tma_store = 0;
   static const bool tma_store_enabled = [] {   // debug knob: VLM_GEMM_TMA_STORE=0 keeps the direct-store epilogue
     const char* v = getenv("VLM_GEMM_TMA_STORE");
@@ -539,21 +561,33 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
     const uint32_t box[3] = {32, 32, 1};
     if (make_tmap_bf16_nd(&tc, c, 3, dims, strides, box, 64)) return -1;
     tma_store = 1;
+    if (act == 1 && aux_out) {               // GELU stash leaves through the same staging tile
+      if ((ld_aux % 8) == 0 && (reinterpret_cast<uintptr_t>(aux_out) & 15) == 0 && (batch == 1 || (aux_batch_stride % 8) == 0)) {
+        const uint64_t xstrides[2] = {(uint64_t)ld_aux, (uint64_t)(batch > 1 ? aux_batch_stride : ld_aux * (long long)M)};
+        if (make_tmap_bf16_nd(&tx, aux_out, 3, dims, xstrides, box, 64)) return -1;
+      } else {
+        tma_store = 0;
+      }
+    }
+    // the fast path reads the GELU' argument / residual rows with 16-byte loads
+    if (act == 2 && ((ld_aux % 8) != 0 || (reinterpret_cast<uintptr_t>(aux_in) & 15) != 0)) tma_store = 0;
+    if (residual && ((ldr % 8) != 0 || (reinterpret_cast<uintptr_t>(residual) & 15) != 0)) tma_store = 0;
+    if (bias && (reinterpret_cast<uintptr_t>(bias) & 15) != 0) tma_store = 0;
   }
   if (bn2 != 0) return gemm2_dispatch(a, lda, a_mn_major, b, ldb, b_mn_major, M, N, K, bn2, e, s);
 
 #define VLM_GEMM_DISPATCH(BN_)                                                                                      \
   if (a_mn_major) {                                                                                                 \
     if (b_mn_major)                                                                                                 \
-      return launch_gemm<BN_, true, true>(ta, tb, tc, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                 \
+      return launch_gemm<BN_, true, true>(ta, tb, tc, tx, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                 \
                                           res_batch_stride, e, max_ctas, s);                                        \
-    return launch_gemm<BN_, true, false>(ta, tb, tc, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride, res_batch_stride, \
+    return launch_gemm<BN_, true, false>(ta, tb, tc, tx, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride, res_batch_stride, \
                                          e, max_ctas, s);                                                           \
   } else {                                                                                                          \
     if (b_mn_major)                                                                                                 \
-      return launch_gemm<BN_, false, true>(ta, tb, tc, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                \
+      return launch_gemm<BN_, false, true>(ta, tb, tc, tx, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                \
                                            res_batch_stride, e, max_ctas, s);                                       \
-    return launch_gemm<BN_, false, false>(ta, tb, tc, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                 \
+    return launch_gemm<BN_, false, false>(ta, tb, tc, tx, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k, c_batch_stride, aux_batch_stride,                 \
                                           res_batch_stride, e, max_ctas, s);                                        \
   }
   switch (bn) {
