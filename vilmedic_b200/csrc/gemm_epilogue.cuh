@@ -261,7 +261,7 @@ __device__ __forceinline__ void stg_write_row(uint8_t* stg, int lane, const uint
   }
 }
 
-__device__ __noinline__ void epilogue_span_staged(uint32_t taddr, int row, int row0, int col0, int batch_idx, int lane,
+static __device__ __noinline__ void epilogue_span_staged(uint32_t taddr, int row, int row0, int col0, int batch_idx, int lane,
                                                   const GemmEpilogue& e, float alpha, uint4 pre0, uint4 pre1, uint4 pre2,
                                                   uint4 pre3, bool has_pre, uint8_t* stg, const CUtensorMap* tmap_c,
                                                   const CUtensorMap* tmap_aux) {
