@@ -261,14 +261,18 @@ __device__ __forceinline__ void stg_write_row(uint8_t* stg, int lane, const uint
   }
 }
 
-static __device__ __noinline__ void epilogue_span_staged(uint32_t taddr, int row, int row0, int col0, int batch_idx, int lane,
-                                                  const GemmEpilogue& e, float alpha, uint4 pre0, uint4 pre1, uint4 pre2,
-                                                  uint4 pre3, bool has_pre, uint8_t* stg, const CUtensorMap* tmap_c,
-                                                  const CUtensorMap* tmap_aux) {
+// Epilogue modes the staged fast path is specialised for at compile time (one kernel instantiation each: the generic
+// runtime-flag epilogue needs ~150 live registers, the specialised ones fit the 128-register budget of 14 warps / CTA).
+enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_GELU = 2, EPI_GELUGRAD = 3, EPI_RESID = 4 };
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_span_fast(uint32_t taddr, int row, int row0, int col0, int batch_idx, int lane,
+                                                   const GemmEpilogue& e, float alpha, const uint4 (&pre)[4], uint8_t* stg,
+                                                   const CUtensorMap* tmap_c, const CUtensorMap* tmap_aux) {
   if (lane == 0) bulk_wait_read_all();          // the previous TMA store has drained the staging tile
   __syncwarp();
-  const bool stash = e.act == 1 && e.aux_out != nullptr;
-  uint32_t stashed[16];
+  const bool stash = MODE == EPI_GELU && e.aux_out != nullptr;
+  uint32_t stashed[MODE == EPI_GELU ? 16 : 1];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {                 // two 16-column halves
     uint32_t acc[16];
@@ -288,44 +292,48 @@ static __device__ __noinline__ void epilogue_span_staged(uint32_t taddr, int row
         v[4 * j + 3] += b.w;
       }
     }
-    const uint4 pa = h == 0 ? pre0 : pre2, pb = h == 0 ? pre1 : pre3;
-    const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-    if (e.act == 1) {
+    if constexpr (MODE == EPI_GELU) {
       if (stash) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) stashed[8 * h + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
-    } else if (e.act == 2) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 x = unpack_bf16x2(pw[j]);
-        v[2 * j] *= gelu_erf_grad(x.x);
-        v[2 * j + 1] *= gelu_erf_grad(x.y);
-      }
     }
-    if (e.p_drop > 0.f) {
-      const Philox rng(e.seed);
-      const uint32_t thr = (uint32_t)(e.p_drop * 4294967296.0f);
-      const float inv_keep = 1.f / (1.f - e.p_drop);
-      const unsigned long long base =
-          ((unsigned long long)row * (unsigned long long)e.drop_ld + (unsigned long long)(col0 + 16 * h)) >> 2;
+    if constexpr (MODE == EPI_GELUGRAD || MODE == EPI_RESID) {
+      const uint4 pa = pre[2 * h], pb = pre[2 * h + 1];
+      const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+      if constexpr (MODE == EPI_GELUGRAD) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 r = rng(base + j, e.offset);
-        v[4 * j + 0] = r.x >= thr ? v[4 * j + 0] * inv_keep : 0.f;
-        v[4 * j + 1] = r.y >= thr ? v[4 * j + 1] * inv_keep : 0.f;
-        v[4 * j + 2] = r.z >= thr ? v[4 * j + 2] * inv_keep : 0.f;
-        v[4 * j + 3] = r.w >= thr ? v[4 * j + 3] * inv_keep : 0.f;
-      }
-    }
-    if (e.act != 2 && has_pre) {                // residual add (bf16)
+        for (int j = 0; j < 8; ++j) {
+          const float2 x = unpack_bf16x2(pw[j]);
+          v[2 * j] *= gelu_erf_grad(x.x);
+          v[2 * j + 1] *= gelu_erf_grad(x.y);
+        }
+      } else {
+        if (e.p_drop > 0.f) {
+          const Philox rng(e.seed);
+          const uint32_t thr = (uint32_t)(e.p_drop * 4294967296.0f);
+          const float inv_keep = 1.f / (1.f - e.p_drop);
+          const unsigned long long base =
+              ((unsigned long long)row * (unsigned long long)e.drop_ld + (unsigned long long)(col0 + 16 * h)) >> 2;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 x = unpack_bf16x2(pw[j]);
-        v[2 * j] += x.x;
-        v[2 * j + 1] += x.y;
+          for (int j = 0; j < 4; ++j) {
+            const uint4 r = rng(base + j, e.offset);
+            v[4 * j + 0] = r.x >= thr ? v[4 * j + 0] * inv_keep : 0.f;
+            v[4 * j + 1] = r.y >= thr ? v[4 * j + 1] * inv_keep : 0.f;
+            v[4 * j + 2] = r.z >= thr ? v[4 * j + 2] * inv_keep : 0.f;
+            v[4 * j + 3] = r.w >= thr ? v[4 * j + 3] * inv_keep : 0.f;
+          }
+        }
+        if (e.residual) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 x = unpack_bf16x2(pw[j]);
+            v[2 * j] += x.x;
+            v[2 * j + 1] += x.y;
+          }
+        }
       }
     }
 #pragma unroll
@@ -342,15 +350,17 @@ static __device__ __noinline__ void epilogue_span_staged(uint32_t taddr, int row
     tma_store_3d(tmap_c, stg, col0, row0, batch_idx);
     bulk_commit_group();
   }
-  if (stash) {                                  // second trip through the same tile for the GELU pre-activation
-    if (lane == 0) bulk_wait_read_all();
-    __syncwarp();
-    stg_write_row(stg, lane, stashed);
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_3d(tmap_aux, stg, col0, row0, batch_idx);
-      bulk_commit_group();
+  if constexpr (MODE == EPI_GELU) {
+    if (stash) {                                // second trip through the same tile for the GELU pre-activation
+      if (lane == 0) bulk_wait_read_all();
+      __syncwarp();
+      stg_write_row(stg, lane, stashed);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(tmap_aux, stg, col0, row0, batch_idx);
+        bulk_commit_group();
+      }
     }
   }
 }

@@ -43,7 +43,7 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
 };
 
-template <int BN, bool A_MN, bool B_MN, int PARTS, int GEMM_EPI_W>
+template <int BN, bool A_MN, bool B_MN, int PARTS, int GEMM_EPI_W, int MODE>
 __global__ void __launch_bounds__(gemm_threads(PARTS), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux, int tma_store,
@@ -229,39 +229,46 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (e.aux_out) e.aux_out += (size_t)b * aux_batch_stride;
       }
       const int row = m0 + quad * 32 + lane;
-      // Fast path: bf16 C by TMA store, every span of the tile inside N.  The per-row inputs of this warp's spans (GELU'
-      // argument or residual) are requested now, before waiting for the accumulator: their DRAM latency hides under the
-      // mainloop of this tile.
-      const bool fast = tma_store != 0 && n0 + BN <= N;                  // warp-uniform
-      constexpr int NSP = (SPANS + PARTS - 1) / PARTS;
-      uint4 pre[NSP][4];
-      const bf16* pre_src = e.act == 2 ? e.aux_in : reinterpret_cast<const bf16*>(e.residual);
-      const long long pre_ld = e.act == 2 ? e.ld_aux : e.ldr;
-      const bool has_pre = fast && pre_src != nullptr;
-      if (has_pre && row < M) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      // Fast path (MODE != EPI_GENERIC; host guarantees bf16 C by TMA store): every span of the tile inside N.  The per-row
+      // inputs of this warp's spans (GELU' argument or residual) are requested now, before waiting for the accumulator:
+      // their DRAM latency hides under the mainloop of this tile.
+      bool fast = false;
+      if constexpr (MODE != EPI_GENERIC) fast = n0 + BN <= N;           // warp-uniform
+      if (fast) {
+        if constexpr (MODE != EPI_GENERIC) {
+          constexpr int NSP = (SPANS + PARTS - 1) / PARTS;
+          constexpr bool HAS_PRE = MODE == EPI_GELUGRAD || MODE == EPI_RESID;
+          uint4 pre[HAS_PRE ? NSP : 1][4];
+          if constexpr (HAS_PRE) {
+            const bf16* pre_src = MODE == EPI_GELUGRAD ? e.aux_in : reinterpret_cast<const bf16*>(e.residual);
+            const long long pre_ld = MODE == EPI_GELUGRAD ? e.ld_aux : e.ldr;
+            if (pre_src != nullptr && row < M) {
 #pragma unroll
-        for (int i = 0; i < NSP; ++i) {
-          const int sp = part + i * PARTS;
-          if (sp < SPANS) {
-            const uint4* src = reinterpret_cast<const uint4*>(pre_src + (long long)row * pre_ld + n0 + sp * 32);
+              for (int i = 0; i < NSP; ++i) {
+                const int sp = part + i * PARTS;
+                if (sp < SPANS) {
+                  const uint4* src = reinterpret_cast<const uint4*>(pre_src + (long long)row * pre_ld + n0 + sp * 32);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) pre[i][j] = __ldg(src + j);
+                  for (int j = 0; j < 4; ++j) pre[i][j] = __ldg(src + j);
+                }
+              }
+            }
+          }
+          mbar_wait(&tmem_full_bar[acc], acc_phase);
+          tc_fence_after();
+          const float alpha = e.alpha_ptr ? e.alpha * __ldg(e.alpha_ptr) : e.alpha;
+#pragma unroll
+          for (int i = 0; i < NSP; ++i) {
+            const int sp = part + i * PARTS;
+            if (sp < SPANS)
+              epilogue_span_fast<MODE>(taddr + sp * 32, row, m0 + quad * 32, n0 + sp * 32, b, lane, e, alpha, pre[HAS_PRE ? i : 0],
+                                       stg, &tmap_c, &tmap_aux);
           }
         }
-      }
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      if (fast) {
-        const float alpha = e.alpha_ptr ? e.alpha * __ldg(e.alpha_ptr) : e.alpha;
-#pragma unroll
-        for (int i = 0; i < NSP; ++i) {
-          const int sp = part + i * PARTS;
-          if (sp < SPANS)
-            epilogue_span_staged(taddr + sp * 32, row, m0 + quad * 32, n0 + sp * 32, b, lane, e, alpha, pre[i][0], pre[i][1],
-                                 pre[i][2], pre[i][3], has_pre, stg, &tmap_c, &tmap_aux);
-        }
       } else {
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
         for (int sp = part; sp < SPANS; sp += PARTS) {
           const int col_s = n0 + sp * 32;
@@ -372,13 +379,13 @@ void bind_context_for_driver_calls() {
 
 static constexpr int GEMM_PARTS = 3;   // epilogue warps per TMEM lane quadrant (14 warps per CTA, <= 128 registers each)
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx, int tma_store,
+template <int BN, bool A_MN, bool B_MN, int MODE>
+static int launch_gemm_m(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx, int tma_store,
                        int M, int N, int K,
                        int batch, int a_bmul, int b_bmul, int split_k, long long c_bs, long long aux_bs, long long res_bs,
                        const GemmEpilogue& epi, int max_ctas, cudaStream_t stream) {
   using S = GemmSmem<BN>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN, GEMM_PARTS, 16>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN, GEMM_PARTS, 16, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -395,6 +402,28 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   kern<<<grid, gemm_threads(GEMM_PARTS), S::TOTAL, stream>>>(ta, tb, tc, tx, tma_store, M, N, K, batch, a_bmul, b_bmul, split_k,
                                                              c_bs, aux_bs, res_bs, epi);
   return check_launch("gemm_bf16_tcgen05");
+}
+
+// `tma_store` carries the epilogue mode (EPI_GENERIC = direct stores).  Specialised kernels exist for the operand layouts
+// the modes occur with: forward (both operands K-major): bias / GELU+stash / dropout+residual; dgrad (B MN-major): plain / GELU'.
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx, int mode,
+                       int M, int N, int K, int batch, int a_bmul, int b_bmul, int split_k, long long c_bs, long long aux_bs,
+                       long long res_bs, const GemmEpilogue& epi, int max_ctas, cudaStream_t stream) {
+#define VLM_MODE_CASE(M_) \
+  return launch_gemm_m<BN, A_MN, B_MN, M_>(ta, tb, tc, tx, M_ != EPI_GENERIC, M, N, K, batch, a_bmul, b_bmul, split_k, c_bs, aux_bs, \
+                                           res_bs, epi, max_ctas, stream)
+  if constexpr (!A_MN && !B_MN) {
+    if (mode == EPI_BIAS) VLM_MODE_CASE(EPI_BIAS);
+    if (mode == EPI_GELU) VLM_MODE_CASE(EPI_GELU);
+    if (mode == EPI_RESID) VLM_MODE_CASE(EPI_RESID);
+  }
+  if constexpr (!A_MN && B_MN) {
+    if (mode == EPI_BIAS) VLM_MODE_CASE(EPI_BIAS);
+    if (mode == EPI_GELUGRAD) VLM_MODE_CASE(EPI_GELUGRAD);
+  }
+  VLM_MODE_CASE(EPI_GENERIC);
+#undef VLM_MODE_CASE
 }
 
 static int pick_bn(int M, int N, int batch, int force_bn) {
@@ -573,6 +602,9 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
     if (act == 2 && ((ld_aux % 8) != 0 || (reinterpret_cast<uintptr_t>(aux_in) & 15) != 0)) tma_store = 0;
     if (residual && ((ldr % 8) != 0 || (reinterpret_cast<uintptr_t>(residual) & 15) != 0)) tma_store = 0;
     if (bias && (reinterpret_cast<uintptr_t>(bias) & 15) != 0) tma_store = 0;
+    if (act == 2 && (residual || p_drop > 0.f)) tma_store = 0;          // combinations without a specialised kernel
+    if (act == 1 && (residual || p_drop > 0.f)) tma_store = 0;
+    if (tma_store) tma_store = act == 1 ? EPI_GELU : (act == 2 ? EPI_GELUGRAD : ((residual || p_drop > 0.f) ? EPI_RESID : EPI_BIAS));
   }
   if (bn2 != 0) return gemm2_dispatch(a, lda, a_mn_major, b, ldb, b_mn_major, M, N, K, bn2, e, s);
 
