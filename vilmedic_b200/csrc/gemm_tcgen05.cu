@@ -207,6 +207,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const unsigned long long rng_add = (epi.p_drop > 0.f && epi.offset_ptr) ? __ldg(epi.offset_ptr) : 0ull;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // Row inputs of the fast path (GELU' argument / residual), one 32-column span each.  They are requested one tile ahead:
+    // slot i is refilled for the NEXT tile as soon as span i of the current tile has consumed it, so the DRAM latency hides
+    // under the rest of this tile's epilogue instead of being exposed at the start of the next one.
+    constexpr int NSP = (SPANS + PARTS - 1) / PARTS;
+    constexpr bool HAS_PRE = MODE == EPI_GELUGRAD || MODE == EPI_RESID;
+    uint4 pre[HAS_PRE ? NSP : 1][4];
+    bool have_pre = false;
+    const bf16* const pre_base = MODE == EPI_GELUGRAD ? epi.aux_in : reinterpret_cast<const bf16*>(epi.residual);
+    const long long pre_ld = MODE == EPI_GELUGRAD ? epi.ld_aux : epi.ldr;
+    const long long pre_bs = MODE == EPI_GELUGRAD ? aux_batch_stride : res_batch_stride;
+    auto load_pre = [&](int i, int tb, int tm0, int tn0) {
+      const int sp = part + i * PARTS;
+      const int prow = tm0 + quad * 32 + lane;
+      if (sp < SPANS && prow < M) {
+        const uint4* src = reinterpret_cast<const uint4*>(pre_base + (size_t)tb * pre_bs + (long long)prow * pre_ld + tn0 + sp * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pre[i][j] = __ldg(src + j);
+      }
+    };
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
       const int tile = work % total_tiles, split = work / total_tiles;
       const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
@@ -230,29 +249,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      // Fast path (MODE != EPI_GENERIC; host guarantees bf16 C by TMA store): every span of the tile inside N.  The per-row
-      // inputs of this warp's spans (GELU' argument or residual) are requested now, before waiting for the accumulator:
-      // their DRAM latency hides under the mainloop of this tile.
+      // Fast path (MODE != EPI_GENERIC; host guarantees bf16 C by TMA store, split_k == 1): every span of the tile inside N.
       bool fast = false;
       if constexpr (MODE != EPI_GENERIC) fast = n0 + BN <= N;           // warp-uniform
       if (fast) {
         if constexpr (MODE != EPI_GENERIC) {
-          constexpr int NSP = (SPANS + PARTS - 1) / PARTS;
-          constexpr bool HAS_PRE = MODE == EPI_GELUGRAD || MODE == EPI_RESID;
-          uint4 pre[HAS_PRE ? NSP : 1][4];
+          // the tile this CTA processes next (for the one-tile-ahead input requests)
+          const int nwork = work + gridDim.x;
+          int nb = 0, nm0 = 0, nn0 = 0;
+          bool nfast = false;
+          if (HAS_PRE && pre_base != nullptr && nwork < total_work) {
+            const int ntile = nwork % total_tiles;
+            nb = ntile / tiles_per_batch;
+            const int nt = ntile - nb * tiles_per_batch;
+            nm0 = (nt / n_tiles) * GEMM_BM;
+            nn0 = (nt % n_tiles) * BN;
+            nfast = nn0 + BN <= N;
+          }
           if constexpr (HAS_PRE) {
-            const bf16* pre_src = MODE == EPI_GELUGRAD ? e.aux_in : reinterpret_cast<const bf16*>(e.residual);
-            const long long pre_ld = MODE == EPI_GELUGRAD ? e.ld_aux : e.ldr;
-            if (pre_src != nullptr && row < M) {
+            if (pre_base != nullptr && !have_pre) {                     // first tile of this CTA (or after a ragged tile)
 #pragma unroll
-              for (int i = 0; i < NSP; ++i) {
-                const int sp = part + i * PARTS;
-                if (sp < SPANS) {
-                  const uint4* src = reinterpret_cast<const uint4*>(pre_src + (long long)row * pre_ld + n0 + sp * 32);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) pre[i][j] = __ldg(src + j);
-                }
-              }
+              for (int i = 0; i < NSP; ++i) load_pre(i, b, m0, n0);
             }
           }
           mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -264,9 +281,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             if (sp < SPANS)
               epilogue_span_fast<MODE>(taddr + sp * 32, row, m0 + quad * 32, n0 + sp * 32, b, lane, e, alpha, pre[HAS_PRE ? i : 0],
                                        stg, &tmap_c, &tmap_aux);
+            if constexpr (HAS_PRE) {
+              if (nfast) load_pre(i, nb, nm0, nn0);
+            }
           }
+          have_pre = nfast;
         }
       } else {
+        have_pre = false;
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
