@@ -44,10 +44,13 @@ class _Hyps:
 
 
 @torch.no_grad()
-def ensemble_beam_search(decoders, encs, masks, num_beams, max_length, bos, eos, pad, length_penalty=1.0, gaps=None):
+def ensemble_beam_search(decoders, encs, masks, num_beams, max_length, bos, eos, pad, length_penalty=1.0, gaps=None,
+                         trace=None):
     """Sum-of-logits ensemble beam search (beam_search.py:243-320); greedy when num_beams == 1.
     gaps: optional list that receives, per step, the smallest score gap between adjacent candidates among the top
-    2k+1 (k>1) or top-2 (greedy) — how close the fp32 search came to a tie (tests use it to qualify bit-exactness)."""
+    2k+1 (k>1) or top-2 (greedy) — how close the fp32 search came to a tie (tests use it to qualify bit-exactness).
+    trace: optional list that receives (step, batch row, gap, max |summed logit| of that row's beams) for the same decisions:
+    a bf16 implementation carries a logit error proportional to the logit magnitude, so tests qualify by gap / scale."""
     B, k = encs[0].shape[0], num_beams
     ids = torch.full((B * k, 1), bos, dtype=torch.long)
     encs = [e.repeat_interleave(k, 0) for e in encs]
@@ -71,11 +74,15 @@ def ensemble_beam_search(decoders, encs, masks, num_beams, max_length, bos, eos,
                 if k == 1:
                     top = torch.topk(lp[b], 2).values
                     gaps.append(float(top[0] - top[1]))
+                    if trace is not None:
+                        trace.append((cur, b, float(top[0] - top[1]), float(logits[b].abs().max())))
                 else:
                     ts_, ti_ = torch.topk(lp.view(B, k * V)[b], min(2 * k + 2, k * V))
                     keep = [float(v) for v, i in zip(ts_, ti_) if int(i) % V != eos and float(v) > -1e8]
                     if len(keep) > k:
                         gaps.append(keep[k - 1] - keep[k])
+                        if trace is not None:
+                            trace.append((cur, b, keep[k - 1] - keep[k], float(logits.view(B, k, V)[b].abs().max())))
         if k == 1:
             s, t = lp.max(-1)
             t = torch.where(torch.tensor(done), torch.full_like(t, pad), t)

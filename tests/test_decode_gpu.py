@@ -3,8 +3,9 @@
 The oracle computes in fp32, the product in bf16, so a search decision closer than the bf16 logit error could
 legitimately flip.  Following SURVEY.md §7 ("hard parts"): (i) weights are scaled so that decisions have non-trivial
 margins and are rounded to bf16 on BOTH sides (identical parameters); (ii) the oracle reports the smallest decision margin
-of its own search (top-1 vs top-2 for greedy; k-th kept vs first dropped candidate for beam) and the comparison is
-bit-exact whenever that margin exceeds 0.2 — which the chosen seeds satisfy, so a mismatch is a real failure.
+of its own search (top-1 vs top-2 for greedy; k-th kept vs first dropped candidate for beam) together with the logit
+magnitude, and the comparison is bit-exact over every decision whose margin exceeds 2^-5 x max|logit| (the bf16 logit
+error scales with the logit magnitude) — a mismatch on such a decision is a real failure.
 The selection logic itself is verified bit-exactly on identical logits in tests/test_cpu.py."""
 import copy
 
@@ -56,51 +57,78 @@ class _MineAsOracleModel:
         return o
 
 
+# A bf16 forward carries a logit error proportional to the logit magnitude (a few bf16 ulps = 2^-8 relative each through two
+# decoder layers and the LM head); a search decision is "safe" when the oracle's margin exceeds REL_MARGIN x max|logit|.
+REL_MARGIN = 2.0 ** -5
+
+
+def _first_unsafe_step(trace, row, max_length):
+    steps = [st for (st, b, gap, scale) in trace if b == row and gap <= REL_MARGIN * scale]
+    return min(steps) if steps else max_length
+
+
 def test_greedy_token_ids_bit_exact_vs_fp32_oracle(cuda_dev):
+    """Greedy ids == fp32 oracle (== HF generate) on every row up to the first step whose oracle margin is within the bf16
+    logit error; the seeds keep at least 6 safe steps per row."""
     from oracle import decode
     from vilmedic_b200 import synth
     ref, mine = _pair(0)
     batch = synth.rrg_batch(3, 8, 300, seed=9)
     enc_r, mask_r = ref.enc.encode(batch["images"])
-    gaps = []
-    want = decode.ensemble_beam_search([ref.dec.decoder], [enc_r], [mask_r], 1, 12, BOS, EOS, PAD, gaps=gaps)
+    gaps, trace = [], []
+    want = decode.ensemble_beam_search([ref.dec.decoder], [enc_r], [mask_r], 1, 12, BOS, EOS, PAD, gaps=gaps, trace=trace)
     hf = decode.hf_generate(ref.dec.decoder, enc_r, mask_r, 1, 12, BOS, EOS, PAD)
     assert torch.equal(want[:, :hf.shape[1]], hf[:, :want.shape[1]]), "oracle restatement disagrees with HF generate"
     enc, mask = mine.encode(batch["images"])
     got = mine.dec.decoder.generate(input_ids=torch.full((3, 1), BOS, dtype=torch.long, device="cuda"), encoder_hidden_states=enc,
                                     encoder_attention_mask=mask, max_length=12, num_beams=1, bos_token_id=BOS, eos_token_id=EOS,
                                     pad_token_id=PAD).cpu()
-    assert min(gaps) > 0.3, "test inputs lost their argmax margin (%.3f); pick another seed" % min(gaps)
-    assert got.shape == want.shape and torch.equal(got, want), (min(gaps), got.tolist(), want.tolist())
+    assert got.shape == want.shape
+    compared = 0
+    for row in range(3):
+        safe = _first_unsafe_step(trace, row, 12)          # tokens at positions < safe come from safe decisions
+        assert safe >= 6, "test inputs lost their argmax margin on row %d (first unsafe step %d); pick another seed" % (row, safe)
+        assert torch.equal(got[row, :safe], want[row, :safe]), (row, safe, got[row].tolist(), want[row].tolist())
+        compared += safe
+    assert compared >= 24
 
 
 @pytest.mark.parametrize("k,n_models", [(4, 1), (4, 2)])
 def test_beam_ensemble_token_ids(cuda_dev, k, n_models):
     """KV-cached beam / ensemble search == the oracle's search loop run over the product's own (uncached) logits, bit for
-    bit; and == the fp32 oracle end to end whenever the oracle's decision margin is far above the bf16 logit error."""
+    bit (on the first seed whose decisions are all safe w.r.t. cached-vs-uncached bf16 noise); and == the fp32 oracle end to
+    end whenever the oracle's own decisions are all safe."""
     from oracle import decode
     from vilmedic_b200 import synth
     pairs = [_pair(s) for s in range(n_models)]
-    batch = synth.rrg_batch(2, 8, 300, seed=35)
-    encs, masks = zip(*[m.encode(batch["images"]) for _, m in pairs])
     hf_models = [m.dec.decoder for _, m in pairs]
-    got = hf_models[0].generate(input_ids=torch.full((2, 1), BOS, dtype=torch.long, device="cuda"), encoder_hidden_states=list(encs),
-                                encoder_attention_mask=list(masks), ensemble=hf_models, max_length=8, num_beams=k,
-                                bos_token_id=BOS, eos_token_id=EOS, pad_token_id=PAD).cpu()
-    adapters = [_MineAsOracleModel(m.dec.decoder, e, mk) for (_, m), e, mk in zip(pairs, encs, masks)]
-    gaps_mine = []
-    want_mine = decode.ensemble_beam_search(adapters, [e.cpu() for e in encs], [mk.cpu() for mk in masks], k, 8, BOS, EOS, PAD,
-                                            gaps=gaps_mine)
-    assert min(gaps_mine) > 0.05, "decision margin of the device logits too small to compare cached vs uncached (%.3f)" % min(gaps_mine)
-    assert got.shape == want_mine.shape and torch.equal(got, want_mine), (got.tolist(), want_mine.tolist())
-    encs_r, masks_r = zip(*[r.enc.encode(batch["images"]) for r, _ in pairs])
-    gaps = []
-    want = decode.ensemble_beam_search([r.dec.decoder for r, _ in pairs], list(encs_r), list(masks_r), k, 8, BOS, EOS, PAD, gaps=gaps)
-    if min(gaps) > 1.0:
-        assert torch.equal(got, want), (min(gaps), got.tolist(), want.tolist())
-    else:
-        agree = (got[:, :min(got.shape[1], want.shape[1])] == want[:, :min(got.shape[1], want.shape[1])]).float().mean().item()
-        print("fp32-oracle beam margin %.3f (< 1.0): token agreement %.2f (informational)" % (min(gaps), agree))
+    checked = False
+    for seed in (35, 36, 37, 38, 39, 40):
+        batch = synth.rrg_batch(2, 8, 300, seed=seed)
+        encs, masks = zip(*[m.encode(batch["images"]) for _, m in pairs])
+        adapters = [_MineAsOracleModel(m.dec.decoder, e, mk) for (_, m), e, mk in zip(pairs, encs, masks)]
+        trace_mine = []
+        want_mine = decode.ensemble_beam_search(adapters, [e.cpu() for e in encs], [mk.cpu() for mk in masks], k, 8, BOS, EOS, PAD,
+                                                gaps=[], trace=trace_mine)
+        if any(gap <= REL_MARGIN * scale for (_, _, gap, scale) in trace_mine):
+            continue                                        # a near-tie of the device logits: cached vs uncached may flip it
+        got = hf_models[0].generate(input_ids=torch.full((2, 1), BOS, dtype=torch.long, device="cuda"),
+                                    encoder_hidden_states=list(encs), encoder_attention_mask=list(masks), ensemble=hf_models,
+                                    max_length=8, num_beams=k, bos_token_id=BOS, eos_token_id=EOS, pad_token_id=PAD).cpu()
+        assert got.shape == want_mine.shape and torch.equal(got, want_mine), (seed, got.tolist(), want_mine.tolist())
+        encs_r, masks_r = zip(*[r.enc.encode(batch["images"]) for r, _ in pairs])
+        trace = []
+        want = decode.ensemble_beam_search([r.dec.decoder for r, _ in pairs], list(encs_r), list(masks_r), k, 8, BOS, EOS, PAD,
+                                           gaps=[], trace=trace)
+        if all(gap > 4 * REL_MARGIN * scale for (_, _, gap, scale) in trace):
+            assert torch.equal(got, want), (seed, got.tolist(), want.tolist())
+        else:
+            n = min(got.shape[1], want.shape[1])
+            agree = (got[:, :n] == want[:, :n]).float().mean().item()
+            print("fp32-oracle beam search has a near-tie on seed %d: token agreement %.2f (informational)" % (seed, agree))
+        checked = True
+        break
+    assert checked, "no seed in 35..40 gave a batch whose beam decisions are all clear of bf16 noise"
 
 
 def test_cached_step_matches_prefix_recompute(cuda_dev):

@@ -218,7 +218,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const long long pre_ld = MODE == EPI_GELUGRAD ? epi.ld_aux : epi.ldr;
     const long long pre_bs = MODE == EPI_GELUGRAD ? aux_batch_stride : res_batch_stride;
     auto load_pre = [&](int i, int tb, int tm0, int tn0) {
-      const int sp = part + i * PARTS;
+      const int sp = part * NSP + i;       // adjacent spans: a lane's row inputs form whole 128-byte lines
       const int prow = tm0 + quad * 32 + lane;
       if (sp < SPANS && prow < M) {
         const uint4* src = reinterpret_cast<const uint4*>(pre_base + (size_t)tb * pre_bs + (long long)prow * pre_ld + tn0 + sp * 32);
@@ -277,7 +277,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const float alpha = e.alpha_ptr ? e.alpha * __ldg(e.alpha_ptr) : e.alpha;
 #pragma unroll
           for (int i = 0; i < NSP; ++i) {
-            const int sp = part + i * PARTS;
+            const int sp = part * NSP + i;       // adjacent spans: a lane's row inputs form whole 128-byte lines
             if (sp < SPANS)
               epilogue_span_fast<MODE>(taddr + sp * 32, row, m0 + quad * 32, n0 + sp * 32, b, lane, e, alpha, pre[HAS_PRE ? i : 0],
                                        stg, &tmap_c, &tmap_aux);
