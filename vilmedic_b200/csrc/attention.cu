@@ -725,7 +725,7 @@ extern "C" int vlm_attention_fwd_tc(const void* q, long long q_bs, long long q_r
   const int r = attention_fwd_tc_dispatch(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, kmask, B, H, Tq, Sk, DH,
                                           causal, scale, p_drop, seed, offset, rng_offset_ptr, (cudaStream_t)stream);
   if (r == 0) {
-    set_error("vlm_attention_fwd_tc: shape outside the tcgen05 envelope (DH=64, Sk<=256)");
+    set_error("vlm_attention_fwd_tc: shape outside the tcgen05 envelope (DH=64, Sk<=224)");
     return -1;
   }
   return r < 0 ? r : 0;

@@ -240,6 +240,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
     const float inv_keep = DROPOUT ? 1.f / (1.f - p.p_drop) : 1.f;
     const int half_cols = Nq >> 1;             // multiple of 16
+    const uint32_t pt_row = (uint32_t)(r * 128);   // row offset inside a 64-column atom of the P^T / dS^T tile
+    const int r7 = r & 7;
     uint32_t tile_cnt = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int b = item / p.H, h = item % p.H;
@@ -263,26 +265,48 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         // ---------------- pass A: P^T
         mbar_wait(s_full, tph);
         tc_fence_after();
+        // causal: query q sees key kk iff kk <= q.  For this warp's key rows [k_lo, k_lo + 31] a 16-query chunk starting at
+        // q0 is fully visible iff q0 >= k_lo + 31 and fully masked iff q0 + 15 < k_lo; only the chunks on the diagonal test
+        // per element.  Key rows that are padding / masked (kvalid == false) produce zeros without any math.
+        const int k_lo = j * 128 + quad * 32;
         auto pass_a_chunk = [&](const uint32_t* v, int q0) {
           float pv[16], pd[16];
+          if (kvalid && !(p.causal && q0 + 15 < k_lo)) {
+            float ls[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int q = q0 + i;
-            const bool ok = kvalid && (!p.causal || kk <= q);
-            pv[i] = ok ? exp2f(__uint_as_float(v[i]) * sl2 - sLse[q]) : 0.f;
-            if (DROPOUT) pd[i] = attn_drop_rand(dkey, q, kk, p.Sk) >= thr ? pv[i] * inv_keep : 0.f;
+            for (int i = 0; i < 4; ++i) {
+              const float4 t = *reinterpret_cast<const float4*>(sLse + q0 + 4 * i);
+              ls[4 * i] = t.x; ls[4 * i + 1] = t.y; ls[4 * i + 2] = t.z; ls[4 * i + 3] = t.w;
+            }
+            if (!p.causal || q0 >= k_lo + 31) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -ls[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pv[i] = (kk <= q0 + i) ? ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -ls[i])) : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pv[i] = 0.f;
           }
+          if (DROPOUT) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pd[i] = attn_drop_rand(dkey, q0 + i, kk, p.Sk) >= thr ? pv[i] * inv_keep : 0.f;
+          }
+          const uint32_t off0 = (uint32_t)((q0 >> 6) * 16384) + pt_row;
+          const int u0 = (q0 & 63) >> 3;
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
+            const uint32_t off = off0 + (uint32_t)(((u0 + u) ^ r7) << 4);
             uint4 w;
             if (DROPOUT) {
               w.x = pack_bf16x2(pd[8 * u + 0], pd[8 * u + 1]); w.y = pack_bf16x2(pd[8 * u + 2], pd[8 * u + 3]);
               w.z = pack_bf16x2(pd[8 * u + 4], pd[8 * u + 5]); w.w = pack_bf16x2(pd[8 * u + 6], pd[8 * u + 7]);
-              *reinterpret_cast<uint4*>(sPT + pt_offset16(r, q0 + 8 * u)) = w;
+              *reinterpret_cast<uint4*>(sPT + off) = w;
             }
             w.x = pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]); w.y = pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]);
             w.z = pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]); w.w = pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]);
-            *reinterpret_cast<uint4*>((DROPOUT ? sP2 : sPT) + pt_offset16(r, q0 + 8 * u)) = w;
+            *reinterpret_cast<uint4*>((DROPOUT ? sP2 : sPT) + off) = w;
           }
         };
         {  // TMEM loads are software-pipelined: the next chunk is in flight while the current one is processed
@@ -308,10 +332,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mbar_wait(dp_full, tph);
         mbar_wait(dv_done, tph);
         tc_fence_after();
+        // dS^T = P^T * (dP^T - delta) — the softmax scale is applied once per dK / dQ output element in the epilogue instead
+        // of once per score element here.
         auto pass_b_chunk = [&](const uint32_t* v, int q0) {
+          float dl[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 t = *reinterpret_cast<const float4*>(sDelta + q0 + 4 * i);
+            dl[4 * i] = t.x; dl[4 * i + 1] = t.y; dl[4 * i + 2] = t.z; dl[4 * i + 3] = t.w;
+          }
+          const uint32_t off0 = (uint32_t)((q0 >> 6) * 16384) + pt_row;
+          const int u0 = (q0 & 63) >> 3;
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const uint32_t off = pt_offset16(r, q0 + 8 * u);
+            const uint32_t off = off0 + (uint32_t)(((u0 + u) ^ r7) << 4);
             const uint4 pw = *reinterpret_cast<const uint4*>((DROPOUT ? sP2 : sPT) + off);
             uint4 kw = pw;
             if (DROPOUT) kw = *reinterpret_cast<const uint4*>(sPT + off);   // dropped P: zero <=> dropped (or P == 0)
@@ -320,13 +354,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 pp = unpack_bf16x2(pw4[e]), kp = unpack_bf16x2(kw4[e]);
-              const int q = q0 + 8 * u + 2 * e;
               float d0 = __uint_as_float(v[8 * u + 2 * e]), d1 = __uint_as_float(v[8 * u + 2 * e + 1]);
               if (DROPOUT) {
                 d0 = kp.x != 0.f ? d0 * inv_keep : 0.f;
                 d1 = kp.y != 0.f ? d1 * inv_keep : 0.f;
               }
-              ow[e] = pack_bf16x2(pp.x * (d0 - sDelta[q]) * p.scale, pp.y * (d1 - sDelta[q + 1]) * p.scale);
+              ow[e] = pack_bf16x2(pp.x * (d0 - dl[8 * u + 2 * e]), pp.y * (d1 - dl[8 * u + 2 * e + 1]));
             }
             *reinterpret_cast<uint4*>(sPT + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
           }
@@ -366,16 +399,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                                   pack_bf16x2(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])),
                                   pack_bf16x2(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7])));
           }
+          const float sc = p.scale;          // dS was left unscaled (pass B)
           tmem_ld32(lane_taddr + ATC_DK_COL + half * 32, acc);
           tmem_ld_wait();
           if (kk < p.Sk) {
             uint4* dst = reinterpret_cast<uint4*>(p.dk + (long long)b * p.dk_bs + (long long)kk * p.dk_rs + h * 64 + half * 32);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]), __uint_as_float(acc[8 * i + 1])),
-                                  pack_bf16x2(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3])),
-                                  pack_bf16x2(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])),
-                                  pack_bf16x2(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7])));
+              dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]) * sc, __uint_as_float(acc[8 * i + 1]) * sc),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 2]) * sc, __uint_as_float(acc[8 * i + 3]) * sc),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 4]) * sc, __uint_as_float(acc[8 * i + 5]) * sc),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 6]) * sc, __uint_as_float(acc[8 * i + 7]) * sc));
           }
           if (j == ntiles - 1) {
             const int q_blocks = (Nq + 127) / 128;
@@ -387,10 +421,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 uint4* dst = reinterpret_cast<uint4*>(p.dq + (long long)b * p.dq_bs + (long long)q * p.dq_rs + h * 64 + half * 32);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]), __uint_as_float(acc[8 * i + 1])),
-                                      pack_bf16x2(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3])),
-                                      pack_bf16x2(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])),
-                                      pack_bf16x2(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7])));
+                  dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]) * sc, __uint_as_float(acc[8 * i + 1]) * sc),
+                                      pack_bf16x2(__uint_as_float(acc[8 * i + 2]) * sc, __uint_as_float(acc[8 * i + 3]) * sc),
+                                      pack_bf16x2(__uint_as_float(acc[8 * i + 4]) * sc, __uint_as_float(acc[8 * i + 5]) * sc),
+                                      pack_bf16x2(__uint_as_float(acc[8 * i + 6]) * sc, __uint_as_float(acc[8 * i + 7]) * sc));
               }
             }
           }
@@ -501,7 +535,7 @@ int attention_bwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
 }
 
 // =====================================================================================================================
-// tcgen05 attention FORWARD (head dim 64, Sk <= 256 — single key block, so no online-softmax rescaling is needed).
+// tcgen05 attention FORWARD (head dim 64, Sk <= 224 — single key block, so no online-softmax rescaling is needed).
 // Item = (batch, head): K / V are staged once, then every 128-query tile runs  S = Q K^T  (N = Sk padded to 16) ->
 // row softmax by the 256 compute threads (thread <-> query row, two warps per TMEM lane quadrant split the key
 // columns; row max / row sum are combined through shared memory) -> P (bf16, dropout applied) written in the K-major
@@ -519,61 +553,73 @@ struct AttnTcFwdParams {
   const unsigned long long* offset_ptr;
 };
 
+// Shared memory (dynamic, sized by Nk = keys rounded up to 32): two Q tiles, two K and two V buffers (item parity), one P tile.
 struct AtcFwdSmem {
   static constexpr int Q_BYTES = 128 * 128;      // one 128-query tile
-  static constexpr int KV_BYTES = 256 * 128;     // up to 256 keys
-  static constexpr int P_BYTES = 4 * 16384;      // 128 x 256 bf16
-  static constexpr int OFF_Q = 0;                // 2 buffers
-  static constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;
-  static constexpr int OFF_V = OFF_K + KV_BYTES;
-  static constexpr int OFF_P = OFF_V + KV_BYTES;
-  static constexpr int OFF_RED = OFF_P + P_BYTES;          // float [2][2][128]: partial row max / row sum per column half
-  static constexpr int OFF_KOK = OFF_RED + 2 * 2 * 128 * 4;  // uint8 [256] key validity
-  static constexpr int OFF_BAR = OFF_KOK + 256;
-  static constexpr int NUM_BARS = 10;
-  static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
+  static constexpr int NUM_BARS = 13;
+  __host__ __device__ static int kv_bytes(int Nk) { return Nk * 128; }
+  __host__ __device__ static int p_bytes(int Nk) { return ((Nk + 63) / 64) * 16384; }
+  __host__ __device__ static int off_k(int) { return 2 * Q_BYTES; }
+  __host__ __device__ static int off_v(int Nk) { return off_k(Nk) + 2 * kv_bytes(Nk); }
+  __host__ __device__ static int off_p(int Nk) { return off_v(Nk) + 2 * kv_bytes(Nk); }
+  __host__ __device__ static int off_red(int Nk) { return off_p(Nk) + p_bytes(Nk); }   // float [2][2][128]
+  __host__ __device__ static int off_kok(int Nk) { return off_red(Nk) + 2 * 2 * 128 * 4; }   // uint8 [256]
+  __host__ __device__ static int off_bal(int Nk) { return off_kok(Nk) + 256; }             // uint32 [8]
+  __host__ __device__ static int off_bar(int Nk) { return off_bal(Nk) + 32; }
+  __host__ __device__ static int total(int Nk) { return off_bar(Nk) + NUM_BARS * 8 + 16 + 1024; }
 };
 
+// Pipeline (per CTA, tiles t = 0, 1, ... over its (item, 128-query tile) sequence):
+//   TMA warp   : K/V of item n -> buffer n&1 (freed by the last P V of item n-2), Q of tile t -> buffer t&1 (freed by S(t-2)).
+//   MMA warp   : S(0), S(1); then for every t: wait P(t) -> O = P V (TMEM cols [2 Nk, 2 Nk + 64)) -> S(t+2) into the S buffer
+//                t&1 that the softmax of tile t has just drained.  So S(t+1) is always complete when the softmax warps get to it.
+//   softmax    : pass 1 (row max) of tile t, then the EPILOGUE OF TILE t-1 (its P V ran under pass 1), then pass 2 (P -> smem).
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, AttnTcFwdParams p) {
   using S = AtcFwdSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem + S::OFF_Q;
-  uint8_t* sK = smem + S::OFF_K;
-  uint8_t* sV = smem + S::OFF_V;
-  uint8_t* sP = smem + S::OFF_P;
-  float* sRed = reinterpret_cast<float*>(smem + S::OFF_RED);
-  uint8_t* sKok = smem + S::OFF_KOK;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
-  uint64_t* kv_full = bars + 0;
-  uint64_t* kv_empty = bars + 1;
-  uint64_t* q_full = bars + 2;     // [2]
-  uint64_t* q_empty = bars + 4;    // [2]
-  uint64_t* s_full = bars + 6;
-  uint64_t* p_ready = bars + 7;
-  uint64_t* o_full = bars + 8;
-  uint64_t* o_free = bars + 9;
+  const int Nk = p.Nk;
+  const int KVB = S::kv_bytes(Nk);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + S::off_k(Nk);
+  uint8_t* sV = smem + S::off_v(Nk);
+  uint8_t* sP = smem + S::off_p(Nk);
+  float* sRed = reinterpret_cast<float*>(smem + S::off_red(Nk));
+  uint8_t* sKok = smem + S::off_kok(Nk);
+  uint32_t* sBal = reinterpret_cast<uint32_t*>(smem + S::off_bal(Nk));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::off_bar(Nk));
+  uint64_t* kv_full = bars + 0;    // [2]
+  uint64_t* kv_empty = bars + 2;   // [2]
+  uint64_t* q_full = bars + 4;     // [2]
+  uint64_t* q_empty = bars + 6;    // [2]
+  uint64_t* s_full = bars + 8;     // [2]
+  uint64_t* p_ready = bars + 10;
+  uint64_t* o_full = bars + 11;
+  uint64_t* o_free = bars + 12;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + S::NUM_BARS);
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nitems = p.B * p.H;
   const int qtiles = (p.Tq + 127) / 128;
-  const int Nk = p.Nk;
-  constexpr int O_COL = 256;
+  const int my_items = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int ntot = my_items * qtiles;             // tiles this CTA processes
+  const int SB = Nk;                              // TMEM column stride between the two S buffers (Nk <= 224)
+  const int O_COL = 2 * Nk;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
-    mbar_init(kv_full, 1);
-    mbar_init(kv_empty, 1);
-    mbar_init(&q_full[0], 1);
-    mbar_init(&q_full[1], 1);
-    mbar_init(&q_empty[0], 1);
-    mbar_init(&q_empty[1], 1);
-    mbar_init(s_full, 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
     mbar_init(p_ready, 8);
     mbar_init(o_full, 1);
     mbar_init(o_free, 8);
@@ -588,59 +634,64 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
   if (warp_idx == 0) {
     if (lane == 0) {
-      uint32_t item_cnt = 0, tile_cnt = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++item_cnt) {
+      int t = 0, it = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
         const int b = item / p.H, h = item % p.H;
-        mbar_wait(kv_empty, (item_cnt & 1u) ^ 1u);
-        mbar_expect_tx(kv_full, 2u * (uint32_t)Nk * 128u);
-        tma_load_4d(&tm_k, kv_full, sK, 0, h, 0, b);
-        tma_load_4d(&tm_v, kv_full, sV, 0, h, 0, b);
-        for (int i = 0; i < qtiles; ++i, ++tile_cnt) {
-          const int buf = tile_cnt & 1u;
-          mbar_wait(&q_empty[buf], ((tile_cnt >> 1) & 1u) ^ 1u);
-          mbar_expect_tx(&q_full[buf], S::Q_BYTES);
-          tma_load_4d(&tm_q, &q_full[buf], sQ + buf * S::Q_BYTES, 0, h, i * 128, b);
+        const int kvb = it & 1;
+        mbar_wait(&kv_empty[kvb], ((it >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&kv_full[kvb], 2u * (uint32_t)KVB);
+        tma_load_4d(&tm_k, &kv_full[kvb], sK + kvb * KVB, 0, h, 0, b);
+        tma_load_4d(&tm_v, &kv_full[kvb], sV + kvb * KVB, 0, h, 0, b);
+        for (int i = 0; i < qtiles; ++i, ++t) {
+          const int qb = t & 1;
+          mbar_wait(&q_empty[qb], ((t >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&q_full[qb], S::Q_BYTES);
+          tma_load_4d(&tm_q, &q_full[qb], sQ + qb * S::Q_BYTES, 0, h, i * 128, b);
         }
       }
     }
   } else if (warp_idx == 1) {
-    {   // whole warp runs the loop, one elected lane issues (see the backward kernel)
-      const bool leader = elect_one();
-      const uint32_t id_s = make_idesc_bf16(128, Nk, false, false);
-      const uint32_t id_o = make_idesc_bf16(128, 64, false, true);
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
-      const int nk16 = Nk / 16;
-      uint32_t item_cnt = 0, tile_cnt = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++item_cnt) {
-        mbar_wait(kv_full, item_cnt & 1u);
-        tc_fence_after();
-        for (int i = 0; i < qtiles; ++i, ++tile_cnt) {
-          const int buf = tile_cnt & 1u;
-          const uint32_t tph = tile_cnt & 1u;
-          const uint32_t aQ = smem_u32(sQ + buf * S::Q_BYTES);
-          mbar_wait(&q_full[buf], (tile_cnt >> 1) & 1u);
-          tc_fence_after();
-          if (leader) {
+    // whole warp runs the loop (uniform datapath for descriptors / barriers), one elected lane issues the tcgen05 ops
+    const bool leader = elect_one();
+    const uint32_t id_s = make_idesc_bf16(128, Nk, false, false);
+    const uint32_t id_o = make_idesc_bf16(128, 64, false, true);
+    const uint32_t aP = smem_u32(sP);
+    const int nk16 = Nk / 16;
+    auto issue_s = [&](int t) {
+      const int it = t / qtiles;
+      const int kvb = it & 1, qb = t & 1;
+      mbar_wait(&kv_full[kvb], (it >> 1) & 1u);
+      mbar_wait(&q_full[qb], (t >> 1) & 1u);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t aQ = smem_u32(sQ + qb * S::Q_BYTES), aK = smem_u32(sK + kvb * KVB);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), id_s, k > 0);
-            umma_commit(s_full);
-            umma_commit(&q_empty[buf]);
-          }
-          __syncwarp();
-          mbar_wait(p_ready, tph);
-          mbar_wait(o_free, tph ^ 1u);
-          tc_fence_after();
-          if (leader) {
-            for (int k = 0; k < nk16; ++k)
-              umma_bf16(tmem_base + O_COL, make_smem_desc(aP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                        make_smem_desc(aV + k * 2048, 16384, 1024), id_o, k > 0);
-            umma_commit(o_full);
-            if (i == qtiles - 1) umma_commit(kv_empty);
-          }
-          __syncwarp();
-        }
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + (uint32_t)(qb * SB), make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024),
+                    id_s, k > 0);
+        umma_commit(&s_full[qb]);
+        umma_commit(&q_empty[qb]);
       }
+      __syncwarp();
+    };
+    if (ntot > 0) issue_s(0);
+    if (ntot > 1) issue_s(1);
+    for (int t = 0; t < ntot; ++t) {
+      const int it = t / qtiles, i = t - it * qtiles;
+      const int kvb = it & 1;
+      mbar_wait(p_ready, t & 1u);
+      mbar_wait(o_free, (t & 1u) ^ 1u);          // epilogue of tile t-1 has drained the O accumulator
+      tc_fence_after();
+      if (leader) {
+        const uint32_t aV = smem_u32(sV + kvb * KVB);
+        for (int k = 0; k < nk16; ++k)
+          umma_bf16(tmem_base + (uint32_t)O_COL, make_smem_desc(aP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    make_smem_desc(aV + k * 2048, 16384, 1024), id_o, k > 0);
+        umma_commit(o_full);
+        if (i == qtiles - 1) umma_commit(&kv_empty[kvb]);
+      }
+      __syncwarp();
+      if (t + 2 < ntot) issue_s(t + 2);
     }
   } else {
     const int quad = warp_idx & 3;
@@ -648,68 +699,171 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int r = quad * 32 + lane;              // query row inside the tile
     const int ct = threadIdx.x - 64;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const float sl2 = p.scale * 1.4426950408889634f;
+    const float sl2 = p.scale * 1.4426950408889634f;   // > 0 (host checks): max and scaling commute
     const unsigned long long off_eff = p.offset + ((p.p_drop > 0.f && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
     const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     const int half_cols = Nk >> 1;               // multiple of 16
+    const int c0 = half * half_cols;             // first key column of this thread's half
+    const int nchunks = half_cols >> 4;
+    const uint32_t p_row = (uint32_t)(r * 128);  // row offset inside a 64-column atom of the P tile
+    const int r7 = r & 7;
     float* redmax = sRed;                        // [2][128]
     float* redsum = sRed + 256;                  // [2][128]
-    uint32_t tile_cnt = 0;
+    // deferred epilogue state (tile t-1)
+    float l_prev = 0.f, mref_prev = 0.f;
+    long long o_off_prev = 0, lse_off_prev = 0;
+    bool row_prev = false;
+    auto epilogue_prev = [&](int tprev) {
+      mbar_wait(o_full, tprev & 1u);
+      tc_fence_after();
+      uint32_t acc[32];
+      tmem_ld32(lane_taddr + (uint32_t)O_COL + half * 32, acc);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);        // accumulator is in registers: the next P V may start
+      if (row_prev) {
+        const float l = l_prev;
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        uint4* dst = reinterpret_cast<uint4*>(p.o + o_off_prev + half * 32);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          dst[e] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * e]) * inv, __uint_as_float(acc[8 * e + 1]) * inv),
+                              pack_bf16x2(__uint_as_float(acc[8 * e + 2]) * inv, __uint_as_float(acc[8 * e + 3]) * inv),
+                              pack_bf16x2(__uint_as_float(acc[8 * e + 4]) * inv, __uint_as_float(acc[8 * e + 5]) * inv),
+                              pack_bf16x2(__uint_as_float(acc[8 * e + 6]) * inv, __uint_as_float(acc[8 * e + 7]) * inv));
+        if (half == 0 && p.lse) p.lse[lse_off_prev] = l > 0.f ? (mref_prev + log2f(l)) * 0.6931471805599453f : -INFINITY;
+      }
+    };
+    int t = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int b = item / p.H, h = item % p.H;
       const uint32_t dkey = attn_drop_key(p.seed, off_eff, item);
+      // ---- per-item key validity.  The usual masks (no mask, right padding) make the valid keys a PREFIX [0, nvalid): then a
+      // 16-key chunk is either fully valid for the whole warp (no per-element predicate at all), fully masked (skipped) or
+      // one of the few mixed ones (causal diagonal / last partial chunk).  Arbitrary masks keep the per-element test.
       named_bar_sync(1, 256);
-      if (ct < Nk) sKok[ct] = (ct < p.Sk) && (!p.kmask || p.kmask[(long long)b * p.Sk + ct]);
+      {
+        const bool ok = (ct < p.Sk) && (!p.kmask || p.kmask[(long long)b * p.Sk + ct]);
+        sKok[ct] = ok;
+        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) sBal[ct >> 5] = bal;
+      }
       named_bar_sync(1, 256);
-      for (int i = 0; i < qtiles; ++i, ++tile_cnt) {
-        const uint32_t tph = tile_cnt & 1u;
-        const int qq = i * 128 + r;
-        mbar_wait(s_full, tph);
-        tc_fence_after();
-        // ---- pass 1: masked row max over this thread's half of the key columns
-        float mx = -INFINITY;
-        for (int c = 0; c < half_cols; c += 16) {
-          const int k0 = half * half_cols + c;
-          uint32_t v[16];
-          tmem_ld16(lane_taddr + k0, v);
-          tmem_ld_wait();
+      int nvalid = 0;
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int kk = k0 + e;
-            const bool ok = sKok[kk] && (!p.causal || kk <= qq);
-            mx = fmaxf(mx, ok ? __uint_as_float(v[e]) * sl2 : -INFINITY);
+      for (int w = 0; w < 8; ++w) nvalid += __popc(sBal[w]);
+      bool prefix = true;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const int lo = nvalid - 32 * w;
+        const uint32_t expect = lo >= 32 ? 0xffffffffu : (lo <= 0 ? 0u : ((1u << lo) - 1u));
+        prefix = prefix && (sBal[w] == expect);
+      }
+      for (int i = 0; i < qtiles; ++i, ++t) {
+        const int sb = t & 1;
+        const uint32_t s_taddr = lane_taddr + (uint32_t)(sb * SB + c0);
+        const int qq = i * 128 + r;
+        // key k is visible to this row iff k < kmax_row (prefix masks); every lane of the warp sees all keys < kfull and no
+        // key >= kany.  Generic masks: kfull = 0, kany = Nk, visibility from sKok.
+        int kmax_row = 0, kfull = 0, kany = Nk;
+        if (prefix) {
+          const int q_lo = i * 128 + quad * 32;
+          kmax_row = p.causal ? min(nvalid, qq + 1) : nvalid;
+          kfull = p.causal ? min(nvalid, q_lo + 1) : nvalid;
+          kany = p.causal ? min(nvalid, q_lo + 32) : nvalid;
+        }
+        auto visible = [&](int kk) -> bool {
+          return prefix ? (kk < kmax_row) : (sKok[kk] && (!p.causal || kk <= qq));
+        };
+        int nact = (kany - c0 + 15) >> 4;        // chunks of this half that hold at least one visible key (warp-uniform)
+        nact = nact < 0 ? 0 : (nact > nchunks ? nchunks : nact);
+        mbar_wait(&s_full[sb], (t >> 1) & 1u);
+        tc_fence_after();
+        // ---- pass 1: row max (raw scores) over this thread's half of the key columns; TMEM loads are software-pipelined
+        float mx = -INFINITY;
+        {
+          uint32_t va[16], vb[16];
+          auto chunk_max = [&](const uint32_t* v, int c) {
+            const int k0 = c0 + c * 16;
+            if (k0 + 16 <= kfull) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (visible(k0 + e)) mx = fmaxf(mx, __uint_as_float(v[e]));
+            }
+          };
+          if (nact > 0) tmem_ld16(s_taddr, va);
+          for (int c = 0; c < nact; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nact) tmem_ld16(s_taddr + (c + 1) * 16, vb);
+            chunk_max(va, c);
+            if (c + 1 < nact) {
+              tmem_ld_wait();
+              if (c + 2 < nact) tmem_ld16(s_taddr + (c + 2) * 16, va);
+              chunk_max(vb, c + 1);
+            }
           }
         }
         redmax[half * 128 + r] = mx;
         named_bar_sync(2, 256);
         mx = fmaxf(redmax[r], redmax[128 + r]);
-        const float mref = (mx == -INFINITY) ? 0.f : mx;
-        // ---- pass 2: P = exp2(s - m), row sum, dropout, bf16 -> swizzled smem
+        const float mref = (mx == -INFINITY) ? 0.f : mx * sl2;
+        // ---- deferred epilogue of the previous tile: its P V product ran while pass 1 was executing.  Waiting for it also
+        // guarantees that the tensor core has finished reading the (single) P tile before pass 2 overwrites it.
+        if (t > 0) epilogue_prev(t - 1);
+        // ---- pass 2: P = exp2(s * scale * log2e - m), row sum, dropout, bf16 -> swizzled smem
         float sum = 0.f;
-        for (int c = 0; c < half_cols; c += 16) {
-          const int k0 = half * half_cols + c;
-          uint32_t v[16];
-          tmem_ld16(lane_taddr + k0, v);
-          tmem_ld_wait();
-          float pe[16];
+        {
+          uint32_t va[16], vb[16];
+          auto chunk_exp = [&](const uint32_t* v, int c) {
+            const int k0 = c0 + c * 16;
+            float pe[16];
+            if (k0 + 16 <= kfull) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int kk = k0 + e;
-            const bool ok = sKok[kk] && (!p.causal || kk <= qq);
-            pe[e] = ok ? exp2f(__uint_as_float(v[e]) * sl2 - mref) : 0.f;
-            sum += pe[e];
+              for (int e = 0; e < 16; ++e) pe[e] = ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -mref));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                pe[e] = visible(k0 + e) ? ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -mref)) : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sum += pe[e];
+            if (p.p_drop > 0.f) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) pe[e] = attn_drop_rand(dkey, qq, k0 + e, p.Sk) >= thr ? pe[e] * inv_keep : 0.f;
+            }
+            uint8_t* atom = sP + (k0 >> 6) * 16384 + p_row;
+            const int u0 = (k0 & 63) >> 3;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              uint4 w;
+              w.x = pack_bf16x2(pe[8 * u + 0], pe[8 * u + 1]); w.y = pack_bf16x2(pe[8 * u + 2], pe[8 * u + 3]);
+              w.z = pack_bf16x2(pe[8 * u + 4], pe[8 * u + 5]); w.w = pack_bf16x2(pe[8 * u + 6], pe[8 * u + 7]);
+              *reinterpret_cast<uint4*>(atom + (((u0 + u) ^ r7) << 4)) = w;
+            }
+          };
+          if (nact > 0) tmem_ld16(s_taddr, va);
+          for (int c = 0; c < nact; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nact) tmem_ld16(s_taddr + (c + 1) * 16, vb);
+            chunk_exp(va, c);
+            if (c + 1 < nact) {
+              tmem_ld_wait();
+              if (c + 2 < nact) tmem_ld16(s_taddr + (c + 2) * 16, va);
+              chunk_exp(vb, c + 1);
+            }
           }
-          if (p.p_drop > 0.f) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) pe[e] = attn_drop_rand(dkey, qq, k0 + e, p.Sk) >= thr ? pe[e] * inv_keep : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            uint4 w;
-            w.x = pack_bf16x2(pe[8 * u + 0], pe[8 * u + 1]); w.y = pack_bf16x2(pe[8 * u + 2], pe[8 * u + 3]);
-            w.z = pack_bf16x2(pe[8 * u + 4], pe[8 * u + 5]); w.w = pack_bf16x2(pe[8 * u + 6], pe[8 * u + 7]);
-            *reinterpret_cast<uint4*>(sP + pt_offset16(r, k0 + 8 * u)) = w;
+          // chunks without any visible key: P = 0 (the P V product runs over all Nk columns)
+          for (int c = nact; c < nchunks; ++c) {
+            const int k0 = c0 + c * 16;
+            uint8_t* atom = sP + (k0 >> 6) * 16384 + p_row;
+            const int u0 = (k0 & 63) >> 3;
+            *reinterpret_cast<uint4*>(atom + ((u0 ^ r7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(atom + (((u0 + 1) ^ r7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
           }
         }
         redsum[half * 128 + r] = sum;
@@ -718,30 +872,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);
         named_bar_sync(2, 256);
-        const float l = redsum[r] + redsum[128 + r];
-        // ---- epilogue: O / l, LSE
-        mbar_wait(o_full, tph);
-        tc_fence_after();
-        uint32_t acc[32];
-        tmem_ld32(lane_taddr + O_COL + half * 32, acc);
-        tmem_ld_wait();
-        if (qq < p.Tq) {
-          const float inv = l > 0.f ? 1.f / l : 0.f;
-          uint4* dst = reinterpret_cast<uint4*>(p.o + (long long)b * p.o_bs + (long long)qq * p.o_rs + h * 64 + half * 32);
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            dst[e] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * e]) * inv, __uint_as_float(acc[8 * e + 1]) * inv),
-                                pack_bf16x2(__uint_as_float(acc[8 * e + 2]) * inv, __uint_as_float(acc[8 * e + 3]) * inv),
-                                pack_bf16x2(__uint_as_float(acc[8 * e + 4]) * inv, __uint_as_float(acc[8 * e + 5]) * inv),
-                                pack_bf16x2(__uint_as_float(acc[8 * e + 6]) * inv, __uint_as_float(acc[8 * e + 7]) * inv));
-          if (half == 0 && p.lse)
-            p.lse[(long long)item * p.Tq + qq] = l > 0.f ? (mx + log2f(l)) * 0.6931471805599453f : -INFINITY;
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_free);
+        l_prev = redsum[r] + redsum[128 + r];
+        mref_prev = mref;
+        row_prev = qq < p.Tq;
+        o_off_prev = (long long)b * p.o_bs + (long long)qq * p.o_rs + h * 64;
+        lse_off_prev = (long long)item * p.Tq + qq;
       }
     }
+    if (t > 0) epilogue_prev(t - 1);
   }
 
   tc_fence_before();
@@ -758,7 +896,7 @@ int attention_fwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
                               const uint8_t* kmask, int B, int H, int Tq, int Sk, int DH, int causal, float scale, float p_drop,
                               unsigned long long seed, unsigned long long offset, const unsigned long long* rng_offset_ptr,
                               cudaStream_t stream) {
-  if (DH != 64 || Sk > 256 || (o_rs % 8) || (o_bs % 8)) return 0;
+  if (DH != 64 || Sk > 224 || (o_rs % 8) || (o_bs % 8) || !(scale > 0.f)) return 0;   // two S buffers + O in 512 TMEM columns
   bind_context_for_driver_calls();
   const int Nk = (Sk + 31) / 32 * 32;
   CUtensorMap tq, tk, tv;
@@ -775,16 +913,16 @@ int attention_fwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
   p.seed = seed; p.offset = offset; p.offset_ptr = rng_offset_ptr;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AtcFwdSmem::TOTAL);
+    cudaError_t err = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AtcFwdSmem::total(224));
     if (err != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(attn_fwd_tc smem=%d): %s", AtcFwdSmem::TOTAL, cudaGetErrorString(err));
+      set_error("cudaFuncSetAttribute(attn_fwd_tc smem=%d): %s", AtcFwdSmem::total(224), cudaGetErrorString(err));
       return -1;
     }
     attr_set = true;
   }
   const int items = B * H;
   const int grid = items < num_sms() ? items : num_sms();
-  attn_fwd_tc_kernel<<<grid, ATC_THREADS, AtcFwdSmem::TOTAL, stream>>>(tq, tk, tv, p);
+  attn_fwd_tc_kernel<<<grid, ATC_THREADS, AtcFwdSmem::total(Nk), stream>>>(tq, tk, tv, p);
   const int rc = check_launch("attn_fwd_tc");
   return rc ? rc : 1;
 }

@@ -427,7 +427,8 @@ static int launch_gemm_m(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
 }
 
 // `tma_store` carries the epilogue mode (EPI_GENERIC = direct stores).  Specialised kernels exist for the operand layouts
-// the modes occur with: forward (both operands K-major): bias / GELU+stash / dropout+residual; dgrad (B MN-major): plain / GELU'.
+// the modes occur with: forward (both operands K-major): bias / GELU+stash / dropout+residual; dgrad (B MN-major): plain / GELU' /
+// residual.
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx, int mode,
                        int M, int N, int K, int batch, int a_bmul, int b_bmul, int split_k, long long c_bs, long long aux_bs,
@@ -443,6 +444,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   if constexpr (!A_MN && B_MN) {
     if (mode == EPI_BIAS) VLM_MODE_CASE(EPI_BIAS);
     if (mode == EPI_GELUGRAD) VLM_MODE_CASE(EPI_GELUGRAD);
+    if (mode == EPI_RESID) VLM_MODE_CASE(EPI_RESID);     // dgrad + residual-gradient add (post-LN blocks)
   }
   VLM_MODE_CASE(EPI_GENERIC);
 #undef VLM_MODE_CASE

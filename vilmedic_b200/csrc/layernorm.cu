@@ -113,27 +113,57 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
   const uint32_t thr = (uint32_t)(p_drop * 4294967296.0f);
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
 
+  // Rows are software-pipelined: the raw x / dy vectors (and mean / rstd) of this warp's NEXT row are requested before the
+  // current row is reduced, so two rows of loads are in flight per warp (the kernel is latency-bound at 12 warps / SM).
+  constexpr int XW = sizeof(TIn) == 2 ? 1 : 2;   // uint4 words per 8-element vector of x
+  uint4 nx[NV][XW], ndy[NV];
+  float nmu = 0.f, nrs = 0.f;
+  auto prefetch = [&](int prow) {
+    if (prow < M) {
+      const uint4* xr4 = reinterpret_cast<const uint4*>(x + (size_t)prow * D);
+      const uint4* dy4 = reinterpret_cast<const uint4*>(dy + (size_t)prow * D);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nvec) {
+#pragma unroll
+          for (int w = 0; w < XW; ++w) nx[i][w] = xr4[vi * XW + w];
+          ndy[i] = dy4[vi];
+        }
+      }
+      nmu = mean[prow];
+      nrs = rstd[prow];
+    }
+  };
+  prefetch(blockIdx.x * 4 + warp);
   for (int row = blockIdx.x * 4 + warp; row < M; row += gridDim.x * 4) {
-    const TIn* xr = x + (size_t)row * D;
-    const bf16* dyr = dy + (size_t)row * D;
-    const float mu = mean[row], rs = rstd[row];
-    float xh[NV][8], g[NV][8];
+    const float mu = nmu, rs = nrs;
+    uint4 cx[NV][XW], cdy[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+      for (int w = 0; w < XW; ++w) cx[i][w] = nx[i][w];
+      cdy[i] = ndy[i];
+    }
+    prefetch(row + gridDim.x * 4);
+    // pass 1 over the raw registers: row statistics + column partials; pass 2 re-derives xhat / dy*gamma from the same raw
+    // registers (cheaper in registers than keeping 2 x 8 x NV floats alive across the warp reductions)
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
         float xv[8], dv[8], gm[8];
-        Vec8<TIn>::load(xr + vi * 8, xv);
-        Vec8<bf16>::load(dyr + vi * 8, dv);
+        Vec8<TIn>::load(reinterpret_cast<const TIn*>(&cx[i][0]), xv);
+        Vec8<bf16>::load(reinterpret_cast<const bf16*>(&cdy[i]), dv);
         Vec8<float>::load(gamma + vi * 8, gm);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xv[j] - mu) * rs;
-          g[i][j] = dv[j] * gm[j];
-          s1 += g[i][j];
-          s2 += g[i][j] * xh[i][j];
-          dg[i][j] += dv[j] * xh[i][j];
+          const float xh = (xv[j] - mu) * rs;
+          const float g = dv[j] * gm[j];
+          s1 += g;
+          s2 += g * xh;
+          dg[i][j] += dv[j] * xh;
           db[i][j] += dv[j];
         }
       }
@@ -145,8 +175,14 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
       const int vi = lane + 32 * i;
       if (vi < nvec) {
         float o[8];
+        {
+          float xv[8], dv[8], gm[8];
+          Vec8<TIn>::load(reinterpret_cast<const TIn*>(&cx[i][0]), xv);
+          Vec8<bf16>::load(reinterpret_cast<const bf16*>(&cdy[i]), dv);
+          Vec8<float>::load(gamma + vi * 8, gm);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - c1 - xh[i][j] * c2);
+          for (int j = 0; j < 8; ++j) o[j] = rs * (dv[j] * gm[j] - c1 - (xv[j] - mu) * rs * c2);
+        }
         if (dres) {
           float r[8];
           Vec8<TIn>::load(dres + (size_t)row * D + vi * 8, r);
