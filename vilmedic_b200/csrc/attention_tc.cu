@@ -46,9 +46,6 @@ __device__ __forceinline__ void tma_load_4d(const void* desc, uint64_t* bar, voi
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 static constexpr int ATC_THREADS = 320;          // 2 control warps + 8 compute warps
 static constexpr int ATC_S_COL = 0, ATC_DV_COL = 256, ATC_DK_COL = 320, ATC_DQ_COL = 384;

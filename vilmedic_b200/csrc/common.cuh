@@ -99,6 +99,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// named barrier over a subset of the CTA (all participating warps must use the same id / thread count)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- TMA ----
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
@@ -226,15 +231,29 @@ __device__ __forceinline__ float erf_as(float x, float& e) {
   e = ex2_approx(ax * ax * -1.4426950408889634f);
   return copysignf(fmaf(-p, e, 1.0f), x);
 }
-// exact-erf GELU of HF (hidden_act="gelu"): 0.5 x (1 + erf(x / sqrt 2))
+// exact-erf GELU of HF (hidden_act="gelu"): 0.5 x (1 + erf(x / sqrt 2)), with erf by the same A&S 7.1.26 polynomial evaluated
+// directly on |x| (constants folded):  w = 0.5 (1 - erf(|x| / sqrt 2)) = 0.5 P(t) exp(-x^2 / 2),  t = 1 / (1 + p |x| / sqrt 2).
+// `e` returns exp(-x^2 / 2).  GELU(x) = relu(x) - |x| w  (x >= 0: x (1 - w); x < 0: x w — no cancellation in the negative tail).
+__device__ __forceinline__ float gelu_half_erfc(float ax, float& e) {
+  const float t = rcp_approx(fmaf(ax, 0.3275911f * 0.70710678118654752f, 1.0f));
+  float q = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  q = fmaf(q, t, 0.5f * 1.421413741f);
+  q = fmaf(q, t, 0.5f * -0.284496736f);
+  q = fmaf(q, t, 0.5f * 0.254829592f);
+  e = ex2_approx((ax * ax) * (-0.5f * 1.4426950408889634f));
+  return (q * t) * e;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   float e;
-  const float h = 0.5f * x;
-  return fmaf(h, erf_as(x * 0.70710678118654752f, e), h);
+  const float ax = fabsf(x);
+  const float w = gelu_half_erfc(ax, e);
+  return fmaf(-ax, w, fmaxf(x, 0.f));
 }
+// d/dx GELU = Phi(x) + x phi(x);  Phi = 1 - w (x >= 0) | w (x < 0);  phi = exp(-x^2 / 2) / sqrt(2 pi)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float e;  // = exp(-x^2 / 2)
-  const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f, e));
+  float e;
+  const float w = gelu_half_erfc(fabsf(x), e);
+  const float cdf = 0.5f + copysignf(0.5f - w, x);
   return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 

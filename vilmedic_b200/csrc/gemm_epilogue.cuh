@@ -247,50 +247,73 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0
 
 // ---- staged fast path -------------------------------------------------------------------------------------------------
 // One 32-column span of one accumulator row per lane, bf16 C without accumulation, interior of the N range (col0 + 32 <= N).
-// `pre` holds the row's 32 bf16 inputs of this span (GELU' argument if act == 2, else the residual) loaded at tile start,
-// i.e. under the mainloop of the tile, so no global-load latency is exposed here.  The result (and, for act == 1 with
-// aux_out, the pre-activation) leaves through the warp's 32x32 bf16 staging tile (dense 64-byte rows, SWIZZLE_64B: 16-byte
-// unit ^= (row >> 1) & 3 — conflict-free for row-per-lane 16-byte accesses) and TMA tensor stores issued by lane 0; rows
-// >= M are clipped by the tensor map.  Must be called by all 32 lanes.
-__device__ __forceinline__ void stg_write_row(uint8_t* stg, int lane, const uint32_t* packed /* 16 x bf16x2 */) {
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int unit = u ^ ((lane >> 1) & 3);
-    *reinterpret_cast<uint4*>(stg + lane * 64 + (unit << 4)) =
-        make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
-  }
+// `pre` holds the row's 32 bf16 inputs of this span (GELU' argument if act == 2, else the residual) loaded one tile ahead, so
+// no global-load latency is exposed here; the bias of the tile sits in shared memory (staged by the epilogue warps while the
+// mainloop of the tile runs).  The result (and, for act == 1 with aux_out, the pre-activation) leaves through one of the
+// warp's BUFS 32x32 bf16 staging tiles (dense 64-byte rows, SWIZZLE_64B: 16-byte unit ^= (row >> 1) & 3 — conflict-free for
+// row-per-lane 16-byte accesses) and a TMA tensor store issued by lane 0; rows >= M are clipped by the tensor map.  With
+// BUFS == 2 the tiles alternate, so a tile is only rewritten after the store issued two stores ago has drained it (ncu showed
+// 18 % of the epilogue time waiting for the drain of a single tile, profiles/ncu_r1b_attention_gemm.txt).
+// Must be called by all 32 lanes.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_3d_s(const void* desc, uint32_t smem_addr, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_addr), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 
 // Epilogue modes the staged fast path is specialised for at compile time (one kernel instantiation each: the generic
 // runtime-flag epilogue needs ~150 live registers, the specialised ones fit the 128-register budget of 14 warps / CTA).
 enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_GELU = 2, EPI_GELUGRAD = 3, EPI_RESID = 4 };
 
-template <int MODE>
-__device__ __forceinline__ void epilogue_span_fast(uint32_t taddr, int row, int row0, int col0, int batch_idx, int lane,
-                                                   const GemmEpilogue& e, float alpha, const uint4 (&pre)[4], uint8_t* stg,
-                                                   const CUtensorMap* tmap_c, const CUtensorMap* tmap_aux) {
-  if (lane == 0) bulk_wait_read_all();          // the previous TMA store has drained the staging tile
+// claims the warp's next staging tile: waits until the TMA store that last read it has drained, returns its smem address
+template <int BUFS>
+__device__ __forceinline__ uint32_t stg_acquire(uint32_t stg_base, uint32_t& stg_cnt, int lane) {
+  if (lane == 0) bulk_wait_read<BUFS - 1>();
   __syncwarp();
+  const uint32_t a = stg_base + (stg_cnt & (uint32_t)(BUFS - 1)) * 2048u;
+  ++stg_cnt;
+  return a;
+}
+
+template <int MODE, int BUFS>
+__device__ __forceinline__ void epilogue_span_fast(uint32_t taddr, int row, int row0, int col0, int batch_idx, int lane,
+                                                   const GemmEpilogue& e, float alpha, const uint4 (&pre)[4], uint32_t stg_base,
+                                                   uint32_t& stg_cnt, uint32_t sbias /* smem address of the span's 32 bias floats, 0 = none */,
+                                                   const CUtensorMap* tmap_c, const CUtensorMap* tmap_aux) {
   const bool stash = MODE == EPI_GELU && e.aux_out != nullptr;
   uint32_t stashed[MODE == EPI_GELU ? 16 : 1];
+  const uint32_t stg = stg_acquire<BUFS>(stg_base, stg_cnt, lane);
+  const uint32_t srow = stg + (uint32_t)lane * 64u;
+  const int sw = (lane >> 1) & 3;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {                 // two 16-column halves
     uint32_t acc[16];
     tmem_ld16(taddr + 16 * h, acc);
     tmem_ld_wait();
     float v[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) * alpha;
-    if (e.bias) {
-      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0 + 16 * h);
+    if (sbias) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 b = __ldg(b4 + j);
-        v[4 * j + 0] += b.x;
-        v[4 * j + 1] += b.y;
-        v[4 * j + 2] += b.z;
-        v[4 * j + 3] += b.w;
+        const float4 b = lds128f(sbias + (uint32_t)(64 * h + 16 * j));
+        v[4 * j + 0] = fmaf(__uint_as_float(acc[4 * j + 0]), alpha, b.x);
+        v[4 * j + 1] = fmaf(__uint_as_float(acc[4 * j + 1]), alpha, b.y);
+        v[4 * j + 2] = fmaf(__uint_as_float(acc[4 * j + 2]), alpha, b.z);
+        v[4 * j + 3] = fmaf(__uint_as_float(acc[4 * j + 3]), alpha, b.w);
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) * alpha;
     }
     if constexpr (MODE == EPI_GELU) {
       if (stash) {
@@ -337,28 +360,27 @@ __device__ __forceinline__ void epilogue_span_fast(uint32_t taddr, int row, int 
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int unit = (2 * h + u) ^ ((lane >> 1) & 3);
-      *reinterpret_cast<uint4*>(stg + lane * 64 + (unit << 4)) =
-          make_uint4(pack_bf16x2(v[8 * u + 0], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
-                     pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
-    }
+    for (int u = 0; u < 2; ++u)
+      sts128(srow + (uint32_t)(((2 * h + u) ^ sw) << 4), pack_bf16x2(v[8 * u + 0], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+             pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
   }
   fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0) {
-    tma_store_3d(tmap_c, stg, col0, row0, batch_idx);
+    tma_store_3d_s(tmap_c, stg, col0, row0, batch_idx);
     bulk_commit_group();
   }
   if constexpr (MODE == EPI_GELU) {
-    if (stash) {                                // second trip through the same tile for the GELU pre-activation
-      if (lane == 0) bulk_wait_read_all();
-      __syncwarp();
-      stg_write_row(stg, lane, stashed);
+    if (stash) {                                // the GELU pre-activation leaves through the warp's next staging tile
+      const uint32_t stg2 = stg_acquire<BUFS>(stg_base, stg_cnt, lane);
+      const uint32_t srow2 = stg2 + (uint32_t)lane * 64u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        sts128(srow2 + (uint32_t)((u ^ sw) << 4), stashed[4 * u], stashed[4 * u + 1], stashed[4 * u + 2], stashed[4 * u + 3]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_3d(tmap_aux, stg, col0, row0, batch_idx);
+        tma_store_3d_s(tmap_aux, stg2, col0, row0, batch_idx);
         bulk_commit_group();
       }
     }

@@ -31,26 +31,35 @@ static constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle row
 __host__ __device__ constexpr int gemm_threads(int parts) { return 64 + 128 * parts; }
 static constexpr int GEMM_MAX_EPI_WARPS = 12;
 
-template <int BN>
+// Shared-memory plan.  Specialised (staged-epilogue) kernels carry, per epilogue warp, STG_BUFS 32x32 bf16 staging tiles for
+// the TMA-store epilogue plus two BN-float bias buffers; they pay for it with one pipeline stage (K = 768..3072 mainloops are
+// consumer-bound: the ring was full at 5-6 stages, profiles/ncu_gemm_r1_epilogue.txt).
+// SBUFS = 2 (double-buffered staging, one stage less) is used for short mainloops (K <= 1536: epilogue-bound), SBUFS = 1 for
+// long ones (K = 3072: mainloop-bound, the extra stage matters more) — measured with tools/gemm_bench.py.
+template <int BN, int MODE, int SBUFS>
 struct GemmSmem {
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+  static constexpr bool FAST = MODE != EPI_GENERIC;
+  static constexpr int STG_BUFS = FAST ? SBUFS : 0;
+  static constexpr int STAGES = (FAST && SBUFS == 2) ? (BN >= 192 ? 4 : (BN >= 128 ? 5 : 6)) : ((BN >= 256) ? 4 : (BN >= 192 ? 5 : 6));
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;            // epilogue staging: one 32x32 bf16 tile per epilogue warp
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;            // epilogue staging tiles
   static constexpr int STG_BYTES = 32 * 32 * 2;
-  static constexpr int BAR_OFFSET = STG_OFFSET + GEMM_MAX_EPI_WARPS * STG_BYTES;
+  static constexpr int BIAS_OFFSET = STG_OFFSET + GEMM_MAX_EPI_WARPS * STG_BUFS * STG_BYTES;   // float [2][BN]
+  static constexpr int BAR_OFFSET = BIAS_OFFSET + (FAST ? 2 * BN * 4 : 0);
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
+  static_assert(TOTAL <= 232448, "shared memory plan exceeds 227 KB");
 };
 
-template <int BN, bool A_MN, bool B_MN, int PARTS, int GEMM_EPI_W, int MODE>
+template <int BN, bool A_MN, bool B_MN, int PARTS, int GEMM_EPI_W, int MODE, int SBUFS>
 __global__ void __launch_bounds__(gemm_threads(PARTS), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux, int tma_store,
                          int M, int N, int K, int batch, int a_bmul, int b_bmul, int split_k,
                          long long c_batch_stride, long long aux_batch_stride, long long res_batch_stride,
                          GemmEpilogue epi) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, MODE, SBUFS>;
   constexpr int STAGES = S::STAGES;
   constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;  // two accumulator buffers of BN fp32 columns
   extern __shared__ uint8_t smem_raw[];
@@ -203,7 +212,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int quad = warp_idx & 3;                 // TMEM lane quadrant this warp may access
     const int part = (warp_idx - 2) >> 2;          // which spans of the tile's columns this warp drains
     constexpr int SPANS = BN / 32;
-    uint8_t* stg = smem + S::STG_OFFSET + (warp_idx - 2) * S::STG_BYTES;
+    constexpr int STG_BUFS = S::STG_BUFS > 0 ? S::STG_BUFS : 1;
+    const uint32_t stg_base = smem_u32(smem + S::STG_OFFSET) + (uint32_t)((warp_idx - 2) * STG_BUFS * S::STG_BYTES);
+    uint32_t stg_cnt = 0;
+    const uint32_t sbias_base = smem_u32(smem + S::BIAS_OFFSET);
     const unsigned long long rng_add = (epi.p_drop > 0.f && epi.offset_ptr) ? __ldg(epi.offset_ptr) : 0ull;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -272,6 +284,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               for (int i = 0; i < NSP; ++i) load_pre(i, b, m0, n0);
             }
           }
+          // bias of this tile -> shared memory (buffer by accumulator parity), while the mainloop of the tile is still running
+          if (e.bias) {
+            for (int i = threadIdx.x - 64; i < BN; i += 128 * PARTS)
+              reinterpret_cast<float*>(smem + S::BIAS_OFFSET)[acc * BN + i] = __ldg(e.bias + n0 + i);
+            named_bar_sync(1, 128 * PARTS);
+          }
           mbar_wait(&tmem_full_bar[acc], acc_phase);
           tc_fence_after();
           const float alpha = e.alpha_ptr ? e.alpha * __ldg(e.alpha_ptr) : e.alpha;
@@ -279,8 +297,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int i = 0; i < NSP; ++i) {
             const int sp = part * NSP + i;       // adjacent spans: a lane's row inputs form whole 128-byte lines
             if (sp < SPANS)
-              epilogue_span_fast<MODE>(taddr + sp * 32, row, m0 + quad * 32, n0 + sp * 32, b, lane, e, alpha, pre[HAS_PRE ? i : 0],
-                                       stg, &tmap_c, &tmap_aux);
+              epilogue_span_fast<MODE, STG_BUFS>(taddr + sp * 32, row, m0 + quad * 32, n0 + sp * 32, b, lane, e, alpha,
+                                                 pre[HAS_PRE ? i : 0], stg_base, stg_cnt,
+                                                 e.bias ? sbias_base + (uint32_t)((acc * BN + sp * 32) * 4) : 0u, &tmap_c, &tmap_aux);
             if constexpr (HAS_PRE) {
               if (nfast) load_pre(i, nb, nm0, nn0);
             }
@@ -401,13 +420,13 @@ void bind_context_for_driver_calls() {
 
 static constexpr int GEMM_PARTS = 3;   // epilogue warps per TMEM lane quadrant (14 warps per CTA, <= 128 registers each)
 
-template <int BN, bool A_MN, bool B_MN, int MODE>
+template <int BN, bool A_MN, bool B_MN, int MODE, int SBUFS>
 static int launch_gemm_m(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx, int tma_store,
                        int M, int N, int K,
                        int batch, int a_bmul, int b_bmul, int split_k, long long c_bs, long long aux_bs, long long res_bs,
                        const GemmEpilogue& epi, int max_ctas, cudaStream_t stream) {
-  using S = GemmSmem<BN>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN, GEMM_PARTS, 16, MODE>;
+  using S = GemmSmem<BN, MODE, SBUFS>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN, GEMM_PARTS, 16, MODE, SBUFS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -433,9 +452,18 @@ template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx, int mode,
                        int M, int N, int K, int batch, int a_bmul, int b_bmul, int split_k, long long c_bs, long long aux_bs,
                        long long res_bs, const GemmEpilogue& epi, int max_ctas, cudaStream_t stream) {
-#define VLM_MODE_CASE(M_) \
-  return launch_gemm_m<BN, A_MN, B_MN, M_>(ta, tb, tc, tx, M_ != EPI_GENERIC, M, N, K, batch, a_bmul, b_bmul, split_k, c_bs, aux_bs, \
-                                           res_bs, epi, max_ctas, stream)
+  // double-buffered staging only where it pays (short K) and where the smem plan has room for it (BN 128 / 192)
+  const bool dbl = (BN == 128 || BN == 192) && K <= 1536;
+#define VLM_MODE_CASE(M_)                                                                                                            \
+  do {                                                                                                                               \
+    if constexpr ((BN == 128 || BN == 192) && M_ != EPI_GENERIC) {                                                                   \
+      if (dbl)                                                                                                                       \
+        return launch_gemm_m<BN, A_MN, B_MN, M_, 2>(ta, tb, tc, tx, 1, M, N, K, batch, a_bmul, b_bmul, split_k, c_bs, aux_bs, res_bs, \
+                                                    epi, max_ctas, stream);                                                          \
+    }                                                                                                                                \
+    return launch_gemm_m<BN, A_MN, B_MN, M_, 1>(ta, tb, tc, tx, M_ != EPI_GENERIC, M, N, K, batch, a_bmul, b_bmul, split_k, c_bs,      \
+                                                aux_bs, res_bs, epi, max_ctas, stream);                                              \
+  } while (0)
   if constexpr (!A_MN && !B_MN) {
     if (mode == EPI_BIAS) VLM_MODE_CASE(EPI_BIAS);
     if (mode == EPI_GELU) VLM_MODE_CASE(EPI_GELU);
