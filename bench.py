@@ -311,36 +311,55 @@ def peaks():
 
 
 def gemm_roofline(train_step, batch, ops):
-    """One instrumented training step: CUDA events around every tcgen05 GEMM launch (on the launching stream)."""
-    # Eager launches are host-bound (~1.1 k ctypes launches per step), so an empty stream would make the events time the
-    # host, not the kernels: park the GPU behind a spin kernel first, then every launch of the step is queued back to back
-    # and the event pairs bracket pure device execution.
+    """Dominant-kernel roofline: every tcgen05 GEMM launch of one training step, timed with CUDA events on the launching
+    stream.  The step is first run once with recording on (exact arguments + operands of all its GEMM launches are kept);
+    the recorded launches are then replayed in step order, back to back, each bracketed by an event pair.  (Timing them
+    inside the eager step itself is not robust: the ~1.9 k stream entries of a step make the host the bottleneck on some
+    boxes, and the event pairs then also measure launch gaps.)  The replay runs behind a short spin kernel, so the queue
+    is never empty; operands are the real tensors of the step, > 126 MB apart from launch to launch (no L2 reuse beyond what
+    the step itself has)."""
     torch.cuda.synchronize()
-    torch.cuda._sleep(int(0.25 * 1.9e9))
     ops.GEMM_TIMING = []
     train_step(batch, False)
     torch.cuda.synchronize()
     recs = ops.GEMM_TIMING
     ops.GEMM_TIMING = None
-    tot_ms, tot_flop = 0.0, 0.0
+    for r in recs[:8]:                       # warm the replay path (ctypes thunks, event pool)
+        r[5]()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in recs]
+    torch.cuda._sleep(int(0.02 * 1.9e9))
+    for r, (e0, e1) in zip(recs, evs):
+        e0.record()
+        r[5]()
+        e1.record()
+    torch.cuda.synchronize()
+    tot_ms, tot_flop, tot_bytes = 0.0, 0.0, 0.0
     by_shape = {}
-    for (M, N, K, nb, e0, e1) in recs:
+    for (M, N, K, nb, nbytes, _call, _keep), (e0, e1) in zip(recs, evs):
         ms = e0.elapsed_time(e1)
         fl = 2.0 * M * N * K * nb
         tot_ms += ms
         tot_flop += fl
+        tot_bytes += nbytes
         k = (M, N, K, nb)
         a = by_shape.setdefault(k, [0, 0.0, 0.0])
         a[0] += 1
         a[1] += ms
         a[2] += fl
     pk = peaks()
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")     # ncu dram__bytes_{read,write}.sum over the same launches
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
     achieved = tot_flop / (tot_ms / 1e3) / 1e12 if tot_ms > 0 else 0.0
     top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:6]
     return {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all launches of one training step)",
             "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
-            "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)", "traffic": None,
-            "launches": len(recs), "gemm_ms_per_step": tot_ms, "gemm_flop_per_step": tot_flop,
+            "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+            "traffic": traffic.get("dram_bytes_per_step"), "traffic_source": traffic.get("source"),
+            "algorithmic_bytes": tot_bytes, "launches": len(recs),
+            "method": "all GEMM launches of one step recorded, then replayed in order under CUDA event pairs", "gemm_ms_per_step": tot_ms, "gemm_flop_per_step": tot_flop,
             "top_shapes": [{"MNKb": list(k), "n": v[0], "ms": round(v[1], 3), "tflops": round(v[2] / (v[1] / 1e3) / 1e12, 1)} for k, v in top]}
 
 

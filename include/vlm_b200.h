@@ -31,8 +31,9 @@ int vlm_device_check(void);
 /* ---- GEMM (tcgen05 + TMA) --------------------------------------------------------------------------------------- */
 /* C[M,N] = epi(alpha * A'[M,K] * B'[N,K]^T), bf16 operands, fp32 accumulate in TMEM.
  *   a_mn_major=0: A' stored [M][lda] (k contiguous); 1: stored [K][lda] (m contiguous).  Same for b / N.
- *   epi: (+bias[N] fp32) -> act (0 none | 1 GELU-erf, pre-activation stashed to aux_out if non-null |
- *        2 multiply by GELU'(aux_in)) -> dropout(p_drop; Philox(seed, offset, (row*N+col)/4), same stream as
+ *   epi: (+bias[N] fp32) -> act (0 none | 1 GELU-erf; if aux_out is non-null the DERIVATIVE GELU'(pre-activation) is
+ *        stashed there (bf16), so that the backward epilogue is a plain multiply | 2 multiply by aux_in, i.e. by the
+ *        stashed GELU') -> dropout(p_drop; Philox(seed, offset, (row*N+col)/4), same stream as
  *        vlm_dropout_bf16 on the flat [M,N] tensor) -> (+residual, dtype of C) -> (accumulate into C) -> store.
  *   alpha_ptr: optional device scalar multiplied into alpha (e.g. the upstream loss gradient, no host sync).
  *   batch>1: strided-batched; operands advance by *_batch_stride ELEMENTS per batch (bias is shared).

@@ -238,6 +238,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const float inv_keep = DROPOUT ? 1.f / (1.f - p.p_drop) : 1.f;
     const int half_cols = Nq >> 1;             // multiple of 16
     const uint32_t pt_row = (uint32_t)(r * 128);   // row offset inside a 64-column atom of the P^T / dS^T tile
+    const uint32_t aPTs = smem_u32(sPT), aP2s = smem_u32(sP2), aLse = smem_u32(sLse), aDelta = smem_u32(sDelta);   // shared-space addresses
     const int r7 = r & 7;
     uint32_t tile_cnt = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -272,7 +273,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             float ls[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 t = *reinterpret_cast<const float4*>(sLse + q0 + 4 * i);
+              const float4 t = lds128f(aLse + (uint32_t)((q0 + 4 * i) * 4));
               ls[4 * i] = t.x; ls[4 * i + 1] = t.y; ls[4 * i + 2] = t.z; ls[4 * i + 3] = t.w;
             }
             if (!p.causal || q0 >= k_lo + 31) {
@@ -299,11 +300,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             if (DROPOUT) {
               w.x = pack_bf16x2(pd[8 * u + 0], pd[8 * u + 1]); w.y = pack_bf16x2(pd[8 * u + 2], pd[8 * u + 3]);
               w.z = pack_bf16x2(pd[8 * u + 4], pd[8 * u + 5]); w.w = pack_bf16x2(pd[8 * u + 6], pd[8 * u + 7]);
-              *reinterpret_cast<uint4*>(sPT + off) = w;
+              sts128(aPTs + off, w.x, w.y, w.z, w.w);
             }
             w.x = pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]); w.y = pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]);
             w.z = pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]); w.w = pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]);
-            *reinterpret_cast<uint4*>((DROPOUT ? sP2 : sPT) + off) = w;
+            sts128((DROPOUT ? aP2s : aPTs) + off, w.x, w.y, w.z, w.w);
           }
         };
         {  // TMEM loads are software-pipelined: the next chunk is in flight while the current one is processed
@@ -335,7 +336,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           float dl[16];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 t = *reinterpret_cast<const float4*>(sDelta + q0 + 4 * i);
+            const float4 t = lds128f(aDelta + (uint32_t)((q0 + 4 * i) * 4));
             dl[4 * i] = t.x; dl[4 * i + 1] = t.y; dl[4 * i + 2] = t.z; dl[4 * i + 3] = t.w;
           }
           const uint32_t off0 = (uint32_t)((q0 >> 6) * 16384) + pt_row;
@@ -343,9 +344,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const uint32_t off = off0 + (uint32_t)(((u0 + u) ^ r7) << 4);
-            const uint4 pw = *reinterpret_cast<const uint4*>((DROPOUT ? sP2 : sPT) + off);
+            const uint4 pw = lds128u((DROPOUT ? aP2s : aPTs) + off);
             uint4 kw = pw;
-            if (DROPOUT) kw = *reinterpret_cast<const uint4*>(sPT + off);   // dropped P: zero <=> dropped (or P == 0)
+            if (DROPOUT) kw = lds128u(aPTs + off);   // dropped P: zero <=> dropped (or P == 0)
             const uint32_t pw4[4] = {pw.x, pw.y, pw.z, pw.w}, kw4[4] = {kw.x, kw.y, kw.z, kw.w};
             uint32_t ow[4];
 #pragma unroll
@@ -358,7 +359,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
               }
               ow[e] = pack_bf16x2(pp.x * (d0 - dl[8 * u + 2 * e]), pp.y * (d1 - dl[8 * u + 2 * e + 1]));
             }
-            *reinterpret_cast<uint4*>(sPT + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            sts128(aPTs + off, ow[0], ow[1], ow[2], ow[3]);
           }
         };
         {
@@ -703,7 +704,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int half_cols = Nk >> 1;               // multiple of 16
     const int c0 = half * half_cols;             // first key column of this thread's half
     const int nchunks = half_cols >> 4;
-    const uint32_t p_row = (uint32_t)(r * 128);  // row offset inside a 64-column atom of the P tile
+    const uint32_t p_row = smem_u32(sP) + (uint32_t)(r * 128);  // shared-space address of this row inside atom 0 of the P tile
     const int r7 = r & 7;
     float* redmax = sRed;                        // [2][128]
     float* redsum = sRed + 256;                  // [2][128]
@@ -833,14 +834,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 #pragma unroll
               for (int e = 0; e < 16; ++e) pe[e] = attn_drop_rand(dkey, qq, k0 + e, p.Sk) >= thr ? pe[e] * inv_keep : 0.f;
             }
-            uint8_t* atom = sP + (k0 >> 6) * 16384 + p_row;
+            const uint32_t atom = (uint32_t)((k0 >> 6) * 16384) + p_row;
             const int u0 = (k0 & 63) >> 3;
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               uint4 w;
               w.x = pack_bf16x2(pe[8 * u + 0], pe[8 * u + 1]); w.y = pack_bf16x2(pe[8 * u + 2], pe[8 * u + 3]);
               w.z = pack_bf16x2(pe[8 * u + 4], pe[8 * u + 5]); w.w = pack_bf16x2(pe[8 * u + 6], pe[8 * u + 7]);
-              *reinterpret_cast<uint4*>(atom + (((u0 + u) ^ r7) << 4)) = w;
+              sts128(atom + (uint32_t)(((u0 + u) ^ r7) << 4), w.x, w.y, w.z, w.w);
             }
           };
           if (nact > 0) tmem_ld16(s_taddr, va);
@@ -857,10 +858,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           // chunks without any visible key: P = 0 (the P V product runs over all Nk columns)
           for (int c = nact; c < nchunks; ++c) {
             const int k0 = c0 + c * 16;
-            uint8_t* atom = sP + (k0 >> 6) * 16384 + p_row;
+            const uint32_t atom = (uint32_t)((k0 >> 6) * 16384) + p_row;
             const int u0 = (k0 & 63) >> 3;
-            *reinterpret_cast<uint4*>(atom + ((u0 ^ r7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(atom + (((u0 + 1) ^ r7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            sts128(atom + (uint32_t)((u0 ^ r7) << 4), 0u, 0u, 0u, 0u);
+            sts128(atom + (uint32_t)(((u0 + 1) ^ r7) << 4), 0u, 0u, 0u, 0u);
           }
         }
         redsum[half * 128 + r] = sum;

@@ -16,7 +16,7 @@ struct GemmEpilogue {
   const float* bias;          // [N] or null
   const void* residual;       // same dtype as c, ld = ldr
   long long ldr;
-  int act;                    // 0 none, 1 GELU (optionally stash pre-activation), 2 multiply by GELU'(aux_in)
+  int act;                    // 0 none, 1 GELU (optionally stash GELU'(pre-activation) to aux_out), 2 multiply by aux_in
   const bf16* aux_in;         // [M, ld_aux]
   bf16* aux_out;              // [M, ld_aux]
   long long ld_aux;
@@ -88,32 +88,36 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0
     }
     if (e.act == 1) {
       if (e.aux_out) {
+        float dg[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) v[j] = gelu_erf_both(v[j], dg[j]);
         uint4* dst = reinterpret_cast<uint4*>(e.aux_out + (long long)row * e.ld_aux + col0);
 #pragma unroll
         for (int j = 0; j < W / 8; ++j) {
           uint4 u;
-          u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-          u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-          u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-          u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+          u.x = pack_bf16x2(dg[8 * j + 0], dg[8 * j + 1]);
+          u.y = pack_bf16x2(dg[8 * j + 2], dg[8 * j + 3]);
+          u.z = pack_bf16x2(dg[8 * j + 4], dg[8 * j + 5]);
+          u.w = pack_bf16x2(dg[8 * j + 6], dg[8 * j + 7]);
           dst[j] = u;
         }
-      }
+      } else {
 #pragma unroll
-      for (int j = 0; j < W; ++j) v[j] = gelu_erf(v[j]);
+        for (int j = 0; j < W; ++j) v[j] = gelu_erf(v[j]);
+      }
     } else if (e.act == 2) {
 #pragma unroll
       for (int j = 0; j < W / 8; ++j) {
         const uint4 u = aux[j];
         const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
-        v[8 * j + 0] *= gelu_erf_grad(p0.x);
-        v[8 * j + 1] *= gelu_erf_grad(p0.y);
-        v[8 * j + 2] *= gelu_erf_grad(p1.x);
-        v[8 * j + 3] *= gelu_erf_grad(p1.y);
-        v[8 * j + 4] *= gelu_erf_grad(p2.x);
-        v[8 * j + 5] *= gelu_erf_grad(p2.y);
-        v[8 * j + 6] *= gelu_erf_grad(p3.x);
-        v[8 * j + 7] *= gelu_erf_grad(p3.y);
+        v[8 * j + 0] *= p0.x;
+        v[8 * j + 1] *= p0.y;
+        v[8 * j + 2] *= p1.x;
+        v[8 * j + 3] *= p1.y;
+        v[8 * j + 4] *= p2.x;
+        v[8 * j + 5] *= p2.y;
+        v[8 * j + 6] *= p3.x;
+        v[8 * j + 7] *= p3.y;
       }
     }
     if (e.p_drop > 0.f) {
@@ -213,10 +217,11 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0
       float x = v[j];
       if (e.bias) x += e.bias[col];
       if (e.act == 1) {
-        if (e.aux_out) e.aux_out[(long long)row * e.ld_aux + col] = __float2bfloat16(x);
-        x = gelu_erf(x);
+        float dg;
+        x = gelu_erf_both(x, dg);
+        if (e.aux_out) e.aux_out[(long long)row * e.ld_aux + col] = __float2bfloat16(dg);
       } else if (e.act == 2) {
-        x *= gelu_erf_grad(__bfloat162float(e.aux_in[(long long)row * e.ld_aux + col]));
+        x *= __bfloat162float(e.aux_in[(long long)row * e.ld_aux + col]);
       }
       if (e.p_drop > 0.f) {
         const Philox rng(e.seed);
@@ -247,9 +252,9 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int row, int col0
 
 // ---- staged fast path -------------------------------------------------------------------------------------------------
 // One 32-column span of one accumulator row per lane, bf16 C without accumulation, interior of the N range (col0 + 32 <= N).
-// `pre` holds the row's 32 bf16 inputs of this span (GELU' argument if act == 2, else the residual) loaded one tile ahead, so
+// `pre` holds the row's 32 bf16 inputs of this span (the stashed GELU' if act == 2, else the residual) loaded one tile ahead, so
 // no global-load latency is exposed here; the bias of the tile sits in shared memory (staged by the epilogue warps while the
-// mainloop of the tile runs).  The result (and, for act == 1 with aux_out, the pre-activation) leaves through one of the
+// mainloop of the tile runs).  The result (and, for act == 1 with aux_out, GELU' of the pre-activation) leaves through one of the
 // warp's BUFS 32x32 bf16 staging tiles (dense 64-byte rows, SWIZZLE_64B: 16-byte unit ^= (row >> 1) & 3 — conflict-free for
 // row-per-lane 16-byte accesses) and a TMA tensor store issued by lane 0; rows >= M are clipped by the tensor map.  With
 // BUFS == 2 the tiles alternate, so a tile is only rewritten after the store issued two stores ago has drained it (ncu showed
@@ -261,6 +266,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
 template <int N>
@@ -316,22 +326,28 @@ __device__ __forceinline__ void epilogue_span_fast(uint32_t taddr, int row, int 
       for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) * alpha;
     }
     if constexpr (MODE == EPI_GELU) {
-      if (stash) {
+      if (stash) {                              // GELU and GELU' share every transcendental; the derivative is what is stashed
 #pragma unroll
-        for (int j = 0; j < 8; ++j) stashed[8 * h + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        for (int j = 0; j < 8; ++j) {
+          float d0, d1;
+          v[2 * j] = gelu_erf_both(v[2 * j], d0);
+          v[2 * j + 1] = gelu_erf_both(v[2 * j + 1], d1);
+          stashed[8 * h + j] = pack_bf16x2(d0, d1);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
       }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
     }
     if constexpr (MODE == EPI_GELUGRAD || MODE == EPI_RESID) {
       const uint4 pa = pre[2 * h], pb = pre[2 * h + 1];
       const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-      if constexpr (MODE == EPI_GELUGRAD) {
+      if constexpr (MODE == EPI_GELUGRAD) {   // aux_in holds GELU'(pre-activation), stashed by the forward epilogue
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float2 x = unpack_bf16x2(pw[j]);
-          v[2 * j] *= gelu_erf_grad(x.x);
-          v[2 * j + 1] *= gelu_erf_grad(x.y);
+          v[2 * j] *= x.x;
+          v[2 * j + 1] *= x.y;
         }
       } else {
         if (e.p_drop > 0.f) {

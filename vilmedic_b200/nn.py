@@ -220,7 +220,7 @@ class ViTLayerFn(torch.autograd.Function):
         x1 = ops.gemm(ctxv.view(B * S, D), Po.w, bias=Po.b, residual=x)
         h2, mean2, rstd2 = ops.layernorm_fwd(x1, ln2[0], ln2[1], eps)
         pre = torch.empty((B * S, cfg.intermediate_size), device=x.device, dtype=torch.bfloat16) if save else None
-        hmid = ops.gemm(h2, P1.w, bias=P1.b, act=ops.ACT_GELU, aux_out=pre)
+        hmid = ops.gemm(h2, P1.w, bias=P1.b, act=ops.ACT_GELU, aux_out=pre)   # pre <- GELU'(pre-activation)
         x2 = ops.gemm(hmid, P2.w, bias=P2.b, residual=x1)
         if save:
             ctx.saved = (x, h1, mean1, rstd1, qkv, ctxv, lse, x1, h2, mean2, rstd2, pre, hmid, Pqkv, Po, P1, P2, ln1, ln2, B, S, H, DH)
@@ -507,7 +507,7 @@ class BertLayerFn(torch.autograd.Function):
         else:
             x2 = x1
         pre = torch.empty((B * T, cfg.intermediate_size), device=x.device, dtype=torch.bfloat16) if save else None
-        hmid = ops.gemm(x2, P1.w, bias=P1.b, act=ops.ACT_GELU, aux_out=pre)
+        hmid = ops.gemm(x2, P1.w, bias=P1.b, act=ops.ACT_GELU, aux_out=pre)   # pre <- GELU'(pre-activation)
         s, o = R("h3")
         z3 = ops.gemm(hmid, P2.w, bias=P2.b, residual=x2, p_drop=p_h, seed=s, offset=o)
         x3, m3, r3 = ops.layernorm_fwd(z3, ln3[0], ln3[1], eps)

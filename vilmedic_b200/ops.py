@@ -15,7 +15,8 @@ ACT_NONE, ACT_GELU, ACT_GELU_GRAD = 0, 1, 2
 # Number of OUR kernels launched through this module (bench.py reports it as `gpu_launches`).
 LAUNCHES = [0]
 _KERNELS_PER_CALL = {"vlm_attention_bwd": 2, "vlm_attention_bwd_tc": 2, "vlm_adamw_step": 2}
-# Optional per-call CUDA-event timing of the GEMM launches (bench.py roofline pass): list of (M, N, K, batch, start, end)
+# Optional recording of the GEMM launches (bench.py roofline pass): list of (M, N, K, batch, algorithmic HBM bytes =
+# operands read once + outputs written once, replay closure, operands kept alive)
 GEMM_TIMING = None
 # Optional device uint64 added to every dropout offset (see vlm_rng_advance): set by GraphedTrainStep.
 RNG_COUNTER = [None]
@@ -88,11 +89,7 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, out=None, out_dtype=torch.
             ld_aux = t.stride(-2)
             if batched:
                 aux_bs = t.stride(0)
-    if GEMM_TIMING is not None:
-        ev0 = torch.cuda.Event(enable_timing=True)
-        ev1 = torch.cuda.Event(enable_timing=True)
-        ev0.record()
-    rc = _lib.lib().vlm_gemm_bf16(
+    args = (
         ptr(a), c_ll(a.stride(-2)), c_int(int(a_mn_major)),
         ptr(b), c_ll(b.stride(-2)), c_int(int(b_mn_major)),
         ptr(out), c_ll(out.stride(-2)), c_int(int(c_fp32)),
@@ -101,11 +98,16 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, out=None, out_dtype=torch.
         c_float(alpha), ptr(alpha_t), c_int(int(accumulate)), c_int(batch),
         c_ll(a.stride(0) if batched else 0), c_ll(b.stride(0) if batched else 0),
         c_ll(out.stride(0) if batched else 0), c_ll(aux_bs), c_ll(res_bs),
-        c_float(p_drop), c_u64(seed), c_u64(offset), ptr(RNG_COUNTER[0]), c_int(force_bn), c_int(max_ctas), stream_ptr())
+        c_float(p_drop), c_u64(seed), c_u64(offset), ptr(RNG_COUNTER[0]), c_int(force_bn), c_int(max_ctas))
+    rc = _lib.lib().vlm_gemm_bf16(*args, stream_ptr())
     check(rc, "vlm_gemm_bf16")
     if GEMM_TIMING is not None:
-        ev1.record()
-        GEMM_TIMING.append((M, N, K, batch, ev0, ev1))
+        # bench.py roofline pass: keep the exact call (and its operands alive) so that it can be replayed under CUDA events
+        esz = out.element_size()
+        nbytes = batch * (2 * (M * K + N * K) + M * N * esz * (1 + int(residual is not None) + int(bool(accumulate)))
+                          + 2 * M * N * (int(aux_in is not None) + int(aux_out is not None)))
+        keep = (a, b, out, bias, residual, aux_in, aux_out, alpha_t)
+        GEMM_TIMING.append((M, N, K, batch, nbytes, lambda: _lib.lib().vlm_gemm_bf16(*args, stream_ptr()), keep))
     return out
 
 
