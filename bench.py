@@ -54,6 +54,16 @@ def model_cfgs(dropout):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
+def host_threads():
+    """Use every host core this process may run on (torchrun pins OMP_NUM_THREADS=1 for its workers)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_reference_step_rate(batch, seq_len, steps, warmup, dropout):
     """pairs/s of the oracle training step (fp32, eager, AdamW) on the host cores."""
     import copy
@@ -83,7 +93,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
+    cores = host_threads()
     steps = max(1, min(args.steps, 3))
     warmup = max(1, min(args.warmup, 1))
     v, mean = cpu_reference_step_rate(args.cpu_batch, args.seq_len, steps, warmup, args.dropout)
@@ -163,8 +173,21 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    t_start = time.time()
+
+    def trace(msg):                      # progress markers on stderr (VLM_BENCH_TRACE=1): where a multi-rank run got to
+        if os.environ.get("VLM_BENCH_TRACE"):
+            sys.stderr.write("[bench rank %d +%.1fs] %s\n" % (rank, time.time() - t_start, msg))
+            sys.stderr.flush()
+
+    if os.environ.get("VLM_BENCH_TRACE"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("VLM_BENCH_TRACE_AFTER", "90")), repeat=False, file=sys.stderr)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a protocol bug must fail within minutes, not hang the box for the default 10-minute NCCL timeout
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    trace("process group up")
     torch.manual_seed(0)
     dec, cnn = model_cfgs(args.dropout)
     model = RRG(dec, cnn).cuda().train()
@@ -178,8 +201,9 @@ def run_ours(args):
     from vilmedic_b200.ddp import GradSync
     sync = GradSync(arena)
 
-    def train_step(batch, read_loss):
-        if world > 1:
+    def train_step(batch, read_loss, exchange=True):
+        """exchange=False: rank-local step without the gradient all-reduce (instrumented passes that only one rank runs)."""
+        if world > 1 and exchange:
             # the decoder's gradients are complete once the backward reaches the image features: all-reduce that span
             # (NCCL stream, NVLink) while the ViT backward is still running; the encoder span follows.
             feats, fmask = model.encode(batch["images"], batch.get("images_mask"))
@@ -191,7 +215,7 @@ def run_ours(args):
             out = model(**batch)
         loss = out["loss"]
         loss.backward()
-        opt.step(grad_scale=sync.finish())
+        opt.step(grad_scale=sync.finish() if exchange else 1.0)
         if read_loss:
             return loss.item()
         return loss
@@ -235,6 +259,7 @@ def run_ours(args):
         train_step(devb, False)
         launches = ops.LAUNCHES[0] - l0      # kernels of ours per step (the graph replays exactly these)
     torch.cuda.synchronize()
+    trace("warm-up done (%d launches / step)" % launches)
     graph_note = "eager launches"
     if not args.no_graph:
         try:
@@ -245,34 +270,44 @@ def run_ours(args):
             for _ in range(2):
                 graphed(devb)
             torch.cuda.synchronize()
+            trace("graph captured and replayed")
         except Exception as e:  # pragma: no cover - reported, never silent
             graphed = None
             graph_note = "eager launches (graph capture failed: %s)" % (str(e).splitlines()[0][:160],)
             torch.cuda.synchronize()
 
+    if world > 1:                         # all ranks replay a graph, or none does
+        ok = torch.tensor([1 if graphed is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and graphed is not None:
+            graphed = None
+            graph_note = "eager launches (graph capture failed on another rank)"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms, last = timed(lambda: devb, args.steps, False)
+    trace("resident leg timed: %.2f ms / step" % (ms / args.steps))
     if args.quick:
         ms_e2e, last_loss = ms, None
         args.no_roofline = args.no_cpu_baseline = True
     else:
         ms_e2e, last_loss = timed(host_batch, args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
+    trace("e2e leg timed")
 
     value = world * B * args.steps / (ms / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
 
     roof = None
     if rank == 0 and not args.no_roofline:
-        roof = gemm_roofline(train_step, devb, ops)   # eager, instrumented pass
+        roof = gemm_roofline(lambda b, r: train_step(b, r, exchange=False), devb, ops)   # rank-local: no collectives
+    trace("roofline pass done")
     if world > 1:
         dist.barrier()
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        cores = torch.get_num_threads()
+    if rank == 0 and not args.no_cpu_baseline and world == 1:      # reported at N=1 only (the contract)
+        cores = host_threads()
         v, mean = cpu_reference_step_rate(args.cpu_batch, T, 2, 1, args.dropout)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "oracle RRG train step (HF ViTModel + BertGenerationDecoder, fp32 eager, AdamW), B=%d, T=%d, 1 warm-up + 2 timed steps (%.1f s/step)" % (
@@ -298,7 +333,15 @@ def run_ours(args):
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # destroy_process_group() blocks forever here (both ranks, observed on 2 x B200 with torch 2.11 / NCCL 2.28): the
+        # captured CUDA graph still holds NCCL work.  Everything is flushed and every rank has passed a final barrier, so
+        # leave without the communicator teardown.
+        dist.barrier()
+        torch.cuda.synchronize()
+        trace("done")
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def peaks():
