@@ -145,6 +145,37 @@ def test_state_dict_is_hf_compatible():
     assert d.lm_head.decoder.bias is d.lm_head.bias
 
 
+def test_reference_checkpoint_interchange(tmp_path):
+    """A checkpoint in the reference's layout (DataParallel `module.` prefix, pre-1.3.2 visual-encoder keys,
+    vilmedic/executors/utils.py:26-34,113-119) loads into the kernel towers, and the dict written back loads into the
+    HF-composed oracle with strict=True."""
+    from oracle.rrg import OracleRRG
+    from vilmedic_b200.checkpoint import load_reference_checkpoint, normalize_reference_keys, reference_state_dict
+    from vilmedic_b200.models import RRG
+    dec, cnn = _small_cfgs()
+    cnn["visual_projection"] = {"in_features": 128, "out_features": 768}
+    torch.manual_seed(3)
+    ref = OracleRRG(copy.deepcopy(dec), copy.deepcopy(cnn))
+    old = {}
+    for k, v in ref.state_dict().items():          # as a 1.3.1 DataParallel run would have saved it
+        k = k.replace("enc.visual_projection.weight", "enc.1.weight").replace("enc.visual_projection.bias", "enc.1.bias")
+        k = k.replace("enc.model.", "enc.0.cnn.")
+        old["module." + k] = v.clone()
+    path = tmp_path / "0.5_3_123456.pth"
+    torch.save({"model": old, "__version__": "1.3.1", "config": {}}, path)
+    mine = RRG(copy.deepcopy(dec), copy.deepcopy(cnn))
+    load_reference_checkpoint(mine, str(path))
+    a, b = ref.state_dict(), mine.state_dict()
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k].cpu()) for k in a)
+    assert set(normalize_reference_keys(old, None)) == set(a)
+    with pytest.raises(KeyError):
+        load_reference_checkpoint(mine, {"optimizer": {}})
+    back = reference_state_dict(mine, config={"x": 1})
+    ref2 = OracleRRG(copy.deepcopy(dec), copy.deepcopy(cnn))
+    ref2.load_state_dict(back["model"], strict=True)
+    assert all(torch.equal(v, ref2.state_dict()[k]) for k, v in a.items())
+
+
 def test_arena_views_groups_and_spans():
     from vilmedic_b200.arena import get_arena
     from vilmedic_b200.models import RRG

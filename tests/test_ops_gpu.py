@@ -444,6 +444,9 @@ def test_attention_bwd_tcgen05_dropout_matches_mma_path(cuda_dev):
     (1, 2, 5, 3, False, False, 0.0),        # tiny / ragged
     (2, 3, 300, 224, False, True, 0.0),     # three query tiles, max keys (two S buffers + O in 512 TMEM columns)
     (2, 4, 128, 128, True, False, 0.1),     # dropout: must reproduce the mma.sync kernel's mask bit for bit
+    (2, 4, 150, 200, False, "holes", 0.0),  # arbitrary (non-prefix) key mask: per-element visibility path
+    (2, 4, 128, 128, True, "holes", 0.0),   # ... combined with the causal mask
+    (3, 2, 128, 96, True, True, 0.0),       # causal with fewer keys than queries, right padding
 ])
 def test_attention_fwd_tcgen05(cuda_dev, B, H, Tq, Sk, causal, masked, p_drop):
     from vilmedic_b200 import ops
@@ -453,7 +456,12 @@ def test_attention_fwd_tcgen05(cuda_dev, B, H, Tq, Sk, causal, masked, p_drop):
     kv = _bf((B, Sk, 2 * D), cuda_dev, 4)
     k, v = kv[:, :, :D], kv[:, :, D:]
     kmask = None
-    if masked:
+    if masked == "holes":
+        g = torch.Generator().manual_seed(17)
+        kmask = (torch.rand(B, Sk, generator=g) > 0.3).to(torch.uint8)
+        kmask[:, 0] = 1                                          # key 0 visible to every causal row
+        kmask = kmask.to(cuda_dev).contiguous()
+    elif masked:
         lens = torch.randint(max(1, Sk // 2), Sk + 1, (B,))
         kmask = (torch.arange(Sk)[None, :] < lens[:, None]).to(torch.uint8).to(cuda_dev).contiguous()
     o, lse = ops.attention_fwd(q, k, v, H, DH, kmask=kmask, causal=causal, p_drop=p_drop, seed=5, offset=9, force_tc=True)
