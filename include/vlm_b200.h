@@ -200,6 +200,15 @@ int vlm_gloria_region_softmax_bwd(const float* P2, float* G, int NI, int S, long
 int vlm_gloria_word_softmax_bwd(const float* P1, const float* G, void* dA, const int* cap_lens, int rows, int NB, int L,
                                 long long ld, void* stream);
 
+/* ---- input pipeline (vilmedic/datasets/base/ImageDataset.py:97-104) ------------------------------------ */
+/* RandomCrop + RandomHorizontalFlip + ToTensor + Normalize of the reference's train transform, after its (host-side) Resize:
+ * in  uint8 [B, Hin, Win, 3] (HWC, what PIL / numpy hand over; device memory), top/left int32 [B] crop origins,
+ * flip uint8 [B]; out fp32 [B, 3, crop, crop] = ((in / 255) - mean[c]) / std[c] with IEEE fp32 division — bit-identical to
+ * torchvision's ToTensor().div(255) -> Normalize sub_().div_().  mean3 / std3 are HOST arrays of 3 floats.  Byte work,
+ * HBM-bound: reads 3 B, writes 12 B per pixel. */
+int vlm_image_crop_flip_normalize(const uint8_t* in, float* out, const int* top, const int* left, const uint8_t* flip, int B,
+                                  int Hin, int Win, int crop, const float* mean3, const float* std3, void* stream);
+
 /* ---- optimizer (vilmedic/executors/trainor.py:119-124) ------------------------------------------ */
 /* out[0] += sum(g^2)  (caller zeroes). */
 int vlm_sumsq_f32(const float* g, long long n, float* out, void* stream);

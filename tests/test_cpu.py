@@ -176,6 +176,24 @@ def test_reference_checkpoint_interchange(tmp_path):
     assert all(torch.equal(v, ref2.state_dict()[k]) for k, v in a.items())
 
 
+def test_preprocess_oracle_and_rng_match_torchvision():
+    """The oracle restatement of crop/flip/ToTensor/Normalize and the host-side draw of (top, left, flip) reproduce the
+    reference's torchvision Compose (vilmedic/datasets/base/ImageDataset.py:97-104) bit for bit under the same seed."""
+    from oracle.preprocess import crop_flip_normalize, torchvision_train_transform
+    from vilmedic_b200.blocks.vision.preprocess import IMAGENET_MEAN, IMAGENET_STD, GpuImageTransform
+    g = torch.Generator().manual_seed(5)
+    imgs = torch.randint(0, 256, (5, 40, 52, 3), generator=g, dtype=torch.uint8)
+    torch.manual_seed(4)
+    want = torchvision_train_transform(imgs, 32, IMAGENET_MEAN, IMAGENET_STD)
+    torch.manual_seed(4)
+    top, left, flip = GpuImageTransform(crop=32).draw(5, 40, 52)
+    got = crop_flip_normalize(imgs, top, left, flip, 32, IMAGENET_MEAN, IMAGENET_STD)
+    assert flip.sum().item() not in (0, 5), "seed should exercise both flip branches"
+    assert torch.equal(got, want)
+    with pytest.raises(ValueError):
+        GpuImageTransform(crop=64).draw(1, 40, 52)
+
+
 def test_arena_views_groups_and_spans():
     from vilmedic_b200.arena import get_arena
     from vilmedic_b200.models import RRG

@@ -539,3 +539,26 @@ def test_gloria_local_loss(cuda_dev):
     gw, ga = gloria_attention_fn(q.cuda(), ctxt.cuda(), 4.0)
     assert (ga.cpu() - ra).abs().max().item() <= 2e-3
     assert ((gw.cpu() - rw).norm() / rw.norm()).item() <= 1e-2
+
+
+def test_image_crop_flip_normalize_bit_exact(cuda_dev):
+    """On-GPU tail of the reference's train transform (ImageDataset.py:97-104): bit-identical to the CPU oracle (itself pinned
+    to torchvision's Compose in tests/test_cpu.py), ragged crop origins, both flip branches, non-square inputs."""
+    from oracle.preprocess import crop_flip_normalize
+    from vilmedic_b200.blocks.vision.preprocess import IMAGENET_MEAN, IMAGENET_STD, GpuImageTransform
+    g = torch.Generator().manual_seed(3)
+    for (B, H, W, crop) in [(6, 256, 301, 224), (3, 33, 32, 32), (2, 224, 224, 224)]:
+        imgs = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+        t = GpuImageTransform(crop=crop)
+        torch.manual_seed(B)
+        top, left, flip = t.draw(B, H, W)
+        got = t(imgs.pin_memory(), params=(top, left, flip), device=cuda_dev)
+        want = crop_flip_normalize(imgs, top, left, flip, crop, IMAGENET_MEAN, IMAGENET_STD)
+        torch.cuda.synchronize()
+        assert got.shape == want.shape and torch.equal(got.cpu(), want), (B, H, W, crop)
+    ev = GpuImageTransform(crop=32, train=False)
+    x = torch.randint(0, 256, (2, 32, 32, 3), generator=g, dtype=torch.uint8)
+    z = torch.zeros(2, dtype=torch.int32)
+    assert torch.equal(ev(x, device=cuda_dev).cpu(), crop_flip_normalize(x, z, z, z, 32, IMAGENET_MEAN, IMAGENET_STD))
+    with pytest.raises(ValueError):
+        ev(torch.zeros(1, 40, 32, 3, dtype=torch.uint8), device=cuda_dev)

@@ -153,6 +153,30 @@ __global__ void __launch_bounds__(256) colsum8_kernel(const bf16* __restrict__ x
   }
 }
 
+// ---------------------------------------------------------------- input pipeline: crop + flip + ToTensor + Normalize
+// One thread per output pixel (all three channels): the three input bytes of a pixel are adjacent (HWC), the three output
+// planes are written with unit stride along x.  Arithmetic order = torchvision: x.float().div(255) -> sub(mean) -> div(std),
+// with IEEE round-to-nearest division and no FMA contraction, so the result is bit-identical to the CPU transform
+// (vilmedic/datasets/base/ImageDataset.py:97-104).
+__global__ void image_crop_flip_normalize_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, const int* __restrict__ top,
+                                                 const int* __restrict__ left, const uint8_t* __restrict__ flip, int B, int Hin, int Win,
+                                                 int crop, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const long long n = (long long)B * crop * crop;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % crop);
+    const int y = (int)((i / crop) % crop);
+    const int b = (int)(i / ((long long)crop * crop));
+    const int sx = left[b] + (flip[b] ? crop - 1 - x : x);
+    const int sy = top[b] + y;
+    const uint8_t* px = in + (((long long)b * Hin + sy) * Win + sx) * 3;
+    const float r = __fdiv_rn((float)px[0], 255.0f), g = __fdiv_rn((float)px[1], 255.0f), bl = __fdiv_rn((float)px[2], 255.0f);
+    float* o = out + (long long)b * 3 * crop * crop + (long long)y * crop + x;
+    o[0] = __fdiv_rn(__fsub_rn(r, m0), s0);
+    o[(long long)crop * crop] = __fdiv_rn(__fsub_rn(g, m1), s1);
+    o[2LL * crop * crop] = __fdiv_rn(__fsub_rn(bl, m2), s2);
+  }
+}
+
 // ---------------------------------------------------------------- VisualEncoder.encode feature mask
 // mask[r] = (sum_d |f[r,d]| != 0)      (vilmedic/blocks/vision/visual_encoder.py:138)
 __global__ void features_mask_kernel(const bf16* __restrict__ f, uint8_t* __restrict__ mask, int R, int D) {
@@ -334,6 +358,18 @@ extern "C" int vlm_colsum_bf16(const void* x, long long ld, float* out, int M, i
   const int rows_per_block = (M + row_blocks - 1) / row_blocks;
   colsum_kernel<<<dim3(col_blocks, row_blocks), dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, M, N, rows_per_block, scale_ptr);
   return check_launch("colsum");
+}
+
+extern "C" int vlm_image_crop_flip_normalize(const uint8_t* in, float* out, const int* top, const int* left, const uint8_t* flip, int B,
+                                             int Hin, int Win, int crop, const float* mean3, const float* std3, void* stream) {
+  VLM_REQUIRE(in && out && top && left && flip && mean3 && std3, "vlm_image_crop_flip_normalize: null pointer");
+  VLM_REQUIRE(B > 0 && crop > 0 && Hin >= crop && Win >= crop, "vlm_image_crop_flip_normalize: crop %d larger than image %dx%d (B=%d)",
+              crop, Hin, Win, B);
+  VLM_REQUIRE(std3[0] != 0.f && std3[1] != 0.f && std3[2] != 0.f, "vlm_image_crop_flip_normalize: std must be non-zero");
+  const long long n = (long long)B * crop * crop;
+  image_crop_flip_normalize_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, top, left, flip, B, Hin, Win, crop, mean3[0],
+                                                                                     mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+  return check_launch("image_crop_flip_normalize");
 }
 
 extern "C" int vlm_features_mask(const void* feats, uint8_t* mask, int R, int D, void* stream) {

@@ -433,5 +433,21 @@ def gloria_word_softmax_bwd(P1, G, cap_lens, NB, L):
     return dA
 
 
+def image_crop_flip_normalize(images_u8, top, left, flip, crop, mean, std):
+    """images_u8 uint8 [B,H,W,3] (CUDA) + per-image crop origin / flip flag -> fp32 [B,3,crop,crop] (ImageDataset.py:97-104)."""
+    _req(images_u8.is_cuda and images_u8.dtype == torch.uint8 and images_u8.dim() == 4 and images_u8.shape[3] == 3 and
+         images_u8.is_contiguous(), "image_crop_flip_normalize: contiguous CUDA uint8 [B,H,W,3]")
+    B, H, W, _ = images_u8.shape
+    _req(top.dtype == torch.int32 and left.dtype == torch.int32 and flip.dtype == torch.uint8 and top.numel() == B and
+         left.numel() == B and flip.numel() == B and top.is_cuda and left.is_cuda and flip.is_cuda,
+         "image_crop_flip_normalize: top/left int32 [B], flip uint8 [B] on the device")
+    out = torch.empty((B, 3, crop, crop), device=images_u8.device, dtype=torch.float32)
+    m = (ctypes.c_float * 3)(*[float(x) for x in mean])
+    sd = (ctypes.c_float * 3)(*[float(x) for x in std])
+    check(_L().vlm_image_crop_flip_normalize(ptr(images_u8), ptr(out), ptr(top), ptr(left), ptr(flip), c_int(B), c_int(H), c_int(W),
+                                             c_int(crop), m, sd, stream_ptr()), "vlm_image_crop_flip_normalize")
+    return out
+
+
 def rng_advance(counter, delta):
     check(_L().vlm_rng_advance(ptr(counter), c_u64(delta), stream_ptr()), "vlm_rng_advance")
