@@ -200,6 +200,40 @@ int vlm_gloria_region_softmax_bwd(const float* P2, float* G, int NI, int S, long
 int vlm_gloria_word_softmax_bwd(const float* P1, const float* G, void* dA, const int* cap_lens, int rows, int NB, int L,
                                 long long ld, void* stream);
 
+/* ---- CNN backbone pieces (torchvision ResNet-18/50 of vilmedic/blocks/vision/visual_encoder.py:71-83) --
+ * Convolutions = vlm_gemm_bf16 over NHWC bf16 activations [B*H*W, C] (C % 8 == 0) and the im2col matrix
+ * col[m, (kh*KW + kw)*C + c]; weights are packed from torchvision's OIHW fp32 masters into [Cout, Kp] bf16 in the same
+ * (kh, kw, ci) order (Kp = kh*kw*Cin rounded up to 8, zero padded). */
+int vlm_conv_weight_pack(const float* w_oihw, void* wm_bf16, int Cout, int Cin, int KH, int KW, int Kp, void* stream);
+/* gw_oihw[co,ci,kh,kw] += dwm[co, (kh*KW + kw)*Cin + ci]  (dwm fp32 [Cout, Kp] from the wgrad GEMM). */
+int vlm_conv_wgrad_unpack(const float* dwm, float* gw_oihw, int Cout, int Cin, int KH, int KW, int Kp, void* stream);
+/* x bf16 [B,H,W,C] -> col bf16 [B*Ho*Wo, KH*KW*C], Ho = (H + 2 pad - KH)/stride + 1; zero outside the image. */
+int vlm_im2col_nhwc(const void* x, void* col, int B, int H, int W, int C, int KH, int KW, int stride, int pad, void* stream);
+/* Stem: fp32 NCHW images (what the reference's datasets hand over) -> col bf16 [B*Ho*Wo, Kp]. */
+int vlm_im2col_nchw_f32(const float* img, void* col, int B, int Cin, int H, int W, int KH, int KW, int stride, int pad, int Kp,
+                        void* stream);
+/* Transposed gather: dx bf16 [B,H,W,C] = (add or 0) + sum of the dcol entries every input pixel contributed to. */
+int vlm_col2im_nhwc(const void* dcol, const void* add, void* dx, int B, int H, int W, int C, int KH, int KW, int stride, int pad,
+                    void* stream);
+/* nn.BatchNorm2d, training mode, on x bf16 [M = B*H*W, C]: batch statistics (fp32), y = relu?(bn(x) (+ res)), running statistics
+ * updated as torch does (momentum, unbiased variance, num_batches_tracked).  mean/rstd/scale/shift: fp32 [C] outputs (saved for
+ * the backward); sum_ws: fp32 [2C] workspace. */
+int vlm_bn_train_fwd(const void* x, const void* res, void* y, const float* gamma, const float* beta, float* mean, float* rstd,
+                     float* scale, float* shift, float* sum_ws, float* running_mean, float* running_var, long long* num_batches,
+                     int M, int C, float eps, float momentum, int relu, void* stream);
+/* Evaluation mode: running statistics. */
+int vlm_bn_eval_fwd(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* running_mean,
+                    const float* running_var, float* scale, float* shift, int M, int C, float eps, int relu, void* stream);
+/* Backward of relu?(bn(x) (+ res)): g = dy masked by y > 0 (if relu); dx (bf16), dres = g (bf16, optional), dgamma/dbeta +=. */
+int vlm_bn_train_bwd(const void* dy, const void* y, const void* x, const float* mean, const float* rstd, const float* gamma,
+                     float* dgamma, float* dbeta, float* sum_ws, void* dx, void* dres, int M, int C, int relu, void* stream);
+/* nn.MaxPool2d(3, 2, 1) on NHWC bf16; idx uint8 [B*Ho*Wo, C] = window position (kh*3 + kw) of the first maximum (ATen's rule). */
+int vlm_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* idx, int B, int H, int W, int C, void* stream);
+int vlm_maxpool3x3s2_bwd(const void* dy, const uint8_t* idx, void* dx, int B, int H, int W, int C, void* stream);
+/* nn.AdaptiveAvgPool2d((1, 1)): y[b, c] = mean over the HW positions. */
+int vlm_avgpool_fwd(const void* x, void* y, int B, int HW, int C, void* stream);
+int vlm_avgpool_bwd(const void* dy, void* dx, int B, int HW, int C, void* stream);
+
 /* ---- input pipeline (vilmedic/datasets/base/ImageDataset.py:97-104) ------------------------------------ */
 /* RandomCrop + RandomHorizontalFlip + ToTensor + Normalize of the reference's train transform, after its (host-side) Resize:
  * in  uint8 [B, Hin, Win, 3] (HWC, what PIL / numpy hand over; device memory), top/left int32 [B] crop origins,

@@ -194,6 +194,66 @@ def test_preprocess_oracle_and_rng_match_torchvision():
         GpuImageTransform(crop=64).draw(1, 40, 52)
 
 
+@pytest.mark.parametrize("name,output_layer,size,bf16_tol", [("resnet18", "layer4", 64, 5e-2), ("resnet50", "avgpool", 64, None)])
+def test_resnet_runner_host_logic_vs_torchvision(monkeypatch, name, output_layer, size, bf16_tol):
+    """Host logic of vilmedic_b200/cnn.py (execution plan over torchvision's module tree, tape, residual / downsample wiring,
+    weight packing, BatchNorm buffers) with every kernel replaced by its plain-torch specification (tests/cnn_standins.py).
+    With fp32 stand-ins the runner must reproduce torchvision autograd EXACTLY (features, every parameter gradient, BatchNorm
+    running statistics, evaluation mode); with bf16 stand-ins (the kernels' rounding points) the features stay within bf16
+    noise.  The CUDA kernels themselves are checked against the same specifications in tests/test_cnn_gpu.py."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    import cnn_standins
+    import torchvision.models as tvm
+    from vilmedic_b200 import ops
+    from vilmedic_b200.blocks.vision import VisualEncoder
+    cnn_standins.install(monkeypatch, ops)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)      # VisualEncoder moves its inputs itself (RRG.py:28-30)
+
+    def flat(t):
+        t = t.view(*t.shape[:2], -1).permute(0, 2, 1)                          # visual_encoder.py:200-203 (batch_first)
+        return t.squeeze(1) if t.shape[1] == 1 else t
+
+    import copy
+
+    def rel(a, b):
+        return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+    for dt, tol_out in ((torch.float32, 1e-4), (torch.bfloat16, bf16_tol)):
+        if tol_out is None:      # an untrained ResNet-50 on 4 x 64^2 images (16 samples per BN batch at layer4) amplifies bf16
+            continue             # rounding beyond any meaningful bound; the GPU test uses a better conditioned batch
+        monkeypatch.setattr(cnn_standins, "DT", dt)
+        torch.manual_seed(0)
+        enc = VisualEncoder(backbone=name, permute="batch_first", output_layer=output_layer, pretrained=False)
+        assert enc._resnet is not None and "ResNet(sm_100a)" in repr(enc)
+        net = getattr(tvm, name)(weights=None)
+        ref = torch.nn.Sequential(*list(net.children())[:{"layer4": 8, "avgpool": 9}[output_layer]])
+        ref.load_state_dict(enc.model.state_dict(), strict=True)               # identical keys (Sequential indices) and shapes
+        ref64 = copy.deepcopy(ref).double()                                    # ground truth: untrained ResNets with tiny BN
+        x = torch.randn(4, 3, size, size)                                      # batches are ill-conditioned even in fp32
+        enc.train(), ref.train(), ref64.train()
+        out, want, want64 = enc(x), flat(ref(x)), flat(ref64(x.double()))
+        assert out.shape == want.shape and out.dtype == dt
+        assert rel(out, want64) < tol_out
+        if dt == torch.float32:
+            g = torch.randn(out.shape)
+            out.backward(g), want.backward(g), want64.backward(g.double())
+            trip = list(zip(enc.model.named_parameters(), ref.named_parameters(), ref64.named_parameters()))
+            noise = max(rel(q.grad, q64.grad) for _, (_, q), (_, q64) in trip)      # torchvision's own fp32 error vs fp64
+            for (n, p), _, (_, q64) in trip:
+                assert p.grad is not None, n
+                # exact host logic: our fp32 run is as close to the fp64 truth as torchvision's own fp32 run (a wiring bug
+                # shows up as an O(1) error)
+                assert rel(p.grad, q64.grad) <= 3.0 * noise + 1e-3, (n, noise)
+            for (n, b), (_, c) in zip(enc.model.named_buffers(), ref.named_buffers()):
+                assert torch.allclose(b.float(), c.float(), rtol=1e-4, atol=1e-5), n
+            assert int(enc.model[1].num_batches_tracked) == 1
+        enc.eval(), ref64.eval()
+        with torch.no_grad():
+            o2, w2 = enc(x), flat(ref64(x.double()))
+        assert rel(o2, w2) < tol_out
+
+
 def test_arena_views_groups_and_spans():
     from vilmedic_b200.arena import get_arena
     from vilmedic_b200.models import RRG

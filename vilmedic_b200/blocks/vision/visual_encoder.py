@@ -10,8 +10,10 @@ Reference behaviour kept (file:line in /root/reference/vilmedic/blocks/vision/vi
 Reference defects resolved to the intended semantics (SURVEY.md §8 "Reference defects" #3): `num_images` is read from
 the 5-D input (the reference reads it after flattening, i.e. the channel count); `freeze` freezes `self.model`.
 Out of scope here (raise): DeiT / HF-ResNet / PoolFormer / monai 3-D backbones (not in any BASELINE config).
-The CNN backbones (ResNet-18/50, cfg #1/#3) run through torchvision/cuDNN on the GPU for now (interim library path,
-SURVEY.md §8f rank 3); their output feeds the native decoder kernels.
+The torchvision ResNets (ResNet-18/50 of cfg #1/#3; BasicBlock / Bottleneck, groups=1) run on the sm_100a kernels through
+vilmedic_b200/cnn.py (im2col + tcgen05 GEMM convolutions, fused BatchNorm/ReLU/residual, hand-written backward); the
+parameter tree stays torchvision's, so state_dict keys are the reference's.  Other CNN families (DenseNet, ResNeXt) still
+go through torchvision/cuDNN (interim library path) and feed the native decoder kernels.
 """
 import json
 
@@ -68,6 +70,13 @@ class VisualEncoder(nn.Module):
         self.is_vit = "vit" in backbone.lower()
         self.model = get_network(self.backbone, self.output_layer, self.pretrained and not self.is_vit, **kwargs)
         self.dropout_out = nn.Dropout(p=dropout_out)
+        self._resnet = None
+        if not self.is_vit:
+            from ...cnn import ResNetRunner
+            try:                                  # ResNet-18/34/50/101/152 run on the kernels; other CNN families stay interim
+                object.__setattr__(self, "_resnet", ResNetRunner(self.model, self))
+            except NotImplementedError:
+                object.__setattr__(self, "_resnet", None)
         self.is3D = "3d" in backbone
         self.slice_encode = slice_encode
         self.slice_dim = slice_dim
@@ -135,7 +144,10 @@ class VisualEncoder(nn.Module):
             if p > 0 and self.training and torch.is_grad_enabled():
                 out = DropoutFn.apply(out.contiguous(), p)
             return out
-        # interim CNN path (torchvision / cuDNN); output handed to the native kernels as bf16
+        if self._resnet is not None:
+            return self._forward_resnet(images)
+        # interim library path for the remaining CNN families (DenseNet, ResNeXt, ...): torchvision / cuDNN, output handed
+        # to the native kernels as bf16
         out = self.model(images.float())
         out = self.dropout_out(out)
         if self.permute == "no_permute":
@@ -150,6 +162,25 @@ class VisualEncoder(nn.Module):
             raise NotImplementedError()
         return CastBf16Fn.apply(out.contiguous())
 
+    def _forward_resnet(self, images):
+        """torchvision ResNet on the sm_100a kernels (vilmedic_b200/cnn.py).  The kernels work on [B, H*W, C] (NHWC), which IS
+        the reference's `batch_first` layout `out.view(B, C, -1).permute(0, 2, 1)` (:200-203) — no data movement."""
+        from ...cnn import resnet_forward
+        x, (B, H, W, C), pooled = resnet_forward(self._resnet, images, self.training)
+        p = self.dropout_out.p
+        if p > 0 and self.training and torch.is_grad_enabled():
+            pad = (-x.numel()) % 8
+            if pad:
+                raise NotImplementedError("dropout_out needs numel % 8 == 0")
+            x = DropoutFn.apply(x.contiguous(), p)
+        hw = 1 if pooled else H * W
+        if self.permute == "batch_first":
+            return x.view(B, C) if hw == 1 else x.view(B, hw, C)              # squeeze(1) when one position is left (:202-203)
+        x4 = x.view(B, 1, 1, C) if pooled else x.view(B, H, W, C)
+        if self.permute == "no_permute":
+            return x4.permute(0, 3, 1, 2)                                     # NCHW view, as torchvision returns it
+        return x4.reshape(B, hw, C).permute(1, 0, 2)                          # spatial_first
+
     def train(self, mode: bool = True):
         if self.freeze:
             mode = False
@@ -160,7 +191,7 @@ class VisualEncoder(nn.Module):
 
     def __repr__(self):
         repr_dict = {
-            "type": "ViTTower(sm_100a)" if self.is_vit else None,
+            "type": "ViTTower(sm_100a)" if self.is_vit else ("ResNet(sm_100a)" if self._resnet is not None else None),
             "config": str(self.model.config) if self.is_vit else None,
             "dropout_out": self.dropout_out.p,
             "freeze": self.freeze,

@@ -449,5 +449,125 @@ def image_crop_flip_normalize(images_u8, top, left, flip, crop, mean, std):
     return out
 
 
+# ---- CNN backbone pieces (csrc/conv.cu) -----------------------------------------------------------------------------------
+def conv_out_size(H, k, stride, pad):
+    return (H + 2 * pad - k) // stride + 1
+
+
+def conv_weight_pack(w, Kp):
+    """w fp32 OIHW -> bf16 [Cout, Kp] with columns ordered (kh, kw, ci), zero padded to Kp."""
+    Cout, Cin, KH, KW = w.shape
+    _req(w.is_cuda and w.dtype == torch.float32 and w.is_contiguous(), "conv_weight_pack: contiguous CUDA fp32 OIHW")
+    wm = torch.empty((Cout, Kp), device=w.device, dtype=torch.bfloat16)
+    check(_L().vlm_conv_weight_pack(ptr(w), ptr(wm), c_int(Cout), c_int(Cin), c_int(KH), c_int(KW), c_int(Kp), stream_ptr()),
+          "vlm_conv_weight_pack")
+    return wm
+
+
+def conv_wgrad_unpack(dwm, gw):
+    """gw (fp32 OIHW view of the gradient arena) += dwm fp32 [Cout, Kp]."""
+    Cout, Cin, KH, KW = gw.shape
+    _req(dwm.dtype == torch.float32 and dwm.is_contiguous() and gw.dtype == torch.float32 and gw.is_contiguous(), "conv_wgrad_unpack: fp32")
+    check(_L().vlm_conv_wgrad_unpack(ptr(dwm), ptr(gw), c_int(Cout), c_int(Cin), c_int(KH), c_int(KW), c_int(dwm.shape[1]), stream_ptr()),
+          "vlm_conv_wgrad_unpack")
+
+
+def im2col_nhwc(x, B, H, W, C, KH, KW, stride, pad):
+    """x bf16 [B*H*W, C] -> col bf16 [B*Ho*Wo, KH*KW*C]."""
+    _req(_is_bf16_cuda(x) and x.is_contiguous() and x.numel() == B * H * W * C, "im2col_nhwc: contiguous bf16 [B*H*W, C]")
+    Ho, Wo = conv_out_size(H, KH, stride, pad), conv_out_size(W, KW, stride, pad)
+    col = torch.empty((B * Ho * Wo, KH * KW * C), device=x.device, dtype=torch.bfloat16)
+    check(_L().vlm_im2col_nhwc(ptr(x), ptr(col), c_int(B), c_int(H), c_int(W), c_int(C), c_int(KH), c_int(KW), c_int(stride), c_int(pad),
+                               stream_ptr()), "vlm_im2col_nhwc")
+    return col
+
+
+def im2col_nchw_f32(img, KH, KW, stride, pad, Kp):
+    """img fp32 [B,Cin,H,W] -> col bf16 [B*Ho*Wo, Kp] (columns (kh, kw, ci), zero padded)."""
+    _req(img.is_cuda and img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 4, "im2col_nchw_f32: contiguous fp32 NCHW")
+    B, Cin, H, W = img.shape
+    Ho, Wo = conv_out_size(H, KH, stride, pad), conv_out_size(W, KW, stride, pad)
+    col = torch.empty((B * Ho * Wo, Kp), device=img.device, dtype=torch.bfloat16)
+    check(_L().vlm_im2col_nchw_f32(ptr(img), ptr(col), c_int(B), c_int(Cin), c_int(H), c_int(W), c_int(KH), c_int(KW), c_int(stride),
+                                   c_int(pad), c_int(Kp), stream_ptr()), "vlm_im2col_nchw_f32")
+    return col
+
+
+def col2im_nhwc(dcol, B, H, W, C, KH, KW, stride, pad, add=None):
+    """dcol bf16 [B*Ho*Wo, KH*KW*C] -> dx bf16 [B*H*W, C] (+ add)."""
+    _req(_is_bf16_cuda(dcol) and dcol.is_contiguous(), "col2im_nhwc: contiguous bf16")
+    if add is not None:
+        _req(_is_bf16_cuda(add) and add.is_contiguous() and add.numel() == B * H * W * C, "col2im_nhwc: add must be bf16 [B*H*W, C]")
+    dx = torch.empty((B * H * W, C), device=dcol.device, dtype=torch.bfloat16)
+    check(_L().vlm_col2im_nhwc(ptr(dcol), ptr(add), ptr(dx), c_int(B), c_int(H), c_int(W), c_int(C), c_int(KH), c_int(KW), c_int(stride),
+                               c_int(pad), stream_ptr()), "vlm_col2im_nhwc")
+    return dx
+
+
+def bn_train_fwd(x, gamma, beta, running_mean, running_var, num_batches, eps, momentum, relu, res=None):
+    """x bf16 [M,C] -> (y bf16, mean, rstd) with torch.nn.BatchNorm2d training semantics (running buffers updated in place)."""
+    M, C = x.shape
+    _req(_is_bf16_cuda(x) and x.is_contiguous(), "bn_train_fwd: contiguous bf16 [M,C]")
+    y = torch.empty_like(x)
+    mean, rstd, scale, shift = (torch.empty(C, device=x.device, dtype=torch.float32) for _ in range(4))
+    ws = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+    check(_L().vlm_bn_train_fwd(ptr(x), ptr(res), ptr(y), ptr(gamma), ptr(beta), ptr(mean), ptr(rstd), ptr(scale), ptr(shift), ptr(ws),
+                                ptr(running_mean), ptr(running_var), ptr(num_batches), c_int(M), c_int(C), c_float(eps), c_float(momentum),
+                                c_int(int(relu)), stream_ptr()), "vlm_bn_train_fwd")
+    return y, mean, rstd
+
+
+def bn_eval_fwd(x, gamma, beta, running_mean, running_var, eps, relu, res=None):
+    M, C = x.shape
+    _req(_is_bf16_cuda(x) and x.is_contiguous(), "bn_eval_fwd: contiguous bf16 [M,C]")
+    y = torch.empty_like(x)
+    scale, shift = (torch.empty(C, device=x.device, dtype=torch.float32) for _ in range(2))
+    check(_L().vlm_bn_eval_fwd(ptr(x), ptr(res), ptr(y), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(scale), ptr(shift),
+                               c_int(M), c_int(C), c_float(eps), c_int(int(relu)), stream_ptr()), "vlm_bn_eval_fwd")
+    return y
+
+
+def bn_train_bwd(dy, y, x, mean, rstd, gamma, dgamma, dbeta, relu, want_dres):
+    """-> (dx bf16, dres bf16|None); ACCUMULATES into dgamma / dbeta."""
+    M, C = x.shape
+    _req(_is_bf16_cuda(dy) and dy.is_contiguous() and tuple(dy.shape) == (M, C), "bn_train_bwd: dy must be contiguous bf16 [M,C]")
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres else None
+    ws = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+    check(_L().vlm_bn_train_bwd(ptr(dy), ptr(y), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dgamma), ptr(dbeta), ptr(ws), ptr(dx),
+                                ptr(dres), c_int(M), c_int(C), c_int(int(relu)), stream_ptr()), "vlm_bn_train_bwd")
+    return dx, dres
+
+
+def maxpool3x3s2_fwd(x, B, H, W, C):
+    Ho, Wo = conv_out_size(H, 3, 2, 1), conv_out_size(W, 3, 2, 1)
+    _req(_is_bf16_cuda(x) and x.is_contiguous() and x.numel() == B * H * W * C, "maxpool3x3s2_fwd: contiguous bf16 [B*H*W, C]")
+    y = torch.empty((B * Ho * Wo, C), device=x.device, dtype=torch.bfloat16)
+    idx = torch.empty((B * Ho * Wo, C), device=x.device, dtype=torch.uint8)
+    check(_L().vlm_maxpool3x3s2_fwd(ptr(x), ptr(y), ptr(idx), c_int(B), c_int(H), c_int(W), c_int(C), stream_ptr()), "vlm_maxpool3x3s2_fwd")
+    return y, idx
+
+
+def maxpool3x3s2_bwd(dy, idx, B, H, W, C):
+    _req(_is_bf16_cuda(dy) and dy.is_contiguous(), "maxpool3x3s2_bwd: contiguous bf16")
+    dx = torch.empty((B * H * W, C), device=dy.device, dtype=torch.bfloat16)
+    check(_L().vlm_maxpool3x3s2_bwd(ptr(dy), ptr(idx), ptr(dx), c_int(B), c_int(H), c_int(W), c_int(C), stream_ptr()), "vlm_maxpool3x3s2_bwd")
+    return dx
+
+
+def avgpool_fwd(x, B, HW, C):
+    _req(_is_bf16_cuda(x) and x.is_contiguous() and x.numel() == B * HW * C, "avgpool_fwd: contiguous bf16 [B*HW, C]")
+    y = torch.empty((B, C), device=x.device, dtype=torch.bfloat16)
+    check(_L().vlm_avgpool_fwd(ptr(x), ptr(y), c_int(B), c_int(HW), c_int(C), stream_ptr()), "vlm_avgpool_fwd")
+    return y
+
+
+def avgpool_bwd(dy, B, HW, C):
+    _req(_is_bf16_cuda(dy) and dy.is_contiguous() and dy.numel() == B * C, "avgpool_bwd: contiguous bf16 [B, C]")
+    dx = torch.empty((B * HW, C), device=dy.device, dtype=torch.bfloat16)
+    check(_L().vlm_avgpool_bwd(ptr(dy), ptr(dx), c_int(B), c_int(HW), c_int(C), stream_ptr()), "vlm_avgpool_bwd")
+    return dx
+
+
 def rng_advance(counter, delta):
     check(_L().vlm_rng_advance(ptr(counter), c_u64(delta), stream_ptr()), "vlm_rng_advance")
