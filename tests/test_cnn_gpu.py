@@ -1,0 +1,161 @@
+"""CNN backbone: every CUDA kernel of csrc/conv.cu against its plain-torch specification
+(tests/cnn_standins.py), and the ResNet-18 / ResNet-50 towers end to end against torchvision (the module the reference
+instantiates, vilmedic/blocks/vision/visual_encoder.py:71-83)."""
+import copy
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(__file__))
+import cnn_standins as S  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(shape, dev, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).to(dev)
+
+
+def _close(a, b, ulps=2.0, atol=1e-3):
+    a, b = a.float().cpu(), b.float().cpu()
+    bad = (a - b).abs() - (ulps * 2.0 ** -8 * b.abs() + atol)
+    assert bad.max().item() <= 0, "max violation %g" % bad.max().item()
+
+
+def test_conv_weight_pack_unpack_and_im2col_exact(cuda_dev):
+    from vilmedic_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for (Cout, Cin, k) in [(64, 3, 7), (16, 8, 3), (32, 24, 1)]:
+        w = torch.randn(Cout, Cin, k, k, generator=g)
+        Kp = (k * k * Cin + 7) // 8 * 8
+        assert torch.equal(ops.conv_weight_pack(w.to(cuda_dev), Kp).cpu(), S.conv_weight_pack(w, Kp))
+        dwm = torch.randn(Cout, Kp, generator=g)
+        gw, gw_ref = torch.ones(Cout, Cin, k, k, device=cuda_dev), torch.ones(Cout, Cin, k, k)
+        ops.conv_wgrad_unpack(dwm.to(cuda_dev), gw)
+        S.conv_wgrad_unpack(dwm, gw_ref)
+        assert torch.equal(gw.cpu(), gw_ref)
+    for (B, H, W, C, k, s, p) in [(2, 9, 11, 16, 3, 1, 1), (3, 8, 8, 8, 3, 2, 1), (2, 7, 10, 24, 1, 2, 0), (1, 5, 5, 8, 3, 1, 1)]:
+        x = _bf((B * H * W, C), cuda_dev, 1)
+        assert torch.equal(ops.im2col_nhwc(x, B, H, W, C, k, k, s, p).cpu(), S.im2col_nhwc(x.cpu(), B, H, W, C, k, k, s, p))
+        Ho, Wo = S.conv_out_size(H, k, s, p), S.conv_out_size(W, k, s, p)
+        dcol = _bf((B * Ho * Wo, k * k * C), cuda_dev, 2)
+        add = _bf((B * H * W, C), cuda_dev, 3)
+        _close(ops.col2im_nhwc(dcol, B, H, W, C, k, k, s, p), S.col2im_nhwc(dcol.cpu(), B, H, W, C, k, k, s, p))
+        _close(ops.col2im_nhwc(dcol, B, H, W, C, k, k, s, p, add=add), S.col2im_nhwc(dcol.cpu(), B, H, W, C, k, k, s, p, add=add.cpu()))
+    img = torch.randn(2, 3, 37, 41, generator=g)
+    assert torch.equal(ops.im2col_nchw_f32(img.to(cuda_dev), 7, 7, 2, 3, 152).cpu(), S.im2col_nchw_f32(img, 7, 7, 2, 3, 152))
+
+
+@pytest.mark.parametrize("M,C,relu,with_res", [(300, 64, True, False), (1000, 24, False, True), (77, 512, True, True), (4096, 8, True, False)])
+def test_batchnorm_kernels(cuda_dev, M, C, relu, with_res):
+    from vilmedic_b200 import ops
+    g = torch.Generator().manual_seed(M)
+    x = _bf((M, C), cuda_dev, 1, 2.0) + 0.5
+    res = _bf((M, C), cuda_dev, 2) if with_res else None
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    rm, rv, nb = torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.5, torch.tensor(3)
+    rm_d, rv_d, nb_d = rm.to(cuda_dev), rv.to(cuda_dev), nb.to(cuda_dev)
+    y, mean, rstd = ops.bn_train_fwd(x, gamma.to(cuda_dev), beta.to(cuda_dev), rm_d, rv_d, nb_d, 1e-5, 0.1, relu, res)
+    y_r, mean_r, rstd_r = S.bn_train_fwd(x.cpu(), gamma, beta, rm, rv, nb, 1e-5, 0.1, relu, None if res is None else res.cpu())
+    torch.cuda.synchronize()
+    _close(y, y_r)
+    assert torch.allclose(mean.cpu(), mean_r, rtol=1e-4, atol=1e-5) and torch.allclose(rstd.cpu(), rstd_r, rtol=1e-3, atol=1e-5)
+    assert torch.allclose(rm_d.cpu(), rm, rtol=1e-4, atol=1e-5) and torch.allclose(rv_d.cpu(), rv, rtol=1e-3, atol=1e-5)
+    assert int(nb_d) == 4 == int(nb)
+    _close(ops.bn_eval_fwd(x, gamma.to(cuda_dev), beta.to(cuda_dev), rm_d, rv_d, 1e-5, relu, res),
+           S.bn_eval_fwd(x.cpu(), gamma, beta, rm, rv, 1e-5, relu, None if res is None else res.cpu()))
+    dy = _bf((M, C), cuda_dev, 4)
+    dg, db = torch.ones(C, device=cuda_dev), torch.ones(C, device=cuda_dev)
+    dg_r, db_r = torch.ones(C), torch.ones(C)
+    # backward from the SAME saved tensors (the specification's), so that only the backward kernels are compared
+    dx, dres = ops.bn_train_bwd(dy, y_r.to(cuda_dev), x, mean_r.to(cuda_dev), rstd_r.to(cuda_dev), gamma.to(cuda_dev), dg, db, relu, with_res)
+    dx_r, dres_r = S.bn_train_bwd(dy.cpu(), y_r, x.cpu(), mean_r, rstd_r, gamma, dg_r, db_r, relu, with_res)
+    torch.cuda.synchronize()
+    _close(dx, dx_r, ulps=3.0, atol=2e-3)
+    if with_res:
+        assert torch.equal(dres.cpu(), dres_r)
+    assert torch.allclose(dg.cpu(), dg_r, rtol=2e-3, atol=2e-2) and torch.allclose(db.cpu(), db_r, rtol=2e-3, atol=2e-2)
+
+
+def test_pooling_kernels(cuda_dev):
+    from vilmedic_b200 import ops
+    for (B, H, W, C) in [(2, 8, 8, 16), (3, 7, 9, 8), (1, 112, 112, 64)]:
+        x = _bf((B * H * W, C), cuda_dev, 5)
+        x = torch.where(x > 0, x, torch.zeros_like(x))            # post-ReLU input: many exact ties at zero
+        y, idx = ops.maxpool3x3s2_fwd(x, B, H, W, C)
+        y_r, idx_r = S.maxpool3x3s2_fwd(x.cpu(), B, H, W, C)
+        assert torch.equal(y.cpu(), y_r)
+        dy = _bf(tuple(y.shape), cuda_dev, 6)
+        _close(ops.maxpool3x3s2_bwd(dy, idx, B, H, W, C), S.maxpool3x3s2_bwd(dy.cpu(), idx_r, B, H, W, C))
+    x = _bf((4 * 49, 512), cuda_dev, 7)
+    _close(ops.avgpool_fwd(x, 4, 49, 512), S.avgpool_fwd(x.cpu(), 4, 49, 512))
+    dy = _bf((4, 512), cuda_dev, 8)
+    _close(ops.avgpool_bwd(dy, 4, 49, 512), S.avgpool_bwd(dy.cpu(), 4, 49, 512))
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _grad_errors(model, ref):
+    rels = []
+    for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+        rels.append(_rel(p.grad, q.grad))
+    return max(rels), sum(rels) / len(rels)
+
+
+@pytest.mark.parametrize("name,output_layer,B,size", [("resnet18", "layer4", 8, 128), ("resnet50", "avgpool", 8, 128)])
+def test_resnet_tower_vs_torchvision(cuda_dev, name, output_layer, B, size):
+    """End to end: VisualEncoder(resnetXX) on the kernels vs the torchvision module the reference builds (fp32, CPU oracle).
+    Evaluation mode (running statistics) is well conditioned: features within bf16 tolerance.  Training mode (batch
+    statistics): bf16 activations through 20-53 BatchNorm backward passes carry 15-30 % gradient noise on a randomly
+    initialised network whatever the implementation (measured: torch's own bf16 autocast of the SAME torchvision module
+    shows the same level), so the tolerance is the repo's model-level policy: within a stated absolute bound
+    AND within 2x of the error torch's bf16 autocast of the oracle makes on the same GPU.  The residual branches are scaled
+    down (last BatchNorm weight of every block = 0.1) so that the comparison is not dominated by chaotic amplification."""
+    from oracle.rrg import OracleVisualEncoder
+    from vilmedic_b200.blocks.vision import VisualEncoder
+    torch.manual_seed(0)
+    ref = OracleVisualEncoder(backbone=name, permute="batch_first", output_layer=output_layer)
+    with torch.no_grad():
+        for m in ref.modules():
+            if hasattr(m, "conv1") and hasattr(m, "bn2"):
+                (m.bn3 if hasattr(m, "conv3") else m.bn2).weight.fill_(0.1)
+            if isinstance(m, torch.nn.BatchNorm2d):                # running statistics that matter in evaluation mode
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+    enc = VisualEncoder(backbone=name, permute="batch_first", output_layer=output_layer, pretrained=False)
+    enc.load_state_dict(ref.state_dict(), strict=True)
+    enc = enc.cuda()
+    amp = copy.deepcopy(ref).cuda()
+    x = torch.randn(B, 3, size, size)
+    # ---- evaluation mode
+    ref.eval(), enc.eval()
+    with torch.no_grad():
+        want, got = ref(x), enc(x)
+    assert got.shape == want.shape and got.dtype == torch.bfloat16
+    assert _rel(got, want) < 3e-2
+    # ---- training mode
+    ref.train(), enc.train(), amp.train()
+    want, got = ref(x), enc(x)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        got_amp = amp(x.cuda())
+    e_out, e_amp = _rel(got, want), _rel(got_amp.float(), want)
+    assert e_out < 6e-2 and e_out <= 2.0 * e_amp + 5e-3, (e_out, e_amp)
+    g = torch.randn(want.shape)
+    want.backward(g)
+    got.backward(g.to(torch.bfloat16).cuda())
+    got_amp.float().backward(g.cuda())
+    torch.cuda.synchronize()
+    (mx, mean), (mx_amp, mean_amp) = _grad_errors(enc, ref), _grad_errors(amp, ref)
+    print("%s gradient rel L2 error vs fp32 oracle: ours max %.3f mean %.3f | torch bf16 autocast max %.3f mean %.3f" % (
+        name, mx, mean, mx_amp, mean_amp))
+    assert mean < 0.35 and mean <= 2.0 * mean_amp + 0.02, (mean, mean_amp)
+    assert mx < 0.6 and mx <= 2.0 * mx_amp + 0.05, (mx, mx_amp)
+    for (n, b), (_, c) in zip(enc.named_buffers(), ref.named_buffers()):
+        assert torch.allclose(b.float().cpu(), c.float(), rtol=3e-2, atol=3e-3), n
