@@ -159,3 +159,32 @@ def test_resnet_tower_vs_torchvision(cuda_dev, name, output_layer, B, size):
     assert mx < 0.6 and mx <= 2.0 * mx_amp + 0.05, (mx, mx_amp)
     for (n, b), (_, c) in zip(enc.named_buffers(), ref.named_buffers()):
         assert torch.allclose(b.float().cpu(), c.float(), rtol=3e-2, atol=3e-3), n
+
+
+def test_rrg_cfg1_resnet18_plumbing(cuda_dev):
+    """BASELINE configs[0] (the reference's CPU-runnable case): RRG = ResNet-18 (output_layer layer4, batch_first,
+    visual_projection 512 -> 768) + 2-layer decoder, 4 images, 32-token reports — now entirely on the kernels.  Loss vs the
+    fp32 oracle (vilmedic/models/rrg/RRG.py:25-41 composition), all gradients finite, state_dict interchangeable."""
+    from oracle.rrg import OracleRRG
+    from vilmedic_b200 import synth
+    from vilmedic_b200.models import RRG
+    torch.manual_seed(0)
+    dec = synth.bert_base_decoder(vocab=500, layers=2, dropout=0.0)
+    cnn = dict(proto="VisualEncoder", backbone="resnet18", output_layer="layer4", permute="batch_first", pretrained=False,
+               visual_projection={"in_features": 512, "out_features": 768})
+    ref_cnn = {k: v for k, v in cnn.items() if k != "pretrained"}
+    ref = OracleRRG(copy.deepcopy(dec), ref_cnn).train()
+    mine = RRG(copy.deepcopy(dec), copy.deepcopy(cnn))
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    mine = mine.cuda().train()
+    assert "ResNet(sm_100a)" in repr(mine.enc)
+    batch = synth.rrg_batch(4, 32, 500)
+    out = mine(**batch)
+    out["loss"].backward()
+    torch.cuda.synchronize()
+    ref_out = ref(batch["input_ids"], batch["attention_mask"], batch["images"])
+    l, lr = out["loss"].item(), ref_out["loss"].item()
+    assert abs(l - lr) <= 3e-2 * abs(lr), (l, lr)
+    for n, p in mine.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    assert mine.enc.model[0].weight.grad.abs().sum().item() > 0          # the stem convolution received a gradient
