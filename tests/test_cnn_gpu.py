@@ -188,3 +188,36 @@ def test_rrg_cfg1_resnet18_plumbing(cuda_dev):
     for n, p in mine.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
     assert mine.enc.model[0].weight.grad.abs().sum().item() > 0          # the stem convolution received a gradient
+
+
+def test_convirt_cfg3_resnet50(cuda_dev):
+    """BASELINE configs[2] composition (config/SELFSUP/convirt-mimic.yml:27-28): ConVIRT = ResNet-50 (output_layer avgpool ->
+    [b, 2048]) + BERT text tower + Linear-ReLU-Linear projections + ConVIRTLoss, image tower on the kernels.  Loss vs the fp32
+    oracle; residual branches scaled as in test_resnet_tower_vs_torchvision (conditioning of an untrained ResNet-50)."""
+    from oracle.models import OracleConVIRT
+    from vilmedic_b200 import synth
+    from vilmedic_b200.models import ConVIRT
+    torch.manual_seed(0)
+    enc = dict(proto=None, add_pooling_layer=True, vocab_size=600, hidden_size=768, num_hidden_layers=2, num_attention_heads=12,
+               intermediate_size=3072, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, max_position_embeddings=64)
+    cnn = dict(proto="VisualEncoder", backbone="resnet50", output_layer="avgpool", permute="batch_first", pretrained=False)
+    proj = dict(visual_embedding_dim=2048, textual_embedding_dim=768, projection_dim=256)
+    loss = dict(proto="ConVIRTLoss", tau=0.1, lambda_=0.75)
+    ref = OracleConVIRT(enc, cnn, proj, loss).train()
+    with torch.no_grad():
+        for m in ref.visual.modules():
+            if hasattr(m, "conv1") and hasattr(m, "bn3"):
+                m.bn3.weight.fill_(0.1)
+    mine = ConVIRT(copy.deepcopy(enc), copy.deepcopy(cnn), copy.deepcopy(proj), copy.deepcopy(loss), forward_batch_size=8)
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    mine = mine.cuda().train()
+    b = synth.rrg_batch(8, 32, 600, image_size=128, seed=11)
+    o_ref = ref(b["input_ids"], b["attention_mask"], b["images"])
+    o = mine(b["input_ids"], b["attention_mask"], b["images"])
+    o["loss"].backward()
+    torch.cuda.synchronize()
+    assert _rel(o["visual"], o_ref["visual"]) < 5e-2 and _rel(o["linguistic"], o_ref["linguistic"]) < 3e-2
+    assert abs(o["loss"].item() - o_ref["loss"].item()) <= 3e-2 * abs(o_ref["loss"].item()), (o["loss"].item(), o_ref["loss"].item())
+    for n, p in mine.named_parameters():
+        if "pooler" not in n or p.grad is not None:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), n
