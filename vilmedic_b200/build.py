@@ -33,7 +33,7 @@ def _sources():
 
 def _digest(path):
     h = hashlib.sha1()
-    for dep in [path, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "gemm_epilogue.cuh"),
+    for dep in [path, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "gemm_epilogue.cuh"), os.path.join(CSRC, "gemm_kernel.cuh"),
                 os.path.join(ROOT, "include", "vlm_b200.h")]:
         with open(dep, "rb") as f:
             h.update(f.read())
