@@ -1,10 +1,10 @@
-"""Diagnostic for tests/test_decode_gpu.py: prints the measured bf16-vs-fp32 logit error, the cached-vs-uncached logit
+"""Diagnostic for tests/test_decode_gpu.py (lives under tests/ because it drives the oracle, which only test code may import): prints the measured bf16-vs-fp32 logit error, the cached-vs-uncached logit
 difference and the decision margins (relative to the logit scale) of the oracle's searches.  GPU only; not a test."""
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch  # noqa: E402
 
 import test_decode_gpu as T  # noqa: E402

@@ -61,7 +61,7 @@ class _MineAsOracleModel:
 # oracle's, same bf16-rounded weights, same prefix): if every device logit is within e of the oracle's, a decision whose oracle
 # margin exceeds 2e (+ a small cushion for cached-vs-uncached reduction order) cannot flip — such decisions are "safe" and
 # must match bit for bit; the tolerance on e itself is LOGIT_TOL (measured on B200: 1.2-4.2 % of the logit scale over 66
-# teacher-forced steps with these x3 / x30 scaled weights, which amplify the bf16 rounding of the activations; tools/decode_diag.py).
+# teacher-forced steps with these x3 / x30 scaled weights, which amplify the bf16 rounding of the activations; tests/decode_diag.py).
 LOGIT_TOL = 0.08          # max |device logit - fp32 logit| / max |fp32 logit|
 CUSHION = 2.0 ** -10      # x logit scale
 
