@@ -18,6 +18,7 @@
 // delta = rowsum(dO * O) and lse2 are staged per item by the same threads.  Same math / same dropout stream as the
 // mma.sync kernels in attention.cu (those remain the path for other head dims, longer queries and the forward).
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "vlm_b200.h"
@@ -442,6 +443,411 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (opt-in: VLM_ATTN_BWD_PIPE=1; not yet run on a GPU): software-pipelined variant of the backward for Tq <= 128
+// (decoder self- and cross-attention).  dP^T gets its own TMEM columns [128, 256), Q / dO are double-buffered by item, and
+// the MMA warp issues S^T(t+1) as soon as pass A of tile t has drained the S columns and dP^T(t+1) as soon as pass B has
+// drained the dP columns — so the softmax warps never wait for those two products or for the TMA loads of the next item
+// (profiles/ncu_r1c_gemm_attn_bwd.txt: half of the stall samples of the serial kernel sit on those waits).  The passes and the
+// epilogue are the code of attn_bwd_tc_kernel above, unchanged.
+static constexpr int PIPE_DP_COL = 128;
+
+template <bool DROPOUT>
+struct AtcPipeSmem {
+  static constexpr int Q_BYTES = 128 * 128;
+  static constexpr int KV_BYTES = 128 * 128;
+  static constexpr int PT_BYTES = 2 * 16384;
+  static constexpr int OFF_Q = 0;                           // 2 buffers (item parity)
+  static constexpr int OFF_DO = OFF_Q + 2 * Q_BYTES;        // 2 buffers
+  static constexpr int OFF_K = OFF_DO + 2 * Q_BYTES;        // 2 buffers (tile parity)
+  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;        // 2 buffers
+  static constexpr int OFF_PT = OFF_V + 2 * KV_BYTES;
+  static constexpr int OFF_P2 = OFF_PT + PT_BYTES;
+  static constexpr int OFF_LSE = OFF_P2 + (DROPOUT ? PT_BYTES : 0);   // float [2][128]
+  static constexpr int OFF_DELTA = OFF_LSE + 2 * 128 * 4;             // float [2][128]
+  static constexpr int OFF_BAR = OFF_DELTA + 2 * 128 * 4;
+  static constexpr int NUM_BARS = 15;
+  static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
+};
+
+template <bool DROPOUT>
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, AttnTcParams p) {
+  using S = AtcPipeSmem<DROPOUT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + S::OFF_Q;
+  uint8_t* sDO = smem + S::OFF_DO;
+  uint8_t* sK = smem + S::OFF_K;
+  uint8_t* sV = smem + S::OFF_V;
+  uint8_t* sPT = smem + S::OFF_PT;
+  uint8_t* sP2 = smem + S::OFF_P2;
+  float* sLse = reinterpret_cast<float*>(smem + S::OFF_LSE);
+  float* sDelta = reinterpret_cast<float*>(smem + S::OFF_DELTA);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* qdo_full = bars + 0;   // [2]
+  uint64_t* qdo_empty = bars + 2;  // [2]
+  uint64_t* kv_full = bars + 4;    // [2]
+  uint64_t* kv_empty = bars + 6;   // [2]
+  uint64_t* s_full = bars + 8;
+  uint64_t* p_ready = bars + 9;
+  uint64_t* dp_full = bars + 10;
+  uint64_t* dv_done = bars + 11;
+  uint64_t* ds_ready = bars + 12;
+  uint64_t* out_full = bars + 13;
+  uint64_t* out_free = bars + 14;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + S::NUM_BARS);
+
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nitems = p.B * p.H;
+  const int ntiles = (p.Sk + 127) / 128;
+  const int Nq = p.Nq;                                       // <= 128
+  const int my_items = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int ntot = my_items * ntiles;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_do);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 8);
+    mbar_init(dp_full, 1);
+    mbar_init(dv_done, 1);
+    mbar_init(ds_ready, 8);
+    mbar_init(out_full, 1);
+    mbar_init(out_free, 8);
+    fence_barrier_init();
+  } else if (warp_idx == 1) {
+    tmem_alloc<512>(tmem_ptr_smem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0, t = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        const int b = item / p.H, h = item % p.H;
+        const uint32_t qb = it & 1u;
+        mbar_wait(&qdo_empty[qb], ((it >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&qdo_full[qb], 2u * (uint32_t)Nq * 128u);
+        tma_load_4d(&tm_q, &qdo_full[qb], sQ + qb * S::Q_BYTES, 0, h, 0, b);
+        tma_load_4d(&tm_do, &qdo_full[qb], sDO + qb * S::Q_BYTES, 0, h, 0, b);
+        for (int j = 0; j < ntiles; ++j, ++t) {
+          const uint32_t kb = t & 1u;
+          mbar_wait(&kv_empty[kb], ((t >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&kv_full[kb], 2u * S::KV_BYTES);
+          tma_load_4d(&tm_k, &kv_full[kb], sK + kb * S::KV_BYTES, 0, h, j * 128, b);
+          tma_load_4d(&tm_v, &kv_full[kb], sV + kb * S::KV_BYTES, 0, h, j * 128, b);
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================================== MMA issuer (whole warp runs the loop, one elected lane issues)
+    const bool leader = elect_one();
+    const uint32_t id_s = make_idesc_bf16(128, Nq, false, false);     // S^T, dP^T : K-major x K-major
+    const uint32_t id_dv = make_idesc_bf16(128, 64, false, true);      // dV, dK   : K-major A, MN-major B
+    const uint32_t id_dq = make_idesc_bf16(128, 64, true, true);       // dQ       : MN-major A and B
+    const uint32_t aPT = smem_u32(sPT);
+    const int nq16 = Nq / 16;
+    auto wait_operands = [&](int t) {
+      const uint32_t it = (uint32_t)(t / ntiles);
+      mbar_wait(&kv_full[t & 1], ((uint32_t)t >> 1) & 1u);
+      mbar_wait(&qdo_full[it & 1u], (it >> 1) & 1u);
+      tc_fence_after();
+    };
+    auto issue_s = [&](int t) {        // S^T(t) = K_t Q^T
+      wait_operands(t);
+      if (leader) {
+        const uint32_t aK = smem_u32(sK + (t & 1) * S::KV_BYTES), aQ = smem_u32(sQ + ((t / ntiles) & 1) * S::Q_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + ATC_S_COL, make_smem_desc(aK + k * 32, 16, 1024), make_smem_desc(aQ + k * 32, 16, 1024), id_s, k > 0);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+    };
+    auto issue_dp = [&](int t) {       // dP^T(t) = V_t dO^T
+      wait_operands(t);
+      if (leader) {
+        const uint32_t aV = smem_u32(sV + (t & 1) * S::KV_BYTES), aDO = smem_u32(sDO + ((t / ntiles) & 1) * S::Q_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + PIPE_DP_COL, make_smem_desc(aV + k * 32, 16, 1024), make_smem_desc(aDO + k * 32, 16, 1024), id_s, k > 0);
+        umma_commit(dp_full);
+      }
+      __syncwarp();
+    };
+    if (ntot > 0) {
+      issue_s(0);
+      issue_dp(0);
+    }
+    for (int t = 0; t < ntot; ++t) {
+      const int it = t / ntiles, j = t - it * ntiles;
+      const uint32_t tph = (uint32_t)t & 1u;
+      const uint32_t aK = smem_u32(sK + (t & 1) * S::KV_BYTES);
+      const uint32_t aQ = smem_u32(sQ + (it & 1) * S::Q_BYTES), aDO = smem_u32(sDO + (it & 1) * S::Q_BYTES);
+      mbar_wait(p_ready, tph);
+      mbar_wait(out_free, tph ^ 1u);   // dV / dK / dQ accumulators of the previous tile have been drained
+      tc_fence_after();
+      if (leader) {                    // dV_t = P^T dO
+        for (int k = 0; k < nq16; ++k)
+          umma_bf16(tmem_base + ATC_DV_COL, make_smem_desc(aPT + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    make_smem_desc(aDO + k * 2048, 16384, 1024), id_dv, k > 0);
+        umma_commit(dv_done);
+      }
+      __syncwarp();
+      if (t + 1 < ntot) issue_s(t + 1);          // the S columns were drained by pass A of tile t
+      mbar_wait(ds_ready, tph);
+      tc_fence_after();
+      if (leader) {
+        for (int k = 0; k < nq16; ++k)            // dK_t = dS^T Q
+          umma_bf16(tmem_base + ATC_DK_COL, make_smem_desc(aPT + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    make_smem_desc(aQ + k * 2048, 16384, 1024), id_dv, k > 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)               // dQ += dS K_t (one 128-query block: Nq <= 128)
+          umma_bf16(tmem_base + ATC_DQ_COL, make_smem_desc(aPT + k * 2048, 16384, 1024), make_smem_desc(aK + k * 2048, 16384, 1024),
+                    id_dq, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(out_full);
+        umma_commit(&kv_empty[t & 1]);
+        if (j == ntiles - 1) umma_commit(&qdo_empty[it & 1]);
+      }
+      __syncwarp();
+      if (t + 1 < ntot) issue_dp(t + 1);         // the dP columns were drained by pass B of tile t
+    }
+  } else {
+    // ===================================================== compute warps (256 threads)
+    const int quad = warp_idx & 3;             // TMEM lane quadrant
+    const int half = (warp_idx - 2) >> 2;      // which half of the query columns / output columns
+    const int r = quad * 32 + lane;            // key row inside the tile
+    const int ct = threadIdx.x - 64;           // 0..255
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const unsigned long long off_eff = p.offset + ((DROPOUT && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
+    const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
+    const float inv_keep = DROPOUT ? 1.f / (1.f - p.p_drop) : 1.f;
+    const int half_cols = Nq >> 1;             // multiple of 16
+    const uint32_t pt_row = (uint32_t)(r * 128);   // row offset inside a 64-column atom of the P^T / dS^T tile
+    const uint32_t aPTs = smem_u32(sPT), aP2s = smem_u32(sP2), aLse0 = smem_u32(sLse), aDelta0 = smem_u32(sDelta);   // shared-space addresses
+    const int r7 = r & 7;
+    uint32_t tile_cnt = 0, item_cnt = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++item_cnt) {
+      const int b = item / p.H, h = item % p.H;
+      const uint32_t dkey = attn_drop_key(p.seed, off_eff, item);
+      // ---- per-item staging: lse (log2 units, +inf beyond Tq) and delta = rowsum(dO * O), buffer = item parity (the barrier
+      // of item n+1 orders the reuse of buffer n&1 by item n+2)
+      const uint32_t lb = (item_cnt & 1u) * 128u;
+      const uint32_t aLse = aLse0 + lb * 4u, aDelta = aDelta0 + lb * 4u;
+      if (ct < Nq) {
+        float l2 = INFINITY, dl = 0.f;
+        if (ct < p.Tq) {
+          l2 = p.lse[(long long)item * p.Tq + ct] * 1.4426950408889634f;
+          dl = p.delta[(long long)item * p.Tq + ct];
+        }
+        sLse[lb + ct] = l2;
+        sDelta[lb + ct] = dl;
+      }
+      named_bar_sync(1, 256);
+      for (int j = 0; j < ntiles; ++j, ++tile_cnt) {
+        const uint32_t tph = tile_cnt & 1u;
+        const int kk = j * 128 + r;
+        const bool kvalid = (kk < p.Sk) && (!p.kmask || p.kmask[(long long)b * p.Sk + kk]);
+        // ---------------- pass A: P^T
+        mbar_wait(s_full, tph);
+        tc_fence_after();
+        // causal: query q sees key kk iff kk <= q.  For this warp's key rows [k_lo, k_lo + 31] a 16-query chunk starting at
+        // q0 is fully visible iff q0 >= k_lo + 31 and fully masked iff q0 + 15 < k_lo; only the chunks on the diagonal test
+        // per element.  Key rows that are padding / masked (kvalid == false) produce zeros without any math.
+        const int k_lo = j * 128 + quad * 32;
+        auto pass_a_chunk = [&](const uint32_t* v, int q0) {
+          float pv[16], pd[16];
+          if (kvalid && !(p.causal && q0 + 15 < k_lo)) {
+            float ls[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 t = lds128f(aLse + (uint32_t)((q0 + 4 * i) * 4));
+              ls[4 * i] = t.x; ls[4 * i + 1] = t.y; ls[4 * i + 2] = t.z; ls[4 * i + 3] = t.w;
+            }
+            if (!p.causal || q0 >= k_lo + 31) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -ls[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pv[i] = (kk <= q0 + i) ? ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -ls[i])) : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pv[i] = 0.f;
+          }
+          if (DROPOUT) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pd[i] = attn_drop_rand(dkey, q0 + i, kk, p.Sk) >= thr ? pv[i] * inv_keep : 0.f;
+          }
+          const uint32_t off0 = (uint32_t)((q0 >> 6) * 16384) + pt_row;
+          const int u0 = (q0 & 63) >> 3;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t off = off0 + (uint32_t)(((u0 + u) ^ r7) << 4);
+            uint4 w;
+            if (DROPOUT) {
+              w.x = pack_bf16x2(pd[8 * u + 0], pd[8 * u + 1]); w.y = pack_bf16x2(pd[8 * u + 2], pd[8 * u + 3]);
+              w.z = pack_bf16x2(pd[8 * u + 4], pd[8 * u + 5]); w.w = pack_bf16x2(pd[8 * u + 6], pd[8 * u + 7]);
+              sts128(aPTs + off, w.x, w.y, w.z, w.w);
+            }
+            w.x = pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]); w.y = pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]);
+            w.z = pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]); w.w = pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]);
+            sts128((DROPOUT ? aP2s : aPTs) + off, w.x, w.y, w.z, w.w);
+          }
+        };
+        {  // TMEM loads are software-pipelined: the next chunk is in flight while the current one is processed
+          const int qbase = half * half_cols;
+          uint32_t va[16], vb[16];
+          tmem_ld16(lane_taddr + ATC_S_COL + qbase, va);
+          for (int c = 0; c < half_cols; c += 32) {
+            tmem_ld_wait();
+            if (c + 16 < half_cols) tmem_ld16(lane_taddr + ATC_S_COL + qbase + c + 16, vb);
+            pass_a_chunk(va, qbase + c);
+            if (c + 16 < half_cols) {
+              tmem_ld_wait();
+              if (c + 32 < half_cols) tmem_ld16(lane_taddr + ATC_S_COL + qbase + c + 32, va);
+              pass_a_chunk(vb, qbase + c + 16);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+        // ---------------- pass B: dS^T (in place over P^T)
+        mbar_wait(dp_full, tph);
+        mbar_wait(dv_done, tph);
+        tc_fence_after();
+        // dS^T = P^T * (dP^T - delta) — the softmax scale is applied once per dK / dQ output element in the epilogue instead
+        // of once per score element here.
+        auto pass_b_chunk = [&](const uint32_t* v, int q0) {
+          float dl[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 t = lds128f(aDelta + (uint32_t)((q0 + 4 * i) * 4));
+            dl[4 * i] = t.x; dl[4 * i + 1] = t.y; dl[4 * i + 2] = t.z; dl[4 * i + 3] = t.w;
+          }
+          const uint32_t off0 = (uint32_t)((q0 >> 6) * 16384) + pt_row;
+          const int u0 = (q0 & 63) >> 3;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t off = off0 + (uint32_t)(((u0 + u) ^ r7) << 4);
+            const uint4 pw = lds128u((DROPOUT ? aP2s : aPTs) + off);
+            uint4 kw = pw;
+            if (DROPOUT) kw = lds128u(aPTs + off);   // dropped P: zero <=> dropped (or P == 0)
+            const uint32_t pw4[4] = {pw.x, pw.y, pw.z, pw.w}, kw4[4] = {kw.x, kw.y, kw.z, kw.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 pp = unpack_bf16x2(pw4[e]), kp = unpack_bf16x2(kw4[e]);
+              float d0 = __uint_as_float(v[8 * u + 2 * e]), d1 = __uint_as_float(v[8 * u + 2 * e + 1]);
+              if (DROPOUT) {
+                d0 = kp.x != 0.f ? d0 * inv_keep : 0.f;
+                d1 = kp.y != 0.f ? d1 * inv_keep : 0.f;
+              }
+              ow[e] = pack_bf16x2(pp.x * (d0 - dl[8 * u + 2 * e]), pp.y * (d1 - dl[8 * u + 2 * e + 1]));
+            }
+            sts128(aPTs + off, ow[0], ow[1], ow[2], ow[3]);
+          }
+        };
+        {
+          const int qbase = half * half_cols;
+          uint32_t va[16], vb[16];
+          tmem_ld16(lane_taddr + PIPE_DP_COL + qbase, va);
+          for (int c = 0; c < half_cols; c += 32) {
+            tmem_ld_wait();
+            if (c + 16 < half_cols) tmem_ld16(lane_taddr + PIPE_DP_COL + qbase + c + 16, vb);
+            pass_b_chunk(va, qbase + c);
+            if (c + 16 < half_cols) {
+              tmem_ld_wait();
+              if (c + 32 < half_cols) tmem_ld16(lane_taddr + PIPE_DP_COL + qbase + c + 32, va);
+              pass_b_chunk(vb, qbase + c + 16);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ds_ready);
+        // ---------------- epilogue: dV_j, dK_j (+ dQ after the last key tile)
+        mbar_wait(out_full, tph);
+        tc_fence_after();
+        {
+          uint32_t acc[32];
+          tmem_ld32(lane_taddr + ATC_DV_COL + half * 32, acc);
+          tmem_ld_wait();
+          if (kk < p.Sk) {
+            uint4* dst = reinterpret_cast<uint4*>(p.dv + (long long)b * p.dv_bs + (long long)kk * p.dv_rs + h * 64 + half * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]), __uint_as_float(acc[8 * i + 1])),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3])),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7])));
+          }
+          const float sc = p.scale;          // dS was left unscaled (pass B)
+          tmem_ld32(lane_taddr + ATC_DK_COL + half * 32, acc);
+          tmem_ld_wait();
+          if (kk < p.Sk) {
+            uint4* dst = reinterpret_cast<uint4*>(p.dk + (long long)b * p.dk_bs + (long long)kk * p.dk_rs + h * 64 + half * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]) * sc, __uint_as_float(acc[8 * i + 1]) * sc),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 2]) * sc, __uint_as_float(acc[8 * i + 3]) * sc),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 4]) * sc, __uint_as_float(acc[8 * i + 5]) * sc),
+                                  pack_bf16x2(__uint_as_float(acc[8 * i + 6]) * sc, __uint_as_float(acc[8 * i + 7]) * sc));
+          }
+          if (j == ntiles - 1) {
+            const int q_blocks = (Nq + 127) / 128;
+            for (int mb = 0; mb < q_blocks; ++mb) {
+              tmem_ld32(lane_taddr + ATC_DQ_COL + mb * 64 + half * 32, acc);
+              tmem_ld_wait();
+              const int q = mb * 128 + r;
+              if (q < p.Tq) {
+                uint4* dst = reinterpret_cast<uint4*>(p.dq + (long long)b * p.dq_bs + (long long)q * p.dq_rs + h * 64 + half * 32);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]) * sc, __uint_as_float(acc[8 * i + 1]) * sc),
+                                      pack_bf16x2(__uint_as_float(acc[8 * i + 2]) * sc, __uint_as_float(acc[8 * i + 3]) * sc),
+                                      pack_bf16x2(__uint_as_float(acc[8 * i + 4]) * sc, __uint_as_float(acc[8 * i + 5]) * sc),
+                                      pack_bf16x2(__uint_as_float(acc[8 * i + 6]) * sc, __uint_as_float(acc[8 * i + 7]) * sc));
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(out_free);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+
 // delta[bh, q] = sum_d dO[q, d] * O[q, d]; 8 lanes per row (one 16-byte unit of O and of dO each), 4 rows per warp
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, long long o_bs, long long o_rs, const bf16* __restrict__ d_o,
                                   long long do_bs, long long do_rs, float* __restrict__ delta, int B, int H, int Tq) {
@@ -487,6 +893,27 @@ static int launch_attn_bwd_tc(const CUtensorMap& tq, const CUtensorMap& tk, cons
   return check_launch("attn_bwd_tc");
 }
 
+template <bool DROPOUT>
+static int launch_attn_bwd_tc_pipe(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                                   const AttnTcParams& p, cudaStream_t stream) {
+  using S = AtcPipeSmem<DROPOUT>;
+  auto kern = attn_bwd_tc_pipe_kernel<DROPOUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (err != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn_bwd_tc_pipe smem=%d): %s", S::TOTAL, cudaGetErrorString(err));
+      return -1;
+    }
+    attr_set = true;
+  }
+  const int items = p.B * p.H;
+  const int grid = items < num_sms() ? items : num_sms();
+  kern<<<grid, ATC_THREADS, S::TOTAL, stream>>>(tq, tk, tv, tdo, p);
+  return check_launch("attn_bwd_tc_pipe");
+}
+
+
 // returns 1 if the shape is handled by the tcgen05 kernel (and it was launched), 0 if not supported, <0 on error
 int attention_bwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                               const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
@@ -526,7 +953,12 @@ int attention_bwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
   p.lse = lse; p.kmask = kmask; p.B = B; p.H = H; p.Tq = Tq; p.Sk = Sk; p.Nq = Nq; p.causal = causal;
   p.scale = scale; p.p_drop = p_drop; p.seed = seed; p.offset = offset; p.offset_ptr = rng_offset_ptr;
   int rc;
-  if (p_drop > 0.f) rc = launch_attn_bwd_tc<2, true>(tq, tk, tv, tdo, p, stream);
+  static const bool pipe = [] {          // EXPERIMENTAL opt-in, see attn_bwd_tc_pipe_kernel
+    const char* v = getenv("VLM_ATTN_BWD_PIPE");
+    return v && v[0] == '1';
+  }();
+  if (pipe && Nq <= 128) rc = p_drop > 0.f ? launch_attn_bwd_tc_pipe<true>(tq, tk, tv, tdo, p, stream) : launch_attn_bwd_tc_pipe<false>(tq, tk, tv, tdo, p, stream);
+  else if (p_drop > 0.f) rc = launch_attn_bwd_tc<2, true>(tq, tk, tv, tdo, p, stream);
   else if (Nq <= 128) rc = launch_attn_bwd_tc<2, false>(tq, tk, tv, tdo, p, stream);
   else rc = launch_attn_bwd_tc<4, false>(tq, tk, tv, tdo, p, stream);
   return rc ? rc : 1;
