@@ -27,6 +27,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("VLM_GELU_F32X2") == "1":      # experimental packed-fp32x2 GELU epilogue (common.cuh: gelu_erf_both_x2)
+    NVCC_FLAGS = NVCC_FLAGS + ["-DVLM_GELU_F32X2=1"]
+
+
 def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 

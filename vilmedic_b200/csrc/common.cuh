@@ -267,6 +267,29 @@ __device__ __forceinline__ float gelu_erf_both(float x, float& dgelu) {
   return fmaf(-ax, w, fmaxf(x, 0.f));
 }
 
+// EXPERIMENTAL (build with VLM_GELU_F32X2=1 in the environment; not yet run on a GPU): the same evaluation for two elements at
+// a time on the packed fp32x2 FMA pipe of sm_100 (FFMA2 / FMUL2 / FADD2): 13 packed + 10 scalar instructions per pair instead of
+// 2 x 19 scalar ones.  The polynomial carries the sign (wn = -w), so that GELU = fma(|x|, wn, relu(x)).
+__device__ __forceinline__ void gelu_erf_both_x2(float x0, float x1, float& g0, float& g1, float& d0, float& d1) {
+  const float2 x = make_float2(x0, x1);
+  const float2 ax = make_float2(fabsf(x0), fabsf(x1));
+  const float2 one = make_float2(1.0f, 1.0f), half = make_float2(0.5f, 0.5f);
+  const float2 den = __ffma2_rn(ax, make_float2(0.3275911f * 0.70710678118654752f, 0.3275911f * 0.70710678118654752f), one);
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  float2 q = __ffma2_rn(make_float2(-0.5f * 1.061405429f, -0.5f * 1.061405429f), t, make_float2(0.5f * 1.453152027f, 0.5f * 1.453152027f));
+  q = __ffma2_rn(q, t, make_float2(-0.5f * 1.421413741f, -0.5f * 1.421413741f));
+  q = __ffma2_rn(q, t, make_float2(0.5f * 0.284496736f, 0.5f * 0.284496736f));
+  q = __ffma2_rn(q, t, make_float2(-0.5f * 0.254829592f, -0.5f * 0.254829592f));
+  const float2 arg = __fmul2_rn(__fmul2_rn(ax, ax), make_float2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f));
+  const float2 e = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
+  const float2 wn = __fmul2_rn(__fmul2_rn(q, t), e);                            // -0.5 (1 - erf(|x| / sqrt 2))
+  const float2 g = __ffma2_rn(ax, wn, make_float2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+  const float2 hp = __fadd2_rn(half, wn);                                       // 0.5 - w
+  const float2 cdf = __fadd2_rn(make_float2(copysignf(hp.x, x0), copysignf(hp.y, x1)), half);
+  const float2 d = __ffma2_rn(__fmul2_rn(x, make_float2(0.39894228040143268f, 0.39894228040143268f)), e, cdf);
+  g0 = g.x; g1 = g.y; d0 = d.x; d1 = d.y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

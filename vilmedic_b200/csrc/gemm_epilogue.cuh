@@ -330,8 +330,12 @@ __device__ __forceinline__ void epilogue_span_fast(uint32_t taddr, int row, int 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float d0, d1;
+#if defined(VLM_GELU_F32X2) && VLM_GELU_F32X2
+          gelu_erf_both_x2(v[2 * j], v[2 * j + 1], v[2 * j], v[2 * j + 1], d0, d1);
+#else
           v[2 * j] = gelu_erf_both(v[2 * j], d0);
           v[2 * j + 1] = gelu_erf_both(v[2 * j + 1], d1);
+#endif
           stashed[8 * h + j] = pack_bf16x2(d0, d1);
         }
       } else {
