@@ -287,11 +287,47 @@ def run_ours(args):
         sampler.start()
     ms, last = timed(lambda: devb, args.steps, False)
     trace("resident leg timed: %.2f ms / step" % (ms / args.steps))
+    e2e_note = "inputs copied host -> device at the start of every step"
     if args.quick:
         ms_e2e, last_loss = ms, None
         args.no_roofline = args.no_cpu_baseline = True
     else:
-        ms_e2e, last_loss = timed(host_batch, args.steps, True)
+        prefetch_ok = graphed is not None and os.environ.get("VLM_BENCH_PREFETCH", "1") == "1"
+        if prefetch_ok:
+            try:                      # input pipeline with one batch of look-ahead: step n+1's H2D copy runs under step n
+                graphed.prefetch(host)
+                graphed.replay_prefetched()
+                torch.cuda.synchronize()
+            except Exception as e:    # pragma: no cover - reported in the JSON line, never silent
+                prefetch_ok = False
+                e2e_note += " (prefetch path failed: %s)" % (str(e).splitlines()[0][:120],)
+                torch.cuda.synchronize()
+        if prefetch_ok:
+            def e2e_leg(steps):
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                graphed.prefetch(host)                       # first batch: its copy is inside the timed region too
+                last = None
+                for _ in range(steps):
+                    loss = graphed.replay_prefetched()
+                    graphed.prefetch(host)                   # next step's inputs travel while this step computes
+                    last = loss.item()                       # D2H read of the step's result
+                e1.record()
+                torch.cuda.synchronize()
+                t_ms = e0.elapsed_time(e1)
+                if world > 1:
+                    tt = torch.tensor([t_ms], device=dev)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    t_ms = tt.item()
+                    dist.barrier()
+                return t_ms, last
+            ms_e2e, last_loss = e2e_leg(args.steps)
+            e2e_note = "every step: pinned host -> device copy of the NEXT batch on a copy stream under the current step (one batch of look-ahead), device-to-device hand-over, loss.item()"
+        else:
+            ms_e2e, last_loss = timed(host_batch, args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
     trace("e2e leg timed")
 
@@ -324,7 +360,8 @@ def run_ours(args):
                        "l2": "per-step working set (activations ~4 GB + 1.3 GB weights/grads) >> 126 MB L2; no explicit flush",
                        "launch": graph_note,
                        "loss_last": float(last_loss) if last_loss is not None else None},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                    "how": e2e_note},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,

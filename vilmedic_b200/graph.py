@@ -41,6 +41,32 @@ class GraphedTrainStep:
         self.opt.step(grad_scale=scale)
         return loss
 
+    # ---- input prefetch: the next step's batch travels host -> device on a copy stream while the current step computes ----
+    def prefetch(self, batch):
+        """Start copying `batch` (pinned host tensors) into device staging buffers on a side stream."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._staging = {k: torch.empty_like(v) for k, v in self.static.items() if isinstance(v, torch.Tensor)}
+            self._ready = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._consumed)      # the previous step has finished reading the staging buffers
+            for k, v in batch.items():
+                if isinstance(v, torch.Tensor):
+                    self._staging[k].copy_(v, non_blocking=True)
+            self._ready.record(self._copy_stream)
+
+    def replay_prefetched(self):
+        """Wait for the prefetched batch, move it into the graph's static inputs (device-to-device), replay."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ready)
+        for k, v in self._staging.items():
+            self.static[k].copy_(v, non_blocking=True)
+        self._consumed.record(cur)
+        self.graph.replay()
+        return self.loss
+
     def __call__(self, batch=None):
         """Copy `batch` (host or device tensors) into the static inputs, replay, return the (device) loss tensor."""
         if batch is not None:
