@@ -324,8 +324,14 @@ def run_ours(args):
                     t_ms = tt.item()
                     dist.barrier()
                 return t_ms, last
-            ms_e2e, last_loss = e2e_leg(args.steps)
-            e2e_note = "every step: pinned host -> device copy of the NEXT batch on a copy stream under the current step (one batch of look-ahead), device-to-device hand-over, loss.item()"
+            try:
+                ms_e2e, last_loss = e2e_leg(args.steps)
+                e2e_note = ("every step: pinned host -> device copy of the NEXT batch on a copy stream under the current step "
+                            "(one batch of look-ahead), device-to-device hand-over, loss.item()")
+            except Exception as e:    # pragma: no cover - reported, never silent
+                torch.cuda.synchronize()
+                e2e_note += " (prefetch leg failed: %s)" % (str(e).splitlines()[0][:120],)
+                ms_e2e, last_loss = timed(host_batch, args.steps, True)
         else:
             ms_e2e, last_loss = timed(host_batch, args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
