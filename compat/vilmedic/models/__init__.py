@@ -1,0 +1,1 @@
+from vilmedic_b200.models import MVQA, RRG, RRG_HF, ConVIRT  # noqa: F401

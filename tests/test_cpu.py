@@ -254,6 +254,41 @@ def test_resnet_runner_host_logic_vs_torchvision(monkeypatch, name, output_layer
         assert rel(o2, w2) < tol_out
 
 
+def test_compat_shim_exposes_reference_import_paths():
+    """compat/vilmedic: the names the reference eval()s from `proto:` strings resolve at the reference's own import paths
+     to the sm_100a classes; a config-style eval in the importing module's namespace works as in
+    vilmedic/executors/utils.py:105-110 and vilmedic/models/rrg/RRG.py:20."""
+    import importlib
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "compat"))
+    try:
+        for m in [k for k in sys.modules if k == "vilmedic" or k.startswith("vilmedic.")]:
+            del sys.modules[m]
+        vision = importlib.import_module("vilmedic.blocks.vision")
+        models = importlib.import_module("vilmedic.models")
+        losses = importlib.import_module("vilmedic.blocks.losses")
+        dec = importlib.import_module("vilmedic.blocks.huggingface.decoder.decoder_model")
+        enc = importlib.import_module("vilmedic.blocks.huggingface.encoder.encoder_model")
+        cls = importlib.import_module("vilmedic.blocks.classifier")
+        import vilmedic_b200.blocks.vision as v2
+        import vilmedic_b200.models as m2
+        assert vision.VisualEncoder is v2.VisualEncoder and models.RRG is m2.RRG and models.ConVIRT is m2.ConVIRT
+        assert dec.DecoderModel.__module__.startswith("vilmedic_b200") and enc.EncoderModel.__module__.startswith("vilmedic_b200")
+        assert cls.Classifier.__module__.startswith("vilmedic_b200")
+        ns = {}
+        exec("from vilmedic.models import *\nfrom vilmedic.blocks.vision import *\nfrom vilmedic.blocks.losses import *", ns)
+        for proto in ("RRG", "RRG_HF", "ConVIRT", "MVQA", "VisualEncoder", "ConVIRTLoss", "InfoNCELoss", "GLoRIALoss",
+                      "LabelSmoothingCrossEntropy", "BCEWithLogitsLoss"):
+            assert callable(eval(proto, ns)), proto
+        assert losses.gloria_attention_fn is not None and losses.cosine_similarity is not None
+    finally:
+        sys.path.remove(os.path.join(root, "compat"))
+        for m in [k for k in sys.modules if k == "vilmedic" or k.startswith("vilmedic.")]:
+            del sys.modules[m]
+
+
 def test_arena_views_groups_and_spans():
     from vilmedic_b200.arena import get_arena
     from vilmedic_b200.models import RRG
