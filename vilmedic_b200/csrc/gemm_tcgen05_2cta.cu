@@ -167,6 +167,56 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
+#if defined(VLM_GEMM2_UNIFORM_ISSUE) && VLM_GEMM2_UNIFORM_ISSUE
+    // EXPERIMENTAL (build with VLM_GEMM2_UNIFORM_ISSUE=1; not yet run on a GPU): the issuer of the 1-CTA kernel — the whole warp
+    // runs the loop so that stage / descriptor arithmetic stays on the uniform datapath and one elected lane issues.  The
+    // single-lane loop below costs ~900 cycles of dependent issue latency per k-block (profiles/ncu_gemm_r1_epilogue.txt), more
+    // than the 512 tensor cycles of a 256 x 256 x 64 block — the reason this kernel is slower than the 1-CTA one today.
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * G2_BM, BN, A_MN, B_MN);
+      constexpr uint32_t A_LBO = A_MN ? G2_BK * 128 : 16, B_LBO = B_MN ? G2_BK * 128 : 16;
+      constexpr uint32_t A_KSTEP = A_MN ? 2048 : 32, B_KSTEP = B_MN ? 2048 : 32;
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+      const uint32_t a_lo0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | ((A_LBO >> 4) << 16);
+      const uint32_t b_lo0 = (((smem_u32(smem) + S::A_BYTES) >> 4) & 0x3FFFu) | ((B_LBO >> 4) << 16);
+      const bool issuer = elect_one();
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * (S::STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + (uint32_t)stage * (S::STAGE_BYTES >> 4);
+          if (issuer) {
+#pragma unroll
+            for (int k = 0; k < G2_BK / 16; ++k) {
+              const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(a_lo + k * (A_KSTEP >> 4));
+              const uint64_t db = ((uint64_t)DESC_HI << 32) | (uint64_t)(b_lo + k * (B_KSTEP >> 4));
+              umma_bf16_2cta(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2cta(&empty_bar[stage]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (issuer) umma_commit_2cta(&tmem_full_bar[acc]);
+        __syncwarp();
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+#else
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * G2_BM, BN, A_MN, B_MN);
       constexpr uint32_t A_LBO = A_MN ? G2_BK * 128 : 16, B_LBO = B_MN ? G2_BK * 128 : 16;
@@ -203,6 +253,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         }
       }
     }
+#endif
   } else {
     // ===================== epilogue warps (2..9), both CTAs: own 128 rows =====================
     const int quad = warp_idx & 3;
