@@ -143,7 +143,7 @@ static int pick_bn(int M, int N, int batch, int force_bn) {
 }
 
 int gemm2_dispatch(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, int M, int N, int K,
-                   int bn, const GemmEpilogue& e, cudaStream_t s);
+                   int bn, const GemmEpilogue& e, const CUtensorMap* tc, const CUtensorMap* tx, int mode, cudaStream_t s);
 
 // 0 = 1-CTA kernel, else the N tile (128 | 256) of the 2-CTA kernel.  force_bn >= 1000 forces 2-CTA with bn = force_bn-1000.
 static int pick_2cta(int M, int N, int K, int batch, int force_bn, int bn1) {
@@ -277,7 +277,12 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
     const char* v = getenv("VLM_GEMM_TMA_STORE");
     return !(v && v[0] == '0');
   }();
-  if (tma_store_enabled && bn2 == 0 && !c_is_fp32 && !accumulate && !e.atomic && (ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0 &&
+#if defined(VLM_GEMM2_STAGED) && VLM_GEMM2_STAGED
+  constexpr bool pair_staged = true;    // experimental build: the CTA-pair kernel has the staged epilogue too
+#else
+  constexpr bool pair_staged = false;
+#endif
+  if (tma_store_enabled && (bn2 == 0 || pair_staged) && !c_is_fp32 && !accumulate && !e.atomic && (ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0 &&
       (batch == 1 || (c_batch_stride % 8) == 0)) {
     const uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)batch};
     const uint64_t strides[2] = {(uint64_t)ldc, (uint64_t)(batch > 1 ? c_batch_stride : ldc * (long long)M)};
@@ -300,7 +305,9 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
     if (act == 1 && (residual || p_drop > 0.f)) tma_store = 0;
     if (tma_store) tma_store = act == 1 ? EPI_GELU : (act == 2 ? EPI_GELUGRAD : ((residual || p_drop > 0.f) ? EPI_RESID : EPI_BIAS));
   }
-  if (bn2 != 0) return gemm2_dispatch(a, lda, a_mn_major, b, ldb, b_mn_major, M, N, K, bn2, e, s);
+  if (bn2 != 0)   // CTA pair; the C / aux tensor maps + mode feed its staged epilogue when built with VLM_GEMM2_STAGED=1
+    return gemm2_dispatch(a, lda, a_mn_major, b, ldb, b_mn_major, M, N, K, bn2, e, tma_store ? &tc : nullptr, tma_store ? &tx : nullptr,
+                          tma_store, s);
 
   switch (bn) {
     case 64:

@@ -22,13 +22,26 @@ static constexpr int G2_EPI_WARPS = 8;
 static constexpr int G2_THREADS = 64 + 32 * G2_EPI_WARPS;
 static constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
 
-template <int BN>
+#if defined(VLM_GEMM2_STAGED) && VLM_GEMM2_STAGED
+#define G2_STAGED 1
+#else
+#define G2_STAGED 0
+#endif
+
+// MODE != EPI_GENERIC (only with the build flag VLM_GEMM2_STAGED=1, EXPERIMENTAL / not yet run on a GPU): the staged TMA-store
+// epilogue of the 1-CTA kernel (gemm_epilogue.cuh: epilogue_span_fast) — two 32x32 bf16 staging tiles per epilogue warp and two
+// BN-float bias buffers live behind the operand ring.
+template <int BN, int MODE = EPI_GENERIC>
 struct G2Smem {
+  static constexpr bool FAST = MODE != EPI_GENERIC;
   static constexpr int A_BYTES = G2_BM * G2_BK * 2;            // 16 KB
   static constexpr int B_BYTES = (BN / 2) * G2_BK * 2;         // this CTA's half of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int EXTRA = FAST ? (G2_EPI_WARPS * 2 * 2048 + 2 * BN * 4) : 0;
+  static constexpr int STAGES = (200 * 1024 - EXTRA) / STAGE_BYTES > 8 ? 8 : (200 * 1024 - EXTRA) / STAGE_BYTES;
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BIAS_OFFSET = STG_OFFSET + (FAST ? G2_EPI_WARPS * 2 * 2048 : 0);
+  static constexpr int BAR_OFFSET = BIAS_OFFSET + (FAST ? 2 * BN * 4 : 0);
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
@@ -82,11 +95,12 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar_local_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
-gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
+gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                          const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux, int M, int N,
                           int K, GemmEpilogue epi) {
-  using S = G2Smem<BN>;
+  using S = G2Smem<BN, MODE>;
   constexpr int STAGES = S::STAGES;
   constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
@@ -262,17 +276,80 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     const int c_begin = half * (CHUNKS / 2), c_end = (half + 1) * (CHUNKS / 2);
     int acc = 0;
     uint32_t acc_phase = 0;
+    // ---- staged fast path state (MODE != EPI_GENERIC): see the 1-CTA kernel (gemm_kernel.cuh) for the scheme
+    constexpr int PARTS = G2_EPI_WARPS / 4;                 // epilogue warps per TMEM lane quadrant
+    constexpr int NSP = (CHUNKS + PARTS - 1) / PARTS;       // 32-column spans per warp
+    constexpr bool HAS_PRE = MODE == EPI_GELUGRAD || MODE == EPI_RESID;
+    const int part = half;
+    const uint32_t stg_base = smem_u32(smem + S::STG_OFFSET) + (uint32_t)((warp_idx - 2) * 2 * 2048);
+    uint32_t stg_cnt = 0;
+    const uint32_t sbias_base = smem_u32(smem + S::BIAS_OFFSET);
+    uint4 pre[HAS_PRE ? NSP : 1][4];
+    bool have_pre = false;
+    const bf16* const pre_base = MODE == EPI_GELUGRAD ? epi.aux_in : reinterpret_cast<const bf16*>(epi.residual);
+    const long long pre_ld = MODE == EPI_GELUGRAD ? epi.ld_aux : epi.ldr;
+    auto load_pre = [&](int i, int tm0, int tn0) {
+      const int sp = part * NSP + i;
+      const int prow = tm0 + quad * 32 + lane;
+      if (sp < CHUNKS && prow < M) {
+        const uint4* src = reinterpret_cast<const uint4*>(pre_base + (long long)prow * pre_ld + tn0 + sp * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pre[i][j] = __ldg(src + j);
+      }
+    };
     for (int tile = pair; tile < total_tiles; tile += num_pairs) {
       const int m0 = (tile / n_tiles) * (2 * G2_BM) + (int)rank * G2_BM;
       const int n0 = (tile % n_tiles) * BN;
       GemmEpilogue e = epi;
       if (e.p_drop > 0.f && e.offset_ptr) e.offset += __ldg(e.offset_ptr);
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
       const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      bool fast = false;
+      if constexpr (MODE != EPI_GENERIC) fast = n0 + BN <= N;           // warp-uniform
+      if (fast) {
+        if constexpr (MODE != EPI_GENERIC) {
+          const int ntile = tile + num_pairs;                            // the tile this pair processes next
+          int nm0 = 0, nn0 = 0;
+          bool nfast = false;
+          if (HAS_PRE && pre_base != nullptr && ntile < total_tiles) {
+            nm0 = (ntile / n_tiles) * (2 * G2_BM) + (int)rank * G2_BM;
+            nn0 = (ntile % n_tiles) * BN;
+            nfast = nn0 + BN <= N;
+          }
+          if constexpr (HAS_PRE) {
+            if (pre_base != nullptr && !have_pre) {
+#pragma unroll
+              for (int i = 0; i < NSP; ++i) load_pre(i, m0, n0);
+            }
+          }
+          if (e.bias) {                                                   // bias of this tile -> smem under the mainloop
+            for (int i = threadIdx.x - 64; i < BN; i += 32 * G2_EPI_WARPS)
+              reinterpret_cast<float*>(smem + S::BIAS_OFFSET)[acc * BN + i] = __ldg(e.bias + n0 + i);
+            named_bar_sync(1, 32 * G2_EPI_WARPS);
+          }
+          mbar_wait(&tmem_full_bar[acc], acc_phase);
+          tc_fence_after();
+          const float alpha = e.alpha_ptr ? e.alpha * __ldg(e.alpha_ptr) : e.alpha;
+#pragma unroll
+          for (int i = 0; i < NSP; ++i) {
+            const int sp = part * NSP + i;
+            if (sp < CHUNKS)
+              epilogue_span_fast<MODE, 2>(taddr + sp * 32, row, m0 + quad * 32, n0 + sp * 32, 0, lane, e, alpha, pre[HAS_PRE ? i : 0],
+                                          stg_base, stg_cnt, e.bias ? sbias_base + (uint32_t)((acc * BN + sp * 32) * 4) : 0u, &tmap_c,
+                                          &tmap_aux);
+            if constexpr (HAS_PRE) {
+              if (nfast) load_pre(i, nm0, nn0);
+            }
+          }
+          have_pre = nfast;
+        }
+      } else {
+        have_pre = false;
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) epilogue_chunk<32>(taddr + c * 32, row, n0 + c * 32, M, N, e);
+        for (int c = c_begin; c < c_end; ++c) epilogue_chunk<32>(taddr + c * 32, row, n0 + c * 32, M, N, e);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
@@ -281,6 +358,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         acc_phase ^= 1u;
       }
     }
+    if (MODE != EPI_GENERIC && lane == 0) bulk_wait_all();              // TMA stores complete before the CTA retires
   }
 
   tc_fence_before();
@@ -291,11 +369,11 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpilogue& epi,
-                        cudaStream_t stream) {
-  using S = G2Smem<BN>;
-  auto kern = gemm2_bf16_tcgen05_kernel<BN, A_MN, B_MN>;
+template <int BN, bool A_MN, bool B_MN, int MODE>
+static int launch_gemm2_m(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx, int M, int N, int K,
+                          const GemmEpilogue& epi, cudaStream_t stream) {
+  using S = G2Smem<BN, MODE>;
+  auto kern = gemm2_bf16_tcgen05_kernel<BN, A_MN, B_MN, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -309,13 +387,35 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int
   const long long tiles = (long long)m_tiles * n_tiles;
   const int max_pairs = num_sms() / 2;
   const int pairs = (int)(tiles < max_pairs ? tiles : max_pairs);
-  kern<<<2 * pairs, G2_THREADS, S::TOTAL, stream>>>(ta, tb, M, N, K, epi);
+  kern<<<2 * pairs, G2_THREADS, S::TOTAL, stream>>>(ta, tb, tc, tx, M, N, K, epi);
   return check_launch("gemm2_bf16_tcgen05");
 }
 
-// Entry used by vlm_gemm_bf16 for large non-batched problems.  bn in {128, 256}.
+// mode = EPI_* of the staged epilogue (only honoured when built with VLM_GEMM2_STAGED=1 and for the layouts the 1-CTA kernel
+// specialises: forward bias / GELU / residual, dgrad bias / GELU' / residual), else the generic direct-store epilogue.
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx, int mode, int M, int N,
+                        int K, const GemmEpilogue& epi, cudaStream_t stream) {
+#if G2_STAGED
+  if constexpr (!A_MN && !B_MN) {
+    if (mode == EPI_BIAS) return launch_gemm2_m<BN, A_MN, B_MN, EPI_BIAS>(ta, tb, tc, tx, M, N, K, epi, stream);
+    if (mode == EPI_GELU) return launch_gemm2_m<BN, A_MN, B_MN, EPI_GELU>(ta, tb, tc, tx, M, N, K, epi, stream);
+    if (mode == EPI_RESID) return launch_gemm2_m<BN, A_MN, B_MN, EPI_RESID>(ta, tb, tc, tx, M, N, K, epi, stream);
+  }
+  if constexpr (!A_MN && B_MN) {
+    if (mode == EPI_BIAS) return launch_gemm2_m<BN, A_MN, B_MN, EPI_BIAS>(ta, tb, tc, tx, M, N, K, epi, stream);
+    if (mode == EPI_GELUGRAD) return launch_gemm2_m<BN, A_MN, B_MN, EPI_GELUGRAD>(ta, tb, tc, tx, M, N, K, epi, stream);
+    if (mode == EPI_RESID) return launch_gemm2_m<BN, A_MN, B_MN, EPI_RESID>(ta, tb, tc, tx, M, N, K, epi, stream);
+  }
+#endif
+  (void)mode;
+  return launch_gemm2_m<BN, A_MN, B_MN, EPI_GENERIC>(ta, tb, tc, tx, M, N, K, epi, stream);
+}
+
+// Entry used by vlm_gemm_bf16 for large non-batched problems.  bn in {128, 256}.  tc / tx / mode: C and aux tensor maps + epilogue
+// mode prepared by the caller for the staged epilogue (ignored by the generic path).
 int gemm2_dispatch(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, int M, int N, int K,
-                   int bn, const GemmEpilogue& e, cudaStream_t s) {
+                   int bn, const GemmEpilogue& e, const CUtensorMap* tc_in, const CUtensorMap* tx_in, int mode, cudaStream_t s) {
   CUtensorMap ta, tb;
   if (a_mn) {
     if (make_tmap_bf16(&ta, a, (uint64_t)M, (uint64_t)K, 1, lda, 0, G2_BK)) return -1;
@@ -327,13 +427,16 @@ int gemm2_dispatch(const void* a, long long lda, int a_mn, const void* b, long l
   } else {
     if (make_tmap_bf16(&tb, b, (uint64_t)K, (uint64_t)N, 1, ldb, 0, bn / 2)) return -1;
   }
-#define G2_DISPATCH(BN_)                                                                 \
-  if (a_mn) {                                                                            \
-    if (b_mn) return launch_gemm2<BN_, true, true>(ta, tb, M, N, K, e, s);               \
-    return launch_gemm2<BN_, true, false>(ta, tb, M, N, K, e, s);                        \
-  } else {                                                                               \
-    if (b_mn) return launch_gemm2<BN_, false, true>(ta, tb, M, N, K, e, s);              \
-    return launch_gemm2<BN_, false, false>(ta, tb, M, N, K, e, s);                       \
+  const CUtensorMap& tc = tc_in ? *tc_in : ta;
+  const CUtensorMap& tx = tx_in ? *tx_in : ta;
+  if (!tc_in) mode = EPI_GENERIC;
+#define G2_DISPATCH(BN_)                                                                           \
+  if (a_mn) {                                                                                      \
+    if (b_mn) return launch_gemm2<BN_, true, true>(ta, tb, tc, tx, mode, M, N, K, e, s);           \
+    return launch_gemm2<BN_, true, false>(ta, tb, tc, tx, mode, M, N, K, e, s);                    \
+  } else {                                                                                         \
+    if (b_mn) return launch_gemm2<BN_, false, true>(ta, tb, tc, tx, mode, M, N, K, e, s);          \
+    return launch_gemm2<BN_, false, false>(ta, tb, tc, tx, mode, M, N, K, e, s);                   \
   }
   if (bn == 128) { G2_DISPATCH(128) }
   G2_DISPATCH(256)
