@@ -8,7 +8,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvlmb200.so")
+# VLM_LIB=<path> selects an experimental build variant (vilmedic_b200/build.py, VLM_BUILD_TAG); default: the in-tree library.
+LIB_PATH = os.environ.get("VLM_LIB") or os.path.join(_HERE, "libvlmb200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vlm_b200.h")
 
 _lib = None

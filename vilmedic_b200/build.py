@@ -13,8 +13,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ_DIR = os.path.join(HERE, "_obj")
-LIB_PATH = os.path.join(HERE, "libvlmb200.so")
+# VLM_BUILD_TAG=<tag> builds an experimental variant next to the default library (libvlmb200_<tag>.so, own object dir);
+# select it at run time with VLM_LIB=<path> (see _lib.py).  The default build never carries a tag.
+_TAG = os.environ.get("VLM_BUILD_TAG", "")
+OBJ_DIR = os.path.join(HERE, "_obj" + ("_" + _TAG if _TAG else ""))
+LIB_PATH = os.path.join(HERE, "libvlmb200%s.so" % ("_" + _TAG if _TAG else ""))
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
