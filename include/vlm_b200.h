@@ -252,6 +252,17 @@ int vlm_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, long lo
                    float eps, float weight_decay, int* step_ptr, int increment_step, const float* lr_scale_ptr,
                    float grad_scale, const float* gnorm_sq_ptr, float max_norm, int zero_grad, void* stream);
 
+/* The optimizers the reference's configs select by name (vilmedic/executors/utils.py:81-86 `getattr(torch.optim, name)`;
+ * config/ uses RAdam and Adam): kind 0 = AdamW, 1 = Adam (L2 weight decay), 2 = RAdam (torch defaults: L2 decay, rectified once
+ * rho_t > 5) — torch/optim/{adamw,adam,radam}.py single-tensor semantics over a flat span.  Same fusions as vlm_adamw_step.
+ * Device-side skip instead of the host syncs of vilmedic/executors/trainor.py:109-112: when *loss_ptr or *gnorm_sq_ptr is
+ * NaN/Inf the span is left untouched (gradients still zeroed).  Call vlm_optim_step_begin ONCE per optimizer step before the
+ * span launches: it advances *step_ptr (or bumps *skip_count when the step is skipped). */
+int vlm_optim_step_begin(int* step_ptr, const float* gnorm_sq_ptr, const float* loss_ptr, int* skip_count, void* stream);
+int vlm_optim_step(int kind, float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, const int* step_ptr, const float* lr_scale_ptr, float grad_scale,
+                   const float* gnorm_sq_ptr, float max_norm, const float* loss_ptr, int zero_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

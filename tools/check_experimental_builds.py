@@ -14,8 +14,6 @@ from vilmedic_b200 import build as b  # noqa: E402
 
 CASES = [
     ("packed fp32x2 GELU epilogue", ["-DVLM_GELU_F32X2=1"], ["gemm_tcgen05_bn192.cu"]),
-    ("2-CTA GEMM: warp-uniform issuer + staged epilogue", ["-DVLM_GEMM2_UNIFORM_ISSUE=1", "-DVLM_GEMM2_STAGED=1"],
-     ["gemm_tcgen05_2cta.cu", "gemm_tcgen05.cu"]),
 ]
 
 

@@ -34,14 +34,6 @@ if os.environ.get("VLM_GELU_F32X2") == "1":      # experimental packed-fp32x2 GE
     NVCC_FLAGS = NVCC_FLAGS + ["-DVLM_GELU_F32X2=1"]
 
 
-if os.environ.get("VLM_GEMM2_UNIFORM_ISSUE") == "1":   # experimental warp-uniform MMA issuer of the 2-CTA GEMM
-    NVCC_FLAGS = NVCC_FLAGS + ["-DVLM_GEMM2_UNIFORM_ISSUE=1"]
-
-
-if os.environ.get("VLM_GEMM2_STAGED") == "1":          # experimental staged TMA-store epilogue in the 2-CTA GEMM
-    NVCC_FLAGS = NVCC_FLAGS + ["-DVLM_GEMM2_STAGED=1"]
-
-
 def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 

@@ -296,20 +296,65 @@ __device__ __forceinline__ uint32_t stg_acquire(uint32_t stg_base, uint32_t& stg
   return a;
 }
 
+// Row inputs of a span (the stashed GELU' if MODE == EPI_GELUGRAD, else the residual): 32 rows x 64 bytes.  They are requested ONE
+// SPAN AHEAD with the coalesced mapping "lane l holds the 16-byte unit (l & 3) of rows 8 j + (l >> 2), j = 0..3" (one request touches
+// 8 whole 64-byte row segments instead of 32 quarter-used sectors), kept in 16 registers while the current span is processed, and
+// scattered into the warp's staging tile at the start of their own span, where every lane then reads back its own row.
+// (Round 1 kept a whole tile of row-per-lane inputs in an array filled through a lambda: ptxas placed it in local memory, so every
+// "prefetch" stalled on its own STL — profiles/ncu_r2a_gemm_out_resid.txt: the residual epilogue cost 14 of 33 us on 12608x768x768.)
+struct PreReq {
+  const bf16* base;     // element (row0, col0) of the span, nullptr = no request
+  long long ld;
+  int rows;             // valid rows from row0 on (M - row0), may exceed 32
+  int cols;             // valid columns from col0 on (N - col0), may exceed 32; 16-byte units starting at or beyond it are not read
+};
+__device__ __forceinline__ void pre_issue(uint4 (&pre)[4], const PreReq& rq, int lane) {
+  if (rq.base == nullptr) return;
+  const int r = lane >> 2, c = lane & 3;
+  if (8 * c >= rq.cols) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (8 * j + r < rq.rows) pre[j] = __ldg(reinterpret_cast<const uint4*>(rq.base + (long long)(8 * j + r) * rq.ld) + c);
+}
+
+// `next`: request for the span this warp processes after this one (issued right after this span's own inputs left the registers).
+// `e` is the kernel parameter itself (constant bank): nothing of it is copied into registers ahead of use.
 template <int MODE, int BUFS>
-__device__ __forceinline__ void epilogue_span_fast(uint32_t taddr, int row, int row0, int col0, int batch_idx, int lane,
-                                                   const GemmEpilogue& e, float alpha, const uint4 (&pre)[4], uint32_t stg_base,
-                                                   uint32_t& stg_cnt, uint32_t sbias /* smem address of the span's 32 bias floats, 0 = none */,
+__device__ __forceinline__ void epilogue_span_fast(uint32_t taddr, int row0, int col0, int batch_idx, int lane, const GemmEpilogue& e,
+                                                   float alpha, unsigned long long drop_offset, bool use_pre, uint4 (&pre)[4],
+                                                   const PreReq& next, uint32_t stg_base, uint32_t& stg_cnt,
+                                                   uint32_t sbias /* smem address of the span's 32 bias floats, 0 = none */,
                                                    const CUtensorMap* tmap_c, const CUtensorMap* tmap_aux) {
+  constexpr bool HAS_PRE = MODE == EPI_GELUGRAD || MODE == EPI_RESID;
+  const int row = row0 + lane;
   const bool stash = MODE == EPI_GELU && e.aux_out != nullptr;
   uint32_t stashed[MODE == EPI_GELU ? 16 : 1];
   const uint32_t stg = stg_acquire<BUFS>(stg_base, stg_cnt, lane);
   const uint32_t srow = stg + (uint32_t)lane * 64u;
   const int sw = (lane >> 1) & 3;
+  if constexpr (HAS_PRE) {
+    if (use_pre) {
+      const int r = lane >> 2, c = lane & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = 8 * j + r;
+        sts128(stg + (uint32_t)(rr * 64 + ((c ^ ((rr >> 1) & 3)) << 4)), pre[j].x, pre[j].y, pre[j].z, pre[j].w);
+      }
+      __syncwarp();
+      pre_issue(pre, next, lane);
+    }
+  }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {                 // two 16-column halves
     uint32_t acc[16];
     tmem_ld16(taddr + 16 * h, acc);
+    uint4 pa = make_uint4(0, 0, 0, 0), pb = make_uint4(0, 0, 0, 0);
+    if constexpr (HAS_PRE) {
+      if (use_pre) {
+        pa = lds128u(srow + (uint32_t)(((2 * h) ^ sw) << 4));
+        pb = lds128u(srow + (uint32_t)(((2 * h + 1) ^ sw) << 4));
+      }
+    }
     tmem_ld_wait();
     float v[16];
     if (sbias) {
@@ -343,8 +388,7 @@ __device__ __forceinline__ void epilogue_span_fast(uint32_t taddr, int row, int 
         for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
       }
     }
-    if constexpr (MODE == EPI_GELUGRAD || MODE == EPI_RESID) {
-      const uint4 pa = pre[2 * h], pb = pre[2 * h + 1];
+    if constexpr (HAS_PRE) {
       const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
       if constexpr (MODE == EPI_GELUGRAD) {   // aux_in holds GELU'(pre-activation), stashed by the forward epilogue
 #pragma unroll
@@ -362,14 +406,14 @@ __device__ __forceinline__ void epilogue_span_fast(uint32_t taddr, int row, int 
               ((unsigned long long)row * (unsigned long long)e.drop_ld + (unsigned long long)(col0 + 16 * h)) >> 2;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 r = rng(base + j, e.offset);
+            const uint4 r = rng(base + j, drop_offset);
             v[4 * j + 0] = r.x >= thr ? v[4 * j + 0] * inv_keep : 0.f;
             v[4 * j + 1] = r.y >= thr ? v[4 * j + 1] * inv_keep : 0.f;
             v[4 * j + 2] = r.z >= thr ? v[4 * j + 2] * inv_keep : 0.f;
             v[4 * j + 3] = r.w >= thr ? v[4 * j + 3] * inv_keep : 0.f;
           }
         }
-        if (e.residual) {
+        if (use_pre) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float2 x = unpack_bf16x2(pw[j]);

@@ -200,102 +200,114 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int quad = warp_idx & 3;                 // TMEM lane quadrant this warp may access
     const int part = (warp_idx - 2) >> 2;          // which spans of the tile's columns this warp drains
     constexpr int SPANS = BN / 32;
-    constexpr int STG_BUFS = S::STG_BUFS > 0 ? S::STG_BUFS : 1;
-    const uint32_t stg_base = smem_u32(smem + S::STG_OFFSET) + (uint32_t)((warp_idx - 2) * STG_BUFS * S::STG_BYTES);
-    uint32_t stg_cnt = 0;
-    const uint32_t sbias_base = smem_u32(smem + S::BIAS_OFFSET);
     const unsigned long long rng_add = (epi.p_drop > 0.f && epi.offset_ptr) ? __ldg(epi.offset_ptr) : 0ull;
     int acc = 0;
     uint32_t acc_phase = 0;
-    // Row inputs of the fast path (GELU' argument / residual), one 32-column span each.  They are requested one tile ahead:
-    // slot i is refilled for the NEXT tile as soon as span i of the current tile has consumed it, so the DRAM latency hides
-    // under the rest of this tile's epilogue instead of being exposed at the start of the next one.
-    constexpr int NSP = (SPANS + PARTS - 1) / PARTS;
-    constexpr bool HAS_PRE = MODE == EPI_GELUGRAD || MODE == EPI_RESID;
-    uint4 pre[HAS_PRE ? NSP : 1][4];
-    bool have_pre = false;
-    const bf16* const pre_base = MODE == EPI_GELUGRAD ? epi.aux_in : reinterpret_cast<const bf16*>(epi.residual);
-    const long long pre_ld = MODE == EPI_GELUGRAD ? epi.ld_aux : epi.ldr;
-    const long long pre_bs = MODE == EPI_GELUGRAD ? aux_batch_stride : res_batch_stride;
-    auto load_pre = [&](int i, int tb, int tm0, int tn0) {
-      const int sp = part * NSP + i;       // adjacent spans: a lane's row inputs form whole 128-byte lines
-      const int prow = tm0 + quad * 32 + lane;
-      if (sp < SPANS && prow < M) {
-        const uint4* src = reinterpret_cast<const uint4*>(pre_base + (size_t)tb * pre_bs + (long long)prow * pre_ld + tn0 + sp * 32);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pre[i][j] = __ldg(src + j);
-      }
-    };
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-      const int tile = work % total_tiles, split = work / total_tiles;
-      const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
-      if (kb0 >= kb1) continue;
-      const int b = tile / tiles_per_batch;
-      const int t = tile - b * tiles_per_batch;
-      const int m0 = (t / n_tiles) * GEMM_BM;
-      const int n0 = (t % n_tiles) * BN;
-      GemmEpilogue e = epi;
-      if (split > 0) {  // bias / residual are added once, by the first K split
-        e.bias = nullptr;
-        e.residual = nullptr;
-      }
-      e.offset += rng_add;
-      if (b > 0) {
-        const size_t esz = e.c_fp32 ? 4 : 2;
-        e.c = reinterpret_cast<uint8_t*>(e.c) + (size_t)b * c_batch_stride * esz;
-        if (e.residual) e.residual = reinterpret_cast<const uint8_t*>(e.residual) + (size_t)b * res_batch_stride * esz;
-        if (e.aux_in) e.aux_in += (size_t)b * aux_batch_stride;
-        if (e.aux_out) e.aux_out += (size_t)b * aux_batch_stride;
-      }
-      const int row = m0 + quad * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      // Fast path (MODE != EPI_GENERIC; host guarantees bf16 C by TMA store, split_k == 1): every span of the tile inside N.
-      bool fast = false;
-      if constexpr (MODE != EPI_GENERIC) fast = n0 + BN <= N;           // warp-uniform
-      if (fast) {
-        if constexpr (MODE != EPI_GENERIC) {
-          // the tile this CTA processes next (for the one-tile-ahead input requests)
-          const int nwork = work + gridDim.x;
-          int nb = 0, nm0 = 0, nn0 = 0;
-          bool nfast = false;
-          if (HAS_PRE && pre_base != nullptr && nwork < total_work) {
-            const int ntile = nwork % total_tiles;
-            nb = ntile / tiles_per_batch;
-            const int nt = ntile - nb * tiles_per_batch;
-            nm0 = (nt / n_tiles) * GEMM_BM;
-            nn0 = (nt % n_tiles) * BN;
-            nfast = nn0 + BN <= N;
-          }
-          if constexpr (HAS_PRE) {
-            if (pre_base != nullptr && !have_pre) {                     // first tile of this CTA (or after a ragged tile)
-#pragma unroll
-              for (int i = 0; i < NSP; ++i) load_pre(i, b, m0, n0);
-            }
-          }
-          // bias of this tile -> shared memory (buffer by accumulator parity), while the mainloop of the tile is still running
-          if (e.bias) {
-            for (int i = threadIdx.x - 64; i < BN; i += 128 * PARTS)
-              reinterpret_cast<float*>(smem + S::BIAS_OFFSET)[acc * BN + i] = __ldg(e.bias + n0 + i);
-            named_bar_sync(1, 128 * PARTS);
-          }
-          mbar_wait(&tmem_full_bar[acc], acc_phase);
-          tc_fence_after();
-          const float alpha = e.alpha_ptr ? e.alpha * __ldg(e.alpha_ptr) : e.alpha;
-#pragma unroll
-          for (int i = 0; i < NSP; ++i) {
-            const int sp = part * NSP + i;       // adjacent spans: a lane's row inputs form whole 128-byte lines
-            if (sp < SPANS)
-              epilogue_span_fast<MODE, STG_BUFS>(taddr + sp * 32, row, m0 + quad * 32, n0 + sp * 32, b, lane, e, alpha,
-                                                 pre[HAS_PRE ? i : 0], stg_base, stg_cnt,
-                                                 e.bias ? sbias_base + (uint32_t)((acc * BN + sp * 32) * 4) : 0u, &tmap_c, &tmap_aux);
-            if constexpr (HAS_PRE) {
-              if (nfast) load_pre(i, nb, nm0, nn0);
-            }
-          }
-          have_pre = nfast;
+    if constexpr (MODE != EPI_GENERIC) {
+      // ---- staged path only (host guarantees: bf16 C by TMA store, no accumulation, split_k == 1).  Ragged M / N edges are clipped
+      // by the C / aux tensor maps; bias and row-input reads are guarded.  The kernel carries no direct-store fallback, which keeps
+      // the epilogue warps inside their 128-register budget without spilling the in-flight row inputs.
+      constexpr int STG_BUFS = S::STG_BUFS;
+      constexpr int NSP = (SPANS + PARTS - 1) / PARTS;
+      constexpr bool HAS_PRE = MODE == EPI_GELUGRAD || MODE == EPI_RESID;
+      const uint32_t stg_base = smem_u32(smem + S::STG_OFFSET) + (uint32_t)((warp_idx - 2) * STG_BUFS * S::STG_BYTES);
+      uint32_t stg_cnt = 0;
+      const uint32_t sbias_base = smem_u32(smem + S::BIAS_OFFSET);
+      const unsigned long long drop_off = epi.offset + rng_add;
+      // Row inputs (GELU' argument / residual) are requested one span ahead into 16 registers (gemm_epilogue.cuh: PreReq / pre_issue);
+      // the request for the first span of the NEXT tile is issued under the last span of this one.
+      uint4 pre[4];
+      bool have_pre = false;
+      const bf16* const pre_base = MODE == EPI_GELUGRAD ? epi.aux_in : reinterpret_cast<const bf16*>(epi.residual);
+      const long long pre_ld = MODE == EPI_GELUGRAD ? epi.ld_aux : epi.ldr;
+      const long long pre_bs = MODE == EPI_GELUGRAD ? aux_batch_stride : res_batch_stride;
+      const bool use_pre = HAS_PRE && pre_base != nullptr;
+      const int nv = max(0, min(NSP, SPANS - part * NSP));      // spans of a tile this warp drains
+      auto pre_req = [&](int i, int tb, int tm0, int tn0) {
+        PreReq rq;
+        const int r0 = tm0 + quad * 32, c0 = tn0 + (part * NSP + i) * 32;
+        rq.base = (use_pre && i < nv && c0 < N) ? pre_base + (size_t)tb * pre_bs + (long long)r0 * pre_ld + c0 : nullptr;
+        rq.ld = pre_ld;
+        rq.rows = M - r0;
+        rq.cols = N - c0;
+        return rq;
+      };
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int b = work / tiles_per_batch;
+        const int t = work - b * tiles_per_batch;
+        const int m0 = (t / n_tiles) * GEMM_BM;
+        const int n0 = (t % n_tiles) * BN;
+        // the tile this CTA processes next (its first span's inputs are requested under this tile's last span)
+        const int nwork = work + gridDim.x;
+        int nb = 0, nm0 = 0, nn0 = 0;
+        const bool has_next = use_pre && nwork < total_work;
+        if (has_next) {
+          nb = nwork / tiles_per_batch;
+          const int nt = nwork - nb * tiles_per_batch;
+          nm0 = (nt / n_tiles) * GEMM_BM;
+          nn0 = (nt % n_tiles) * BN;
         }
-      } else {
-        have_pre = false;
+        if constexpr (HAS_PRE) {
+          if (use_pre && !have_pre) pre_issue(pre, pre_req(0, b, m0, n0), lane);   // first tile of this CTA
+        }
+        // bias of this tile -> shared memory (buffer by accumulator parity), while the mainloop of the tile is still running
+        if (epi.bias) {
+          for (int i = threadIdx.x - 64; i < BN; i += 128 * PARTS)
+            reinterpret_cast<float*>(smem + S::BIAS_OFFSET)[acc * BN + i] = (n0 + i < N) ? __ldg(epi.bias + n0 + i) : 0.f;
+          named_bar_sync(1, 128 * PARTS);
+        }
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        const float alpha = epi.alpha_ptr ? epi.alpha * __ldg(epi.alpha_ptr) : epi.alpha;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll
+        for (int i = 0; i < NSP; ++i) {
+          const int sp = part * NSP + i;       // adjacent spans: a warp's row inputs form whole 128-byte lines
+          if (i < nv && n0 + sp * 32 < N) {    // warp-uniform
+            PreReq nx;
+            nx.base = nullptr;
+            if constexpr (HAS_PRE) {
+              if (i + 1 < nv && n0 + (sp + 1) * 32 < N) nx = pre_req(i + 1, b, m0, n0);
+              else if (has_next) nx = pre_req(0, nb, nm0, nn0);
+            }
+            epilogue_span_fast<MODE, STG_BUFS>(taddr + sp * 32, m0 + quad * 32, n0 + sp * 32, b, lane, epi, alpha, drop_off, use_pre, pre, nx,
+                                               stg_base, stg_cnt, epi.bias ? sbias_base + (uint32_t)((acc * BN + sp * 32) * 4) : 0u, &tmap_c,
+                                               &tmap_aux);
+          }
+        }
+        have_pre = has_next;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    } else {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int tile = work % total_tiles, split = work / total_tiles;
+        const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+        if (kb0 >= kb1) continue;
+        const int b = tile / tiles_per_batch;
+        const int t = tile - b * tiles_per_batch;
+        const int m0 = (t / n_tiles) * GEMM_BM;
+        const int n0 = (t % n_tiles) * BN;
+        GemmEpilogue e = epi;
+        if (split > 0) {  // bias / residual are added once, by the first K split
+          e.bias = nullptr;
+          e.residual = nullptr;
+        }
+        e.offset += rng_add;
+        if (b > 0) {
+          const size_t esz = e.c_fp32 ? 4 : 2;
+          e.c = reinterpret_cast<uint8_t*>(e.c) + (size_t)b * c_batch_stride * esz;
+          if (e.residual) e.residual = reinterpret_cast<const uint8_t*>(e.residual) + (size_t)b * res_batch_stride * esz;
+          if (e.aux_in) e.aux_in += (size_t)b * aux_batch_stride;
+          if (e.aux_out) e.aux_out += (size_t)b * aux_batch_stride;
+        }
+        const int row = m0 + quad * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
@@ -305,13 +317,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           epilogue_chunk<16>(taddr + sp * 32, row, col_s, M, N, e);
           epilogue_chunk<16>(taddr + sp * 32 + 16, row, col_s + 16, M, N, e);
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1u;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
       }
     }
     if (tma_store && lane == 0) bulk_wait_all();                     // global writes complete before the CTA retires

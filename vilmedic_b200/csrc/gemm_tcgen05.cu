@@ -277,11 +277,7 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
     const char* v = getenv("VLM_GEMM_TMA_STORE");
     return !(v && v[0] == '0');
   }();
-#if defined(VLM_GEMM2_STAGED) && VLM_GEMM2_STAGED
-  constexpr bool pair_staged = true;    // experimental build: the CTA-pair kernel has the staged epilogue too
-#else
-  constexpr bool pair_staged = false;
-#endif
+  constexpr bool pair_staged = true;    // the CTA-pair kernel has the staged epilogue too
   if (tma_store_enabled && (bn2 == 0 || pair_staged) && !c_is_fp32 && !accumulate && !e.atomic && (ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0 &&
       (batch == 1 || (c_batch_stride % 8) == 0)) {
     const uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)batch};
@@ -305,7 +301,7 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
     if (act == 1 && (residual || p_drop > 0.f)) tma_store = 0;
     if (tma_store) tma_store = act == 1 ? EPI_GELU : (act == 2 ? EPI_GELUGRAD : ((residual || p_drop > 0.f) ? EPI_RESID : EPI_BIAS));
   }
-  if (bn2 != 0)   // CTA pair; the C / aux tensor maps + mode feed its staged epilogue when built with VLM_GEMM2_STAGED=1
+  if (bn2 != 0)   // CTA pair; the C / aux tensor maps + mode feed its staged epilogue
     return gemm2_dispatch(a, lda, a_mn_major, b, ldb, b_mn_major, M, N, K, bn2, e, tma_store ? &tc : nullptr, tma_store ? &tx : nullptr,
                           tma_store, s);
 

@@ -22,15 +22,8 @@ static constexpr int G2_EPI_WARPS = 8;
 static constexpr int G2_THREADS = 64 + 32 * G2_EPI_WARPS;
 static constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
 
-#if defined(VLM_GEMM2_STAGED) && VLM_GEMM2_STAGED
-#define G2_STAGED 1
-#else
-#define G2_STAGED 0
-#endif
-
-// MODE != EPI_GENERIC (only with the build flag VLM_GEMM2_STAGED=1, EXPERIMENTAL / not yet run on a GPU): the staged TMA-store
-// epilogue of the 1-CTA kernel (gemm_epilogue.cuh: epilogue_span_fast) — two 32x32 bf16 staging tiles per epilogue warp and two
-// BN-float bias buffers live behind the operand ring.
+// MODE != EPI_GENERIC: the staged TMA-store epilogue of the 1-CTA kernel (gemm_epilogue.cuh: epilogue_span_fast) — two 32x32 bf16
+// staging tiles per epilogue warp and two BN-float bias buffers live behind the operand ring.
 template <int BN, int MODE = EPI_GENERIC>
 struct G2Smem {
   static constexpr bool FAST = MODE != EPI_GENERIC;
@@ -181,11 +174,8 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-#if defined(VLM_GEMM2_UNIFORM_ISSUE) && VLM_GEMM2_UNIFORM_ISSUE
-    // EXPERIMENTAL (build with VLM_GEMM2_UNIFORM_ISSUE=1; not yet run on a GPU): the issuer of the 1-CTA kernel — the whole warp
-    // runs the loop so that stage / descriptor arithmetic stays on the uniform datapath and one elected lane issues.  The
-    // single-lane loop below costs ~900 cycles of dependent issue latency per k-block (profiles/ncu_gemm_r1_epilogue.txt), more
-    // than the 512 tensor cycles of a 256 x 256 x 64 block — the reason this kernel is slower than the 1-CTA one today.
+    // The whole warp runs the loop so that stage / descriptor arithmetic stays on the uniform datapath and one elected lane issues
+    // (the single-lane loop of round 1 cost ~900 cycles of dependent issue latency per k-block, profiles/ncu_gemm_r1_epilogue.txt).
     if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * G2_BM, BN, A_MN, B_MN);
       constexpr uint32_t A_LBO = A_MN ? G2_BK * 128 : 16, B_LBO = B_MN ? G2_BK * 128 : 16;
@@ -230,132 +220,104 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         }
       }
     }
-#else
-    if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * G2_BM, BN, A_MN, B_MN);
-      constexpr uint32_t A_LBO = A_MN ? G2_BK * 128 : 16, B_LBO = B_MN ? G2_BK * 128 : 16;
-      constexpr uint32_t A_KSTEP = A_MN ? 2048 : 32, B_KSTEP = B_MN ? 2048 : 32;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint32_t sb = sa + S::A_BYTES;
-#pragma unroll
-          for (int k = 0; k < G2_BK / 16; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * A_KSTEP, A_LBO, 1024);
-            const uint64_t db = make_smem_desc(sb + k * B_KSTEP, B_LBO, 1024);
-            umma_bf16_2cta(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit_2cta(&empty_bar[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
-        umma_commit_2cta(&tmem_full_bar[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1u;
-        }
-      }
-    }
-#endif
   } else {
     // ===================== epilogue warps (2..9), both CTAs: own 128 rows =====================
     const int quad = warp_idx & 3;
     const int half = (warp_idx - 2) >> 2;
     constexpr int CHUNKS = BN / 32;
-    const int c_begin = half * (CHUNKS / 2), c_end = (half + 1) * (CHUNKS / 2);
     int acc = 0;
     uint32_t acc_phase = 0;
-    // ---- staged fast path state (MODE != EPI_GENERIC): see the 1-CTA kernel (gemm_kernel.cuh) for the scheme
-    constexpr int PARTS = G2_EPI_WARPS / 4;                 // epilogue warps per TMEM lane quadrant
-    constexpr int NSP = (CHUNKS + PARTS - 1) / PARTS;       // 32-column spans per warp
-    constexpr bool HAS_PRE = MODE == EPI_GELUGRAD || MODE == EPI_RESID;
-    const int part = half;
-    const uint32_t stg_base = smem_u32(smem + S::STG_OFFSET) + (uint32_t)((warp_idx - 2) * 2 * 2048);
-    uint32_t stg_cnt = 0;
-    const uint32_t sbias_base = smem_u32(smem + S::BIAS_OFFSET);
-    uint4 pre[HAS_PRE ? NSP : 1][4];
-    bool have_pre = false;
-    const bf16* const pre_base = MODE == EPI_GELUGRAD ? epi.aux_in : reinterpret_cast<const bf16*>(epi.residual);
-    const long long pre_ld = MODE == EPI_GELUGRAD ? epi.ld_aux : epi.ldr;
-    auto load_pre = [&](int i, int tm0, int tn0) {
-      const int sp = part * NSP + i;
-      const int prow = tm0 + quad * 32 + lane;
-      if (sp < CHUNKS && prow < M) {
-        const uint4* src = reinterpret_cast<const uint4*>(pre_base + (long long)prow * pre_ld + tn0 + sp * 32);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pre[i][j] = __ldg(src + j);
-      }
-    };
-    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
-      const int m0 = (tile / n_tiles) * (2 * G2_BM) + (int)rank * G2_BM;
-      const int n0 = (tile % n_tiles) * BN;
-      GemmEpilogue e = epi;
-      if (e.p_drop > 0.f && e.offset_ptr) e.offset += __ldg(e.offset_ptr);
-      const int row = m0 + quad * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      bool fast = false;
-      if constexpr (MODE != EPI_GENERIC) fast = n0 + BN <= N;           // warp-uniform
-      if (fast) {
-        if constexpr (MODE != EPI_GENERIC) {
-          const int ntile = tile + num_pairs;                            // the tile this pair processes next
-          int nm0 = 0, nn0 = 0;
-          bool nfast = false;
-          if (HAS_PRE && pre_base != nullptr && ntile < total_tiles) {
-            nm0 = (ntile / n_tiles) * (2 * G2_BM) + (int)rank * G2_BM;
-            nn0 = (ntile % n_tiles) * BN;
-            nfast = nn0 + BN <= N;
-          }
-          if constexpr (HAS_PRE) {
-            if (pre_base != nullptr && !have_pre) {
-#pragma unroll
-              for (int i = 0; i < NSP; ++i) load_pre(i, m0, n0);
-            }
-          }
-          if (e.bias) {                                                   // bias of this tile -> smem under the mainloop
-            for (int i = threadIdx.x - 64; i < BN; i += 32 * G2_EPI_WARPS)
-              reinterpret_cast<float*>(smem + S::BIAS_OFFSET)[acc * BN + i] = __ldg(e.bias + n0 + i);
-            named_bar_sync(1, 32 * G2_EPI_WARPS);
-          }
-          mbar_wait(&tmem_full_bar[acc], acc_phase);
-          tc_fence_after();
-          const float alpha = e.alpha_ptr ? e.alpha * __ldg(e.alpha_ptr) : e.alpha;
-#pragma unroll
-          for (int i = 0; i < NSP; ++i) {
-            const int sp = part * NSP + i;
-            if (sp < CHUNKS)
-              epilogue_span_fast<MODE, 2>(taddr + sp * 32, row, m0 + quad * 32, n0 + sp * 32, 0, lane, e, alpha, pre[HAS_PRE ? i : 0],
-                                          stg_base, stg_cnt, e.bias ? sbias_base + (uint32_t)((acc * BN + sp * 32) * 4) : 0u, &tmap_c,
-                                          &tmap_aux);
-            if constexpr (HAS_PRE) {
-              if (nfast) load_pre(i, nm0, nn0);
-            }
-          }
-          have_pre = nfast;
+    if constexpr (MODE != EPI_GENERIC) {
+      // ---- staged path only: see the 1-CTA kernel (gemm_kernel.cuh) for the scheme; ragged edges are clipped by the tensor maps
+      constexpr int PARTS = G2_EPI_WARPS / 4;                 // epilogue warps per TMEM lane quadrant
+      constexpr int NSP = (CHUNKS + PARTS - 1) / PARTS;       // 32-column spans per warp
+      constexpr bool HAS_PRE = MODE == EPI_GELUGRAD || MODE == EPI_RESID;
+      const int part = half;
+      const uint32_t stg_base = smem_u32(smem + S::STG_OFFSET) + (uint32_t)((warp_idx - 2) * 2 * 2048);
+      uint32_t stg_cnt = 0;
+      const uint32_t sbias_base = smem_u32(smem + S::BIAS_OFFSET);
+      const unsigned long long drop_off = epi.offset + ((epi.p_drop > 0.f && epi.offset_ptr) ? __ldg(epi.offset_ptr) : 0ull);
+      uint4 pre[4];                                           // row inputs of the NEXT span (gemm_epilogue.cuh: PreReq / pre_issue)
+      bool have_pre = false;
+      const bf16* const pre_base = MODE == EPI_GELUGRAD ? epi.aux_in : reinterpret_cast<const bf16*>(epi.residual);
+      const long long pre_ld = MODE == EPI_GELUGRAD ? epi.ld_aux : epi.ldr;
+      const bool use_pre = HAS_PRE && pre_base != nullptr;
+      const int nv = max(0, min(NSP, CHUNKS - part * NSP));
+      auto pre_req = [&](int i, int tm0, int tn0) {
+        PreReq rq;
+        const int r0 = tm0 + quad * 32, c0 = tn0 + (part * NSP + i) * 32;
+        rq.base = (use_pre && i < nv && c0 < N) ? pre_base + (long long)r0 * pre_ld + c0 : nullptr;
+        rq.ld = pre_ld;
+        rq.rows = M - r0;
+        rq.cols = N - c0;
+        return rq;
+      };
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        const int m0 = (tile / n_tiles) * (2 * G2_BM) + (int)rank * G2_BM;
+        const int n0 = (tile % n_tiles) * BN;
+        const int ntile = tile + num_pairs;                            // the tile this pair processes next
+        const bool has_next = use_pre && ntile < total_tiles;
+        int nm0 = 0, nn0 = 0;
+        if (has_next) {
+          nm0 = (ntile / n_tiles) * (2 * G2_BM) + (int)rank * G2_BM;
+          nn0 = (ntile % n_tiles) * BN;
         }
-      } else {
-        have_pre = false;
+        if constexpr (HAS_PRE) {
+          if (use_pre && !have_pre) pre_issue(pre, pre_req(0, m0, n0), lane);
+        }
+        if (epi.bias) {                                                 // bias of this tile -> smem under the mainloop
+          for (int i = threadIdx.x - 64; i < BN; i += 32 * G2_EPI_WARPS)
+            reinterpret_cast<float*>(smem + S::BIAS_OFFSET)[acc * BN + i] = (n0 + i < N) ? __ldg(epi.bias + n0 + i) : 0.f;
+          named_bar_sync(1, 32 * G2_EPI_WARPS);
+        }
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        const float alpha = epi.alpha_ptr ? epi.alpha * __ldg(epi.alpha_ptr) : epi.alpha;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll
+        for (int i = 0; i < NSP; ++i) {
+          const int sp = part * NSP + i;
+          if (i < nv && n0 + sp * 32 < N) {
+            PreReq nx;
+            nx.base = nullptr;
+            if constexpr (HAS_PRE) {
+              if (i + 1 < nv && n0 + (sp + 1) * 32 < N) nx = pre_req(i + 1, m0, n0);
+              else if (has_next) nx = pre_req(0, nm0, nn0);
+            }
+            epilogue_span_fast<MODE, 2>(taddr + sp * 32, m0 + quad * 32, n0 + sp * 32, 0, lane, epi, alpha, drop_off, use_pre, pre, nx,
+                                        stg_base, stg_cnt, epi.bias ? sbias_base + (uint32_t)((acc * BN + sp * 32) * 4) : 0u, &tmap_c,
+                                        &tmap_aux);
+          }
+        }
+        have_pre = has_next;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    } else {
+      const int c_begin = half * (CHUNKS / 2), c_end = (half + 1) * (CHUNKS / 2);
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        const int m0 = (tile / n_tiles) * (2 * G2_BM) + (int)rank * G2_BM;
+        const int n0 = (tile % n_tiles) * BN;
+        GemmEpilogue e = epi;
+        if (e.p_drop > 0.f && e.offset_ptr) e.offset += __ldg(e.offset_ptr);
+        const int row = m0 + quad * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) epilogue_chunk<32>(taddr + c * 32, row, n0 + c * 32, M, N, e);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1u;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
       }
     }
     if (MODE != EPI_GENERIC && lane == 0) bulk_wait_all();              // TMA stores complete before the CTA retires
@@ -391,12 +353,11 @@ static int launch_gemm2_m(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   return check_launch("gemm2_bf16_tcgen05");
 }
 
-// mode = EPI_* of the staged epilogue (only honoured when built with VLM_GEMM2_STAGED=1 and for the layouts the 1-CTA kernel
-// specialises: forward bias / GELU / residual, dgrad bias / GELU' / residual), else the generic direct-store epilogue.
+// mode = EPI_* of the staged epilogue (for the layouts the 1-CTA kernel specialises: forward bias / GELU / residual, dgrad bias /
+// GELU' / residual), else the generic direct-store epilogue.
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx, int mode, int M, int N,
                         int K, const GemmEpilogue& epi, cudaStream_t stream) {
-#if G2_STAGED
   if constexpr (!A_MN && !B_MN) {
     if (mode == EPI_BIAS) return launch_gemm2_m<BN, A_MN, B_MN, EPI_BIAS>(ta, tb, tc, tx, M, N, K, epi, stream);
     if (mode == EPI_GELU) return launch_gemm2_m<BN, A_MN, B_MN, EPI_GELU>(ta, tb, tc, tx, M, N, K, epi, stream);
@@ -407,7 +368,6 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
     if (mode == EPI_GELUGRAD) return launch_gemm2_m<BN, A_MN, B_MN, EPI_GELUGRAD>(ta, tb, tc, tx, M, N, K, epi, stream);
     if (mode == EPI_RESID) return launch_gemm2_m<BN, A_MN, B_MN, EPI_RESID>(ta, tb, tc, tx, M, N, K, epi, stream);
   }
-#endif
   (void)mode;
   return launch_gemm2_m<BN, A_MN, B_MN, EPI_GENERIC>(ta, tb, tc, tx, M, N, K, epi, stream);
 }

@@ -29,24 +29,63 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
   }
 }
 
-__global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                             bf16* __restrict__ p_bf16, long long n, float lr, float beta1, float beta2, float eps,
-                             float weight_decay, const int* __restrict__ step_ptr, const float* __restrict__ lr_scale_ptr,
-                             float grad_scale, const float* __restrict__ gnorm_sq_ptr, float max_norm, int zero_grad) {
+// One kernel for the three optimizers the reference's configs name (vilmedic/executors/utils.py:81-86 getattr(torch.optim, name);
+// config/*: RAdam 6x, Adam 3x; AdamW is what the bench uses): KIND 0 = AdamW (decoupled decay), 1 = Adam (L2 decay folded into the
+// gradient), 2 = RAdam (torch.optim.RAdam, decoupled_weight_decay=False: L2 decay; variance rectification once rho_t > 5).
+// Update formulas restate torch/optim/{adamw,adam,radam}.py (_single_tensor_* paths, fp32).
+// Device-side skip (replaces the two host syncs of vilmedic/executors/trainor.py:109-112 `isnan(loss) or isinf(loss)` and
+// GradScaler's found-inf): if *loss_ptr or *gnorm_sq_ptr is not finite the launch leaves p/m/v untouched, still zeroes the
+// gradients and bumps *skip_count; the step counter is only advanced by a step that was applied.
+struct OptimScalars {
+  float lr, beta1, beta2, eps, weight_decay, grad_scale, max_norm;
+};
+
+__device__ __forceinline__ bool optim_skip(const float* loss_ptr, const float* gnorm_sq_ptr) {
+  bool skip = false;
+  if (loss_ptr) skip |= !isfinite(*loss_ptr);
+  if (gnorm_sq_ptr) skip |= !isfinite(*gnorm_sq_ptr);
+  return skip;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, bf16* __restrict__ p_bf16, long long n, OptimScalars sc,
+                                                    const int* __restrict__ step_ptr, const float* __restrict__ lr_scale_ptr,
+                                                    const float* __restrict__ gnorm_sq_ptr, const float* __restrict__ loss_ptr,
+                                                    int zero_grad) {
+  const long long n4 = n / 4;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  if (optim_skip(loss_ptr, gnorm_sq_ptr)) {
+    if (zero_grad)
+      for (long long i = i0; i < n4; i += stride) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   const int step = step_ptr ? *step_ptr : 1;
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2 = 1.f - powf(beta2, (float)step);
-  float lr_eff = lr * (lr_scale_ptr ? *lr_scale_ptr : 1.f);
-  float gs = grad_scale;
-  if (gnorm_sq_ptr && max_norm > 0.f) {
-    const float norm = sqrtf(*gnorm_sq_ptr) * grad_scale;
-    const float coef = max_norm / (norm + 1e-6f);
+  const float beta1 = sc.beta1, beta2 = sc.beta2, eps = sc.eps, wd = sc.weight_decay;
+  const float b1t = powf(beta1, (float)step), b2t = powf(beta2, (float)step);
+  const float bc1 = 1.f - b1t, bc2 = 1.f - b2t;
+  const float lr_eff = sc.lr * (lr_scale_ptr ? *lr_scale_ptr : 1.f);
+  float gs = sc.grad_scale;
+  if (gnorm_sq_ptr && sc.max_norm > 0.f) {
+    const float norm = sqrtf(*gnorm_sq_ptr) * sc.grad_scale;
+    const float coef = sc.max_norm / (norm + 1e-6f);
     if (coef < 1.f) gs *= coef;
   }
   const float step_size = lr_eff / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
-  const long long n4 = n / 4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+  // RAdam rectification (torch/optim/radam.py: rho_inf, rho_t, rect)
+  float rect = 0.f;
+  bool rectified = false;
+  const float sqrt_bc2 = sqrtf(bc2);
+  if (KIND == 2) {
+    const float rho_inf = 2.f / (1.f - beta2) - 1.f;
+    const float rho_t = rho_inf - 2.f * (float)step * b2t / bc2;
+    if (rho_t > 5.f) {
+      rectified = true;
+      rect = sqrtf((rho_t - 4.f) * (rho_t - 2.f) * rho_inf / ((rho_inf - 4.f) * (rho_inf - 2.f) * rho_t));
+    }
+  }
+  for (long long i = i0; i < n4; i += stride) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
     const float4 gv = reinterpret_cast<float4*>(g)[i];
     float4 mv = reinterpret_cast<float4*>(m)[i];
@@ -54,11 +93,21 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
     float* pp = &pv.x; const float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float gj = gp[j] * gs;
+      float gj = gp[j] * gs;
+      if (KIND != 0) gj = fmaf(wd, pp[j], gj);                 // Adam / RAdam: L2 decay folded into the gradient
       mp[j] = beta1 * mp[j] + (1.f - beta1) * gj;
       vp[j] = beta2 * vp[j] + (1.f - beta2) * gj * gj;
-      const float denom = sqrtf(vp[j]) * inv_sqrt_bc2 + eps;
-      pp[j] = pp[j] * (1.f - lr_eff * weight_decay) - step_size * mp[j] / denom;
+      if (KIND == 0) {
+        const float denom = sqrtf(vp[j]) * inv_sqrt_bc2 + eps;
+        pp[j] = pp[j] * (1.f - lr_eff * wd) - step_size * mp[j] / denom;
+      } else if (KIND == 1) {
+        const float denom = sqrtf(vp[j]) * inv_sqrt_bc2 + eps;
+        pp[j] = pp[j] - step_size * mp[j] / denom;
+      } else {
+        const float mhat = mp[j] / bc1;
+        if (rectified) pp[j] = pp[j] - mhat * lr_eff * (sqrt_bc2 / (sqrtf(vp[j]) + eps)) * rect;
+        else pp[j] = pp[j] - mhat * lr_eff;
+      }
     }
     reinterpret_cast<float4*>(p)[i] = pv;
     reinterpret_cast<float4*>(m)[i] = mv;
@@ -73,7 +122,14 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
   }
 }
 
-__global__ void step_inc_kernel(int* step) { *step += 1; }
+// step += 1 unless the step is skipped (then *skip_count += 1)
+__global__ void step_inc_kernel(int* step, const float* gnorm_sq_ptr, const float* loss_ptr, int* skip_count) {
+  if (optim_skip(loss_ptr, gnorm_sq_ptr)) {
+    if (skip_count) *skip_count += 1;
+  } else {
+    *step += 1;
+  }
+}
 
 }  // namespace vlm
 
@@ -89,17 +145,50 @@ extern "C" int vlm_sumsq_f32(const float* g, long long n, float* out, void* stre
   return check_launch("sumsq");
 }
 
+static int optim_launch(int kind, float* p, float* g, float* m, float* v, void* p_bf16, long long n, const OptimScalars& sc,
+                        const int* step_ptr, const float* lr_scale_ptr, const float* gnorm_sq_ptr, const float* loss_ptr,
+                        int zero_grad, cudaStream_t s) {
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (kind == 0)
+    optim_kernel<0><<<(int)blocks, 256, 0, s>>>(p, g, m, v, (bf16*)p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad);
+  else if (kind == 1)
+    optim_kernel<1><<<(int)blocks, 256, 0, s>>>(p, g, m, v, (bf16*)p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad);
+  else
+    optim_kernel<2><<<(int)blocks, 256, 0, s>>>(p, g, m, v, (bf16*)p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad);
+  return check_launch("optim_step");
+}
+
+extern "C" int vlm_optim_step_begin(int* step_ptr, const float* gnorm_sq_ptr, const float* loss_ptr, int* skip_count, void* stream) {
+  VLM_REQUIRE(step_ptr, "vlm_optim_step_begin: null step pointer");
+  step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_ptr, gnorm_sq_ptr, loss_ptr, skip_count);
+  return check_launch("optim_step_begin");
+}
+
+extern "C" int vlm_optim_step(int kind, float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, const int* step_ptr, const float* lr_scale_ptr,
+                              float grad_scale, const float* gnorm_sq_ptr, float max_norm, const float* loss_ptr, int zero_grad,
+                              void* stream) {
+  VLM_REQUIRE(kind >= 0 && kind <= 2, "vlm_optim_step: kind must be 0 (AdamW) | 1 (Adam) | 2 (RAdam)");
+  VLM_REQUIRE(p && g && m && v && n > 0 && n % 4 == 0, "vlm_optim_step: flat buffers must be non-null with n %% 4 == 0");
+  VLM_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
+                  ((uintptr_t)p_bf16 % 8 == 0), "vlm_optim_step: buffers must be 16-byte aligned");
+  OptimScalars sc{lr, beta1, beta2, eps, weight_decay, grad_scale, max_norm};
+  return optim_launch(kind, p, g, m, v, p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad, (cudaStream_t)stream);
+}
+
 extern "C" int vlm_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
                               float beta2, float eps, float weight_decay, int* step_ptr, int increment_step,
                               const float* lr_scale_ptr, float grad_scale, const float* gnorm_sq_ptr, float max_norm,
                               int zero_grad, void* stream) {
   VLM_REQUIRE(p && g && m && v && n > 0 && n % 4 == 0, "vlm_adamw_step: flat buffers must be non-null with n %% 4 == 0");
   cudaStream_t s = (cudaStream_t)stream;
-  if (step_ptr && increment_step) step_inc_kernel<<<1, 1, 0, s>>>(step_ptr);
-  long long blocks = (n / 4 + 255) / 256;
-  const long long cap = (long long)num_sms() * 8;
-  if (blocks > cap) blocks = cap;
-  adamw_kernel<<<(int)blocks, 256, 0, s>>>(p, g, m, v, (bf16*)p_bf16, n, lr, beta1, beta2, eps, weight_decay, step_ptr,
-                                           lr_scale_ptr, grad_scale, gnorm_sq_ptr, max_norm, zero_grad);
-  return check_launch("adamw_step");
+  if (step_ptr && increment_step) {
+    step_inc_kernel<<<1, 1, 0, s>>>(step_ptr, nullptr, nullptr, nullptr);
+    if (check_launch("adamw_step_inc")) return -1;
+  }
+  OptimScalars sc{lr, beta1, beta2, eps, weight_decay, grad_scale, max_norm};
+  return optim_launch(0, p, g, m, v, p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, nullptr, zero_grad, s);
 }

@@ -349,7 +349,8 @@ class ViTTower(nn.Module):
             raise ValueError("Input image size (%d*%d) doesn't match model (%d*%d)." % (
                 pixel_values.shape[2], pixel_values.shape[3], cfg.image_size, cfg.image_size))
         arena = get_arena(_root_of(self))
-        grad = torch.is_grad_enabled()
+        # nothing is saved for a backward that cannot happen (frozen tower: VisualEncoder(freeze=True), visual_encoder.py:124-128)
+        grad = torch.is_grad_enabled() and (pixel_values.requires_grad or any(p.requires_grad for p in self.parameters()))
         _prepare(arena, self)
         anchor = self.layernorm.weight
         images = pixel_values.contiguous().float()
