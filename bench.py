@@ -439,7 +439,13 @@ def gemm_roofline(train_step, batch, ops):
     if os.path.exists(tp):
         traffic = json.load(open(tp))
     achieved = tot_flop / (tot_ms / 1e3) / 1e12 if tot_ms > 0 else 0.0
-    top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:6]
+    ranked = sorted(by_shape.items(), key=lambda kv: -kv[1][1])
+    top = ranked[:6]
+    if os.environ.get("VLM_BENCH_SHAPES"):      # full per-shape table (builder diagnostics, not part of the JSON line)
+        with open(os.environ["VLM_BENCH_SHAPES"], "w") as f:
+            for k, v in ranked:
+                f.write("%-28s n=%3d  %8.3f ms  %7.1f us/launch  %7.1f TF/s\n" % (
+                    "x".join(map(str, k)), v[0], v[1], v[1] * 1e3 / v[0], v[2] / (v[1] / 1e3) / 1e12))
     return {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all launches of one training step)",
             "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
             "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",

@@ -97,14 +97,14 @@ def test_forward_dropout_residual(cuda_dev, M, N, K, p, bn):
     bias = torch.randn(N, device="cuda")
     y = a.float() @ w.float().t() + bias
     if p > 0:
-        keep = ops.dropout(torch.ones(M, N, device="cuda", dtype=torch.bfloat16), p, 77, 5).float()      # 0 or 1/(1-p)
-        frac = (keep == 0).float().mean().item()
+        keep = ops.dropout(torch.ones(M, N, device="cuda", dtype=torch.bfloat16), p, 77, 5) != 0      # the Philox keep mask
+        frac = 1.0 - keep.float().mean().item()
         assert abs(frac - p) < 5e-3
-        y = y * keep
+        y = y * keep.float() * (1.0 / (1.0 - p))
     ref = y + res.float()
     out = ops.gemm(a, w, bias=bias, residual=res, p_drop=p, seed=77, offset=5, force_bn=bn)
     torch.cuda.synchronize()
-    _check(out, ref, "dropout+residual", 2e-5 * K ** 0.5 + (2e-2 if p > 0 else 0.0) * 0)
+    _check(out, ref, "dropout+residual", 2e-5 * K ** 0.5)
     # and the dgrad flavour (B MN-major) with a residual-gradient add
     w2 = _rand((K, N), 10, 0.05)
     dy = _rand((M, K), 11)

@@ -101,15 +101,46 @@ class GenerationMixinB200:
 
     @torch.no_grad()
     def generate(self, input_ids=None, encoder_hidden_states=None, encoder_attention_mask=None, max_length=None,
-                 num_beams=1, bos_token_id=None, eos_token_id=None, pad_token_id=None, length_penalty=1.0,
-                 ensemble=None, use_cache=True, **kwargs):
+                 num_beams=None, bos_token_id=None, eos_token_id=None, pad_token_id=None, length_penalty=None,
+                 ensemble=None, use_cache=True, generation_config=None, **kwargs):
+        """Greedy / beam decoding (ensemble = sum of next-token logits over `ensemble`).  Arguments may come individually or in a
+        HF-style `generation_config` (any object or dict with max_length / num_beams / length_penalty / *_token_id attributes — the
+        call of vilmedic/blocks/huggingface/decoder/evaluation.py:73-78 and vision_multi_evaluation.py:42-57); explicit keyword
+        arguments win, then generation_config, then the model config.  Unknown arguments raise instead of being ignored."""
         from .beam import beam_search
+        gc = generation_config
+
+        def pick(name, explicit, default):
+            if explicit is not None:
+                return explicit
+            if gc is not None:
+                v = gc.get(name) if isinstance(gc, dict) else getattr(gc, name, None)
+                if v is not None:
+                    return v
+            return default
+
+        harmless = {"num_return_sequences": 1, "do_sample": False, "return_dict_in_generate": False, "output_scores": False,
+                    "early_stopping": False, "decoder_start_token_id": None}
+        for k_, v_ in kwargs.items():
+            if k_ not in harmless:
+                raise TypeError("generate() got an unsupported argument %r" % k_)
+            if k_ in ("num_return_sequences", "do_sample", "return_dict_in_generate", "output_scores", "early_stopping") and v_ not in (harmless[k_], None):
+                raise NotImplementedError("generate(%s=%r) is not supported" % (k_, v_))
+        if gc is not None:
+            for k_ in ("do_sample", "early_stopping"):
+                v_ = gc.get(k_) if isinstance(gc, dict) else getattr(gc, k_, None)
+                if v_:
+                    raise NotImplementedError("generation_config.%s=%r is not supported" % (k_, v_))
+            nrs = gc.get("num_return_sequences") if isinstance(gc, dict) else getattr(gc, "num_return_sequences", None)
+            if nrs not in (None, 1):
+                raise NotImplementedError("num_return_sequences=%r is not supported" % (nrs,))
         models = [self] if ensemble is None else list(ensemble)
         enc = encoder_hidden_states if isinstance(encoder_hidden_states, (list, tuple)) else [encoder_hidden_states] * len(models)
         msk = encoder_attention_mask if isinstance(encoder_attention_mask, (list, tuple)) else [encoder_attention_mask] * len(models)
         cfg = self.config
-        return beam_search(models, enc, msk, input_ids=input_ids, max_length=max_length or 20, num_beams=num_beams,
-                           bos_token_id=cfg.bos_token_id if bos_token_id is None else bos_token_id,
-                           eos_token_id=cfg.eos_token_id if eos_token_id is None else eos_token_id,
-                           pad_token_id=cfg.pad_token_id if pad_token_id is None else pad_token_id,
-                           length_penalty=length_penalty, use_cache=use_cache)
+        return beam_search(models, enc, msk, input_ids=input_ids, max_length=pick("max_length", max_length, 20),
+                           num_beams=pick("num_beams", num_beams, 1),
+                           bos_token_id=pick("bos_token_id", bos_token_id, cfg.bos_token_id),
+                           eos_token_id=pick("eos_token_id", eos_token_id, cfg.eos_token_id),
+                           pad_token_id=pick("pad_token_id", pad_token_id, cfg.pad_token_id),
+                           length_penalty=pick("length_penalty", length_penalty, 1.0), use_cache=use_cache)

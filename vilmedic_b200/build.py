@@ -30,8 +30,8 @@ NVCC_FLAGS = [
 ]
 
 
-if os.environ.get("VLM_GELU_F32X2") == "1":      # experimental packed-fp32x2 GELU epilogue (common.cuh: gelu_erf_both_x2)
-    NVCC_FLAGS = NVCC_FLAGS + ["-DVLM_GELU_F32X2=1"]
+if os.environ.get("VLM_GELU_F32X2") == "0":      # scalar GELU epilogue instead of the packed-fp32x2 one (common.cuh: gelu_erf_both_x2)
+    NVCC_FLAGS = NVCC_FLAGS + ["-DVLM_GELU_F32X2=0"]
 
 
 def _sources():

@@ -267,7 +267,7 @@ __device__ __forceinline__ float gelu_erf_both(float x, float& dgelu) {
   return fmaf(-ax, w, fmaxf(x, 0.f));
 }
 
-// EXPERIMENTAL (build with VLM_GELU_F32X2=1 in the environment; not yet run on a GPU): the same evaluation for two elements at
+// The same evaluation for two elements at
 // a time on the packed fp32x2 FMA pipe of sm_100 (FFMA2 / FMUL2 / FADD2): 13 packed + 10 scalar instructions per pair instead of
 // 2 x 19 scalar ones.  The polynomial carries the sign (wn = -w), so that GELU = fma(|x|, wn, relu(x)).
 __device__ __forceinline__ void gelu_erf_both_x2(float x0, float x1, float& g0, float& g1, float& d0, float& d1) {

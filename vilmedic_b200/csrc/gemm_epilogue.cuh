@@ -7,6 +7,13 @@
 #include <cuda.h>
 #include "common.cuh"
 
+// Packed fp32x2 (FFMA2 / FMUL2 / FADD2) evaluation of GELU + GELU' in the staged epilogue: 13 packed + 10 scalar instructions per
+// pair instead of 2 x 19 scalar ones; measured -5 % on the FFN-up forward GEMM (gpurun_out r2a: 87 vs 92 us), same results.
+// Build with -DVLM_GELU_F32X2=0 for the scalar form.
+#ifndef VLM_GELU_F32X2
+#define VLM_GELU_F32X2 1
+#endif
+
 namespace vlm {
 
 struct GemmEpilogue {

@@ -146,15 +146,20 @@ int gemm2_dispatch(const void* a, long long lda, int a_mn, const void* b, long l
                    int bn, const GemmEpilogue& e, const CUtensorMap* tc, const CUtensorMap* tx, int mode, cudaStream_t s);
 
 // 0 = 1-CTA kernel, else the N tile (128 | 256) of the 2-CTA kernel.  force_bn >= 1000 forces 2-CTA with bn = force_bn-1000.
-static int pick_2cta(int M, int N, int K, int batch, int force_bn, int bn1) {
+// Default rule (measured, gpurun_out r2b gemm bench): the pair kernel wins where the 1-CTA kernel is bound by L2 -> smem operand
+// traffic and the epilogue is light — wide bias-only forward products (QKV 12608x2304x768: 40 vs 43 us, LM head 8192x30522x768:
+// 305 vs 340 us); with GELU / residual epilogues or few output tiles it loses to wave quantisation (256-row tiles on 74 pairs).
+// VLM_GEMM_2CTA=1 applies the cost model below to every shape, =0 disables the kernel.
+static int pick_2cta(int M, int N, int K, int batch, int force_bn, int bn1, bool light_forward) {
   if (batch != 1) return 0;
   if (force_bn >= 1000) return force_bn - 1000;
   if (force_bn != 0) return 0;
   static int enabled = -1;
   if (enabled < 0) {
     const char* env = getenv("VLM_GEMM_2CTA");
-    enabled = (env && env[0] == '1') ? 1 : 0;   // opt-in until the pair kernel has soaked
+    enabled = env ? ((env[0] == '1') ? 1 : 0) : 2;
   }
+  if (enabled == 2) return (light_forward && M >= 2048 && N >= 2048 && K <= 1536) ? 256 : 0;
   if (!enabled || M < 512 || N < 128) return 0;
   const int sms = num_sms();
   const long long m1 = (M + GEMM_BM - 1) / GEMM_BM, m2 = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
@@ -218,7 +223,8 @@ extern "C" int vlm_gemm_bf16(const void* a, long long lda, int a_mn_major, const
     const long long tiles_wide = (long long)((M + GEMM_BM - 1) / GEMM_BM) * ((N + wide - 1) / wide);
     if (tiles_wide < num_sms()) bn = wide;
   }
-  const int bn2 = pick_2cta(M, N, K, batch, force_bn, bn);
+  const int bn2 = pick_2cta(M, N, K, batch, force_bn, bn, !a_mn_major && !b_mn_major && !c_is_fp32 && !accumulate && act == 0 &&
+                                                          !residual && p_drop == 0.f);
   VLM_REQUIRE(bn2 == 0 || bn2 == 128 || bn2 == 256, "vlm_gemm_bf16: 2-CTA N tile must be 128 or 256");
   CUtensorMap ta, tb;
   // a zero batch stride broadcasts that operand: encode a single-batch map and pin the batch coordinate to 0

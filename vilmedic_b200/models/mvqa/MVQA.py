@@ -6,6 +6,7 @@ import torch
 import torch.nn as nn
 
 from ...blocks.classifier import *  # noqa: F401,F403
+from ...blocks.classifier.evaluation import evaluation
 from ...blocks.losses import *  # noqa: F401,F403
 from ...blocks.vision import *  # noqa: F401,F403
 from ...cfgutil import to_attrdict
@@ -32,7 +33,7 @@ class MVQA(nn.Module):
         self.pooler = _Pooler(conf.hidden_size)
         self.classifier = eval(classifier_func)(**classifier)
         self.loss_func = eval(loss_func)(**loss)
-        self.eval_func = None
+        self.eval_func = evaluation
         set_arena_root(self)
 
     def forward(self, images, labels=None, from_training=True, iteration=None, epoch=None, **kwargs):

@@ -1,6 +1,7 @@
 """ConVIRT — mirror of vilmedic/models/selfsup/conVIRT.py:46-110: text tower (EncoderModel pooler_output) and image tower
 (VisualEncoder) -> Linear-ReLU-Linear projections (:58-67) -> ConVIRT / InfoNCE loss (:69,100).  Micro-batching by
 `forward_batch_size` is kept (:83); negatives are the rank-local batch as in the reference."""
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -9,6 +10,24 @@ from ...blocks.losses import *  # noqa: F401,F403
 from ...blocks.vision import *  # noqa: F401,F403
 from ...cfgutil import cfg_get, to_attrdict
 from ...nn import ReluFn, native_linear, set_arena_root
+
+
+def evaluation(models, config, dl, from_training, **kwargs):
+    """Mirror of vilmedic/models/selfsup/conVIRT.py:14-38: no ensembling (model 0), mean loss over the batches, and — outside
+    training — the concatenated projected embeddings for post-processing."""
+    model = models[0]
+    losses, linguistics, visuals = [], [], []
+    with torch.no_grad():
+        for batch in dl:
+            batch = {k: v.cuda() if isinstance(v, torch.Tensor) else v for k, v in batch.items()}
+            out = model(**batch)
+            losses.append(out["loss"].mean().cpu().data.numpy())
+            if not from_training:
+                linguistics.append(out["linguistic"].cpu().data)
+                visuals.append(out["visual"].cpu().data)
+    if from_training:
+        return {"loss": np.ndarray.mean(np.array(losses))}
+    return {"loss": np.ndarray.mean(np.array(losses)), "linguistic": torch.cat(linguistics), "visual": torch.cat(visuals)}
 
 
 def chunks(lst, n):
@@ -38,7 +57,7 @@ class ConVIRT(nn.Module):
         self.lin_proj = _MLP(projection.textual_embedding_dim, projection.projection_dim)
         self.loss_fn = eval(loss.pop("proto"))(**loss)
         self.fbs = forward_batch_size
-        self.eval_func = None
+        self.eval_func = evaluation
         set_arena_root(self)
 
     def forward(self, input_ids, attention_mask, images, **kwargs):
