@@ -234,6 +234,41 @@ int vlm_maxpool3x3s2_bwd(const void* dy, const uint8_t* idx, void* dx, int B, in
 int vlm_avgpool_fwd(const void* x, void* y, int B, int HW, int C, void* stream);
 int vlm_avgpool_bwd(const void* dy, void* dx, int B, int HW, int C, void* stream);
 
+/* ---- incremental decoding + device-side beam search (csrc/decode.cu) ------------------------------------------------------ */
+/* One decode step of the loop behind vilmedic/blocks/huggingface/decoder/evaluation.py:73-78 (HF cached generate) and the
+ * ensemble search of vilmedic/blocks/huggingface/decoder/beam_search.py:243-320, with every per-step scalar in device memory
+ * (counters[0] = t = position of the token being consumed), so that the whole step replays as one CUDA graph.
+ * vlm_embed_step: z[r] = bf16(word[tok[r]] + pos[min(*t, max_pos-1)])   (HF:bert_generation/modeling_bert_generation.py:395-429). */
+int vlm_embed_step(const long long* tok, const float* word, const float* pos, void* z, int R, int D, int V, const int* t_ptr,
+                   int max_pos, void* stream);
+/* T_q = 1 attention for R rows x H heads (DH in {48, 64, 96}); fp32 scores / softmax / PV, bf16 out [R, H*DH].
+ *   self-attention (kv_new != NULL): cache bf16 [R, max_len, 2*H*DH] ([K | V] per position); row r's history at position j < *t is
+ *     read from physical row row_map[r*map_ld + j]; the new key/value kv_new[r] ([K | V], pitch ld_new) is used for position *t,
+ *     appended at (r, *t), and row_map[r][*t] = r is recorded.  Beam reordering permutes row_map, never the cache
+ *     (replaces the index_select cache reorder of beam_search.py:317-319).
+ *   cross-attention (kv_new == NULL): fixed_len keys, K/V of row r read from cache row r / row_div (one projection per image,
+ *     shared by its beams); kmask uint8 [cache rows, kmask_ld] (0 = masked) optional. */
+int vlm_decode_attention(const void* q, long long ldq, const void* kv_new, long long ld_new, void* cache, long long cache_row_stride,
+                         int two_d, int* row_map, int map_ld, const int* t_ptr, int fixed_len, int row_div, const uint8_t* kmask,
+                         int kmask_ld, void* out, long long ldo, int R, int H, int DH, float scale, int max_len, void* stream);
+/* Per row r: x = sum_m logits[m][r, :V] (beam_search.py:254), score = log_softmax(x) + beam_scores[r] (:260-265); writes the row's
+ * top-2k (score desc, token asc) to cand_score / cand_tok [R, 2k].  logits: HOST array of n_models (<= 8) device pointers, fp32,
+ * row pitch ld.  k in 1..8. */
+int vlm_beam_rows(const float* const* logits, int n_models, long long ld, int V, const float* beam_scores, float* cand_score,
+                  int* cand_tok, int R, int k, void* stream);
+/* Per batch element: global top-2k over its k rows' candidates (== torch.topk over k*V, :289-294; ties: lower beam*V+token first),
+ * then BeamSearchScorer.process (:297-304; legacy BeamHypotheses semantics: EOS candidates ranked >= k are skipped, a finished
+ * hypothesis scores sum_logprobs / len**length_penalty (double), is_done when k are finished and the worst kept score >= the best
+ * running score / len**length_penalty).  Writes next_tok / parent / beam_scores [B*k]; k == 1 is greedy argmax decoding (finished
+ * rows emit pad).  counters: {t, number of finished batch elements, sequence length at which the last one finished, -}. */
+int vlm_beam_select(const float* cand_score, const int* cand_tok, int k, int V, int B, int max_len, const long long* ids,
+                    float* beam_scores, uint8_t* done, long long* next_tok, int* parent, double* hyp_score, int* hyp_len,
+                    long long* hyp_tok, int* hyp_count, double* hyp_worst, int* counters, int eos, int pad, double length_penalty,
+                    void* stream);
+/* ids[r] <- ids[parent[r]] + next_tok[r]; row_map[r] <- row_map[parent[r]] (through the tmp buffers); counters[0] += 1. */
+int vlm_beam_advance(long long* ids, long long* ids_tmp, int* row_map, int* map_tmp, const int* parent, const long long* next_tok, int R,
+                     int max_len, int* counters, void* stream);
+
 /* ---- input pipeline (vilmedic/datasets/base/ImageDataset.py:97-104) ------------------------------------ */
 /* RandomCrop + RandomHorizontalFlip + ToTensor + Normalize of the reference's train transform, after its (host-side) Resize:
  * in  uint8 [B, Hin, Win, 3] (HWC, what PIL / numpy hand over; device memory), top/left int32 [B] crop origins,

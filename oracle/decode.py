@@ -45,12 +45,13 @@ class _Hyps:
 
 @torch.no_grad()
 def ensemble_beam_search(decoders, encs, masks, num_beams, max_length, bos, eos, pad, length_penalty=1.0, gaps=None,
-                         trace=None):
+                         trace=None, on_step=None):
     """Sum-of-logits ensemble beam search (beam_search.py:243-320); greedy when num_beams == 1.
     gaps: optional list that receives, per step, the smallest score gap between adjacent candidates among the top
     2k+1 (k>1) or top-2 (greedy) — how close the fp32 search came to a tie (tests use it to qualify bit-exactness).
     trace: optional list that receives (step, batch row, gap, max |summed logit| of that row's beams) for the same decisions:
-    a bf16 implementation carries a logit error proportional to the logit magnitude, so tests qualify by gap / scale."""
+    a bf16 implementation carries a logit error proportional to the logit magnitude, so tests qualify by gap / scale.
+    on_step: optional callback(cur_len, ids [B*k, cur_len], scores [B*k], done list) called after every step's update."""
     B, k = encs[0].shape[0], num_beams
     ids = torch.full((B * k, 1), bos, dtype=torch.long)
     encs = [e.repeat_interleave(k, 0) for e in encs]
@@ -91,6 +92,8 @@ def ensemble_beam_search(decoders, encs, masks, num_beams, max_length, bos, eos,
             cur += 1
             for b, tok in enumerate(t.tolist()):
                 done[b] = done[b] or tok == eos
+            if on_step is not None:
+                on_step(cur, ids.clone(), scores.clone(), list(done))
             if all(done):
                 break
             continue
@@ -117,6 +120,8 @@ def ensemble_beam_search(decoders, encs, masks, num_beams, max_length, bos, eos,
         scores = ns.view(-1)
         ids = torch.cat([ids[nb.view(-1)], nt.view(-1, 1)], 1)
         cur += 1
+        if on_step is not None:
+            on_step(cur, ids.clone(), scores.clone(), list(done))
         if all(done):
             break
     if k == 1:

@@ -493,3 +493,27 @@ def test_yaml_configs_build_through_create_model(path, proto):
     sd = {"model": {"module." + k: v for k, v in model.state_dict().items()}, "__version__": "1.3.3"}
     model2 = executors.create_model(tcfg, dl, state_dict=sd)
     assert all(torch.equal(a, b) for a, b in zip(model.state_dict().values(), model2.state_dict().values()))
+
+
+def test_policy_oracle_fp32_mode_equals_hf_decoder():
+    """oracle/decode_policy.py restates the HF BertGenerationDecoder forward; with the rounding policy off it must reproduce the HF
+    module's logits (that pins the restatement), with the bf16 policy on it stays close (sanity of the rounding points)."""
+    from oracle.decode_policy import PolicyDecoder
+    from oracle.rrg import OracleRRG
+    dec, cnn = _small_cfgs()
+    torch.manual_seed(5)
+    ref = OracleRRG(copy.deepcopy(dec), copy.deepcopy(cnn)).eval()
+    hf = ref.dec.decoder
+    g = torch.Generator().manual_seed(1)
+    V = hf.config.vocab_size
+    ids = torch.randint(3, V, (3, 7), generator=g)
+    ids[:, 0] = 0
+    enc = torch.randn(3, 5, hf.config.hidden_size, generator=g)
+    mask = torch.ones(3, 5, dtype=torch.long)
+    mask[1, 3:] = 0
+    with torch.no_grad():
+        want = hf(input_ids=ids, encoder_hidden_states=enc, encoder_attention_mask=mask, use_cache=False).logits[:, -1].float()
+    got = PolicyDecoder(hf, "fp32")(ids, enc, mask).logits[:, 0]
+    assert (got - want).abs().max().item() <= 2e-5 * want.abs().max().item() + 1e-5
+    got16 = PolicyDecoder(hf, "bf16")(ids, enc, mask).logits[:, 0]
+    assert (got16 - want).abs().max().item() <= 5e-2 * want.abs().max().item() + 1e-3

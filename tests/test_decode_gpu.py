@@ -1,12 +1,25 @@
-"""Greedy / beam / ensemble decoding parity: token ids of the B200 path must equal the oracle's.
+"""Greedy / beam / ensemble decoding parity (north_star: greedy-decode token indices bit-exact).
 
-The oracle computes in fp32, the product in bf16, so a search decision closer than the bf16 logit error could
-legitimately flip.  Following SURVEY.md §7 ("hard parts"): (i) weights are scaled so that decisions have non-trivial
-margins and are rounded to bf16 on BOTH sides (identical parameters); (ii) the oracle reports the smallest decision margin
-of its own search (top-1 vs top-2 for greedy; k-th kept vs first dropped candidate for beam) together with the logit
-magnitude, and the comparison is bit-exact over every decision whose margin exceeds twice the MEASURED device-vs-oracle
-logit error of that very step (itself bounded by a stated tolerance) — a mismatch on such a decision is a real failure.
-The selection logic itself is verified bit-exactly on identical logits in tests/test_cpu.py."""
+Three layers of evidence, each through the C ABI:
+
+ 1. SELECTION MACHINERY, bit-exact, full size (B=32, beam 4, 2-model ensemble, V=30522, 127 steps): the device-side search kernels
+    (vlm_beam_rows / vlm_beam_select / vlm_beam_advance + the final pick) are driven by scripted fp32 logits that are a pure function
+    of each row's token prefix, and the oracle's restatement of vilmedic/blocks/huggingface/decoder/beam_search.py:222-342 is driven by
+    THE SAME logits: token ids, hypotheses and finished flags must be identical — no tolerance, no margin.
+ 2. MODEL STEP NUMERICS at BERT-base size (12 layers, V=30522): teacher-forced on the oracle's prefixes, the logits of the KV-cached
+    decode step (vlm_embed_step, tcgen05 GEMMs, vlm_decode_attention over the indirected cache, LayerNorm) stay within LOGIT_TOL of
+    the numerics-policy oracle (oracle/decode_policy.py: the HF decoder arithmetic with the kernels' bf16 storage points; pinned to
+    the HF module itself in tests/test_cpu.py), and within LOGIT_TOL_FP32 of the fp32 HF module.
+ 3. END TO END: the product's `generate` (CUDA-graph replayed device search) against the oracle search over the policy oracle, greedy
+    (12 layers, V=30522) and beam-4 x 2-model ensemble at the full cfg#5 size (B=32, max_length 128).  Why there is a margin
+    qualifier here and nowhere else: the kernels and ANY other implementation of the same arithmetic differ in fp32 summation order
+    (~1e-6 relative), and one bf16 rounding flipped by that (2^-9 relative on one activation) moves a logit by ~1e-4 of the logit
+    scale; with Gaussian-tailed logits the top-1 / top-2 gap is exponentially distributed with mean sigma / sqrt(2 ln V), so about
+    1 decision in 10^3 has a gap below that noise — over the 4064 decisions of a B=32 x 127-step search a few WILL flip, for this
+    or any two non-bit-identical implementations.  So: every decision whose oracle margin exceeds 2 x the MEASURED logit error
+    must agree bit for bit (>= 95 % of all decisions are of that kind — asserted), a row is compared up to its first sub-margin
+    decision, and the measured error itself is bounded (item 2).  The old 8 % tolerance / toy sizes are gone.
+"""
 import copy
 
 import pytest
@@ -15,13 +28,35 @@ import torch
 pytestmark = pytest.mark.gpu
 BOS, PAD, EOS = 0, 1, 2
 
+LOGIT_TOL = 4e-3          # max |device logit - policy-oracle logit| / max |logit|   (measured on B200: see the assert messages)
+LOGIT_TOL_FP32 = 6e-2     # same against the fp32 HF module (bf16 storage error of a 12-layer stack with x3 / x30 scaled weights)
 
-def _pair(seed, vocab=300):
+
+def _report(name, **kw):
+    """Measured numbers go to $VLM_TEST_REPORT (one JSON line per call) so that tolerances can be kept at ~3x the measurement."""
+    import json
+    import os
+    path = os.environ.get("VLM_TEST_REPORT")
+    if path:
+        with open(path, "a") as f:
+            f.write(json.dumps(dict(test=name, **kw)) + "\n")
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _pair(seed, vocab=300, layers=2):
+    """(oracle RRG, product RRG) with identical, bf16-representable parameters, scaled for non-degenerate argmax margins."""
     from oracle.rrg import OracleRRG
     from vilmedic_b200 import synth
     from vilmedic_b200.models import RRG
     torch.manual_seed(seed)
-    dec = synth.bert_base_decoder(vocab=vocab, layers=2, dropout=0.0)
+    dec = synth.bert_base_decoder(vocab=vocab, layers=layers, dropout=0.0)
     cnn = dict(proto="VisualEncoder", backbone="vit", permute="no_permute", **dict(synth.vit_b16(), num_hidden_layers=1))
     ref = OracleRRG(dec, cnn).eval()
     with torch.no_grad():
@@ -36,174 +71,243 @@ def _pair(seed, vocab=300):
     return ref, mine.cuda().eval()
 
 
-class _MineAsOracleModel:
-    """Adapter: lets the ORACLE's search loop drive the product's (uncached, full-prefix) next-token logits."""
+def _features(ref, n, seed):
+    """Encoder features for n images: the oracle ViT's output rounded to bf16 — the SAME tensor feeds both sides (ViT parity is
+    tests/test_rrg_gpu.py's subject)."""
+    from vilmedic_b200 import synth
+    batch = synth.rrg_batch(n, 8, 300, seed=seed)
+    with torch.no_grad():
+        enc, mask = ref.enc.encode(batch["images"])
+    return enc.to(torch.bfloat16).float(), mask
 
-    def __init__(self, dec, enc, mask):
-        self.dec, self.enc, self.mask = dec, enc, mask
-        self.config = dec.config
+
+# ------------------------------------------------------------------------------------------------ 1. selection machinery
+class _Scripted:
+    """Fake decoder: next-token logits are a pure function of the row's token prefix (rolling hash -> row of a fixed random table),
+    so the oracle loop (CPU) and the device kernels see identical fp32 numbers whatever the beam order."""
+
+    def __init__(self, vocab, seed, n_rows=512, eos_boost=0.08):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        self.table = torch.randn(n_rows, (vocab + 3) // 4 * 4, device="cuda", generator=g) * 4.0
+        boost = torch.rand(n_rows, device="cuda", generator=g) < eos_boost
+        self.table[boost, EOS] += 14.0
+        self.vocab, self.n = vocab, n_rows
+        self.mult = 1000003 + 2 * seed
+
+    def rows(self, ids, cur_len):
+        h = torch.zeros(ids.shape[0], dtype=torch.int64, device=ids.device)
+        for i in range(cur_len):
+            h = (h * self.mult + ids[:, i] + 12345) % 2147483629
+        return h % self.n
+
+    def padded(self, ids, cur_len):
+        return self.table[self.rows(ids.cuda(), cur_len)]
 
     def __call__(self, input_ids, encoder_hidden_states=None, encoder_attention_mask=None, use_cache=False):
-        B = input_ids.shape[0]
-        rep = B // self.enc.shape[0]
-        enc = self.enc.repeat_interleave(rep, 0)
-        mask = self.mask.repeat_interleave(rep, 0) if self.mask is not None else None
-        lg = self.dec.next_token_logits(input_ids.cuda(), enc, mask).float().cpu()
-
         class _O:
             pass
         o = _O()
-        o.logits = lg[:, None, :]
+        o.logits = self.padded(input_ids, input_ids.shape[1])[:, None, :self.vocab].cpu()
         return o
 
 
-# A bf16 forward carries a logit error that scales with the logit magnitude.  It is MEASURED here (device logits vs the fp32
-# oracle's, same bf16-rounded weights, same prefix): if every device logit is within e of the oracle's, a decision whose oracle
-# margin exceeds 2e (+ a small cushion for cached-vs-uncached reduction order) cannot flip — such decisions are "safe" and
-# must match bit for bit; the tolerance on e itself is LOGIT_TOL (measured on B200: 1.2-4.2 % of the logit scale over 66
-# teacher-forced steps with these x3 / x30 scaled weights, which amplify the bf16 rounding of the activations; tests/decode_diag.py).
-LOGIT_TOL = 0.08          # max |device logit - fp32 logit| / max |fp32 logit|
-CUSHION = 2.0 ** -10      # x logit scale
-
-
-def test_greedy_token_ids_bit_exact_vs_fp32_oracle(cuda_dev):
-    """(1) the oracle restatement == HF generate; (2) teacher-forced on the oracle's prefixes, the device logits stay within
-    LOGIT_TOL of the fp32 oracle's and every safe decision has the same argmax; (3) the free-running KV-cached greedy decode
-    reproduces the oracle's token ids on every row up to that row's first unsafe decision."""
+@pytest.mark.parametrize("B,k,n_models,L,V,lp", [(32, 4, 2, 128, 30522, 1.0), (5, 1, 1, 40, 997, 1.0), (7, 3, 2, 33, 1000, 0.6),
+                                                 (3, 8, 1, 20, 64, 2.0)])
+def test_device_search_kernels_equal_oracle_loop_bit_exact(cuda_dev, B, k, n_models, L, V, lp):
     from oracle import decode
-    from vilmedic_b200 import synth
-    ref, mine = _pair(0)
-    L = 12
-    NB = 6
-    batch = synth.rrg_batch(NB, 8, 300, seed=9)
-    enc_r, mask_r = ref.enc.encode(batch["images"])
-    want = decode.ensemble_beam_search([ref.dec.decoder], [enc_r], [mask_r], 1, L, BOS, EOS, PAD)
-    hf = decode.hf_generate(ref.dec.decoder, enc_r, mask_r, 1, L, BOS, EOS, PAD)
-    assert torch.equal(want[:, :hf.shape[1]], hf[:, :want.shape[1]]), "oracle restatement disagrees with HF generate"
-    enc, mask = mine.encode(batch["images"])
-    first_unsafe = [want.shape[1]] * NB
-    safe_decisions = 0
-    for t in range(1, want.shape[1]):
-        lr = decode.next_logits(ref.dec.decoder, want[:, :t], enc_r, mask_r)
-        lm = mine.dec.decoder.next_token_logits(want[:, :t].cuda(), enc, mask).float().cpu()
-        for row in range(NB):
-            if want[row, t] == PAD and (want[row, :t] == EOS).any():
-                continue                                                     # row already finished
-            scale = lr[row].abs().max().item()
-            err = (lm[row] - lr[row]).abs().max().item()
-            assert err <= LOGIT_TOL * scale, "bf16 logit error %.4f of the logit scale at step %d row %d" % (err / scale, t, row)
-            top = torch.topk(lr[row], 2).values
-            if float(top[0] - top[1]) > 2 * err + CUSHION * scale:
-                assert int(lm[row].argmax()) == int(want[row, t]), (t, row)
-                safe_decisions += 1
-            else:
-                first_unsafe[row] = min(first_unsafe[row], t)
-    assert safe_decisions >= 5 * NB, "test inputs lost their argmax margins (%d safe decisions); pick another seed" % safe_decisions
-    got = mine.dec.decoder.generate(input_ids=torch.full((NB, 1), BOS, dtype=torch.long, device="cuda"), encoder_hidden_states=enc,
-                                    encoder_attention_mask=mask, max_length=L, num_beams=1, bos_token_id=BOS, eos_token_id=EOS,
+    from vilmedic_b200.blocks.huggingface.decoder.beam import SearchState
+    scripted = [_Scripted(V, 10 + m) for m in range(n_models)]
+    hist = []
+    dummy = [torch.zeros(B, 1, 1)] * n_models
+    want = decode.ensemble_beam_search(scripted, dummy, [None] * n_models, k, L, BOS, EOS, PAD, length_penalty=lp,
+                                       on_step=lambda cur, ids, sc, done: hist.append((cur, ids, sc, done)))
+    s = SearchState(B, k, L, V, cuda_dev)
+    s.reset(BOS, EOS, PAD, lp)
+    for step in range(1, L):
+        s.select([m.padded(s.st["ids"], step) for m in scripted])
+        torch.cuda.synchronize()
+        if step - 1 < len(hist):
+            cur, ids_w, sc_w, done_w = hist[step - 1]
+            assert int(s.st["counters"][0]) + 1 == cur
+            live = [b for b in range(B) if not (k > 1 and done_w[b])]
+            rows = [b * k + j for b in live for j in range(k)]
+            got_ids = s.st["ids"][:, :cur].cpu()
+            assert torch.equal(got_ids[rows], ids_w[rows]), "token ids differ at step %d" % cur
+            assert s.st["done"].cpu().tolist() == [int(d) for d in done_w], "finished flags differ at step %d" % cur
+            assert (s.st["beam_scores"].cpu()[rows] - sc_w[rows]).abs().max().item() < 1e-3
+        if s.all_done():
+            break
+    got = s.finish().cpu()
+    assert got.shape == want.shape and torch.equal(got, want)
+    if (B, k) == (32, 4):
+        assert len(hist) >= 100          # the full-size case really searched ~127 steps with hypotheses finishing on the way
+        assert int(s.st["hyp_count"].sum()) > 0
+
+
+# ------------------------------------------------------------------------------------------------ 2. model step numerics
+def _teacher_forced_logits(dec, enc, mask, ids):
+    """Device logits of the KV-cached step along the given prefixes (rows independent, k = 1): [steps, rows, V]."""
+    from vilmedic_b200.blocks.huggingface.decoder.generation import DecodeState
+    R, T = ids.shape
+    row_map = torch.zeros((R, T + 1), device="cuda", dtype=torch.int32)
+    t = torch.zeros(1, device="cuda", dtype=torch.int32)
+    st = DecodeState(dec, R, 1, T + 1, row_map, t)
+    st.set_encoder(enc.cuda(), mask.cuda() if mask is not None else None)
+    out = []
+    V = dec.cfg.vocab_size
+    for i in range(T):
+        out.append(dec.decode_step(st, ids[:, i].contiguous().cuda())[:, :V].float().cpu())
+        t.add_(1)
+    assert torch.equal(row_map[:, :T].cpu(), torch.arange(R, dtype=torch.int32)[:, None].expand(R, T))   # identity indirection
+    return torch.stack(out)
+
+
+@pytest.mark.parametrize("layers,vocab,R,T", [(2, 300, 6, 12), (12, 30522, 8, 24)])
+def test_decode_step_logits_vs_policy_oracle_and_hf(cuda_dev, layers, vocab, R, T):
+    from oracle import decode
+    from oracle.decode_policy import PolicyDecoder
+    ref, mine = _pair(0, vocab, layers)
+    enc, mask = _features(ref, R, 9)
+    pol = PolicyDecoder(ref.dec.decoder, "bf16", device="cuda")
+    ids = decode.ensemble_beam_search([pol], [enc], [mask], 1, T + 1, BOS, EOS, PAD)[:, :T]          # the oracle's own greedy prefixes
+    T = ids.shape[1]
+    got = _teacher_forced_logits(mine.dec.decoder, enc, mask, ids)
+    worst_pol, worst_hf = 0.0, 0.0
+    for i in range(T):
+        want = pol(ids[:, :i + 1], enc, mask).logits[:, 0]
+        scale = want.abs().max().item()
+        worst_pol = max(worst_pol, (got[i] - want).abs().max().item() / scale)
+        if i in (0, T // 2, T - 1):
+            with torch.no_grad():
+                hf = ref.dec.decoder(input_ids=ids[:, :i + 1], encoder_hidden_states=enc, encoder_attention_mask=mask,
+                                     use_cache=False).logits[:, -1].float()
+            worst_hf = max(worst_hf, (got[i] - hf).abs().max().item() / hf.abs().max().item())
+    _report("decode_step_logits", layers=layers, vocab=vocab, err_vs_policy=worst_pol, err_vs_fp32=worst_hf)
+    assert worst_pol <= LOGIT_TOL, "device vs bf16-policy oracle: %.2e of the logit scale" % worst_pol
+    assert worst_hf <= LOGIT_TOL_FP32, "device vs fp32 HF module: %.2e of the logit scale" % worst_hf
+
+
+# ------------------------------------------------------------------------------------------------ 3. end to end
+def _measured_error(mine, pol_list, encs, masks, ids, steps):
+    """max over sampled steps of |device logit - oracle logit| (summed over the ensemble), absolute."""
+    got = sum(_teacher_forced_logits(m.dec.decoder, e, mk, ids)[steps] for m, e, mk in zip(mine, encs, masks))
+    err = 0.0
+    for n, i in enumerate(steps):
+        want = sum(p(ids[:, :i + 1], e, mk).logits[:, 0] for p, e, mk in zip(pol_list, encs, masks))
+        err = max(err, (got[n] - want).abs().max().item())
+    return err
+
+
+def test_greedy_generate_12_layers_full_vocab(cuda_dev):
+    """Free-running greedy `generate` (graph-replayed device search) == the oracle's greedy search, 12 layers, V = 30522."""
+    from oracle import decode
+    from oracle.decode_policy import PolicyDecoder
+    ref, mine = _pair(1, 30522, 12)
+    B, L = 16, 48
+    enc, mask = _features(ref, B, 5)
+    pol = PolicyDecoder(ref.dec.decoder, "bf16", device="cuda")
+    trace = []
+    want = decode.ensemble_beam_search([pol], [enc], [mask], 1, L, BOS, EOS, PAD, gaps=[], trace=trace)
+    got = mine.dec.decoder.generate(input_ids=torch.full((B, 1), BOS, dtype=torch.long, device="cuda"), encoder_hidden_states=enc.cuda(),
+                                    encoder_attention_mask=mask.cuda(), max_length=L, num_beams=1, bos_token_id=BOS, eos_token_id=EOS,
                                     pad_token_id=PAD).cpu()
-    assert got.shape == want.shape
-    compared = 0
-    for row in range(NB):
-        n = first_unsafe[row]                                                # tokens at positions < n come from safe decisions
-        assert torch.equal(got[row, :n], want[row, :n]), (row, n, got[row].tolist(), want[row].tolist())
-        compared += n
-    assert compared >= 2 * NB, compared
+    err = _measured_error([mine], [pol], [enc], [mask], want[:, :-1], [0, 7, 23, want.shape[1] - 2])
+    assert err <= LOGIT_TOL * max(s for _, _, _, s in trace)
+    thr = 2.0 * err
+    first_unsafe = {}
+    for cur, b, gap, _ in trace:
+        if gap <= thr:
+            first_unsafe.setdefault(b, cur)
+    n_safe = sum(1 for _, _, gap, _ in trace if gap > thr)
+    _report("greedy_12l", err=err, scale=max(s for _, _, _, s in trace), decisions=len(trace), safe=n_safe,
+            equal=bool(got.shape == want.shape and torch.equal(got, want)))
+    assert n_safe >= 0.95 * len(trace), "only %d of %d decisions have a margin above 2x the measured logit error %.3g" % (n_safe, len(trace), err)
+    full = 0
+    for b in range(B):
+        upto = first_unsafe.get(b, want.shape[1])          # decision at length `cur` writes column `cur`
+        n = min(upto, want.shape[1], got.shape[1])
+        assert torch.equal(got[b, :n], want[b, :n]), (b, n, got[b, :n].tolist(), want[b, :n].tolist())
+        full += int(upto >= want.shape[1])
+    assert full >= B // 2, "only %d of %d rows could be compared over their whole length" % (full, B)
+    if full == B:
+        assert got.shape == want.shape
 
 
-def _rel_cache_noise(mine, images, k):
-    """max |KV-cached step logits - full-prefix logits| / max |logit| over a few steps at the beam-expanded batch size."""
-    from vilmedic_b200.blocks.huggingface.decoder.generation import DecodeState
-    enc, mask = mine.encode(images)
-    enc, mask = enc.repeat_interleave(k, 0), (mask.repeat_interleave(k, 0) if mask is not None else None)
-    dec = mine.dec.decoder
-    ids = torch.randint(5, 300, (enc.shape[0], 6), device="cuda")
-    ids[:, 0] = BOS
-    st = DecodeState(dec, enc.shape[0], 8, enc, mask)
-    worst = 0.0
-    for t in range(ids.shape[1]):
-        step = dec.decode_step(st, ids[:, t])
-        full = dec.next_token_logits(ids[:, :t + 1], enc, mask)
-        worst = max(worst, ((step - full).abs().max() / full.abs().max()).item())
-    return worst
-
-
-@pytest.mark.parametrize("k,n_models", [(4, 1), (4, 2)])
-def test_beam_ensemble_token_ids(cuda_dev, k, n_models):
-    """KV-cached beam / ensemble search == the oracle's search loop (beam_search.py:222-342 restated) run over the product's
-    own uncached logits, bit for bit, on the first seed whose decisions all clear the measured cached-vs-uncached noise; the
-    fp32 oracle's end-to-end result is compared when its own decisions are all safe w.r.t. the bf16 logit error (beam
-    pruning margins among 2k of k*V candidates are usually tighter than that: informational otherwise)."""
+def test_ensemble_beam_generate_cfg5_full_size(cuda_dev):
+    """BASELINE configs[4] shape: two independently seeded 12-layer decoders, V = 30522, B = 32, beam 4, max_length 128, sum-of-logits
+    ensemble — the product's `generate(ensemble=...)` against the oracle search over two policy oracles.  The device search is ALSO
+    stepped eagerly next to the oracle's recorded states: per image, beam token ids and scores must agree at every step up to the
+    image's first decision with a margin below 2 x the measured logit error."""
     from oracle import decode
-    from vilmedic_b200 import synth
-    pairs = [_pair(s) for s in range(n_models)]
-    hf_models = [m.dec.decoder for _, m in pairs]
-    checked = False
-    for seed in range(35, 51):
-        batch = synth.rrg_batch(2, 8, 300, seed=seed)
-        encs, masks = zip(*[m.encode(batch["images"]) for _, m in pairs])
-        adapters = [_MineAsOracleModel(m.dec.decoder, e, mk) for (_, m), e, mk in zip(pairs, encs, masks)]
-        trace_mine = []
-        want_mine = decode.ensemble_beam_search(adapters, [e.cpu() for e in encs], [mk.cpu() for mk in masks], k, 8, BOS, EOS, PAD,
-                                                gaps=[], trace=trace_mine)
-        noise = 2 * n_models * max(_rel_cache_noise(m, batch["images"], k) for _, m in pairs) + CUSHION / 2
-        if any(gap <= noise * scale for (_, _, gap, scale) in trace_mine):
-            continue                                        # a near-tie of the device logits: cached vs uncached may flip it
-        got = hf_models[0].generate(input_ids=torch.full((2, 1), BOS, dtype=torch.long, device="cuda"),
-                                    encoder_hidden_states=list(encs), encoder_attention_mask=list(masks), ensemble=hf_models,
-                                    max_length=8, num_beams=k, bos_token_id=BOS, eos_token_id=EOS, pad_token_id=PAD).cpu()
-        assert got.shape == want_mine.shape and torch.equal(got, want_mine), (seed, got.tolist(), want_mine.tolist())
-        encs_r, masks_r = zip(*[r.enc.encode(batch["images"]) for r, _ in pairs])
-        trace = []
-        want = decode.ensemble_beam_search([r.dec.decoder for r, _ in pairs], list(encs_r), list(masks_r), k, 8, BOS, EOS, PAD,
-                                           gaps=[], trace=trace)
-        rel = 2 * _rel_logit_error(pairs, batch["images"])
-        if all(gap > 2 * rel * scale for (_, _, gap, scale) in trace):
-            assert torch.equal(got, want), (seed, got.tolist(), want.tolist())
-        else:
-            n = min(got.shape[1], want.shape[1])
-            agree = (got[:, :n] == want[:, :n]).float().mean().item()
-            print("fp32-oracle beam search has a near-tie on seed %d: token agreement %.2f (informational)" % (seed, agree))
-        checked = True
-        break
-    assert checked, "no seed in 35..50 gave a batch whose beam decisions are all clear of the cached-vs-uncached noise"
+    from oracle.decode_policy import PolicyDecoder
+    from vilmedic_b200.blocks.huggingface.decoder.beam import DeviceSearch
+    B, k, L = 32, 4, 128
+    pairs = [_pair(s, 30522, 12) for s in (0, 1)]
+    feats = [_features(r, B, 3) for r, _ in pairs]
+    encs, masks = [f[0] for f in feats], [f[1] for f in feats]
+    pols = [PolicyDecoder(r.dec.decoder, "bf16", device="cuda") for r, _ in pairs]
+    trace, hist = [], []
+    want = decode.ensemble_beam_search(pols, encs, masks, k, L, BOS, EOS, PAD, gaps=[], trace=trace,
+                                       on_step=lambda cur, ids, sc, done: hist.append((cur, ids, sc, done)))
+    decs = [m.dec.decoder for _, m in pairs]
+    got = decs[0].generate(input_ids=torch.full((B, 1), BOS, dtype=torch.long, device="cuda"), encoder_hidden_states=[e.cuda() for e in encs],
+                           encoder_attention_mask=[m.cuda() for m in masks], ensemble=decs, max_length=L, num_beams=k, bos_token_id=BOS,
+                           eos_token_id=EOS, pad_token_id=PAD, length_penalty=1.0).cpu()
+    assert got.dim() == 2 and got.shape[0] == B and got.shape[1] <= L and bool((got[:, 0] == BOS).all())
+    # measured ensemble logit error along beam-0 prefixes of the oracle's final beams (rows = images)
+    tf_ids = hist[-1][1][::k][:8, :40]
+    err = _measured_error([m for _, m in pairs], pols, [e[:8] for e in encs], [m[:8] for m in masks], tf_ids,
+                          [0, 13, tf_ids.shape[1] - 1])
+    scale = max(s for _, _, _, s in trace)
+    assert err <= 2 * LOGIT_TOL * scale, "ensemble logit error %.3g vs scale %.3g" % (err, scale)
+    thr = 2.0 * err
+    first_unsafe = {}
+    for cur, b, gap, _ in trace:
+        if gap <= thr:
+            first_unsafe.setdefault(b, cur)
+    n_safe = sum(1 for _, _, gap, _ in trace if gap > thr)
+    assert n_safe >= 0.95 * len(trace), "only %d of %d decisions are above the margin (err %.3g)" % (n_safe, len(trace), err)
+    # step the same engine eagerly beside the oracle's recorded states
+    eng = DeviceSearch.get(decs, B, k, L)
+    eng.search.reset(BOS, EOS, PAD, 1.0)
+    agree_steps = [0] * B
+    for cur, ids_w, sc_w, done_w in hist:
+        eng._step()
+        got_ids = eng.search.st["ids"][:, :cur].cpu()
+        got_sc = eng.search.st["beam_scores"].cpu()
+        for b in range(B):
+            if first_unsafe.get(b, L + 1) < cur or done_w[b]:
+                continue                                      # past this image's first sub-margin decision (or finished)
+            rows = slice(b * k, (b + 1) * k)
+            assert torch.equal(got_ids[rows], ids_w[rows]), "image %d: beams differ at length %d with every margin so far above %.3g" % (b, cur, thr)
+            assert (got_sc[rows] - sc_w[rows]).abs().max().item() <= thr * cur + 1e-3
+            agree_steps[b] = cur
+    safe_images = [b for b in range(B) if b not in first_unsafe]
+    for b in safe_images:                                     # never near a tie: the final hypothesis must be identical too
+        n = min(got.shape[1], want.shape[1])
+        assert torch.equal(got[b, :n], want[b, :n]), b
+    _report("ensemble_beam_cfg5", err=err, scale=scale, decisions=len(trace), safe=n_safe, steps=len(hist), safe_images=len(safe_images),
+            agree_steps=sum(agree_steps), of=B * len(hist), final_equal=bool(got.shape == want.shape and torch.equal(got, want)))
+    assert sum(agree_steps) >= 0.5 * B * len(hist), "device and oracle beams agreed on too few (image, step) pairs: %d" % sum(agree_steps)
 
 
-def _rel_logit_error(pairs, images):
-    """max |device logits - oracle logits| / max |oracle logits| of the (summed) first-step logits."""
-    from oracle.decode import next_logits
-    b = images.shape[0]
-    ids = torch.full((b, 1), BOS, dtype=torch.long)
-    ref_sum, mine_sum = 0.0, 0.0
-    for ref, mine in pairs:
-        enc_r, mask_r = ref.enc.encode(images)
-        enc, mask = mine.encode(images)
-        ref_sum = ref_sum + next_logits(ref.dec.decoder, ids, enc_r, mask_r)
-        mine_sum = mine_sum + mine.dec.decoder.next_token_logits(ids.cuda(), enc, mask).float().cpu()
-    return ((mine_sum - ref_sum).abs().max() / ref_sum.abs().max()).item()
-
-
-def test_cached_step_matches_prefix_recompute(cuda_dev):
-    """KV-cached single-token steps produce the same next-token logits as re-running the whole prefix, and as the oracle."""
-    from oracle.decode import next_logits
-    from vilmedic_b200 import synth
-    from vilmedic_b200.blocks.huggingface.decoder.generation import DecodeState
+def test_generation_config_object_and_unknown_arguments(cuda_dev):
+    """a reference-style generate(generation_config=...) call must be honoured, unknown arguments must raise."""
+    from types import SimpleNamespace
     ref, mine = _pair(3)
-    batch = synth.rrg_batch(3, 10, 300, seed=2)
-    enc, mask = mine.encode(batch["images"])
-    enc_r, mask_r = ref.enc.encode(batch["images"])
+    enc, mask = _features(ref, 3, 2)
     dec = mine.dec.decoder
-    ids = batch["input_ids"].cuda()[:, :9]
-    st = DecodeState(dec, 3, 16, enc, mask)
-    for t in range(ids.shape[1]):
-        step = dec.decode_step(st, ids[:, t])
-        full = dec.next_token_logits(ids[:, :t + 1], enc, mask)
-        want = next_logits(ref.dec.decoder, ids[:, :t + 1].cpu(), enc_r, mask_r)
-        tol = 2 ** -4 * want.abs().max().item() + 5e-2     # logits of these x30-scaled embeddings reach |150|
-        assert (step - full).abs().max().item() <= tol, t
-        assert (step.cpu() - want).abs().max().item() <= tol, t
-    a = dec.generate(input_ids=ids[:, :1], encoder_hidden_states=enc, encoder_attention_mask=mask, max_length=12, num_beams=3,
-                     bos_token_id=BOS, eos_token_id=EOS, pad_token_id=PAD, use_cache=True)
-    b = dec.generate(input_ids=ids[:, :1], encoder_hidden_states=enc, encoder_attention_mask=mask, max_length=12, num_beams=3,
-                     bos_token_id=BOS, eos_token_id=EOS, pad_token_id=PAD, use_cache=False)
-    assert a.shape == b.shape
+    ids = torch.full((3, 1), BOS, dtype=torch.long, device="cuda")
+    gc = SimpleNamespace(max_length=9, num_beams=2, length_penalty=1.0, bos_token_id=BOS, eos_token_id=EOS, pad_token_id=PAD,
+                         num_return_sequences=1, use_cache=True)
+    a = dec.generate(input_ids=ids, encoder_hidden_states=enc.cuda(), encoder_attention_mask=mask.cuda(), generation_config=gc)
+    b = dec.generate(input_ids=ids, encoder_hidden_states=enc.cuda(), encoder_attention_mask=mask.cuda(), max_length=9, num_beams=2,
+                     bos_token_id=BOS, eos_token_id=EOS, pad_token_id=PAD)
+    assert torch.equal(a, b) and a.shape[1] <= 9
+    c = dec.generate(input_ids=ids, encoder_hidden_states=enc.cuda(), encoder_attention_mask=mask.cuda(), max_length=9, num_beams=2,
+                     bos_token_id=BOS, eos_token_id=EOS, pad_token_id=PAD, use_cache=False)               # host loop, full recompute
+    assert c.shape[0] == 3
+    with pytest.raises(TypeError):
+        dec.generate(input_ids=ids, encoder_hidden_states=enc.cuda(), temperature=0.7)
+    with pytest.raises(NotImplementedError):
+        dec.generate(input_ids=ids, encoder_hidden_states=enc.cuda(), generation_config=SimpleNamespace(do_sample=True))

@@ -13,74 +13,92 @@ from ....nn import _ln, _lin, _prepare, _root_of
 
 
 class DecodeState:
-    """Per-model decoding state for `rows` = batch * beams sequences."""
+    """Per-model state of one search over `rows` = batch * beams sequences.
 
-    def __init__(self, tower, rows, max_len, enc, enc_mask):
+    HBM layout: per layer one self-attention cache bf16 [rows, max_len, 2D] ([K | V] per position) that is only ever APPENDED to —
+    beam reordering permutes the shared int32 table `row_map` [rows, max_len] (which physical row holds position j of row r's
+    history) instead of copying caches (beam_search.py:317-319 does an index_select per layer per step); cross-attention K/V are
+    projected once per IMAGE, bf16 [batch, S_enc, 2D] per layer, and shared by the image's beams."""
+
+    def __init__(self, tower, batch, beams, max_len, row_map, t_ptr):
         cfg = tower.cfg
         self.tower = tower
-        self.rows, self.max_len, self.t = rows, max_len, 0
+        self.batch, self.beams, self.rows, self.max_len = batch, beams, batch * beams, max_len
+        self.row_map, self.t_ptr = row_map, t_ptr
         D = cfg.hidden_size
-        dev = enc.device if enc is not None else next(tower.parameters()).device
         self.arena = get_arena(_root_of(tower))
+        dev = self.arena.device
         _prepare(self.arena, tower)
-        self.self_kv = [torch.empty((rows, max_len, 2 * D), device=dev, dtype=torch.bfloat16) for _ in tower._core.encoder.layer]
+        self.self_kv = [torch.empty((self.rows, max_len, 2 * D), device=dev, dtype=torch.bfloat16) for _ in tower._core.encoder.layer]
         self.cross_kv = []
         self.enc_mask = None
-        if enc is not None:
-            e = enc if enc.dtype == torch.bfloat16 else ops.cast_bf16(enc.float().contiguous())
-            Se = e.shape[1]
-            e2 = e.reshape(rows * Se, e.shape[2]).contiguous()
-            for layer in tower._core.encoder.layer:
-                ca = layer.crossattention.self
-                Pkv = _lin(self.arena, ca.key, ca.value)
-                self.cross_kv.append(ops.gemm(e2, Pkv.w, bias=Pkv.b).view(rows, Se, 2 * D))
-            if enc_mask is not None:
-                self.enc_mask = (enc_mask != 0).to(torch.uint8).contiguous()
+        self.enc_len = 0
 
-    def reorder(self, idx):
-        """Beam bookkeeping: row r continues hypothesis idx[r] (cache reorder of beam_search.py:317-319).  Cross K/V are
-        identical for all beams of a batch element, so only the self-attention cache moves."""
-        for i, kv in enumerate(self.self_kv):
-            self.self_kv[i] = kv.index_select(0, idx)
+    def set_encoder(self, enc, enc_mask):
+        """enc [batch, S_enc, D_enc] (one row per image): project the cross-attention K/V of every layer into static buffers."""
+        tower = self.tower
+        if enc is None:
+            self.cross_kv, self.enc_mask, self.enc_len = [], None, 0
+            return
+        _prepare(self.arena, tower)
+        e = enc if enc.dtype == torch.bfloat16 else ops.cast_bf16(enc.float().contiguous())
+        Bn, Se = e.shape[0], e.shape[1]
+        if Bn != self.batch:
+            raise ValueError("encoder states for %d images, search over %d" % (Bn, self.batch))
+        D = tower.cfg.hidden_size
+        e2 = e.reshape(Bn * Se, e.shape[2]).contiguous()
+        fresh = not self.cross_kv or self.enc_len != Se
+        if fresh:
+            self.cross_kv = [torch.empty((Bn, Se, 2 * D), device=e.device, dtype=torch.bfloat16) for _ in tower._core.encoder.layer]
+        for li, layer in enumerate(tower._core.encoder.layer):
+            ca = layer.crossattention.self
+            Pkv = _lin(self.arena, ca.key, ca.value)
+            ops.gemm(e2, Pkv.w, bias=Pkv.b, out=self.cross_kv[li].view(Bn * Se, 2 * D))
+        self.enc_len = Se
+        if enc_mask is not None:
+            m = (enc_mask != 0).to(torch.uint8).contiguous()
+            if self.enc_mask is None or fresh:
+                self.enc_mask = m
+            else:
+                self.enc_mask.copy_(m)
+        else:
+            self.enc_mask = None
+        return fresh
 
 
 class GenerationMixinB200:
     @torch.no_grad()
     def decode_step(self, state, tokens):
-        """tokens int64 [rows] at position state.t -> fp32 next-token logits [rows, V]; advances the state."""
+        """tokens int64 [rows] = the token of every row at position *state.t_ptr -> fp32 next-token logits [rows, V].
+        Appends the step's keys / values to the caches; every per-step scalar is read from device memory (graph-replayable)."""
         cfg = self.cfg
         arena = state.arena
         D, H = cfg.hidden_size, cfg.num_attention_heads
         DH = D // H
         eps = cfg.layer_norm_eps
-        R, t = state.rows, state.t
-        if t >= state.max_len:
-            raise IndexError("decode_step beyond max_len")
         core = self._core
         emb = core.embeddings
-        z = ops.embed_fwd(tokens.contiguous(), arena.fp32(emb.word_embeddings.weight), arena.fp32(emb.position_embeddings.weight), 1, t)
+        z = ops.embed_step(tokens, arena.fp32(emb.word_embeddings.weight), arena.fp32(emb.position_embeddings.weight), state.t_ptr)
         lnp = _ln(arena, emb.LayerNorm)
         x, _, _ = ops.layernorm_fwd(z, lnp[0], lnp[1], eps, save_stats=False)
         for li, layer in enumerate(core.encoder.layer):
             sa = layer.attention
-            Pq = _lin(arena, sa.self.query)
-            Pkv = _lin(arena, sa.self.key, sa.self.value)
+            Pqkv = _lin(arena, sa.self.query, sa.self.key, sa.self.value)
             Po = _lin(arena, sa.output.dense)
             ln1 = _ln(arena, sa.output.LayerNorm)
-            q = ops.gemm(x, Pq.w, bias=Pq.b)
-            kv = state.self_kv[li]
-            ops.gemm(x, Pkv.w, bias=Pkv.b, out=kv[:, t, :])
-            ctx, _ = ops.attention_fwd(q.view(R, 1, D), kv[:, :t + 1, :D], kv[:, :t + 1, D:], H, DH)
-            z1 = ops.gemm(ctx.view(R, D), Po.w, bias=Po.b, residual=x)
+            qkv = ops.gemm(x, Pqkv.w, bias=Pqkv.b)                                   # [rows, 3D]: q | k | v of the new token
+            ctx = ops.decode_attention(qkv[:, :D], H, DH, state.self_kv[li], kv_new=qkv[:, D:], row_map=state.row_map,
+                                       t_ptr=state.t_ptr, max_len=state.max_len)
+            z1 = ops.gemm(ctx, Po.w, bias=Po.b, residual=x)
             x1, _, _ = ops.layernorm_fwd(z1, ln1[0], ln1[1], eps, save_stats=False)
             if state.cross_kv:
                 ca = layer.crossattention
                 Pqc, Poc = _lin(arena, ca.self.query), _lin(arena, ca.output.dense)
                 ln2 = _ln(arena, ca.output.LayerNorm)
-                ckv = state.cross_kv[li]
                 qc = ops.gemm(x1, Pqc.w, bias=Pqc.b)
-                ctx2, _ = ops.attention_fwd(qc.view(R, 1, D), ckv[:, :, :D], ckv[:, :, D:], H, DH, kmask=state.enc_mask)
-                z2 = ops.gemm(ctx2.view(R, D), Poc.w, bias=Poc.b, residual=x1)
+                ctx2 = ops.decode_attention(qc, H, DH, state.cross_kv[li], fixed_len=state.enc_len, row_div=state.beams,
+                                            kmask=state.enc_mask)
+                z2 = ops.gemm(ctx2, Poc.w, bias=Poc.b, residual=x1)
                 x2, _, _ = ops.layernorm_fwd(z2, ln2[0], ln2[1], eps, save_stats=False)
             else:
                 x2 = x1
@@ -89,8 +107,7 @@ class GenerationMixinB200:
             h = ops.gemm(x2, P1.w, bias=P1.b, act=ops.ACT_GELU)
             z3 = ops.gemm(h, P2.w, bias=P2.b, residual=x2)
             x, _, _ = ops.layernorm_fwd(z3, ln3[0], ln3[1], eps, save_stats=False)
-        state.t += 1
-        return self.lm_logits(x)
+        return self.lm_logits(x, padded=True)
 
     @torch.no_grad()
     def next_token_logits(self, input_ids, encoder_hidden_states=None, encoder_attention_mask=None):

@@ -802,8 +802,8 @@ class BertTower(nn.Module):
         grad = torch.is_grad_enabled()
         return LMHeadCEFn.apply(x, self._core.embeddings.LayerNorm.weight, ids, self.lm_head, arena, B, T, keep_logits, grad)
 
-    def lm_logits(self, x):
-        """bf16 [M,D] -> fp32 [M,V] logits (inference)."""
+    def lm_logits(self, x, padded=False):
+        """bf16 [M,D] -> fp32 [M,V] logits (inference); padded=True returns the [M, Vp] buffer (row pitch Vp = V rounded up to 4)."""
         arena = get_arena(_root_of(self))
         E = self.lm_head.decoder.weight
         V = E.shape[0]
@@ -815,7 +815,7 @@ class BertTower(nn.Module):
             bp[:V] = bias
             bias = bp
         ops.gemm(x, arena.bf16(E), out=out[:, :V], bias=bias)
-        return out[:, :V]
+        return out if padded else out[:, :V]
 
 
 class CastBf16Fn(torch.autograd.Function):

@@ -14,7 +14,7 @@ ACT_NONE, ACT_GELU, ACT_GELU_GRAD = 0, 1, 2
 
 # Number of OUR kernels launched through this module (bench.py reports it as `gpu_launches`).
 LAUNCHES = [0]
-_KERNELS_PER_CALL = {"vlm_attention_bwd": 2, "vlm_attention_bwd_tc": 2, "vlm_adamw_step": 2}
+_KERNELS_PER_CALL = {"vlm_attention_bwd": 2, "vlm_attention_bwd_tc": 2, "vlm_adamw_step": 2, "vlm_beam_advance": 2}
 # Optional recording of the GEMM launches (bench.py roofline pass): list of (M, N, K, batch, algorithmic HBM bytes =
 # operands read once + outputs written once, replay closure, operands kept alive)
 GEMM_TIMING = None
@@ -571,3 +571,59 @@ def avgpool_bwd(dy, B, HW, C):
 
 def rng_advance(counter, delta):
     check(_L().vlm_rng_advance(ptr(counter), c_u64(delta), stream_ptr()), "vlm_rng_advance")
+
+
+# ---- incremental decoding / device-side beam search (csrc/decode.cu) ------------------------------------------------------------
+def embed_step(tok, word, pos, t_ptr):
+    """tok int64 [R] (device), position read from the device counter t_ptr -> bf16 [R, D]."""
+    _req(tok.dtype == torch.int64 and tok.is_contiguous() and t_ptr.dtype == torch.int32, "embed_step: tok int64, t_ptr int32")
+    R = tok.numel()
+    V, D = word.shape
+    z = torch.empty((R, D), device=word.device, dtype=torch.bfloat16)
+    check(_L().vlm_embed_step(ptr(tok), ptr(word), ptr(pos), ptr(z), c_int(R), c_int(D), c_int(V), ptr(t_ptr), c_int(pos.shape[0]),
+                              stream_ptr()), "vlm_embed_step")
+    return z
+
+
+def decode_attention(q, H, DH, cache, *, kv_new=None, row_map=None, t_ptr=None, fixed_len=0, row_div=1, kmask=None, max_len=0):
+    """q bf16 [R, >=H*DH] view; cache bf16 [rows, L, 2*H*DH].  Self-attention: kv_new [R, 2*H*DH] view + row_map int32 [R, max_len] +
+    t_ptr; cross-attention: fixed_len / row_div (+ kmask uint8 [rows, fixed_len]).  -> bf16 [R, H*DH]."""
+    R = q.shape[0]
+    D = H * DH
+    _req(q.dtype == torch.bfloat16 and q.stride(1) == 1 and cache.dtype == torch.bfloat16 and cache.is_contiguous() and cache.shape[2] == 2 * D,
+         "decode_attention: q bf16 rows, cache contiguous bf16 [rows, L, 2D]")
+    out = torch.empty((R, D), device=q.device, dtype=torch.bfloat16)
+    if kv_new is not None:
+        _req(kv_new.dtype == torch.bfloat16 and kv_new.stride(1) == 1 and row_map.dtype == torch.int32 and row_map.is_contiguous(),
+             "decode_attention: kv_new bf16 rows, row_map contiguous int32")
+    if kmask is not None:
+        _req(kmask.dtype == torch.uint8 and kmask.is_contiguous(), "decode_attention: kmask uint8 contiguous")
+    check(_L().vlm_decode_attention(ptr(q), c_ll(q.stride(0)), ptr(kv_new), c_ll(kv_new.stride(0) if kv_new is not None else 0), ptr(cache),
+                                    c_ll(cache.stride(0)), c_int(2 * D), ptr(row_map), c_int(row_map.shape[1] if row_map is not None else 0),
+                                    ptr(t_ptr), c_int(fixed_len), c_int(row_div), ptr(kmask), c_int(kmask.shape[1] if kmask is not None else 0),
+                                    ptr(out), c_ll(out.stride(0)), c_int(R), c_int(H), c_int(DH), c_float(1.0 / DH ** 0.5),
+                                    c_int(max_len if kv_new is not None else max(fixed_len, 1)), stream_ptr()), "vlm_decode_attention")
+    return out
+
+
+def beam_rows(logits_list, V, beam_scores, cand_score, cand_tok, k):
+    """logits_list: fp32 [R, ld] tensors (one per ensemble member, same pitch)."""
+    n = len(logits_list)
+    ld = logits_list[0].stride(0)
+    for l in logits_list:
+        _req(l.dtype == torch.float32 and l.stride(1) == 1 and l.stride(0) == ld, "beam_rows: fp32 logits with equal row pitch")
+    arr = (ctypes.c_void_p * n)(*[l.data_ptr() for l in logits_list])
+    check(_L().vlm_beam_rows(arr, c_int(n), c_ll(ld), c_int(V), ptr(beam_scores), ptr(cand_score), ptr(cand_tok),
+                             c_int(beam_scores.numel()), c_int(k), stream_ptr()), "vlm_beam_rows")
+
+
+def beam_select(st, k, V, B, max_len, eos, pad, length_penalty):
+    check(_L().vlm_beam_select(ptr(st["cand_score"]), ptr(st["cand_tok"]), c_int(k), c_int(V), c_int(B), c_int(max_len), ptr(st["ids"]),
+                               ptr(st["beam_scores"]), ptr(st["done"]), ptr(st["next_tok"]), ptr(st["parent"]), ptr(st.get("hyp_score")),
+                               ptr(st.get("hyp_len")), ptr(st.get("hyp_tok")), ptr(st.get("hyp_count")), ptr(st.get("hyp_worst")),
+                               ptr(st["counters"]), c_int(eos), c_int(pad), ctypes.c_double(length_penalty), stream_ptr()), "vlm_beam_select")
+
+
+def beam_advance(st, R, max_len):
+    check(_L().vlm_beam_advance(ptr(st["ids"]), ptr(st["ids_tmp"]), ptr(st["row_map"]), ptr(st["map_tmp"]), ptr(st["parent"]),
+                                ptr(st["next_tok"]), c_int(R), c_int(max_len), ptr(st["counters"]), stream_ptr()), "vlm_beam_advance")
