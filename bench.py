@@ -199,22 +199,22 @@ def run_ours(args):
     devb = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values() if isinstance(v, torch.Tensor))
     from vilmedic_b200.ddp import GradSync
-    sync = GradSync(arena)
+    sync = GradSync(arena).attach()       # per-layer gradient buckets, launched from the backward pass (ddp.py)
 
     def train_step(batch, read_loss, exchange=True):
         """exchange=False: rank-local step without the gradient all-reduce (instrumented passes that only one rank runs)."""
-        if world > 1 and exchange:
-            # the decoder's gradients are complete once the backward reaches the image features: all-reduce that span
-            # (NCCL stream, NVLink) while the ViT backward is still running; the encoder span follows.
-            feats, fmask = model.encode(batch["images"], batch.get("images_mask"))
-            if feats.requires_grad:
-                feats.register_hook(lambda g: (sync.launch_span("dec"), g)[1])
-            out = model(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"], images=None,
-                        encoder_outputs=feats, encoder_attention_mask=fmask)
-        else:
+        # world > 1: every layer's backward announces its gradient span (nn.notify_grad_ready -> GradSync.on_ready) and the
+        # all-reduce of that bucket runs on NCCL's stream / NVLink under the backward of the layers below it
+        from vilmedic_b200 import nn as vnn
+        hook = vnn.GRAD_READY_HOOK[0]
+        if not exchange:
+            vnn.GRAD_READY_HOOK[0] = None
+        try:
             out = model(**batch)
-        loss = out["loss"]
-        loss.backward()
+            loss = out["loss"]
+            loss.backward()
+        finally:
+            vnn.GRAD_READY_HOOK[0] = hook
         opt.step(grad_scale=sync.finish() if exchange else 1.0)
         if read_loss:
             return loss.item()

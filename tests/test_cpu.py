@@ -388,11 +388,29 @@ def _gloo_worker(rank, world, port, q):
     m = RRG(dec, cnn)
     a = get_arena(m)
     a.flat_grad.copy_(torch.arange(a.numel, dtype=torch.float32) * 1e-3 * (rank + 1))
-    sync = GradSync(a)
-    sync.launch_span("dec")           # as the hook at the encoder boundary would
-    scale = sync.finish()             # encoder span + tail, wait for all
+    sync = GradSync(a, bucket_bytes=1 << 16).attach()
+    # announce the layers the way the hand-written backward does (nn.notify_grad_ready): LM head, decoder layers top-down, decoder
+    # embeddings, ViT layers top-down, patch embedding — adjacent spans merge into buckets, finish() sends what nobody announced
+    from vilmedic_b200 import nn as vnn
+    d = m.dec.decoder
+    order = [d.lm_head] + list(reversed(d.bert.encoder.layer)) + [d.bert.embeddings] + list(reversed(m.enc.model.encoder.layer)) + \
+        [m.enc.model.embeddings]
+    spans = [a.module_spans[id(x)] for x in order]
+    layer_spans = [a.module_spans[id(x)] for x in d.bert.encoder.layer]
+    contiguous = all(layer_spans[i][1] == layer_spans[i + 1][0] for i in range(len(layer_spans) - 1))     # one span per layer, adjacent
+    for x in order:
+        vnn.notify_grad_ready(x)
+    launched_early = sync.launches
+    scale = sync.finish()             # leftovers + wait for all
+    sync.detach()
     want = torch.arange(a.numel, dtype=torch.float32) * 1e-3 * sum(r + 1 for r in range(world))
-    ok = torch.allclose(a.flat_grad, want) and abs(scale - 1.0 / world) < 1e-12
+    ok = torch.allclose(a.flat_grad, want) and abs(scale - 1.0 / world) < 1e-12        # every element reduced exactly once
+    ok = ok and contiguous and launched_early >= 2 and all(hi > lo for lo, hi in spans) and vnn.GRAD_READY_HOOK[0] is None
+    # a second step reuses the object (state reset by finish); launch_span still works for tower-level callers
+    a.flat_grad.copy_(torch.arange(a.numel, dtype=torch.float32) * 1e-3 * (rank + 1))
+    sync.launch_span("dec")
+    sync.finish()
+    ok = ok and torch.allclose(a.flat_grad, want)
     # p.grad views see the reduced values
     p = m.enc.model.layernorm.weight
     ok = ok and torch.allclose(p.grad, want[a.offsets[id(p)]:a.offsets[id(p)] + p.numel()])

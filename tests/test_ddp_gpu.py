@@ -1,0 +1,22 @@
+"""Data-parallel gradient exchange on REAL GPUs: launches tools/ddp_check.py under torchrun with 2 ranks — after one
+fused optimizer step the two replicas must be bit-identical and their update must equal the full-batch single-GPU update within
+bf16 gradient noise.  Skipped on single-GPU boxes (the gloo world-2 test in tests/test_cpu.py covers the host logic there)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_rank_step_equals_full_batch_step():
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tools", "ddp_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "replicas identical=True" in r.stdout

@@ -60,7 +60,8 @@ def test_gemm_epilogue(cuda_dev):
     h = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, aux_out=pre)
     torch.cuda.synchronize()
     assert (pre.float() - dgelu_ref).abs().max().item() < 2 ** -8 * 1.2 + 1e-3        # |GELU'| <= 1.13: one bf16 ulp
-    assert (h.float() - torch.nn.functional.gelu(pre_ref)).abs().max().item() < 3e-2
+    g_ref = torch.nn.functional.gelu(pre_ref)
+    assert ((h.float() - g_ref).abs() - 2 ** -8 * g_ref.abs()).max().item() < 2e-3        # one bf16 ulp of the value + erf approximation
     h_nostash = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU)
     assert torch.equal(h, h_nostash)
     # bias + residual, bf16 and fp32 outputs

@@ -40,14 +40,14 @@ def main():
     shard = {k: (v[rank * b:(rank + 1) * b].to(dev) if isinstance(v, torch.Tensor) else v) for k, v in full.items()}
 
     model, arena, opt = make()
-    sync = GradSync(arena)
-    feats, fmask = model.encode(shard["images"], shard.get("images_mask"))
-    feats.register_hook(lambda g: (sync.launch_span("dec"), g)[1])
-    out = model(input_ids=shard["input_ids"], attention_mask=shard["attention_mask"], images=None, encoder_outputs=feats,
-                encoder_attention_mask=fmask)
+    sync = GradSync(arena, bucket_bytes=8 << 20).attach()      # per-layer buckets launched from the backward pass
+    out = model(**shard)
     out["loss"].backward()
+    early = sync.launches
     opt.step(grad_scale=sync.finish())
+    sync.detach()
     torch.cuda.synchronize()
+    assert early >= 2, "no gradient bucket was launched during the backward pass"
 
     # (a) replicas identical after the step
     mine = arena.flat.clone()

@@ -24,15 +24,17 @@ class ParamArena:
         order = []
         placed = set()
         self.child_spans = {}
+        owners = []                     # (module, first group index, one-past-last group index): parameters owned by the subtree
         children = list(root.named_children()) or [("", root)]
         blocks = [(name, child) for name, child in children]
         direct = [p for p in root.parameters(recurse=False)]
-        for name, child in blocks:
+
+        def place_subtree(mod):
+            """Depth-first: a module's fused groups, then its own parameters, then its children — so that the parameters of one
+            transformer layer occupy ONE contiguous span (the gradient exchange is bucketed per layer, ddp.py)."""
             start = len(order)
-            for m in child.modules():
-                fn = getattr(m, "_fused_param_groups", None)
-                if fn is None:
-                    continue
+            fn = getattr(mod, "_fused_param_groups", None)
+            if fn is not None:
                 for g in fn():
                     g = list(g)
                     if any(id(p) in placed for p in g):
@@ -40,10 +42,17 @@ class ParamArena:
                     for p in g:
                         placed.add(id(p))
                     order.append(g)
-            for p in child.parameters():
+            for p in mod.parameters(recurse=False):
                 if id(p) not in placed:
                     placed.add(id(p))
                     order.append([p])
+            for ch in mod.children():
+                place_subtree(ch)
+            owners.append((mod, start, len(order)))
+
+        for name, child in blocks:
+            start = len(order)
+            place_subtree(child)
             self.child_spans[name] = (start, len(order))
         for p in direct:
             if id(p) not in placed:
@@ -68,6 +77,13 @@ class ParamArena:
                 hi = offsets[id(order[g1][0])] if g1 < len(order) else total
                 spans[name] = (lo, hi)
         self.child_spans = spans
+        # element span [lo, hi) of every module that owns at least one parameter slot (layers -> per-layer gradient buckets)
+        self.module_spans = {}
+        for mod, g0, g1 in owners:
+            if g1 > g0:
+                lo = offsets[id(order[g0][0])]
+                hi = offsets[id(order[g1][0])] if g1 < len(order) else total
+                self.module_spans[id(mod)] = (lo, hi)
         self.numel = total
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)

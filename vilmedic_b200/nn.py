@@ -18,6 +18,16 @@ from .arena import get_arena
 
 _RNG = {"seed": None, "offset": 0}
 
+# Data-parallel hook (ddp.GradSync.attach): called by the hand-written backward of a layer / embedding block once every gradient
+# of that module's parameter span is final, so that the exchange of the span can start under the rest of the backward.
+GRAD_READY_HOOK = [None]
+
+
+def notify_grad_ready(module):
+    hook = GRAD_READY_HOOK[0]
+    if hook is not None and module is not None:
+        hook(module)
+
 
 def _next_rng():
     if _RNG["seed"] is None:
@@ -193,6 +203,7 @@ class ViTEmbedFn(torch.autograd.Function):
         ops.gemm(dx, patches.view(B * S, Kp), a_mn_major=True, b_mn_major=True, out=gw, accumulate=True)
         ops.vit_embed_bwd(dx.view(B, S, D), arena.grad(mod.embeddings.position_embeddings, shape=(S, D)),
                           arena.grad(mod.embeddings.cls_token, shape=(D,)), arena.grad(proj.bias))
+        notify_grad_ready(mod.embeddings)
         return None, None, None, None
 
 
@@ -225,6 +236,7 @@ class ViTLayerFn(torch.autograd.Function):
         if save:
             ctx.saved = (x, h1, mean1, rstd1, qkv, ctxv, lse, x1, h2, mean2, rstd2, pre, hmid, Pqkv, Po, P1, P2, ln1, ln2, B, S, H, DH)
             ctx.fuse = (prev_gb, own_b2_fused)
+            ctx.layer = layer
         return x2
 
     @staticmethod
@@ -248,6 +260,7 @@ class ViTLayerFn(torch.autograd.Function):
         _wgrad(dqkv, h1, Pqkv)
         dh1 = _dgrad(dqkv, Pqkv)
         dx = ops.layernorm_bwd(dh1, x, mean1, rstd1, ln1[0], ln1[2], ln1[3], dres=dx1, colsum=prev_gb)
+        notify_grad_ready(ctx.layer)      # (this layer's FFN-down bias gradient was completed by the layer above / the final LayerNorm)
         return dx, None, None, None, None, None, None, None, None
 
 
@@ -453,6 +466,7 @@ class BertEmbedFn(torch.autograd.Function):
         pad = emb.word_embeddings.padding_idx
         ops.embed_bwd(ids, dz, arena.grad(emb.word_embeddings.weight), arena.grad(emb.position_embeddings.weight), T, V,
                       pos_offset, -1 if pad is None else int(pad))
+        notify_grad_ready(emb)            # the tied LM-head weight gradient was accumulated first (LMHeadCEFn.backward)
         return None, None, None, None, None, None, None
 
 
@@ -518,6 +532,7 @@ class BertLayerFn(torch.autograd.Function):
                          kmask=kmask, enc_mask=enc_mask, causal=causal, p_h=p_h, p_a=p_a, rng=rng, cross=cross)
             if cross:
                 ctx.c.update(Pq=Pq, Pkv=Pkv, Poc=Poc, ln2=ln2, qc=qc, kvc=kvc, ctx2=ctx2, lse2=lse2, z2=z2, m2=m2, r2=r2, Se=Se)
+            ctx.layer = layer
         return x3
 
     @staticmethod
@@ -579,6 +594,7 @@ class BertLayerFn(torch.autograd.Function):
                           p_drop=p_a, seed=s, offset=o)
         _wgrad(dqkv, c["x"], c["Pqkv"])
         dx = _dgrad(dqkv, c["Pqkv"], residual=dz1)
+        notify_grad_ready(ctx.layer)
         return (dx, denc) + (None,) * 10
 
 
@@ -622,6 +638,7 @@ class LMHeadCEFn(torch.autograd.Function):
         ops.gemm(dl[:, :V], h, a_mn_major=True, b_mn_major=True, out=gE, accumulate=True, alpha_t=g)
         ops.colsum(dl[:, :V], arena.grad(head.bias), g)
         dh = ops.gemm(dl[:, :V], arena.bf16(E), b_mn_major=True, alpha_t=g)
+        notify_grad_ready(head)           # lm_head.bias; the tied embedding matrix is announced with the embedding block
         return dh, None, None, None, None, None, None, None, None
 
 
