@@ -170,11 +170,14 @@ def test_rrg_parity_at_the_benchmarked_config(cuda_dev):
         e_lg = (out["logits"].float() - lg_ref).abs().max().item()
         worst, worst_ratio = (0.0, None), (0.0, None)
         rels = {}
+        gmax = max(g.norm().item() / g.numel() ** 0.5 for g in ref_grads.values())          # largest RMS gradient of any tensor
         for n, p in mine.named_parameters():
             g_ref = ref_grads[n]
             r = _rel(p.grad, g_ref)
             rels[n] = r
-            small = (p.grad.float() - g_ref).norm().item() <= 1e-5 * g_ref.numel() ** 0.5
+            # gradients that are exactly zero in exact arithmetic (key biases: softmax is shift invariant) — both sides ~0
+            small = g_ref.norm().item() <= 1e-5 * gmax * g_ref.numel() ** 0.5 and \
+                p.grad.float().norm().item() <= 1e-3 * gmax * g_ref.numel() ** 0.5
             if not small and r > worst[0]:
                 worst = (r, n)
             if not small and r / (ac_rel[n] + 1e-3) > worst_ratio[0]:

@@ -4,7 +4,7 @@
              --log-file gpurun_out/launches.csv python bench.py --quick --no-graph --steps 1 --warmup 3'
   python tools/launch_summary.py gpurun_out/launches.csv profiles/launches_rNN [--note "text for the header"]
 
-The last complete training step is cut out between two `adamw_kernel` launches.  Per-launch times under ncu are cold-cache
+The last complete training step is cut out between two `optim_kernel` launches.  Per-launch times under ncu are cold-cache
 and serialised: compare shares, not absolutes."""
 import collections
 import csv

@@ -170,8 +170,25 @@ class DeviceSearch:
         self.sig = None
 
     def _step(self):
+        """One search step.  The ensemble members are independent until their logits are summed: each runs on its own stream, so
+        that inside the captured graph they form parallel branches (a decode step is ~300 small, launch-latency-bound kernels per
+        model; two branches overlap them)."""
         st = self.search.st
-        self.search.select([m.decode_step(s, st["next_tok"]) for m, s in zip(self.models, self.states)])
+        cur = torch.cuda.current_stream()
+        if len(self.models) == 1:
+            logits = [self.models[0].decode_step(self.states[0], st["next_tok"])]
+        else:
+            if not hasattr(self, "_streams"):
+                self._streams = [torch.cuda.Stream() for _ in self.models[1:]]
+            logits = [None] * len(self.models)
+            for i, side in enumerate(self._streams, start=1):
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    logits[i] = self.models[i].decode_step(self.states[i], st["next_tok"])
+            logits[0] = self.models[0].decode_step(self.states[0], st["next_tok"])
+            for side in self._streams:
+                cur.wait_stream(side)
+        self.search.select(logits)
 
     @torch.no_grad()
     def run(self, encs, masks, input_ids, eos, pad, length_penalty):

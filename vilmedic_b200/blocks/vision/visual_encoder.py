@@ -23,7 +23,7 @@ import torch.nn as nn
 from ... import ops
 from ...arena import get_arena
 from ...cfgutil import cfg_get
-from ...nn import CastBf16Fn, DropoutFn, LinearFn, ViTTower, _lin, _root_of, _prepare
+from ...nn import CastBf16Fn, DropoutFn, LinearFn, ViTTower, _lin, _root_of, _prepare, set_arena_root
 
 __all__ = ["VisualEncoder", "get_network"]
 
@@ -91,6 +91,9 @@ class VisualEncoder(nn.Module):
         if freeze:
             for _, param in self.model.named_parameters():
                 param.requires_grad = False
+        # stand-alone use (no enclosing model): tower and projection share ONE parameter arena rooted here; a model that embeds this
+        # block re-roots every sub-module at itself (set_arena_root in RRG / ConVIRT / MVQA)
+        set_arena_root(self)
 
     # ------------------------------------------------------------------------------------------------ encode
     def _project(self, feats2d):
