@@ -596,6 +596,9 @@ def run_other_workload(args):
             graphed = None
             note = "eager launches (graph capture failed: %s)" % (str(e).splitlines()[0][:160],)
             torch.cuda.synchronize()
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
     if world > 1:
         ok = torch.tensor([1 if graphed is not None else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define VLM_B200_ABI_VERSION 1
+#define VLM_B200_ABI_VERSION 2
 
 /* ---- runtime ---------------------------------------------------------------------------------------------------- */
 const char* vlm_last_error(void);
@@ -111,10 +111,12 @@ int vlm_attention_bwd_tc(const void* q, long long q_bs, long long q_rs, const vo
  * shift_T > 0: ids is input_ids [R = B*T]; the label of row (b,t) is ids[b,t+1], the last position of each sequence
  * is ignored — HF:loss/loss_utils.py:45-66 reached via vilmedic/blocks/huggingface/decoder/decoder_model.py:46
  * (labels=input_ids, pads are NOT masked).  shift_T == 0: ids are labels [R], negative = ignore.
- * smoothing: vilmedic/blocks/losses/mvqa/LabelSmoothingCrossEntropyLoss.py:38-48. */
+ * smoothing: vilmedic/blocks/losses/mvqa/LabelSmoothingCrossEntropyLoss.py:38-48.
+ * row_weight (optional fp32 [R]): multiplies the gradient of row r (reward-weighted log-likelihood of vilmedic/blocks/rl/SCST.py:12-44);
+ * -inf logits (filtered tokens) contribute nothing to the log-sum-exp and get a zero gradient. */
 int vlm_softmax_ce(const void* logits, int logits_fp32, long long ld, const long long* ids, int shift_T, int R, int V,
                    float smoothing, float grad_scale, void* dlogits, long long ldd, float* loss_rows, float* lse_rows,
-                   void* stream);
+                   const float* row_weight, void* stream);
 
 /* ---- helpers around the core ------------------------------------------------------------------------------------ */
 int vlm_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
@@ -260,11 +262,21 @@ int vlm_beam_rows(const float* const* logits, int n_models, long long ld, int V,
  * then BeamSearchScorer.process (:297-304; legacy BeamHypotheses semantics: EOS candidates ranked >= k are skipped, a finished
  * hypothesis scores sum_logprobs / len**length_penalty (double), is_done when k are finished and the worst kept score >= the best
  * running score / len**length_penalty).  Writes next_tok / parent / beam_scores [B*k]; k == 1 is greedy argmax decoding (finished
- * rows emit pad).  counters: {t, number of finished batch elements, sequence length at which the last one finished, -}. */
+ * rows emit pad; forced_last_token >= 0 is emitted at the last position like HF's ForcedEOSTokenLogitsProcessor, -1 = off).
+ * counters: {t, number of finished batch elements, sequence length at which the last one finished, -}. */
 int vlm_beam_select(const float* cand_score, const int* cand_tok, int k, int V, int B, int max_len, const long long* ids,
                     float* beam_scores, uint8_t* done, long long* next_tok, int* parent, double* hyp_score, int* hyp_len,
                     long long* hyp_tok, int* hyp_count, double* hyp_worst, int* counters, int eos, int pad, double length_penalty,
-                    void* stream);
+                    int forced_last_token, void* stream);
+/* Sampling rollouts of SCST (vilmedic/blocks/rl/SCST.py:139-153, generate(do_sample=True, top_k, bad_words_ids)).
+ * vlm_logits_filter (in place, bf16 or fp32 rows): HF NoBadWordsLogitsProcessor for <= 8 single-token ids (HOST array) -> -inf, then
+ *   TopKLogitsWarper: scores below the k-th largest -> -inf (ties kept), top_k = 0 off.
+ * vlm_sample_rows: one token per row ~ softmax(logits / temperature) (Gumbel-max over Philox(seed, offset + counters[0] + (counters[3] << 16),
+ *   row, v); t_ptr = the search's 4-int counters: [0] step, [3] per-rollout nonce), written
+ *   with its log-probability to slot 0 of cand_tok / cand_score [R, 2]; vlm_beam_select(k = 1) then does the EOS / pad bookkeeping. */
+int vlm_logits_filter(void* logits, int logits_fp32, long long ld, int R, int V, const int* bad_ids, int n_bad, int top_k, void* stream);
+int vlm_sample_rows(const float* logits, long long ld, int V, float temperature, unsigned long long seed, unsigned long long offset,
+                    const int* t_ptr, float* cand_score, int* cand_tok, int R, void* stream);
 /* ids[r] <- ids[parent[r]] + next_tok[r]; row_map[r] <- row_map[parent[r]] (through the tmp buffers); counters[0] += 1. */
 int vlm_beam_advance(long long* ids, long long* ids_tmp, int* row_map, int* map_tmp, const int* parent, const long long* next_tok, int R,
                      int max_len, int* counters, void* stream);

@@ -51,7 +51,8 @@ def ensemble_beam_search(decoders, encs, masks, num_beams, max_length, bos, eos,
     2k+1 (k>1) or top-2 (greedy) — how close the fp32 search came to a tie (tests use it to qualify bit-exactness).
     trace: optional list that receives (step, batch row, gap, max |summed logit| of that row's beams) for the same decisions:
     a bf16 implementation carries a logit error proportional to the logit magnitude, so tests qualify by gap / scale.
-    on_step: optional callback(cur_len, ids [B*k, cur_len], scores [B*k], done list) called after every step's update."""
+    on_step: optional callback(cur_len, ids [B*k, cur_len], scores [B*k], done list) called after every step's update; with
+    num_beams > 1 it also receives parents=[B*k] (source row of every new beam) and tokens=[B*k] as keyword arguments."""
     B, k = encs[0].shape[0], num_beams
     ids = torch.full((B * k, 1), bos, dtype=torch.long)
     encs = [e.repeat_interleave(k, 0) for e in encs]
@@ -121,7 +122,10 @@ def ensemble_beam_search(decoders, encs, masks, num_beams, max_length, bos, eos,
         ids = torch.cat([ids[nb.view(-1)], nt.view(-1, 1)], 1)
         cur += 1
         if on_step is not None:
-            on_step(cur, ids.clone(), scores.clone(), list(done))
+            try:
+                on_step(cur, ids.clone(), scores.clone(), list(done), parents=nb.view(-1).clone(), tokens=nt.view(-1).clone())
+            except TypeError:
+                on_step(cur, ids.clone(), scores.clone(), list(done))
         if all(done):
             break
     if k == 1:

@@ -46,10 +46,17 @@ class _Hyps:
 
 @torch.no_grad()
 def beam_search(models, encs, masks, input_ids, max_length, num_beams, bos_token_id, eos_token_id, pad_token_id,
-                length_penalty=1.0, use_cache=True):
+                length_penalty=1.0, use_cache=True, sampling=None, forced_last=-1):
+    """sampling: None (greedy / beam) or dict(top_k, bad_ids, temperature, seed) -> multinomial rollouts (SCST.py:139-153)."""
+    if sampling is not None and (num_beams != 1 or len(models) != 1 or not use_cache or input_ids.shape[1] != 1):
+        raise NotImplementedError("sampling is supported for a single model, num_beams=1, from a one-token prompt")
+    if forced_last >= 0 and num_beams != 1:
+        raise NotImplementedError("forced_eos_token_id is supported for num_beams=1 only")
     if use_cache and input_ids.shape[1] == 1:
         return DeviceSearch.get(models, input_ids.shape[0], num_beams, max_length).run(
-            encs, masks, input_ids, eos_token_id, pad_token_id, length_penalty)
+            encs, masks, input_ids, eos_token_id, pad_token_id, length_penalty, sampling=sampling, forced_last=forced_last)
+    if forced_last >= 0:
+        raise NotImplementedError("forced_eos_token_id needs the cached device search")
     return _beam_search_host(models, encs, masks, input_ids, max_length, num_beams, bos_token_id, eos_token_id, pad_token_id,
                              length_penalty)
 
@@ -97,13 +104,25 @@ class SearchState:
             st["hyp_score"].zero_()
         self.consts = (int(eos), int(pad), float(lp))
 
-    def select(self, logits):
-        """logits: list of fp32 [rows, ld >= V] next-token logits (one per ensemble member) for the tokens in st['next_tok']."""
+    def select(self, logits, sampling=None, forced_last=-1, advance=True):
+        """logits: list of fp32 [rows, ld >= V] next-token logits (one per ensemble member) for the tokens in st['next_tok'].
+        sampling = dict(top_k, bad_ids, temperature, seed, offset): filter + draw instead of arg-max (k must be 1)."""
         st = self.st
         eos, pad, lp = self.consts
-        ops.beam_rows(logits, self.V, st["beam_scores"], st["cand_score"], st["cand_tok"], self.k)
-        ops.beam_select(st, self.k, self.V, self.B, self.L, eos, pad, lp)
-        ops.beam_advance(st, self.R, self.L)
+        if sampling is None:
+            ops.beam_rows(logits, self.V, st["beam_scores"], st["cand_score"], st["cand_tok"], self.k)
+        else:
+            lg = logits[0]
+            if sampling.get("bad_ids") or sampling.get("top_k"):
+                ops.logits_filter(lg, self.V, sampling.get("bad_ids") or (), sampling.get("top_k") or 0)
+            ops.sample_rows(lg, self.V, st["cand_score"], st["cand_tok"], 0x5C57, 0, st["counters"], sampling.get("temperature", 1.0))
+        ops.beam_select(st, self.k, self.V, self.B, self.L, eos, pad, lp, forced_last)
+        if advance:
+            self.advance()
+
+    def advance(self):
+        """ids / cache indirection follow the decisions in st['parent'] / st['next_tok']; the step counter advances."""
+        ops.beam_advance(self.st, self.R, self.L)
 
     def all_done(self):
         return int(self.st["counters"][1].item()) >= self.B
@@ -168,8 +187,9 @@ class DeviceSearch:
         self.states = [DecodeState(m, batch, beams, max_len, st["row_map"], st["counters"][0:1]) for m in models]
         self.graph = None
         self.sig = None
+        self.mode = (None, -1)
 
-    def _step(self):
+    def _step(self, advance=True):
         """One search step.  The ensemble members are independent until their logits are summed: each runs on its own stream, so
         that inside the captured graph they form parallel branches (a decode step is ~300 small, launch-latency-bound kernels per
         model; two branches overlap them)."""
@@ -188,18 +208,20 @@ class DeviceSearch:
             logits[0] = self.models[0].decode_step(self.states[0], st["next_tok"])
             for side in self._streams:
                 cur.wait_stream(side)
-        self.search.select(logits)
+        self.search.select(logits, sampling=self.mode[0], forced_last=self.mode[1], advance=advance)
 
     @torch.no_grad()
-    def run(self, encs, masks, input_ids, eos, pad, length_penalty):
+    def run(self, encs, masks, input_ids, eos, pad, length_penalty, sampling=None, forced_last=-1):
         bos = int(input_ids[0, 0])
+        self.mode = (dict(sampling) if sampling is not None else None, int(forced_last))
         if not bool((input_ids == bos).all()):
             raise NotImplementedError("per-row start tokens are not supported")
         fresh = False
         for s, e, mk in zip(self.states, encs, masks):
             fresh = bool(s.set_encoder(e, mk)) or fresh
         sig = (int(eos), int(pad), float(length_penalty), tuple(s.enc_len for s in self.states),
-               tuple(s.enc_mask is not None for s in self.states))
+               tuple(s.enc_mask is not None for s in self.states), int(forced_last),
+               None if sampling is None else tuple(sorted((k_, str(v_)) for k_, v_ in sampling.items() if k_ != "seed")))
         if self.graph is None or fresh or sig != self.sig:
             self.search.reset(bos, eos, pad, length_penalty)
             self._step()                                                # eager warm-up (first-use attribute setup), then reset
@@ -213,6 +235,8 @@ class DeviceSearch:
             torch.cuda.current_stream().wait_stream(side)
             self.sig = sig
         self.search.reset(bos, eos, pad, length_penalty)
+        if sampling is not None:                     # per-rollout nonce of the draw (device memory: the captured graph is reused)
+            self.search.st["counters"][3] = int(sampling.get("seed", 0)) & 0x7FFFFFFF
         for step in range(1, self.search.L):
             self.graph.replay()
             if step % self.CHECK_EVERY == 0 and self.search.all_done():

@@ -119,11 +119,17 @@ class GenerationMixinB200:
     @torch.no_grad()
     def generate(self, input_ids=None, encoder_hidden_states=None, encoder_attention_mask=None, max_length=None,
                  num_beams=None, bos_token_id=None, eos_token_id=None, pad_token_id=None, length_penalty=None,
-                 ensemble=None, use_cache=True, generation_config=None, **kwargs):
+                 ensemble=None, use_cache=True, generation_config=None, do_sample=None, top_k=None, temperature=None,
+                 bad_words_ids=None, forced_eos_token_id=None, return_dict_in_generate=None, seed=None, **kwargs):
         """Greedy / beam decoding (ensemble = sum of next-token logits over `ensemble`).  Arguments may come individually or in a
         HF-style `generation_config` (any object or dict with max_length / num_beams / length_penalty / *_token_id attributes — the
         call of vilmedic/blocks/huggingface/decoder/evaluation.py:73-78 and vision_multi_evaluation.py:42-57); explicit keyword
-        arguments win, then generation_config, then the model config.  Unknown arguments raise instead of being ignored."""
+        arguments win, then generation_config, then the model config.  Unknown arguments raise instead of being ignored.
+        do_sample=True draws multinomial rollouts (HF sample(): NoBadWords -> TopK -> temperature-1 softmax draw) on the device —
+        the call of vilmedic/blocks/rl/SCST.py:139-153; `bad_words_ids` must be single-token lists; `forced_eos_token_id` is emitted
+        at the last position (an int; the reference passes True, which HF — and this code — read as token id 1).
+        return_dict_in_generate=True returns an object with `.sequences` (scores are not materialised: use
+        blocks.rl.sequence_log_probs for the log-probabilities of a rollout)."""
         from .beam import beam_search
         gc = generation_config
 
@@ -136,15 +142,15 @@ class GenerationMixinB200:
                     return v
             return default
 
-        harmless = {"num_return_sequences": 1, "do_sample": False, "return_dict_in_generate": False, "output_scores": False,
-                    "early_stopping": False, "decoder_start_token_id": None}
+        harmless = {"num_return_sequences": 1, "output_scores": None, "early_stopping": False, "decoder_start_token_id": None}
         for k_, v_ in kwargs.items():
             if k_ not in harmless:
                 raise TypeError("generate() got an unsupported argument %r" % k_)
-            if k_ in ("num_return_sequences", "do_sample", "return_dict_in_generate", "output_scores", "early_stopping") and v_ not in (harmless[k_], None):
+            if k_ in ("num_return_sequences", "early_stopping") and v_ not in (harmless[k_], None):
                 raise NotImplementedError("generate(%s=%r) is not supported" % (k_, v_))
+        do_sample = bool(pick("do_sample", do_sample, False))
         if gc is not None:
-            for k_ in ("do_sample", "early_stopping"):
+            for k_ in ("early_stopping",):
                 v_ = gc.get(k_) if isinstance(gc, dict) else getattr(gc, k_, None)
                 if v_:
                     raise NotImplementedError("generation_config.%s=%r is not supported" % (k_, v_))
@@ -155,9 +161,30 @@ class GenerationMixinB200:
         enc = encoder_hidden_states if isinstance(encoder_hidden_states, (list, tuple)) else [encoder_hidden_states] * len(models)
         msk = encoder_attention_mask if isinstance(encoder_attention_mask, (list, tuple)) else [encoder_attention_mask] * len(models)
         cfg = self.config
-        return beam_search(models, enc, msk, input_ids=input_ids, max_length=pick("max_length", max_length, 20),
-                           num_beams=pick("num_beams", num_beams, 1),
-                           bos_token_id=pick("bos_token_id", bos_token_id, cfg.bos_token_id),
-                           eos_token_id=pick("eos_token_id", eos_token_id, cfg.eos_token_id),
-                           pad_token_id=pick("pad_token_id", pad_token_id, cfg.pad_token_id),
-                           length_penalty=pick("length_penalty", length_penalty, 1.0), use_cache=use_cache)
+        sampling = None
+        if do_sample:
+            bad = []
+            for w in (pick("bad_words_ids", bad_words_ids, None) or []):
+                if len(w) != 1:
+                    raise NotImplementedError("multi-token bad_words_ids are not supported")
+                bad.append(int(w[0]))
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())           # follows torch's global generator (torch.manual_seed)
+            sampling = dict(top_k=int(pick("top_k", top_k, 0) or 0), bad_ids=tuple(bad), temperature=float(pick("temperature", temperature, 1.0)),
+                            seed=int(seed))
+        forced = pick("forced_eos_token_id", forced_eos_token_id, None)
+        out = beam_search(models, enc, msk, input_ids=input_ids, max_length=pick("max_length", max_length, 20),
+                          num_beams=pick("num_beams", num_beams, 1),
+                          bos_token_id=pick("bos_token_id", bos_token_id, cfg.bos_token_id),
+                          eos_token_id=pick("eos_token_id", eos_token_id, cfg.eos_token_id),
+                          pad_token_id=pick("pad_token_id", pad_token_id, cfg.pad_token_id),
+                          length_penalty=pick("length_penalty", length_penalty, 1.0), use_cache=use_cache, sampling=sampling,
+                          forced_last=-1 if forced is None else int(forced))
+        if pick("return_dict_in_generate", return_dict_in_generate, False):
+            class _GenerateOutput:
+                pass
+            o = _GenerateOutput()
+            o.sequences = out
+            o.scores = None
+            return o
+        return out

@@ -54,7 +54,7 @@ template <typename TL>
 __global__ void __launch_bounds__(512) softmax_ce_kernel(const TL* __restrict__ logits, long long ld, const long long* __restrict__ ids,
                                                          int shift_T, int V, float smoothing, float grad_scale,
                                                          TL* dlogits, long long ldd, float* __restrict__ loss_rows,
-                                                         float* __restrict__ lse_rows) {
+                                                         float* __restrict__ lse_rows, const float* __restrict__ row_weight) {
   using CV = CeVec<TL>;
   constexpr int VN = CV::N;
   extern __shared__ uint4 row4[];  // row cache, TL[V] (16B aligned)
@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(512) softmax_ce_kernel(const TL* __restrict__ 
   }
   const bool ignore = (label < 0 || label >= V);
   const int nv = V / VN;
+  if (row_weight) grad_scale *= __ldg(row_weight + r);     // per-row weight of the gradient (SCST: reward-weighted log-likelihood)
 
   float mx = -INFINITY;
   for (int v = threadIdx.x; v < nv; v += blockDim.x) {
@@ -146,7 +147,7 @@ using namespace vlm;
 
 extern "C" int vlm_softmax_ce(const void* logits, int logits_fp32, long long ld, const long long* ids, int shift_T, int R,
                               int V, float smoothing, float grad_scale, void* dlogits, long long ldd, float* loss_rows,
-                              float* lse_rows, void* stream) {
+                              float* lse_rows, const float* row_weight, void* stream) {
   VLM_REQUIRE(logits && ids && R > 0 && V > 0 && ld >= V, "vlm_softmax_ce: bad args (R=%d V=%d ld=%lld)", R, V, ld);
   VLM_REQUIRE(ld % (logits_fp32 ? 4 : 8) == 0 && (!dlogits || ldd % (logits_fp32 ? 4 : 8) == 0), "vlm_softmax_ce: rows must be 16B aligned");
   VLM_REQUIRE(!dlogits || ldd >= V, "vlm_softmax_ce: ldd < V");
@@ -159,12 +160,12 @@ extern "C" int vlm_softmax_ce(const void* logits, int logits_fp32, long long ld,
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(softmax_ce_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
     softmax_ce_kernel<float><<<R, threads, smem, s>>>((const float*)logits, ld, ids, shift_T, V, smoothing, grad_scale,
-                                                      (float*)dlogits, ldd, loss_rows, lse_rows);
+                                                      (float*)dlogits, ldd, loss_rows, lse_rows, row_weight);
   } else {
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(softmax_ce_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
     softmax_ce_kernel<bf16><<<R, threads, smem, s>>>((const bf16*)logits, ld, ids, shift_T, V, smoothing, grad_scale,
-                                                     (bf16*)dlogits, ldd, loss_rows, lse_rows);
+                                                     (bf16*)dlogits, ldd, loss_rows, lse_rows, row_weight);
   }
   return check_launch("softmax_ce");
 }

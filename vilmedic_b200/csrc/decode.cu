@@ -255,7 +255,8 @@ __global__ void beam_select_kernel(const float* __restrict__ cand_score, const i
                                    const long long* __restrict__ ids, float* __restrict__ beam_scores, uint8_t* __restrict__ done,
                                    long long* __restrict__ next_tok, int* __restrict__ parent, double* __restrict__ hyp_score,
                                    int* __restrict__ hyp_len, long long* __restrict__ hyp_tok, int* __restrict__ hyp_count,
-                                   double* __restrict__ hyp_worst, int* __restrict__ counters, int eos, int pad, double length_penalty) {
+                                   double* __restrict__ hyp_worst, int* __restrict__ counters, int eos, int pad, double length_penalty,
+                                   int forced_last) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -268,6 +269,7 @@ __global__ void beam_select_kernel(const float* __restrict__ cand_score, const i
     if (lane == 0) {
       const bool was_done = done[b] != 0;
       int tok = cand_tok[(long long)b * k2];
+      if (forced_last >= 0 && cur_len + 1 == max_len) tok = forced_last;   // HF ForcedEOSTokenLogitsProcessor at the last position
       if (was_done) tok = pad;
       next_tok[b] = tok;
       parent[b] = b;
@@ -407,6 +409,134 @@ __global__ void beam_select_kernel(const float* __restrict__ cand_score, const i
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------ sampling
+// Logit filters of the reference's SCST rollouts (vilmedic/blocks/rl/SCST.py:139-153: generate(do_sample=True, top_k=...,
+// bad_words_ids=[[pad], [bos]])): HF NoBadWordsLogitsProcessor sets the listed single-token ids to -inf, TopKLogitsWarper removes
+// every score below the k-th largest (ties with the k-th are kept: `scores < topk(scores, k)[..., -1]`).  In place, one CTA per row;
+// the k-th largest is found by a 32-step binary search over the order-preserving integer image of the fp32 values cached in smem.
+__device__ __forceinline__ uint32_t f32_key(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+struct BadIds {
+  int id[8];
+};
+
+template <typename TL>
+__global__ void __launch_bounds__(256) logits_filter_kernel(TL* __restrict__ logits, long long ld, int V, BadIds bad, int n_bad, int top_k) {
+  extern __shared__ uint32_t keys[];
+  __shared__ int cnt_s[8];
+  __shared__ uint32_t thr_s;
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  TL* row = logits + (long long)r * ld;
+  const TL ninf = sizeof(TL) == 4 ? (TL)(-INFINITY) : (TL)__float2bfloat16(-INFINITY);
+  for (int v = tid; v < V; v += 256) {
+    float x = (float)row[v];
+    for (int i = 0; i < n_bad; ++i)
+      if (v == bad.id[i]) x = -INFINITY;
+    keys[v] = f32_key(x);
+  }
+  __syncthreads();
+  uint32_t thr = 0u;
+  if (top_k > 0 && top_k < V) {
+    // largest key value T such that count(key >= T) >= top_k  == the key of the k-th largest element
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = thr | (1u << bit);
+      int c = 0;
+      for (int v = tid; v < V; v += 256) c += keys[v] >= cand;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == 0) cnt_s[warp] = c;
+      __syncthreads();
+      if (tid == 0) {
+        int t = 0;
+        for (int i = 0; i < 8; ++i) t += cnt_s[i];
+        thr_s = (t >= top_k) ? cand : thr;
+      }
+      __syncthreads();
+      thr = thr_s;
+    }
+  }
+  const uint32_t ninf_key = f32_key(-INFINITY);
+  for (int v = tid; v < V; v += 256) {
+    const uint32_t kv = keys[v];
+    if (kv == ninf_key || kv < thr) row[v] = ninf;
+  }
+}
+
+// One token per row from softmax(logits / temperature) by the Gumbel-max trick: argmax_v (logit_v / T - log(-log u_v)), u from
+// Philox(seed, offset + *t, row * V + v) — one pass, no normalisation needed for the draw; the log-probability of the drawn token
+// (log-softmax of the same scaled logits) is written next to it.  Writes slot 0 of the row's candidate list (cand_* [R, 2]), so
+// that vlm_beam_select's k = 1 path does the EOS / pad / finished bookkeeping.
+__global__ void __launch_bounds__(256) sample_rows_kernel(const float* __restrict__ logits, long long ld, int V, float inv_temp,
+                                                         unsigned long long seed, unsigned long long offset, const int* __restrict__ t_ptr,
+                                                         float* __restrict__ cand_score, int* __restrict__ cand_tok) {
+  __shared__ float red_f[8], red_g[8];
+  __shared__ int red_i[8];
+  __shared__ float bc[2];
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = logits + (long long)r * ld;
+  const Philox rng(seed);
+  // counters[0] = step, counters[3] = per-rollout nonce (set by the host before the first step): both live in device memory so that
+  // one captured graph serves every step of every rollout
+  const unsigned long long off = offset + (t_ptr ? (unsigned long long)t_ptr[0] + ((unsigned long long)(unsigned)t_ptr[3] << 16) : 0ull);
+  float mx = -INFINITY, best = -INFINITY;
+  int best_v = 0x7fffffff;
+  float best_x = -INFINITY;
+  const int nq = (V + 3) / 4;
+  for (int q4 = tid; q4 < nq; q4 += 256) {
+    const uint4 u = rng((unsigned long long)r * (unsigned long long)nq + (unsigned long long)q4, off);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int v = q4 * 4 + j;
+      if (v >= V) break;
+      const float x = row[v] * inv_temp;
+      mx = fmaxf(mx, x);
+      if (x == -INFINITY) continue;
+      const float uu = ((float)(w[j] >> 8) + 0.5f) * (1.0f / 16777216.0f);        // (0, 1)
+      const float g = x - __logf(-__logf(uu));
+      if (g > best || (g == best && v < best_v)) { best = g; best_v = v; best_x = x; }
+    }
+  }
+  // block arg-max of the perturbed scores, block max of the scaled logits
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float og = __shfl_xor_sync(0xffffffffu, best, o), ox = __shfl_xor_sync(0xffffffffu, best_x, o);
+    const int ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+    if (og > best || (og == best && ov < best_v)) { best = og; best_v = ov; best_x = ox; }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) { red_g[warp] = best; red_i[warp] = best_v; red_f[warp] = mx; }
+  __syncthreads();
+  if (tid == 0) {
+    float m = red_f[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red_f[i]);
+    bc[0] = m;
+  }
+  __syncthreads();
+  const float m = bc[0];
+  float se = 0.f;
+  for (int v = tid; v < V; v += 256) se += __expf(row[v] * inv_temp - m);
+  se = warp_sum(se);
+  __syncthreads();
+  if (lane == 0) red_f[warp] = se;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f, bg = red_g[0];
+    int bv = red_i[0];
+    for (int i = 0; i < 8; ++i) t += red_f[i];
+    for (int i = 1; i < 8; ++i)
+      if (red_g[i] > bg || (red_g[i] == bg && red_i[i] < bv)) { bg = red_g[i]; bv = red_i[i]; }
+    if (bv >= V) bv = 0;                                       // whole row filtered out: cannot happen with a sane filter
+    cand_tok[(long long)r * 2] = bv;
+    cand_tok[(long long)r * 2 + 1] = bv;
+    const float lp = row[bv] * inv_temp - m - logf(t);
+    cand_score[(long long)r * 2] = lp;
+    cand_score[(long long)r * 2 + 1] = lp;
+  }
+}
+
 // ids / row_map of every row follow the row's parent; the new token is appended; one CTA per row.
 __global__ void beam_advance_kernel(const long long* __restrict__ ids_in, long long* __restrict__ ids_out, const int* __restrict__ map_in,
                                     int* __restrict__ map_out, const int* __restrict__ parent, const long long* __restrict__ next_tok,
@@ -489,15 +619,16 @@ extern "C" int vlm_beam_rows(const float* const* logits, int n_models, long long
 extern "C" int vlm_beam_select(const float* cand_score, const int* cand_tok, int k, int V, int B, int max_len, const long long* ids,
                                float* beam_scores, uint8_t* done, long long* next_tok, int* parent, double* hyp_score, int* hyp_len,
                                long long* hyp_tok, int* hyp_count, double* hyp_worst, int* counters, int eos, int pad,
-                               double length_penalty, void* stream) {
+                               double length_penalty, int forced_last_token, void* stream) {
   VLM_REQUIRE(cand_score && cand_tok && ids && beam_scores && done && next_tok && parent && counters, "vlm_beam_select: null argument");
   VLM_REQUIRE(k >= 1 && k <= 8 && B > 0 && max_len > 1, "vlm_beam_select: bad sizes");
   VLM_REQUIRE(k == 1 || (hyp_score && hyp_len && hyp_tok && hyp_count && hyp_worst), "vlm_beam_select: beam search needs the hypothesis buffers");
+  VLM_REQUIRE(k == 1 || forced_last_token < 0, "vlm_beam_select: a forced last token is only supported for greedy / sampling (k = 1)");
   const int warps = 4;
   const size_t smem = (size_t)warps * (256 + 128);
   beam_select_kernel<<<(B + warps - 1) / warps, warps * 32, smem, (cudaStream_t)stream>>>(cand_score, cand_tok, k, V, B, max_len, ids, beam_scores,
                                                                                          done, next_tok, parent, hyp_score, hyp_len, hyp_tok,
-                                                                                         hyp_count, hyp_worst, counters, eos, pad, length_penalty);
+                                                                                         hyp_count, hyp_worst, counters, eos, pad, length_penalty, forced_last_token);
   return check_launch("beam_select");
 }
 
@@ -510,4 +641,33 @@ extern "C" int vlm_beam_advance(long long* ids, long long* ids_tmp, int* row_map
   const long long n = (long long)R * max_len;
   beam_commit_kernel<<<(int)((n + 255) / 256 < 296 ? (n + 255) / 256 : 296), 256, 0, s>>>(ids_tmp, ids, map_tmp, row_map, n, counters, max_len);
   return check_launch("beam_commit");
+}
+
+extern "C" int vlm_logits_filter(void* logits, int logits_fp32, long long ld, int R, int V, const int* bad_ids, int n_bad, int top_k,
+                                 void* stream) {
+  VLM_REQUIRE(logits && R > 0 && V > 0 && ld >= V, "vlm_logits_filter: bad args");
+  VLM_REQUIRE(n_bad >= 0 && n_bad <= 8 && (n_bad == 0 || bad_ids), "vlm_logits_filter: at most 8 single-token bad ids (host array)");
+  VLM_REQUIRE(top_k >= 0, "vlm_logits_filter: top_k must be >= 0 (0 = off)");
+  VLM_REQUIRE((size_t)V * 4 <= 200 * 1024, "vlm_logits_filter: V=%d too large for the row cache", V);
+  BadIds bad;
+  for (int i = 0; i < 8; ++i) bad.id[i] = i < n_bad ? bad_ids[i] : -1;
+  const size_t smem = (size_t)V * 4;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (logits_fp32) {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(logits_filter_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
+    logits_filter_kernel<float><<<R, 256, smem, s>>>((float*)logits, ld, V, bad, n_bad, top_k);
+  } else {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(logits_filter_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
+    logits_filter_kernel<bf16><<<R, 256, smem, s>>>((bf16*)logits, ld, V, bad, n_bad, top_k);
+  }
+  return check_launch("logits_filter");
+}
+
+extern "C" int vlm_sample_rows(const float* logits, long long ld, int V, float temperature, unsigned long long seed,
+                               unsigned long long offset, const int* t_ptr, float* cand_score, int* cand_tok, int R, void* stream) {
+  VLM_REQUIRE(logits && cand_score && cand_tok && R > 0 && V > 0 && ld >= V && temperature > 0.f, "vlm_sample_rows: bad args");
+  sample_rows_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(logits, ld, V, 1.f / temperature, seed, offset, t_ptr, cand_score, cand_tok);
+  return check_launch("sample_rows");
 }

@@ -197,7 +197,7 @@ def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, H, DH, *, kmask=None, causal=
                                  ptr(RNG_COUNTER[0]), stream_ptr()), "vlm_attention_bwd")
 
 
-def softmax_ce(logits, ids, V, *, shift_T=0, smoothing=0.0, grad_scale=1.0, dlogits=None, want_lse=False):
+def softmax_ce(logits, ids, V, *, shift_T=0, smoothing=0.0, grad_scale=1.0, dlogits=None, want_lse=False, row_weight=None):
     """logits [R, ld>=V] (bf16|fp32).  Returns (loss_rows fp32 [R], lse_rows|None).  dlogits may alias logits."""
     _req(logits.dim() == 2 and logits.stride(1) == 1, "logits must be [R, ld]")
     R = logits.shape[0]
@@ -208,7 +208,7 @@ def softmax_ce(logits, ids, V, *, shift_T=0, smoothing=0.0, grad_scale=1.0, dlog
         _req(dlogits.dtype == logits.dtype and dlogits.stride(1) == 1, "dlogits dtype must match logits")
     check(_L().vlm_softmax_ce(ptr(logits), c_int(int(logits.dtype == torch.float32)), c_ll(logits.stride(0)), ptr(ids),
                               c_int(shift_T), c_int(R), c_int(V), c_float(smoothing), c_float(grad_scale), ptr(dlogits),
-                              c_ll(dlogits.stride(0) if dlogits is not None else 0), ptr(loss_rows), ptr(lse_rows),
+                              c_ll(dlogits.stride(0) if dlogits is not None else 0), ptr(loss_rows), ptr(lse_rows), ptr(row_weight),
                               stream_ptr()), "vlm_softmax_ce")
     return loss_rows, lse_rows
 
@@ -617,13 +617,29 @@ def beam_rows(logits_list, V, beam_scores, cand_score, cand_tok, k):
                              c_int(beam_scores.numel()), c_int(k), stream_ptr()), "vlm_beam_rows")
 
 
-def beam_select(st, k, V, B, max_len, eos, pad, length_penalty):
+def beam_select(st, k, V, B, max_len, eos, pad, length_penalty, forced_last=-1):
     check(_L().vlm_beam_select(ptr(st["cand_score"]), ptr(st["cand_tok"]), c_int(k), c_int(V), c_int(B), c_int(max_len), ptr(st["ids"]),
                                ptr(st["beam_scores"]), ptr(st["done"]), ptr(st["next_tok"]), ptr(st["parent"]), ptr(st.get("hyp_score")),
                                ptr(st.get("hyp_len")), ptr(st.get("hyp_tok")), ptr(st.get("hyp_count")), ptr(st.get("hyp_worst")),
-                               ptr(st["counters"]), c_int(eos), c_int(pad), ctypes.c_double(length_penalty), stream_ptr()), "vlm_beam_select")
+                               ptr(st["counters"]), c_int(eos), c_int(pad), ctypes.c_double(length_penalty), c_int(forced_last), stream_ptr()), "vlm_beam_select")
 
 
 def beam_advance(st, R, max_len):
     check(_L().vlm_beam_advance(ptr(st["ids"]), ptr(st["ids_tmp"]), ptr(st["row_map"]), ptr(st["map_tmp"]), ptr(st["parent"]),
                                 ptr(st["next_tok"]), c_int(R), c_int(max_len), ptr(st["counters"]), stream_ptr()), "vlm_beam_advance")
+
+
+def logits_filter(logits, V, bad_ids=(), top_k=0):
+    """In place: bad single-token ids -> -inf, then keep the top_k scores of every row (0 = off).  logits bf16 | fp32 [R, ld]."""
+    _req(logits.is_cuda and logits.dim() == 2 and logits.stride(1) == 1 and logits.dtype in (torch.float32, torch.bfloat16), "logits_filter: [R, ld] rows")
+    bad = [int(b) for b in bad_ids]
+    arr = (ctypes.c_int * max(len(bad), 1))(*(bad or [0]))
+    check(_L().vlm_logits_filter(ptr(logits), c_int(int(logits.dtype == torch.float32)), c_ll(logits.stride(0)), c_int(logits.shape[0]),
+                                 c_int(V), arr, c_int(len(bad)), c_int(int(top_k or 0)), stream_ptr()), "vlm_logits_filter")
+    return logits
+
+
+def sample_rows(logits, V, cand_score, cand_tok, seed, offset, t_ptr, temperature=1.0):
+    _req(logits.dtype == torch.float32 and logits.stride(1) == 1, "sample_rows: fp32 logits rows")
+    check(_L().vlm_sample_rows(ptr(logits), c_ll(logits.stride(0)), c_int(V), c_float(temperature), c_u64(seed), c_u64(offset), ptr(t_ptr),
+                               ptr(cand_score), ptr(cand_tok), c_int(logits.shape[0]), stream_ptr()), "vlm_sample_rows")
