@@ -349,6 +349,6 @@ def test_generation_config_object_and_unknown_arguments(cuda_dev):
                      bos_token_id=BOS, eos_token_id=EOS, pad_token_id=PAD, use_cache=False)               # host loop, full recompute
     assert c.shape[0] == 3
     with pytest.raises(TypeError):
-        dec.generate(input_ids=ids, encoder_hidden_states=enc.cuda(), temperature=0.7)
+        dec.generate(input_ids=ids, encoder_hidden_states=enc.cuda(), penalty_alpha=0.7)
     with pytest.raises(NotImplementedError):
         dec.generate(input_ids=ids, encoder_hidden_states=enc.cuda(), generation_config=SimpleNamespace(do_sample=True))

@@ -129,10 +129,10 @@ def test_scst_forward_greedy_and_sampling_end_to_end(cuda_dev):
     tok = _Tokenizer(300)
     dl = SimpleNamespace(dataset=SimpleNamespace(tokenizer=tok, tokenizer_max_len=L))
 
-    def overlap(refs, hyps):          # a REWARD_COMPLIANT-style scorer: per-sample rewards
-        return [len(set(r.split()) & set(h.split())) / (len(set(r.split())) + 1e-6) for r, h in zip(refs, hyps)]
+    def scorer(refs, hyps):           # a REWARD_COMPLIANT-style scorer: per-sample rewards, a deterministic function of the hypothesis
+        return [(sum(int(w[1:]) for w in h.split()) % 11) / 11.0 + 0.01 * len(h.split()) for h in hyps]
 
-    scst = SCST(mine.dec.decoder, dl, scores=[overlap], top_k=10)
+    scst = SCST(mine.dec.decoder, dl, scores=[scorer], top_k=10)
     g = torch.Generator().manual_seed(0)
     input_ids = torch.randint(5, 300, (B, L), generator=g)
     input_ids[:, 0] = BOS

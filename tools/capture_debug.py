@@ -32,6 +32,7 @@ def main():
     for _ in range(2):
         print("eager loss", float(step()))
     torch.cuda.synchronize()
+    torch.autograd.set_detect_anomaly(True)
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())

@@ -26,7 +26,7 @@ def main():
             d["us"] = v / 1000 if unit.startswith("n") else (v if unit.startswith("u") else v * 1000)
         else:
             d[m] = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
-    ad = [i for i in recs if "adamw" in recs[i]["name"]]
+    ad = [i for i in recs if "optim_kernel" in recs[i]["name"] or "adamw" in recs[i]["name"]]
     if len(ad) < 2:
         raise SystemExit("need at least two optimizer launches to delimit a step (found %d)" % len(ad))
     lo, hi = ad[-2] + 1, ad[-1]

@@ -24,7 +24,9 @@ from ...nn import _root_of
 
 
 class _SeqLogProbFn(torch.autograd.Function):
-    """log p(target_t) under softmax(filtered logits) for every row, with the gradient computed by the fused CE kernel."""
+    """log p(target_t) under softmax(filtered logits) for every row, with the gradient computed by the fused CE kernel.
+    The logits of this pass are kept in fp32 (LM-head GEMM with fp32 output): the top-k processor compares scores with the k-th
+    largest one, and bf16-rounded logits tie there far too often (HF applies it to fp32 scores as well)."""
 
     @staticmethod
     def forward(ctx, h, anchor, targets, head, arena, bad_ids, top_k):
@@ -37,24 +39,25 @@ class _SeqLogProbFn(torch.autograd.Function):
             bp = torch.zeros(Vp, device=h.device, dtype=torch.float32)
             bp[:V] = bias
             bias = bp
-        buf = torch.empty((R, Vp), device=h.device, dtype=torch.bfloat16)
+        buf = torch.empty((R, Vp), device=h.device, dtype=torch.float32)
         ops.gemm(h, arena.bf16(E), out=buf[:, :V], bias=bias)
         if bad_ids or top_k:
             ops.logits_filter(buf, V, bad_ids, top_k)
         nll, _ = ops.softmax_ce(buf, targets, V)                       # loss only; the gradient pass runs in backward with the weights
-        ctx.saved = (h, buf, targets, head, arena, V)
+        ctx.saved = (h, buf, targets, head, arena, V, Vp)
         return -nll
 
     @staticmethod
     def backward(ctx, dlogp):
-        h, buf, targets, head, arena, V = ctx.saved
+        h, buf, targets, head, arena, V, Vp = ctx.saved
         # d/dlogits of sum_r w_r * logp_r = -w_r * (softmax - onehot): the CE kernel writes (softmax - onehot) * grad_scale * row_weight
         w = (-dlogp).contiguous().float()
         ops.softmax_ce(buf, targets, V, dlogits=buf, row_weight=w)
+        dl = ops.cast_bf16(buf)                                        # bf16 operand of the two LM-head gradient GEMMs
         E = head.decoder.weight
-        ops.gemm(buf[:, :V], h, a_mn_major=True, b_mn_major=True, out=arena.grad(E), accumulate=True)
-        ops.colsum(buf[:, :V], arena.grad(head.bias))
-        dh = ops.gemm(buf[:, :V], arena.bf16(E), b_mn_major=True)
+        ops.gemm(dl[:, :V], h, a_mn_major=True, b_mn_major=True, out=arena.grad(E), accumulate=True)
+        ops.colsum(dl[:, :V], arena.grad(head.bias))
+        dh = ops.gemm(dl[:, :V], arena.bf16(E), b_mn_major=True)
         return dh, None, None, None, None, None, None
 
 

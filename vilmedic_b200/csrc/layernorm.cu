@@ -42,17 +42,40 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const TIn* __restric
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                             int M, int D, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 4 + warp;
-  if (row >= M) return;
   const int nvec = D >> 3;
-  const TIn* xr = x + (size_t)row * D;
+  // two rows per warp (row, row + half): the loads of both rows are issued before any arithmetic, which doubles the bytes in flight
+  // per warp and halves the number of CTAs the launch has to schedule
+  const int half = (M + 1) >> 1;
+  const int row0 = blockIdx.x * 4 + warp;
+  if (row0 >= half) return;
+  constexpr int XW = sizeof(TIn) == 2 ? 1 : 2;
+  uint4 raw[2][NV][XW];
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int row = row0 + rr * half;
+    if (row < M) {
+      const uint4* xr4 = reinterpret_cast<const uint4*>(x + (size_t)row * D);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nvec) {
+#pragma unroll
+          for (int w = 0; w < XW; ++w) raw[rr][i][w] = xr4[vi * XW + w];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+  const int row = row0 + rr * half;
+  if (row >= M) break;
   float v[NV][8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + 32 * i;
     if (vi < nvec) {
-      Vec8<TIn>::load(xr + vi * 8, v[i]);
+      Vec8<TIn>::load(reinterpret_cast<const TIn*>(&raw[rr][i][0]), v[i]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
     }
@@ -88,6 +111,7 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const TIn* __restric
       Vec8<bf16>::store(yr + vi * 8, o);
     }
   }
+  }
 }
 
 // Backward.  Persistent over rows so that the per-column dgamma/dbeta partials live in registers; one atomicAdd per
@@ -116,12 +140,15 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
   // Rows are software-pipelined: the raw x / dy vectors (and mean / rstd) of this warp's NEXT row are requested before the
   // current row is reduced, so two rows of loads are in flight per warp (the kernel is latency-bound at 12 warps / SM).
   constexpr int XW = sizeof(TIn) == 2 ? 1 : 2;   // uint4 words per 8-element vector of x
-  uint4 nx[NV][XW], ndy[NV];
+  // (round 2: the residual gradient `dres` travels with them — it used to be loaded where it is consumed, one exposed DRAM
+  //  round trip per row and warp; profiles/launches_r2 LayerNorm backward 26 us -> see ROUND_NOTES)
+  uint4 nx[NV][XW], ndy[NV], nres[NV][XW];
   float nmu = 0.f, nrs = 0.f;
   auto prefetch = [&](int prow) {
     if (prow < M) {
       const uint4* xr4 = reinterpret_cast<const uint4*>(x + (size_t)prow * D);
       const uint4* dy4 = reinterpret_cast<const uint4*>(dy + (size_t)prow * D);
+      const uint4* rs4 = dres ? reinterpret_cast<const uint4*>(dres + (size_t)prow * D) : nullptr;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int vi = lane + 32 * i;
@@ -129,6 +156,10 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
 #pragma unroll
           for (int w = 0; w < XW; ++w) nx[i][w] = xr4[vi * XW + w];
           ndy[i] = dy4[vi];
+          if (rs4) {
+#pragma unroll
+            for (int w = 0; w < XW; ++w) nres[i][w] = rs4[vi * XW + w];
+          }
         }
       }
       nmu = mean[prow];
@@ -138,11 +169,14 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
   prefetch(blockIdx.x * 4 + warp);
   for (int row = blockIdx.x * 4 + warp; row < M; row += gridDim.x * 4) {
     const float mu = nmu, rs = nrs;
-    uint4 cx[NV][XW], cdy[NV];
+    uint4 cx[NV][XW], cdy[NV], cres[NV][XW];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
 #pragma unroll
-      for (int w = 0; w < XW; ++w) cx[i][w] = nx[i][w];
+      for (int w = 0; w < XW; ++w) {
+        cx[i][w] = nx[i][w];
+        cres[i][w] = nres[i][w];
+      }
       cdy[i] = ndy[i];
     }
     prefetch(row + gridDim.x * 4);
@@ -185,7 +219,7 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
         }
         if (dres) {
           float r[8];
-          Vec8<TIn>::load(dres + (size_t)row * D + vi * 8, r);
+          Vec8<TIn>::load(reinterpret_cast<const TIn*>(&cres[i][0]), r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += r[j];
         }
@@ -236,7 +270,7 @@ template <typename TIn>
 static int ln_fwd_dispatch(const TIn* x, const float* gamma, const float* beta, bf16* y, float* mean, float* rstd, int M,
                            int D, float eps, cudaStream_t s) {
   const int nv = (D / 8 + 31) / 32;
-  const int grid = (M + 3) / 4;
+  const int grid = ((M + 1) / 2 + 3) / 4;      // two rows per warp, four warps per CTA
 #define LN_FWD(NV_) layernorm_fwd_kernel<TIn, NV_><<<grid, 128, 0, s>>>(x, gamma, beta, y, mean, rstd, M, D, eps)
   switch (nv) {
     case 1: LN_FWD(1); break;
