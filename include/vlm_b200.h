@@ -120,25 +120,29 @@ int vlm_softmax_ce(const void* logits, int logits_fp32, long long ld, const long
 
 /* ---- helpers around the core ------------------------------------------------------------------------------------ */
 int vlm_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
-/* images fp32 [B,C,H,W] -> bf16 [B, 1+(H/P)(W/P), C*P*P], row 0 of every image = 0 (CLS slot); column order = Conv2d
- * weight flatten (HF:vit/modeling_vit.py:151,166). */
-int vlm_patchify(const float* images, void* patches, int B, int C, int H, int W, int P, void* stream);
-/* x[b,0,:] = cls + pos[0]  (HF:vit/modeling_vit.py:117-124). */
-int vlm_vit_cls_pos(void* x, int x_is_fp32, const float* cls, const float* pos, int B, int S, int D, void* stream);
-/* dpos[s] += sum_b dx[b,s]; dcls += sum_b dx[b,0]; dbias += sum_{b,s>=1} dx[b,s]  (any of the three may be null). */
-int vlm_vit_embed_bwd(const void* dx, int dx_is_fp32, float* dpos, float* dcls, float* dbias, int B, int S, int D,
-                      void* stream);
+/* images fp32 [B,C,H,W] -> bf16 [B, n_prefix+(H/P)(W/P), C*P*P], the first n_prefix rows of every image = 0 (CLS slot; DeiT: CLS +
+ * distillation token, HF:deit/modeling_deit.py embeddings); column order = Conv2d weight flatten (HF:vit/modeling_vit.py:151,166). */
+int vlm_patchify(const float* images, void* patches, int B, int C, int H, int W, int P, int n_prefix, void* stream);
+/* x[b,row,:] = tok + pos[row]  (HF:vit/modeling_vit.py:117-124; row 0 = CLS, DeiT row 1 = distillation token). */
+int vlm_vit_cls_pos(void* x, int x_is_fp32, const float* tok, const float* pos, int B, int S, int D, int row, void* stream);
+/* dpos[s] += sum_b dx[b,s]; dcls += sum_b dx[b,0]; ddist += sum_b dx[b,1] (n_prefix == 2); dbias += sum_{b,s>=n_prefix} dx[b,s]
+ * (any of the outputs may be null). */
+int vlm_vit_embed_bwd(const void* dx, int dx_is_fp32, float* dpos, float* dcls, float* ddist, float* dbias, int B, int S, int D,
+                      int n_prefix, void* stream);
 /* out[n] += (scale_ptr ? *scale_ptr : 1) * sum_m x[m,n]  (bias gradients; caller zeroes). */
 int vlm_colsum_bf16(const void* x, long long ld, float* out, int M, int N, const float* scale_ptr, void* stream);
 /* mask[r] = (sum_d |f[r,d]| != 0)  — vilmedic/blocks/vision/visual_encoder.py:138. */
 int vlm_features_mask(const void* feats, uint8_t* mask, int R, int D, void* stream);
-/* z[r] = word[ids[r]] + pos[pos_offset + r % T]  (HF:bert_generation/modeling_bert_generation.py:410-429, pre-LN). */
+/* z[r] = word[ids[r]] (+ tt_row) + pos[pos_ids ? pos_ids[r] : pos_offset + r % T]  (HF:bert_generation/modeling_bert_generation.py:
+ * 410-429, pre-LN).  pos_ids (optional int32 [R]): explicit positions — RoBERTa's padding-aware ids (HF:roberta/modeling_roberta.py
+ * create_position_ids_from_input_ids); tt_row (optional fp32 [D]): token_type_embeddings[0] of BERT / RoBERTa checkpoints loaded through
+ * `proto` (vilmedic/blocks/huggingface/encoder/encoder_model.py:20-22, decoder/decoder_model.py:17-21). */
 int vlm_embed_fwd(const long long* ids, const float* word, const float* pos, void* z, int R, int T, int D, int V,
-                  int pos_offset, void* stream);
+                  int pos_offset, const int* pos_ids, const float* tt_row, void* stream);
 /* scatter-add of dz into dword / dpos (fp32, atomics; either may be null); rows with id == padding_idx (< 0: none) get no
  * gradient, as nn.Embedding(padding_idx=pad_token_id) in HF:bert_generation/modeling_bert_generation.py:400. */
 int vlm_embed_bwd(const long long* ids, const void* dz, float* dword, float* dpos, int R, int T, int D, int V,
-                  int pos_offset, int padding_idx, void* stream);
+                  int pos_offset, int padding_idx, const int* pos_ids, void* stream);
 /* y = x * keep / (1-p), keep ~ Philox(seed, offset, element); same call on grads is the backward.  n % 8 == 0. */
 int vlm_dropout_bf16(const void* x, void* y, long long n, float p, unsigned long long seed, unsigned long long offset,
                      const unsigned long long* rng_offset_ptr, void* stream);
@@ -240,9 +244,10 @@ int vlm_avgpool_bwd(const void* dy, void* dx, int B, int HW, int C, void* stream
 /* One decode step of the loop behind vilmedic/blocks/huggingface/decoder/evaluation.py:73-78 (HF cached generate) and the
  * ensemble search of vilmedic/blocks/huggingface/decoder/beam_search.py:243-320, with every per-step scalar in device memory
  * (counters[0] = t = position of the token being consumed), so that the whole step replays as one CUDA graph.
- * vlm_embed_step: z[r] = bf16(word[tok[r]] + pos[min(*t, max_pos-1)])   (HF:bert_generation/modeling_bert_generation.py:395-429). */
+ * vlm_embed_step: z[r] = bf16(word[tok[r]] (+ tt_row) + pos[min(*t + pos_shift, max_pos-1)])
+ *   (HF:bert_generation/modeling_bert_generation.py:395-429; pos_shift = padding_idx + 1 and tt_row for RoBERTa-family checkpoints). */
 int vlm_embed_step(const long long* tok, const float* word, const float* pos, void* z, int R, int D, int V, const int* t_ptr,
-                   int max_pos, void* stream);
+                   int max_pos, int pos_shift, const float* tt_row, void* stream);
 /* T_q = 1 attention for R rows x H heads (DH in {48, 64, 96}); fp32 scores / softmax / PV, bf16 out [R, H*DH].
  *   self-attention (kv_new != NULL): cache bf16 [R, max_len, 2*H*DH] ([K | V] per position); row r's history at position j < *t is
  *     read from physical row row_map[r*map_ld + j]; the new key/value kv_new[r] ([K | V], pitch ld_new) is used for position *t,

@@ -20,6 +20,10 @@ class OracleVisualEncoder(nn.Module):
         if "vit" in backbone.lower():
             self.model = ViTModel(ViTConfig(return_dict=True, **kwargs), add_pooling_layer=False)   # :56-58
             self.model.config._attn_implementation = "eager"
+        elif "deit" in backbone.lower():
+            from transformers import DeiTConfig, DeiTModel
+            self.model = DeiTModel(DeiTConfig(return_dict=True, **kwargs), add_pooling_layer=False)  # :60-61
+            self.model.config._attn_implementation = "eager"
         else:
             import torchvision.models as tvm
             network = getattr(tvm, backbone)(weights=None, **kwargs)                                # :71
@@ -39,7 +43,7 @@ class OracleVisualEncoder(nn.Module):
 
     def forward(self, images):
         out = self.model(images)
-        if isinstance(self.model, ViTModel):
+        if hasattr(out, "last_hidden_state"):                                                        # ViTModel / DeiTModel
             return self.dropout_out(out.last_hidden_state)                                           # :182-186
         out = self.dropout_out(out)
         if self.permute == "batch_first":                                                           # :200-203

@@ -367,7 +367,7 @@ def test_config_errors_and_defaults():
     with pytest.raises(NotImplementedError):
         DecoderModel(AttrDict(proto="bert-base-uncased"))
     with pytest.raises(NotImplementedError):
-        VisualEncoder(backbone="deit", permute="no_permute")
+        VisualEncoder(backbone="hfresnet", permute="no_permute")
     with pytest.raises(AssertionError):
         VisualEncoder(backbone="vit", permute="bogus", num_hidden_layers=1)
     d = to_attrdict({"a": {"b": 1}, "proto": None})

@@ -351,4 +351,4 @@ def test_generation_config_object_and_unknown_arguments(cuda_dev):
     with pytest.raises(TypeError):
         dec.generate(input_ids=ids, encoder_hidden_states=enc.cuda(), penalty_alpha=0.7)
     with pytest.raises(NotImplementedError):
-        dec.generate(input_ids=ids, encoder_hidden_states=enc.cuda(), generation_config=SimpleNamespace(do_sample=True))
+        dec.generate(input_ids=ids, encoder_hidden_states=enc.cuda(), generation_config=SimpleNamespace(early_stopping=True))

@@ -225,4 +225,35 @@ def test_visual_encoder_multi_image_encode_forward_backward(cuda_dev):
     torch.cuda.synchronize()
     for (n, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
         r = _rel(p.grad.cpu(), q.grad)
-        assert r <= 6e-2 or (p.grad.cpu().float() - q.grad).norm().item() <= 1e-5 * q.grad.numel() ** 0.5, (n, r)
+        # key biases have an exactly-zero gradient in exact arithmetic (softmax shift invariance): only rounding noise on both sides
+        assert r <= 6e-2 or n.endswith("key.bias") or (p.grad.cpu().float() - q.grad).norm().item() <= 1e-5 * q.grad.numel() ** 0.5, (n, r)
+
+
+def test_deit_backbone_forward_backward(cuda_dev):
+    """`backbone: deit` (vilmedic/blocks/vision/visual_encoder.py:60-61 -> HF DeiTModel): the ViT blocks plus a distillation token and
+    an [N+2] position table; state_dict keys are HF's, features and gradients follow the fp32 HF module."""
+    from vilmedic_b200 import synth
+    from oracle.rrg import OracleVisualEncoder
+    from vilmedic_b200.blocks.vision import VisualEncoder
+    torch.manual_seed(0)
+    kw = dict(synth.vit_b16(), num_hidden_layers=2)
+    ref = OracleVisualEncoder(backbone="deit", permute="no_permute", **kw).eval()
+    with torch.no_grad():                                   # HF initialises the tokens to zero: make them matter
+        ref.model.embeddings.distillation_token.normal_(0, 0.5)
+        ref.model.embeddings.cls_token.normal_(0, 0.5)
+    mine = VisualEncoder(backbone="deit", permute="no_permute", **kw)
+    assert set(mine.state_dict()) == set(ref.state_dict())
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.cuda().train()
+    images = synth.rrg_batch(3, 8, 100, seed=5)["images"]
+    f_ref = ref(images)
+    feats = mine(images)
+    assert feats.shape == f_ref.shape == (3, 198, 768)
+    assert (feats.float().cpu() - f_ref).abs().max().item() <= 3e-2 + 2 ** -7 * f_ref.abs().max().item()
+    w = torch.randn(f_ref.shape, generator=torch.Generator().manual_seed(2))
+    (f_ref * w).sum().backward()
+    (feats.float() * w.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    for (n, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        r = _rel(p.grad.cpu(), q.grad)
+        assert r <= 6e-2 or n.endswith("key.bias"), (n, r)

@@ -102,7 +102,8 @@ def test_sequence_log_probs_and_gradients_vs_fp32_oracle(cuda_dev):
     # ---- product: teacher-forced pass + vlm_logits_filter + weighted CE kernel
     lp = sequence_log_probs(mine.dec.decoder, seq, enc.cuda(), mask.cuda(), bad_ids=[PAD, BOS], top_k=K, targets=tgt)
     assert lp.shape == (B, L - 1) and torch.isfinite(lp).all()
-    assert (lp.float().cpu() - lp_ref.detach()).abs().max().item() <= 6e-2
+    # log-probabilities down to -120 here (x10 embeddings): bf16 activations give ~1e-3 relative on the logits behind them
+    assert (lp.float().cpu() - lp_ref.detach()).abs().max().item() <= 3e-2 + 2e-3 * lp_ref.abs().max().item()
     (lp * w.cuda()).sum().backward()
     torch.cuda.synchronize()
 

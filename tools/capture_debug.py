@@ -29,13 +29,13 @@ def main():
         opt.step()
         return out["loss"]
 
-    for _ in range(2):
-        print("eager loss", float(step()))
-    torch.cuda.synchronize()
-    torch.autograd.set_detect_anomaly(True)
-    g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            print("eager loss (side stream)", float(step()))
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
     try:
         with torch.cuda.stream(s):
             with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):

@@ -3,7 +3,10 @@
 `decoder.proto is None` -> a BertGenerationDecoder-shaped tower (is_decoder=True, add_cross_attention=True, LM head tied to
 the word embeddings) built from `decoder` exactly as BertGenerationConfig(**decoder) would be (:23-26);  forward passes
 labels=input_ids (:46), i.e. next-token CE where pad tokens count as targets and the last position is ignored.
-`decoder.proto` set (AutoModelForCausalLM.from_pretrained, :17-21) needs the HF hub -> NotImplementedError here.
+`decoder.proto` = a LOCAL HuggingFace directory (BERT / RoBERTa / bert-generation checkpoint) builds the causal LM of that family
+(is_decoder, add_cross_attention as :19-20; cross-attention blocks absent from the checkpoint stay randomly initialised, exactly like
+AutoModelForCausalLM.from_pretrained(path, config=dec_config) :21) on the kernel tower; a hub NAME needs network access ->
+NotImplementedError.
 state_dict keys are identical to the reference's (`decoder.bert.…`, `decoder.lm_head.…`).
 """
 import torch
@@ -43,14 +46,23 @@ class BertGenerationDecoderB200(BertTower, GenerationMixinB200):
 class DecoderModel(nn.Module):
     def __init__(self, decoder, **kwargs):
         super().__init__()
+        from ....hf_loader import is_local_checkpoint, load_into, read_config
         decoder = to_attrdict(decoder)
-        if cfg_get(decoder, "proto") is not None:
-            raise NotImplementedError("DecoderModel(proto=%r): pretrained HF checkpoints need hub access" % decoder["proto"])
+        proto = cfg_get(decoder, "proto")
         d = dict(decoder)
         d.pop("proto", None)
+        if proto is not None:
+            if not is_local_checkpoint(proto):
+                raise NotImplementedError("DecoderModel(proto=%r): not a local HuggingFace directory (hub access is not available)" % (proto,))
+            d = read_config(proto)
         d["is_decoder"] = True
         d["add_cross_attention"] = True
         self.decoder = BertGenerationDecoderB200(bert_config(**d))
+        if proto is not None:
+            missing, unexpected = load_into(self.decoder, proto, flat=False)
+            missing = [k for k in missing if "crossattention" not in k]      # newly initialised, as HF reports for the same call
+            if missing or unexpected:
+                raise RuntimeError("proto %r does not match the tower: missing %s, unexpected %s" % (proto, missing[:5], unexpected[:5]))
         self.generate = self.decoder.generate
         self.config = self.decoder.config
 

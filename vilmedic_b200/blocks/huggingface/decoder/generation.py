@@ -78,7 +78,10 @@ class GenerationMixinB200:
         eps = cfg.layer_norm_eps
         core = self._core
         emb = core.embeddings
-        z = ops.embed_step(tokens, arena.fp32(emb.word_embeddings.weight), arena.fp32(emb.position_embeddings.weight), state.t_ptr)
+        tt = getattr(emb, "token_type_embeddings", None)
+        z = ops.embed_step(tokens, arena.fp32(emb.word_embeddings.weight), arena.fp32(emb.position_embeddings.weight), state.t_ptr,
+                           pos_shift=(cfg.pad_token_id + 1) if cfg.family == "roberta" else 0,
+                           tt_row=arena.fp32(tt.weight)[0].contiguous() if tt is not None else None)
         lnp = _ln(arena, emb.LayerNorm)
         x, _, _ = ops.layernorm_fwd(z, lnp[0], lnp[1], eps, save_stats=False)
         for li, layer in enumerate(core.encoder.layer):

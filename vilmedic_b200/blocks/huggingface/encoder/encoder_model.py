@@ -1,6 +1,8 @@
 """B200-native EncoderModel — mirror of vilmedic/blocks/huggingface/encoder/encoder_model.py:10-66: a bidirectional
 BERT-shaped text tower (BertGenerationEncoder when `encoder.proto` is None) with an optional BertPooler
-(tanh(W h[:,0] + b), :28-29,58-60).  `proto` set needs the HF hub -> NotImplementedError."""
+(tanh(W h[:,0] + b), :28-29,58-60).  `encoder.proto` = a LOCAL HuggingFace directory (config.json + weights of a BERT / RoBERTa /
+bert-generation model) loads that checkpoint into the kernel tower (hf_loader.py) — the offline form of :20-22
+`AutoModel.from_pretrained(proto)`; a hub NAME needs network access -> NotImplementedError."""
 import torch
 import torch.nn as nn
 
@@ -12,12 +14,16 @@ from ....nn import BertTower, LinearFn, TanhFn, _lin, _root_of, bert_config
 class EncoderModel(nn.Module):
     def __init__(self, encoder, **kwargs):
         super().__init__()
+        from ....hf_loader import is_local_checkpoint, load_into, read_config
         encoder = to_attrdict(encoder)
-        if cfg_get(encoder, "proto") is not None:
-            raise NotImplementedError("EncoderModel(proto=%r): pretrained HF checkpoints need hub access" % encoder["proto"])
+        proto = cfg_get(encoder, "proto")
         d = dict(encoder)
         d.pop("proto", None)
         add_pool = bool(d.pop("add_pooling_layer", False))
+        if proto is not None:
+            if not is_local_checkpoint(proto):
+                raise NotImplementedError("EncoderModel(proto=%r): not a local HuggingFace directory (hub access is not available)" % (proto,))
+            d = read_config(proto)                          # AutoConfig.from_pretrained(path): the checkpoint's own architecture
         d["is_decoder"] = False
         d["add_cross_attention"] = False
         self.encoder = BertTower(bert_config(**d), with_lm_head=False, flat=True)
@@ -26,6 +32,10 @@ class EncoderModel(nn.Module):
         if add_pool:
             self.pooler = nn.Module()
             self.pooler.dense = nn.Linear(self.config.hidden_size, self.config.hidden_size)
+        if proto is not None:
+            missing, unexpected = load_into(self.encoder, proto, flat=True)
+            if missing or unexpected:
+                raise RuntimeError("proto %r does not match the tower: missing %s, unexpected %s" % (proto, missing[:5], unexpected[:5]))
 
     def forward(self, input_ids, attention_mask=None, **kwargs):
         input_ids = input_ids.cuda(non_blocking=True)

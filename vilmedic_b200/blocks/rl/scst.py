@@ -71,7 +71,7 @@ def sequence_log_probs(decoder, sequences, encoder_hidden_states, encoder_attent
     x, _, T = decoder.hidden_states(inp, None, encoder_hidden_states, encoder_attention_mask)
     arena = get_arena(_root_of(decoder))
     targets = (seq[:, 1:] if targets is None else targets.cuda()).contiguous().view(-1)
-    lp = _SeqLogProbFn.apply(x, decoder._core.embeddings.LayerNorm.weight, targets, decoder.lm_head, arena, tuple(int(b) for b in bad_ids),
+    lp = _SeqLogProbFn.apply(decoder.head_input(x), decoder._core.embeddings.LayerNorm.weight, targets, decoder._head, arena, tuple(int(b) for b in bad_ids),
                              int(top_k or 0))
     return lp.view(B, L - 1)
 

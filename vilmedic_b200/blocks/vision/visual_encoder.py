@@ -9,7 +9,8 @@ Reference behaviour kept (file:line in /root/reference/vilmedic/blocks/vision/vi
   * multi-image 5-D input: flatten -> forward -> x images_mask -> concat along positions                    (:159-178)
 Reference defects resolved to the intended semantics (SURVEY.md §8 "Reference defects" #3): `num_images` is read from
 the 5-D input (the reference reads it after flattening, i.e. the channel count); `freeze` freezes `self.model`.
-Out of scope here (raise): DeiT / HF-ResNet / PoolFormer / monai 3-D backbones (not in any BASELINE config).
+"deit" in backbone -> the same tower with HF DeiTModel's distillation token and [N+2] position table (:60-61).
+Out of scope here (raise): HF-ResNet / PoolFormer / monai 3-D backbones (not in any BASELINE config).
 The torchvision ResNets (ResNet-18/50 of cfg #1/#3; BasicBlock / Bottleneck, groups=1) run on the sm_100a kernels through
 vilmedic_b200/cnn.py (im2col + tcgen05 GEMM convolutions, fused BatchNorm/ReLU/residual, hand-written backward); the
 parameter tree stays torchvision's, so state_dict keys are the reference's.  Other CNN families (DenseNet, ResNeXt) still
@@ -31,7 +32,9 @@ __all__ = ["VisualEncoder", "get_network"]
 def get_network(backbone, output_layer, pretrained, **kwargs):
     if "vit" in backbone.lower():
         return ViTTower(**kwargs)
-    for tag in ("deit", "hfresnet", "hfpoolformer", "3d"):
+    if "deit" in backbone.lower():        # DeiTModel(DeiTConfig(**kwargs), add_pooling_layer=False), :60-61: ViT blocks + distillation token
+        return ViTTower(distillation=True, **kwargs)
+    for tag in ("hfresnet", "hfpoolformer", "3d"):
         if tag in backbone.lower():
             raise NotImplementedError("backbone %r is outside the B200 hot path (SURVEY.md §2 #5)" % backbone)
     import torchvision.models as tvm
@@ -67,7 +70,7 @@ class VisualEncoder(nn.Module):
         self.permute = permute
         self.freeze = freeze
         self.pretrained = pretrained
-        self.is_vit = "vit" in backbone.lower()
+        self.is_vit = "vit" in backbone.lower() or "deit" in backbone.lower()
         self.model = get_network(self.backbone, self.output_layer, self.pretrained and not self.is_vit, **kwargs)
         self.dropout_out = nn.Dropout(p=dropout_out)
         self._resnet = None

@@ -20,17 +20,23 @@ namespace vlm {
 
 // ------------------------------------------------------------------------------------------------------------------ embedding
 __global__ void embed_step_kernel(const long long* __restrict__ tok, const float* __restrict__ word, const float* __restrict__ pos,
-                                  bf16* __restrict__ z, int R, int D, int V, const int* __restrict__ t_ptr, int max_pos) {
+                                  bf16* __restrict__ z, int R, int D, int V, const int* __restrict__ t_ptr, int max_pos, int pos_shift,
+                                  const float* __restrict__ tt_row) {
   const int nvec = D / 8;
-  const int t = min(*t_ptr, max_pos - 1);
+  const int t = min(*t_ptr + pos_shift, max_pos - 1);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R * nvec; i += gridDim.x * blockDim.x) {
     const int v = i % nvec, r = i / nvec;
     long long id = tok[r];
     if (id < 0 || id >= V) id = 0;
     const float* w = word + (size_t)id * D + v * 8;
     const float* p = pos + (size_t)t * D + v * 8;
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w)), w1 = __ldg(reinterpret_cast<const float4*>(w) + 1);
+    float4 w0 = __ldg(reinterpret_cast<const float4*>(w)), w1 = __ldg(reinterpret_cast<const float4*>(w) + 1);
     const float4 p0 = __ldg(reinterpret_cast<const float4*>(p)), p1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    if (tt_row) {
+      const float4 t0 = __ldg(reinterpret_cast<const float4*>(tt_row + v * 8)), t1 = __ldg(reinterpret_cast<const float4*>(tt_row + v * 8) + 1);
+      w0.x += t0.x; w0.y += t0.y; w0.z += t0.z; w0.w += t0.w;
+      w1.x += t1.x; w1.y += t1.y; w1.z += t1.z; w1.w += t1.w;
+    }
     uint4 u;
     u.x = pack_bf16x2(w0.x + p0.x, w0.y + p0.y); u.y = pack_bf16x2(w0.z + p0.z, w0.w + p0.w);
     u.z = pack_bf16x2(w1.x + p1.x, w1.y + p1.y); u.w = pack_bf16x2(w1.z + p1.z, w1.w + p1.w);
@@ -568,10 +574,10 @@ __global__ void beam_commit_kernel(const long long* __restrict__ ids_tmp, long l
 using namespace vlm;
 
 extern "C" int vlm_embed_step(const long long* tok, const float* word, const float* pos, void* z, int R, int D, int V, const int* t_ptr,
-                              int max_pos, void* stream) {
+                              int max_pos, int pos_shift, const float* tt_row, void* stream) {
   VLM_REQUIRE(tok && word && pos && z && t_ptr && R > 0 && D % 8 == 0 && V > 0 && max_pos > 0, "vlm_embed_step: bad args");
   const int n = R * (D / 8);
-  embed_step_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tok, word, pos, (bf16*)z, R, D, V, t_ptr, max_pos);
+  embed_step_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tok, word, pos, (bf16*)z, R, D, V, t_ptr, max_pos, pos_shift, tt_row);
   return check_launch("embed_step");
 }
 

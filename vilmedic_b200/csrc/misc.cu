@@ -26,9 +26,9 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __rest
 // images fp32 [B,C,H,W] -> patches bf16 [B, 1 + (H/P)*(W/P), C*P*P]; row 0 of each image is zero (CLS slot), so the
 // patch-embedding GEMM and its wgrad run on the same [B*S] row space as the rest of the encoder.
 // Column order (c, ky, kx) matches Conv2d.weight[out, c, ky, kx].flatten(1)  (HF modeling_vit.py:151,166).
-__global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int C, int H, int W, int P) {
+__global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int C, int H, int W, int P, int n_prefix) {
   const int gw = W / P, gh = H / P;
-  const int S = 1 + gh * gw;
+  const int S = n_prefix + gh * gw;
   const int Kp = C * P * P;
   const int vec_per_row = Kp / 8;
   const long long total = (long long)B * S * vec_per_row;
@@ -37,8 +37,8 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
     const long long rs = i / vec_per_row;
     const int s = (int)(rs % S), b = (int)(rs / S);
     uint4 u = make_uint4(0, 0, 0, 0);
-    if (s > 0) {
-      const int p = s - 1, py = p / gw, px = p % gw;
+    if (s >= n_prefix) {
+      const int p = s - n_prefix, py = p / gw, px = p % gw;
       const int col = v * 8;  // 8 consecutive kx within one (c, ky) row since P % 8 == 0
       const int c = col / (P * P), rem = col % (P * P), ky = rem / P, kx = rem % P;
       const float* src = img + (((long long)b * C + c) * H + (py * P + ky)) * W + px * P + kx;
@@ -50,21 +50,21 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
   }
 }
 
-// x[b,0,:] = cls + pos[0]   (HF modeling_vit.py:117-124: cat(cls, patches) + position_embeddings)
+// x[b,row,:] = tok + pos[row]   (HF modeling_vit.py:117-124: cat(cls, patches) + position_embeddings; DeiT: row 1 = distillation token)
 template <typename T>
-__global__ void vit_cls_kernel(T* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos, int B, int S, int D) {
+__global__ void vit_cls_kernel(T* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos, int B, int S, int D, int row) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * D) return;
   const int b = i / D, d = i % D;
-  const float v = cls[d] + pos[d];
-  if constexpr (sizeof(T) == 4) x[(size_t)b * S * D + d] = v;
-  else x[(size_t)b * S * D + d] = __float2bfloat16(v);
+  const float v = cls[d] + pos[(size_t)row * D + d];
+  if constexpr (sizeof(T) == 4) x[((size_t)b * S + row) * D + d] = v;
+  else x[((size_t)b * S + row) * D + d] = __float2bfloat16(v);
 }
 
 // dpos[s,d] += sum_b dx[b,s,d];  dcls[d] += sum_b dx[b,0,d];  dbias[d] += sum_{b,s>=1} dx[b,s,d]
 template <typename T>
 __global__ void vit_embed_bwd_kernel(const T* __restrict__ dx, float* __restrict__ dpos, float* __restrict__ dcls,
-                                     float* __restrict__ dbias, int B, int S, int D) {
+                                     float* __restrict__ ddist, float* __restrict__ dbias, int B, int S, int D, int n_prefix) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = blockIdx.y;
   if (d >= D) return;
@@ -75,6 +75,7 @@ __global__ void vit_embed_bwd_kernel(const T* __restrict__ dx, float* __restrict
   }
   if (dpos) dpos[(size_t)s * D + d] += acc;
   if (s == 0) { if (dcls) dcls[d] += acc; }
+  else if (s < n_prefix) { if (ddist) ddist[d] += acc; }
   else if (dbias) atomicAdd(dbias + d, acc);
 }
 
@@ -195,8 +196,12 @@ __global__ void features_mask_kernel(const bf16* __restrict__ f, uint8_t* __rest
 
 // ---------------------------------------------------------------- token + position embeddings
 // z[r,:] = word[ids[r],:] + pos[pos_offset + r % T,:]   (HF modeling_bert_generation.py:410-429, before LayerNorm)
+// pos_ids (optional int32 [R]): explicit position index per token (RoBERTa: padding_idx + running count of non-pad tokens,
+// HF:roberta/modeling_roberta.py create_position_ids_from_input_ids), else pos_offset + (r % T).  tt_row (optional fp32 [D]): row 0 of
+// the token-type table, added to every token (BERT / RoBERTa embeddings with token_type_ids = 0, which is all the reference passes).
 __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ pos,
-                                 bf16* __restrict__ z, int R, int T, int D, int V, int pos_offset) {
+                                 bf16* __restrict__ z, int R, int T, int D, int V, int pos_offset, const int* __restrict__ pos_ids,
+                                 const float* __restrict__ tt_row) {
   const int nvec = D / 8;
   const long long total = (long long)R * nvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -205,9 +210,15 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float*
     long long id = ids[r];
     if (id < 0 || id >= V) id = 0;  // defensive: the reference would raise an index error
     const float* w = word + (size_t)id * D + v * 8;
-    const float* p = pos + (size_t)(pos_offset + r % T) * D + v * 8;
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w)), w1 = __ldg(reinterpret_cast<const float4*>(w) + 1);
+    const int pi = pos_ids ? pos_ids[r] : pos_offset + r % T;
+    const float* p = pos + (size_t)pi * D + v * 8;
+    float4 w0 = __ldg(reinterpret_cast<const float4*>(w)), w1 = __ldg(reinterpret_cast<const float4*>(w) + 1);
     const float4 p0 = __ldg(reinterpret_cast<const float4*>(p)), p1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    if (tt_row) {       // HF sums word + token_type first, then + position (modeling_bert.py BertEmbeddings.forward)
+      const float4 t0 = __ldg(reinterpret_cast<const float4*>(tt_row + v * 8)), t1 = __ldg(reinterpret_cast<const float4*>(tt_row + v * 8) + 1);
+      w0.x += t0.x; w0.y += t0.y; w0.z += t0.z; w0.w += t0.w;
+      w1.x += t1.x; w1.y += t1.y; w1.z += t1.z; w1.w += t1.w;
+    }
     uint4 u;
     u.x = pack_bf16x2(w0.x + p0.x, w0.y + p0.y); u.y = pack_bf16x2(w0.z + p0.z, w0.w + p0.w);
     u.z = pack_bf16x2(w1.x + p1.x, w1.y + p1.y); u.w = pack_bf16x2(w1.z + p1.z, w1.w + p1.w);
@@ -215,9 +226,10 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float*
   }
 }
 
-// dword[ids[r],:] += dz[r,:] ; dpos[pos_offset + r % T,:] += dz[r,:]
+// dword[ids[r],:] += dz[r,:] ; dpos[position of r,:] += dz[r,:]
 __global__ void embed_bwd_kernel(const long long* __restrict__ ids, const bf16* __restrict__ dz, float* __restrict__ dword,
-                                 float* __restrict__ dpos, int R, int T, int D, int V, int pos_offset, int padding_idx) {
+                                 float* __restrict__ dpos, int R, int T, int D, int V, int pos_offset, int padding_idx,
+                                 const int* __restrict__ pos_ids) {
   const int nvec = D / 2;
   const long long total = (long long)R * nvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -231,8 +243,9 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ ids, const bf16* 
       atomicAdd(dword + (size_t)id * D + v * 2 + 1, g.y);
     }
     if (dpos) {
-      atomicAdd(dpos + (size_t)(pos_offset + r % T) * D + v * 2, g.x);
-      atomicAdd(dpos + (size_t)(pos_offset + r % T) * D + v * 2 + 1, g.y);
+      const int pi = pos_ids ? pos_ids[r] : pos_offset + r % T;
+      atomicAdd(dpos + (size_t)pi * D + v * 2, g.x);
+      atomicAdd(dpos + (size_t)pi * D + v * 2 + 1, g.y);
     }
   }
 }
@@ -315,28 +328,28 @@ extern "C" int vlm_cast_f32_to_bf16(const float* src, void* dst, long long n, vo
   return check_launch("cast_f32_bf16");
 }
 
-extern "C" int vlm_patchify(const float* images, void* patches, int B, int C, int H, int W, int P, void* stream) {
-  VLM_REQUIRE(images && patches && B > 0 && C > 0, "vlm_patchify: bad args");
+extern "C" int vlm_patchify(const float* images, void* patches, int B, int C, int H, int W, int P, int n_prefix, void* stream) {
+  VLM_REQUIRE(images && patches && B > 0 && C > 0 && n_prefix >= 0 && n_prefix <= 2, "vlm_patchify: bad args");
   VLM_REQUIRE(P % 8 == 0 && H % P == 0 && W % P == 0 && W % 4 == 0, "vlm_patchify: need P%%8==0, H,W multiples of P (H=%d W=%d P=%d)", H, W, P);
-  const long long total = (long long)B * (1 + (H / P) * (W / P)) * (C * P * P / 8);
-  patchify_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(images, (bf16*)patches, B, C, H, W, P);
+  const long long total = (long long)B * (n_prefix + (H / P) * (W / P)) * (C * P * P / 8);
+  patchify_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(images, (bf16*)patches, B, C, H, W, P, n_prefix);
   return check_launch("patchify");
 }
 
-extern "C" int vlm_vit_cls_pos(void* x, int x_is_fp32, const float* cls, const float* pos, int B, int S, int D, void* stream) {
-  VLM_REQUIRE(x && cls && pos && B > 0 && S > 0 && D > 0, "vlm_vit_cls_pos: bad args");
+extern "C" int vlm_vit_cls_pos(void* x, int x_is_fp32, const float* cls, const float* pos, int B, int S, int D, int row, void* stream) {
+  VLM_REQUIRE(x && cls && pos && B > 0 && S > 0 && D > 0 && row >= 0 && row < S, "vlm_vit_cls_pos: bad args");
   const int n = B * D;
-  if (x_is_fp32) vit_cls_kernel<float><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float*)x, cls, pos, B, S, D);
-  else vit_cls_kernel<bf16><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((bf16*)x, cls, pos, B, S, D);
+  if (x_is_fp32) vit_cls_kernel<float><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float*)x, cls, pos, B, S, D, row);
+  else vit_cls_kernel<bf16><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((bf16*)x, cls, pos, B, S, D, row);
   return check_launch("vit_cls_pos");
 }
 
-extern "C" int vlm_vit_embed_bwd(const void* dx, int dx_is_fp32, float* dpos, float* dcls, float* dbias, int B, int S, int D,
-                                 void* stream) {
-  VLM_REQUIRE(dx && B > 0 && S > 0 && D > 0, "vlm_vit_embed_bwd: bad args");
+extern "C" int vlm_vit_embed_bwd(const void* dx, int dx_is_fp32, float* dpos, float* dcls, float* ddist, float* dbias, int B, int S, int D,
+                                 int n_prefix, void* stream) {
+  VLM_REQUIRE(dx && B > 0 && S > 0 && D > 0 && n_prefix >= 1 && n_prefix <= 2, "vlm_vit_embed_bwd: bad args");
   dim3 grid((D + 127) / 128, S);
-  if (dx_is_fp32) vit_embed_bwd_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((const float*)dx, dpos, dcls, dbias, B, S, D);
-  else vit_embed_bwd_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)dx, dpos, dcls, dbias, B, S, D);
+  if (dx_is_fp32) vit_embed_bwd_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((const float*)dx, dpos, dcls, ddist, dbias, B, S, D, n_prefix);
+  else vit_embed_bwd_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)dx, dpos, dcls, ddist, dbias, B, S, D, n_prefix);
   return check_launch("vit_embed_bwd");
 }
 
@@ -379,16 +392,16 @@ extern "C" int vlm_features_mask(const void* feats, uint8_t* mask, int R, int D,
 }
 
 extern "C" int vlm_embed_fwd(const long long* ids, const float* word, const float* pos, void* z, int R, int T, int D, int V,
-                             int pos_offset, void* stream) {
+                             int pos_offset, const int* pos_ids, const float* tt_row, void* stream) {
   VLM_REQUIRE(ids && word && pos && z && R > 0 && T > 0 && D % 8 == 0 && V > 0, "vlm_embed_fwd: bad args");
-  embed_fwd_kernel<<<grid_for((long long)R * D / 8, 256), 256, 0, (cudaStream_t)stream>>>(ids, word, pos, (bf16*)z, R, T, D, V, pos_offset);
+  embed_fwd_kernel<<<grid_for((long long)R * D / 8, 256), 256, 0, (cudaStream_t)stream>>>(ids, word, pos, (bf16*)z, R, T, D, V, pos_offset, pos_ids, tt_row);
   return check_launch("embed_fwd");
 }
 
 extern "C" int vlm_embed_bwd(const long long* ids, const void* dz, float* dword, float* dpos, int R, int T, int D, int V,
-                             int pos_offset, int padding_idx, void* stream) {
+                             int pos_offset, int padding_idx, const int* pos_ids, void* stream) {
   VLM_REQUIRE(ids && dz && R > 0 && T > 0 && D % 2 == 0 && V > 0, "vlm_embed_bwd: bad args");
-  embed_bwd_kernel<<<grid_for((long long)R * D / 2, 256), 256, 0, (cudaStream_t)stream>>>(ids, (const bf16*)dz, dword, dpos, R, T, D, V, pos_offset, padding_idx);
+  embed_bwd_kernel<<<grid_for((long long)R * D / 2, 256), 256, 0, (cudaStream_t)stream>>>(ids, (const bf16*)dz, dword, dpos, R, T, D, V, pos_offset, padding_idx, pos_ids);
   return check_launch("embed_bwd");
 }
 

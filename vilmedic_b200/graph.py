@@ -28,7 +28,10 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture on the SAME side stream the warm-up ran on: autograd ties every leaf's gradient accumulation to the stream on which
+        # the leaf was first used, and waits for those streams at the end of backward — a leaf first used on a stream that is not
+        # being captured makes the capture fail ("dependency created on uncaptured work in another stream")
+        with torch.cuda.graph(self.graph, stream=s):
             self.loss = self._step_fn(self.static)
         torch.cuda.synchronize()
 

@@ -94,6 +94,28 @@ class LinearFn(torch.autograd.Function):
         return dx, None, None, None
 
 
+class LinearGeluFn(torch.autograd.Function):
+    """y = GELU(x W^T + b) with GELU' stashed by the GEMM epilogue (the LM-head transform of BERT / RoBERTa checkpoints:
+    HF:bert/modeling_bert.py BertPredictionHeadTransform, HF:roberta/modeling_roberta.py RobertaLMHead)."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, P):
+        stash = torch.empty((x.shape[0], P.w.shape[0]), device=x.device, dtype=torch.bfloat16) if torch.is_grad_enabled() else None
+        y = ops.gemm(x, P.w, bias=P.b, act=ops.ACT_GELU, aux_out=stash)
+        ctx.saved = (x, stash, P)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stash, P = ctx.saved
+        dy = dy.contiguous()
+        dpre = torch.empty_like(dy)
+        # dpre = dy * GELU'(pre): the x-stash epilogue needs a GEMM in front of it; here the product is elementwise on [M, D] only
+        dpre = (dy.float() * stash.float()).to(torch.bfloat16)
+        _wgrad(dpre, x, P)
+        return _dgrad(dpre, P), None, None
+
+
 def _bf16_rows(t):
     """2-D bf16 tensor whose row pitch is a multiple of 8 elements (TMA needs 16-byte strides); zero padded."""
     N = t.shape[-1]
@@ -176,7 +198,8 @@ class ViTEmbedFn(torch.autograd.Function):
     def forward(ctx, images, anchor, mod, arena):
         cfg = mod.cfg
         B = images.shape[0]
-        patches = ops.patchify(images, cfg.patch_size)            # [B, S, C*P*P], row 0 zero
+        dist = getattr(mod.embeddings, "distillation_token", None)
+        patches = ops.patchify(images, cfg.patch_size, 2 if dist is not None else 1)   # [B, S, C*P*P], token rows zero
         S, Kp = patches.shape[1], patches.shape[2]
         D = cfg.hidden_size
         proj = mod.embeddings.patch_embeddings.projection
@@ -189,6 +212,8 @@ class ViTEmbedFn(torch.autograd.Function):
         x = torch.empty((B, S, D), device=images.device, dtype=torch.bfloat16)
         ops.gemm(patches, w.unsqueeze(0).expand(B, D, Kp), out=x, bias=bias, residual=pos16)
         ops.vit_cls_pos(x, cls, pos)
+        if dist is not None:                                      # DeiT: row 1 = distillation token + its position (HF:deit/modeling_deit.py)
+            ops.vit_cls_pos(x, arena.fp32(dist, shape=(D,)), pos, row=1)
         ctx.saved = (patches, mod, arena)
         return x.view(B * S, D)
 
@@ -201,8 +226,10 @@ class ViTEmbedFn(torch.autograd.Function):
         proj = mod.embeddings.patch_embeddings.projection
         gw = arena.grad(proj.weight, shape=(D, Kp))
         ops.gemm(dx, patches.view(B * S, Kp), a_mn_major=True, b_mn_major=True, out=gw, accumulate=True)
+        dist = getattr(mod.embeddings, "distillation_token", None)
         ops.vit_embed_bwd(dx.view(B, S, D), arena.grad(mod.embeddings.position_embeddings, shape=(S, D)),
-                          arena.grad(mod.embeddings.cls_token, shape=(D,)), arena.grad(proj.bias))
+                          arena.grad(mod.embeddings.cls_token, shape=(D,)), arena.grad(proj.bias),
+                          ddist=arena.grad(dist, shape=(D,)) if dist is not None else None)
         notify_grad_ready(mod.embeddings)
         return None, None, None, None
 
@@ -279,7 +306,7 @@ def vit_config(**kw):
     """Defaults of transformers.ViTConfig (HF configuration_vit.py) for the keys the kernels consume."""
     d = dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072, hidden_act="gelu",
              hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, initializer_range=0.02, layer_norm_eps=1e-12,
-             image_size=224, patch_size=16, num_channels=3, qkv_bias=True)
+             image_size=224, patch_size=16, num_channels=3, qkv_bias=True, distillation=False)
     d.update(kw)
     cfg = _Cfg(**d)
     if cfg.hidden_act != "gelu":
@@ -312,7 +339,9 @@ class ViTTower(nn.Module):
         n_patches = (cfg.image_size // cfg.patch_size) ** 2
         emb = self.embeddings = _Holder()
         emb.cls_token = nn.Parameter(torch.zeros(1, 1, D))
-        emb.position_embeddings = nn.Parameter(torch.zeros(1, n_patches + 1, D))
+        if cfg.distillation:          # DeiTModel (vilmedic/blocks/vision/visual_encoder.py:60-61): same blocks + a distillation token
+            emb.distillation_token = nn.Parameter(torch.zeros(1, 1, D))
+        emb.position_embeddings = nn.Parameter(torch.zeros(1, n_patches + (2 if cfg.distillation else 1), D))
         emb.patch_embeddings = _Holder()
         emb.patch_embeddings.projection = nn.Conv2d(cfg.num_channels, D, cfg.patch_size, cfg.patch_size)
         self.encoder = _Holder()
@@ -352,6 +381,8 @@ class ViTTower(nn.Module):
                 m.bias.data.zero_()
         _trunc_normal_(self.embeddings.cls_token.data, std)
         _trunc_normal_(self.embeddings.position_embeddings.data, std)
+        if self.cfg.distillation:
+            _trunc_normal_(self.embeddings.distillation_token.data, std)
 
     def forward(self, pixel_values):
         """pixel_values fp32 [B,C,H,W] (CUDA) -> last_hidden_state bf16 [B,S,D]."""
@@ -428,11 +459,18 @@ def bert_config(**kw):
              hidden_act="gelu", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, max_position_embeddings=512,
              initializer_range=0.02, layer_norm_eps=1e-12, pad_token_id=0, bos_token_id=2, eos_token_id=1,
              is_decoder=False, add_cross_attention=False, tie_word_embeddings=True, type_vocab_size=0,
-             encoder_hidden_size=None)
+             encoder_hidden_size=None,
+             # checkpoints loaded through `proto` (hf_loader.py): "bert-generation" (default, what the reference builds when proto is
+             # null), "bert" (token-type table, cls.predictions head) or "roberta" (padding-aware positions, lm_head with a transform)
+             family="bert-generation")
     d.update({k: v for k, v in kw.items() if k not in ("proto", "return_dict")})
     cfg = _Cfg(**d)
     if cfg.hidden_act != "gelu":
         raise NotImplementedError("hidden_act %r: only exact-erf 'gelu' has a kernel" % cfg.hidden_act)
+    if cfg.family not in ("bert-generation", "bert", "roberta"):
+        raise NotImplementedError("model family %r has no kernel tower (bert-generation, bert, roberta)" % cfg.family)
+    if cfg.family == "bert-generation":
+        cfg.type_vocab_size = 0                                   # BertGenerationEmbeddings has no token-type table
     if cfg.hidden_size % cfg.num_attention_heads != 0:
         raise ValueError("The hidden size (%d) is not a multiple of the number of attention heads (%d)" % (
             cfg.hidden_size, cfg.num_attention_heads))
@@ -446,28 +484,30 @@ class BertEmbedFn(torch.autograd.Function):
     """word + position (+ token_type 0) -> LayerNorm.  HF modeling_bert_generation.py:395-429 / modeling_bert.py embeddings."""
 
     @staticmethod
-    def forward(ctx, ids, anchor, emb, arena, T, pos_offset, eps):
+    def forward(ctx, ids, anchor, emb, arena, T, pos_offset, eps, pos_ids=None):
         word = arena.fp32(emb.word_embeddings.weight)
         pos = arena.fp32(emb.position_embeddings.weight)
-        z = ops.embed_fwd(ids, word, pos, T, pos_offset)
         tt = getattr(emb, "token_type_embeddings", None)
-        if tt is not None:
-            raise NotImplementedError("token_type_embeddings are not wired")
+        tt_row = arena.fp32(tt.weight)[0].contiguous() if tt is not None else None      # token_type_ids = 0 everywhere
+        z = ops.embed_fwd(ids, word, pos, T, pos_offset, pos_ids=pos_ids, tt_row=tt_row)
         lnp = _ln(arena, emb.LayerNorm)
         y, mean, rstd = ops.layernorm_fwd(z, lnp[0], lnp[1], eps)
-        ctx.saved = (ids, z, mean, rstd, lnp, emb, arena, T, pos_offset)
+        ctx.saved = (ids, z, mean, rstd, lnp, emb, arena, T, pos_offset, pos_ids)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        ids, z, mean, rstd, lnp, emb, arena, T, pos_offset = ctx.saved
+        ids, z, mean, rstd, lnp, emb, arena, T, pos_offset, pos_ids = ctx.saved
         dz = ops.layernorm_bwd(dy.contiguous(), z, mean, rstd, lnp[0], lnp[2], lnp[3])
         V = emb.word_embeddings.weight.shape[0]
         pad = emb.word_embeddings.padding_idx
         ops.embed_bwd(ids, dz, arena.grad(emb.word_embeddings.weight), arena.grad(emb.position_embeddings.weight), T, V,
-                      pos_offset, -1 if pad is None else int(pad))
+                      pos_offset, -1 if pad is None else int(pad), pos_ids=pos_ids)
+        tt = getattr(emb, "token_type_embeddings", None)
+        if tt is not None:                                            # every token used row 0: its gradient is the column sum of dz
+            ops.colsum(dz, arena.grad(tt.weight)[0])
         notify_grad_ready(emb)            # the tied LM-head weight gradient was accumulated first (LMHeadCEFn.backward)
-        return None, None, None, None, None, None, None
+        return None, None, None, None, None, None, None, None
 
 
 class BertLayerFn(torch.autograd.Function):
@@ -750,25 +790,47 @@ class BertTower(nn.Module):
         super().__init__()
         self.cfg = self.config = cfg
         D = cfg.hidden_size
+        fam = cfg.family
         if flat:
             core = self
-        else:
-            core = self.bert = _Holder()
+        else:                                      # BertGenerationDecoder / BertLMHeadModel keep the stack under `bert.`, Roberta under `roberta.`
+            core = _Holder()
+            setattr(self, "roberta" if fam == "roberta" else "bert", core)
         object.__setattr__(self, "_core", core)
         emb = core.embeddings = _Holder()
         emb.word_embeddings = nn.Embedding(cfg.vocab_size, D, padding_idx=cfg.pad_token_id)
-        emb.position_embeddings = nn.Embedding(cfg.max_position_embeddings, D)
+        emb.position_embeddings = nn.Embedding(cfg.max_position_embeddings, D,
+                                               padding_idx=cfg.pad_token_id if fam == "roberta" else None)
+        if cfg.type_vocab_size:
+            emb.token_type_embeddings = nn.Embedding(cfg.type_vocab_size, D)
         emb.LayerNorm = nn.LayerNorm(D, eps=cfg.layer_norm_eps)
         core.encoder = _Holder()
         core.encoder.layer = nn.ModuleList([make_bert_layer(cfg) for _ in range(cfg.num_hidden_layers)])
         self.lm_head = None
+        object.__setattr__(self, "_head", None)
+        object.__setattr__(self, "_head_transform", None)
         if with_lm_head:
-            head = self.lm_head = _Holder()
+            head = _Holder()
             head.bias = nn.Parameter(torch.zeros(cfg.vocab_size))
             head.decoder = nn.Linear(D, cfg.vocab_size)
             head.decoder.bias = head.bias
             if cfg.tie_word_embeddings:
                 head.decoder.weight = emb.word_embeddings.weight
+            if fam == "bert-generation":           # lm_head.{decoder, bias}
+                self.lm_head = head
+            elif fam == "roberta":                 # lm_head.{dense, layer_norm, decoder, bias}
+                head.dense = nn.Linear(D, D)
+                head.layer_norm = nn.LayerNorm(D, eps=cfg.layer_norm_eps)
+                self.lm_head = head
+                object.__setattr__(self, "_head_transform", (head.dense, head.layer_norm))
+            else:                                  # cls.predictions.{transform.{dense, LayerNorm}, decoder, bias}
+                self.cls = _Holder()
+                self.cls.predictions = head
+                head.transform = _Holder()
+                head.transform.dense = nn.Linear(D, D)
+                head.transform.LayerNorm = nn.LayerNorm(D, eps=cfg.layer_norm_eps)
+                object.__setattr__(self, "_head_transform", (head.transform.dense, head.transform.LayerNorm))
+            object.__setattr__(self, "_head", head)
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -794,7 +856,12 @@ class BertTower(nn.Module):
             B, T = ids.shape
             if T > cfg.max_position_embeddings:
                 raise IndexError("sequence length %d exceeds max_position_embeddings %d" % (T, cfg.max_position_embeddings))
-            x = BertEmbedFn.apply(ids.view(-1), anchor, self._core.embeddings, arena, T, 0, cfg.layer_norm_eps)
+            pos_ids = None
+            if cfg.family == "roberta":            # HF create_position_ids_from_input_ids: padding_idx + running count of non-pad tokens
+                pad = cfg.pad_token_id
+                m = (ids != pad).to(torch.int32)
+                pos_ids = ((torch.cumsum(m, dim=1).to(torch.int32) * m) + pad).contiguous().view(-1)
+            x = BertEmbedFn.apply(ids.view(-1), anchor, self._core.embeddings, arena, T, 0, cfg.layer_norm_eps, pos_ids)
         x = dropout(x, cfg.hidden_dropout_prob, training and grad)
         kmask = None
         if attention_mask is not None:
@@ -813,20 +880,30 @@ class BertTower(nn.Module):
                             training=training)
         return x, B, T
 
+    def head_input(self, x):
+        """BERT / RoBERTa LM heads transform the hidden state first: LayerNorm(GELU(dense(x)))."""
+        if self._head_transform is None:
+            return x
+        dense, ln = self._head_transform
+        arena = get_arena(_root_of(self))
+        h = LinearGeluFn.apply(x, dense.weight, _lin(arena, dense))
+        return LayerNormFn.apply(h, ln.weight, _ln(arena, ln), ln.eps)
+
     def lm_loss(self, x, input_ids, B, T, keep_logits):
         arena = get_arena(_root_of(self))
         ids = input_ids.to(arena.device).long().contiguous().view(-1)
         grad = torch.is_grad_enabled()
-        return LMHeadCEFn.apply(x, self._core.embeddings.LayerNorm.weight, ids, self.lm_head, arena, B, T, keep_logits, grad)
+        return LMHeadCEFn.apply(self.head_input(x), self._core.embeddings.LayerNorm.weight, ids, self._head, arena, B, T, keep_logits, grad)
 
     def lm_logits(self, x, padded=False):
         """bf16 [M,D] -> fp32 [M,V] logits (inference); padded=True returns the [M, Vp] buffer (row pitch Vp = V rounded up to 4)."""
         arena = get_arena(_root_of(self))
-        E = self.lm_head.decoder.weight
+        x = self.head_input(x)
+        E = self._head.decoder.weight
         V = E.shape[0]
         Vp = (V + 3) // 4 * 4
         out = torch.empty((x.shape[0], Vp), device=x.device, dtype=torch.float32)
-        bias = arena.fp32(self.lm_head.bias)
+        bias = arena.fp32(self._head.bias)
         if Vp != V:
             bp = torch.zeros(Vp, device=x.device, dtype=torch.float32)
             bp[:V] = bias

@@ -221,26 +221,27 @@ def cast_bf16(src, dst=None):
     return dst
 
 
-def patchify(images, P):
+def patchify(images, P, n_prefix=1):
     _req(images.is_cuda and images.dtype == torch.float32 and images.is_contiguous() and images.dim() == 4, "patchify: fp32 NCHW")
     B, C, Hh, W = images.shape
-    S = 1 + (Hh // P) * (W // P)
+    S = n_prefix + (Hh // P) * (W // P)
     out = torch.empty((B, S, C * P * P), device=images.device, dtype=torch.bfloat16)
-    check(_L().vlm_patchify(ptr(images), ptr(out), c_int(B), c_int(C), c_int(Hh), c_int(W), c_int(P), stream_ptr()), "vlm_patchify")
+    check(_L().vlm_patchify(ptr(images), ptr(out), c_int(B), c_int(C), c_int(Hh), c_int(W), c_int(P), c_int(n_prefix), stream_ptr()),
+          "vlm_patchify")
     return out
 
 
-def vit_cls_pos(x, cls, pos):
+def vit_cls_pos(x, tok, pos, row=0):
     B, S, D = x.shape
-    check(_L().vlm_vit_cls_pos(ptr(x), c_int(int(x.dtype == torch.float32)), ptr(cls), ptr(pos), c_int(B), c_int(S), c_int(D),
+    check(_L().vlm_vit_cls_pos(ptr(x), c_int(int(x.dtype == torch.float32)), ptr(tok), ptr(pos), c_int(B), c_int(S), c_int(D), c_int(row),
                                stream_ptr()), "vlm_vit_cls_pos")
 
 
-def vit_embed_bwd(dx, dpos, dcls, dbias):
+def vit_embed_bwd(dx, dpos, dcls, dbias, ddist=None):
     B, S, D = dx.shape
     _req(dx.is_contiguous(), "vit_embed_bwd: dx must be contiguous")
-    check(_L().vlm_vit_embed_bwd(ptr(dx), c_int(int(dx.dtype == torch.float32)), ptr(dpos), ptr(dcls), ptr(dbias), c_int(B),
-                                 c_int(S), c_int(D), stream_ptr()), "vlm_vit_embed_bwd")
+    check(_L().vlm_vit_embed_bwd(ptr(dx), c_int(int(dx.dtype == torch.float32)), ptr(dpos), ptr(dcls), ptr(ddist), ptr(dbias), c_int(B),
+                                 c_int(S), c_int(D), c_int(2 if ddist is not None else 1), stream_ptr()), "vlm_vit_embed_bwd")
 
 
 def colsum(x, out, scale_t=None):
@@ -259,21 +260,23 @@ def features_mask(feats):
     return mask
 
 
-def embed_fwd(ids, word, pos, T, pos_offset=0):
+def embed_fwd(ids, word, pos, T, pos_offset=0, pos_ids=None, tt_row=None):
     _req(ids.dtype == torch.int64 and ids.is_contiguous(), "ids must be contiguous int64")
     R = ids.numel()
     V, D = word.shape
     z = torch.empty((R, D), device=word.device, dtype=torch.bfloat16)
+    if pos_ids is not None:
+        _req(pos_ids.dtype == torch.int32 and pos_ids.is_contiguous() and pos_ids.numel() == R, "embed_fwd: pos_ids int32 [R]")
     check(_L().vlm_embed_fwd(ptr(ids), ptr(word), ptr(pos), ptr(z), c_int(R), c_int(T), c_int(D), c_int(V), c_int(pos_offset),
-                             stream_ptr()), "vlm_embed_fwd")
+                             ptr(pos_ids), ptr(tt_row), stream_ptr()), "vlm_embed_fwd")
     return z
 
 
-def embed_bwd(ids, dz, dword, dpos, T, V, pos_offset=0, padding_idx=-1):
+def embed_bwd(ids, dz, dword, dpos, T, V, pos_offset=0, padding_idx=-1, pos_ids=None):
     R, D = dz.shape
     _req(dz.is_contiguous() and dz.dtype == torch.bfloat16, "embed_bwd: dz contiguous bf16")
     check(_L().vlm_embed_bwd(ptr(ids), ptr(dz), ptr(dword), ptr(dpos), c_int(R), c_int(T), c_int(D), c_int(V),
-                             c_int(pos_offset), c_int(padding_idx), stream_ptr()), "vlm_embed_bwd")
+                             c_int(pos_offset), c_int(padding_idx), ptr(pos_ids), stream_ptr()), "vlm_embed_bwd")
 
 
 def dropout(x, p, seed, offset, out=None):
@@ -574,14 +577,14 @@ def rng_advance(counter, delta):
 
 
 # ---- incremental decoding / device-side beam search (csrc/decode.cu) ------------------------------------------------------------
-def embed_step(tok, word, pos, t_ptr):
+def embed_step(tok, word, pos, t_ptr, pos_shift=0, tt_row=None):
     """tok int64 [R] (device), position read from the device counter t_ptr -> bf16 [R, D]."""
     _req(tok.dtype == torch.int64 and tok.is_contiguous() and t_ptr.dtype == torch.int32, "embed_step: tok int64, t_ptr int32")
     R = tok.numel()
     V, D = word.shape
     z = torch.empty((R, D), device=word.device, dtype=torch.bfloat16)
     check(_L().vlm_embed_step(ptr(tok), ptr(word), ptr(pos), ptr(z), c_int(R), c_int(D), c_int(V), ptr(t_ptr), c_int(pos.shape[0]),
-                              stream_ptr()), "vlm_embed_step")
+                              c_int(pos_shift), ptr(tt_row), stream_ptr()), "vlm_embed_step")
     return z
 
 
