@@ -580,16 +580,22 @@ def run_other_workload(args):
         opt.step(grad_scale=sync.finish())
         return out["loss"]
 
-    for _ in range(max(args.warmup, 3)):
-        l0 = ops.LAUNCHES[0]
-        train_step(devb)
-        launches = ops.LAUNCHES[0] - l0
+    # eager warm-up on the side stream the graph will be captured on (autograd ties a leaf's gradient accumulation to the stream of
+    # its first use; these models have leaves that receive gradients through autograd — see graph.py)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(max(args.warmup, 3)):
+            l0 = ops.LAUNCHES[0]
+            train_step(devb)
+            launches = ops.LAUNCHES[0] - l0
+    torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     graphed, note = None, "eager launches"
     if not args.no_graph:
         try:
             from vilmedic_b200.graph import GraphedTrainStep
-            graphed = GraphedTrainStep(model, opt, devb, warmup=1,
+            graphed = GraphedTrainStep(model, opt, devb, warmup=1, stream=side,
                                        step_fn=lambda b: (ops.rng_advance(ops.RNG_COUNTER[0], 4096), train_step(b))[1])
             note = "whole step replayed as one CUDA graph"
         except Exception as e:      # pragma: no cover - reported, never silent
@@ -645,6 +651,7 @@ def run_other_workload(args):
             "e2e": {"value": world * per_gpu * args.steps / (ms_e2e / 1e3), "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps, "how": "pinned host batch copied to the device at the start of every step, loss.item()"},
             "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": None,
+            "peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9,
             "mfu_vs_sustained_peak": value / world * flop / (peaks()["bf16_tflops_sustained"] * 1e12)}))
     if world > 1:
         dist.barrier()

@@ -1,1 +1,1 @@
-from vilmedic_b200.models import MVQA, RRG, RRG_HF, ConVIRT  # noqa: F401
+from vilmedic_b200.models import MVQA, RRG, RRG_HF, ConVIRT, GLoRIA  # noqa: F401

@@ -295,6 +295,14 @@ int vlm_beam_advance(long long* ids, long long* ids_tmp, int* row_map, int* map_
 int vlm_image_crop_flip_normalize(const uint8_t* in, float* out, const int* top, const int* left, const uint8_t* flip, int B,
                                   int Hin, int Win, int crop, const float* mean3, const float* std3, void* stream);
 
+/* Resize of the same transform on the device: one pass of Pillow's separable fixed-point resampling (what torchvision's Resize does to
+ * a PIL image) along one axis of uint8 [B, H, W, 3] images; axis 0 resamples columns (Hout == Hin), axis 1 rows (Wout == Win).
+ * bounds int32 [out, 2] = (first source index, tap count), coefs int32 [out, ksize] = round(k * 2^22), computed on the host exactly as
+ * Pillow does (vilmedic_b200/blocks/vision/preprocess.py: pil_resample_tables); out = clip8((2^21 + sum pix * coef) >> 22).
+ * Horizontal pass first, then vertical, like Pillow — bit-identical to PIL.Image.resize(size, BILINEAR). */
+int vlm_image_resample_u8(const uint8_t* in, uint8_t* out, const int* bounds, const int* coefs, int ksize, int B, int Hin, int Win,
+                          int Hout, int Wout, int axis, void* stream);
+
 /* ---- optimizer (vilmedic/executors/trainor.py:119-124) ------------------------------------------ */
 /* out[0] += sum(g^2)  (caller zeroes). */
 int vlm_sumsq_f32(const float* g, long long n, float* out, void* stream);

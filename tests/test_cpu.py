@@ -480,6 +480,7 @@ def test_beam_search_logic_matches_oracle_and_hf(k, n_models):
     ("config/RRG/synthetic-vit-b16.yml", "RRG"),
     ("config/RRG/synthetic-vit-b16-ensemble.yml", "RRG"),
     ("config/SELFSUP/synthetic-convirt-resnet50.yml", "ConVIRT"),
+    ("config/SELFSUP/synthetic-gloria-resnet50.yml", "GLoRIA"),
     ("config/MVQA/synthetic-vit-b16.yml", "MVQA"),
 ])
 def test_yaml_configs_build_through_create_model(path, proto):
@@ -489,8 +490,8 @@ def test_yaml_configs_build_through_create_model(path, proto):
     from vilmedic_b200 import executors
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     overrides = ["model.decoder.num_hidden_layers=1", "model.cnn.num_hidden_layers=1"] if proto == "RRG" and "vit" in path else []
-    if proto == "ConVIRT":
-        overrides = ["model.encoder.num_hidden_layers=1"]
+    if proto in ("ConVIRT", "GLoRIA"):
+        overrides = ["model.encoder.num_hidden_layers=%d" % (1 if proto == "ConVIRT" else 4)]
     if proto == "MVQA":
         overrides = ["model.cnn.num_hidden_layers=1", "model.transformer.num_hidden_layers=1"]
     config = executors.load_config(os.path.join(root, path), overrides)

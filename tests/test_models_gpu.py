@@ -114,3 +114,39 @@ def test_convirt(cuda_dev, loss_proto):
     torch.cuda.synchronize()
     assert abs(o["loss"].item() - o_ref["loss"].item()) <= 2e-2 * abs(o_ref["loss"].item()), (o["loss"].item(), o_ref["loss"].item())
     _check_grads(mine, ref, tol=2.5e-1)   # 8-sample contrastive loss through two towers: bf16 noise is amplified
+
+
+def test_gloria_model_forward_backward(cuda_dev):
+    """`model.proto: GLoRIA` (vilmedic/models/selfsup/GLoRIA.py:47-130; config/SELFSUP/gloria-mimic.yml): built through create_model from
+    the synthetic YAML config (smaller towers), one training forward + backward.  The loss must equal GLoRIALoss (golden-tested against
+    the reference's own file) evaluated on the features the model returns, and gradients must reach the text tower, the layer3 tap
+    (local embedder + ResNet stages up to layer3) and layer4 (global path)."""
+    import os
+    from vilmedic_b200 import executors
+    from vilmedic_b200.blocks.losses import GLoRIALoss
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    config = executors.load_config(os.path.join(root, "config/SELFSUP/synthetic-gloria-resnet50.yml"),
+                                   ["model.encoder.num_hidden_layers=4", "model.encoder.hidden_dropout_prob=0.0",
+                                    "model.encoder.attention_probs_dropout_prob=0.0", "model.forward_batch_size=3",
+                                    "dataset.seq.tokenizer_max_len=16", "dataset.seq.vocab_size=400", "model.encoder.vocab_size=400"])
+    tcfg = executors.utils.get(config, "trainor")
+    dl = executors.SyntheticLoader(tcfg, 6, n_batches=1)
+    model = executors.create_model(tcfg, dl).train()
+    batch = {k: v for k, v in next(iter(dl)).items() if v is not None}
+    out = model(**batch)
+    loss = out["loss"]
+    assert loss.dim() == 0 and torch.isfinite(loss)
+    assert out["local_features"].shape == (6, 768, 19, 19) and out["global_features"].shape == (6, 768)
+    assert out["word_embeddings"].shape == (6, 768, 16) and out["sent_embeddings"].shape == (6, 768)
+    # same loss from the returned features
+    ids = batch["input_ids"]
+    _, sents = model.aggregate_tokens(torch.zeros(4, 6, 16, 8), ids)
+    again, _ = GLoRIALoss(**dict(config.model.loss))(out["global_features"].detach(), out["local_features"].detach(),
+                                                     out["word_embeddings"].detach(), out["sent_embeddings"].detach(), sents)
+    assert abs(again.item() - loss.item()) <= 1e-4 * abs(loss.item()) + 1e-5
+    loss.backward()
+    torch.cuda.synchronize()
+    for p in (model.local_embedder.weight, model.global_embedder.weight, model.linguistic.encoder.encoder.layer[0].intermediate.dense.weight,
+              model.visual.model[6][0].conv1.weight, model.visual.model[7][0].conv1.weight, model.visual.model[0].weight):
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum().item() > 0
+    assert callable(model.eval_func)

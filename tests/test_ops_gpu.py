@@ -562,3 +562,27 @@ def test_image_crop_flip_normalize_bit_exact(cuda_dev):
     assert torch.equal(ev(x, device=cuda_dev).cpu(), crop_flip_normalize(x, z, z, z, 32, IMAGENET_MEAN, IMAGENET_STD))
     with pytest.raises(ValueError):
         ev(torch.zeros(1, 40, 32, 3, dtype=torch.uint8), device=cuda_dev)
+
+
+def test_gpu_resize_bit_identical_to_pillow(cuda_dev):
+    """`transforms.Resize(resize)` of the reference's transform (vilmedic/datasets/base/ImageDataset.py:99) on the device: Pillow's
+    separable fixed-point bilinear resampling, bit for bit, down- and up-scaling, and the whole Resize -> crop -> flip -> normalize chain
+    against torchvision's own Compose on PIL images."""
+    import numpy as np
+    from PIL import Image
+    import torchvision.transforms as T
+    from vilmedic_b200.blocks.vision.preprocess import GpuImageTransform, GpuResize, IMAGENET_MEAN, IMAGENET_STD, resize_output_size
+    rng = np.random.default_rng(0)
+    for (H, W, size) in [(300, 400, 256), (512, 512, 256), (200, 333, 256), (1024, 900, 256), (256, 256, 256)]:
+        imgs = rng.integers(0, 256, (3, H, W, 3), dtype=np.uint8)
+        oh, ow = resize_output_size(H, W, size)
+        want = np.stack([np.asarray(Image.fromarray(im).resize((ow, oh), Image.BILINEAR)) for im in imgs])
+        got = GpuResize(size)(torch.from_numpy(imgs)).cpu().numpy()
+        assert got.shape == want.shape and np.array_equal(got, want), (H, W, int(np.abs(got.astype(int) - want.astype(int)).max()))
+        assert want.shape[1:3] == tuple(T.Resize(size)(Image.fromarray(imgs[0])).size[::-1])
+    # full chain, evaluation flavour (center of randomness removed): Resize((224, 224)) -> ToTensor -> Normalize
+    imgs = rng.integers(0, 256, (2, 320, 320, 3), dtype=np.uint8)
+    ref_tf = T.Compose([T.Resize((224, 224)), T.ToTensor(), T.Normalize(IMAGENET_MEAN, IMAGENET_STD)])
+    want = torch.stack([ref_tf(Image.fromarray(im)) for im in imgs])
+    got = GpuImageTransform(crop=224, train=False, resize=(224, 224))(torch.from_numpy(imgs))
+    assert torch.equal(got.cpu(), want)

@@ -37,12 +37,15 @@ class EncoderModel(nn.Module):
             if missing or unexpected:
                 raise RuntimeError("proto %r does not match the tower: missing %s, unexpected %s" % (proto, missing[:5], unexpected[:5]))
 
-    def forward(self, input_ids, attention_mask=None, **kwargs):
+    def forward(self, input_ids, attention_mask=None, output_hidden_states=None, **kwargs):
         input_ids = input_ids.cuda(non_blocking=True)
         attention_mask = attention_mask.cuda(non_blocking=True) if attention_mask is not None else None
-        x, B, T = self.encoder.hidden_states(input_ids, attention_mask)
+        states = [] if output_hidden_states else None
+        x, B, T = self.encoder.hidden_states(input_ids, attention_mask, collect=states)
         D = x.shape[-1]
         out = {"last_hidden_state": x.view(B, T, D), "pooler_output": None}
+        if states is not None:                       # embedding output + one entry per layer, as HF's `hidden_states` tuple
+            out["hidden_states"] = tuple(h.view(B, T, D) for h in states)
         if self.pooler is not None:
             arena = get_arena(_root_of(self))
             first = x.view(B, T, D)[:, 0].contiguous()

@@ -172,7 +172,10 @@ class VisualEncoder(nn.Module):
         """torchvision ResNet on the sm_100a kernels (vilmedic_b200/cnn.py).  The kernels work on [B, H*W, C] (NHWC), which IS
         the reference's `batch_first` layout `out.view(B, C, -1).permute(0, 2, 1)` (:200-203) — no data movement."""
         from ...cnn import resnet_forward
-        x, (B, H, W, C), pooled = resnet_forward(self._resnet, images, self.training)
+        tap_stage = getattr(self, "tap_stage", None)
+        x, (B, H, W, C), pooled = resnet_forward(self._resnet, images, self.training, tap_stage)
+        if tap_stage is not None:                 # (bf16 [B*h*w, c], (B, h, w, c)) of torchvision `layer<tap_stage>` — GLoRIA's hook
+            object.__setattr__(self, "tapped", self._resnet.last_tap)
         p = self.dropout_out.p
         if p > 0 and self.training and torch.is_grad_enabled():
             pad = (-x.numel()) % 8

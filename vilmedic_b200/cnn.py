@@ -155,8 +155,10 @@ class ResNetRunner:
         blocks = [_Block(arena, b) for layer in self.layers for b in layer]
         return stem, blocks
 
-    def run(self, images, training, save):
-        """images fp32 [B,3,H,W] (CUDA) -> (features bf16 [B*Ho*Wo, C] or [B, C] after the average pool, shape, tape)."""
+    def run(self, images, training, save, tap_stage=None):
+        """images fp32 [B,3,H,W] (CUDA) -> (features bf16 [B*Ho*Wo, C] or [B, C] after the average pool, shape, tape).
+        tap_stage = n: the output of residual stage n (1-based, torchvision `layer<n>`) is returned as tape/aux (GLoRIA reads layer3
+        through a forward hook, vilmedic/models/selfsup/GLoRIA.py:72-79)."""
         stem, blocks = self._build()
         B, Cin, H, W = images.shape
         if Cin != self.stem_conv.in_channels:
@@ -165,21 +167,29 @@ class ResNetRunner:
         pool_in = shp
         x, idx = ops.maxpool3x3s2_fwd(x, *shp)
         shp = (B, ops.conv_out_size(shp[1], 3, 2, 1), ops.conv_out_size(shp[2], 3, 2, 1), shp[3])
-        for blk in blocks:
+        tap, tap_shp, tap_idx = None, None, -1
+        if tap_stage is not None:
+            tap_idx = sum(len(l) for l in self.layers[:tap_stage]) - 1          # index of the last block of that stage
+        for bi, blk in enumerate(blocks):
             x, shp = blk.forward(x, shp, training, save)
+            if bi == tap_idx:
+                tap, tap_shp = x, shp
         if self.avgpool:
             x = ops.avgpool_fwd(x, B, shp[1] * shp[2], shp[3])
-        tape = (stem, blocks, idx, pool_in, shp) if save else None
+        tape = (stem, blocks, idx, pool_in, shp, tap_idx) if save else None
+        self.last_tap = (tap, tap_shp)
         return x, shp, tape
 
-    def backward(self, tape, dy):
-        stem, blocks, idx, pool_in, shp = tape
+    def backward(self, tape, dy, dtap=None):
+        stem, blocks, idx, pool_in, shp, tap_idx = tape
         B = shp[0]
         d = dy.contiguous()
         if self.avgpool:
             d = ops.avgpool_bwd(d, B, shp[1] * shp[2], shp[3])
-        for blk in reversed(blocks):
-            d = blk.backward(d)
+        for bi in range(len(blocks) - 1, -1, -1):
+            if bi == tap_idx and dtap is not None:
+                d = d + dtap.to(d.dtype).reshape(d.shape)       # gradient of the tapped activation joins the main path
+            d = blocks[bi].backward(d)
         d = ops.maxpool3x3s2_bwd(d, idx, *pool_in)
         stem.backward(d, need_dx=False)
 
@@ -188,29 +198,35 @@ class ResNetFn(torch.autograd.Function):
     """Whole backbone as one autograd node (the images need no gradient; `anchor` is a parameter that does)."""
 
     @staticmethod
-    def forward(ctx, images, anchor, runner):
-        x, shp, tape = runner.run(images, training=True, save=True)
+    def forward(ctx, images, anchor, runner, tap_stage=None):
+        x, shp, tape = runner.run(images, training=True, save=True, tap_stage=tap_stage)
         ctx.runner, ctx.tape = runner, tape
         ctx.out_shape = shp
-        return x
+        if tap_stage is None:
+            return x
+        return x, runner.last_tap[0]
 
     @staticmethod
-    def backward(ctx, dy):
-        ctx.runner.backward(ctx.tape, dy)
+    def backward(ctx, dy, dtap=None):
+        ctx.runner.backward(ctx.tape, dy, dtap)
         ctx.tape = None
-        return None, None, None
+        return None, None, None, None
 
 
-def resnet_forward(runner, images, training):
-    """-> (features bf16, (B, Ho, Wo, C), pooled: bool)."""
+def resnet_forward(runner, images, training, tap_stage=None):
+    """-> (features bf16, (B, Ho, Wo, C), pooled: bool); with tap_stage also runner.last_tap = (bf16 [B*h*w, c], (B, h, w, c))."""
     images = images.contiguous().float()
     if training and torch.is_grad_enabled() and any(p.requires_grad for p in runner.model.parameters()):
-        x = ResNetFn.apply(images, runner.stem_bn.weight, runner)
+        if tap_stage is None:
+            x = ResNetFn.apply(images, runner.stem_bn.weight, runner)
+        else:
+            x, tap = ResNetFn.apply(images, runner.stem_bn.weight, runner, tap_stage)
+            runner.last_tap = (tap, runner.last_tap[1])          # the autograd-connected tensor
         B, H, W = images.shape[0], images.shape[2], images.shape[3]
         shp = _out_shape(runner, B, H, W)
     else:
         with torch.no_grad():      # evaluation, or train mode without autograd (BatchNorm still uses / updates batch statistics)
-            x, shp, _ = runner.run(images, training=training, save=False)
+            x, shp, _ = runner.run(images, training=training, save=False, tap_stage=tap_stage)
     return x, shp, runner.avgpool
 
 

@@ -178,6 +178,38 @@ __global__ void image_crop_flip_normalize_kernel(const uint8_t* __restrict__ in,
   }
 }
 
+// ---------------------------------------------------------------- Resize of the reference's transform on the device
+// torchvision Resize on a PIL image (vilmedic/datasets/base/ImageDataset.py:97-104 `transforms.Resize(resize)`) is Pillow's two-pass
+// separable convolution resampling (ImagingResample: horizontal pass into an 8-bit intermediate, then the vertical pass), bilinear
+// = triangle filter whose support grows with the down-scaling factor (antialias), coefficients normalised in double and applied in
+// fixed point: acc = 2^21 + sum pixel * round(k * 2^22); out = clip8(acc >> 22).  The coefficient tables (bounds = first source index
+// and tap count per output coordinate, ksize taps each) are computed on the host exactly as Pillow computes them
+// (blocks/vision/preprocess.py: pil_resample_tables) and passed in; this kernel is one pass along one axis of uint8 HWC images.
+// axis 0: out[b, y, xx, c] = sum_x in[b, y, xmin + x, c] * k[xx][x]  (Wout columns);  axis 1: the same along rows.
+__global__ void resample_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int* __restrict__ bounds,
+                                   const int* __restrict__ coefs, int ksize, int B, int Hin, int Win, int Hout, int Wout, int axis) {
+  const long long n = (long long)B * Hout * Wout * 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % 3);
+    const int xx = (int)((i / 3) % Wout);
+    const int yy = (int)((i / (3LL * Wout)) % Hout);
+    const int b = (int)(i / (3LL * Wout * Hout));
+    const int o = axis == 0 ? xx : yy;
+    const int lo = bounds[2 * o], cnt = bounds[2 * o + 1];
+    const int* k = coefs + (long long)o * ksize;
+    int acc = 1 << 21;
+    if (axis == 0) {
+      const uint8_t* src = in + (((long long)b * Hin + yy) * Win + lo) * 3 + c;
+      for (int x = 0; x < cnt; ++x) acc += (int)src[3 * x] * k[x];
+    } else {
+      const uint8_t* src = in + (((long long)b * Hin + lo) * Win + xx) * 3 + c;
+      for (int y = 0; y < cnt; ++y) acc += (int)src[(long long)y * Win * 3] * k[y];
+    }
+    acc >>= 22;
+    out[i] = (uint8_t)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+  }
+}
+
 // ---------------------------------------------------------------- VisualEncoder.encode feature mask
 // mask[r] = (sum_d |f[r,d]| != 0)      (vilmedic/blocks/vision/visual_encoder.py:138)
 __global__ void features_mask_kernel(const bf16* __restrict__ f, uint8_t* __restrict__ mask, int R, int D) {
@@ -383,6 +415,15 @@ extern "C" int vlm_image_crop_flip_normalize(const uint8_t* in, float* out, cons
   image_crop_flip_normalize_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, top, left, flip, B, Hin, Win, crop, mean3[0],
                                                                                      mean3[1], mean3[2], std3[0], std3[1], std3[2]);
   return check_launch("image_crop_flip_normalize");
+}
+
+extern "C" int vlm_image_resample_u8(const uint8_t* in, uint8_t* out, const int* bounds, const int* coefs, int ksize, int B, int Hin,
+                                     int Win, int Hout, int Wout, int axis, void* stream) {
+  VLM_REQUIRE(in && out && bounds && coefs && ksize > 0 && B > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, "vlm_image_resample_u8: bad args");
+  VLM_REQUIRE(axis == 0 ? Hout == Hin : (axis == 1 && Wout == Win), "vlm_image_resample_u8: one axis per pass (axis 0: columns, axis 1: rows)");
+  const long long n = (long long)B * Hout * Wout * 3;
+  resample_u8_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, bounds, coefs, ksize, B, Hin, Win, Hout, Wout, axis);
+  return check_launch("image_resample_u8");
 }
 
 extern "C" int vlm_features_mask(const void* feats, uint8_t* mask, int R, int D, void* stream) {

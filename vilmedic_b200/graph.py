@@ -11,7 +11,7 @@ from . import ops
 
 
 class GraphedTrainStep:
-    def __init__(self, model, optimizer, example_batch, grad_sync=None, warmup=3, step_fn=None):
+    def __init__(self, model, optimizer, example_batch, grad_sync=None, warmup=3, step_fn=None, stream=None):
         self.model = model
         self.opt = optimizer
         self.sync = grad_sync
@@ -20,7 +20,7 @@ class GraphedTrainStep:
         self.counter = torch.zeros(1, device=dev, dtype=torch.int64)
         ops.RNG_COUNTER[0] = self.counter
         self._step_fn = step_fn or self._default_step
-        s = torch.cuda.Stream()
+        s = stream if stream is not None else torch.cuda.Stream()      # pass the stream earlier eager steps ran on, if any
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):

@@ -100,7 +100,8 @@ class LinearGeluFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, anchor, P):
-        stash = torch.empty((x.shape[0], P.w.shape[0]), device=x.device, dtype=torch.bfloat16) if torch.is_grad_enabled() else None
+        # (grad mode is off inside Function.forward: ask the context whether a backward can follow)
+        stash = torch.empty((x.shape[0], P.w.shape[0]), device=x.device, dtype=torch.bfloat16) if any(ctx.needs_input_grad) else None
         y = ops.gemm(x, P.w, bias=P.b, act=ops.ACT_GELU, aux_out=stash)
         ctx.saved = (x, stash, P)
         return y
@@ -109,7 +110,6 @@ class LinearGeluFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, stash, P = ctx.saved
         dy = dy.contiguous()
-        dpre = torch.empty_like(dy)
         # dpre = dy * GELU'(pre): the x-stash epilogue needs a GEMM in front of it; here the product is elementwise on [M, D] only
         dpre = (dy.float() * stash.float()).to(torch.bfloat16)
         _wgrad(dpre, x, P)
@@ -735,10 +735,13 @@ def _init_bert_weights(module, std):
             m.bias.data.zero_()
 
 
-def run_bert_layers(layers, x, B, T, arena, anchor, cfg, kmask=None, enc=None, enc_mask=None, training=False):
+def run_bert_layers(layers, x, B, T, arena, anchor, cfg, kmask=None, enc=None, enc_mask=None, training=False, collect=None):
+    """collect: optional list that receives the hidden states after every layer (HF output_hidden_states)."""
     grad = torch.is_grad_enabled()
     for layer in layers:
         x = BertLayerFn.apply(x, enc, anchor, layer, arena, B, T, kmask, enc_mask, bool(cfg.is_decoder), training and grad, grad)
+        if collect is not None:
+            collect.append(x)
     return x
 
 
@@ -838,8 +841,9 @@ class BertTower(nn.Module):
 
     # ---- hidden states --------------------------------------------------------------------------------------------
     def hidden_states(self, input_ids, attention_mask=None, encoder_hidden_states=None, encoder_attention_mask=None,
-                      inputs_embeds=None):
-        """-> bf16 [B*T, D] after the last layer.  encoder_hidden_states: bf16 [B,S,De] (CUDA)."""
+                      inputs_embeds=None, collect=None):
+        """-> bf16 [B*T, D] after the last layer.  encoder_hidden_states: bf16 [B,S,De] (CUDA).
+        collect: optional list that receives the embedding output and every layer's output (HF `output_hidden_states=True`)."""
         cfg = self.cfg
         arena = get_arena(_root_of(self))
         grad = torch.is_grad_enabled()
@@ -863,6 +867,8 @@ class BertTower(nn.Module):
                 pos_ids = ((torch.cumsum(m, dim=1).to(torch.int32) * m) + pad).contiguous().view(-1)
             x = BertEmbedFn.apply(ids.view(-1), anchor, self._core.embeddings, arena, T, 0, cfg.layer_norm_eps, pos_ids)
         x = dropout(x, cfg.hidden_dropout_prob, training and grad)
+        if collect is not None:
+            collect.append(x)
         kmask = None
         if attention_mask is not None:
             kmask = (attention_mask.to(dev) != 0).to(torch.uint8).contiguous()
@@ -877,7 +883,7 @@ class BertTower(nn.Module):
             if encoder_attention_mask is not None:
                 enc_mask = (encoder_attention_mask.to(dev) != 0).to(torch.uint8).contiguous()
         x = run_bert_layers(self._core.encoder.layer, x, B, T, arena, anchor, cfg, kmask=kmask, enc=enc, enc_mask=enc_mask,
-                            training=training)
+                            training=training, collect=collect)
         return x, B, T
 
     def head_input(self, x):

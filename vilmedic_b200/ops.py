@@ -646,3 +646,13 @@ def sample_rows(logits, V, cand_score, cand_tok, seed, offset, t_ptr, temperatur
     _req(logits.dtype == torch.float32 and logits.stride(1) == 1, "sample_rows: fp32 logits rows")
     check(_L().vlm_sample_rows(ptr(logits), c_ll(logits.stride(0)), c_int(V), c_float(temperature), c_u64(seed), c_u64(offset), ptr(t_ptr),
                                ptr(cand_score), ptr(cand_tok), c_int(logits.shape[0]), stream_ptr()), "vlm_sample_rows")
+
+
+def image_resample_u8(x, bounds, coefs, out_h, out_w, axis):
+    """One Pillow-compatible resampling pass over uint8 [B,H,W,3] (axis 0: columns -> out_w, axis 1: rows -> out_h)."""
+    _req(x.is_cuda and x.dtype == torch.uint8 and x.dim() == 4 and x.shape[3] == 3 and x.is_contiguous(), "image_resample_u8: uint8 [B,H,W,3]")
+    B, H, W, _ = x.shape
+    out = torch.empty((B, out_h, out_w, 3), device=x.device, dtype=torch.uint8)
+    check(_L().vlm_image_resample_u8(ptr(x), ptr(out), ptr(bounds), ptr(coefs), c_int(coefs.shape[1]), c_int(B), c_int(H), c_int(W),
+                                     c_int(out_h), c_int(out_w), c_int(axis), stream_ptr()), "vlm_image_resample_u8")
+    return out
