@@ -48,7 +48,8 @@ __device__ __forceinline__ void tma_load_4d(const void* desc, uint64_t* bar, voi
       : "memory");
 }
 
-static constexpr int ATC_THREADS = 320;          // 2 control warps + 8 compute warps
+static constexpr int ATC_SPLIT = 4;                              // compute warps per TMEM lane quadrant (each owns Nq / 4 query columns)
+static constexpr int ATC_THREADS = 64 + 128 * ATC_SPLIT;         // 2 control warps + 16 compute warps
 static constexpr int ATC_S_COL = 0, ATC_DV_COL = 256, ATC_DK_COL = 320, ATC_DQ_COL = 384;
 
 template <int ATOMS, bool DROPOUT>
@@ -121,12 +122,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     mbar_init(&kv_empty[0], 1);
     mbar_init(&kv_empty[1], 1);
     mbar_init(s_full, 1);
-    mbar_init(p_ready, 8);
+    mbar_init(p_ready, 4 * ATC_SPLIT);
     mbar_init(dp_full, 1);
     mbar_init(dv_done, 1);
-    mbar_init(ds_ready, 8);
+    mbar_init(ds_ready, 4 * ATC_SPLIT);
     mbar_init(out_full, 1);
-    mbar_init(out_free, 8);
+    mbar_init(out_free, 4 * ATC_SPLIT);
     fence_barrier_init();
   } else if (warp_idx == 1) {
     tmem_alloc<512>(tmem_ptr_smem);
@@ -227,17 +228,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
     }
   } else {
-    // ===================================================== compute warps (256 threads)
+    // ===================================================== compute warps (128 * ATC_SPLIT threads)
+    // Each softmax-side thread runs one long dependent chain per chunk (TMEM load -> ex2 -> pack -> st.shared); with two warps per
+    // scheduler the issue slots sat idle ~90 % of the time (ncu, round 2), so every lane quadrant is shared by ATC_SPLIT warps.
     const int quad = warp_idx & 3;             // TMEM lane quadrant
-    const int half = (warp_idx - 2) >> 2;      // which half of the query columns / output columns
+    const int part = (warp_idx - 2) >> 2;      // which slice of the query columns / output columns
     const int r = quad * 32 + lane;            // key row inside the tile
-    const int ct = threadIdx.x - 64;           // 0..255
+    const int ct = threadIdx.x - 64;           // 0 .. 128 * ATC_SPLIT - 1
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float sl2 = p.scale * 1.4426950408889634f;
     const unsigned long long off_eff = p.offset + ((DROPOUT && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
     const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
     const float inv_keep = DROPOUT ? 1.f / (1.f - p.p_drop) : 1.f;
-    const int half_cols = Nq >> 1;             // multiple of 16
+    const int part_cols = Nq / ATC_SPLIT;      // multiple of 8
     const uint32_t pt_row = (uint32_t)(r * 128);   // row offset inside a 64-column atom of the P^T / dS^T tile
     const uint32_t aPTs = smem_u32(sPT), aP2s = smem_u32(sP2), aLse = smem_u32(sLse), aDelta = smem_u32(sDelta);   // shared-space addresses
     const int r7 = r & 7;
@@ -246,7 +249,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const int b = item / p.H, h = item % p.H;
       const uint32_t dkey = attn_drop_key(p.seed, off_eff, item);
       // ---- per-item staging: lse (log2 units, +inf beyond Tq) and delta = rowsum(dO * O)
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 128 * ATC_SPLIT);
       if (ct < Nq) {
         float l2 = INFINITY, dl = 0.f;
         if (ct < p.Tq) {
@@ -256,7 +259,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         sLse[ct] = l2;
         sDelta[ct] = dl;
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 128 * ATC_SPLIT);
       for (int j = 0; j < ntiles; ++j, ++tile_cnt) {
         const uint32_t tph = tile_cnt & 1u;
         const int kk = j * 128 + r;
@@ -268,58 +271,48 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         // q0 is fully visible iff q0 >= k_lo + 31 and fully masked iff q0 + 15 < k_lo; only the chunks on the diagonal test
         // per element.  Key rows that are padding / masked (kvalid == false) produce zeros without any math.
         const int k_lo = j * 128 + quad * 32;
-        auto pass_a_chunk = [&](const uint32_t* v, int q0) {
-          float pv[16], pd[16];
-          if (kvalid && !(p.causal && q0 + 15 < k_lo)) {
-            float ls[16];
+        auto pass_a_chunk = [&](const uint32_t* v, int q0) {      // 8 query columns = one 16-byte unit of the P^T row
+          float pv[8], pd[8];
+          if (kvalid && !(p.causal && q0 + 7 < k_lo)) {
+            float ls[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 2; ++i) {
               const float4 t = lds128f(aLse + (uint32_t)((q0 + 4 * i) * 4));
               ls[4 * i] = t.x; ls[4 * i + 1] = t.y; ls[4 * i + 2] = t.z; ls[4 * i + 3] = t.w;
             }
             if (!p.causal || q0 >= k_lo + 31) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -ls[i]));
+              for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -ls[i]));
             } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) pv[i] = (kk <= q0 + i) ? ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -ls[i])) : 0.f;
+              for (int i = 0; i < 8; ++i) pv[i] = (kk <= q0 + i) ? ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -ls[i])) : 0.f;
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) pv[i] = 0.f;
+            for (int i = 0; i < 8; ++i) pv[i] = 0.f;
           }
           if (DROPOUT) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) pd[i] = attn_drop_rand(dkey, q0 + i, kk, p.Sk) >= thr ? pv[i] * inv_keep : 0.f;
+            for (int i = 0; i < 8; ++i) pd[i] = attn_drop_rand(dkey, q0 + i, kk, p.Sk) >= thr ? pv[i] * inv_keep : 0.f;
           }
-          const uint32_t off0 = (uint32_t)((q0 >> 6) * 16384) + pt_row;
-          const int u0 = (q0 & 63) >> 3;
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const uint32_t off = off0 + (uint32_t)(((u0 + u) ^ r7) << 4);
-            uint4 w;
-            if (DROPOUT) {
-              w.x = pack_bf16x2(pd[8 * u + 0], pd[8 * u + 1]); w.y = pack_bf16x2(pd[8 * u + 2], pd[8 * u + 3]);
-              w.z = pack_bf16x2(pd[8 * u + 4], pd[8 * u + 5]); w.w = pack_bf16x2(pd[8 * u + 6], pd[8 * u + 7]);
-              sts128(aPTs + off, w.x, w.y, w.z, w.w);
-            }
-            w.x = pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]); w.y = pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]);
-            w.z = pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]); w.w = pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]);
-            sts128((DROPOUT ? aP2s : aPTs) + off, w.x, w.y, w.z, w.w);
-          }
+          const uint32_t off = (uint32_t)((q0 >> 6) * 16384) + pt_row + (uint32_t)((((q0 & 63) >> 3) ^ r7) << 4);
+          if (DROPOUT)
+            sts128(aPTs + off, pack_bf16x2(pd[0], pd[1]), pack_bf16x2(pd[2], pd[3]), pack_bf16x2(pd[4], pd[5]), pack_bf16x2(pd[6], pd[7]));
+          sts128((DROPOUT ? aP2s : aPTs) + off, pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]),
+                 pack_bf16x2(pv[6], pv[7]));
         };
         {  // TMEM loads are software-pipelined: the next chunk is in flight while the current one is processed
-          const int qbase = half * half_cols;
-          uint32_t va[16], vb[16];
-          tmem_ld16(lane_taddr + ATC_S_COL + qbase, va);
-          for (int c = 0; c < half_cols; c += 32) {
+          const int qbase = part * part_cols;
+          uint32_t va[8], vb[8];
+          tmem_ld8(lane_taddr + ATC_S_COL + qbase, va);
+          for (int c = 0; c < part_cols; c += 16) {
             tmem_ld_wait();
-            if (c + 16 < half_cols) tmem_ld16(lane_taddr + ATC_S_COL + qbase + c + 16, vb);
+            if (c + 8 < part_cols) tmem_ld8(lane_taddr + ATC_S_COL + qbase + c + 8, vb);
             pass_a_chunk(va, qbase + c);
-            if (c + 16 < half_cols) {
+            if (c + 8 < part_cols) {
               tmem_ld_wait();
-              if (c + 32 < half_cols) tmem_ld16(lane_taddr + ATC_S_COL + qbase + c + 32, va);
-              pass_a_chunk(vb, qbase + c + 16);
+              if (c + 16 < part_cols) tmem_ld8(lane_taddr + ATC_S_COL + qbase + c + 16, va);
+              pass_a_chunk(vb, qbase + c + 8);
             }
           }
         }
@@ -334,451 +327,42 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         // dS^T = P^T * (dP^T - delta) — the softmax scale is applied once per dK / dQ output element in the epilogue instead
         // of once per score element here.
         auto pass_b_chunk = [&](const uint32_t* v, int q0) {
-          float dl[16];
+          float dl[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 2; ++i) {
             const float4 t = lds128f(aDelta + (uint32_t)((q0 + 4 * i) * 4));
             dl[4 * i] = t.x; dl[4 * i + 1] = t.y; dl[4 * i + 2] = t.z; dl[4 * i + 3] = t.w;
           }
-          const uint32_t off0 = (uint32_t)((q0 >> 6) * 16384) + pt_row;
-          const int u0 = (q0 & 63) >> 3;
+          const uint32_t off = (uint32_t)((q0 >> 6) * 16384) + pt_row + (uint32_t)((((q0 & 63) >> 3) ^ r7) << 4);
+          const uint4 pw = lds128u((DROPOUT ? aP2s : aPTs) + off);
+          uint4 kw = pw;
+          if (DROPOUT) kw = lds128u(aPTs + off);   // dropped P: zero <=> dropped (or P == 0)
+          const uint32_t pw4[4] = {pw.x, pw.y, pw.z, pw.w}, kw4[4] = {kw.x, kw.y, kw.z, kw.w};
+          uint32_t ow[4];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const uint32_t off = off0 + (uint32_t)(((u0 + u) ^ r7) << 4);
-            const uint4 pw = lds128u((DROPOUT ? aP2s : aPTs) + off);
-            uint4 kw = pw;
-            if (DROPOUT) kw = lds128u(aPTs + off);   // dropped P: zero <=> dropped (or P == 0)
-            const uint32_t pw4[4] = {pw.x, pw.y, pw.z, pw.w}, kw4[4] = {kw.x, kw.y, kw.z, kw.w};
-            uint32_t ow[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 pp = unpack_bf16x2(pw4[e]), kp = unpack_bf16x2(kw4[e]);
-              float d0 = __uint_as_float(v[8 * u + 2 * e]), d1 = __uint_as_float(v[8 * u + 2 * e + 1]);
-              if (DROPOUT) {
-                d0 = kp.x != 0.f ? d0 * inv_keep : 0.f;
-                d1 = kp.y != 0.f ? d1 * inv_keep : 0.f;
-              }
-              ow[e] = pack_bf16x2(pp.x * (d0 - dl[8 * u + 2 * e]), pp.y * (d1 - dl[8 * u + 2 * e + 1]));
-            }
-            sts128(aPTs + off, ow[0], ow[1], ow[2], ow[3]);
-          }
-        };
-        {
-          const int qbase = half * half_cols;
-          uint32_t va[16], vb[16];
-          tmem_ld16(lane_taddr + ATC_S_COL + qbase, va);
-          for (int c = 0; c < half_cols; c += 32) {
-            tmem_ld_wait();
-            if (c + 16 < half_cols) tmem_ld16(lane_taddr + ATC_S_COL + qbase + c + 16, vb);
-            pass_b_chunk(va, qbase + c);
-            if (c + 16 < half_cols) {
-              tmem_ld_wait();
-              if (c + 32 < half_cols) tmem_ld16(lane_taddr + ATC_S_COL + qbase + c + 32, va);
-              pass_b_chunk(vb, qbase + c + 16);
-            }
-          }
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(ds_ready);
-        // ---------------- epilogue: dV_j, dK_j (+ dQ after the last key tile)
-        mbar_wait(out_full, tph);
-        tc_fence_after();
-        {
-          uint32_t acc[32];
-          tmem_ld32(lane_taddr + ATC_DV_COL + half * 32, acc);
-          tmem_ld_wait();
-          if (kk < p.Sk) {
-            uint4* dst = reinterpret_cast<uint4*>(p.dv + (long long)b * p.dv_bs + (long long)kk * p.dv_rs + h * 64 + half * 32);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]), __uint_as_float(acc[8 * i + 1])),
-                                  pack_bf16x2(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3])),
-                                  pack_bf16x2(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])),
-                                  pack_bf16x2(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7])));
-          }
-          const float sc = p.scale;          // dS was left unscaled (pass B)
-          tmem_ld32(lane_taddr + ATC_DK_COL + half * 32, acc);
-          tmem_ld_wait();
-          if (kk < p.Sk) {
-            uint4* dst = reinterpret_cast<uint4*>(p.dk + (long long)b * p.dk_bs + (long long)kk * p.dk_rs + h * 64 + half * 32);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]) * sc, __uint_as_float(acc[8 * i + 1]) * sc),
-                                  pack_bf16x2(__uint_as_float(acc[8 * i + 2]) * sc, __uint_as_float(acc[8 * i + 3]) * sc),
-                                  pack_bf16x2(__uint_as_float(acc[8 * i + 4]) * sc, __uint_as_float(acc[8 * i + 5]) * sc),
-                                  pack_bf16x2(__uint_as_float(acc[8 * i + 6]) * sc, __uint_as_float(acc[8 * i + 7]) * sc));
-          }
-          if (j == ntiles - 1) {
-            const int q_blocks = (Nq + 127) / 128;
-            for (int mb = 0; mb < q_blocks; ++mb) {
-              tmem_ld32(lane_taddr + ATC_DQ_COL + mb * 64 + half * 32, acc);
-              tmem_ld_wait();
-              const int q = mb * 128 + r;
-              if (q < p.Tq) {
-                uint4* dst = reinterpret_cast<uint4*>(p.dq + (long long)b * p.dq_bs + (long long)q * p.dq_rs + h * 64 + half * 32);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]) * sc, __uint_as_float(acc[8 * i + 1]) * sc),
-                                      pack_bf16x2(__uint_as_float(acc[8 * i + 2]) * sc, __uint_as_float(acc[8 * i + 3]) * sc),
-                                      pack_bf16x2(__uint_as_float(acc[8 * i + 4]) * sc, __uint_as_float(acc[8 * i + 5]) * sc),
-                                      pack_bf16x2(__uint_as_float(acc[8 * i + 6]) * sc, __uint_as_float(acc[8 * i + 7]) * sc));
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(out_free);
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp_idx == 1) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (opt-in: VLM_ATTN_BWD_PIPE=1; not yet run on a GPU): software-pipelined variant of the backward for Tq <= 128
-// (decoder self- and cross-attention).  dP^T gets its own TMEM columns [128, 256), Q / dO are double-buffered by item, and
-// the MMA warp issues S^T(t+1) as soon as pass A of tile t has drained the S columns and dP^T(t+1) as soon as pass B has
-// drained the dP columns — so the softmax warps never wait for those two products or for the TMA loads of the next item
-// (profiles/ncu_r1c_gemm_attn_bwd.txt: half of the stall samples of the serial kernel sit on those waits).  The passes and the
-// epilogue are the code of attn_bwd_tc_kernel above, unchanged.
-static constexpr int PIPE_DP_COL = 128;
-
-template <bool DROPOUT>
-struct AtcPipeSmem {
-  static constexpr int Q_BYTES = 128 * 128;
-  static constexpr int KV_BYTES = 128 * 128;
-  static constexpr int PT_BYTES = 2 * 16384;
-  static constexpr int OFF_Q = 0;                           // 2 buffers (item parity)
-  static constexpr int OFF_DO = OFF_Q + 2 * Q_BYTES;        // 2 buffers
-  static constexpr int OFF_K = OFF_DO + 2 * Q_BYTES;        // 2 buffers (tile parity)
-  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;        // 2 buffers
-  static constexpr int OFF_PT = OFF_V + 2 * KV_BYTES;
-  static constexpr int OFF_P2 = OFF_PT + PT_BYTES;
-  static constexpr int OFF_LSE = OFF_P2 + (DROPOUT ? PT_BYTES : 0);   // float [2][128]
-  static constexpr int OFF_DELTA = OFF_LSE + 2 * 128 * 4;             // float [2][128]
-  static constexpr int OFF_BAR = OFF_DELTA + 2 * 128 * 4;
-  static constexpr int NUM_BARS = 15;
-  static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
-};
-
-template <bool DROPOUT>
-__global__ void __launch_bounds__(ATC_THREADS, 1)
-attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                        const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, AttnTcParams p) {
-  using S = AtcPipeSmem<DROPOUT>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem + S::OFF_Q;
-  uint8_t* sDO = smem + S::OFF_DO;
-  uint8_t* sK = smem + S::OFF_K;
-  uint8_t* sV = smem + S::OFF_V;
-  uint8_t* sPT = smem + S::OFF_PT;
-  uint8_t* sP2 = smem + S::OFF_P2;
-  float* sLse = reinterpret_cast<float*>(smem + S::OFF_LSE);
-  float* sDelta = reinterpret_cast<float*>(smem + S::OFF_DELTA);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
-  uint64_t* qdo_full = bars + 0;   // [2]
-  uint64_t* qdo_empty = bars + 2;  // [2]
-  uint64_t* kv_full = bars + 4;    // [2]
-  uint64_t* kv_empty = bars + 6;   // [2]
-  uint64_t* s_full = bars + 8;
-  uint64_t* p_ready = bars + 9;
-  uint64_t* dp_full = bars + 10;
-  uint64_t* dv_done = bars + 11;
-  uint64_t* ds_ready = bars + 12;
-  uint64_t* out_full = bars + 13;
-  uint64_t* out_free = bars + 14;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + S::NUM_BARS);
-
-  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nitems = p.B * p.H;
-  const int ntiles = (p.Sk + 127) / 128;
-  const int Nq = p.Nq;                                       // <= 128
-  const int my_items = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int ntot = my_items * ntiles;
-
-  if (warp_idx == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_q);
-    tma_prefetch_desc(&tm_k);
-    tma_prefetch_desc(&tm_v);
-    tma_prefetch_desc(&tm_do);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&qdo_full[i], 1);
-      mbar_init(&qdo_empty[i], 1);
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 8);
-    mbar_init(dp_full, 1);
-    mbar_init(dv_done, 1);
-    mbar_init(ds_ready, 8);
-    mbar_init(out_full, 1);
-    mbar_init(out_free, 8);
-    fence_barrier_init();
-  } else if (warp_idx == 1) {
-    tmem_alloc<512>(tmem_ptr_smem);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  if (warp_idx == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
-      uint32_t it = 0, t = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-        const int b = item / p.H, h = item % p.H;
-        const uint32_t qb = it & 1u;
-        mbar_wait(&qdo_empty[qb], ((it >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(&qdo_full[qb], 2u * (uint32_t)Nq * 128u);
-        tma_load_4d(&tm_q, &qdo_full[qb], sQ + qb * S::Q_BYTES, 0, h, 0, b);
-        tma_load_4d(&tm_do, &qdo_full[qb], sDO + qb * S::Q_BYTES, 0, h, 0, b);
-        for (int j = 0; j < ntiles; ++j, ++t) {
-          const uint32_t kb = t & 1u;
-          mbar_wait(&kv_empty[kb], ((t >> 1) & 1u) ^ 1u);
-          mbar_expect_tx(&kv_full[kb], 2u * S::KV_BYTES);
-          tma_load_4d(&tm_k, &kv_full[kb], sK + kb * S::KV_BYTES, 0, h, j * 128, b);
-          tma_load_4d(&tm_v, &kv_full[kb], sV + kb * S::KV_BYTES, 0, h, j * 128, b);
-        }
-      }
-    }
-  } else if (warp_idx == 1) {
-    // ===================================================== MMA issuer (whole warp runs the loop, one elected lane issues)
-    const bool leader = elect_one();
-    const uint32_t id_s = make_idesc_bf16(128, Nq, false, false);     // S^T, dP^T : K-major x K-major
-    const uint32_t id_dv = make_idesc_bf16(128, 64, false, true);      // dV, dK   : K-major A, MN-major B
-    const uint32_t id_dq = make_idesc_bf16(128, 64, true, true);       // dQ       : MN-major A and B
-    const uint32_t aPT = smem_u32(sPT);
-    const int nq16 = Nq / 16;
-    auto wait_operands = [&](int t) {
-      const uint32_t it = (uint32_t)(t / ntiles);
-      mbar_wait(&kv_full[t & 1], ((uint32_t)t >> 1) & 1u);
-      mbar_wait(&qdo_full[it & 1u], (it >> 1) & 1u);
-      tc_fence_after();
-    };
-    auto issue_s = [&](int t) {        // S^T(t) = K_t Q^T
-      wait_operands(t);
-      if (leader) {
-        const uint32_t aK = smem_u32(sK + (t & 1) * S::KV_BYTES), aQ = smem_u32(sQ + ((t / ntiles) & 1) * S::Q_BYTES);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + ATC_S_COL, make_smem_desc(aK + k * 32, 16, 1024), make_smem_desc(aQ + k * 32, 16, 1024), id_s, k > 0);
-        umma_commit(s_full);
-      }
-      __syncwarp();
-    };
-    auto issue_dp = [&](int t) {       // dP^T(t) = V_t dO^T
-      wait_operands(t);
-      if (leader) {
-        const uint32_t aV = smem_u32(sV + (t & 1) * S::KV_BYTES), aDO = smem_u32(sDO + ((t / ntiles) & 1) * S::Q_BYTES);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + PIPE_DP_COL, make_smem_desc(aV + k * 32, 16, 1024), make_smem_desc(aDO + k * 32, 16, 1024), id_s, k > 0);
-        umma_commit(dp_full);
-      }
-      __syncwarp();
-    };
-    if (ntot > 0) {
-      issue_s(0);
-      issue_dp(0);
-    }
-    for (int t = 0; t < ntot; ++t) {
-      const int it = t / ntiles, j = t - it * ntiles;
-      const uint32_t tph = (uint32_t)t & 1u;
-      const uint32_t aK = smem_u32(sK + (t & 1) * S::KV_BYTES);
-      const uint32_t aQ = smem_u32(sQ + (it & 1) * S::Q_BYTES), aDO = smem_u32(sDO + (it & 1) * S::Q_BYTES);
-      mbar_wait(p_ready, tph);
-      mbar_wait(out_free, tph ^ 1u);   // dV / dK / dQ accumulators of the previous tile have been drained
-      tc_fence_after();
-      if (leader) {                    // dV_t = P^T dO
-        for (int k = 0; k < nq16; ++k)
-          umma_bf16(tmem_base + ATC_DV_COL, make_smem_desc(aPT + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                    make_smem_desc(aDO + k * 2048, 16384, 1024), id_dv, k > 0);
-        umma_commit(dv_done);
-      }
-      __syncwarp();
-      if (t + 1 < ntot) issue_s(t + 1);          // the S columns were drained by pass A of tile t
-      mbar_wait(ds_ready, tph);
-      tc_fence_after();
-      if (leader) {
-        for (int k = 0; k < nq16; ++k)            // dK_t = dS^T Q
-          umma_bf16(tmem_base + ATC_DK_COL, make_smem_desc(aPT + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                    make_smem_desc(aQ + k * 2048, 16384, 1024), id_dv, k > 0);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)               // dQ += dS K_t (one 128-query block: Nq <= 128)
-          umma_bf16(tmem_base + ATC_DQ_COL, make_smem_desc(aPT + k * 2048, 16384, 1024), make_smem_desc(aK + k * 2048, 16384, 1024),
-                    id_dq, (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(out_full);
-        umma_commit(&kv_empty[t & 1]);
-        if (j == ntiles - 1) umma_commit(&qdo_empty[it & 1]);
-      }
-      __syncwarp();
-      if (t + 1 < ntot) issue_dp(t + 1);         // the dP columns were drained by pass B of tile t
-    }
-  } else {
-    // ===================================================== compute warps (256 threads)
-    const int quad = warp_idx & 3;             // TMEM lane quadrant
-    const int half = (warp_idx - 2) >> 2;      // which half of the query columns / output columns
-    const int r = quad * 32 + lane;            // key row inside the tile
-    const int ct = threadIdx.x - 64;           // 0..255
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const float sl2 = p.scale * 1.4426950408889634f;
-    const unsigned long long off_eff = p.offset + ((DROPOUT && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
-    const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
-    const float inv_keep = DROPOUT ? 1.f / (1.f - p.p_drop) : 1.f;
-    const int half_cols = Nq >> 1;             // multiple of 16
-    const uint32_t pt_row = (uint32_t)(r * 128);   // row offset inside a 64-column atom of the P^T / dS^T tile
-    const uint32_t aPTs = smem_u32(sPT), aP2s = smem_u32(sP2), aLse0 = smem_u32(sLse), aDelta0 = smem_u32(sDelta);   // shared-space addresses
-    const int r7 = r & 7;
-    uint32_t tile_cnt = 0, item_cnt = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++item_cnt) {
-      const int b = item / p.H, h = item % p.H;
-      const uint32_t dkey = attn_drop_key(p.seed, off_eff, item);
-      // ---- per-item staging: lse (log2 units, +inf beyond Tq) and delta = rowsum(dO * O), buffer = item parity (the barrier
-      // of item n+1 orders the reuse of buffer n&1 by item n+2)
-      const uint32_t lb = (item_cnt & 1u) * 128u;
-      const uint32_t aLse = aLse0 + lb * 4u, aDelta = aDelta0 + lb * 4u;
-      if (ct < Nq) {
-        float l2 = INFINITY, dl = 0.f;
-        if (ct < p.Tq) {
-          l2 = p.lse[(long long)item * p.Tq + ct] * 1.4426950408889634f;
-          dl = p.delta[(long long)item * p.Tq + ct];
-        }
-        sLse[lb + ct] = l2;
-        sDelta[lb + ct] = dl;
-      }
-      named_bar_sync(1, 256);
-      for (int j = 0; j < ntiles; ++j, ++tile_cnt) {
-        const uint32_t tph = tile_cnt & 1u;
-        const int kk = j * 128 + r;
-        const bool kvalid = (kk < p.Sk) && (!p.kmask || p.kmask[(long long)b * p.Sk + kk]);
-        // ---------------- pass A: P^T
-        mbar_wait(s_full, tph);
-        tc_fence_after();
-        // causal: query q sees key kk iff kk <= q.  For this warp's key rows [k_lo, k_lo + 31] a 16-query chunk starting at
-        // q0 is fully visible iff q0 >= k_lo + 31 and fully masked iff q0 + 15 < k_lo; only the chunks on the diagonal test
-        // per element.  Key rows that are padding / masked (kvalid == false) produce zeros without any math.
-        const int k_lo = j * 128 + quad * 32;
-        auto pass_a_chunk = [&](const uint32_t* v, int q0) {
-          float pv[16], pd[16];
-          if (kvalid && !(p.causal && q0 + 15 < k_lo)) {
-            float ls[16];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 t = lds128f(aLse + (uint32_t)((q0 + 4 * i) * 4));
-              ls[4 * i] = t.x; ls[4 * i + 1] = t.y; ls[4 * i + 2] = t.z; ls[4 * i + 3] = t.w;
-            }
-            if (!p.causal || q0 >= k_lo + 31) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -ls[i]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) pv[i] = (kk <= q0 + i) ? ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -ls[i])) : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pv[i] = 0.f;
-          }
-          if (DROPOUT) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pd[i] = attn_drop_rand(dkey, q0 + i, kk, p.Sk) >= thr ? pv[i] * inv_keep : 0.f;
-          }
-          const uint32_t off0 = (uint32_t)((q0 >> 6) * 16384) + pt_row;
-          const int u0 = (q0 & 63) >> 3;
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const uint32_t off = off0 + (uint32_t)(((u0 + u) ^ r7) << 4);
-            uint4 w;
+          for (int e = 0; e < 4; ++e) {
+            const float2 pp = unpack_bf16x2(pw4[e]), kp = unpack_bf16x2(kw4[e]);
+            float d0 = __uint_as_float(v[2 * e]), d1 = __uint_as_float(v[2 * e + 1]);
             if (DROPOUT) {
-              w.x = pack_bf16x2(pd[8 * u + 0], pd[8 * u + 1]); w.y = pack_bf16x2(pd[8 * u + 2], pd[8 * u + 3]);
-              w.z = pack_bf16x2(pd[8 * u + 4], pd[8 * u + 5]); w.w = pack_bf16x2(pd[8 * u + 6], pd[8 * u + 7]);
-              sts128(aPTs + off, w.x, w.y, w.z, w.w);
+              d0 = kp.x != 0.f ? d0 * inv_keep : 0.f;
+              d1 = kp.y != 0.f ? d1 * inv_keep : 0.f;
             }
-            w.x = pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]); w.y = pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]);
-            w.z = pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]); w.w = pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]);
-            sts128((DROPOUT ? aP2s : aPTs) + off, w.x, w.y, w.z, w.w);
+            ow[e] = pack_bf16x2(pp.x * (d0 - dl[2 * e]), pp.y * (d1 - dl[2 * e + 1]));
           }
-        };
-        {  // TMEM loads are software-pipelined: the next chunk is in flight while the current one is processed
-          const int qbase = half * half_cols;
-          uint32_t va[16], vb[16];
-          tmem_ld16(lane_taddr + ATC_S_COL + qbase, va);
-          for (int c = 0; c < half_cols; c += 32) {
-            tmem_ld_wait();
-            if (c + 16 < half_cols) tmem_ld16(lane_taddr + ATC_S_COL + qbase + c + 16, vb);
-            pass_a_chunk(va, qbase + c);
-            if (c + 16 < half_cols) {
-              tmem_ld_wait();
-              if (c + 32 < half_cols) tmem_ld16(lane_taddr + ATC_S_COL + qbase + c + 32, va);
-              pass_a_chunk(vb, qbase + c + 16);
-            }
-          }
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_ready);
-        // ---------------- pass B: dS^T (in place over P^T)
-        mbar_wait(dp_full, tph);
-        mbar_wait(dv_done, tph);
-        tc_fence_after();
-        // dS^T = P^T * (dP^T - delta) — the softmax scale is applied once per dK / dQ output element in the epilogue instead
-        // of once per score element here.
-        auto pass_b_chunk = [&](const uint32_t* v, int q0) {
-          float dl[16];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 t = lds128f(aDelta + (uint32_t)((q0 + 4 * i) * 4));
-            dl[4 * i] = t.x; dl[4 * i + 1] = t.y; dl[4 * i + 2] = t.z; dl[4 * i + 3] = t.w;
-          }
-          const uint32_t off0 = (uint32_t)((q0 >> 6) * 16384) + pt_row;
-          const int u0 = (q0 & 63) >> 3;
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const uint32_t off = off0 + (uint32_t)(((u0 + u) ^ r7) << 4);
-            const uint4 pw = lds128u((DROPOUT ? aP2s : aPTs) + off);
-            uint4 kw = pw;
-            if (DROPOUT) kw = lds128u(aPTs + off);   // dropped P: zero <=> dropped (or P == 0)
-            const uint32_t pw4[4] = {pw.x, pw.y, pw.z, pw.w}, kw4[4] = {kw.x, kw.y, kw.z, kw.w};
-            uint32_t ow[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 pp = unpack_bf16x2(pw4[e]), kp = unpack_bf16x2(kw4[e]);
-              float d0 = __uint_as_float(v[8 * u + 2 * e]), d1 = __uint_as_float(v[8 * u + 2 * e + 1]);
-              if (DROPOUT) {
-                d0 = kp.x != 0.f ? d0 * inv_keep : 0.f;
-                d1 = kp.y != 0.f ? d1 * inv_keep : 0.f;
-              }
-              ow[e] = pack_bf16x2(pp.x * (d0 - dl[8 * u + 2 * e]), pp.y * (d1 - dl[8 * u + 2 * e + 1]));
-            }
-            sts128(aPTs + off, ow[0], ow[1], ow[2], ow[3]);
-          }
+          sts128(aPTs + off, ow[0], ow[1], ow[2], ow[3]);
         };
         {
-          const int qbase = half * half_cols;
-          uint32_t va[16], vb[16];
-          tmem_ld16(lane_taddr + PIPE_DP_COL + qbase, va);
-          for (int c = 0; c < half_cols; c += 32) {
+          const int qbase = part * part_cols;
+          uint32_t va[8], vb[8];
+          tmem_ld8(lane_taddr + ATC_S_COL + qbase, va);
+          for (int c = 0; c < part_cols; c += 16) {
             tmem_ld_wait();
-            if (c + 16 < half_cols) tmem_ld16(lane_taddr + PIPE_DP_COL + qbase + c + 16, vb);
+            if (c + 8 < part_cols) tmem_ld8(lane_taddr + ATC_S_COL + qbase + c + 8, vb);
             pass_b_chunk(va, qbase + c);
-            if (c + 16 < half_cols) {
+            if (c + 8 < part_cols) {
               tmem_ld_wait();
-              if (c + 32 < half_cols) tmem_ld16(lane_taddr + PIPE_DP_COL + qbase + c + 32, va);
-              pass_b_chunk(vb, qbase + c + 16);
+              if (c + 16 < part_cols) tmem_ld8(lane_taddr + ATC_S_COL + qbase + c + 16, va);
+              pass_b_chunk(vb, qbase + c + 8);
             }
           }
         }
@@ -790,45 +374,31 @@ attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         mbar_wait(out_full, tph);
         tc_fence_after();
         {
-          uint32_t acc[32];
-          tmem_ld32(lane_taddr + ATC_DV_COL + half * 32, acc);
-          tmem_ld_wait();
-          if (kk < p.Sk) {
-            uint4* dst = reinterpret_cast<uint4*>(p.dv + (long long)b * p.dv_bs + (long long)kk * p.dv_rs + h * 64 + half * 32);
+          constexpr int OC = 64 / ATC_SPLIT;     // output columns per part (16)
+          uint32_t acc[OC];
+          auto store16 = [&](bf16* base, float sc) {
+            uint4* dst = reinterpret_cast<uint4*>(base);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]), __uint_as_float(acc[8 * i + 1])),
-                                  pack_bf16x2(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3])),
-                                  pack_bf16x2(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])),
-                                  pack_bf16x2(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7])));
-          }
-          const float sc = p.scale;          // dS was left unscaled (pass B)
-          tmem_ld32(lane_taddr + ATC_DK_COL + half * 32, acc);
-          tmem_ld_wait();
-          if (kk < p.Sk) {
-            uint4* dst = reinterpret_cast<uint4*>(p.dk + (long long)b * p.dk_bs + (long long)kk * p.dk_rs + h * 64 + half * 32);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < OC / 8; ++i)
               dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]) * sc, __uint_as_float(acc[8 * i + 1]) * sc),
                                   pack_bf16x2(__uint_as_float(acc[8 * i + 2]) * sc, __uint_as_float(acc[8 * i + 3]) * sc),
                                   pack_bf16x2(__uint_as_float(acc[8 * i + 4]) * sc, __uint_as_float(acc[8 * i + 5]) * sc),
                                   pack_bf16x2(__uint_as_float(acc[8 * i + 6]) * sc, __uint_as_float(acc[8 * i + 7]) * sc));
-          }
+          };
+          tmem_ld16(lane_taddr + ATC_DV_COL + part * OC, acc);
+          tmem_ld_wait();
+          if (kk < p.Sk) store16(p.dv + (long long)b * p.dv_bs + (long long)kk * p.dv_rs + h * 64 + part * OC, 1.f);
+          const float sc = p.scale;          // dS was left unscaled (pass B)
+          tmem_ld16(lane_taddr + ATC_DK_COL + part * OC, acc);
+          tmem_ld_wait();
+          if (kk < p.Sk) store16(p.dk + (long long)b * p.dk_bs + (long long)kk * p.dk_rs + h * 64 + part * OC, sc);
           if (j == ntiles - 1) {
             const int q_blocks = (Nq + 127) / 128;
             for (int mb = 0; mb < q_blocks; ++mb) {
-              tmem_ld32(lane_taddr + ATC_DQ_COL + mb * 64 + half * 32, acc);
+              tmem_ld16(lane_taddr + ATC_DQ_COL + mb * 64 + part * OC, acc);
               tmem_ld_wait();
               const int q = mb * 128 + r;
-              if (q < p.Tq) {
-                uint4* dst = reinterpret_cast<uint4*>(p.dq + (long long)b * p.dq_bs + (long long)q * p.dq_rs + h * 64 + half * 32);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  dst[i] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * i]) * sc, __uint_as_float(acc[8 * i + 1]) * sc),
-                                      pack_bf16x2(__uint_as_float(acc[8 * i + 2]) * sc, __uint_as_float(acc[8 * i + 3]) * sc),
-                                      pack_bf16x2(__uint_as_float(acc[8 * i + 4]) * sc, __uint_as_float(acc[8 * i + 5]) * sc),
-                                      pack_bf16x2(__uint_as_float(acc[8 * i + 6]) * sc, __uint_as_float(acc[8 * i + 7]) * sc));
-              }
+              if (q < p.Tq) store16(p.dq + (long long)b * p.dq_bs + (long long)q * p.dq_rs + h * 64 + part * OC, sc);
             }
           }
         }
@@ -893,25 +463,6 @@ static int launch_attn_bwd_tc(const CUtensorMap& tq, const CUtensorMap& tk, cons
   return check_launch("attn_bwd_tc");
 }
 
-template <bool DROPOUT>
-static int launch_attn_bwd_tc_pipe(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
-                                   const AttnTcParams& p, cudaStream_t stream) {
-  using S = AtcPipeSmem<DROPOUT>;
-  auto kern = attn_bwd_tc_pipe_kernel<DROPOUT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-    if (err != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(attn_bwd_tc_pipe smem=%d): %s", S::TOTAL, cudaGetErrorString(err));
-      return -1;
-    }
-    attr_set = true;
-  }
-  const int items = p.B * p.H;
-  const int grid = items < num_sms() ? items : num_sms();
-  kern<<<grid, ATC_THREADS, S::TOTAL, stream>>>(tq, tk, tv, tdo, p);
-  return check_launch("attn_bwd_tc_pipe");
-}
 
 
 // returns 1 if the shape is handled by the tcgen05 kernel (and it was launched), 0 if not supported, <0 on error
@@ -953,12 +504,7 @@ int attention_bwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
   p.lse = lse; p.kmask = kmask; p.B = B; p.H = H; p.Tq = Tq; p.Sk = Sk; p.Nq = Nq; p.causal = causal;
   p.scale = scale; p.p_drop = p_drop; p.seed = seed; p.offset = offset; p.offset_ptr = rng_offset_ptr;
   int rc;
-  static const bool pipe = [] {          // EXPERIMENTAL opt-in, see attn_bwd_tc_pipe_kernel
-    const char* v = getenv("VLM_ATTN_BWD_PIPE");
-    return v && v[0] == '1';
-  }();
-  if (pipe && Nq <= 128) rc = p_drop > 0.f ? launch_attn_bwd_tc_pipe<true>(tq, tk, tv, tdo, p, stream) : launch_attn_bwd_tc_pipe<false>(tq, tk, tv, tdo, p, stream);
-  else if (p_drop > 0.f) rc = launch_attn_bwd_tc<2, true>(tq, tk, tv, tdo, p, stream);
+  if (p_drop > 0.f) rc = launch_attn_bwd_tc<2, true>(tq, tk, tv, tdo, p, stream);
   else if (Nq <= 128) rc = launch_attn_bwd_tc<2, false>(tq, tk, tv, tdo, p, stream);
   else rc = launch_attn_bwd_tc<4, false>(tq, tk, tv, tdo, p, stream);
   return rc ? rc : 1;
@@ -983,6 +529,13 @@ struct AttnTcFwdParams {
   const unsigned long long* offset_ptr;
 };
 
+// Softmax warps: ATF_SPLIT per TMEM lane quadrant (thread <-> query row, the warps of a quadrant split the key columns).  Round 1 ran 2 per
+// quadrant: one warp then owned up to 112 score columns of its rows and its dependent instruction stream (TMEM load -> FFMA -> EX2 ->
+// dropout hash -> pack -> STS, ~10 cycles per issued instruction with 2 warps per scheduler: profiles/ncu_r1c_attention_fwd.txt) WAS the
+// tile time.  4 per quadrant halve the stream of every warp and double the warps each scheduler can interleave.
+static constexpr int ATF_SPLIT = 4;
+static constexpr int ATF_THREADS = 64 + 128 * ATF_SPLIT;     // 2 control warps + 16 softmax warps
+
 // Shared memory (dynamic, sized by Nk = keys rounded up to 32): two Q tiles, two K and two V buffers (item parity), one P tile.
 struct AtcFwdSmem {
   static constexpr int Q_BYTES = 128 * 128;      // one 128-query tile
@@ -992,8 +545,8 @@ struct AtcFwdSmem {
   __host__ __device__ static int off_k(int) { return 2 * Q_BYTES; }
   __host__ __device__ static int off_v(int Nk) { return off_k(Nk) + 2 * kv_bytes(Nk); }
   __host__ __device__ static int off_p(int Nk) { return off_v(Nk) + 2 * kv_bytes(Nk); }
-  __host__ __device__ static int off_red(int Nk) { return off_p(Nk) + p_bytes(Nk); }   // float [2][2][128]
-  __host__ __device__ static int off_kok(int Nk) { return off_red(Nk) + 2 * 2 * 128 * 4; }   // uint8 [256]
+  __host__ __device__ static int off_red(int Nk) { return off_p(Nk) + p_bytes(Nk); }   // float [2][ATF_SPLIT][128]
+  __host__ __device__ static int off_kok(int Nk) { return off_red(Nk) + 2 * ATF_SPLIT * 128 * 4; }   // uint8 [256]
   __host__ __device__ static int off_bal(int Nk) { return off_kok(Nk) + 256; }             // uint32 [8]
   __host__ __device__ static int off_bar(int Nk) { return off_bal(Nk) + 32; }
   __host__ __device__ static int total(int Nk) { return off_bar(Nk) + NUM_BARS * 8 + 16 + 1024; }
@@ -1004,10 +557,11 @@ struct AtcFwdSmem {
 //   MMA warp   : S(0), S(1); then for every t: wait P(t) -> O = P V (TMEM cols [2 Nk, 2 Nk + 64)) -> S(t+2) into the S buffer
 //                t&1 that the softmax of tile t has just drained.  So S(t+1) is always complete when the softmax warps get to it.
 //   softmax    : pass 1 (row max) of tile t, then the EPILOGUE OF TILE t-1 (its P V ran under pass 1), then pass 2 (P -> smem).
-__global__ void __launch_bounds__(ATC_THREADS, 1)
+__global__ void __launch_bounds__(ATF_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, AttnTcFwdParams p) {
   using S = AtcFwdSmem;
+  constexpr int NCT = 128 * ATF_SPLIT;            // softmax threads
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int Nk = p.Nk;
@@ -1050,9 +604,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
     }
-    mbar_init(p_ready, 8);
+    mbar_init(p_ready, 4 * ATF_SPLIT);
     mbar_init(o_full, 1);
-    mbar_init(o_free, 8);
+    mbar_init(o_free, 4 * ATF_SPLIT);
     fence_barrier_init();
   } else if (warp_idx == 1) {
     tmem_alloc<512>(tmem_ptr_smem);
@@ -1125,7 +679,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   } else {
     const int quad = warp_idx & 3;
-    const int half = (warp_idx - 2) >> 2;
+    const int part = (warp_idx - 2) >> 2;        // which slice of the key columns this warp handles
     const int r = quad * 32 + lane;              // query row inside the tile
     const int ct = threadIdx.x - 64;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -1133,13 +687,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const unsigned long long off_eff = p.offset + ((p.p_drop > 0.f && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
     const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
-    const int half_cols = Nk >> 1;               // multiple of 16
-    const int c0 = half * half_cols;             // first key column of this thread's half
-    const int nchunks = half_cols >> 4;
+    const int part_cols = Nk / ATF_SPLIT;        // multiple of 8 (Nk is a multiple of 32)
+    const int c0 = part * part_cols;             // first key column of this thread's slice
+    const int nchunks = part_cols >> 3;          // 8-column chunks (one 16-byte unit of the P tile each)
     const uint32_t p_row = smem_u32(sP) + (uint32_t)(r * 128);  // shared-space address of this row inside atom 0 of the P tile
     const int r7 = r & 7;
-    float* redmax = sRed;                        // [2][128]
-    float* redsum = sRed + 256;                  // [2][128]
+    float* redmax = sRed;                        // [ATF_SPLIT][128]
+    float* redsum = sRed + ATF_SPLIT * 128;      // [ATF_SPLIT][128]
     // deferred epilogue state (tile t-1)
     float l_prev = 0.f, mref_prev = 0.f;
     long long o_off_prev = 0, lse_off_prev = 0;
@@ -1147,8 +701,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     auto epilogue_prev = [&](int tprev) {
       mbar_wait(o_full, tprev & 1u);
       tc_fence_after();
-      uint32_t acc[32];
-      tmem_ld32(lane_taddr + (uint32_t)O_COL + half * 32, acc);
+      uint32_t acc[16];
+      tmem_ld16(lane_taddr + (uint32_t)O_COL + part * 16, acc);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -1156,31 +710,31 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (row_prev) {
         const float l = l_prev;
         const float inv = l > 0.f ? 1.f / l : 0.f;
-        uint4* dst = reinterpret_cast<uint4*>(p.o + o_off_prev + half * 32);
+        uint4* dst = reinterpret_cast<uint4*>(p.o + o_off_prev + part * 16);
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
+        for (int e = 0; e < 2; ++e)
           dst[e] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * e]) * inv, __uint_as_float(acc[8 * e + 1]) * inv),
                               pack_bf16x2(__uint_as_float(acc[8 * e + 2]) * inv, __uint_as_float(acc[8 * e + 3]) * inv),
                               pack_bf16x2(__uint_as_float(acc[8 * e + 4]) * inv, __uint_as_float(acc[8 * e + 5]) * inv),
                               pack_bf16x2(__uint_as_float(acc[8 * e + 6]) * inv, __uint_as_float(acc[8 * e + 7]) * inv));
-        if (half == 0 && p.lse) p.lse[lse_off_prev] = l > 0.f ? (mref_prev + log2f(l)) * 0.6931471805599453f : -INFINITY;
+        if (part == 0 && p.lse) p.lse[lse_off_prev] = l > 0.f ? (mref_prev + log2f(l)) * 0.6931471805599453f : -INFINITY;
       }
     };
     int t = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int b = item / p.H, h = item % p.H;
       const uint32_t dkey = attn_drop_key(p.seed, off_eff, item);
-      // ---- per-item key validity.  The usual masks (no mask, right padding) make the valid keys a PREFIX [0, nvalid): then a
-      // 16-key chunk is either fully valid for the whole warp (no per-element predicate at all), fully masked (skipped) or
+      // ---- per-item key validity.  The usual masks (no mask, right padding) make the valid keys a PREFIX [0, nvalid): then an
+      // 8-key chunk is either fully valid for the whole warp (no per-element predicate at all), fully masked (skipped) or
       // one of the few mixed ones (causal diagonal / last partial chunk).  Arbitrary masks keep the per-element test.
-      named_bar_sync(1, 256);
-      {
+      named_bar_sync(1, NCT);
+      if (ct < 256) {                            // warps 2..9: one key per thread (Nk <= 224)
         const bool ok = (ct < p.Sk) && (!p.kmask || p.kmask[(long long)b * p.Sk + ct]);
         sKok[ct] = ok;
         const uint32_t bal = __ballot_sync(0xffffffffu, ok);
         if (lane == 0) sBal[ct >> 5] = bal;
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(1, NCT);
       int nvalid = 0;
 #pragma unroll
       for (int w = 0; w < 8; ++w) nvalid += __popc(sBal[w]);
@@ -1207,40 +761,41 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         auto visible = [&](int kk) -> bool {
           return prefix ? (kk < kmax_row) : (sKok[kk] && (!p.causal || kk <= qq));
         };
-        int nact = (kany - c0 + 15) >> 4;        // chunks of this half that hold at least one visible key (warp-uniform)
+        int nact = (kany - c0 + 7) >> 3;         // chunks of this slice that hold at least one visible key (warp-uniform)
         nact = nact < 0 ? 0 : (nact > nchunks ? nchunks : nact);
         mbar_wait(&s_full[sb], (t >> 1) & 1u);
         tc_fence_after();
-        // ---- pass 1: row max (raw scores) over this thread's half of the key columns; TMEM loads are software-pipelined
+        // ---- pass 1: row max (raw scores) over this thread's slice of the key columns; TMEM loads are software-pipelined
         float mx = -INFINITY;
         {
-          uint32_t va[16], vb[16];
+          uint32_t va[8], vb[8];
           auto chunk_max = [&](const uint32_t* v, int c) {
-            const int k0 = c0 + c * 16;
-            if (k0 + 16 <= kfull) {
+            const int k0 = c0 + c * 8;
+            if (k0 + 8 <= kfull) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+              for (int e = 0; e < 8; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
             } else {
 #pragma unroll
-              for (int e = 0; e < 16; ++e)
+              for (int e = 0; e < 8; ++e)
                 if (visible(k0 + e)) mx = fmaxf(mx, __uint_as_float(v[e]));
             }
           };
-          if (nact > 0) tmem_ld16(s_taddr, va);
+          if (nact > 0) tmem_ld8(s_taddr, va);
           for (int c = 0; c < nact; c += 2) {
             tmem_ld_wait();
-            if (c + 1 < nact) tmem_ld16(s_taddr + (c + 1) * 16, vb);
+            if (c + 1 < nact) tmem_ld8(s_taddr + (c + 1) * 8, vb);
             chunk_max(va, c);
             if (c + 1 < nact) {
               tmem_ld_wait();
-              if (c + 2 < nact) tmem_ld16(s_taddr + (c + 2) * 16, va);
+              if (c + 2 < nact) tmem_ld8(s_taddr + (c + 2) * 8, va);
               chunk_max(vb, c + 1);
             }
           }
         }
-        redmax[half * 128 + r] = mx;
-        named_bar_sync(2, 256);
-        mx = fmaxf(redmax[r], redmax[128 + r]);
+        redmax[part * 128 + r] = mx;
+        named_bar_sync(2, NCT);
+#pragma unroll
+        for (int s2 = 0; s2 < ATF_SPLIT; ++s2) mx = fmaxf(mx, redmax[s2 * 128 + r]);
         const float mref = (mx == -INFINITY) ? 0.f : mx * sl2;
         // ---- deferred epilogue of the previous tile: its P V product ran while pass 1 was executing.  Waiting for it also
         // guarantees that the tensor core has finished reading the (single) P tile before pass 2 overwrites it.
@@ -1248,61 +803,58 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         // ---- pass 2: P = exp2(s * scale * log2e - m), row sum, dropout, bf16 -> swizzled smem
         float sum = 0.f;
         {
-          uint32_t va[16], vb[16];
+          uint32_t va[8], vb[8];
           auto chunk_exp = [&](const uint32_t* v, int c) {
-            const int k0 = c0 + c * 16;
-            float pe[16];
-            if (k0 + 16 <= kfull) {
+            const int k0 = c0 + c * 8;
+            float pe[8];
+            if (k0 + 8 <= kfull) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) pe[e] = ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -mref));
+              for (int e = 0; e < 8; ++e) pe[e] = ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -mref));
             } else {
 #pragma unroll
-              for (int e = 0; e < 16; ++e)
+              for (int e = 0; e < 8; ++e)
                 pe[e] = visible(k0 + e) ? ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -mref)) : 0.f;
             }
 #pragma unroll
-            for (int e = 0; e < 16; ++e) sum += pe[e];
+            for (int e = 0; e < 8; ++e) sum += pe[e];
             if (p.p_drop > 0.f) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) pe[e] = attn_drop_rand(dkey, qq, k0 + e, p.Sk) >= thr ? pe[e] * inv_keep : 0.f;
+              for (int e = 0; e < 8; ++e) pe[e] = attn_drop_rand(dkey, qq, k0 + e, p.Sk) >= thr ? pe[e] * inv_keep : 0.f;
             }
             const uint32_t atom = (uint32_t)((k0 >> 6) * 16384) + p_row;
             const int u0 = (k0 & 63) >> 3;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              uint4 w;
-              w.x = pack_bf16x2(pe[8 * u + 0], pe[8 * u + 1]); w.y = pack_bf16x2(pe[8 * u + 2], pe[8 * u + 3]);
-              w.z = pack_bf16x2(pe[8 * u + 4], pe[8 * u + 5]); w.w = pack_bf16x2(pe[8 * u + 6], pe[8 * u + 7]);
-              sts128(atom + (uint32_t)(((u0 + u) ^ r7) << 4), w.x, w.y, w.z, w.w);
-            }
+            sts128(atom + (uint32_t)((u0 ^ r7) << 4), pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]),
+                   pack_bf16x2(pe[6], pe[7]));
           };
-          if (nact > 0) tmem_ld16(s_taddr, va);
+          if (nact > 0) tmem_ld8(s_taddr, va);
           for (int c = 0; c < nact; c += 2) {
             tmem_ld_wait();
-            if (c + 1 < nact) tmem_ld16(s_taddr + (c + 1) * 16, vb);
+            if (c + 1 < nact) tmem_ld8(s_taddr + (c + 1) * 8, vb);
             chunk_exp(va, c);
             if (c + 1 < nact) {
               tmem_ld_wait();
-              if (c + 2 < nact) tmem_ld16(s_taddr + (c + 2) * 16, va);
+              if (c + 2 < nact) tmem_ld8(s_taddr + (c + 2) * 8, va);
               chunk_exp(vb, c + 1);
             }
           }
           // chunks without any visible key: P = 0 (the P V product runs over all Nk columns)
           for (int c = nact; c < nchunks; ++c) {
-            const int k0 = c0 + c * 16;
+            const int k0 = c0 + c * 8;
             const uint32_t atom = (uint32_t)((k0 >> 6) * 16384) + p_row;
             const int u0 = (k0 & 63) >> 3;
             sts128(atom + (uint32_t)((u0 ^ r7) << 4), 0u, 0u, 0u, 0u);
-            sts128(atom + (uint32_t)(((u0 + 1) ^ r7) << 4), 0u, 0u, 0u, 0u);
           }
         }
-        redsum[half * 128 + r] = sum;
+        redsum[part * 128 + r] = sum;
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);
-        named_bar_sync(2, 256);
-        l_prev = redsum[r] + redsum[128 + r];
+        named_bar_sync(2, NCT);
+        float l = 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < ATF_SPLIT; ++s2) l += redsum[s2 * 128 + r];
+        l_prev = l;
         mref_prev = mref;
         row_prev = qq < p.Tq;
         o_off_prev = (long long)b * p.o_bs + (long long)qq * p.o_rs + h * 64;
@@ -1352,7 +904,7 @@ int attention_fwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
   }
   const int items = B * H;
   const int grid = items < num_sms() ? items : num_sms();
-  attn_fwd_tc_kernel<<<grid, ATC_THREADS, AtcFwdSmem::total(Nk), stream>>>(tq, tk, tv, p);
+  attn_fwd_tc_kernel<<<grid, ATF_THREADS, AtcFwdSmem::total(Nk), stream>>>(tq, tk, tv, p);
   const int rc = check_launch("attn_fwd_tc");
   return rc ? rc : 1;
 }

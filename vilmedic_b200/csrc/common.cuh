@@ -180,6 +180,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- UMMA descriptors (bit layout: cute/arch/mma_sm100_desc.hpp of CUTLASS; restated, not copied) ----
@@ -320,11 +326,14 @@ __device__ __forceinline__ uint32_t attn_drop_key(unsigned long long seed, unsig
   z ^= z >> 31;
   return (uint32_t)z ^ (uint32_t)(z >> 32);
 }
+// Round 2: one multiply round instead of two (the softmax warps of the decoder attention kernels were integer-issue bound on this
+// hash: LOP3 / ISETP / IMAD / SHF were 50 % of their instructions, profiles/ncu_r1c_attention_fwd.txt).  The word is only compared with
+// a threshold, i.e. its high bits matter; Weyl-sequence input + xorshift-multiply keeps those equidistributed (tests/test_ops_gpu.py
+// checks the drop rate, the independence across rows / keys / heads and the fwd = bwd mask identity).
 __device__ __forceinline__ uint32_t attn_drop_rand(uint32_t key, int q, int k, int Sk) {
   uint32_t x = ((uint32_t)q * (uint32_t)Sk + (uint32_t)k) * 0x9E3779B1u ^ key;
-  x ^= x >> 16; x *= 0x7FEB352Du;
-  x ^= x >> 15; x *= 0x846CA68Bu;
-  x ^= x >> 16;
+  x ^= x >> 15; x *= 0x2C1B3C6Du;
+  x ^= x >> 12;
   return x;
 }
 
