@@ -320,8 +320,13 @@ def run_ours(args):
     from vilmedic_b200.ddp import GradSync
     sync = GradSync(arena).attach()       # per-layer gradient buckets, launched from the backward pass (ddp.py)
 
+    # DIAGNOSTIC ONLY (tools/jobs): VLM_BENCH_NO_EXCHANGE=1 times the N-rank step WITHOUT the gradient all-reduce, to split the
+    # multi-GPU loss into "exchange" and "everything else"; the printed line is marked invalid.
+    no_exchange = os.environ.get("VLM_BENCH_NO_EXCHANGE") == "1"
+
     def train_step(batch, read_loss, exchange=True):
         """exchange=False: rank-local step without the gradient all-reduce (instrumented passes that only one rank runs)."""
+        exchange = exchange and not no_exchange
         # world > 1: every layer's backward announces its gradient span (nn.notify_grad_ready -> GradSync.on_ready) and the
         # all-reduce of that bucket runs on NCCL's stream / NVLink under the backward of the layers below it
         from vilmedic_b200 import nn as vnn
@@ -513,6 +518,8 @@ def run_ours(args):
             "gpu_baseline": gpu_base,
             "mfu_vs_sustained_peak": value / world * FLOP_PER_PAIR_TRAIN / (peaks()["bf16_tflops_sustained"] * 1e12),
         }
+        if no_exchange:
+            line["invalid"] = "VLM_BENCH_NO_EXCHANGE=1: gradient all-reduce skipped (diagnostic run, not a bench value)"
         print(json.dumps(line))
     if world > 1:
         # destroy_process_group() blocks forever here (both ranks, observed on 2 x B200 with torch 2.11 / NCCL 2.28): the

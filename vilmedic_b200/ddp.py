@@ -8,6 +8,8 @@ The 1/world factor is folded into the fused optimizer step (grad_scale).  No act
 contrastive negatives are rank-local as in the reference (vilmedic/executors/trainor_accelerate.py:122,132).
 Round 1 sent two unbucketed spans and launched the encoder one after the backward had ended (fully exposed: the whole 6 % loss of
 the 1 -> 8 curve, VERDICT r1 weak #8)."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -15,7 +17,9 @@ from . import nn as _nn
 
 
 class GradSync:
-    def __init__(self, arena, group=None, bucket_bytes=32 << 20):
+    def __init__(self, arena, group=None, bucket_bytes=None):
+        if bucket_bytes is None:        # VLM_DDP_BUCKET_MB: tuning knob for tools/jobs (default 32 MB)
+            bucket_bytes = int(float(os.environ.get("VLM_DDP_BUCKET_MB", "32")) * (1 << 20))
         self.arena = arena
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
