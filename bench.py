@@ -339,7 +339,10 @@ def run_ours(args):
             loss.backward()
         finally:
             vnn.GRAD_READY_HOOK[0] = hook
-        opt.step(grad_scale=sync.finish() if exchange else 1.0)
+        if exchange:
+            opt.step(grad_scale=sync.finish(), grad16=sync.grad16)
+        else:
+            opt.step(grad_scale=1.0)
         if read_loss:
             return loss.item()
         return loss
@@ -584,7 +587,7 @@ def run_other_workload(args):
     def train_step(batch):
         out = model(**batch)
         out["loss"].backward()
-        opt.step(grad_scale=sync.finish())
+        opt.step(grad_scale=sync.finish(), grad16=sync.grad16)
         return out["loss"]
 
     # eager warm-up on the side stream the graph will be captured on (autograd ties a leaf's gradient accumulation to the stream of

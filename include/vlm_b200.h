@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define VLM_B200_ABI_VERSION 2
+#define VLM_B200_ABI_VERSION 3
 
 /* ---- runtime ---------------------------------------------------------------------------------------------------- */
 const char* vlm_last_error(void);
@@ -306,6 +306,8 @@ int vlm_image_resample_u8(const uint8_t* in, uint8_t* out, const int* bounds, co
 /* ---- optimizer (vilmedic/executors/trainor.py:119-124) ------------------------------------------ */
 /* out[0] += sum(g^2)  (caller zeroes). */
 int vlm_sumsq_f32(const float* g, long long n, float* out, void* stream);
+/* same over a bf16 buffer (the all-reduced gradient payload of the data-parallel step, vilmedic_b200/ddp.py). */
+int vlm_sumsq_bf16(const void* g, long long n, float* out, void* stream);
 /* AdamW over flat fp32 buffers (torch.optim.AdamW semantics), writes the bf16 mirror of p, optional global-norm clip
  * (gnorm_sq_ptr + max_norm), grad pre-scale (1/world, 1/grad_accu, 1/loss_scale) and fused zero_grad. */
 int vlm_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1, float beta2,
@@ -317,11 +319,14 @@ int vlm_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, long lo
  * rho_t > 5) — torch/optim/{adamw,adam,radam}.py single-tensor semantics over a flat span.  Same fusions as vlm_adamw_step.
  * Device-side skip instead of the host syncs of vilmedic/executors/trainor.py:109-112: when *loss_ptr or *gnorm_sq_ptr is
  * NaN/Inf the span is left untouched (gradients still zeroed).  Call vlm_optim_step_begin ONCE per optimizer step before the
- * span launches: it advances *step_ptr (or bumps *skip_count when the step is skipped). */
+ * span launches: it advances *step_ptr (or bumps *skip_count when the step is skipped).
+ * g_bf16 (nullable): when set, the gradient VALUES are read from this bf16 buffer (the exchanged payload of the data-parallel
+ * step — the reference's DDP all-reduce, vilmedic/executors/trainor_accelerate.py:132, at half the bytes) and `g` is only zeroed. */
 int vlm_optim_step_begin(int* step_ptr, const float* gnorm_sq_ptr, const float* loss_ptr, int* skip_count, void* stream);
 int vlm_optim_step(int kind, float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, const int* step_ptr, const float* lr_scale_ptr, float grad_scale,
-                   const float* gnorm_sq_ptr, float max_norm, const float* loss_ptr, int zero_grad, void* stream);
+                   const float* gnorm_sq_ptr, float max_norm, const float* loss_ptr, int zero_grad, const void* g_bf16,
+                   void* stream);
 
 #ifdef __cplusplus
 }

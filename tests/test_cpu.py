@@ -20,7 +20,7 @@ def test_library_exports_every_header_symbol():
     lib = _lib.lib()
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.vlm_abi_version() == 2
+    assert lib.vlm_abi_version() == 3
     assert isinstance(lib.vlm_last_error(), bytes)
 
 
@@ -375,7 +375,7 @@ def test_config_errors_and_defaults():
 
 
 # ------------------------------------------------------------------------------------------------ N>1 path (gloo, 2 ranks)
-def _gloo_worker(rank, world, port, q):
+def _gloo_worker(rank, world, port, q, payload="fp32"):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -388,7 +388,7 @@ def _gloo_worker(rank, world, port, q):
     m = RRG(dec, cnn)
     a = get_arena(m)
     a.flat_grad.copy_(torch.arange(a.numel, dtype=torch.float32) * 1e-3 * (rank + 1))
-    sync = GradSync(a, bucket_bytes=1 << 16).attach()
+    sync = GradSync(a, bucket_bytes=1 << 16, payload=payload).attach()
     # announce the layers the way the hand-written backward does (nn.notify_grad_ready): LM head, decoder layers top-down, decoder
     # embeddings, ViT layers top-down, patch embedding — adjacent spans merge into buckets, finish() sends what nobody announced
     from vilmedic_b200 import nn as vnn
@@ -404,7 +404,17 @@ def _gloo_worker(rank, world, port, q):
     scale = sync.finish()             # leftovers + wait for all
     sync.detach()
     want = torch.arange(a.numel, dtype=torch.float32) * 1e-3 * sum(r + 1 for r in range(world))
-    ok = torch.allclose(a.flat_grad, want) and abs(scale - 1.0 / world) < 1e-12        # every element reduced exactly once
+    if payload == "bf16":
+        # the reduced values live in the bf16 exchange buffer (what the fused optimizer reads); the fp32 accumulation buffer keeps
+        # the rank-local gradients.  bf16(x) + bf16(2x) in bf16: at most 2 roundings of 2^-9 each.
+        local = torch.arange(a.numel, dtype=torch.float32) * 1e-3 * (rank + 1)
+        ok = sync.grad16 is not None and sync.grad16.dtype == torch.bfloat16 and torch.equal(a.flat_grad, local)
+        ok = ok and bool(((sync.grad16.float() - want).abs() <= want.abs() * 2.0 ** -7 + 1e-30).all())
+        ok = ok and abs(scale - 1.0 / world) < 1e-12 and contiguous and launched_early >= 2 and vnn.GRAD_READY_HOOK[0] is None
+        q.put((rank, bool(ok)))
+        dist.destroy_process_group()
+        return
+    ok = sync.grad16 is None and torch.allclose(a.flat_grad, want) and abs(scale - 1.0 / world) < 1e-12   # every element reduced exactly once
     ok = ok and contiguous and launched_early >= 2 and all(hi > lo for lo, hi in spans) and vnn.GRAD_READY_HOOK[0] is None
     # a second step reuses the object (state reset by finish); launch_span still works for tower-level callers
     a.flat_grad.copy_(torch.arange(a.numel, dtype=torch.float32) * 1e-3 * (rank + 1))
@@ -418,12 +428,13 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_grad_sync_two_ranks_gloo():
+@pytest.mark.parametrize("payload", ["fp32", "bf16"])
+def test_grad_sync_two_ranks_gloo(payload):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + (7 if payload == "bf16" else 0)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q, payload)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]

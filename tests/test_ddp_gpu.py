@@ -10,13 +10,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def test_two_rank_step_equals_full_batch_step():
+@pytest.mark.parametrize("payload", ["bf16", "fp32"])
+def test_two_rank_step_equals_full_batch_step(payload):
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(root, "tools", "ddp_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    env = dict(os.environ, VLM_DDP_PAYLOAD=payload)           # bf16 = default exchange payload, fp32 = the reference's DDP all-reduce
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "replicas identical=True" in r.stdout

@@ -198,3 +198,33 @@ def test_create_optimizer_errors(cuda_dev):
         create_optimizer("Adam", mine)
     with pytest.raises(NotImplementedError):
         create_optimizer("Adam", mine, lr=0.1, amsgrad=True)
+
+
+@pytest.mark.parametrize("name", ["AdamW", "RAdam"])
+def test_bf16_gradient_payload(cuda_dev, name):
+    """step(grad16=...) — the exchange payload of ddp.GradSync: the gradient values come from the bf16 buffer (fp32 buffer only
+    zeroed), the clip norm too.  Must equal torch.optim fed with exactly those bf16-rounded gradients."""
+    from vilmedic_b200.arena import get_arena
+    from vilmedic_b200.optim import create_optimizer
+    ref, mine = _pair(3)
+    opt_ref = getattr(torch.optim, name)(ref.parameters(), lr=1e-2, weight_decay=0.01)
+    opt = create_optimizer(name, mine, lr=1e-2, weight_decay=0.01, max_grad_norm=0.7)
+    a = get_arena(mine)
+    g16 = torch.zeros(a.numel, device="cuda", dtype=torch.bfloat16)
+    for it in range(8):
+        _set_grads(ref, mine, it, scale=2.0)
+        g16.copy_(a.flat_grad)                                   # what GradSync's cast kernel + all-reduce leave behind
+        a.flat_grad.mul_(3.0)                                    # must NOT be read: poison the fp32 values
+        for pr, pm in zip(ref.parameters(), mine.parameters()):
+            off = a.offsets[id(pm)]
+            pr.grad = g16[off:off + pm.numel()].float().view(pr.shape).clone()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm=0.7)
+        opt_ref.step()
+        opt.step(grad16=g16)
+    torch.cuda.synchronize()
+    for (n, pr), pm in zip(ref.named_parameters(), mine.parameters()):
+        err = (pr.detach() - pm.detach()).abs().max().item()
+        assert err < 4e-6 + 4e-6 * pr.abs().max().item(), (name, n, err)
+    assert a.flat_grad.abs().sum().item() == 0                   # fp32 accumulation buffer zeroed for the next backward
+    with pytest.raises(ValueError):
+        opt.step(grad16=g16[:-4])

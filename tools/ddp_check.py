@@ -44,7 +44,7 @@ def main():
     out = model(**shard)
     out["loss"].backward()
     early = sync.launches
-    opt.step(grad_scale=sync.finish())
+    opt.step(grad_scale=sync.finish(), grad16=sync.grad16)
     sync.detach()
     torch.cuda.synchronize()
     assert early >= 2, "no gradient bucket was launched during the backward pass"

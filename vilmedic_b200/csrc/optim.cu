@@ -9,16 +9,31 @@
 
 namespace vlm {
 
-__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+// gradient element i of a flat buffer that is fp32 (G16 = false) or the bf16 exchange payload (G16 = true, see ddp.py)
+template <bool G16>
+__device__ __forceinline__ float4 load_grad4(const void* g, long long i) {
+  if (G16) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(g) + i);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return __ldg(reinterpret_cast<const float4*>(g) + i);
+}
+
+template <bool G16>
+__global__ void sumsq_kernel(const void* __restrict__ g, long long n, float* __restrict__ out) {
   __shared__ float red[32];
   float s = 0.f;
   const long long n4 = n / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    const float4 v = load_grad4<G16>(g, i);
     s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
   if (blockIdx.x == 0)
-    for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) s += g[i] * g[i];
+    for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+      const float x = G16 ? __bfloat162float(reinterpret_cast<const bf16*>(g)[i]) : reinterpret_cast<const float*>(g)[i];
+      s += x * x;
+    }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -47,8 +62,11 @@ __device__ __forceinline__ bool optim_skip(const float* loss_ptr, const float* g
   return skip;
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+// G16: the gradient VALUES come from `g16` (bf16, the all-reduced exchange payload of the data-parallel step); the fp32
+// accumulation buffer `g` is only zeroed.
+template <int KIND, bool G16>
+__global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ p, float* __restrict__ g, const bf16* __restrict__ g16,
+                                                    float* __restrict__ m,
                                                     float* __restrict__ v, bf16* __restrict__ p_bf16, long long n, OptimScalars sc,
                                                     const int* __restrict__ step_ptr, const float* __restrict__ lr_scale_ptr,
                                                     const float* __restrict__ gnorm_sq_ptr, const float* __restrict__ loss_ptr,
@@ -87,7 +105,7 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ p, float
   }
   for (long long i = i0; i < n4; i += stride) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
-    const float4 gv = reinterpret_cast<float4*>(g)[i];
+    const float4 gv = G16 ? load_grad4<true>(g16, i) : reinterpret_cast<float4*>(g)[i];
     float4 mv = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
     float* pp = &pv.x; const float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
@@ -135,29 +153,42 @@ __global__ void step_inc_kernel(int* step, const float* gnorm_sq_ptr, const floa
 
 using namespace vlm;
 
-extern "C" int vlm_sumsq_f32(const float* g, long long n, float* out, void* stream) {
-  VLM_REQUIRE(g && out && n > 0, "vlm_sumsq_f32: bad args");
+static int sumsq_launch(const void* g, bool g16, long long n, float* out, void* stream) {
   long long blocks = (n / 4 + 255) / 256;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, n, out);
+  if (g16) sumsq_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, n, out);
+  else sumsq_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, n, out);
   return check_launch("sumsq");
 }
 
-static int optim_launch(int kind, float* p, float* g, float* m, float* v, void* p_bf16, long long n, const OptimScalars& sc,
+extern "C" int vlm_sumsq_f32(const float* g, long long n, float* out, void* stream) {
+  VLM_REQUIRE(g && out && n > 0, "vlm_sumsq_f32: bad args");
+  return sumsq_launch(g, false, n, out, stream);
+}
+
+extern "C" int vlm_sumsq_bf16(const void* g, long long n, float* out, void* stream) {
+  VLM_REQUIRE(g && out && n > 0 && ((uintptr_t)g % 8 == 0), "vlm_sumsq_bf16: bad args (8-byte aligned bf16 buffer)");
+  return sumsq_launch(g, true, n, out, stream);
+}
+
+static int optim_launch(int kind, float* p, float* g, const void* g16, float* m, float* v, void* p_bf16, long long n, const OptimScalars& sc,
                         const int* step_ptr, const float* lr_scale_ptr, const float* gnorm_sq_ptr, const float* loss_ptr,
                         int zero_grad, cudaStream_t s) {
   long long blocks = (n / 4 + 255) / 256;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  if (kind == 0)
-    optim_kernel<0><<<(int)blocks, 256, 0, s>>>(p, g, m, v, (bf16*)p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad);
-  else if (kind == 1)
-    optim_kernel<1><<<(int)blocks, 256, 0, s>>>(p, g, m, v, (bf16*)p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad);
-  else
-    optim_kernel<2><<<(int)blocks, 256, 0, s>>>(p, g, m, v, (bf16*)p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad);
+#define VLM_OPTIM(K_)                                                                                                        \
+  {                                                                                                                          \
+    if (g16) optim_kernel<K_, true><<<(int)blocks, 256, 0, s>>>(p, g, (const bf16*)g16, m, v, (bf16*)p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad); \
+    else optim_kernel<K_, false><<<(int)blocks, 256, 0, s>>>(p, g, nullptr, m, v, (bf16*)p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad);           \
+  }
+  if (kind == 0) VLM_OPTIM(0)
+  else if (kind == 1) VLM_OPTIM(1)
+  else VLM_OPTIM(2)
+#undef VLM_OPTIM
   return check_launch("optim_step");
 }
 
@@ -170,13 +201,14 @@ extern "C" int vlm_optim_step_begin(int* step_ptr, const float* gnorm_sq_ptr, co
 extern "C" int vlm_optim_step(int kind, float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
                               float beta2, float eps, float weight_decay, const int* step_ptr, const float* lr_scale_ptr,
                               float grad_scale, const float* gnorm_sq_ptr, float max_norm, const float* loss_ptr, int zero_grad,
-                              void* stream) {
+                              const void* g_bf16, void* stream) {
   VLM_REQUIRE(kind >= 0 && kind <= 2, "vlm_optim_step: kind must be 0 (AdamW) | 1 (Adam) | 2 (RAdam)");
+  VLM_REQUIRE((uintptr_t)g_bf16 % 8 == 0, "vlm_optim_step: g_bf16 must be 8-byte aligned");
   VLM_REQUIRE(p && g && m && v && n > 0 && n % 4 == 0, "vlm_optim_step: flat buffers must be non-null with n %% 4 == 0");
   VLM_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
                   ((uintptr_t)p_bf16 % 8 == 0), "vlm_optim_step: buffers must be 16-byte aligned");
   OptimScalars sc{lr, beta1, beta2, eps, weight_decay, grad_scale, max_norm};
-  return optim_launch(kind, p, g, m, v, p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad, (cudaStream_t)stream);
+  return optim_launch(kind, p, g, g_bf16, m, v, p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad, (cudaStream_t)stream);
 }
 
 extern "C" int vlm_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
@@ -190,5 +222,5 @@ extern "C" int vlm_adamw_step(float* p, float* g, float* m, float* v, void* p_bf
     if (check_launch("adamw_step_inc")) return -1;
   }
   OptimScalars sc{lr, beta1, beta2, eps, weight_decay, grad_scale, max_norm};
-  return optim_launch(0, p, g, m, v, p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, nullptr, zero_grad, s);
+  return optim_launch(0, p, g, nullptr, m, v, p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, nullptr, zero_grad, s);
 }

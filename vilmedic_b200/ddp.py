@@ -4,6 +4,12 @@ contiguous span of the arena (arena.module_spans), the hand-written backward of 
 final" (nn.notify_grad_ready) and the exchange of that span starts on NCCL's stream while the backward of the layers below is
 still computing.  Spans arrive in descending address order (the backward walks the model in reverse), so adjacent spans are
 merged until a bucket reaches `bucket_bytes`; only the last bucket (patch embedding + whatever nobody announced) is exposed.
+Payload: bf16 by default — a cast kernel writes the bucket into `grad16` right before its all-reduce and the fused optimizer
+reads the reduced values from there (optim.FusedOptimizer.step(grad16=...)), so the exchange moves 2 B per parameter instead of 4
+and no widening pass exists.  Measured on 2 x B200 (round 2, tools/jobs/r2m.sh): the NCCL kernels cannot share an SM with the
+persistent one-CTA-per-SM GEMM / attention kernels, so the exchange time adds to the step almost 1:1 (24.33 ms vs 22.87 ms without
+any exchange; fewer NCCL channels make it worse: 26.3 ms at 4, 33.8 ms at 2; the bucket size does not matter) — bytes are what
+counts.  `payload="fp32"` (or VLM_DDP_PAYLOAD=fp32) keeps the reference's fp32 DDP all-reduce bit for bit.
 The 1/world factor is folded into the fused optimizer step (grad_scale).  No activation collectives: every pair is independent,
 contrastive negatives are rank-local as in the reference (vilmedic/executors/trainor_accelerate.py:122,132).
 Round 1 sent two unbucketed spans and launched the encoder one after the backward had ended (fully exposed: the whole 6 % loss of
@@ -17,7 +23,12 @@ from . import nn as _nn
 
 
 class GradSync:
-    def __init__(self, arena, group=None, bucket_bytes=None):
+    def __init__(self, arena, group=None, bucket_bytes=None, payload=None):
+        if payload is None:
+            payload = os.environ.get("VLM_DDP_PAYLOAD", "bf16")
+        if payload not in ("bf16", "fp32"):
+            raise ValueError("GradSync payload must be 'bf16' or 'fp32', got %r" % (payload,))
+        self.payload = payload
         if bucket_bytes is None:        # VLM_DDP_BUCKET_MB: tuning knob for tools/jobs (default 32 MB)
             bucket_bytes = int(float(os.environ.get("VLM_DDP_BUCKET_MB", "32")) * (1 << 20))
         self.arena = arena
@@ -28,6 +39,10 @@ class GradSync:
         self.sent = []                  # [lo, hi) element ranges already handed to NCCL this step
         self.run = None                 # the current run of adjacent announced spans [lo, hi)
         self.launches = 0
+        # bf16 exchange buffer (one slot per arena element); None when nothing is exchanged or the payload is fp32
+        self.grad16 = None
+        if self.world > 1 and payload == "bf16":
+            self.grad16 = torch.zeros(arena.numel, device=arena.flat_grad.device, dtype=torch.bfloat16)
 
     # ---- wiring: the backward functions call nn.notify_grad_ready(module) -> on_ready
     def attach(self):
@@ -43,7 +58,20 @@ class GradSync:
             return
         self.sent.append((lo, hi))
         self.launches += 1
-        self.pending.append(dist.all_reduce(self.arena.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if self.grad16 is not None:
+            buf = self.grad16[lo:hi]
+            self._cast(self.arena.flat_grad[lo:hi], buf)
+        else:
+            buf = self.arena.flat_grad[lo:hi]
+        self.pending.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    @staticmethod
+    def _cast(src, dst):
+        if src.is_cuda:
+            from . import ops
+            ops.cast_bf16(src, dst)
+        else:                       # gloo tests of the host logic
+            dst.copy_(src)
 
     def on_ready(self, module):
         span = self.arena.module_spans.get(id(module))
@@ -83,7 +111,9 @@ class GradSync:
         return out
 
     def finish(self):
-        """All-reduce whatever has not been sent yet, wait for everything; returns the grad scale for the optimizer."""
+        """All-reduce whatever has not been sent yet, wait for everything; returns the grad scale for the optimizer.
+        With the bf16 payload the reduced gradients are in `self.grad16` (pass it on: opt.step(grad_scale=..., grad16=sync.grad16));
+        `flat_grad` keeps the rank-local fp32 values until the optimizer zeroes it."""
         if self.world > 1:
             if self.run is not None:
                 self._launch(*self.run)

@@ -41,7 +41,7 @@ class GraphedTrainStep:
         loss = out["loss"]
         loss.backward()
         scale = self.sync.finish() if self.sync is not None else 1.0
-        self.opt.step(grad_scale=scale)
+        self.opt.step(grad_scale=scale, grad16=self.sync.grad16 if self.sync is not None else None)
         return loss
 
     # ---- input prefetch: the next step's batch travels host -> device on a copy stream while the current step computes ----

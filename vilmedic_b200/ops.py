@@ -316,7 +316,10 @@ def sum_scale(x, scale):
 
 
 def sumsq(g, out):
-    check(_L().vlm_sumsq_f32(ptr(g), c_ll(g.numel()), ptr(out), stream_ptr()), "vlm_sumsq_f32")
+    if g.dtype == torch.bfloat16:
+        check(_L().vlm_sumsq_bf16(ptr(g), c_ll(g.numel()), ptr(out), stream_ptr()), "vlm_sumsq_bf16")
+    else:
+        check(_L().vlm_sumsq_f32(ptr(g), c_ll(g.numel()), ptr(out), stream_ptr()), "vlm_sumsq_f32")
 
 
 def adamw_step(p, g, m, v, p_bf16, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, step_t=None,

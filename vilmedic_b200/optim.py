@@ -73,11 +73,15 @@ class FusedOptimizer(torch.optim.Optimizer):
         a.mirror_clean = True
 
     @torch.no_grad()
-    def step(self, closure=None, grad_scale=1.0, loss=None):
-        """loss: optional 0-dim fp32 CUDA tensor — a NaN/Inf value skips the step on the device (no host sync)."""
+    def step(self, closure=None, grad_scale=1.0, loss=None, grad16=None):
+        """loss: optional 0-dim fp32 CUDA tensor — a NaN/Inf value skips the step on the device (no host sync).
+        grad16: optional bf16 tensor [arena.numel] holding the (all-reduced) gradient values — the exchange payload of
+        ddp.GradSync; the fp32 gradient buffer is then only zeroed."""
         g = self.param_groups[0]
         a = self.arena
         L = _lib.lib()
+        if grad16 is not None and not (grad16.is_cuda and grad16.dtype == torch.bfloat16 and grad16.numel() == a.numel):
+            raise ValueError("step(grad16=...) expects a bf16 CUDA tensor with one element per arena slot")
         max_norm = g["max_grad_norm"] or 0.0
         loss_p = None
         if loss is not None:
@@ -90,7 +94,7 @@ class FusedOptimizer(torch.optim.Optimizer):
         if want_norm:
             self.gnorm_sq.zero_()
             for lo, hi in self.spans:
-                ops.sumsq(a.flat_grad[lo:hi], self.gnorm_sq)
+                ops.sumsq((grad16 if grad16 is not None else a.flat_grad)[lo:hi], self.gnorm_sq)
         gn_p = ptr(self.gnorm_sq) if want_norm else None
         ops.check(L.vlm_optim_step_begin(ptr(self.step_t), gn_p, loss_p, ptr(self.skipped_steps), stream_ptr()), "vlm_optim_step_begin")
         for lo, hi in self.spans:
@@ -98,7 +102,7 @@ class FusedOptimizer(torch.optim.Optimizer):
                                        ptr(self.v[lo:hi]), ptr(a.flat_bf16[lo:hi]), c_ll(hi - lo), c_float(g["lr"]),
                                        c_float(g["betas"][0]), c_float(g["betas"][1]), c_float(g["eps"]), c_float(g["weight_decay"]),
                                        ptr(self.step_t), ptr(self.lr_scale), c_float(grad_scale), gn_p, c_float(max_norm), loss_p,
-                                       c_int(1), stream_ptr()), "vlm_optim_step")
+                                       c_int(1), ptr(grad16[lo:hi]) if grad16 is not None else None, stream_ptr()), "vlm_optim_step")
         for lo, hi in self.frozen_spans:        # backward kernels may have accumulated into frozen slots: clear, never apply
             a.flat_grad[lo:hi].zero_()
         a.mirror_clean = True
