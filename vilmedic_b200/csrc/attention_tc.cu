@@ -301,7 +301,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           sts128((DROPOUT ? aP2s : aPTs) + off, pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]),
                  pack_bf16x2(pv[6], pv[7]));
         };
-        {  // TMEM loads are software-pipelined: the next chunk is in flight while the current one is processed
+        // key rows beyond Sk (the tail of the last key tile: 59 of 256 rows at Sk = 197) or masked for the whole warp: zeros, no math
+        const bool any_valid = __any_sync(0xffffffffu, kvalid);
+        if (any_valid) {  // TMEM loads are software-pipelined: the next chunk is in flight while the current one is processed
           const int qbase = part * part_cols;
           uint32_t va[8], vb[8];
           tmem_ld8(lane_taddr + ATC_S_COL + qbase, va);
@@ -314,6 +316,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
               if (c + 16 < part_cols) tmem_ld8(lane_taddr + ATC_S_COL + qbase + c + 16, va);
               pass_a_chunk(vb, qbase + c + 8);
             }
+          }
+        } else {
+          for (int c = 0; c < part_cols; c += 8) {
+            const int q0 = part * part_cols + c;
+            const uint32_t off = (uint32_t)((q0 >> 6) * 16384) + pt_row + (uint32_t)((((q0 & 63) >> 3) ^ r7) << 4);
+            sts128(aPTs + off, 0u, 0u, 0u, 0u);          // P^T = 0  =>  dS^T = 0 as well: pass B leaves these rows alone
+            if (DROPOUT) sts128(aP2s + off, 0u, 0u, 0u, 0u);
           }
         }
         fence_proxy_async_smem();
@@ -351,7 +360,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           }
           sts128(aPTs + off, ow[0], ow[1], ow[2], ow[3]);
         };
-        {
+        if (any_valid) {
           const int qbase = part * part_cols;
           uint32_t va[8], vb[8];
           tmem_ld8(lane_taddr + ATC_S_COL + qbase, va);
@@ -547,8 +556,8 @@ struct AtcFwdSmem {
   __host__ __device__ static int off_p(int Nk) { return off_v(Nk) + 2 * kv_bytes(Nk); }
   __host__ __device__ static int off_red(int Nk) { return off_p(Nk) + p_bytes(Nk); }   // float [2][ATF_SPLIT][128]
   __host__ __device__ static int off_kok(int Nk) { return off_red(Nk) + 2 * ATF_SPLIT * 128 * 4; }   // uint8 [256]
-  __host__ __device__ static int off_bal(int Nk) { return off_kok(Nk) + 256; }             // uint32 [8]
-  __host__ __device__ static int off_bar(int Nk) { return off_bal(Nk) + 32; }
+  __host__ __device__ static int off_bal(int Nk) { return off_kok(Nk) + 256; }             // uint32 [4 * ATF_SPLIT warps][8]
+  __host__ __device__ static int off_bar(int Nk) { return off_bal(Nk) + 4 * ATF_SPLIT * 32; }
   __host__ __device__ static int total(int Nk) { return off_bar(Nk) + NUM_BARS * 8 + 16 + 1024; }
 };
 
@@ -557,11 +566,11 @@ struct AtcFwdSmem {
 //   MMA warp   : S(0), S(1); then for every t: wait P(t) -> O = P V (TMEM cols [2 Nk, 2 Nk + 64)) -> S(t+2) into the S buffer
 //                t&1 that the softmax of tile t has just drained.  So S(t+1) is always complete when the softmax warps get to it.
 //   softmax    : pass 1 (row max) of tile t, then the EPILOGUE OF TILE t-1 (its P V ran under pass 1), then pass 2 (P -> smem).
+template <int NC>
 __global__ void __launch_bounds__(ATF_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, AttnTcFwdParams p) {
   using S = AtcFwdSmem;
-  constexpr int NCT = 128 * ATF_SPLIT;            // softmax threads
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int Nk = p.Nk;
@@ -571,7 +580,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint8_t* sV = smem + S::off_v(Nk);
   uint8_t* sP = smem + S::off_p(Nk);
   float* sRed = reinterpret_cast<float*>(smem + S::off_red(Nk));
-  uint8_t* sKok = smem + S::off_kok(Nk);
   uint32_t* sBal = reinterpret_cast<uint32_t*>(smem + S::off_bal(Nk));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::off_bar(Nk));
   uint64_t* kv_full = bars + 0;    // [2]
@@ -681,19 +689,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int quad = warp_idx & 3;
     const int part = (warp_idx - 2) >> 2;        // which slice of the key columns this warp handles
     const int r = quad * 32 + lane;              // query row inside the tile
-    const int ct = threadIdx.x - 64;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float sl2 = p.scale * 1.4426950408889634f;   // > 0 (host checks): max and scaling commute
     const unsigned long long off_eff = p.offset + ((p.p_drop > 0.f && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
     const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
-    const int part_cols = Nk / ATF_SPLIT;        // multiple of 8 (Nk is a multiple of 32)
-    const int c0 = part * part_cols;             // first key column of this thread's slice
-    const int nchunks = part_cols >> 3;          // 8-column chunks (one 16-byte unit of the P tile each)
+    // Key columns are dealt to the ATF_SPLIT warps of a quadrant in 8-key chunks, round robin: chunk c of this thread covers keys
+    // [32 c + 8 part, +8).  (A contiguous slice per warp left the warps of the high slices idle under a causal mask: 30 % of all
+    // stall samples were barrier waits, profiles/ncu_r2_attention.txt.)  NC = max chunks per thread (Nk <= 32 NC): the chunk loops
+    // are fully unrolled and the raw scores stay in registers between the max pass and the exp pass — S is read from TMEM once.
+    const int nchunks = Nk >> 5;
     const uint32_t p_row = smem_u32(sP) + (uint32_t)(r * 128);  // shared-space address of this row inside atom 0 of the P tile
     const int r7 = r & 7;
+    // 16-byte unit of chunk c inside its 64-key atom: (c & 1) * 4 + part, XOR-swizzled with the row
+    const uint32_t p_even = p_row + (uint32_t)(((part) ^ r7) << 4), p_odd = p_row + (uint32_t)(((4 + part) ^ r7) << 4);
     float* redmax = sRed;                        // [ATF_SPLIT][128]
     float* redsum = sRed + ATF_SPLIT * 128;      // [ATF_SPLIT][128]
+    uint32_t* sBalW = sBal + (warp_idx - 2) * 8; // this warp's copy of the key-validity words (generic masks only)
     // deferred epilogue state (tile t-1)
     float l_prev = 0.f, mref_prev = 0.f;
     long long o_off_prev = 0, lse_off_prev = 0;
@@ -724,33 +736,44 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int b = item / p.H, h = item % p.H;
       const uint32_t dkey = attn_drop_key(p.seed, off_eff, item);
-      // ---- per-item key validity.  The usual masks (no mask, right padding) make the valid keys a PREFIX [0, nvalid): then an
-      // 8-key chunk is either fully valid for the whole warp (no per-element predicate at all), fully masked (skipped) or
-      // one of the few mixed ones (causal diagonal / last partial chunk).  Arbitrary masks keep the per-element test.
-      named_bar_sync(1, NCT);
-      if (ct < 256) {                            // warps 2..9: one key per thread (Nk <= 224)
-        const bool ok = (ct < p.Sk) && (!p.kmask || p.kmask[(long long)b * p.Sk + ct]);
-        sKok[ct] = ok;
-        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) sBal[ct >> 5] = bal;
-      }
-      named_bar_sync(1, NCT);
+      // ---- per-item key validity, computed by every warp for itself (no CTA-wide barrier in the tile loop).  The usual masks
+      // (no mask, right padding) make the valid keys a PREFIX [0, nvalid): then an 8-key chunk is either fully valid for the whole
+      // warp (no per-element predicate at all), fully masked (skipped) or one of the few mixed ones (causal diagonal / last
+      // partial chunk).  Arbitrary masks keep a per-element test against the ballot words.
       int nvalid = 0;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) nvalid += __popc(sBal[w]);
       bool prefix = true;
+      {
+        uint32_t bal[7];
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        const int lo = nvalid - 32 * w;
-        const uint32_t expect = lo >= 32 ? 0xffffffffu : (lo <= 0 ? 0u : ((1u << lo) - 1u));
-        prefix = prefix && (sBal[w] == expect);
+        for (int w = 0; w < 7; ++w) {
+          const int key = w * 32 + lane;
+          const bool ok = (key < p.Sk) && (!p.kmask || p.kmask[(long long)b * p.Sk + key]);
+          bal[w] = __ballot_sync(0xffffffffu, ok);
+          nvalid += __popc(bal[w]);
+        }
+#pragma unroll
+        for (int w = 0; w < 7; ++w) {
+          const int lo = nvalid - 32 * w;
+          const uint32_t expect = lo >= 32 ? 0xffffffffu : (lo <= 0 ? 0u : ((1u << lo) - 1u));
+          prefix = prefix && (bal[w] == expect);
+        }
+        if (!prefix) {
+          __syncwarp();
+          if (lane < 7) {
+            uint32_t mine = 0;
+#pragma unroll
+            for (int w = 0; w < 7; ++w) mine = (lane == w) ? bal[w] : mine;
+            sBalW[lane] = mine;
+          }
+          __syncwarp();
+        }
       }
       for (int i = 0; i < qtiles; ++i, ++t) {
         const int sb = t & 1;
-        const uint32_t s_taddr = lane_taddr + (uint32_t)(sb * SB + c0);
+        const uint32_t s_taddr = lane_taddr + (uint32_t)(sb * SB + part * 8);
         const int qq = i * 128 + r;
         // key k is visible to this row iff k < kmax_row (prefix masks); every lane of the warp sees all keys < kfull and no
-        // key >= kany.  Generic masks: kfull = 0, kany = Nk, visibility from sKok.
+        // key >= kany.  Generic masks: kfull = 0, kany = Nk, visibility from the ballot words.
         int kmax_row = 0, kfull = 0, kany = Nk;
         if (prefix) {
           const int q_lo = i * 128 + quad * 32;
@@ -758,62 +781,65 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           kfull = p.causal ? min(nvalid, q_lo + 1) : nvalid;
           kany = p.causal ? min(nvalid, q_lo + 32) : nvalid;
         }
-        auto visible = [&](int kk) -> bool {
-          return prefix ? (kk < kmax_row) : (sKok[kk] && (!p.causal || kk <= qq));
+        auto visible = [&](int kk) -> bool {     // generic masks only
+          return ((sBalW[kk >> 5] >> (kk & 31)) & 1u) && (!p.causal || kk <= qq);
         };
-        int nact = (kany - c0 + 7) >> 3;         // chunks of this slice that hold at least one visible key (warp-uniform)
+        int nact = (kany - part * 8 + 31) >> 5;  // chunks of this thread that hold at least one visible key (warp-uniform)
         nact = nact < 0 ? 0 : (nact > nchunks ? nchunks : nact);
         mbar_wait(&s_full[sb], (t >> 1) & 1u);
         tc_fence_after();
-        // ---- pass 1: row max (raw scores) over this thread's slice of the key columns; TMEM loads are software-pipelined
+        // ---- pass 1: this thread's raw scores TMEM -> registers (once), row max over them
+        uint32_t sv[NC][8];
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          if (c < nact) tmem_ld8(s_taddr + (uint32_t)(c * 32), sv[c]);
+        tmem_ld_wait();
         float mx = -INFINITY;
-        {
-          uint32_t va[8], vb[8];
-          auto chunk_max = [&](const uint32_t* v, int c) {
-            const int k0 = c0 + c * 8;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          if (c < nact) {
+            const int k0 = c * 32 + part * 8;
             if (k0 + 8 <= kfull) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+              for (int e = 0; e < 8; ++e) mx = fmaxf(mx, __uint_as_float(sv[c][e]));
+            } else if (prefix) {
+              const int n = kmax_row - k0;       // visible keys of this row inside the chunk
+#pragma unroll
+              for (int e = 0; e < 8; ++e) mx = (e < n) ? fmaxf(mx, __uint_as_float(sv[c][e])) : mx;
             } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e)
-                if (visible(k0 + e)) mx = fmaxf(mx, __uint_as_float(v[e]));
-            }
-          };
-          if (nact > 0) tmem_ld8(s_taddr, va);
-          for (int c = 0; c < nact; c += 2) {
-            tmem_ld_wait();
-            if (c + 1 < nact) tmem_ld8(s_taddr + (c + 1) * 8, vb);
-            chunk_max(va, c);
-            if (c + 1 < nact) {
-              tmem_ld_wait();
-              if (c + 2 < nact) tmem_ld8(s_taddr + (c + 2) * 8, va);
-              chunk_max(vb, c + 1);
+                if (visible(k0 + e)) mx = fmaxf(mx, __uint_as_float(sv[c][e]));
             }
           }
         }
         redmax[part * 128 + r] = mx;
-        named_bar_sync(2, NCT);
+        named_bar_sync(2 + quad, 32 * ATF_SPLIT);          // only the warps that share these 32 rows
 #pragma unroll
         for (int s2 = 0; s2 < ATF_SPLIT; ++s2) mx = fmaxf(mx, redmax[s2 * 128 + r]);
         const float mref = (mx == -INFINITY) ? 0.f : mx * sl2;
         // ---- deferred epilogue of the previous tile: its P V product ran while pass 1 was executing.  Waiting for it also
         // guarantees that the tensor core has finished reading the (single) P tile before pass 2 overwrites it.
         if (t > 0) epilogue_prev(t - 1);
-        // ---- pass 2: P = exp2(s * scale * log2e - m), row sum, dropout, bf16 -> swizzled smem
+        // ---- pass 2: P = exp2(s * scale * log2e - m) from the registers, row sum, dropout, bf16 -> swizzled smem
         float sum = 0.f;
-        {
-          uint32_t va[8], vb[8];
-          auto chunk_exp = [&](const uint32_t* v, int c) {
-            const int k0 = c0 + c * 8;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const uint32_t dst = ((c & 1) ? p_odd : p_even) + (uint32_t)((c >> 1) * 16384);
+          if (c < nact) {
+            const int k0 = c * 32 + part * 8;
             float pe[8];
             if (k0 + 8 <= kfull) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) pe[e] = ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -mref));
+              for (int e = 0; e < 8; ++e) pe[e] = ex2_approx(fmaf(__uint_as_float(sv[c][e]), sl2, -mref));
+            } else if (prefix) {
+              const int n = kmax_row - k0;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pe[e] = (e < n) ? ex2_approx(fmaf(__uint_as_float(sv[c][e]), sl2, -mref)) : 0.f;
             } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e)
-                pe[e] = visible(k0 + e) ? ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -mref)) : 0.f;
+                pe[e] = visible(k0 + e) ? ex2_approx(fmaf(__uint_as_float(sv[c][e]), sl2, -mref)) : 0.f;
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) sum += pe[e];
@@ -821,28 +847,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 #pragma unroll
               for (int e = 0; e < 8; ++e) pe[e] = attn_drop_rand(dkey, qq, k0 + e, p.Sk) >= thr ? pe[e] * inv_keep : 0.f;
             }
-            const uint32_t atom = (uint32_t)((k0 >> 6) * 16384) + p_row;
-            const int u0 = (k0 & 63) >> 3;
-            sts128(atom + (uint32_t)((u0 ^ r7) << 4), pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]),
-                   pack_bf16x2(pe[6], pe[7]));
-          };
-          if (nact > 0) tmem_ld8(s_taddr, va);
-          for (int c = 0; c < nact; c += 2) {
-            tmem_ld_wait();
-            if (c + 1 < nact) tmem_ld8(s_taddr + (c + 1) * 8, vb);
-            chunk_exp(va, c);
-            if (c + 1 < nact) {
-              tmem_ld_wait();
-              if (c + 2 < nact) tmem_ld8(s_taddr + (c + 2) * 8, va);
-              chunk_exp(vb, c + 1);
-            }
-          }
-          // chunks without any visible key: P = 0 (the P V product runs over all Nk columns)
-          for (int c = nact; c < nchunks; ++c) {
-            const int k0 = c0 + c * 8;
-            const uint32_t atom = (uint32_t)((k0 >> 6) * 16384) + p_row;
-            const int u0 = (k0 & 63) >> 3;
-            sts128(atom + (uint32_t)((u0 ^ r7) << 4), 0u, 0u, 0u, 0u);
+            sts128(dst, pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]), pack_bf16x2(pe[6], pe[7]));
+          } else if (c < nchunks) {
+            sts128(dst, 0u, 0u, 0u, 0u);         // no visible key: P = 0 (the P V product runs over all Nk columns)
           }
         }
         redsum[part * 128 + r] = sum;
@@ -850,7 +857,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);
-        named_bar_sync(2, NCT);
+        named_bar_sync(2 + quad, 32 * ATF_SPLIT);
         float l = 0.f;
 #pragma unroll
         for (int s2 = 0; s2 < ATF_SPLIT; ++s2) l += redsum[s2 * 128 + r];
@@ -895,7 +902,9 @@ int attention_fwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
   p.seed = seed; p.offset = offset; p.offset_ptr = rng_offset_ptr;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AtcFwdSmem::total(224));
+    cudaError_t err = cudaFuncSetAttribute(attn_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtcFwdSmem::total(128));
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(attn_fwd_tc_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtcFwdSmem::total(224));
     if (err != cudaSuccess) {
       set_error("cudaFuncSetAttribute(attn_fwd_tc smem=%d): %s", AtcFwdSmem::total(224), cudaGetErrorString(err));
       return -1;
@@ -904,7 +913,8 @@ int attention_fwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
   }
   const int items = B * H;
   const int grid = items < num_sms() ? items : num_sms();
-  attn_fwd_tc_kernel<<<grid, ATF_THREADS, AtcFwdSmem::total(Nk), stream>>>(tq, tk, tv, p);
+  if (Nk <= 128) attn_fwd_tc_kernel<4><<<grid, ATF_THREADS, AtcFwdSmem::total(Nk), stream>>>(tq, tk, tv, p);
+  else attn_fwd_tc_kernel<7><<<grid, ATF_THREADS, AtcFwdSmem::total(Nk), stream>>>(tq, tk, tv, p);
   const int rc = check_launch("attn_fwd_tc");
   return rc ? rc : 1;
 }
