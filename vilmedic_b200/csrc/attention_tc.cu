@@ -566,7 +566,7 @@ struct AtcFwdSmem {
 //   MMA warp   : S(0), S(1); then for every t: wait P(t) -> O = P V (TMEM cols [2 Nk, 2 Nk + 64)) -> S(t+2) into the S buffer
 //                t&1 that the softmax of tile t has just drained.  So S(t+1) is always complete when the softmax warps get to it.
 //   softmax    : pass 1 (row max) of tile t, then the EPILOGUE OF TILE t-1 (its P V ran under pass 1), then pass 2 (P -> smem).
-template <int NC>
+template <int NC, int NKEEP>
 __global__ void __launch_bounds__(ATF_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, AttnTcFwdParams p) {
@@ -788,31 +788,48 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         nact = nact < 0 ? 0 : (nact > nchunks ? nchunks : nact);
         mbar_wait(&s_full[sb], (t >> 1) & 1u);
         tc_fence_after();
-        // ---- pass 1: this thread's raw scores TMEM -> registers (once), row max over them
-        uint32_t sv[NC][8];
-#pragma unroll
-        for (int c = 0; c < NC; ++c)
-          if (c < nact) tmem_ld8(s_taddr + (uint32_t)(c * 32), sv[c]);
-        tmem_ld_wait();
+        // ---- pass 1: row max.  The first NKEEP chunks of this thread go TMEM -> registers ONCE and stay there for pass 2; the
+        // remaining ones (NKEEP < NC: register budget, 96 per thread at 18 warps) are streamed through a two-deep register
+        // pipeline here and again in pass 2.
+        uint32_t sv[NKEEP > 0 ? NKEEP : 1][8];
+        uint32_t ta[8], tb[8];
         float mx = -INFINITY;
+        auto max_chunk = [&](int c, const uint32_t* v) {
+          const int k0 = c * 32 + part * 8;
+          if (k0 + 8 <= kfull) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
+            for (int e = 0; e < 8; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+          } else if (prefix) {
+            const int n = kmax_row - k0;         // visible keys of this row inside the chunk
+#pragma unroll
+            for (int e = 0; e < 8; ++e) mx = (e < n) ? fmaxf(mx, __uint_as_float(v[e])) : mx;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (visible(k0 + e)) mx = fmaxf(mx, __uint_as_float(v[e]));
+          }
+        };
+#pragma unroll
+        for (int c = 0; c < NKEEP; ++c)
+          if (c < nact) tmem_ld8(s_taddr + (uint32_t)(c * 32), sv[c]);
+        if (NKEEP < NC && NKEEP < nact) tmem_ld8(s_taddr + (uint32_t)(NKEEP * 32), ta);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = NKEEP; c < NC; c += 2) {    // streamed chunks: the next load is in flight while this one is reduced
           if (c < nact) {
-            const int k0 = c * 32 + part * 8;
-            if (k0 + 8 <= kfull) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) mx = fmaxf(mx, __uint_as_float(sv[c][e]));
-            } else if (prefix) {
-              const int n = kmax_row - k0;       // visible keys of this row inside the chunk
-#pragma unroll
-              for (int e = 0; e < 8; ++e) mx = (e < n) ? fmaxf(mx, __uint_as_float(sv[c][e])) : mx;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (visible(k0 + e)) mx = fmaxf(mx, __uint_as_float(sv[c][e]));
-            }
+            if (c + 1 < NC && c + 1 < nact) tmem_ld8(s_taddr + (uint32_t)((c + 1) * 32), tb);
+            max_chunk(c, ta);
+          }
+          if (c + 1 < NC && c + 1 < nact) {
+            tmem_ld_wait();
+            if (c + 2 < NC && c + 2 < nact) tmem_ld8(s_taddr + (uint32_t)((c + 2) * 32), ta);
+            max_chunk(c + 1, tb);
+            if (c + 2 < NC && c + 2 < nact) tmem_ld_wait();
           }
         }
+#pragma unroll
+        for (int c = 0; c < NKEEP; ++c)
+          if (c < nact) max_chunk(c, sv[c]);
         redmax[part * 128 + r] = mx;
         named_bar_sync(2 + quad, 32 * ATF_SPLIT);          // only the warps that share these 32 rows
 #pragma unroll
@@ -821,37 +838,52 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         // ---- deferred epilogue of the previous tile: its P V product ran while pass 1 was executing.  Waiting for it also
         // guarantees that the tensor core has finished reading the (single) P tile before pass 2 overwrites it.
         if (t > 0) epilogue_prev(t - 1);
-        // ---- pass 2: P = exp2(s * scale * log2e - m) from the registers, row sum, dropout, bf16 -> swizzled smem
+        // ---- pass 2: P = exp2(s * scale * log2e - m), row sum, dropout, bf16 -> swizzled smem
         float sum = 0.f;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
+        auto exp_chunk = [&](int c, const uint32_t* v) {
           const uint32_t dst = ((c & 1) ? p_odd : p_even) + (uint32_t)((c >> 1) * 16384);
+          const int k0 = c * 32 + part * 8;
+          float pe[8];
+          if (k0 + 8 <= kfull) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pe[e] = ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -mref));
+          } else if (prefix) {
+            const int n = kmax_row - k0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pe[e] = (e < n) ? ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -mref)) : 0.f;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pe[e] = visible(k0 + e) ? ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -mref)) : 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sum += pe[e];
+          if (p.p_drop > 0.f) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pe[e] = attn_drop_rand(dkey, qq, k0 + e, p.Sk) >= thr ? pe[e] * inv_keep : 0.f;
+          }
+          sts128(dst, pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]), pack_bf16x2(pe[6], pe[7]));
+        };
+        if (NKEEP < NC && NKEEP < nact) tmem_ld8(s_taddr + (uint32_t)(NKEEP * 32), ta);   // in flight under the kept chunks
+#pragma unroll
+        for (int c = 0; c < NKEEP; ++c)
+          if (c < nact) exp_chunk(c, sv[c]);
+        if (NKEEP < NC && NKEEP < nact) tmem_ld_wait();
+#pragma unroll
+        for (int c = NKEEP; c < NC; c += 2) {
           if (c < nact) {
-            const int k0 = c * 32 + part * 8;
-            float pe[8];
-            if (k0 + 8 <= kfull) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) pe[e] = ex2_approx(fmaf(__uint_as_float(sv[c][e]), sl2, -mref));
-            } else if (prefix) {
-              const int n = kmax_row - k0;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) pe[e] = (e < n) ? ex2_approx(fmaf(__uint_as_float(sv[c][e]), sl2, -mref)) : 0.f;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                pe[e] = visible(k0 + e) ? ex2_approx(fmaf(__uint_as_float(sv[c][e]), sl2, -mref)) : 0.f;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) sum += pe[e];
-            if (p.p_drop > 0.f) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) pe[e] = attn_drop_rand(dkey, qq, k0 + e, p.Sk) >= thr ? pe[e] * inv_keep : 0.f;
-            }
-            sts128(dst, pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]), pack_bf16x2(pe[6], pe[7]));
-          } else if (c < nchunks) {
-            sts128(dst, 0u, 0u, 0u, 0u);         // no visible key: P = 0 (the P V product runs over all Nk columns)
+            if (c + 1 < NC && c + 1 < nact) tmem_ld8(s_taddr + (uint32_t)((c + 1) * 32), tb);
+            exp_chunk(c, ta);
+          }
+          if (c + 1 < NC && c + 1 < nact) {
+            tmem_ld_wait();
+            if (c + 2 < NC && c + 2 < nact) tmem_ld8(s_taddr + (uint32_t)((c + 2) * 32), ta);
+            exp_chunk(c + 1, tb);
+            if (c + 2 < NC && c + 2 < nact) tmem_ld_wait();
           }
         }
+#pragma unroll
+        for (int c = 0; c < NC; ++c)             // no visible key: P = 0 (the P V product runs over all Nk columns)
+          if (c >= nact && c < nchunks) sts128(((c & 1) ? p_odd : p_even) + (uint32_t)((c >> 1) * 16384), 0u, 0u, 0u, 0u);
         redsum[part * 128 + r] = sum;
         fence_proxy_async_smem();
         tc_fence_before();
@@ -900,21 +932,34 @@ int attention_fwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
   p.o = (bf16*)o; p.o_bs = o_bs; p.o_rs = o_rs; p.lse = lse; p.kmask = kmask;
   p.B = B; p.H = H; p.Tq = Tq; p.Sk = Sk; p.Nk = Nk; p.causal = causal; p.scale = scale; p.p_drop = p_drop;
   p.seed = seed; p.offset = offset; p.offset_ptr = rng_offset_ptr;
+  // how many of a thread's 8-key chunks stay in registers between the two softmax passes (the rest is re-read from TMEM);
+  // VLM_ATTN_FWD_KEEP overrides the choice for Nk > 128 (tools/jobs experiments): 0 | 2 | 4 | 7
+  static const int keep_wide = [] {
+    const char* v = getenv("VLM_ATTN_FWD_KEEP");
+    return v ? atoi(v) : 4;
+  }();
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(attn_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtcFwdSmem::total(128));
-    if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(attn_fwd_tc_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtcFwdSmem::total(224));
+    const int big = AtcFwdSmem::total(224);
+    cudaError_t err = cudaFuncSetAttribute(attn_fwd_tc_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtcFwdSmem::total(128));
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(attn_fwd_tc_kernel<7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(attn_fwd_tc_kernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(attn_fwd_tc_kernel<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(attn_fwd_tc_kernel<7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     if (err != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(attn_fwd_tc smem=%d): %s", AtcFwdSmem::total(224), cudaGetErrorString(err));
+      set_error("cudaFuncSetAttribute(attn_fwd_tc smem=%d): %s", big, cudaGetErrorString(err));
       return -1;
     }
     attr_set = true;
   }
   const int items = B * H;
   const int grid = items < num_sms() ? items : num_sms();
-  if (Nk <= 128) attn_fwd_tc_kernel<4><<<grid, ATF_THREADS, AtcFwdSmem::total(Nk), stream>>>(tq, tk, tv, p);
-  else attn_fwd_tc_kernel<7><<<grid, ATF_THREADS, AtcFwdSmem::total(Nk), stream>>>(tq, tk, tv, p);
+  const int smem_bytes = AtcFwdSmem::total(Nk);
+  if (Nk <= 128) attn_fwd_tc_kernel<4, 4><<<grid, ATF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
+  else if (keep_wide >= 7) attn_fwd_tc_kernel<7, 7><<<grid, ATF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
+  else if (keep_wide >= 4) attn_fwd_tc_kernel<7, 4><<<grid, ATF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
+  else if (keep_wide >= 2) attn_fwd_tc_kernel<7, 2><<<grid, ATF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
+  else attn_fwd_tc_kernel<7, 0><<<grid, ATF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
   const int rc = check_launch("attn_fwd_tc");
   return rc ? rc : 1;
 }
