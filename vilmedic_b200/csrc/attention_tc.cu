@@ -19,6 +19,7 @@
 // mma.sync kernels in attention.cu (those remain the path for other head dims, longer queries and the forward).
 #include <cuda.h>
 #include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "vlm_b200.h"
@@ -566,7 +567,18 @@ struct AtcFwdSmem {
 //   MMA warp   : S(0), S(1); then for every t: wait P(t) -> O = P V (TMEM cols [2 Nk, 2 Nk + 64)) -> S(t+2) into the S buffer
 //                t&1 that the softmax of tile t has just drained.  So S(t+1) is always complete when the softmax warps get to it.
 //   softmax    : pass 1 (row max) of tile t, then the EPILOGUE OF TILE t-1 (its P V ran under pass 1), then pass 2 (P -> smem).
-template <int NC, int NKEEP>
+// calls f(std::integral_constant<int, n>) for the runtime n in [0, MAXN] — a compare chain, used once per pass and tile
+template <int MAXN, typename F>
+__device__ __forceinline__ void dispatch_count(int n, F&& f) {
+  if constexpr (MAXN == 0) {
+    f(std::integral_constant<int, 0>{});
+  } else {
+    if (n >= MAXN) f(std::integral_constant<int, MAXN>{});
+    else dispatch_count<MAXN - 1>(n, f);
+  }
+}
+
+template <int NC, bool DROPOUT>
 __global__ void __launch_bounds__(ATF_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, AttnTcFwdParams p) {
@@ -691,9 +703,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int r = quad * 32 + lane;              // query row inside the tile
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float sl2 = p.scale * 1.4426950408889634f;   // > 0 (host checks): max and scaling commute
-    const unsigned long long off_eff = p.offset + ((p.p_drop > 0.f && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
+    const unsigned long long off_eff = p.offset + ((DROPOUT && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
     const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
-    const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+    const float inv_keep = DROPOUT ? 1.f / (1.f - p.p_drop) : 1.f;
     // Key columns are dealt to the ATF_SPLIT warps of a quadrant in 8-key chunks, round robin: chunk c of this thread covers keys
     // [32 c + 8 part, +8).  (A contiguous slice per warp left the warps of the high slices idle under a causal mask: 30 % of all
     // stall samples were barrier waits, profiles/ncu_r2_attention.txt.)  NC = max chunks per thread (Nk <= 32 NC): the chunk loops
@@ -788,48 +800,48 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         nact = nact < 0 ? 0 : (nact > nchunks ? nchunks : nact);
         mbar_wait(&s_full[sb], (t >> 1) & 1u);
         tc_fence_after();
-        // ---- pass 1: row max.  The first NKEEP chunks of this thread go TMEM -> registers ONCE and stay there for pass 2; the
-        // remaining ones (NKEEP < NC: register budget, 96 per thread at 18 warps) are streamed through a two-deep register
-        // pipeline here and again in pass 2.
-        uint32_t sv[NKEEP > 0 ? NKEEP : 1][8];
+        // ---- pass 1: row max.  Chunks [0, nfull) are fully visible to every lane of the warp: straight-line code selected by
+        // nfull (compile-time chunk count: no per-chunk compare / branch, constant TMEM columns), TMEM loads two deep.  The few
+        // chunks [nfull, nact) on the causal diagonal / at the end of the valid keys take the predicated loop.
+        // (S stays in TMEM between the passes: keeping it in registers was measured SLOWER at 96 registers per thread —
+        //  62 vs 52 us on the ViT shape, tools/jobs/r2p.sh.)
+        int nfull = kfull - part * 8 + 24;       // = 32 * (#chunks with k0 + 8 <= kfull)  rounded down below
+        nfull = nfull < 0 ? 0 : (nfull >> 5);
+        nfull = nfull > nact ? nact : nfull;
         uint32_t ta[8], tb[8];
         float mx = -INFINITY;
-        auto max_chunk = [&](int c, const uint32_t* v) {
-          const int k0 = c * 32 + part * 8;
-          if (k0 + 8 <= kfull) {
+        dispatch_count<NC>(nfull, [&](auto nconst) {
+          constexpr int N = decltype(nconst)::value;
+          if (N > 0) tmem_ld8(s_taddr, ta);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
-          } else if (prefix) {
+          for (int c = 0; c < N; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < N) tmem_ld8(s_taddr + (uint32_t)((c + 1) * 32), tb);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) mx = fmaxf(mx, __uint_as_float(ta[e]));
+            if (c + 1 < N) {
+              tmem_ld_wait();
+              if (c + 2 < N) tmem_ld8(s_taddr + (uint32_t)((c + 2) * 32), ta);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) mx = fmaxf(mx, __uint_as_float(tb[e]));
+            }
+          }
+        });
+#pragma unroll 1
+        for (int c = nfull; c < nact; ++c) {
+          tmem_ld8(s_taddr + (uint32_t)(c * 32), ta);
+          tmem_ld_wait();
+          const int k0 = c * 32 + part * 8;
+          if (prefix) {
             const int n = kmax_row - k0;         // visible keys of this row inside the chunk
 #pragma unroll
-            for (int e = 0; e < 8; ++e) mx = (e < n) ? fmaxf(mx, __uint_as_float(v[e])) : mx;
+            for (int e = 0; e < 8; ++e) mx = (e < n) ? fmaxf(mx, __uint_as_float(ta[e])) : mx;
           } else {
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-              if (visible(k0 + e)) mx = fmaxf(mx, __uint_as_float(v[e]));
-          }
-        };
-#pragma unroll
-        for (int c = 0; c < NKEEP; ++c)
-          if (c < nact) tmem_ld8(s_taddr + (uint32_t)(c * 32), sv[c]);
-        if (NKEEP < NC && NKEEP < nact) tmem_ld8(s_taddr + (uint32_t)(NKEEP * 32), ta);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = NKEEP; c < NC; c += 2) {    // streamed chunks: the next load is in flight while this one is reduced
-          if (c < nact) {
-            if (c + 1 < NC && c + 1 < nact) tmem_ld8(s_taddr + (uint32_t)((c + 1) * 32), tb);
-            max_chunk(c, ta);
-          }
-          if (c + 1 < NC && c + 1 < nact) {
-            tmem_ld_wait();
-            if (c + 2 < NC && c + 2 < nact) tmem_ld8(s_taddr + (uint32_t)((c + 2) * 32), ta);
-            max_chunk(c + 1, tb);
-            if (c + 2 < NC && c + 2 < nact) tmem_ld_wait();
+              if (visible(k0 + e)) mx = fmaxf(mx, __uint_as_float(ta[e]));
           }
         }
-#pragma unroll
-        for (int c = 0; c < NKEEP; ++c)
-          if (c < nact) max_chunk(c, sv[c]);
         redmax[part * 128 + r] = mx;
         named_bar_sync(2 + quad, 32 * ATF_SPLIT);          // only the warps that share these 32 rows
 #pragma unroll
@@ -838,52 +850,61 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         // ---- deferred epilogue of the previous tile: its P V product ran while pass 1 was executing.  Waiting for it also
         // guarantees that the tensor core has finished reading the (single) P tile before pass 2 overwrites it.
         if (t > 0) epilogue_prev(t - 1);
-        // ---- pass 2: P = exp2(s * scale * log2e - m), row sum, dropout, bf16 -> swizzled smem
+        // ---- pass 2: P = exp2(s * scale * log2e - m), row sum, dropout, bf16 -> swizzled smem (same fast / predicated split)
         float sum = 0.f;
-        auto exp_chunk = [&](int c, const uint32_t* v) {
-          const uint32_t dst = ((c & 1) ? p_odd : p_even) + (uint32_t)((c >> 1) * 16384);
-          const int k0 = c * 32 + part * 8;
-          float pe[8];
-          if (k0 + 8 <= kfull) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) pe[e] = ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -mref));
-          } else if (prefix) {
-            const int n = kmax_row - k0;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) pe[e] = (e < n) ? ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -mref)) : 0.f;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) pe[e] = visible(k0 + e) ? ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -mref)) : 0.f;
-          }
+        auto finish_chunk = [&](float (&pe)[8], int k0, uint32_t dst) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) sum += pe[e];
-          if (p.p_drop > 0.f) {
+          if (DROPOUT) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) pe[e] = attn_drop_rand(dkey, qq, k0 + e, p.Sk) >= thr ? pe[e] * inv_keep : 0.f;
           }
           sts128(dst, pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]), pack_bf16x2(pe[6], pe[7]));
         };
-        if (NKEEP < NC && NKEEP < nact) tmem_ld8(s_taddr + (uint32_t)(NKEEP * 32), ta);   // in flight under the kept chunks
+        dispatch_count<NC>(nfull, [&](auto nconst) {
+          constexpr int N = decltype(nconst)::value;
+          if (N > 0) tmem_ld8(s_taddr, ta);
 #pragma unroll
-        for (int c = 0; c < NKEEP; ++c)
-          if (c < nact) exp_chunk(c, sv[c]);
-        if (NKEEP < NC && NKEEP < nact) tmem_ld_wait();
-#pragma unroll
-        for (int c = NKEEP; c < NC; c += 2) {
-          if (c < nact) {
-            if (c + 1 < NC && c + 1 < nact) tmem_ld8(s_taddr + (uint32_t)((c + 1) * 32), tb);
-            exp_chunk(c, ta);
-          }
-          if (c + 1 < NC && c + 1 < nact) {
+          for (int c = 0; c < N; c += 2) {
             tmem_ld_wait();
-            if (c + 2 < NC && c + 2 < nact) tmem_ld8(s_taddr + (uint32_t)((c + 2) * 32), ta);
-            exp_chunk(c + 1, tb);
-            if (c + 2 < NC && c + 2 < nact) tmem_ld_wait();
-          }
-        }
+            if (c + 1 < N) tmem_ld8(s_taddr + (uint32_t)((c + 1) * 32), tb);
+            {
+              float pe[8];
 #pragma unroll
-        for (int c = 0; c < NC; ++c)             // no visible key: P = 0 (the P V product runs over all Nk columns)
-          if (c >= nact && c < nchunks) sts128(((c & 1) ? p_odd : p_even) + (uint32_t)((c >> 1) * 16384), 0u, 0u, 0u, 0u);
+              for (int e = 0; e < 8; ++e) pe[e] = ex2_approx(fmaf(__uint_as_float(ta[e]), sl2, -mref));
+              finish_chunk(pe, c * 32 + part * 8, p_even + (uint32_t)((c >> 1) * 16384));          // c is even here
+            }
+            if (c + 1 < N) {
+              tmem_ld_wait();
+              if (c + 2 < N) tmem_ld8(s_taddr + (uint32_t)((c + 2) * 32), ta);
+              float pe[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pe[e] = ex2_approx(fmaf(__uint_as_float(tb[e]), sl2, -mref));
+              finish_chunk(pe, (c + 1) * 32 + part * 8, p_odd + (uint32_t)((c >> 1) * 16384));
+            }
+          }
+        });
+#pragma unroll 1
+        for (int c = nfull; c < nchunks; ++c) {
+          const uint32_t dst = ((c & 1) ? p_odd : p_even) + (uint32_t)((c >> 1) * 16384);
+          if (c >= nact) {                       // no visible key: P = 0 (the P V product runs over all Nk columns)
+            sts128(dst, 0u, 0u, 0u, 0u);
+            continue;
+          }
+          tmem_ld8(s_taddr + (uint32_t)(c * 32), ta);
+          tmem_ld_wait();
+          const int k0 = c * 32 + part * 8;
+          float pe[8];
+          if (prefix) {
+            const int n = kmax_row - k0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pe[e] = (e < n) ? ex2_approx(fmaf(__uint_as_float(ta[e]), sl2, -mref)) : 0.f;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pe[e] = visible(k0 + e) ? ex2_approx(fmaf(__uint_as_float(ta[e]), sl2, -mref)) : 0.f;
+          }
+          finish_chunk(pe, k0, dst);
+        }
         redsum[part * 128 + r] = sum;
         fence_proxy_async_smem();
         tc_fence_before();
@@ -932,20 +953,13 @@ int attention_fwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
   p.o = (bf16*)o; p.o_bs = o_bs; p.o_rs = o_rs; p.lse = lse; p.kmask = kmask;
   p.B = B; p.H = H; p.Tq = Tq; p.Sk = Sk; p.Nk = Nk; p.causal = causal; p.scale = scale; p.p_drop = p_drop;
   p.seed = seed; p.offset = offset; p.offset_ptr = rng_offset_ptr;
-  // how many of a thread's 8-key chunks stay in registers between the two softmax passes (the rest is re-read from TMEM);
-  // VLM_ATTN_FWD_KEEP overrides the choice for Nk > 128 (tools/jobs experiments): 0 | 2 | 4 | 7
-  static const int keep_wide = [] {
-    const char* v = getenv("VLM_ATTN_FWD_KEEP");
-    return v ? atoi(v) : 4;
-  }();
   static bool attr_set = false;
   if (!attr_set) {
-    const int big = AtcFwdSmem::total(224);
-    cudaError_t err = cudaFuncSetAttribute(attn_fwd_tc_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtcFwdSmem::total(128));
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(attn_fwd_tc_kernel<7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(attn_fwd_tc_kernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(attn_fwd_tc_kernel<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(attn_fwd_tc_kernel<7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    const int big = AtcFwdSmem::total(224), small = AtcFwdSmem::total(128);
+    cudaError_t err = cudaFuncSetAttribute(attn_fwd_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(attn_fwd_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(attn_fwd_tc_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(attn_fwd_tc_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     if (err != cudaSuccess) {
       set_error("cudaFuncSetAttribute(attn_fwd_tc smem=%d): %s", big, cudaGetErrorString(err));
       return -1;
@@ -955,11 +969,14 @@ int attention_fwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
   const int items = B * H;
   const int grid = items < num_sms() ? items : num_sms();
   const int smem_bytes = AtcFwdSmem::total(Nk);
-  if (Nk <= 128) attn_fwd_tc_kernel<4, 4><<<grid, ATF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
-  else if (keep_wide >= 7) attn_fwd_tc_kernel<7, 7><<<grid, ATF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
-  else if (keep_wide >= 4) attn_fwd_tc_kernel<7, 4><<<grid, ATF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
-  else if (keep_wide >= 2) attn_fwd_tc_kernel<7, 2><<<grid, ATF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
-  else attn_fwd_tc_kernel<7, 0><<<grid, ATF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
+  const bool drop = p_drop > 0.f;
+  if (Nk <= 128) {
+    if (drop) attn_fwd_tc_kernel<4, true><<<grid, ATF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
+    else attn_fwd_tc_kernel<4, false><<<grid, ATF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
+  } else {
+    if (drop) attn_fwd_tc_kernel<7, true><<<grid, ATF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
+    else attn_fwd_tc_kernel<7, false><<<grid, ATF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
+  }
   const int rc = check_launch("attn_fwd_tc");
   return rc ? rc : 1;
 }
