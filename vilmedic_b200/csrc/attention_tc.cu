@@ -49,6 +49,17 @@ __device__ __forceinline__ void tma_load_4d(const void* desc, uint64_t* bar, voi
       : "memory");
 }
 
+// calls f(std::integral_constant<int, n>) for the runtime n in [0, MAXN] — a compare chain, used once per pass and tile
+template <int MAXN, typename F>
+__device__ __forceinline__ void dispatch_count(int n, F&& f) {
+  if constexpr (MAXN == 0) {
+    f(std::integral_constant<int, 0>{});
+  } else {
+    if (n >= MAXN) f(std::integral_constant<int, MAXN>{});
+    else dispatch_count<MAXN - 1>(n, f);
+  }
+}
+
 static constexpr int ATC_SPLIT = 4;                              // compute warps per TMEM lane quadrant (each owns Nq / 4 query columns)
 static constexpr int ATC_THREADS = 64 + 128 * ATC_SPLIT;         // 2 control warps + 16 compute warps
 static constexpr int ATC_S_COL = 0, ATC_DV_COL = 256, ATC_DK_COL = 320, ATC_DQ_COL = 384;
@@ -241,7 +252,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const unsigned long long off_eff = p.offset + ((DROPOUT && p.offset_ptr) ? __ldg(p.offset_ptr) : 0ull);
     const uint32_t thr = (uint32_t)(p.p_drop * 4294967296.0f);
     const float inv_keep = DROPOUT ? 1.f / (1.f - p.p_drop) : 1.f;
-    const int part_cols = Nq / ATC_SPLIT;      // multiple of 8
     const uint32_t pt_row = (uint32_t)(r * 128);   // row offset inside a 64-column atom of the P^T / dS^T tile
     const uint32_t aPTs = smem_u32(sPT), aP2s = smem_u32(sP2), aLse = smem_u32(sLse), aDelta = smem_u32(sDelta);   // shared-space addresses
     const int r7 = r & 7;
@@ -268,60 +278,92 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         // ---------------- pass A: P^T
         mbar_wait(s_full, tph);
         tc_fence_after();
-        // causal: query q sees key kk iff kk <= q.  For this warp's key rows [k_lo, k_lo + 31] a 16-query chunk starting at
-        // q0 is fully visible iff q0 >= k_lo + 31 and fully masked iff q0 + 15 < k_lo; only the chunks on the diagonal test
-        // per element.  Key rows that are padding / masked (kvalid == false) produce zeros without any math.
+        // Query columns are dealt to the ATC_SPLIT warps of a quadrant in 8-query chunks, round robin: chunk c of this thread covers
+        // queries [32 c + 8 part, +8) = one 16-byte unit of the P^T row.  causal: query q sees key kk iff kk <= q, so for this warp's
+        // key rows [k_lo, k_lo + 31] chunk c is fully masked iff q0 + 7 < k_lo (c < c_any), fully visible iff q0 >= k_lo + 31
+        // (c >= c_full) and tests per element only on the diagonal in between.  The fully visible chunks run straight-line code
+        // selected by their COUNT (compile-time offsets relative to the first of them).  Key rows that are padding / masked
+        // (kvalid == false) produce zeros; warps whose 32 key rows are all padding only write zeros.
         const int k_lo = j * 128 + quad * 32;
-        auto pass_a_chunk = [&](const uint32_t* v, int q0) {      // 8 query columns = one 16-byte unit of the P^T row
-          float pv[8], pd[8];
-          if (kvalid && !(p.causal && q0 + 7 < k_lo)) {
-            float ls[8];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float4 t = lds128f(aLse + (uint32_t)((q0 + 4 * i) * 4));
-              ls[4 * i] = t.x; ls[4 * i + 1] = t.y; ls[4 * i + 2] = t.z; ls[4 * i + 3] = t.w;
-            }
-            if (!p.causal || q0 >= k_lo + 31) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -ls[i]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) pv[i] = (kk <= q0 + i) ? ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -ls[i])) : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pv[i] = 0.f;
-          }
+        const int nch = Nq >> 5;                 // chunks per thread
+        int c_any = 0, c_full = 0;
+        if (p.causal) {
+          c_any = (k_lo - 7 - part * 8 + 31) >> 5;             // first c with 32 c + 8 part + 7 >= k_lo
+          c_full = (k_lo + 31 - part * 8 + 31) >> 5;           // first c with 32 c + 8 part >= k_lo + 31
+          c_any = c_any < 0 ? 0 : (c_any > nch ? nch : c_any);
+          c_full = c_full < 0 ? 0 : (c_full > nch ? nch : c_full);
+        }
+        const bool any_valid = __any_sync(0xffffffffu, kvalid);
+        // offsets of chunk c inside the P^T / dS^T tile: 64-query atom c >> 1, 16-byte unit (c & 1) * 4 + part, XOR-swizzled
+        auto pt_off = [&](int c) -> uint32_t {
+          return (uint32_t)((c >> 1) * 16384) + pt_row + (uint32_t)(((((c & 1) << 2) + part) ^ r7) << 4);
+        };
+        const uint32_t s_col = lane_taddr + ATC_S_COL + (uint32_t)(part * 8);
+        uint32_t va[8], vb[8];
+        auto store_p = [&](float (&pv)[8], int q0, uint32_t off) {
           if (DROPOUT) {
+            float pd[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) pd[i] = attn_drop_rand(dkey, q0 + i, kk, p.Sk) >= thr ? pv[i] * inv_keep : 0.f;
-          }
-          const uint32_t off = (uint32_t)((q0 >> 6) * 16384) + pt_row + (uint32_t)((((q0 & 63) >> 3) ^ r7) << 4);
-          if (DROPOUT)
             sts128(aPTs + off, pack_bf16x2(pd[0], pd[1]), pack_bf16x2(pd[2], pd[3]), pack_bf16x2(pd[4], pd[5]), pack_bf16x2(pd[6], pd[7]));
+          }
           sts128((DROPOUT ? aP2s : aPTs) + off, pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]),
                  pack_bf16x2(pv[6], pv[7]));
         };
-        // key rows beyond Sk (the tail of the last key tile: 59 of 256 rows at Sk = 197) or masked for the whole warp: zeros, no math
-        const bool any_valid = __any_sync(0xffffffffu, kvalid);
-        if (any_valid) {  // TMEM loads are software-pipelined: the next chunk is in flight while the current one is processed
-          const int qbase = part * part_cols;
-          uint32_t va[8], vb[8];
-          tmem_ld8(lane_taddr + ATC_S_COL + qbase, va);
-          for (int c = 0; c < part_cols; c += 16) {
-            tmem_ld_wait();
-            if (c + 8 < part_cols) tmem_ld8(lane_taddr + ATC_S_COL + qbase + c + 8, vb);
-            pass_a_chunk(va, qbase + c);
-            if (c + 8 < part_cols) {
-              tmem_ld_wait();
-              if (c + 16 < part_cols) tmem_ld8(lane_taddr + ATC_S_COL + qbase + c + 16, va);
-              pass_a_chunk(vb, qbase + c + 8);
+        if (any_valid) {
+          // ---- masked and diagonal chunks (causal only)
+#pragma unroll 1
+          for (int c = 0; c < c_full; ++c) {
+            const int q0 = c * 32 + part * 8;
+            const uint32_t off = pt_off(c);
+            float pv[8];
+            if (c < c_any) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pv[i] = 0.f;
+              sts128(aPTs + off, 0u, 0u, 0u, 0u);
+              if (DROPOUT) sts128(aP2s + off, 0u, 0u, 0u, 0u);
+              continue;
             }
+            tmem_ld8(s_col + (uint32_t)(c * 32), va);
+            const float4 l0 = lds128f(aLse + (uint32_t)(q0 * 4)), l1 = lds128f(aLse + (uint32_t)(q0 * 4 + 16));
+            const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              pv[i] = (kvalid && kk <= q0 + i) ? ex2_approx(fmaf(__uint_as_float(va[i]), sl2, -ls[i])) : 0.f;
+            store_p(pv, q0, off);
           }
+          // ---- fully visible chunks [c_full, nch): straight-line, TMEM loads two deep
+          const uint32_t colb = s_col + (uint32_t)(c_full * 32);
+          const uint32_t lseb = aLse + (uint32_t)((c_full * 32 + part * 8) * 4);
+          const int q0b = c_full * 32 + part * 8;
+          const uint32_t off0 = pt_off(c_full), off1 = pt_off(c_full + 1);
+          dispatch_count<ATOMS * 2>(nch - c_full, [&](auto nconst) {
+            constexpr int N = decltype(nconst)::value;
+            auto body = [&](const uint32_t* v, int i) {
+              const float4 l0 = lds128f(lseb + (uint32_t)(i * 128)), l1 = lds128f(lseb + (uint32_t)(i * 128 + 16));
+              const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+              float pv[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pv[e] = kvalid ? ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -ls[e])) : 0.f;
+              store_p(pv, q0b + i * 32, ((i & 1) ? off1 : off0) + (uint32_t)((i >> 1) * 16384));
+            };
+            if (N > 0) tmem_ld8(colb, va);
+#pragma unroll
+            for (int i = 0; i < N; i += 2) {
+              tmem_ld_wait();
+              if (i + 1 < N) tmem_ld8(colb + (uint32_t)((i + 1) * 32), vb);
+              body(va, i);
+              if (i + 1 < N) {
+                tmem_ld_wait();
+                if (i + 2 < N) tmem_ld8(colb + (uint32_t)((i + 2) * 32), va);
+                body(vb, i + 1);
+              }
+            }
+          });
         } else {
-          for (int c = 0; c < part_cols; c += 8) {
-            const int q0 = part * part_cols + c;
-            const uint32_t off = (uint32_t)((q0 >> 6) * 16384) + pt_row + (uint32_t)((((q0 & 63) >> 3) ^ r7) << 4);
+          for (int c = 0; c < nch; ++c) {
+            const uint32_t off = pt_off(c);
             sts128(aPTs + off, 0u, 0u, 0u, 0u);          // P^T = 0  =>  dS^T = 0 as well: pass B leaves these rows alone
             if (DROPOUT) sts128(aP2s + off, 0u, 0u, 0u, 0u);
           }
@@ -336,45 +378,48 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tc_fence_after();
         // dS^T = P^T * (dP^T - delta) — the softmax scale is applied once per dK / dQ output element in the epilogue instead
         // of once per score element here.
-        auto pass_b_chunk = [&](const uint32_t* v, int q0) {
-          float dl[8];
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const float4 t = lds128f(aDelta + (uint32_t)((q0 + 4 * i) * 4));
-            dl[4 * i] = t.x; dl[4 * i + 1] = t.y; dl[4 * i + 2] = t.z; dl[4 * i + 3] = t.w;
-          }
-          const uint32_t off = (uint32_t)((q0 >> 6) * 16384) + pt_row + (uint32_t)((((q0 & 63) >> 3) ^ r7) << 4);
-          const uint4 pw = lds128u((DROPOUT ? aP2s : aPTs) + off);
-          uint4 kw = pw;
-          if (DROPOUT) kw = lds128u(aPTs + off);   // dropped P: zero <=> dropped (or P == 0)
-          const uint32_t pw4[4] = {pw.x, pw.y, pw.z, pw.w}, kw4[4] = {kw.x, kw.y, kw.z, kw.w};
-          uint32_t ow[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 pp = unpack_bf16x2(pw4[e]), kp = unpack_bf16x2(kw4[e]);
-            float d0 = __uint_as_float(v[2 * e]), d1 = __uint_as_float(v[2 * e + 1]);
-            if (DROPOUT) {
-              d0 = kp.x != 0.f ? d0 * inv_keep : 0.f;
-              d1 = kp.y != 0.f ? d1 * inv_keep : 0.f;
-            }
-            ow[e] = pack_bf16x2(pp.x * (d0 - dl[2 * e]), pp.y * (d1 - dl[2 * e + 1]));
-          }
-          sts128(aPTs + off, ow[0], ow[1], ow[2], ow[3]);
-        };
+        // Chunks [0, c_any) hold P^T = 0 (fully masked): dS^T = 0 is already there.  The rest is one straight-line sequence
+        // selected by its length.
         if (any_valid) {
-          const int qbase = part * part_cols;
-          uint32_t va[8], vb[8];
-          tmem_ld8(lane_taddr + ATC_S_COL + qbase, va);
-          for (int c = 0; c < part_cols; c += 16) {
-            tmem_ld_wait();
-            if (c + 8 < part_cols) tmem_ld8(lane_taddr + ATC_S_COL + qbase + c + 8, vb);
-            pass_b_chunk(va, qbase + c);
-            if (c + 8 < part_cols) {
+          const uint32_t colb = s_col + (uint32_t)(c_any * 32);
+          const uint32_t delb = aDelta + (uint32_t)((c_any * 32 + part * 8) * 4);
+          const uint32_t off0 = pt_off(c_any), off1 = pt_off(c_any + 1);
+          dispatch_count<ATOMS * 2>(nch - c_any, [&](auto nconst) {
+            constexpr int N = decltype(nconst)::value;
+            auto body = [&](const uint32_t* v, int i) {
+              const float4 d0 = lds128f(delb + (uint32_t)(i * 128)), d1 = lds128f(delb + (uint32_t)(i * 128 + 16));
+              const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+              const uint32_t off = ((i & 1) ? off1 : off0) + (uint32_t)((i >> 1) * 16384);
+              const uint4 pw = lds128u((DROPOUT ? aP2s : aPTs) + off);
+              uint4 kw = pw;
+              if (DROPOUT) kw = lds128u(aPTs + off);   // dropped P: zero <=> dropped (or P == 0)
+              const uint32_t pw4[4] = {pw.x, pw.y, pw.z, pw.w}, kw4[4] = {kw.x, kw.y, kw.z, kw.w};
+              uint32_t ow[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 pp = unpack_bf16x2(pw4[e]), kp = unpack_bf16x2(kw4[e]);
+                float x0 = __uint_as_float(v[2 * e]), x1 = __uint_as_float(v[2 * e + 1]);
+                if (DROPOUT) {
+                  x0 = kp.x != 0.f ? x0 * inv_keep : 0.f;
+                  x1 = kp.y != 0.f ? x1 * inv_keep : 0.f;
+                }
+                ow[e] = pack_bf16x2(pp.x * (x0 - dl[2 * e]), pp.y * (x1 - dl[2 * e + 1]));
+              }
+              sts128(aPTs + off, ow[0], ow[1], ow[2], ow[3]);
+            };
+            if (N > 0) tmem_ld8(colb, va);
+#pragma unroll
+            for (int i = 0; i < N; i += 2) {
               tmem_ld_wait();
-              if (c + 16 < part_cols) tmem_ld8(lane_taddr + ATC_S_COL + qbase + c + 16, va);
-              pass_b_chunk(vb, qbase + c + 8);
+              if (i + 1 < N) tmem_ld8(colb + (uint32_t)((i + 1) * 32), vb);
+              body(va, i);
+              if (i + 1 < N) {
+                tmem_ld_wait();
+                if (i + 2 < N) tmem_ld8(colb + (uint32_t)((i + 2) * 32), va);
+                body(vb, i + 1);
+              }
             }
-          }
+          });
         }
         fence_proxy_async_smem();
         tc_fence_before();
@@ -567,17 +612,6 @@ struct AtcFwdSmem {
 //   MMA warp   : S(0), S(1); then for every t: wait P(t) -> O = P V (TMEM cols [2 Nk, 2 Nk + 64)) -> S(t+2) into the S buffer
 //                t&1 that the softmax of tile t has just drained.  So S(t+1) is always complete when the softmax warps get to it.
 //   softmax    : pass 1 (row max) of tile t, then the EPILOGUE OF TILE t-1 (its P V ran under pass 1), then pass 2 (P -> smem).
-// calls f(std::integral_constant<int, n>) for the runtime n in [0, MAXN] — a compare chain, used once per pass and tile
-template <int MAXN, typename F>
-__device__ __forceinline__ void dispatch_count(int n, F&& f) {
-  if constexpr (MAXN == 0) {
-    f(std::integral_constant<int, 0>{});
-  } else {
-    if (n >= MAXN) f(std::integral_constant<int, MAXN>{});
-    else dispatch_count<MAXN - 1>(n, f);
-  }
-}
-
 template <int NC, bool DROPOUT>
 __global__ void __launch_bounds__(ATF_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
