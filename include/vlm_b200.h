@@ -25,6 +25,11 @@ extern "C" {
 /* ---- runtime ---------------------------------------------------------------------------------------------------- */
 const char* vlm_last_error(void);
 int vlm_abi_version(void);
+/* SMs that every persistent kernel of this library leaves free (grid = SM count - margin) for concurrent work such as the NCCL
+ * kernels of the data-parallel gradient exchange (vilmedic_b200/ddp.py).  Default: env VLM_SM_MARGIN, else 0.  Set it before a
+ * CUDA graph is captured — grid sizes are baked into the graph. */
+int vlm_set_sm_margin(int margin);
+int vlm_get_sm_margin(void);
 /* 0 iff the current CUDA device is sm_100 (B200). */
 int vlm_device_check(void);
 

@@ -3,6 +3,7 @@
 #include "vlm_b200.h"
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 
 namespace vlm {
 
@@ -24,7 +25,21 @@ int check_launch(const char* what) {
   return 0;
 }
 
-int num_sms() {
+// SMs left to other work (the NCCL kernels of the data-parallel exchange): every persistent grid is sized num_sms() = SM count -
+// margin.  A persistent kernel with a static tile schedule whose CTAs cannot all be resident runs a second wave — leaving a few
+// SMs free costs margin/148 of the compute instead.  Default: env VLM_SM_MARGIN (0); vlm_set_sm_margin() overrides.
+static int g_sm_margin = -1;
+
+int sm_margin() {
+  if (g_sm_margin < 0) {
+    const char* v = getenv("VLM_SM_MARGIN");
+    int m = v ? atoi(v) : 0;
+    g_sm_margin = (m < 0 || m > 64) ? 0 : m;
+  }
+  return g_sm_margin;
+}
+
+static int num_sms_physical() {
   static int cached[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -37,11 +52,24 @@ int num_sms() {
   return cached[dev];
 }
 
+int num_sms() { return num_sms_physical() - sm_margin(); }
+
 }  // namespace vlm
 
 extern "C" const char* vlm_last_error(void) { return vlm::g_err; }
 
 extern "C" int vlm_abi_version(void) { return VLM_B200_ABI_VERSION; }
+
+extern "C" int vlm_set_sm_margin(int margin) {
+  if (margin < 0 || margin > 64) {
+    vlm::set_error("vlm_set_sm_margin: margin must be in [0, 64], got %d", margin);
+    return -1;
+  }
+  vlm::g_sm_margin = margin;
+  return 0;
+}
+
+extern "C" int vlm_get_sm_margin(void) { return vlm::sm_margin(); }
 
 extern "C" int vlm_device_check(void) {
   int dev = 0;
