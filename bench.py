@@ -318,7 +318,7 @@ def run_ours(args):
     devb = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values() if isinstance(v, torch.Tensor))
     from vilmedic_b200.ddp import GradSync
-    sync = GradSync(arena).attach()       # per-layer gradient buckets, launched from the backward pass (ddp.py)
+    sync = GradSync(arena, optimizer=opt).attach()       # per-layer gradient buckets, launched from the backward pass (ddp.py)
 
     # DIAGNOSTIC ONLY (tools/jobs): VLM_BENCH_NO_EXCHANGE=1 times the N-rank step WITHOUT the gradient all-reduce, to split the
     # multi-GPU loss into "exchange" and "everything else"; the printed line is marked invalid.
@@ -340,7 +340,7 @@ def run_ours(args):
         finally:
             vnn.GRAD_READY_HOOK[0] = hook
         if exchange:
-            opt.step(grad_scale=sync.finish(), grad16=sync.grad16)
+            sync.step(opt)              # gradient exchange + fused optimizer, bucket by bucket under the backward pass (ddp.py)
         else:
             opt.step(grad_scale=1.0)
         if read_loss:
@@ -578,7 +578,7 @@ def run_other_workload(args):
     model = executors.create_model(tcfg, dl).train()
     opt = executors.create_optimizer(tcfg, None, model)
     arena = get_arena(model)
-    sync = GradSync(arena).attach()
+    sync = GradSync(arena, optimizer=opt).attach()
     host = next(iter(dl))
     host = {k: v for k, v in host.items() if v is not None}
     devb = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
@@ -587,7 +587,7 @@ def run_other_workload(args):
     def train_step(batch):
         out = model(**batch)
         out["loss"].backward()
-        opt.step(grad_scale=sync.finish(), grad16=sync.grad16)
+        sync.step(opt)
         return out["loss"]
 
     # eager warm-up on the side stream the graph will be captured on (autograd ties a leaf's gradient accumulation to the stream of

@@ -40,11 +40,13 @@ def main():
     shard = {k: (v[rank * b:(rank + 1) * b].to(dev) if isinstance(v, torch.Tensor) else v) for k, v in full.items()}
 
     model, arena, opt = make()
-    sync = GradSync(arena, bucket_bytes=8 << 20).attach()      # per-layer buckets launched from the backward pass
+    # per-layer buckets launched from the backward pass; VLM_DDP_PIPELINE=1: optimizer update pipelined behind each bucket
+    pipe = os.environ.get("VLM_DDP_PIPELINE") == "1"
+    sync = GradSync(arena, bucket_bytes=8 << 20, optimizer=opt if pipe else None).attach()
     out = model(**shard)
     out["loss"].backward()
     early = sync.launches
-    opt.step(grad_scale=sync.finish(), grad16=sync.grad16)
+    sync.step(opt)
     sync.detach()
     torch.cuda.synchronize()
     assert early >= 2, "no gradient bucket was launched during the backward pass"

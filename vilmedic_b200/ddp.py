@@ -1,19 +1,29 @@
-"""Data-parallel gradient exchange for the flat arena: one process per GPU, NCCL all-reduce (SUM) over
-`flat_grad`, bucketed PER TRANSFORMER LAYER and launched from the backward pass itself: every layer's parameters occupy one
+"""Gradient exchange + optimizer pipeline for the flat arena: one process per GPU, NCCL all-reduce (SUM)
+over `flat_grad`, bucketed PER TRANSFORMER LAYER and launched from the backward pass itself: every layer's parameters occupy one
 contiguous span of the arena (arena.module_spans), the hand-written backward of a layer announces "gradients of this span are
 final" (nn.notify_grad_ready) and the exchange of that span starts on NCCL's stream while the backward of the layers below is
 still computing.  Spans arrive in descending address order (the backward walks the model in reverse), so adjacent spans are
 merged until a bucket reaches `bucket_bytes`; only the last bucket (patch embedding + whatever nobody announced) is exposed.
+
 Payload: bf16 by default — a cast kernel writes the bucket into `grad16` right before its all-reduce and the fused optimizer
 reads the reduced values from there (optim.FusedOptimizer.step(grad16=...)), so the exchange moves 2 B per parameter instead of 4
-and no widening pass exists.  Measured on 2 x B200 (round 2, tools/jobs/r2m.sh): the NCCL kernels cannot share an SM with the
-persistent one-CTA-per-SM GEMM / attention kernels, so the exchange time adds to the step almost 1:1 (24.33 ms vs 22.87 ms without
-any exchange; fewer NCCL channels make it worse: 26.3 ms at 4, 33.8 ms at 2; the bucket size does not matter) — bytes are what
-counts.  `payload="fp32"` (or VLM_DDP_PAYLOAD=fp32) keeps the reference's fp32 DDP all-reduce bit for bit.
-The 1/world factor is folded into the fused optimizer step (grad_scale).  No activation collectives: every pair is independent,
-contrastive negatives are rank-local as in the reference (vilmedic/executors/trainor_accelerate.py:122,132).
-Round 1 sent two unbucketed spans and launched the encoder one after the backward had ended (fully exposed: the whole 6 % loss of
-the 1 -> 8 curve)."""
+and no widening pass exists.  `payload="fp32"` (or VLM_DDP_PAYLOAD=fp32) keeps the reference's fp32 DDP all-reduce bit for bit
+(vilmedic/executors/trainor_accelerate.py:122,132).  The 1/world factor is folded into the fused optimizer step (grad_scale).
+No activation collectives: every pair is independent, contrastive negatives are rank-local as in the reference.
+
+Pipelined optimizer (`optimizer=` given, no global-norm clipping): the fused optimizer update of a bucket is issued on a side
+stream right behind that bucket's all-reduce, i.e. UNDER the backward pass of the layers below — the update is pure HBM traffic
+(30 B per parameter, 1.15 ms for the 223 M parameters of the RRG model when run alone at the end of the step) and its thread
+blocks fit next to the one-CTA-per-SM GEMM kernels.  This also works, and pays, on ONE GPU (no exchange, just the update).
+Safe because a layer announces its span only after its own dgrad/wgrad kernels were issued (stream order), tied parameters live
+in the span of the module that is announced last (the embedding table: LM-head wgrad first, embedding scatter last), and the
+forward of the next step starts after `step()` has joined the side stream.
+
+What was measured on 2 x B200 (round 2, tools/jobs/r2m.sh, r2t.sh, r2u.sh): the NCCL kernels (32 channels = 32 CTAs) cannot share
+an SM with the persistent one-CTA-per-SM GEMM / attention kernels; 22.45 ms without any exchange, 23.87 ms with the fp32 payload,
+23.69 ms with bf16, fewer channels are worse (4: 26.3 ms, 2: 33.8 ms with fp32), the bucket size does not matter (8 / 32 / 128 MB
+within 0.1 ms), leaving 4 SMs free for 4 high-priority channels gives 23.42 ms (VLM_SM_MARGIN, NCCL_MAX_NCHANNELS).
+Round 1 sent two unbucketed fp32 spans and launched the encoder one after the backward had ended."""
 import os
 
 import torch
@@ -23,7 +33,7 @@ from . import nn as _nn
 
 
 class GradSync:
-    def __init__(self, arena, group=None, bucket_bytes=None, payload=None):
+    def __init__(self, arena, group=None, bucket_bytes=None, payload=None, optimizer=None):
         if payload is None:
             payload = os.environ.get("VLM_DDP_PAYLOAD", "bf16")
         if payload not in ("bf16", "fp32"):
@@ -36,34 +46,64 @@ class GradSync:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.pending = []
-        self.sent = []                  # [lo, hi) element ranges already handed to NCCL this step
+        self.sent = []                  # [lo, hi) element ranges already handed to NCCL / the optimizer this step
         self.run = None                 # the current run of adjacent announced spans [lo, hi)
         self.launches = 0
         # bf16 exchange buffer (one slot per arena element); None when nothing is exchanged or the payload is fp32
         self.grad16 = None
         if self.world > 1 and payload == "bf16":
             self.grad16 = torch.zeros(arena.numel, device=arena.flat_grad.device, dtype=torch.bfloat16)
+        # pipelined optimizer: needs every decision of the update to be local to a span (no global gradient norm)
+        self.opt = None
+        if optimizer is not None and os.environ.get("VLM_PIPELINE_OPTIMIZER", "1") != "0" and not optimizer.needs_global_norm() \
+                and arena.flat_grad.is_cuda:
+            self.opt = optimizer
+            self.side = torch.cuda.Stream(device=arena.flat_grad.device)
+            self._begun = False
+
+    @property
+    def pipelined(self):
+        return self.opt is not None
 
     # ---- wiring: the backward functions call nn.notify_grad_ready(module) -> on_ready
     def attach(self):
-        _nn.GRAD_READY_HOOK[0] = self.on_ready if self.world > 1 else None
+        _nn.GRAD_READY_HOOK[0] = self.on_ready if (self.world > 1 or self.pipelined) else None
         return self
 
     def detach(self):
         if _nn.GRAD_READY_HOOK[0] == self.on_ready:
             _nn.GRAD_READY_HOOK[0] = None
 
-    def _launch(self, lo, hi):
-        if hi <= lo:
-            return
-        self.sent.append((lo, hi))
-        self.launches += 1
+    def _exchange(self, lo, hi):
+        """cast (bf16 payload) + async all-reduce of [lo, hi) issued from the CURRENT stream; returns the work handle."""
         if self.grad16 is not None:
             buf = self.grad16[lo:hi]
             self._cast(self.arena.flat_grad[lo:hi], buf)
         else:
             buf = self.arena.flat_grad[lo:hi]
-        self.pending.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _launch(self, lo, hi):
+        if hi <= lo:
+            return
+        self.sent.append((lo, hi))
+        self.launches += 1
+        if not self.pipelined:
+            if self.world > 1:
+                self.pending.append(self._exchange(lo, hi))
+            return
+        # pipelined: the exchange is issued from the main stream (NCCL's stream waits for the kernels that produced these
+        # gradients), the update of the bucket runs on the side stream behind it — neither blocks the backward pass
+        work = self._exchange(lo, hi) if self.world > 1 else None
+        if work is None:
+            self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            if work is not None:
+                work.wait()                             # side stream waits for NCCL's stream; the host does not
+            if not self._begun:
+                self.opt.begin_step()
+                self._begun = True
+            self.opt.step_range(lo, hi, grad_scale=1.0 / self.world, grad16=self.grad16)
 
     @staticmethod
     def _cast(src, dst):
@@ -75,7 +115,7 @@ class GradSync:
 
     def on_ready(self, module):
         span = self.arena.module_spans.get(id(module))
-        if span is None or self.world == 1:
+        if span is None or not (self.world > 1 or self.pipelined):
             return
         lo, hi = span
         if self.run is not None and hi == self.run[0]:
@@ -92,7 +132,7 @@ class GradSync:
 
     def launch_span(self, name):
         """Asynchronously all-reduce the whole gradient span of top-level child `name` (kept for callers that bucket by tower)."""
-        if self.world == 1 or name not in self.arena.child_spans:
+        if not (self.world > 1 or self.pipelined) or name not in self.arena.child_spans:
             return
         lo, hi = self.arena.child_spans[name]
         for a, b in self._uncovered(lo, hi):
@@ -113,8 +153,9 @@ class GradSync:
     def finish(self):
         """All-reduce whatever has not been sent yet, wait for everything; returns the grad scale for the optimizer.
         With the bf16 payload the reduced gradients are in `self.grad16` (pass it on: opt.step(grad_scale=..., grad16=sync.grad16));
-        `flat_grad` keeps the rank-local fp32 values until the optimizer zeroes it."""
-        if self.world > 1:
+        `flat_grad` keeps the rank-local fp32 values until the optimizer zeroes it.  In pipelined mode this also issues the update
+        of the leftover ranges and joins the side stream: the optimizer step is complete when it returns (use step())."""
+        if self.world > 1 or self.pipelined:
             if self.run is not None:
                 self._launch(*self.run)
                 self.run = None
@@ -122,7 +163,22 @@ class GradSync:
                 self._launch(lo, hi)
             for w in self.pending:
                 w.wait()
+            if self.pipelined:
+                torch.cuda.current_stream().wait_stream(self.side)
+                self._begun = False
         self.pending = []
         self.sent = []
         self.run = None
         return 1.0 / self.world
+
+    def step(self, optimizer, loss=None):
+        """finish() + the optimizer step, whichever way it is scheduled — the call a training loop makes after backward()."""
+        if self.pipelined:
+            if optimizer is not self.opt:
+                raise ValueError("GradSync.step: this GradSync pipelines a different optimizer")
+            if loss is not None:
+                raise NotImplementedError("device-side loss skip needs the whole-arena step: build GradSync without optimizer=")
+            self.finish()
+            return
+        scale = self.finish()
+        optimizer.step(grad_scale=scale, loss=loss, grad16=self.grad16)

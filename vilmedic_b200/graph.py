@@ -40,8 +40,10 @@ class GraphedTrainStep:
         out = self.model(**batch)
         loss = out["loss"]
         loss.backward()
-        scale = self.sync.finish() if self.sync is not None else 1.0
-        self.opt.step(grad_scale=scale, grad16=self.sync.grad16 if self.sync is not None else None)
+        if self.sync is not None:
+            self.sync.step(self.opt)          # exchange + update, bucket by bucket under the backward pass when pipelined (ddp.py)
+        else:
+            self.opt.step()
         return loss
 
     # ---- input prefetch: the next step's batch travels host -> device on a copy stream while the current step computes ----

@@ -77,6 +77,14 @@ class FusedOptimizer(torch.optim.Optimizer):
         """loss: optional 0-dim fp32 CUDA tensor — a NaN/Inf value skips the step on the device (no host sync).
         grad16: optional bf16 tensor [arena.numel] holding the (all-reduced) gradient values — the exchange payload of
         ddp.GradSync; the fp32 gradient buffer is then only zeroed."""
+        a = self.arena
+        self.begin_step(loss=loss, grad16=grad16)
+        self.step_range(0, a.numel, grad_scale=grad_scale, grad16=grad16)
+
+    @torch.no_grad()
+    def begin_step(self, loss=None, grad16=None):
+        """First half of step(): global gradient norm (when clipping / skipping is on) and the step counter.  The second half,
+        step_range(), may then be issued span by span — ddp.GradSync does that from the backward pass, bucket by bucket."""
         g = self.param_groups[0]
         a = self.arena
         L = _lib.lib()
@@ -95,16 +103,36 @@ class FusedOptimizer(torch.optim.Optimizer):
             self.gnorm_sq.zero_()
             for lo, hi in self.spans:
                 ops.sumsq((grad16 if grad16 is not None else a.flat_grad)[lo:hi], self.gnorm_sq)
-        gn_p = ptr(self.gnorm_sq) if want_norm else None
-        ops.check(L.vlm_optim_step_begin(ptr(self.step_t), gn_p, loss_p, ptr(self.skipped_steps), stream_ptr()), "vlm_optim_step_begin")
-        for lo, hi in self.spans:
-            ops.check(L.vlm_optim_step(c_int(self.kind), ptr(a.flat[lo:hi]), ptr(a.flat_grad[lo:hi]), ptr(self.m[lo:hi]),
-                                       ptr(self.v[lo:hi]), ptr(a.flat_bf16[lo:hi]), c_ll(hi - lo), c_float(g["lr"]),
+        self._gn_p = ptr(self.gnorm_sq) if want_norm else None
+        self._loss_p = loss_p
+        self._loss_ref = loss                  # keep the tensor alive until the span launches have been issued
+        ops.check(L.vlm_optim_step_begin(ptr(self.step_t), self._gn_p, loss_p, ptr(self.skipped_steps), stream_ptr()), "vlm_optim_step_begin")
+
+    def needs_global_norm(self):
+        """True when step() has to see ALL gradients before it may touch any parameter (global-norm clipping)."""
+        return (self.param_groups[0]["max_grad_norm"] or 0.0) > 0
+
+    @torch.no_grad()
+    def step_range(self, lo, hi, grad_scale=1.0, grad16=None):
+        """Update the trainable parameters inside arena elements [lo, hi) (begin_step() must have run for this step)."""
+        g = self.param_groups[0]
+        a = self.arena
+        L = _lib.lib()
+        max_norm = g["max_grad_norm"] or 0.0
+        for slo, shi in self.spans:
+            x, y = max(lo, slo), min(hi, shi)
+            if y <= x:
+                continue
+            ops.check(L.vlm_optim_step(c_int(self.kind), ptr(a.flat[x:y]), ptr(a.flat_grad[x:y]), ptr(self.m[x:y]),
+                                       ptr(self.v[x:y]), ptr(a.flat_bf16[x:y]), c_ll(y - x), c_float(g["lr"]),
                                        c_float(g["betas"][0]), c_float(g["betas"][1]), c_float(g["eps"]), c_float(g["weight_decay"]),
-                                       ptr(self.step_t), ptr(self.lr_scale), c_float(grad_scale), gn_p, c_float(max_norm), loss_p,
-                                       c_int(1), ptr(grad16[lo:hi]) if grad16 is not None else None, stream_ptr()), "vlm_optim_step")
-        for lo, hi in self.frozen_spans:        # backward kernels may have accumulated into frozen slots: clear, never apply
-            a.flat_grad[lo:hi].zero_()
+                                       ptr(self.step_t), ptr(self.lr_scale), c_float(grad_scale), self._gn_p, c_float(max_norm),
+                                       self._loss_p, c_int(1), ptr(grad16[x:y]) if grad16 is not None else None, stream_ptr()),
+                      "vlm_optim_step")
+        for slo, shi in self.frozen_spans:      # backward kernels may have accumulated into frozen slots: clear, never apply
+            x, y = max(lo, slo), min(hi, shi)
+            if y > x:
+                a.flat_grad[x:y].zero_()
         a.mirror_clean = True
 
     def zero_grad(self, set_to_none=False):
