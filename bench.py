@@ -500,6 +500,12 @@ def run_ours(args):
                 gpu_base = {"error": str(e).splitlines()[0][:200]}
                 torch.cuda.synchronize()
 
+    # peer-memory transport: the device-side error flag of every rank (bounded waits, csrc/p2p.cu) must be clear
+    px_err = False
+    if world > 1 and sync.px is not None:
+        t = torch.tensor([int(sync.px.err.item())], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        px_err = int(t.item()) != 0
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -510,6 +516,10 @@ def run_ours(args):
                        "global_batch": world * B, "seq_len": T, "parallelism": "dp%d" % world,
                        "l2": "per-step working set (activations ~4 GB + 1.3 GB weights/grads) >> 126 MB L2; no explicit flush",
                        "launch": graph_note,
+                       "grad_exchange": ("none (1 GPU)" if world == 1 else
+                                         ("peer memory: every rank's optimizer kernel reads all ranks' bf16 gradient buckets over NVLink "
+                                          "(csrc/p2p.cu), no collective in the step" if sync.transport == "p2p" else
+                                          "NCCL all-reduce, %s payload, per-layer buckets under the backward pass" % sync.payload)),
                        "loss_last": float(last_loss) if last_loss is not None else None},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                     "how": e2e_note},
@@ -523,6 +533,8 @@ def run_ours(args):
         }
         if no_exchange:
             line["invalid"] = "VLM_BENCH_NO_EXCHANGE=1: gradient all-reduce skipped (diagnostic run, not a bench value)"
+        if px_err:
+            line["invalid"] = "peer-memory exchange: a wait on a peer flag timed out on some rank (csrc/p2p.cu) — not a bench value"
         print(json.dumps(line))
     if world > 1:
         # destroy_process_group() blocks forever here (both ranks, observed on 2 x B200 with torch 2.11 / NCCL 2.28): the

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define VLM_B200_ABI_VERSION 3
+#define VLM_B200_ABI_VERSION 4
 
 /* ---- runtime ---------------------------------------------------------------------------------------------------- */
 const char* vlm_last_error(void);
@@ -30,6 +30,10 @@ int vlm_abi_version(void);
  * CUDA graph is captured — grid sizes are baked into the graph. */
 int vlm_set_sm_margin(int margin);
 int vlm_get_sm_margin(void);
+/* Background mode (process-wide flag, returns the previous value): while on, vlm_optim_step and vlm_colsum_bf16 launch as many
+ * small CTAs (128 threads, few registers) that fit on an SM next to a resident persistent GEMM / attention CTA — for work the
+ * host issues on a side stream under the backward pass (vilmedic_b200/ddp.py, nn.py). Results are identical in either mode. */
+int vlm_set_background(int on);
 /* 0 iff the current CUDA device is sm_100 (B200). */
 int vlm_device_check(void);
 
@@ -332,6 +336,40 @@ int vlm_optim_step(int kind, float* p, float* g, float* m, float* v, void* p_bf1
                    float beta2, float eps, float weight_decay, const int* step_ptr, const float* lr_scale_ptr, float grad_scale,
                    const float* gnorm_sq_ptr, float max_norm, const float* loss_ptr, int zero_grad, const void* g_bf16,
                    void* stream);
+
+/* ---- data-parallel gradient exchange over peer memory (NVLink / NVSwitch), fused into the optimizer ----------------- */
+/* Replaces the NCCL all-reduce of DistributedDataParallel / accelerate (vilmedic/executors/trainor_accelerate.py:122,132) followed
+ * by torch.optim.step (vilmedic/executors/trainor.py:119-124): every rank publishes the bf16 cast of a gradient bucket in a buffer
+ * its peers have mapped with CUDA IPC and raises READY[bucket][rank] = epoch in every rank's flag block; vlm_optim_step_p2p polls
+ * the `world` READY flags of its bucket in LOCAL memory, then reads the bucket of every rank with peer loads, sums in fp32 in rank
+ * order (replicas stay bit-identical) and applies the update of vlm_optim_step in the same pass.  Flag block of a rank: int32
+ * [slots][world].  Epoch: device int, advanced once per step (vlm_p2p_epoch_inc) so that the step replays as a CUDA graph.
+ * Waits are bounded (20 s): on expiry *err_flag is set to 1 and the kernel returns without touching the parameters.
+ *   vlm_ipc_alloc  cudaMalloc (zero-filled) + the 64-byte cudaIpcMemHandle_t of the allocation
+ *   vlm_ipc_open   map a peer's allocation into this process (peer access enabled lazily); vlm_ipc_close unmaps it
+ *   vlm_p2p_signal flags[w][slot][rank] = *epoch for every rank w (system-scope release after a fence); peer_flags = host array of
+ *                  `world` device pointers;  vlm_p2p_wait: until my flags[slot][w] >= *epoch + epoch_delta for all w */
+int vlm_ipc_alloc(long long bytes, void** dev_ptr, void* handle64);
+int vlm_ipc_open(const void* handle64, void** dev_ptr);
+int vlm_ipc_close(void* dev_ptr);
+int vlm_ipc_free(void* dev_ptr);
+int vlm_p2p_epoch_inc(int* epoch_ptr, void* stream);
+int vlm_p2p_signal(void* const* peer_flags, int world, int rank, int slot, const int* epoch_ptr, void* stream);
+int vlm_p2p_wait(const int* my_flags, int world, int slot, const int* epoch_ptr, int epoch_delta, int* err_flag, void* stream);
+/* peer_g16: host array of `world` device pointers to every rank's bf16 gradient buffer (whole arena); elem_offset: first element
+ * of this span in those buffers (multiple of 4); p/g/m/v/p_bf16 point at the span itself.  No clipping / loss skip on this path.
+ * One-shot (peer_r32 == NULL): the kernel sums the `world` bf16 buckets itself — (N-1) * 2 bytes per parameter over NVLink.
+ * Two-shot (peer_r32 = host array of every rank's fp32 buffer of reduced slices): vlm_p2p_reduce_slice has summed this rank's slice
+ * of the bucket (units of 4 elements [rank * units_per_rank, ...) counted from the bucket start) into its own fp32 buffer and
+ * raised the bucket's REDUCED flag; the update kernel waits for the REDUCED flags (`slot`) and reads unit i of the span from rank
+ * (unit_base + i) / units_per_rank (unit_base = span start - bucket start, in units) — (N-1)/N * 6 bytes per parameter. */
+int vlm_p2p_reduce_slice(const void* const* peer_g16, long long elem_offset, float* out, long long n, int world,
+                         const int* my_flags, int slot, const int* epoch_ptr, int* err_flag, void* stream);
+int vlm_optim_step_p2p(int kind, float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, const int* step_ptr, const float* lr_scale_ptr,
+                       float grad_scale, const void* const* peer_g16, const void* const* peer_r32, long long elem_offset,
+                       long long unit_base, long long units_per_rank, int world, const int* my_flags,
+                       int slot, const int* epoch_ptr, int* err_flag, void* stream);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ def test_library_exports_every_header_symbol():
     lib = _lib.lib()
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.vlm_abi_version() == 3
+    assert lib.vlm_abi_version() == 4
     assert isinstance(lib.vlm_last_error(), bytes)
 
 

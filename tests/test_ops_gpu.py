@@ -53,6 +53,44 @@ def test_layernorm(cuda_dev, M, D, fp32_in):
     assert (db - br.grad).abs().max().item() < 1e-3 * max(1.0, br.grad.abs().max().item())
 
 
+@pytest.mark.parametrize("M,D,drop,res", [(12608, 768, False, True), (8192, 768, True, False), (4099, 512, True, True), (1031, 1024, False, False)])
+def test_layernorm_rows_shared_by_warps(cuda_dev, M, D, drop, res, monkeypatch):
+    """Round-2 LayerNorm kernels (a row shared by D/256 warps, persistent row groups, packed fp32x2 math, vector atomics) at the
+    step's own sizes (many rows per group) against torch fp32 and against the warp-per-row kernels (VLM_LN_V2=0)."""
+    from vilmedic_b200 import ops
+    x, dy = _bf((M, D), cuda_dev, 1, 2.0), _bf((M, D), cuda_dev, 2)
+    x = (x.float() + torch.randn(M, 1, device=cuda_dev) * 3).to(torch.bfloat16)        # row means far from zero
+    gamma, beta = torch.randn(D, device=cuda_dev) * 0.5 + 1, torch.randn(D, device=cuda_dev) * 0.1
+    dres = _bf((M, D), cuda_dev, 3) if res else None
+    out = {}
+    for v2 in ("1", "0"):
+        monkeypatch.setenv("VLM_LN_V2", v2)
+        y, mean, rstd = ops.layernorm_fwd(x, gamma, beta, 1e-12)
+        dg, db, cs = (torch.zeros(D, device=cuda_dev) for _ in range(3))
+        r = ops.layernorm_bwd(dy, x, mean, rstd, gamma, dg, db, dres=dres, drop=(0.1, 7, 3) if drop else None, colsum=cs)
+        torch.cuda.synchronize()
+        out[v2] = (y, mean, rstd, dg, db, cs) + (tuple(r) if drop else (r,))
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (D,), gr, br, 1e-12)
+    yr.backward(dy.float())
+    y, mean, rstd, dg, db, cs, dx = out["1"][:7]
+    assert _bf16_close(y, yr, atol=2e-3)
+    assert (mean - xr.mean(-1)).abs().max().item() < 1e-4
+    assert ((rstd - 1 / torch.sqrt(xr.var(-1, unbiased=False) + 1e-12)).abs() / rstd).max().item() < 1e-4
+    want = xr.grad + (dres.float() if res else 0)
+    assert _bf16_close(dx, want, atol=2e-3 * max(1.0, want.abs().max().item()))
+    assert (dg - gr.grad).abs().max().item() < 1e-3 * max(1.0, gr.grad.abs().max().item())
+    assert (db - br.grad).abs().max().item() < 1e-3 * max(1.0, br.grad.abs().max().item())
+    last = out["1"][7] if drop else dx
+    assert (cs - last.float().sum(0)).abs().max().item() < 1e-3 * max(1.0, last.float().abs().sum(0).max().item())
+    # old kernels: same results within rounding, same dropout mask
+    for a, b in zip(out["1"], out["0"]):
+        assert (a.float() - b.float()).abs().max().item() <= 2e-2 * max(1.0, b.float().abs().max().item())
+    if drop:
+        assert torch.equal(out["1"][7] != 0, out["0"][7] != 0)
+
+
 def _attn_ref(q, k, v, H, DH, kmask, causal):
     B, Tq, _ = q.shape
     Sk = k.shape[1]

@@ -41,14 +41,22 @@ def main():
 
     model, arena, opt = make()
     # per-layer buckets launched from the backward pass; VLM_DDP_PIPELINE=1: optimizer update pipelined behind each bucket
-    pipe = os.environ.get("VLM_DDP_PIPELINE") == "1"
+    # VLM_DDP_TRANSPORT=p2p: no NCCL in the step — the optimizer kernel reads all ranks' gradient buckets through peer memory
+    pipe = os.environ.get("VLM_DDP_PIPELINE") == "1" or os.environ.get("VLM_DDP_TRANSPORT") == "p2p"
+    nsteps = int(os.environ.get("VLM_DDP_STEPS", "1"))
     sync = GradSync(arena, bucket_bytes=8 << 20, optimizer=opt if pipe else None).attach()
-    out = model(**shard)
-    out["loss"].backward()
-    early = sync.launches
-    sync.step(opt)
+    if os.environ.get("VLM_DDP_TRANSPORT") == "p2p":
+        assert sync.transport == "p2p", "peer-memory transport was requested but is not active"
+    for _ in range(nsteps):
+        sync.launches = 0
+        out = model(**shard)
+        out["loss"].backward()
+        early = sync.launches
+        sync.step(opt)
     sync.detach()
     torch.cuda.synchronize()
+    if sync.px is not None:
+        sync.px.check()
     assert early >= 2, "no gradient bucket was launched during the backward pass"
 
     # (a) replicas identical after the step
@@ -63,16 +71,17 @@ def main():
     if rank == 0:
         m2, a2, o2 = make()
         fb = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in full.items()}
-        m2(**fb)["loss"].backward()
-        o2.step(grad_scale=1.0)
+        for _ in range(nsteps):
+            m2(**fb)["loss"].backward()
+            o2.step(grad_scale=1.0)
         torch.cuda.synchronize()
         torch.manual_seed(0)
         init = get_arena(RRG(dict(dec), dict(cnn)).cuda()).flat
         d_ddp, d_full = mine - init, a2.flat - init
         rel = ((d_ddp - d_full).norm() / d_full.norm()).item()
         ok_b = rel < 5e-2
-        print("ddp_check: replicas identical=%s  update rel. diff vs full-batch step=%.3e  (|update|=%.3e)" % (
-            all(flags), rel, d_full.norm().item()), flush=True)
+        print("ddp_check[%s, %d step(s)]: replicas identical=%s  update rel. diff vs full-batch step=%.3e  (|update|=%.3e)" % (
+            sync.transport, nsteps, all(flags), rel, d_full.norm().item()), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not (all(flags) and ok_b):

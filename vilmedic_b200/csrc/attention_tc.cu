@@ -255,20 +255,49 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t pt_row = (uint32_t)(r * 128);   // row offset inside a 64-column atom of the P^T / dS^T tile
     const uint32_t aPTs = smem_u32(sPT), aP2s = smem_u32(sP2), aLse = smem_u32(sLse), aDelta = smem_u32(sDelta);   // shared-space addresses
     const int r7 = r & 7;
-    uint32_t tile_cnt = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    uint32_t tile_cnt = 0, item_cnt = 0;
+    const uint32_t aDOs = smem_u32(sDO);
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++item_cnt) {
       const int b = item / p.H, h = item % p.H;
       const uint32_t dkey = attn_drop_key(p.seed, off_eff, item);
-      // ---- per-item staging: lse (log2 units, +inf beyond Tq) and delta = rowsum(dO * O)
+      // ---- per-item staging: lse (log2 units, +inf beyond Tq) and delta = rowsum(dO * O).
+      // delta is computed HERE (round 2; it used to be a separate pre-pass kernel per launch: 36 launches, 0.32 ms / step and a second
+      // read of dO): two threads per query row, each multiplies four 16-byte units of the O row (global) with the same units of
+      // the dO row that TMA has just put into shared memory (swizzled K-major rows of 128 bytes).  The O rows of the CTA's NEXT
+      // item are requested into L2 now, so that this read is an L2 hit next time.
       named_bar_sync(1, 128 * ATC_SPLIT);
-      if (ct < Nq) {
-        float l2 = INFINITY, dl = 0.f;
-        if (ct < p.Tq) {
-          l2 = p.lse[(long long)item * p.Tq + ct] * 1.4426950408889634f;
-          dl = p.delta[(long long)item * p.Tq + ct];
+      {
+        const int qrow = ct >> 1, half = ct & 1;
+        uint4 ov[4];
+        const bool live = qrow < p.Tq;
+        if (live) {
+          const uint4* op = reinterpret_cast<const uint4*>(p.o + (long long)b * p.o_bs + (long long)qrow * p.o_rs + h * 64) + half * 4;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) ov[u] = __ldg(op + u);
+          const int nitem = item + gridDim.x;
+          if (nitem < nitems) {
+            const bf16* np = p.o + (long long)(nitem / p.H) * p.o_bs + (long long)qrow * p.o_rs + (nitem % p.H) * 64 + half * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(np));
+          }
         }
-        sLse[ct] = l2;
-        sDelta[ct] = dl;
+        if (ct < Nq) sLse[ct] = ct < p.Tq ? p.lse[(long long)item * p.Tq + ct] * 1.4426950408889634f : INFINITY;
+        mbar_wait(qdo_full, item_cnt & 1u);        // dO (and Q) of this item are in shared memory
+        float acc = 0.f;
+        if (live) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint4 dv = lds128u(aDOs + (uint32_t)(qrow * 128) + (uint32_t)((((half << 2) + u) ^ (qrow & 7)) << 4));
+            const uint32_t ow[4] = {ov[u].x, ov[u].y, ov[u].z, ov[u].w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 a = unpack_bf16x2(ow[e]), g = unpack_bf16x2(dw[e]);
+              acc = fmaf(a.x, g.x, acc);
+              acc = fmaf(a.y, g.y, acc);
+            }
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (half == 0 && qrow < Nq) sDelta[qrow] = acc;      // rows in [Tq, Nq): 0
       }
       named_bar_sync(1, 128 * ATC_SPLIT);
       for (int j = 0; j < ntiles; ++j, ++tile_cnt) {
@@ -544,14 +573,10 @@ int attention_bwd_tc_dispatch(const void* q, long long q_bs, long long q_rs, con
   if (mk(&tq, q, q_bs, q_rs, Tq, Nq) || mk(&tdo, d_o, do_bs, do_rs, Tq, Nq) || mk(&tk, k, k_bs, k_rs, Sk, 128) ||
       mk(&tv, v, v_bs, v_rs, Sk, 128))
     return -1;
-  {
-    const long long rows = (long long)B * H * Tq;
-    const long long warps = (rows + 3) / 4;
-    attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>((const bf16*)o, o_bs, o_rs, (const bf16*)d_o, do_bs, do_rs,
-                                                                            delta, B, H, Tq);
-  }
+  // (delta = rowsum(dO * O) is computed inside the kernel since round 2; `delta` stays in the signature for the mma.sync path)
+  (void)delta;
   AttnTcParams p;
-  p.delta = delta;
+  p.delta = nullptr;
   p.o = (const bf16*)o; p.d_o = (const bf16*)d_o;
   p.o_bs = o_bs; p.o_rs = o_rs; p.do_bs = do_bs; p.do_rs = do_rs;
   p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv;

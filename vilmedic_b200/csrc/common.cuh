@@ -25,6 +25,8 @@ int check_launch(const char* what);
   } while (0)
 
 int num_sms();
+int num_sms_all();      // physical SM count (ignores the margin)
+int background_mode();  // runtime.cu: helper kernels launch as small co-resident CTAs while set
 
 // ----------------------------------------------------------------------------------------------
 // device helpers

@@ -4,6 +4,7 @@
 // (modeling_bert_generation.py:52-56 SelfOutput.LayerNorm, 288-292 Output.LayerNorm, 410-429 embeddings.LayerNorm),
 // reached from vilmedic/blocks/vision/visual_encoder.py:180-186 and vilmedic/blocks/huggingface/decoder/decoder_model.py:42-47.
 #include "common.cuh"
+#include <cstdlib>
 #include "vlm_b200.h"
 
 namespace vlm {
@@ -242,9 +243,251 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Round-2 kernels for bf16 rows with D = WPR * 256 (768 -> WPR = 3): a row is shared by WPR warps, every lane owns ONE 16-byte
+// vector (8 columns).  Compared with the warp-per-row kernels above this cuts the per-thread state of the backward from 226
+// registers (8 warps / SM, issue-latency bound: ncu r2l_ln_bwd — 36 instructions per element, 48 % issue-active) to < 85
+// (24 warps / SM), keeps gamma in registers for the whole persistent loop, does the arithmetic on the packed fp32x2 pipe and
+// derives xhat / dy*gamma once.  Row statistics cross the WPR warps through a double-buffered shared-memory slot and one named
+// barrier per row; the column partials (dgamma, dbeta, bias-gradient column sums) leave with 16-byte vector atomics.
+static constexpr int LN2_G = 4;   // row groups per CTA
+
+__device__ __forceinline__ void unpack8(const uint4& u, float2 (&v)[4]) {
+  v[0] = unpack_bf16x2(u.x); v[1] = unpack_bf16x2(u.y); v[2] = unpack_bf16x2(u.z); v[3] = unpack_bf16x2(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float2 (&v)[4]) {
+  return make_uint4(pack_bf16x2(v[0].x, v[0].y), pack_bf16x2(v[1].x, v[1].y), pack_bf16x2(v[2].x, v[2].y), pack_bf16x2(v[3].x, v[3].y));
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {      // read-once data: do not keep it in L1
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+template <int WPR>
+__global__ void __launch_bounds__(WPR * 32 * LN2_G, 2)
+layernorm_fwd_v2_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, float eps) {
+  constexpr int D = WPR * 256;
+  __shared__ float xch[2][2][LN2_G][WPR];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp / WPR, wr = warp - grp * WPR;
+  const int col = (wr * 32 + lane) * 8;
+  float2 gm[4], bt[4];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + col), g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + col), b1 = *reinterpret_cast<const float4*>(beta + col + 4);
+    gm[0] = make_float2(g0.x, g0.y); gm[1] = make_float2(g0.z, g0.w); gm[2] = make_float2(g1.x, g1.y); gm[3] = make_float2(g1.z, g1.w);
+    bt[0] = make_float2(b0.x, b0.y); bt[1] = make_float2(b0.z, b0.w); bt[2] = make_float2(b1.x, b1.y); bt[3] = make_float2(b1.z, b1.w);
+  }
+  const int stride = gridDim.x * LN2_G;
+  int row = blockIdx.x * LN2_G + grp;
+  uint4 nx = make_uint4(0u, 0u, 0u, 0u);
+  if (row < M) nx = ldg_stream(reinterpret_cast<const uint4*>(x + (size_t)row * D + col));
+  for (int it = 0; row < M; row += stride, ++it) {
+    const uint4 cx = nx;
+    if (row + stride < M) nx = ldg_stream(reinterpret_cast<const uint4*>(x + (size_t)(row + stride) * D + col));
+    float2 v[4];
+    unpack8(cx, v);
+    float2 s2 = __fadd2_rn(__fadd2_rn(v[0], v[1]), __fadd2_rn(v[2], v[3]));
+    float s = warp_sum(s2.x + s2.y);
+    if (WPR > 1) {
+      if (lane == 0) xch[it & 1][0][grp][wr] = s;
+      named_bar_sync(1 + grp, WPR * 32);
+      s = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPR; ++w) s += xch[it & 1][0][grp][w];
+    }
+    const float mean = s * (1.f / (float)D);
+    const float2 nm = make_float2(-mean, -mean);
+    float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = __fadd2_rn(v[j], nm);
+      q2 = __ffma2_rn(v[j], v[j], q2);
+    }
+    float q = warp_sum(q2.x + q2.y);
+    if (WPR > 1) {
+      if (lane == 0) xch[it & 1][1][grp][wr] = q;
+      named_bar_sync(1 + grp, WPR * 32);
+      q = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPR; ++w) q += xch[it & 1][1][grp][w];
+    }
+    const float rstd = rsqrtf(q * (1.f / (float)D) + eps);
+    if (wr == 0 && lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+    const float2 r2 = make_float2(rstd, rstd);
+    float2 o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = __ffma2_rn(__fmul2_rn(v[j], r2), gm[j], bt[j]);
+    *reinterpret_cast<uint4*>(y + (size_t)row * D + col) = pack8(o);
+  }
+}
+
+template <int WPR, bool DROP, bool COLSUM>
+__global__ void __launch_bounds__(WPR * 32 * LN2_G, WPR <= 3 ? 2 : 1)
+layernorm_bwd_v2_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, const float* __restrict__ gamma, const bf16* __restrict__ dres,
+                        bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
+                        bf16* __restrict__ dx_drop, float p_drop, unsigned long long seed, unsigned long long offset,
+                        const unsigned long long* __restrict__ offset_ptr, float* __restrict__ colsum) {
+  constexpr int D = WPR * 256;
+  __shared__ float2 xch[2][LN2_G][WPR];
+  __shared__ __align__(16) float red[LN2_G][D];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp / WPR, wr = warp - grp * WPR;
+  const int col = (wr * 32 + lane) * 8;
+  float2 gm[4];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + col), g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
+    gm[0] = make_float2(g0.x, g0.y); gm[1] = make_float2(g0.z, g0.w); gm[2] = make_float2(g1.x, g1.y); gm[3] = make_float2(g1.z, g1.w);
+  }
+  float2 dg[4], db[4], cs[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) dg[j] = db[j] = cs[j] = make_float2(0.f, 0.f);
+  const Philox rng(seed);
+  if (DROP && offset_ptr) offset += __ldg(offset_ptr);
+  const uint32_t thr = (uint32_t)(p_drop * 4294967296.0f);
+  const float inv_keep = DROP ? 1.f / (1.f - p_drop) : 1.f;
+
+  const int stride = gridDim.x * LN2_G;
+  int row = blockIdx.x * LN2_G + grp;
+  uint4 nx, ndy, nres = make_uint4(0u, 0u, 0u, 0u);
+  float nmu = 0.f, nrs = 0.f;
+  auto prefetch = [&](int prow) {
+    if (prow < M) {
+      const size_t o = (size_t)prow * D + col;
+      nx = ldg_stream(reinterpret_cast<const uint4*>(x + o));
+      ndy = ldg_stream(reinterpret_cast<const uint4*>(dy + o));
+      if (dres) nres = ldg_stream(reinterpret_cast<const uint4*>(dres + o));
+      nmu = __ldg(mean + prow);
+      nrs = __ldg(rstd + prow);
+    }
+  };
+  nx = ndy = nres;
+  prefetch(row);
+  for (int it = 0; row < M; row += stride, ++it) {
+    const uint4 cx = nx, cdy = ndy, cres = nres;
+    const float mu = nmu, rs = nrs;
+    prefetch(row + stride);
+    float2 xh[4], g[4];
+    {
+      float2 xv[4], dv[4];
+      unpack8(cx, xv);
+      unpack8(cdy, dv);
+      const float2 rs2 = make_float2(rs, rs), nmr = make_float2(-mu * rs, -mu * rs);
+      float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        xh[j] = __ffma2_rn(xv[j], rs2, nmr);
+        g[j] = __fmul2_rn(dv[j], gm[j]);
+        s1 = __fadd2_rn(s1, g[j]);
+        s2 = __ffma2_rn(g[j], xh[j], s2);
+        dg[j] = __ffma2_rn(dv[j], xh[j], dg[j]);
+        db[j] = __fadd2_rn(db[j], dv[j]);
+      }
+      float a = warp_sum(s1.x + s1.y), b = warp_sum(s2.x + s2.y);
+      if (WPR > 1) {
+        if (lane == 0) xch[it & 1][grp][wr] = make_float2(a, b);
+        named_bar_sync(1 + grp, WPR * 32);
+        a = b = 0.f;
+#pragma unroll
+        for (int w = 0; w < WPR; ++w) {
+          const float2 t = xch[it & 1][grp][w];
+          a += t.x;
+          b += t.y;
+        }
+      }
+      // dx = rs * (g - c1 - xhat * c2)  (+ dres)
+      const float c1 = a * (1.f / (float)D), c2 = b * (1.f / (float)D);
+      const float2 nc1 = make_float2(-c1 * rs, -c1 * rs), nc2 = make_float2(-c2 * rs, -c2 * rs);
+      float2 rv[4];
+      unpack8(cres, rv);                      // zeros when there is no residual gradient
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 t = __ffma2_rn(g[j], rs2, nc1);
+        t = __ffma2_rn(xh[j], nc2, t);
+        g[j] = __fadd2_rn(t, rv[j]);
+      }
+    }
+    const size_t o = (size_t)row * D + col;
+    *reinterpret_cast<uint4*>(dx + o) = pack8(g);
+    if (DROP) {
+      // same Philox stream as the GEMM epilogue / vlm_dropout_bf16 on the flat [M, D] tensor
+      const unsigned long long base = (unsigned long long)o >> 2;
+      const uint4 r0 = rng(base, offset), r1 = rng(base + 1, offset);
+      g[0].x = r0.x >= thr ? g[0].x * inv_keep : 0.f; g[0].y = r0.y >= thr ? g[0].y * inv_keep : 0.f;
+      g[1].x = r0.z >= thr ? g[1].x * inv_keep : 0.f; g[1].y = r0.w >= thr ? g[1].y * inv_keep : 0.f;
+      g[2].x = r1.x >= thr ? g[2].x * inv_keep : 0.f; g[2].y = r1.y >= thr ? g[2].y * inv_keep : 0.f;
+      g[3].x = r1.z >= thr ? g[3].x * inv_keep : 0.f; g[3].y = r1.w >= thr ? g[3].y * inv_keep : 0.f;
+      *reinterpret_cast<uint4*>(dx_drop + o) = pack8(g);
+    }
+    if (COLSUM) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cs[j] = __fadd2_rn(cs[j], g[j]);
+    }
+  }
+
+  // column partials: across the row groups of the CTA through shared memory, then one 16-byte vector atomic per 4 columns
+  constexpr int NPASS = COLSUM ? 3 : 2;
+#pragma unroll
+  for (int pass = 0; pass < NPASS; ++pass) {
+    const float2* src = pass == 0 ? dg : (pass == 1 ? db : cs);
+    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : colsum);
+    __syncthreads();
+    *reinterpret_cast<float4*>(&red[grp][col]) = make_float4(src[0].x, src[0].y, src[1].x, src[1].y);
+    *reinterpret_cast<float4*>(&red[grp][col + 4]) = make_float4(src[2].x, src[2].y, src[3].x, src[3].y);
+    __syncthreads();
+    if (dst) {
+      for (int c = threadIdx.x * 4; c < D; c += WPR * 32 * LN2_G * 4) {
+        float4 t = *reinterpret_cast<const float4*>(&red[0][c]);
+#pragma unroll
+        for (int gi = 1; gi < LN2_G; ++gi) {
+          const float4 u = *reinterpret_cast<const float4*>(&red[gi][c]);
+          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        atomicAdd(reinterpret_cast<float4*>(dst + c), t);
+      }
+    }
+  }
+}
+
+static int ln_variant() {          // VLM_LN_V2=0 selects the warp-per-row kernels (kept for fp32 rows and other widths)
+  const char* v = getenv("VLM_LN_V2");
+  return (v && v[0] == '0') ? 0 : 1;
+}
+
+// grid of the persistent v2 kernels: every row group gets the same number of rows (no partial last pass)
+static int ln2_grid(int M, int max_ctas) {
+  const int groups = max_ctas * LN2_G;
+  const int rpg = (M + groups - 1) / groups;
+  return (M + LN2_G * rpg - 1) / (LN2_G * rpg);
+}
+
 template <typename TIn>
 static int ln_fwd_dispatch(const TIn* x, const float* gamma, const float* beta, bf16* y, float* mean, float* rstd, int M,
                            int D, float eps, cudaStream_t s) {
+  if constexpr (sizeof(TIn) == 2) {
+    if (D % 256 == 0 && D >= 512 && D <= 1024 && ln_variant() == 1 && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(beta) & 15) == 0) {
+#define LN_FWD2(W_)                                                                                                     \
+  {                                                                                                                     \
+    static int occ = 0;                                                                                                 \
+    if (occ == 0) {                                                                                                     \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_fwd_v2_kernel<W_>, W_ * 32 * LN2_G, 0) != cudaSuccess || occ < 1) occ = 2; \
+    }                                                                                                                   \
+    layernorm_fwd_v2_kernel<W_><<<ln2_grid(M, num_sms() * occ), W_ * 32 * LN2_G, 0, s>>>(x, gamma, beta, y, mean, rstd, M, eps); \
+  }
+      if (D == 512) LN_FWD2(2)
+      else if (D == 768) LN_FWD2(3)
+      else LN_FWD2(4)
+#undef LN_FWD2
+      return check_launch("layernorm_fwd_v2");
+    }
+  }
   const int nv = (D / 8 + 31) / 32;
   const int grid = (M + 3) / 4;                // (two rows per warp was tried in round 2: 0.78 vs 0.66 ms per step — worse)
 #define LN_FWD(NV_) layernorm_fwd_kernel<TIn, NV_><<<grid, 128, 0, s>>>(x, gamma, beta, y, mean, rstd, M, D, eps)
@@ -266,6 +509,32 @@ static int ln_bwd_dispatch(const bf16* dy, const TIn* x, const float* mean, cons
                            const TIn* dres, TIn* dx, float* dgamma, float* dbeta, int M, int D, TIn* dx_drop, float p_drop,
                            unsigned long long seed, unsigned long long offset, const unsigned long long* offset_ptr,
                            float* colsum, cudaStream_t s) {
+  if constexpr (sizeof(TIn) == 2) {
+    const bool al16 = ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(dgamma) | reinterpret_cast<uintptr_t>(dbeta) |
+                        reinterpret_cast<uintptr_t>(colsum)) & 15) == 0;
+    if (D % 256 == 0 && D >= 512 && D <= 1024 && ln_variant() == 1 && al16) {
+#define LN_BWD2K(W_, DR_, CS_)                                                                                           \
+  {                                                                                                                     \
+    static int occ = 0;                                                                                                 \
+    if (occ == 0) {                                                                                                     \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_bwd_v2_kernel<W_, DR_, CS_>, W_ * 32 * LN2_G, 0) != cudaSuccess || occ < 1) occ = 1; \
+    }                                                                                                                   \
+    layernorm_bwd_v2_kernel<W_, DR_, CS_><<<ln2_grid(M, num_sms() * occ), W_ * 32 * LN2_G, 0, s>>>(                      \
+        dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, M, dx_drop, p_drop, seed, offset, offset_ptr, colsum);       \
+  }
+#define LN_BWD2(W_)                                                                                                     \
+  {                                                                                                                     \
+    if (dx_drop) { if (colsum) LN_BWD2K(W_, true, true) else LN_BWD2K(W_, true, false) }                                \
+    else { if (colsum) LN_BWD2K(W_, false, true) else LN_BWD2K(W_, false, false) }                                      \
+  }
+      if (D == 512) LN_BWD2(2)
+      else if (D == 768) LN_BWD2(3)
+      else LN_BWD2(4)
+#undef LN_BWD2
+#undef LN_BWD2K
+      return check_launch("layernorm_bwd_v2");
+    }
+  }
   const int nv = (D / 8 + 31) / 32;
   // persistent grid = exactly one resident wave (SMs x occupancy): a partial second wave would cost a full pass
 #define LN_BWD(NV_)                                                                                                     \

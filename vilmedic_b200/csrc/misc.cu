@@ -111,9 +111,12 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, long long ld, float* _
 // 16-byte variant: each thread owns 8 adjacent columns (one uint4 per row), rows unrolled x4 so that four independent loads
 // are in flight per thread.  Needs a 16-byte aligned base and ld % 8 == 0; columns in [N, ld) of the last vector are read
 // but never written back.
-__global__ void __launch_bounds__(256) colsum8_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, int M, int N,
-                                                      int rows_per_block, const float* __restrict__ scale_ptr) {
-  __shared__ float red[8][256 + 8];
+// TY = row lanes per CTA: 8 (256 threads) in the foreground, 4 (128 threads, fits next to a resident persistent GEMM CTA) in
+// background mode (runtime.cu).
+template <int TY>
+__global__ void __launch_bounds__(32 * TY) colsum8_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, int M, int N,
+                                                          int rows_per_block, const float* __restrict__ scale_ptr) {
+  __shared__ float red[TY][256 + 8];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int col = blockIdx.x * 256 + tx * 8;
   const int r0 = blockIdx.y * rows_per_block;
@@ -124,17 +127,17 @@ __global__ void __launch_bounds__(256) colsum8_kernel(const bf16* __restrict__ x
   if (col < N) {
     const bf16* base = x + col;
     int r = r0 + ty;
-    for (; r + 24 < r1; r += 32) {
+    for (; r + 3 * TY < r1; r += 4 * TY) {
       uint4 u[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(r + 8 * k) * ld));
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(r + TY * k) * ld));
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 p0 = unpack_bf16x2(u[k].x), p1 = unpack_bf16x2(u[k].y), p2 = unpack_bf16x2(u[k].z), p3 = unpack_bf16x2(u[k].w);
         a[0] += p0.x; a[1] += p0.y; a[2] += p1.x; a[3] += p1.y; a[4] += p2.x; a[5] += p2.y; a[6] += p3.x; a[7] += p3.y;
       }
     }
-    for (; r < r1; r += 8) {
+    for (; r < r1; r += TY) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r * ld));
       const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
       a[0] += p0.x; a[1] += p0.y; a[2] += p1.x; a[3] += p1.y; a[4] += p2.x; a[5] += p2.y; a[6] += p3.x; a[7] += p3.y;
@@ -143,14 +146,15 @@ __global__ void __launch_bounds__(256) colsum8_kernel(const bf16* __restrict__ x
 #pragma unroll
   for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = a[j];
   __syncthreads();
-  const int c = ty * 32 + tx;                 // 256 threads <-> 256 columns of the block
-  const int gc = blockIdx.x * 256 + c;
-  if (gc < N) {
-    float t = 0.f;
+  const float sc = scale_ptr ? __ldg(scale_ptr) : 1.f;
+  for (int c = ty * 32 + tx; c < 256; c += 32 * TY) {     // threads <-> the 256 columns of the block
+    const int gc = blockIdx.x * 256 + c;
+    if (gc < N) {
+      float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][c];
-    const float sc = scale_ptr ? __ldg(scale_ptr) : 1.f;
-    atomicAdd(out + gc, t * sc);
+      for (int k = 0; k < TY; ++k) t += red[k][c];
+      atomicAdd(out + gc, t * sc);
+    }
   }
 }
 
@@ -389,11 +393,13 @@ extern "C" int vlm_colsum_bf16(const void* x, long long ld, float* out, int M, i
   VLM_REQUIRE(x && out && M > 0 && N > 0 && ld % 2 == 0 && ld >= N + (N & 1), "vlm_colsum_bf16: bad args (M=%d N=%d ld=%lld)", M, N, ld);
   if (ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (long long)((N + 7) / 8 * 8) <= ld) {
     const int col_blocks = (N + 255) / 256;
-    int row_blocks = (num_sms() * 4 + col_blocks - 1) / col_blocks;
+    const bool bg = background_mode();
+    int row_blocks = ((bg ? num_sms_all() * 8 : num_sms() * 4) + col_blocks - 1) / col_blocks;
     if (row_blocks > (M + 63) / 64) row_blocks = (M + 63) / 64;
     if (row_blocks < 1) row_blocks = 1;
     const int rows_per_block = (M + row_blocks - 1) / row_blocks;
-    colsum8_kernel<<<dim3(col_blocks, row_blocks), dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, M, N, rows_per_block, scale_ptr);
+    if (bg) colsum8_kernel<4><<<dim3(col_blocks, row_blocks), dim3(32, 4), 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, M, N, rows_per_block, scale_ptr);
+    else colsum8_kernel<8><<<dim3(col_blocks, row_blocks), dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, M, N, rows_per_block, scale_ptr);
     return check_launch("colsum8");
   }
   const int col_blocks = (N + 63) / 64;

@@ -176,14 +176,18 @@ extern "C" int vlm_sumsq_bf16(const void* g, long long n, float* out, void* stre
 static int optim_launch(int kind, float* p, float* g, const void* g16, float* m, float* v, void* p_bf16, long long n, const OptimScalars& sc,
                         const int* step_ptr, const float* lr_scale_ptr, const float* gnorm_sq_ptr, const float* loss_ptr,
                         int zero_grad, cudaStream_t s) {
-  long long blocks = (n / 4 + 255) / 256;
-  const long long cap = (long long)num_sms() * 8;
+  // foreground: 256-thread CTAs, 8 per SM, grid-stride (6.1 TB/s measured).  background (runtime.cu): 128-thread CTAs of ~4 float4
+  // per thread and array — 128 x <= 56 registers fit next to a resident persistent GEMM CTA, and the many short CTAs trickle
+  // through whatever slots the main stream's kernels leave free.
+  const int threads = background_mode() ? 128 : 256;
+  long long blocks = background_mode() ? (n / 4 + 511) / 512 : (n / 4 + 255) / 256;
+  const long long cap = background_mode() ? (long long)num_sms_all() * 64 : (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
 #define VLM_OPTIM(K_)                                                                                                        \
   {                                                                                                                          \
-    if (g16) optim_kernel<K_, true><<<(int)blocks, 256, 0, s>>>(p, g, (const bf16*)g16, m, v, (bf16*)p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad); \
-    else optim_kernel<K_, false><<<(int)blocks, 256, 0, s>>>(p, g, nullptr, m, v, (bf16*)p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad);           \
+    if (g16) optim_kernel<K_, true><<<(int)blocks, threads, 0, s>>>(p, g, (const bf16*)g16, m, v, (bf16*)p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad); \
+    else optim_kernel<K_, false><<<(int)blocks, threads, 0, s>>>(p, g, nullptr, m, v, (bf16*)p_bf16, n, sc, step_ptr, lr_scale_ptr, gnorm_sq_ptr, loss_ptr, zero_grad);           \
   }
   if (kind == 0) VLM_OPTIM(0)
   else if (kind == 1) VLM_OPTIM(1)

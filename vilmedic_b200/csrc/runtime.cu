@@ -54,6 +54,14 @@ static int num_sms_physical() {
 
 int num_sms() { return num_sms_physical() - sm_margin(); }
 
+// Background mode: while set, the HBM-bound helper kernels that the host issues on a SIDE stream (optimizer update of a gradient
+// bucket, bias-gradient column sums) are launched as many small CTAs (128 threads, <= 48 registers, next to no shared memory) so
+// that one of them fits on an SM NEXT TO the resident persistent tensor CTA (448 threads x <= 128 registers leave 8 K registers)
+// and their memory traffic runs under the tensor-bound kernels of the main stream instead of after them.
+static int g_background = 0;
+int background_mode() { return g_background; }
+int num_sms_all() { return num_sms_physical(); }
+
 }  // namespace vlm
 
 extern "C" const char* vlm_last_error(void) { return vlm::g_err; }
@@ -70,6 +78,12 @@ extern "C" int vlm_set_sm_margin(int margin) {
 }
 
 extern "C" int vlm_get_sm_margin(void) { return vlm::sm_margin(); }
+
+extern "C" int vlm_set_background(int on) {
+  const int prev = vlm::g_background;
+  vlm::g_background = on ? 1 : 0;
+  return prev;
+}
 
 extern "C" int vlm_device_check(void) {
   int dev = 0;

@@ -30,10 +30,13 @@ import torch
 import torch.distributed as dist
 
 from . import nn as _nn
+from . import ops as _ops
+
+_DONE_SLOT = 255        # p2p.DONE_SLOT
 
 
 class GradSync:
-    def __init__(self, arena, group=None, bucket_bytes=None, payload=None, optimizer=None):
+    def __init__(self, arena, group=None, bucket_bytes=None, payload=None, optimizer=None, transport=None):
         if payload is None:
             payload = os.environ.get("VLM_DDP_PAYLOAD", "bf16")
         if payload not in ("bf16", "fp32"):
@@ -51,14 +54,40 @@ class GradSync:
         self.launches = 0
         # bf16 exchange buffer (one slot per arena element); None when nothing is exchanged or the payload is fp32
         self.grad16 = None
-        if self.world > 1 and payload == "bf16":
-            self.grad16 = torch.zeros(arena.numel, device=arena.flat_grad.device, dtype=torch.bfloat16)
         # pipelined optimizer: needs every decision of the update to be local to a span (no global gradient norm)
         self.opt = None
-        if optimizer is not None and os.environ.get("VLM_PIPELINE_OPTIMIZER", "1") != "0" and not optimizer.needs_global_norm() \
-                and arena.flat_grad.is_cuda:
+        pipe_ok = optimizer is not None and not optimizer.needs_global_norm() and arena.flat_grad.is_cuda
+        # transport "p2p" (VLM_DDP_TRANSPORT): no collective at all — the optimizer kernel of every rank reads the bf16 gradient
+        # buckets of all ranks through peer memory (csrc/p2p.cu, p2p.PeerExchange); needs the pipelined optimizer and the bf16 payload
+        self.px = None
+        if transport is None:
+            transport = os.environ.get("VLM_DDP_TRANSPORT", "nccl")
+        if transport not in ("nccl", "p2p"):
+            raise ValueError("GradSync transport must be 'nccl' or 'p2p', got %r" % (transport,))
+        if transport == "p2p" and self.world > 1 and pipe_ok and payload == "bf16":
+            try:
+                from .p2p import PeerExchange
+                self.px = PeerExchange(arena.numel, arena.flat_grad.device, group)
+                self.grad16 = self.px.grad16
+            except Exception as e:      # no peer access on this box / IPC refused: keep the NCCL path, say so
+                import sys
+                sys.stderr.write("GradSync: peer-memory transport unavailable (%s); using NCCL\n" % (str(e).splitlines()[0][:200],))
+                self.px = None
+            # all ranks take the same path
+            ok = torch.tensor([1 if self.px is not None else 0], device=arena.flat_grad.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                self.px = None
+        self.transport = "p2p" if self.px is not None else "nccl"
+        if self.px is None:
+            self.grad16 = None
+            if self.world > 1 and payload == "bf16":
+                self.grad16 = torch.zeros(arena.numel, device=arena.flat_grad.device, dtype=torch.bfloat16)
+        self._slot = 0
+        if pipe_ok and (self.px is not None or os.environ.get("VLM_PIPELINE_OPTIMIZER", "0") != "0"):
             self.opt = optimizer
             self.side = torch.cuda.Stream(device=arena.flat_grad.device)
+            self.pub = torch.cuda.Stream(device=arena.flat_grad.device) if self.px is not None else None
             self._begun = False
 
     @property
@@ -83,7 +112,7 @@ class GradSync:
             buf = self.arena.flat_grad[lo:hi]
         return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
-    def _launch(self, lo, hi):
+    def _launch(self, lo, hi, tail=False):
         if hi <= lo:
             return
         self.sent.append((lo, hi))
@@ -91,6 +120,9 @@ class GradSync:
         if not self.pipelined:
             if self.world > 1:
                 self.pending.append(self._exchange(lo, hi))
+            return
+        if self.px is not None:
+            self._launch_p2p(lo, hi, tail)
             return
         # pipelined: the exchange is issued from the main stream (NCCL's stream waits for the kernels that produced these
         # gradients), the update of the bucket runs on the side stream behind it — neither blocks the backward pass
@@ -103,7 +135,47 @@ class GradSync:
             if not self._begun:
                 self.opt.begin_step()
                 self._begun = True
-            self.opt.step_range(lo, hi, grad_scale=1.0 / self.world, grad16=self.grad16)
+            if tail:        # issued from finish(): the backward pass is over, nothing to hide under — full-size CTAs
+                self.opt.step_range(lo, hi, grad_scale=1.0 / self.world, grad16=self.grad16)
+            else:           # small CTAs that fit next to the resident persistent GEMM / attention CTAs (ops.background)
+                with _ops.background():
+                    self.opt.step_range(lo, hi, grad_scale=1.0 / self.world, grad16=self.grad16)
+
+    def _launch_p2p(self, lo, hi, tail):
+        """Peer-memory transport.  main stream: (first bucket of the step: advance the epoch, wait until the peers are done with my
+        buffers of the previous step).  publish stream: cast the bucket into my bf16 buffer, raise READY[bucket] in every rank's
+        flag block — short kernels that never wait, so a bucket is visible to the peers as soon as its layer's backward is done.
+        side stream: (two-shot: sum my slice of the bucket over all ranks, raise REDUCED[bucket]) the fused exchange + optimizer
+        kernel of the bucket; both poll the flags themselves.  Everything but the tail of the step runs as background CTAs."""
+        px = self.px
+        b = self._slot
+        self._slot += 1
+        if 2 * b + 1 >= _DONE_SLOT:
+            raise RuntimeError("GradSync(p2p): more than 127 gradient buckets in one step")
+        cur = torch.cuda.current_stream()
+        if b == 0:
+            px.begin_step()
+
+        def body():
+            self.pub.wait_stream(cur)
+            with torch.cuda.stream(self.pub):
+                self._cast(self.arena.flat_grad[lo:hi], self.grad16[lo:hi])
+                px.signal(2 * b)
+            self.side.wait_stream(self.pub)
+            with torch.cuda.stream(self.side):
+                if not self._begun:
+                    self.opt.begin_step()
+                    self._begun = True
+                if px.two_shot:
+                    px.reduce_slice(lo, hi, b)
+                    px.signal(2 * b + 1)
+                self.opt.step_range(lo, hi, grad_scale=1.0 / self.world, peer=(px, b))
+
+        if tail:            # issued from finish(): the backward pass is over, nothing to hide under — full-size CTAs
+            body()
+        else:               # small CTAs that fit next to the resident persistent GEMM / attention CTAs (ops.background)
+            with _ops.background():
+                body()
 
     @staticmethod
     def _cast(src, dst):
@@ -157,15 +229,20 @@ class GradSync:
         of the leftover ranges and joins the side stream: the optimizer step is complete when it returns (use step())."""
         if self.world > 1 or self.pipelined:
             if self.run is not None:
-                self._launch(*self.run)
+                self._launch(*self.run, tail=True)
                 self.run = None
             for lo, hi in self._uncovered(0, self.arena.numel):
-                self._launch(lo, hi)
+                self._launch(lo, hi, tail=True)
             for w in self.pending:
                 w.wait()
             if self.pipelined:
+                if self.px is not None and self._slot > 0:
+                    with torch.cuda.stream(self.side):
+                        self.px.signal(_DONE_SLOT)      # I have read everything I need from the peers' buffers of this step
+                    torch.cuda.current_stream().wait_stream(self.pub)
                 torch.cuda.current_stream().wait_stream(self.side)
                 self._begun = False
+                self._slot = 0
         self.pending = []
         self.sent = []
         self.run = None

@@ -20,7 +20,9 @@ class GraphedTrainStep:
         self.counter = torch.zeros(1, device=dev, dtype=torch.int64)
         ops.RNG_COUNTER[0] = self.counter
         self._step_fn = step_fn or self._default_step
-        s = stream if stream is not None else torch.cuda.Stream()      # pass the stream earlier eager steps ran on, if any
+        # (high priority: kernels that the step forks onto side streams — ops.SideWork, the pipelined optimizer of ddp.GradSync — are
+        #  low priority and only take the SMs the dependent chain of this stream leaves idle; captured kernel nodes keep it)
+        s = stream if stream is not None else torch.cuda.Stream(priority=-1)      # pass the stream earlier eager steps ran on, if any
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):

@@ -24,6 +24,8 @@ GRAD_READY_HOOK = [None]
 
 
 def notify_grad_ready(module):
+    ops.SIDE.join()                     # bias-gradient column sums / weight-gradient GEMMs issued on the side streams
+    ops.SIDE_GEMM.join()                # (ops.SideWork) are part of the span
     hook = GRAD_READY_HOOK[0]
     if hook is not None and module is not None:
         hook(module)
@@ -63,11 +65,19 @@ def _ln(arena, ln):
     return (arena.fp32(ln.weight), arena.fp32(ln.bias), arena.grad(ln.weight), arena.grad(ln.bias))
 
 
-def _wgrad(dy, x, P, scale_t=None, bias=True):
-    """P.gw += dy^T x ; P.gb += colsum(dy) (skipped when the producer of dy already accumulated it).  dy [M,N], x [M,K]."""
-    ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out=P.gw, accumulate=True, alpha_t=scale_t)
+def _wgrad(dy, x, P, scale_t=None, bias=True, side=False):
+    """P.gw += dy^T x ; P.gb += colsum(dy) (skipped when the producer of dy already accumulated it).  dy [M,N], x [M,K].
+    side=True (layer backward functions, which end in notify_grad_ready -> join): the column sums run on the side stream under the
+    wgrad / dgrad GEMMs that consume the same dy."""
     if bias and P.gb is not None:
-        ops.colsum(dy, P.gb, scale_t)
+        if side:
+            ops.SIDE.run(lambda: ops.colsum(dy, P.gb, scale_t), dy, scale_t)
+        else:
+            ops.colsum(dy, P.gb, scale_t)
+    if side:
+        ops.SIDE_GEMM.run(lambda: ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out=P.gw, accumulate=True, alpha_t=scale_t), dy, x, scale_t)
+    else:
+        ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out=P.gw, accumulate=True, alpha_t=scale_t)
 
 
 def _dgrad(dy, P, **kw):
@@ -272,19 +282,19 @@ class ViTLayerFn(torch.autograd.Function):
         D = H * DH
         prev_gb, own_b2_fused = ctx.fuse
         dx2 = dx2.contiguous()
-        _wgrad(dx2, hmid, P2, bias=not own_b2_fused)
+        _wgrad(dx2, hmid, P2, bias=not own_b2_fused, side=True)
         dpre = _dgrad(dx2, P2, act=ops.ACT_GELU_GRAD, aux_in=pre)
-        _wgrad(dpre, h2, P1)
+        _wgrad(dpre, h2, P1, side=True)
         dh2 = _dgrad(dpre, P1)
         dx1 = ops.layernorm_bwd(dh2, x1, mean2, rstd2, ln2[0], ln2[2], ln2[3], dres=dx2, colsum=Po.gb)
         ctx2d = ctxv.view(B * S, D)
-        _wgrad(dx1, ctx2d, Po, bias=False)
+        _wgrad(dx1, ctx2d, Po, bias=False, side=True)
         dctx = _dgrad(dx1, Po).view(B, S, D)
         dqkv = torch.empty_like(qkv)
         q3, d3 = qkv.view(B, S, 3 * D), dqkv.view(B, S, 3 * D)
         ops.attention_bwd(q3[:, :, :D], q3[:, :, D:2 * D], q3[:, :, 2 * D:], ctxv, dctx, lse,
                           d3[:, :, :D], d3[:, :, D:2 * D], d3[:, :, 2 * D:], H, DH)
-        _wgrad(dqkv, h1, Pqkv)
+        _wgrad(dqkv, h1, Pqkv, side=True)
         dh1 = _dgrad(dqkv, Pqkv)
         dx = ops.layernorm_bwd(dh1, x, mean1, rstd1, ln1[0], ln1[2], ln1[3], dres=dx1, colsum=prev_gb)
         notify_grad_ready(ctx.layer)      # (this layer's FFN-down bias gradient was completed by the layer above / the final LayerNorm)
@@ -599,16 +609,16 @@ class BertLayerFn(torch.autograd.Function):
             return dz, dz
 
         dz3, dz3d = ln_bwd(dx3.contiguous(), c["z3"], c["m3"], c["r3"], ln3, "h3", c["P2"])
-        _wgrad(dz3d, c["hmid"], c["P2"], bias=False)
+        _wgrad(dz3d, c["hmid"], c["P2"], bias=False, side=True)
         dpre = _dgrad(dz3d, c["P2"], act=ops.ACT_GELU_GRAD, aux_in=c["pre"])
-        _wgrad(dpre, c["x2"], c["P1"])
+        _wgrad(dpre, c["x2"], c["P1"], side=True)
         dx2 = _dgrad(dpre, c["P1"], residual=dz3)
         denc = None
         if c["cross"]:
             ln2 = c["ln2"]
             Se = c["Se"]
             dz2, dz2d = ln_bwd(dx2, c["z2"], c["m2"], c["r2"], ln2, "h2", c["Poc"])
-            _wgrad(dz2d, c["ctx2"].view(B * T, D), c["Poc"], bias=False)
+            _wgrad(dz2d, c["ctx2"].view(B * T, D), c["Poc"], bias=False, side=True)
             dctx2 = _dgrad(dz2d, c["Poc"]).view(B, T, D)
             dqc = torch.empty_like(c["qc"])
             dkvc = torch.empty_like(c["kvc"])
@@ -617,14 +627,14 @@ class BertLayerFn(torch.autograd.Function):
             ops.attention_bwd(c["qc"].view(B, T, D), kv3[:, :, :D], kv3[:, :, D:], c["ctx2"], dctx2, c["lse2"],
                               dqc.view(B, T, D), dkv3[:, :, :D], dkv3[:, :, D:], H, DH, kmask=c["enc_mask"], p_drop=p_a,
                               seed=s, offset=o)
-            _wgrad(dqc, c["x1"], c["Pq"])
+            _wgrad(dqc, c["x1"], c["Pq"], side=True)
             dx1 = _dgrad(dqc, c["Pq"], residual=dz2)
-            _wgrad(dkvc, c["enc"], c["Pkv"])
+            _wgrad(dkvc, c["enc"], c["Pkv"], side=True)
             denc = _dgrad(dkvc, c["Pkv"])
         else:
             dx1 = dx2
         dz1, dz1d = ln_bwd(dx1, c["z1"], c["m1"], c["r1"], ln1, "h1", c["Po"])
-        _wgrad(dz1d, c["ctx1"].view(B * T, D), c["Po"], bias=False)
+        _wgrad(dz1d, c["ctx1"].view(B * T, D), c["Po"], bias=False, side=True)
         dctx1 = _dgrad(dz1d, c["Po"]).view(B, T, D)
         dqkv = torch.empty_like(c["qkv"])
         q3, d3 = c["qkv"].view(B, T, 3 * D), dqkv.view(B, T, 3 * D)
@@ -632,7 +642,7 @@ class BertLayerFn(torch.autograd.Function):
         ops.attention_bwd(q3[:, :, :D], q3[:, :, D:2 * D], q3[:, :, 2 * D:], c["ctx1"], dctx1, c["lse1"],
                           d3[:, :, :D], d3[:, :, D:2 * D], d3[:, :, 2 * D:], H, DH, kmask=c["kmask"], causal=c["causal"],
                           p_drop=p_a, seed=s, offset=o)
-        _wgrad(dqkv, c["x"], c["Pqkv"])
+        _wgrad(dqkv, c["x"], c["Pqkv"], side=True)
         dx = _dgrad(dqkv, c["Pqkv"], residual=dz1)
         notify_grad_ready(ctx.layer)
         return (dx, denc) + (None,) * 10
@@ -675,8 +685,9 @@ class LMHeadCEFn(torch.autograd.Function):
         E = head.decoder.weight
         gE = arena.grad(E)
         # dE += g * dlogits^T h   (rows >= V of the padded product are cut by M = V)
-        ops.gemm(dl[:, :V], h, a_mn_major=True, b_mn_major=True, out=gE, accumulate=True, alpha_t=g)
-        ops.colsum(dl[:, :V], arena.grad(head.bias), g)
+        gbias = arena.grad(head.bias)
+        ops.SIDE.run(lambda: ops.colsum(dl[:, :V], gbias, g), dl, g)     # under the two LM-head GEMMs; joined by notify_grad_ready
+        ops.SIDE_GEMM.run(lambda: ops.gemm(dl[:, :V], h, a_mn_major=True, b_mn_major=True, out=gE, accumulate=True, alpha_t=g), dl, h, g)
         dh = ops.gemm(dl[:, :V], arena.bf16(E), b_mn_major=True, alpha_t=g)
         notify_grad_ready(head)           # lm_head.bias; the tied embedding matrix is announced with the embedding block
         return dh, None, None, None, None, None, None, None, None

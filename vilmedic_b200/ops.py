@@ -14,7 +14,9 @@ ACT_NONE, ACT_GELU, ACT_GELU_GRAD = 0, 1, 2
 
 # Number of OUR kernels launched through this module (bench.py reports it as `gpu_launches`).
 LAUNCHES = [0]
-_KERNELS_PER_CALL = {"vlm_attention_bwd": 2, "vlm_attention_bwd_tc": 2, "vlm_adamw_step": 2, "vlm_beam_advance": 2}
+# (attention backward: one kernel on the tcgen05 path since the delta pre-pass moved into it; the mma.sync fallback launches more —
+#  counted as one, i.e. never over-claimed)
+_KERNELS_PER_CALL = {"vlm_adamw_step": 2, "vlm_beam_advance": 2}
 # Optional recording of the GEMM launches (bench.py roofline pass): list of (M, N, K, batch, algorithmic HBM bytes =
 # operands read once + outputs written once, replay closure, operands kept alive)
 GEMM_TIMING = None
@@ -32,6 +34,71 @@ def check(rc, what):  # noqa: F811
 def _req(cond, msg):
     if not cond:
         raise ValueError(msg)
+
+
+# ------------------------------------------------------------------------------------------------ side stream / background mode
+class background:
+    """with ops.background(): helper kernels (optimizer update, column sums) launch as small co-resident CTAs (vlm_set_background)."""
+
+    def __enter__(self):
+        self.prev = _L().vlm_set_background(c_int(1))
+
+    def __exit__(self, *exc):
+        _L().vlm_set_background(c_int(self.prev))
+
+
+class SideWork:
+    """Kernels of the backward pass that nothing downstream waits for until the layer's gradients are announced run on a SIDE
+    stream, under the dependent chain of the main stream:
+      * SIDE      — the bias-gradient column sums (73 launches / 0.87 ms of the RRG step when serialised), in background mode
+                    (small CTAs that fit next to a resident persistent GEMM CTA).          VLM_SIDE_COLSUM=0 turns it off;
+      * SIDE_GEMM — the weight-gradient GEMMs (a third of the backward GEMM time): a persistent 148-CTA GEMM whose tile count is
+                    1.3-1.7 waves leaves a quarter of the SMs idle in its last wave, and the dgrad -> LayerNorm -> attention chain
+                    of the main stream is full of such tails; CTAs of the wgrad kernel fill them.   VLM_SIDE_WGRAD=1 turns it on.
+    `run(fn, *tensors)` forks from the current stream and keeps the tensors alive; `join()` makes the current stream wait for
+    everything issued so far (nn.notify_grad_ready calls it before a span's gradients are declared final).  Works inside
+    CUDA-graph capture (fork / join become graph edges)."""
+
+    def __init__(self, env, default, bg):
+        import os
+        self.enabled = os.environ.get(env, default) != "0"
+        self.bg = bg
+        self.streams = {}
+        self.pending = []
+        self.dirty = False
+
+    def _stream(self, dev):
+        st = self.streams.get(dev)
+        if st is None:
+            st = self.streams[dev] = torch.cuda.Stream(device=dev)     # default (= lowest) priority
+        return st
+
+    def run(self, fn, *keep):
+        if not self.enabled:
+            fn()
+            return
+        cur = torch.cuda.current_stream()
+        st = self._stream(cur.device)
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            if self.bg:
+                with background():
+                    fn()
+            else:
+                fn()
+        self.pending.append(keep)
+        self.dirty = True
+
+    def join(self):
+        if self.dirty:
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(self._stream(cur.device))
+            self.pending.clear()
+            self.dirty = False
+
+
+SIDE = SideWork("VLM_SIDE_COLSUM", "1", True)
+SIDE_GEMM = SideWork("VLM_SIDE_WGRAD", "0", False)
 
 
 def _is_bf16_cuda(t):

@@ -113,8 +113,10 @@ class FusedOptimizer(torch.optim.Optimizer):
         return (self.param_groups[0]["max_grad_norm"] or 0.0) > 0
 
     @torch.no_grad()
-    def step_range(self, lo, hi, grad_scale=1.0, grad16=None):
-        """Update the trainable parameters inside arena elements [lo, hi) (begin_step() must have run for this step)."""
+    def step_range(self, lo, hi, grad_scale=1.0, grad16=None, peer=None):
+        """Update the trainable parameters inside arena elements [lo, hi) (begin_step() must have run for this step).
+        peer=(p2p.PeerExchange, bucket index) with [lo, hi) = the whole bucket: the gradient values are the sum over all ranks' bf16 buckets, read through peer memory by
+        the update kernel itself (csrc/p2p.cu)."""
         g = self.param_groups[0]
         a = self.arena
         L = _lib.lib()
@@ -122,6 +124,9 @@ class FusedOptimizer(torch.optim.Optimizer):
         for slo, shi in self.spans:
             x, y = max(lo, slo), min(hi, shi)
             if y <= x:
+                continue
+            if peer is not None:
+                peer[0].optim_span(self, x, y, peer[1], grad_scale, bucket_range=(lo, hi))
                 continue
             ops.check(L.vlm_optim_step(c_int(self.kind), ptr(a.flat[x:y]), ptr(a.flat_grad[x:y]), ptr(self.m[x:y]),
                                        ptr(self.v[x:y]), ptr(a.flat_bf16[x:y]), c_ll(y - x), c_float(g["lr"]),

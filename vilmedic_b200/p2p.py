@@ -1,0 +1,171 @@
+"""Peer-memory plumbing of the data-parallel step (csrc/p2p.cu): buffers that every rank of a node maps through CUDA IPC, the flag
+block / epoch counter of the exchange protocol, and the launches of the fused exchange + optimizer kernel.
+
+torch.distributed is only used ONCE, at construction, to hand the 64-byte IPC handles round (all_gather_object) and for a
+barrier; the training step itself contains no collective call (replaces the DDP all-reduce of
+vilmedic/executors/trainor_accelerate.py:122,132)."""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import c_float, c_int, c_ll, c_void_p, ptr, stream_ptr
+from . import ops
+
+MAX_SLOTS = 256                 # READY / REDUCED flags of up to 127 buckets per step (slots 2b, 2b + 1) + the DONE flag
+DONE_SLOT = MAX_SLOTS - 1
+MAX_WORLD = 16
+
+
+class _DevMem:
+    """Raw device allocation exposed to torch through __cuda_array_interface__ (zero-copy view, keeps this object alive)."""
+
+    def __init__(self, addr, nbytes):
+        self.addr, self.nbytes = addr, nbytes
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (addr, False), "version": 3}
+
+    def tensor(self, device):
+        return torch.as_tensor(self, device=device)
+
+
+def _ipc_alloc(nbytes):
+    p = c_void_p()
+    h = ctypes.create_string_buffer(64)
+    ops.check(_lib.lib().vlm_ipc_alloc(c_ll(nbytes), ctypes.byref(p), h), "vlm_ipc_alloc")
+    return p.value, h.raw
+
+
+def _ipc_open(handle):
+    p = c_void_p()
+    ops.check(_lib.lib().vlm_ipc_open(ctypes.create_string_buffer(handle, 64), ctypes.byref(p)), "vlm_ipc_open")
+    return p.value
+
+
+class PeerExchange:
+    def __init__(self, numel, device, group=None, two_shot=None):
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if not (2 <= self.world <= MAX_WORLD):
+            raise ValueError("PeerExchange: world size %d not in [2, %d]" % (self.world, MAX_WORLD))
+        self.device = device
+        self.numel = numel
+        g_bytes = (numel * 2 + 255) // 256 * 256
+        f_bytes = MAX_SLOTS * self.world * 4
+        # two-shot (reduce-scatter into per-rank fp32 slices, then every rank reads the slices): fewer NVLink bytes from 4 ranks on —
+        # (N-1)/N * 6 B per parameter instead of (N-1) * 2 B; one more kernel and flag per bucket.  VLM_P2P_TWO_SHOT=0|1 overrides.
+        if two_shot is None:
+            import os
+            env = os.environ.get("VLM_P2P_TWO_SHOT")
+            two_shot = (env == "1") if env in ("0", "1") else self.world >= 4
+        self.two_shot = bool(two_shot)
+        self._own = [_ipc_alloc(g_bytes), _ipc_alloc(f_bytes)]          # [(ptr, handle)] : bf16 gradients, flags (, fp32 reduced slices)
+        if self.two_shot:
+            self._own.append(_ipc_alloc((numel * 4 + 255) // 256 * 256))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, tuple(h for _, h in self._own), group=group)
+        if any(len(h) != len(self._own) for h in handles):
+            raise RuntimeError("PeerExchange: ranks disagree on the exchange mode")
+        self.g16_ptrs, self.flag_ptrs, self.r32_ptrs, self._opened = [], [], [], []
+        for w in range(self.world):
+            if w == self.rank:
+                ptrs = [p_ for p_, _ in self._own]
+            else:
+                ptrs = [_ipc_open(h) for h in handles[w]]
+                self._opened += ptrs
+            self.g16_ptrs.append(ptrs[0])
+            self.flag_ptrs.append(ptrs[1])
+            if self.two_shot:
+                self.r32_ptrs.append(ptrs[2])
+        self._g16_arr = (c_void_p * self.world)(*self.g16_ptrs)
+        self._flag_arr = (c_void_p * self.world)(*self.flag_ptrs)
+        self._r32_arr = (c_void_p * self.world)(*self.r32_ptrs) if self.two_shot else None
+        self.grad16 = _DevMem(self.g16_ptrs[self.rank], numel * 2).tensor(device).view(torch.bfloat16)
+        self.flags = _DevMem(self.flag_ptrs[self.rank], f_bytes).tensor(device).view(torch.int32)
+        self.epoch = torch.zeros(1, device=device, dtype=torch.int32)
+        self.err = torch.zeros(1, device=device, dtype=torch.int32)
+        self._self_test(group)
+
+    def _self_test(self, group):
+        """Every rank writes a pattern into its buffer and reads everybody else's through the peer mappings; one signal / wait round
+        trip through the flag blocks.  Raises if anything is off (the caller then falls back to NCCL)."""
+        n = 1024
+        self.grad16[:n] = float(self.rank + 1)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
+        for w in range(self.world):
+            peer = _DevMem(self.g16_ptrs[w], n * 2).tensor(self.device).view(torch.bfloat16)
+            if not bool((peer.float() == float(w + 1)).all().item()):
+                raise RuntimeError("PeerExchange: peer read of rank %d's buffer returned wrong data" % w)
+        L = _lib.lib()
+        ops.check(L.vlm_p2p_epoch_inc(ptr(self.epoch), stream_ptr()), "vlm_p2p_epoch_inc")
+        self.signal(0)
+        self.wait(0, 0)
+        self.signal(DONE_SLOT)          # leaves DONE = 1 = epoch: the first real step (epoch 2) waits for DONE >= 1
+        torch.cuda.synchronize(self.device)
+        if int(self.err.item()) != 0:
+            raise RuntimeError("PeerExchange: flag round trip timed out")
+        dist.barrier(group=group)
+        self.grad16[:n] = 0
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
+
+    # ---- protocol steps (all asynchronous launches on the current stream) ----
+    def begin_step(self):
+        L = _lib.lib()
+        ops.check(L.vlm_p2p_epoch_inc(ptr(self.epoch), stream_ptr()), "vlm_p2p_epoch_inc")
+        self.wait(DONE_SLOT, -1)        # every peer has finished reading my buffers of the previous step
+
+    def signal(self, slot):
+        ops.check(_lib.lib().vlm_p2p_signal(self._flag_arr, c_int(self.world), c_int(self.rank), c_int(slot), ptr(self.epoch),
+                                            stream_ptr()), "vlm_p2p_signal")
+
+    def wait(self, slot, delta):
+        ops.check(_lib.lib().vlm_p2p_wait(ptr(self.flags), c_int(self.world), c_int(slot), ptr(self.epoch), c_int(delta),
+                                          ptr(self.err), stream_ptr()), "vlm_p2p_wait")
+
+    def units_per_rank(self, lo, hi):
+        """Slice of bucket [lo, hi) a rank reduces in two-shot mode, in 4-element units."""
+        n4 = (hi - lo) // 4
+        return (n4 + self.world - 1) // self.world
+
+    def reduce_slice(self, lo, hi, bucket):
+        """Two-shot, first half: sum MY slice of bucket [lo, hi) over all ranks' bf16 buffers into my fp32 buffer (waits for the
+        READY flags of the bucket itself); the caller then signals REDUCED."""
+        per = self.units_per_rank(lo, hi)
+        a = lo + 4 * per * self.rank
+        b = min(hi, a + 4 * per)
+        if b <= a:
+            return
+        ops.check(_lib.lib().vlm_p2p_reduce_slice(self._g16_arr, c_ll(a), c_void_p(self.r32_ptrs[self.rank] + 4 * a), c_ll(b - a),
+                                                  c_int(self.world), ptr(self.flags), c_int(2 * bucket), ptr(self.epoch), ptr(self.err),
+                                                  stream_ptr()), "vlm_p2p_reduce_slice")
+
+    def optim_span(self, opt, lo, hi, bucket, grad_scale, bucket_range=None):
+        """Fused exchange + update of arena elements [lo, hi) of bucket `bucket` (= [bucket_range)): one-shot — waits for READY of
+        every rank, sums the ranks' bf16 gradients through peer loads; two-shot — waits for REDUCED of every rank and reads every
+        slice from its owner.  Applies `opt`'s rule.  begin_step() of the optimizer must have run for this step."""
+        a = opt.arena
+        g = opt.param_groups[0]
+        if self.two_shot:
+            blo, bhi = bucket_range
+            per, slot, base = self.units_per_rank(blo, bhi), 2 * bucket + 1, (lo - blo) // 4
+        else:
+            per, slot, base = 0, 2 * bucket, 0
+        ops.check(_lib.lib().vlm_optim_step_p2p(
+            c_int(opt.kind), ptr(a.flat[lo:hi]), ptr(a.flat_grad[lo:hi]), ptr(opt.m[lo:hi]), ptr(opt.v[lo:hi]), ptr(a.flat_bf16[lo:hi]),
+            c_ll(hi - lo), c_float(g["lr"]), c_float(g["betas"][0]), c_float(g["betas"][1]), c_float(g["eps"]), c_float(g["weight_decay"]),
+            ptr(opt.step_t), ptr(opt.lr_scale), c_float(grad_scale), None if self.two_shot else self._g16_arr, self._r32_arr, c_ll(lo),
+            c_ll(base), c_ll(per), c_int(self.world), ptr(self.flags), c_int(slot), ptr(self.epoch), ptr(self.err), stream_ptr()),
+            "vlm_optim_step_p2p")
+
+    def check(self):
+        """Host-side check of the device error flag (synchronises)."""
+        if int(self.err.item()) != 0:
+            raise RuntimeError("PeerExchange: a wait on a peer flag timed out (a rank fell out of the step)")
+
+    def close(self):
+        L = _lib.lib()
+        for p in self._opened:
+            L.vlm_ipc_close(c_void_p(p))
+        self._opened = []
