@@ -18,7 +18,8 @@ def test_two_rank_step_equals_full_batch_step(payload):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(root, "tools", "ddp_check.py")]
-    env = dict(os.environ, VLM_DDP_PAYLOAD=payload)           # bf16 = default exchange payload, fp32 = the reference's DDP all-reduce
+    # bf16 = NCCL all-reduce of the bf16 payload, fp32 = the reference's DDP all-reduce
+    env = dict(os.environ, VLM_DDP_PAYLOAD=payload, VLM_DDP_TRANSPORT="nccl")
     if payload == "p2p":                                        # peer-memory transport (csrc/p2p.cu): bf16 buckets read by the optimizer
         env.update(VLM_DDP_PAYLOAD="bf16", VLM_DDP_TRANSPORT="p2p", VLM_DDP_STEPS="3")      # kernel of every rank, 3 steps (epochs)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)

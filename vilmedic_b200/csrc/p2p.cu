@@ -122,8 +122,9 @@ __global__ void __launch_bounds__(256) p2p_reduce_slice_kernel(P2pPeers peers, f
 // the 2-rank step must equal the full-batch single-GPU step).
 // TWO_SHOT: the gradient of 4-element unit i is read (fp32, already summed) from the rank that owns it:
 // owner = (unit_base + i) / units_per_rank; `ready_flags` are then the REDUCED flags of the bucket.
+// (<= 64 registers: a 128-thread background CTA must fit into the 8 K registers a resident persistent GEMM CTA leaves free)
 template <int KIND, bool TWO_SHOT>
-__global__ void __launch_bounds__(256) optim_p2p_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+__global__ void __launch_bounds__(256, 4) optim_p2p_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                         bf16* __restrict__ p_bf16, long long n, P2pOptimScalars sc, P2pPeers peers,
                                                         P2pReduced red, long long unit_base, long long units_per_rank, int world,
                                                         const int* __restrict__ ready_flags, const int* __restrict__ epoch_ptr,
@@ -157,34 +158,11 @@ __global__ void __launch_bounds__(256) optim_p2p_kernel(float* __restrict__ p, f
       rect = sqrtf((rho_t - 4.f) * (rho_t - 2.f) * rho_inf / ((rho_inf - 4.f) * (rho_inf - 2.f) * rho_t));
     }
   }
-  for (long long i = i0; i < n4; i += stride) {
-    // peer loads first (NVLink latency), then the local state
-    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 pv, mv, vv;
-    if (TWO_SHOT) {
-      const int owner = (int)((unit_base + i) / units_per_rank);
-      gv = __ldcv(reinterpret_cast<const float4*>(red.r32[owner]) + i);
-      pv = reinterpret_cast<float4*>(p)[i];
-      mv = reinterpret_cast<float4*>(m)[i];
-      vv = reinterpret_cast<float4*>(v)[i];
-    }
-    for (int w0 = 0; !TWO_SHOT && w0 < world; w0 += 8) {      // up to 8 peer loads in flight; summation order = rank order on every rank
-      uint2 u[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (w0 + k < world) u[k] = __ldcv(reinterpret_cast<const uint2*>(peers.g16[w0 + k]) + i);   // never from a stale L1 line
-      if (w0 == 0) {
-        pv = reinterpret_cast<float4*>(p)[i];
-        mv = reinterpret_cast<float4*>(m)[i];
-        vv = reinterpret_cast<float4*>(v)[i];
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (w0 + k < world) {
-          const float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y);
-          gv.x += a.x; gv.y += a.y; gv.z += b.x; gv.w += b.y;
-        }
-    }
+  // update of the 4-element unit i with the (unscaled) gradient sum gv
+  auto apply = [&](long long i, float4 gv) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
     float* pp = &pv.x; const float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -212,6 +190,41 @@ __global__ void __launch_bounds__(256) optim_p2p_kernel(float* __restrict__ p, f
     o.x = pack_bf16x2(pv.x, pv.y);
     o.y = pack_bf16x2(pv.z, pv.w);
     reinterpret_cast<uint2*>(p_bf16)[i] = o;
+  };
+  if (TWO_SHOT) {
+    // four peer loads in flight per thread: as a background CTA (128 threads next to a persistent GEMM CTA) the kernel is bound by
+    // NVLink latency x bytes in flight — one 16-byte load per thread gave ~100 GB/s per GPU on 8 GPUs (tools/jobs/r2z.sh)
+    const uint32_t per = (uint32_t)units_per_rank, base = (uint32_t)unit_base;
+    for (long long i = i0; i < n4; i += 4 * stride) {
+      float4 gq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long j = i + u * stride;
+        if (j < n4) gq[u] = __ldcv(reinterpret_cast<const float4*>(red.r32[(base + (uint32_t)j) / per]) + j);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long j = i + u * stride;
+        if (j < n4) apply(j, gq[u]);
+      }
+    }
+  } else {
+    for (long long i = i0; i < n4; i += stride) {
+      float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int w0 = 0; w0 < world; w0 += 8) {      // up to 8 peer loads in flight; summation order = rank order on every rank
+        uint2 u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (w0 + k < world) u[k] = __ldcv(reinterpret_cast<const uint2*>(peers.g16[w0 + k]) + i);   // never from a stale L1 line
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (w0 + k < world) {
+            const float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y);
+            gv.x += a.x; gv.y += a.y; gv.z += b.x; gv.w += b.y;
+          }
+      }
+      apply(i, gv);
+    }
   }
 }
 

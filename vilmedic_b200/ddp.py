@@ -1,28 +1,36 @@
-"""Gradient exchange + optimizer pipeline for the flat arena: one process per GPU, NCCL all-reduce (SUM)
-over `flat_grad`, bucketed PER TRANSFORMER LAYER and launched from the backward pass itself: every layer's parameters occupy one
-contiguous span of the arena (arena.module_spans), the hand-written backward of a layer announces "gradients of this span are
-final" (nn.notify_grad_ready) and the exchange of that span starts on NCCL's stream while the backward of the layers below is
-still computing.  Spans arrive in descending address order (the backward walks the model in reverse), so adjacent spans are
-merged until a bucket reaches `bucket_bytes`; only the last bucket (patch embedding + whatever nobody announced) is exposed.
+"""Data-parallel gradient exchange + optimizer for the flat arena: one process per GPU, rank-local batches,
+no activation collectives (every pair is independent, contrastive negatives are rank-local as in the reference).
 
-Payload: bf16 by default — a cast kernel writes the bucket into `grad16` right before its all-reduce and the fused optimizer
-reads the reduced values from there (optim.FusedOptimizer.step(grad16=...)), so the exchange moves 2 B per parameter instead of 4
-and no widening pass exists.  `payload="fp32"` (or VLM_DDP_PAYLOAD=fp32) keeps the reference's fp32 DDP all-reduce bit for bit
-(vilmedic/executors/trainor_accelerate.py:122,132).  The 1/world factor is folded into the fused optimizer step (grad_scale).
-No activation collectives: every pair is independent, contrastive negatives are rank-local as in the reference.
+Bucketing: every transformer layer's parameters occupy one contiguous span of the arena (arena.module_spans); the hand-written
+backward of a layer announces "the gradients of this span are final" (nn.notify_grad_ready) and the exchange of that span starts
+while the backward of the layers below is still computing.  Spans arrive in descending address order, adjacent ones are merged
+until a bucket reaches `bucket_bytes`; only the last bucket (patch embedding + whatever nobody announced) is exposed.
 
-Pipelined optimizer (`optimizer=` given, no global-norm clipping): the fused optimizer update of a bucket is issued on a side
-stream right behind that bucket's all-reduce, i.e. UNDER the backward pass of the layers below — the update is pure HBM traffic
-(30 B per parameter, 1.15 ms for the 223 M parameters of the RRG model when run alone at the end of the step) and its thread
-blocks fit next to the one-CTA-per-SM GEMM kernels.  This also works, and pays, on ONE GPU (no exchange, just the update).
-Safe because a layer announces its span only after its own dgrad/wgrad kernels were issued (stream order), tied parameters live
-in the span of the module that is announced last (the embedding table: LM-head wgrad first, embedding scatter last), and the
-forward of the next step starts after `step()` has joined the side stream.
+Transport "p2p" (default, csrc/p2p.cu + p2p.PeerExchange): NO collective in the step.  Every rank casts a bucket to bf16 into a
+buffer its peers have mapped through CUDA IPC and raises a READY flag in every rank's memory; the fused optimizer kernel of
+every rank then reads the bucket of ALL ranks through NVLink peer loads, sums in fp32 in rank order (replicas stay bit-identical)
+and applies Adam / AdamW / RAdam in the same pass — exchange and update are one kernel, launched bucket by bucket from the
+backward pass as small background CTAs (128 threads, <= 64 registers) that fit on an SM next to the resident persistent GEMM CTA.
+From 4 ranks on the exchange is two-shot: each rank first sums ITS slice of the bucket over all ranks into an fp32 buffer
+(reduce-scatter through peer memory), the update kernels read every slice from its owner ((N-1)/N * 6 B per parameter over NVLink
+instead of (N-1) * 2 B).  The epoch / READY / REDUCED / DONE flag protocol lives in device memory, so the whole step still replays
+as ONE CUDA graph; every wait is bounded (20 s) and raises an error flag instead of hanging.  Needs `optimizer=` (the update is
+part of the exchange) and no global-norm clipping; otherwise, or when peer memory is unavailable, the NCCL path below is used.
 
-What was measured on 2 x B200 (round 2, tools/jobs/r2m.sh, r2t.sh, r2u.sh): the NCCL kernels (32 channels = 32 CTAs) cannot share
-an SM with the persistent one-CTA-per-SM GEMM / attention kernels; 22.45 ms without any exchange, 23.87 ms with the fp32 payload,
-23.69 ms with bf16, fewer channels are worse (4: 26.3 ms, 2: 33.8 ms with fp32), the bucket size does not matter (8 / 32 / 128 MB
-within 0.1 ms), leaving 4 SMs free for 4 high-priority channels gives 23.42 ms (VLM_SM_MARGIN, NCCL_MAX_NCHANNELS).
+Transport "nccl" (VLM_DDP_TRANSPORT=nccl): async NCCL all-reduce (SUM) per bucket.  Payload bf16 by default — a cast kernel
+writes the bucket into `grad16` right before its all-reduce and the fused optimizer reads the reduced values from there
+(optim.FusedOptimizer.step(grad16=...)): 2 B per parameter, no widening pass.  `payload="fp32"` (VLM_DDP_PAYLOAD=fp32) keeps the
+reference's fp32 DDP all-reduce bit for bit (vilmedic/executors/trainor_accelerate.py:122,132).  The 1/world factor is folded
+into the optimizer kernel (grad_scale).  VLM_PIPELINE_OPTIMIZER=1 additionally issues the optimizer update of a bucket on a side
+stream right behind that bucket's all-reduce (also on one GPU); measured gain on one B200: < 0.1 ms of 22.4 ms, off by default.
+
+Measured (round 2, RRG B=64/GPU, ms per step; tools/jobs/r2m|r2t|r2u|r2x|r2y|r2z|r2z2.sh):
+  2 GPUs: 22.41 on one GPU -> NCCL bf16 23.33, p2p one-shot 22.90 (two-shot 23.34);  NCCL history: 22.45 without any exchange,
+          fp32 payload 23.87, bf16 23.69; fewer channels are worse (4: 26.3, 2: 33.8), the bucket size does not matter (8 / 32 /
+          128 MB within 0.1 ms), 4 SMs left free for 4 high-priority channels 23.42 (VLM_SM_MARGIN, NCCL_MAX_NCHANNELS) — the NCCL
+          kernels (32 CTAs) cannot share an SM with the persistent one-CTA-per-SM GEMM / attention kernels;
+  8 GPUs: NCCL bf16 24.08, p2p one-shot 26.09 (7 x 446 MB of peer reads per GPU and step, latency-bound as background CTAs),
+          p2p two-shot 24.12 -> 23.82 with four peer loads in flight per thread.
 Round 1 sent two unbucketed fp32 spans and launched the encoder one after the backward had ended."""
 import os
 
@@ -61,7 +69,7 @@ class GradSync:
         # buckets of all ranks through peer memory (csrc/p2p.cu, p2p.PeerExchange); needs the pipelined optimizer and the bf16 payload
         self.px = None
         if transport is None:
-            transport = os.environ.get("VLM_DDP_TRANSPORT", "nccl")
+            transport = os.environ.get("VLM_DDP_TRANSPORT", "p2p")      # falls back to NCCL when peer memory is unavailable
         if transport not in ("nccl", "p2p"):
             raise ValueError("GradSync transport must be 'nccl' or 'p2p', got %r" % (transport,))
         if transport == "p2p" and self.world > 1 and pipe_ok and payload == "bf16":

@@ -54,7 +54,8 @@ class SideWork:
                     (small CTAs that fit next to a resident persistent GEMM CTA).          VLM_SIDE_COLSUM=0 turns it off;
       * SIDE_GEMM — the weight-gradient GEMMs (a third of the backward GEMM time): a persistent 148-CTA GEMM whose tile count is
                     1.3-1.7 waves leaves a quarter of the SMs idle in its last wave, and the dgrad -> LayerNorm -> attention chain
-                    of the main stream is full of such tails; CTAs of the wgrad kernel fill them.   VLM_SIDE_WGRAD=1 turns it on.
+                    of the main stream is full of such tails; CTAs of the wgrad kernel fill them (measured: -0.2 ms of 22.4 ms on one
+                    B200, tools/jobs/r2w.sh).                                                   VLM_SIDE_WGRAD=0 turns it off.
     `run(fn, *tensors)` forks from the current stream and keeps the tensors alive; `join()` makes the current stream wait for
     everything issued so far (nn.notify_grad_ready calls it before a span's gradients are declared final).  Works inside
     CUDA-graph capture (fork / join become graph edges)."""
@@ -98,7 +99,7 @@ class SideWork:
 
 
 SIDE = SideWork("VLM_SIDE_COLSUM", "1", True)
-SIDE_GEMM = SideWork("VLM_SIDE_WGRAD", "0", False)
+SIDE_GEMM = SideWork("VLM_SIDE_WGRAD", "1", False)
 
 
 def _is_bf16_cuda(t):
