@@ -15,7 +15,8 @@
 //            to shared memory in the canonical K-major SWIZZLE_128B layout the UMMA descriptors expect;
 //   pass B:  dS^T = P^T * (dP^T - delta[q]) * scale, in place;
 //   epilogue: dV_j, dK_j (and dQ after the last key tile) TMEM -> bf16 -> global.
-// delta = rowsum(dO * O) and lse2 are staged per item by the same threads.  Same math / same dropout stream as the
+// delta = rowsum(dO * O) (computed in the kernel from the O rows in global memory and the dO tile TMA has just loaded) and lse2 are
+// staged per item by the same threads.  Same math / same dropout stream as the
 // mma.sync kernels in attention.cu (those remain the path for other head dims, longer queries and the forward).
 #include <cuda.h>
 #include <cstdlib>
@@ -32,7 +33,7 @@ struct AttnTcParams {
   bf16* dq; bf16* dk; bf16* dv;
   long long dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
   const float* lse;        // [B,H,Tq] natural log
-  const float* delta;      // [B,H,Tq] rowsum(dO * O), produced by attn_delta_kernel right before
+  const float* delta;      // unused since round 2 (delta = rowsum(dO * O) is computed per item inside the kernel)
   const uint8_t* kmask;    // [B,Sk] or null
   int B, H, Tq, Sk, Nq;    // Nq = Tq rounded up to 32
   int causal;
@@ -501,31 +502,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   }
 }
 
-
-// delta[bh, q] = sum_d dO[q, d] * O[q, d]; 8 lanes per row (one 16-byte unit of O and of dO each), 4 rows per warp
-__global__ void attn_delta_kernel(const bf16* __restrict__ o, long long o_bs, long long o_rs, const bf16* __restrict__ d_o,
-                                  long long do_bs, long long do_rs, float* __restrict__ delta, int B, int H, int Tq) {
-  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long row = gw * 4 + (lane >> 3);
-  const int u = lane & 7;
-  const long long total = (long long)B * H * Tq;
-  float acc = 0.f;
-  if (row < total) {
-    const int q = (int)(row % Tq);
-    const long long bh = row / Tq;
-    const int h = (int)(bh % H), b = (int)(bh / H);
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + (long long)b * o_bs + (long long)q * o_rs + h * 64) + u);
-    const uint4 g = __ldg(reinterpret_cast<const uint4*>(d_o + (long long)b * do_bs + (long long)q * do_rs + h * 64) + u);
-    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-    const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
-    acc = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
-  }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  if (row < total && u == 0) delta[row] = acc;
-}
 
 template <int ATOMS, bool DROPOUT>
 static int launch_attn_bwd_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
