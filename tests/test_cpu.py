@@ -547,3 +547,27 @@ def test_policy_oracle_fp32_mode_equals_hf_decoder():
     assert (got - want).abs().max().item() <= 2e-5 * want.abs().max().item() + 1e-5
     got16 = PolicyDecoder(hf, "bf16")(ids, enc, mask).logits[:, 0]
     assert (got16 - want).abs().max().item() <= 5e-2 * want.abs().max().item() + 1e-3
+
+
+def test_two_shot_exchange_slices_partition_every_bucket():
+    """Host arithmetic of the peer-memory exchange (vilmedic_b200/p2p.py, csrc/p2p.cu): the slices the ranks reduce are disjoint,
+    4-element aligned, cover the bucket, and the owner the update kernel computes for a unit (unit // units_per_rank) is the rank
+    whose slice holds it — for ragged bucket sizes and every world size the node can have."""
+    from vilmedic_b200 import p2p
+    for world in (2, 3, 4, 8, 16):
+        for lo, n in ((0, 32), (128, 4), (64, 7087872), (96, 32 * 7), (0, 4 * (world - 1)), (32, 4 * (world + 1))):
+            hi = lo + n
+            per = p2p.units_per_rank(lo, hi, world)
+            assert per >= 1
+            cur = lo
+            for r in range(world):
+                a, b = p2p.slice_of(lo, hi, r, world)
+                assert a == cur or (a == hi and b == hi), (world, lo, hi, r, a, b)
+                assert (a - lo) % 4 == 0 and (b - a) % 4 == 0 and b <= hi
+                for unit in {(a - lo) // 4, (b - lo) // 4 - 1} if b > a else ():
+                    assert unit // per == r
+                cur = max(cur, b)
+            assert cur == hi
+    assert p2p.DONE_SLOT == p2p.MAX_SLOTS - 1
+    from vilmedic_b200 import ddp
+    assert ddp._DONE_SLOT == p2p.DONE_SLOT

@@ -18,6 +18,20 @@ DONE_SLOT = MAX_SLOTS - 1
 MAX_WORLD = 16
 
 
+def units_per_rank(lo, hi, world):
+    """Two-shot exchange: 4-element units of bucket [lo, hi) that one rank reduces (the last ranks may get fewer / none)."""
+    n4 = (hi - lo) // 4
+    return (n4 + world - 1) // world
+
+
+def slice_of(lo, hi, rank, world):
+    """Element range [a, b) of bucket [lo, hi) that `rank` reduces in the two-shot exchange (may be empty).  The update kernel finds the
+    owner of unit i (counted from the bucket start) as i // units_per_rank — csrc/p2p.cu optim_p2p_kernel<.., TWO_SHOT>."""
+    per = units_per_rank(lo, hi, world)
+    a = min(hi, lo + 4 * per * rank)
+    return a, min(hi, a + 4 * per)
+
+
 class _DevMem:
     """Raw device allocation exposed to torch through __cuda_array_interface__ (zero-copy view, keeps this object alive)."""
 
@@ -125,16 +139,12 @@ class PeerExchange:
                                           ptr(self.err), stream_ptr()), "vlm_p2p_wait")
 
     def units_per_rank(self, lo, hi):
-        """Slice of bucket [lo, hi) a rank reduces in two-shot mode, in 4-element units."""
-        n4 = (hi - lo) // 4
-        return (n4 + self.world - 1) // self.world
+        return units_per_rank(lo, hi, self.world)
 
     def reduce_slice(self, lo, hi, bucket):
         """Two-shot, first half: sum MY slice of bucket [lo, hi) over all ranks' bf16 buffers into my fp32 buffer (waits for the
         READY flags of the bucket itself); the caller then signals REDUCED."""
-        per = self.units_per_rank(lo, hi)
-        a = lo + 4 * per * self.rank
-        b = min(hi, a + 4 * per)
+        a, b = slice_of(lo, hi, self.rank, self.world)
         if b <= a:
             return
         ops.check(_lib.lib().vlm_p2p_reduce_slice(self._g16_arr, c_ll(a), c_void_p(self.r32_ptrs[self.rank] + 4 * a), c_ll(b - a),
