@@ -443,6 +443,60 @@ def test_grad_sync_two_ranks_gloo(payload):
     assert sorted(res) == [(0, True), (1, True)]
 
 
+def _peer_setup_failure_worker(rank, world, port, q, fail_phase):
+    """One rank cannot allocate / map its IPC buffers: EVERY rank must leave PeerExchange.__init__ with an exception (so that
+    ddp.GradSync falls back to NCCL on all of them) instead of one rank raising while the other waits in a barrier."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vilmedic_b200 import p2p
+    calls = {"n": 0}
+
+    def fake_alloc(nbytes):
+        if fail_phase == "alloc" and rank == 1:
+            raise RuntimeError("out of IPC handles (injected)")
+        calls["n"] += 1
+        return 4096 * (calls["n"] + 16 * rank), bytes([rank]) * 64
+
+    def fake_open(handle):
+        if fail_phase == "open" and rank == 0:
+            raise RuntimeError("peer access denied (injected)")
+        return 1 << 20
+
+    p2p._ipc_alloc, p2p._ipc_open = fake_alloc, fake_open
+
+    class _NoLib:                                   # close() must not touch the real library with fake pointers
+        def vlm_ipc_close(self, p):
+            return 0
+
+        def vlm_ipc_free(self, p):
+            return 0
+    p2p._lib.lib = lambda: _NoLib()
+    try:
+        p2p.PeerExchange(1024, torch.device("cpu"))
+        q.put((rank, "no exception"))
+    except RuntimeError as e:
+        q.put((rank, "raised: " + str(e)[:60]))
+    dist.barrier()                                  # both ranks are still in step with each other
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_phase", ["alloc", "open"])
+def test_peer_exchange_setup_failure_is_collective(fail_phase):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + (os.getpid() % 2000) + (11 if fail_phase == "open" else 0)
+    procs = [ctx.Process(target=_peer_setup_failure_worker, args=(r, 2, port, q, fail_phase)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(v.startswith("raised: PeerExchange") for v in res.values()), res
+
+
 # ------------------------------------------------------------------------------------------------ beam-search logic
 class _OracleAsModel:
     """Adapter: lets the product's beam_search drive ORACLE logits, so the selection logic is compared on identical numbers."""

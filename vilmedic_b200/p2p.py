@@ -73,24 +73,37 @@ class PeerExchange:
             env = os.environ.get("VLM_P2P_TWO_SHOT")
             two_shot = (env == "1") if env in ("0", "1") else self.world >= 4
         self.two_shot = bool(two_shot)
-        self._own = [_ipc_alloc(g_bytes), _ipc_alloc(f_bytes)]          # [(ptr, handle)] : bf16 gradients, flags (, fp32 reduced slices)
-        if self.two_shot:
-            self._own.append(_ipc_alloc((numel * 4 + 255) // 256 * 256))
-        handles = [None] * self.world
-        dist.all_gather_object(handles, tuple(h for _, h in self._own), group=group)
-        if any(len(h) != len(self._own) for h in handles):
-            raise RuntimeError("PeerExchange: ranks disagree on the exchange mode")
-        self.g16_ptrs, self.flag_ptrs, self.r32_ptrs, self._opened = [], [], [], []
-        for w in range(self.world):
-            if w == self.rank:
-                ptrs = [p_ for p_, _ in self._own]
-            else:
-                ptrs = [_ipc_open(h) for h in handles[w]]
-                self._opened += ptrs
-            self.g16_ptrs.append(ptrs[0])
-            self.flag_ptrs.append(ptrs[1])
+        # Every rank runs the SAME sequence of collectives below whatever fails locally (a rank that raised early while its peers sit
+        # in a barrier would hang the job): local work records its error, _agree() makes the verdict common, then all ranks raise.
+        self._own, self._opened, err = [], [], None
+        try:
+            self._own = [_ipc_alloc(g_bytes), _ipc_alloc(f_bytes)]      # [(ptr, handle)] : bf16 gradients, flags (, fp32 reduced slices)
             if self.two_shot:
-                self.r32_ptrs.append(ptrs[2])
+                self._own.append(_ipc_alloc((numel * 4 + 255) // 256 * 256))
+        except Exception as e:
+            err = "PeerExchange: IPC allocation failed: %s" % (str(e).splitlines()[0][:160],)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, None if err else tuple(h for _, h in self._own), group=group)
+        if err is None and any(h is None or len(h) != len(self._own) for h in handles):
+            err = "PeerExchange: a rank could not allocate, or the ranks disagree on the exchange mode"
+        self._agree(group, err)
+        self.g16_ptrs, self.flag_ptrs, self.r32_ptrs = [], [], []
+        try:
+            for w in range(self.world):
+                if w == self.rank:
+                    ptrs = [p_ for p_, _ in self._own]
+                else:
+                    ptrs = []
+                    for h in handles[w]:
+                        ptrs.append(_ipc_open(h))
+                        self._opened.append(ptrs[-1])
+                self.g16_ptrs.append(ptrs[0])
+                self.flag_ptrs.append(ptrs[1])
+                if self.two_shot:
+                    self.r32_ptrs.append(ptrs[2])
+        except Exception as e:
+            err = "PeerExchange: mapping a peer's buffers failed: %s" % (str(e).splitlines()[0][:160],)
+        self._agree(group, err)
         self._g16_arr = (c_void_p * self.world)(*self.g16_ptrs)
         self._flag_arr = (c_void_p * self.world)(*self.flag_ptrs)
         self._r32_arr = (c_void_p * self.world)(*self.r32_ptrs) if self.two_shot else None
@@ -98,31 +111,59 @@ class PeerExchange:
         self.flags = _DevMem(self.flag_ptrs[self.rank], f_bytes).tensor(device).view(torch.int32)
         self.epoch = torch.zeros(1, device=device, dtype=torch.int32)
         self.err = torch.zeros(1, device=device, dtype=torch.int32)
-        self._self_test(group)
+        self._agree(group, self._self_test(group))
+
+    def _agree(self, group, err):
+        """Collective verdict: raises on EVERY rank if any rank reports an error (after releasing what this rank holds)."""
+        t = torch.tensor([0 if err else 1], device=self.device, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        if int(t.item()) == 0:
+            self.close()
+            raise RuntimeError(err or "PeerExchange: another rank could not set up the peer-memory exchange")
 
     def _self_test(self, group):
         """Every rank writes a pattern into its buffer and reads everybody else's through the peer mappings; one signal / wait round
-        trip through the flag blocks.  Raises if anything is off (the caller then falls back to NCCL)."""
-        n = 1024
-        self.grad16[:n] = float(self.rank + 1)
-        torch.cuda.synchronize(self.device)
+        trip through the flag blocks.  Returns an error string or None; the barriers are executed by every rank in any case."""
+        n, err = 1024, None
+
+        def guarded(fn):
+            nonlocal err
+            try:
+                fn()
+            except Exception as e:
+                err = err or "PeerExchange self-test: %s" % (str(e).splitlines()[0][:160],)
+
+        def fill():
+            self.grad16[:n] = float(self.rank + 1)
+            torch.cuda.synchronize(self.device)
+
+        def check_peers():
+            for w in range(self.world):
+                peer = _DevMem(self.g16_ptrs[w], n * 2).tensor(self.device).view(torch.bfloat16)
+                if not bool((peer.float() == float(w + 1)).all().item()):
+                    raise RuntimeError("peer read of rank %d's buffer returned wrong data" % w)
+
+        def round_trip():
+            ops.check(_lib.lib().vlm_p2p_epoch_inc(ptr(self.epoch), stream_ptr()), "vlm_p2p_epoch_inc")
+            self.signal(0)
+            self.wait(0, 0)
+            self.signal(DONE_SLOT)      # leaves DONE = 1 = epoch: the first real step (epoch 2) waits for DONE >= 1
+            torch.cuda.synchronize(self.device)
+            if int(self.err.item()) != 0:
+                raise RuntimeError("flag round trip timed out")
+
+        def clear():
+            self.grad16[:n] = 0
+            torch.cuda.synchronize(self.device)
+
+        guarded(fill)
         dist.barrier(group=group)
-        for w in range(self.world):
-            peer = _DevMem(self.g16_ptrs[w], n * 2).tensor(self.device).view(torch.bfloat16)
-            if not bool((peer.float() == float(w + 1)).all().item()):
-                raise RuntimeError("PeerExchange: peer read of rank %d's buffer returned wrong data" % w)
-        L = _lib.lib()
-        ops.check(L.vlm_p2p_epoch_inc(ptr(self.epoch), stream_ptr()), "vlm_p2p_epoch_inc")
-        self.signal(0)
-        self.wait(0, 0)
-        self.signal(DONE_SLOT)          # leaves DONE = 1 = epoch: the first real step (epoch 2) waits for DONE >= 1
-        torch.cuda.synchronize(self.device)
-        if int(self.err.item()) != 0:
-            raise RuntimeError("PeerExchange: flag round trip timed out")
+        guarded(check_peers)
+        guarded(round_trip)
         dist.barrier(group=group)
-        self.grad16[:n] = 0
-        torch.cuda.synchronize(self.device)
+        guarded(clear)
         dist.barrier(group=group)
+        return err
 
     # ---- protocol steps (all asynchronous launches on the current stream) ----
     def begin_step(self):
@@ -175,7 +216,11 @@ class PeerExchange:
             raise RuntimeError("PeerExchange: a wait on a peer flag timed out (a rank fell out of the step)")
 
     def close(self):
+        """Unmap the peers' buffers and free this rank's own (the tensors viewing them must not be used afterwards)."""
         L = _lib.lib()
         for p in self._opened:
             L.vlm_ipc_close(c_void_p(p))
         self._opened = []
+        for p, _ in self._own:
+            L.vlm_ipc_free(c_void_p(p))
+        self._own = []
