@@ -661,9 +661,13 @@ def run_other_workload(args):
     ms, _ = timed(False)
     ms_e2e, last = timed(True)
     clocks = sampler.stop() if rank == 0 else None
+    loss_kernels = None
+    if rank == 0 and args.workload == "convirt":
+        loss_kernels = contrastive_loss_timing(dev)
     if rank == 0:
         value = world * per_gpu * args.steps / (ms / 1e3)
         print(json.dumps({
+            "loss_kernels": loss_kernels,
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
@@ -681,6 +685,50 @@ def run_other_workload(args):
         sys.stdout.flush()
         os._exit(0)
 
+
+
+def contrastive_loss_timing(dev, N=512, D=768, iters=20):
+    """The contrastive loss on its own at the GLOBAL batch of BASELINE configs[2] (N = 512 pairs, D = 768): forward + backward of
+    ConVIRTLoss (row-normalise + hi/lo split, tcgen05 similarity GEMM, symmetric LSE / CE kernels and their backward) captured into a
+    CUDA graph and replayed; us per loss evaluation and GB/s on the algorithmic bytes of SURVEY.md §8d (2*N*D*4 read + 3*N*4 written,
+    forward; the backward reads them again and writes 2*N*D*4)."""
+    from vilmedic_b200.blocks.losses import ConVIRTLoss
+    try:
+        g = torch.Generator(device="cpu").manual_seed(0)
+        l = torch.randn(N, D, generator=g).to(dev).requires_grad_(True)
+        v = torch.randn(N, D, generator=g).to(dev).requires_grad_(True)
+        crit = ConVIRTLoss(tau=0.1, lambda_=0.75)
+
+        def once():
+            l.grad = v.grad = None
+            loss = crit(l, v)[0]
+            loss.backward()
+            return loss
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                once()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            loss = once()
+        graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / iters
+        alg = 2 * (2 * N * D * 4) + 3 * N * 4 + 2 * N * D * 4
+        return {"what": "ConVIRTLoss forward + backward, N=%d, D=%d, one CUDA-graph replay" % (N, D), "us": us,
+                "algorithmic_bytes": alg, "gbs_on_algorithmic_bytes": alg / us / 1e3, "loss": float(loss.item())}
+    except Exception as e:      # pragma: no cover - reported, never silent
+        torch.cuda.synchronize()
+        return {"error": str(e).splitlines()[0][:200]}
 
 
 def peaks():
