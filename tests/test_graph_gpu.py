@@ -43,6 +43,11 @@ def test_graphed_step_and_prefetch(cuda_dev):
     lb = b.item()
     c = g.replay_prefetched().item()
     assert abs(la - l1) < 1e-5 and abs(lb - l2) < 1e-5 and abs(c - l1) < 1e-5, (la, lb, c, l1, l2)
+    # loss read-back one step behind (the host never waits for the step it has just launched): values arrive in order, none is lost
+    g.prefetch(b2)
+    got = [g.step_prefetched_async(b1), g.step_prefetched_async(b2), g.step_prefetched_async(b2), g.drain()]
+    assert got[0] is None and g.drain() is None
+    assert abs(got[1] - l2) < 1e-5 and abs(got[2] - l1) < 1e-5 and abs(got[3] - l2) < 1e-5, (got, l1, l2)
 
 
 def _step(model, opt, batch):

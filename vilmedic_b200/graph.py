@@ -74,6 +74,37 @@ class GraphedTrainStep:
         self.graph.replay()
         return self.loss
 
+    # ---- loss read-back without stalling the GPU: the value of step n is copied device -> pinned host behind step n and
+    #      collected by the host while step n + 1 is already running (the host stays one step ahead, the GPU never idles) ----
+    def step_prefetched_async(self, next_batch=None):
+        """replay_prefetched() + prefetch(next_batch) + an asynchronous D2H copy of this step's loss.
+        Returns the loss VALUE (float) of the PREVIOUS call, None on the first; drain() returns the last one."""
+        if not hasattr(self, "_loss_host"):
+            self._loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._loss_ev = [torch.cuda.Event() for _ in range(2)]
+            self._loss_pending = None
+            self._loss_n = 0
+        loss = self.replay_prefetched()
+        if next_batch is not None:
+            self.prefetch(next_batch)
+        slot = self._loss_n & 1
+        self._loss_n += 1
+        self._loss_host[slot].copy_(loss.detach().reshape(1), non_blocking=True)
+        self._loss_ev[slot].record(torch.cuda.current_stream())
+        prev, self._loss_pending = self._loss_pending, slot
+        if prev is None:
+            return None
+        self._loss_ev[prev].synchronize()
+        return float(self._loss_host[prev][0])
+
+    def drain(self):
+        """Loss value of the last step_prefetched_async() call (waits for it)."""
+        if getattr(self, "_loss_pending", None) is None:
+            return None
+        slot, self._loss_pending = self._loss_pending, None
+        self._loss_ev[slot].synchronize()
+        return float(self._loss_host[slot][0])
+
     def __call__(self, batch=None):
         """Copy `batch` (host or device tensors) into the static inputs, replay, return the (device) loss tensor."""
         if batch is not None:
