@@ -344,7 +344,7 @@ int vlm_optim_step(int kind, float* p, float* g, float* m, float* v, void* p_bf1
  * the `world` READY flags of its bucket in LOCAL memory, then reads the bucket of every rank with peer loads, sums in fp32 in rank
  * order (replicas stay bit-identical) and applies the update of vlm_optim_step in the same pass.  Flag block of a rank: int32
  * [slots][world].  Epoch: device int, advanced once per step (vlm_p2p_epoch_inc) so that the step replays as a CUDA graph.
- * Waits are bounded (20 s): on expiry *err_flag is set to 1 and the kernel returns without touching the parameters.
+ * Waits are bounded (90 s): on expiry *err_flag is set to 1 and the kernel returns without touching the parameters.
  *   vlm_ipc_alloc  cudaMalloc (zero-filled) + the 64-byte cudaIpcMemHandle_t of the allocation
  *   vlm_ipc_open   map a peer's allocation into this process (peer access enabled lazily); vlm_ipc_close unmaps it
  *   vlm_p2p_signal flags[w][slot][rank] = *epoch for every rank w (system-scope release after a fence); peer_flags = host array of

@@ -37,7 +37,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-static constexpr unsigned long long P2P_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;   // 20 s
+static constexpr unsigned long long P2P_TIMEOUT_NS = 90ull * 1000ull * 1000ull * 1000ull;   // 90 s: ranks may be seconds apart
+                                                                                           // right after each has captured its CUDA graph
 
 // thread w < world waits for flags[w] >= want; returns false on timeout (and raises *err)
 __device__ __forceinline__ bool p2p_poll(const int* flags, int want, int* err) {

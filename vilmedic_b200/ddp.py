@@ -14,7 +14,7 @@ backward pass as small background CTAs (128 threads, <= 64 registers) that fit o
 From 4 ranks on the exchange is two-shot: each rank first sums ITS slice of the bucket over all ranks into an fp32 buffer
 (reduce-scatter through peer memory), the update kernels read every slice from its owner ((N-1)/N * 6 B per parameter over NVLink
 instead of (N-1) * 2 B).  The epoch / READY / REDUCED / DONE flag protocol lives in device memory, so the whole step still replays
-as ONE CUDA graph; every wait is bounded (20 s) and raises an error flag instead of hanging.  Needs `optimizer=` (the update is
+as ONE CUDA graph; every wait is bounded (90 s) and raises an error flag instead of hanging.  Needs `optimizer=` (the update is
 part of the exchange) and no global-norm clipping; otherwise, or when peer memory is unavailable, the NCCL path below is used.
 
 Transport "nccl" (VLM_DDP_TRANSPORT=nccl): async NCCL all-reduce (SUM) per bucket.  Payload bf16 by default — a cast kernel
