@@ -2,7 +2,8 @@
  *
  * Boundary contract: extern "C", plain pointers + sizes, no torch types.  The caller (PyTorch, via
  * ctypes — see vilmedic_b200/_lib.py — or any other host) owns every buffer and passes its CUDA stream as `void*`
- * (cudaStream_t).  No entry point allocates, synchronises or keeps global state beyond per-device caches.  Every
+ * (cudaStream_t).  No compute entry point allocates or synchronises; state kept by the library: per-device caches, the two launch
+ * policy knobs (vlm_set_sm_margin, vlm_set_background) and the peer-visible buffers a caller explicitly requests with vlm_ipc_*.  Every
  * function returns 0 on success, a negative code on failure; the message is available from vlm_last_error()
  * (thread-local).  Device pointers must be 16-byte aligned unless stated otherwise.
  *
